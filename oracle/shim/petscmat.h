@@ -1,0 +1,2 @@
+/* oracle PETSc/MPI shim (test infrastructure): forwards to petsc.h */
+#include "petsc.h"
