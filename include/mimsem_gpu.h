@@ -1,0 +1,180 @@
+/*
+ * mimsem_gpu.h -- C ABI of the B200-native horizontal mixed-mimetic operator path.
+ *
+ * This is the drop-in boundary for the hot path of davelee2804/MiMSEM that BASELINE.json names:
+ * Basis -> ElMats/Geom -> Assembly/Topo -> MatMult.  Plain pointers and sizes only; every
+ * function returns 0 on success and a negative code on failure (mimsem_last_error() gives the
+ * text); nothing throws across this boundary.  The reference has no error convention of its own
+ * (PETSc return codes are discarded everywhere).
+ *
+ * Two groups:
+ *   mimsem_basis_* / mimsem_topo_* / mimsem_mesh_*   host-only (no GPU needed)
+ *   mimsem_gpu_*                                     device engine (sm_100a CUDA)
+ *
+ * Device field layout ("column layout"): a k-level field over n degrees of freedom is the array
+ *   f[dof * ld + k],   k = 0..nlev-1,   ld >= nlev,
+ * i.e. DOF-major with the vertical level fastest.  The reference keeps one PETSc Vec per level
+ * (`Vec velx[NK]`, eul/UMJS14.cpp:302-316); mimsem_gpu_levels_to_columns / _columns_to_levels
+ * convert on the device.  A single-level apply (the MatShell adaptor) uses ld = 1.
+ *
+ * Element-local conventions are the reference's (eul/ElMats.cpp:38-44, 73-79, 105-111, 135-141):
+ *   x-normal edges j = iy*(p+1)+ix, y-normal edges j = iy*p+ix, faces j = iy*p+ix,
+ *   nodes j = iy*(p+1)+ix, quadrature points q = qy*(m+1)+qx.
+ */
+#ifndef MIMSEM_GPU_H
+#define MIMSEM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMSEM_OK 0
+#define MIMSEM_ERR_ARG (-1)
+#define MIMSEM_ERR_CUDA (-2)
+#define MIMSEM_ERR_STATE (-3)
+#define MIMSEM_ERR_IO (-4)
+#define MIMSEM_ERR_UNSUPPORTED (-5)
+
+#define MIMSEM_MESH_SPHERE 0
+#define MIMSEM_MESH_BOX 1
+
+/* last error text of the calling thread ("" if none) */
+const char* mimsem_last_error(void);
+
+/* ------------------------------------------------------------------ Basis (host) */
+/* GaussLobatto(n): x[n+1], w[n+1].                     replaces eul/Basis.cpp:22-98   */
+int mimsem_basis_gll(int n, double* x, double* w);
+/* LagrangeNode(p,quad m).ljxi [(m+1)*(p+1)] and LagrangeEdge.ejxi [(m+1)*p],
+ * quadrature point first.                               replaces eul/Basis.cpp:105-151, 238-286 */
+int mimsem_basis_tables(int p, int m, double* ljxi, double* ejxi);
+/* ElMats tabulations at the quadrature points, row-major (quad point, dof):
+ * which = 0 M1x_j_xy_i (U), 1 M1y_j_xy_i (V), 2 M2_j_xy_i (W), 3 M0_j_xy_i (P), 4 Wii diagonal.
+ *                                                       replaces eul/ElMats.cpp:20-186 */
+int mimsem_elmat(int which, int p, int m, double* A);
+
+/* ------------------------------------------------------------------ Topo (host) */
+/* Sizes of one reference rank's ghosted maps: out = {n0,n1x,n1y,n2,n0l,n1xl,n1yl,n2l}.
+ * kind = MIMSEM_MESH_*; order = element order; nprocs = 6*n^2 (sphere) or n^2 (box).
+ *                                                       replaces scr/Proc2.py:52-70 */
+int mimsem_topo_patch_sizes(int kind, int order, int ne, int nprocs, int rank, int out[8]);
+/* The maps themselves (what input/{nodes,edges_x,edges_y,faces}_RRRR.txt hold).
+ *                                                       replaces scr/Proc2.py:73-230, scr/ProcBox.py:59-136 */
+int mimsem_topo_patch(int kind, int order, int ne, int nprocs, int rank, int* loc0, int* loc1x, int* loc1y, int* loc2);
+/* Write the complete input/ directory the reference reads at start-up (scr/Setup.py:42-78). */
+int mimsem_topo_write_input(int kind, int p, int m, int ne, int nprocs, const char* dir);
+
+/* ------------------------------------------------------------------ global mesh (host) */
+typedef struct mimsem_mesh mimsem_mesh;
+/* Canonical global mesh (one patch per cube face / one patch for the box); m = quadrature order;
+ * signed_det != 0 keeps the sign of det J as src/Geom.cpp:251 does (eul, box: fabs). */
+int mimsem_mesh_create(int kind, int p, int m, int ne, int signed_det, mimsem_mesh** out);
+void mimsem_mesh_destroy(mimsem_mesh* mesh);
+/* out = {p, m, ne, nel, N0, N1, N2, NQ} */
+int mimsem_mesh_sizes(const mimsem_mesh* mesh, int64_t out[8]);
+/* element -> global DOF tables: el0[nel][(p+1)^2], el1x[nel][p(p+1)], el1y[nel][(p+1)p],
+ * el2[nel][p^2], elq[nel][(m+1)^2]; any pointer may be NULL.   (Topo::elInds*_g, eul/Topo.cpp:253-305) */
+int mimsem_mesh_tables(const mimsem_mesh* mesh, int* el0, int* el1x, int* el1y, int* el2, int* elq);
+/* J[nel][(m+1)^2][4] (J00 J01 J10 J11), det[nel][(m+1)^2]       (Geom::J, Geom::det, eul/Geom.cpp:245-326) */
+int mimsem_mesh_geometry(const mimsem_mesh* mesh, double* J, double* det);
+/* cartesian coordinates of the quadrature points, xyz[NQ][3]   (scr/Geom2.py:10-277) */
+int mimsem_mesh_coords(const mimsem_mesh* mesh, double* xyz);
+
+/* ------------------------------------------------------------------ device engine */
+typedef struct mimsem_gpu_ctx mimsem_gpu_ctx;
+
+int mimsem_gpu_create(int device, mimsem_gpu_ctx** out);
+int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx);
+
+/* Basis tables (host pointers): quadrature weights w[m+1], ljxi[(m+1)(p+1)], ejxi[(m+1)p].
+ * The sum-factorised kernels require m == p, where ljxi is the identity. */
+int mimsem_gpu_set_basis(mimsem_gpu_ctx* ctx, int p, int m, const double* h_w, const double* h_ljxi, const double* h_ejxi);
+
+/* Subdomain topology (host pointers, local 0-based indices).  Elements [0, nel_owned) are
+ * computed; elements [nel_owned, nel_total) are read-only halo elements that only contribute to
+ * shared DOFs of owned elements.  x- and y-normal edge tables index the same 1-form array.
+ * mode: 0 = owner-computes (outputs on DOFs touched by owned elements' west/south/interior side
+ *           are complete; DOFs owned elsewhere are not written),
+ *       1 = partial sums (the reference's ghosted-local convention: east/north DOFs without a
+ *           local owner receive this subdomain's partial sum; finish with a reverse ADD scatter,
+ *           eul/Assembly.cpp:2194-2195). */
+int mimsem_gpu_set_topo(mimsem_gpu_ctx* ctx, int nel_total, int nel_owned, int n0, int n1, int n2, int nq, int mode,
+                        const int* h_el0, const int* h_el1x, const int* h_el1y, const int* h_el2, const int* h_elq);
+
+/* Geometry of the nel_total elements: J[nel][(m+1)^2][4], det[nel][(m+1)^2] (host pointers). */
+int mimsem_gpu_set_geom(mimsem_gpu_ctx* ctx, const double* h_J, const double* h_det);
+
+/* Layer thickness thick[nk][nq] (host pointer, level-major as Geom::thick, eul/Geom.cpp:752-763).
+ * The engine stores 1/thick in column layout. nk = 0 clears it (2-D shallow water, src/). */
+int mimsem_gpu_set_thickness(mimsem_gpu_ctx* ctx, int nk, const double* h_thick);
+
+/* out = {nel_total, nel_owned, n0, n1, n2, nq, nk, p, m} */
+int mimsem_gpu_sizes(const mimsem_gpu_ctx* ctx, int64_t out[9]);
+
+/* Layout helpers (device pointers): levels[k*n + dof]  <->  columns[dof*ld + k] */
+int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* ctx, int64_t n, int nlev, int ld, const double* d_levels, double* d_columns, void* stream);
+int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* ctx, int64_t n, int nlev, int ld, const double* d_columns, double* d_levels, void* stream);
+
+/*
+ * Operator applications.  All field pointers are DEVICE pointers in column layout with leading
+ * dimension ld; column j of a field corresponds to vertical level lev0 + j (thickness level);
+ * nlev columns are processed in one launch.  tpow = number of 1/thick factors per quadrature
+ * point (0, 1 or 2), which is how the reference's vert_scale / const_vert flags and the `src`
+ * (no thickness) variant map onto one kernel:
+ *   Umat::assemble(lev,scale,vert_scale)        -> apply_M1 (tpow = vert_scale)          eul/Assembly.cpp:51-153
+ *   Wmat::assemble(lev,scale,vert_scale)        -> apply_M2 (tpow = vert_scale)          eul/Assembly.cpp:311-373
+ *   Pmat::assemble(lev,scale)                   -> apply_M0 (tpow = 1)                   eul/Assembly.cpp:2004-2043
+ *   Pmat::assemble_h(lev,scale,h2)              -> apply_M0h (tpow = 2)                  eul/Assembly.cpp:2045-2098
+ *   Uhmat::assemble(h2,lev,const_vert,scale)    -> apply_M1h (tpow = 1 + const_vert)     eul/Assembly.cpp:416-474
+ *   Whmat::assemble(rho,lev,scale,vs_rho)       -> apply_M2h (tpow = 1 + vs_rho)         eul/Assembly.cpp:1243-1299
+ *   WtQUmat::assemble(u1,lev,scale)             -> apply_K  (tpow = 2)                   eul/Assembly.cpp:933-986
+ *   src/ variants (no thickness)                -> the same with tpow = 0                src/Assembly.cpp:30-124 ...
+ * followed, in each case, by the MatMult the reference performs on the assembled matrix.
+ * flags: MIMSEM_FIXED_LEVEL uses thickness level lev0 for every column (box/: Umat and Wmat are
+ * assembled once at level 0, box/Assembly.cpp:44-45).
+ */
+#define MIMSEM_FIXED_LEVEL 1
+
+int mimsem_gpu_apply_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                        const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                         const double* d_h2, const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M2(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                        const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M2h(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                         const double* d_h2, const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M0(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                        const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M0h(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                         const double* d_h2, const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_K(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                       const double* d_u1, const double* d_x, double* d_y, void* stream);
+
+/* Incidence operators (exact +-1 stencils), E10mat/E21mat of eul/Assembly.cpp:1102-1226:
+ * which = 0 E10 (0-form -> 1-form), 1 E01 = -E10^T, 2 E21 (1-form -> 2-form), 3 E12 = -E21^T. */
+#define MIMSEM_E10 0
+#define MIMSEM_E01 1
+#define MIMSEM_E21 2
+#define MIMSEM_E12 3
+int mimsem_gpu_apply_incidence(mimsem_gpu_ctx* ctx, int which, int nlev, int ld, const double* d_x, double* d_y, void* stream);
+/* The stencils themselves as CSR over local indices (host output), for bit-exact comparison with
+ * the reference's matrices.  Call with NULL arrays to get sizes: out_sizes = {nrows, ncols, nnz}. */
+int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_sizes[3], int64_t* indptr, int* indices, double* values);
+
+/*
+ * End-to-end convenience with HOST buffers in the reference's per-level layout
+ * (levels[k*n + dof]): copies in, converts, applies, converts back and copies out on the
+ * engine's own streams.  op: 0 M1, 1 M2, 2 M0, 3 M1h, 4 K, 5 M2h, 6 M0h, 10+which incidence.
+ * h_coeff may be NULL for operators without a coefficient field.
+ */
+int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
+                          const double* h_coeff, const double* h_x, double* h_y);
+
+/* number of kernels this library has launched since the context was created */
+int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMSEM_GPU_H */

@@ -1,0 +1,765 @@
+// Host side of the device engine + the mimsem_gpu_* C ABI (include/mimsem_gpu.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mimsem_gpu.h"
+#include "errors.hpp"
+#include "kernels.cuh"
+
+using namespace mimsem;
+
+namespace {
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t upload(const std::vector<T>& h) {
+        cudaError_t e = resize(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    cudaError_t resize(size_t m) {
+        if (m <= n && p) return cudaSuccess;
+        release();
+        n = m;
+        return cudaMalloc((void**)&p, std::max<size_t>(m, 1) * sizeof(T));
+    }
+};
+
+struct HostCsr {
+    int64_t nrows = 0, ncols = 0;
+    std::vector<int64_t> indptr;
+    std::vector<int> indices;
+    std::vector<double> values;
+};
+
+struct DevEll {
+    int64_t nrows = 0;
+    int width = 0;
+    DevBuf<int> col;
+    DevBuf<signed char> sgn;
+    DevBuf<int> rows;
+    int64_t nrows_active = 0;   // rows to compute (owned); == nrows when rows list is empty
+    bool use_rows = false;
+};
+
+}  // namespace
+
+struct mimsem_gpu_ctx {
+    int device = 0;
+    int p = 0, m = 0;
+    bool have_basis = false, have_topo = false, have_geom = false;
+    std::vector<double> w, ejxi;   // w[m+1], ejxi[(m+1)*p]
+
+    int nel_total = 0, nel_owned = 0, n0 = 0, n1 = 0, n2 = 0, nq = 0, mode = 0;
+    std::vector<int> h_el0, h_el1x, h_el1y, h_el2, h_elq;
+    std::vector<int> h_nbr;
+    std::vector<unsigned char> h_eflags;
+    std::vector<int> h_adj_ptr, h_adj_eq, h_node_q;
+
+    DevBuf<int> d_el0, d_el1x, d_el1y, d_el2, d_elq, d_nbr, d_adj_ptr, d_adj_eq, d_node_q;
+    DevBuf<unsigned char> d_eflags;
+    DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
+    int nkT = 0;
+
+    HostCsr csr[4];
+    DevEll ell[4];
+
+    // staging for the host-buffer entry point
+    DevBuf<double> s_lev, s_x, s_y, s_c;
+    cudaStream_t stream = nullptr;
+
+    int64_t launches = 0;
+};
+
+namespace {
+
+#define CUDA_OK(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+            return MIMSEM_ERR_CUDA;                                                                     \
+        }                                                                                               \
+    } while (0)
+
+int fail(int code, const std::string& msg) {
+    set_error(msg);
+    return code;
+}
+
+int bind_device(const mimsem_gpu_ctx* ctx) {
+    CUDA_OK(cudaSetDevice(ctx->device));
+    return MIMSEM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// topology preprocessing (host)
+
+struct EdgeUse {
+    int elem;
+    int type;   // 0 x-normal, 1 y-normal
+    int j;      // element-local index
+};
+
+// For each owned element find the element across its west / south side and which far side
+// (east column of x-edges or north row of y-edges, possibly reversed -- cubed-sphere seams,
+// scr/Proc2.py:165-172, 210-227) of that element the shared edges are.
+int build_neighbours(mimsem_gpu_ctx* c) {
+    const int P = c->p, NP1 = P + 1, N1E = P * NP1;
+    std::vector<std::array<EdgeUse, 2>> use(c->n1);
+    std::vector<unsigned char> cnt(c->n1, 0);
+    auto add = [&](int dof, EdgeUse u) -> bool {
+        if (dof < 0 || dof >= c->n1) return false;
+        if (cnt[dof] >= 2) return false;
+        use[dof][cnt[dof]++] = u;
+        return true;
+    };
+    for (int e = 0; e < c->nel_total; e++)
+        for (int j = 0; j < N1E; j++) {
+            if (!add(c->h_el1x[(size_t)e * N1E + j], EdgeUse{e, 0, j}) ||
+                !add(c->h_el1y[(size_t)e * N1E + j], EdgeUse{e, 1, j}))
+                return fail(MIMSEM_ERR_ARG, "set_topo: an edge index is out of range or shared by more than two elements");
+        }
+    c->h_nbr.assign((size_t)c->nel_owned * 2, -1);
+    c->h_eflags.assign(c->nel_owned, 0);
+    for (int e = 0; e < c->nel_owned; e++) {
+        for (int s = 0; s < 2; s++) {   // 0: west side (x-edges ix=0), 1: south side (y-edges iy=0)
+            int nb = -1, side = -1, rev = -1;
+            bool none = false;
+            for (int i = 0; i < P; i++) {
+                const int type = s, j = (s == 0) ? i * NP1 : i;
+                const int dof = (s == 0) ? c->h_el1x[(size_t)e * N1E + j] : c->h_el1y[(size_t)e * N1E + j];
+                const EdgeUse* other = nullptr;
+                for (int u = 0; u < cnt[dof]; u++) {
+                    const EdgeUse& q = use[dof][u];
+                    if (!(q.elem == e && q.type == type && q.j == j)) other = &q;
+                }
+                if (!other) {
+                    none = true;
+                    continue;
+                }
+                int oside, oi;
+                if (other->type == 0) {
+                    if (other->j % NP1 != P) return fail(MIMSEM_ERR_ARG, "set_topo: west/south edge shared with a non-east side");
+                    oside = 0;
+                    oi = other->j / NP1;
+                } else {
+                    if (other->j / P != P) return fail(MIMSEM_ERR_ARG, "set_topo: west/south edge shared with a non-north side");
+                    oside = 1;
+                    oi = other->j % P;
+                }
+                int r = (oi == i) ? 0 : (oi == P - 1 - i ? 1 : -2);
+                if (P > 1 && oi == i && oi == P - 1 - i) r = -1;   // middle edge: orientation undetermined
+                if (r == -2) return fail(MIMSEM_ERR_ARG, "set_topo: inconsistent edge order across an element side");
+                if (nb == -1) {
+                    nb = other->elem;
+                    side = oside;
+                } else if (nb != other->elem || side != oside) {
+                    return fail(MIMSEM_ERR_ARG, "set_topo: an element side touches more than one neighbour side");
+                }
+                if (r >= 0) {
+                    if (rev >= 0 && rev != r) return fail(MIMSEM_ERR_ARG, "set_topo: inconsistent orientation across an element side");
+                    rev = r;
+                }
+            }
+            if (nb >= 0 && none) return fail(MIMSEM_ERR_ARG, "set_topo: element side only partially shared");
+            if (nb >= 0) {
+                if (nb >= (1 << 29)) return fail(MIMSEM_ERR_UNSUPPORTED, "set_topo: too many elements");
+                c->h_nbr[(size_t)e * 2 + s] = nb | (side << 29) | ((rev > 0 ? 1 : 0) << 30);
+            }
+        }
+        if (c->mode == 1) {
+            // partial-sum mode: east / north edges nobody else in this subdomain computes
+            const int de = c->h_el1x[(size_t)e * N1E + P];
+            const int dn = c->h_el1y[(size_t)e * N1E + P * P];
+            if (cnt[de] == 1) c->h_eflags[e] |= 1;
+            if (cnt[dn] == 1) c->h_eflags[e] |= 2;
+        }
+    }
+    return MIMSEM_OK;
+}
+
+void csr_from_triplets(int64_t nrows, int64_t ncols, std::vector<std::array<int64_t, 3>>& t, HostCsr& out) {
+    // t = (row, col, sign); INSERT semantics: duplicates (same row, col) carry the same value
+    std::sort(t.begin(), t.end());
+    t.erase(std::unique(t.begin(), t.end(), [](const std::array<int64_t, 3>& a, const std::array<int64_t, 3>& b) {
+                return a[0] == b[0] && a[1] == b[1];
+            }),
+            t.end());
+    out.nrows = nrows;
+    out.ncols = ncols;
+    out.indptr.assign(nrows + 1, 0);
+    out.indices.resize(t.size());
+    out.values.resize(t.size());
+    for (size_t i = 0; i < t.size(); i++) {
+        out.indptr[t[i][0] + 1]++;
+        out.indices[i] = (int)t[i][1];
+        out.values[i] = (double)t[i][2];
+    }
+    for (int64_t r = 0; r < nrows; r++) out.indptr[r + 1] += out.indptr[r];
+}
+
+int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows) {
+    int width = 0;
+    for (int64_t r = 0; r < m.nrows; r++) width = std::max<int>(width, (int)(m.indptr[r + 1] - m.indptr[r]));
+    width = std::max(width, 1);
+    std::vector<int> col((size_t)m.nrows * width, -1);
+    std::vector<signed char> sgn((size_t)m.nrows * width, 0);
+    for (int64_t r = 0; r < m.nrows; r++)
+        for (int64_t k = m.indptr[r]; k < m.indptr[r + 1]; k++) {
+            col[(size_t)r * width + (k - m.indptr[r])] = m.indices[k];
+            sgn[(size_t)r * width + (k - m.indptr[r])] = m.values[k] > 0 ? 1 : -1;
+        }
+    d.nrows = m.nrows;
+    d.width = width;
+    CUDA_OK(d.col.upload(col));
+    CUDA_OK(d.sgn.upload(sgn));
+    if (rows) {
+        d.use_rows = true;
+        d.nrows_active = (int64_t)rows->size();
+        CUDA_OK(d.rows.upload(*rows));
+    } else {
+        d.use_rows = false;
+        d.nrows_active = m.nrows;
+    }
+    return MIMSEM_OK;
+}
+
+// Incidence stencils, restating E10mat / E21mat (eul/Assembly.cpp:1102-1162, 1170-1220) over the
+// local element tables; E01 = -E10^T and E12 = -E21^T (ibid. :1156-1161, :1214-1219).
+int build_incidence(mimsem_gpu_ctx* c) {
+    const int P = c->p, NP1 = P + 1, N1E = P * NP1, N2E = P * P, N0E = NP1 * NP1;
+    std::vector<std::array<int64_t, 3>> t10, t21, t01, t12;
+    std::vector<int> rows10, rows21;
+    for (int e = 0; e < c->nel_total; e++) {
+        const int* ix = &c->h_el1x[(size_t)e * N1E];
+        const int* iy = &c->h_el1y[(size_t)e * N1E];
+        const int* i0 = &c->h_el0[(size_t)e * N0E];
+        const int* i2 = &c->h_el2[(size_t)e * N2E];
+        for (int b = 0; b < P; b++)
+            for (int a = 0; a < P; a++) {
+                // edges local to this element (west/south/interior); a = ix, b = iy
+                const int ll = b * NP1 + a;
+                const int rx = ix[b * NP1 + a], ry = iy[b * P + a];
+                t10.push_back({rx, i0[ll], +1});
+                t10.push_back({rx, i0[ll + NP1], -1});
+                t10.push_back({ry, i0[ll], -1});
+                t10.push_back({ry, i0[ll + 1], +1});
+                // face (a, b)
+                const int rf = i2[b * P + a];
+                t21.push_back({rf, ix[b * NP1 + a], -1});
+                t21.push_back({rf, ix[b * NP1 + a + 1], +1});
+                t21.push_back({rf, iy[b * P + a], -1});
+                t21.push_back({rf, iy[(b + 1) * P + a], +1});
+                if (e < c->nel_owned) {
+                    rows10.push_back(rx);
+                    rows10.push_back(ry);
+                    rows21.push_back(rf);
+                }
+            }
+    }
+    for (auto& v : t10) t01.push_back({v[1], v[0], -v[2]});
+    for (auto& v : t21) t12.push_back({v[1], v[0], -v[2]});
+    csr_from_triplets(c->n1, c->n0, t10, c->csr[MIMSEM_E10]);
+    csr_from_triplets(c->n0, c->n1, t01, c->csr[MIMSEM_E01]);
+    csr_from_triplets(c->n2, c->n1, t21, c->csr[MIMSEM_E21]);
+    csr_from_triplets(c->n1, c->n2, t12, c->csr[MIMSEM_E12]);
+    std::sort(rows10.begin(), rows10.end());
+    std::sort(rows21.begin(), rows21.end());
+    const bool all = (c->nel_owned == c->nel_total);
+    int rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E10], c->ell[MIMSEM_E10], all ? nullptr : &rows10))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E21], c->ell[MIMSEM_E21], all ? nullptr : &rows21))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E01], c->ell[MIMSEM_E01], nullptr))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E12], c->ell[MIMSEM_E12], nullptr))) return rc;
+    return MIMSEM_OK;
+}
+
+int build_node_adjacency(mimsem_gpu_ctx* c) {
+    const int NP1 = c->p + 1, Q2 = NP1 * NP1;
+    c->h_adj_ptr.assign(c->n0 + 1, 0);
+    c->h_node_q.assign(c->n0, 0);
+    for (int e = 0; e < c->nel_total; e++)
+        for (int q = 0; q < Q2; q++) {
+            const int n = c->h_el0[(size_t)e * Q2 + q];
+            if (n < 0 || n >= c->n0) return fail(MIMSEM_ERR_ARG, "set_topo: node index out of range");
+            c->h_adj_ptr[n + 1]++;
+            c->h_node_q[n] = c->h_elq[(size_t)e * Q2 + q];
+        }
+    for (int n = 0; n < c->n0; n++) c->h_adj_ptr[n + 1] += c->h_adj_ptr[n];
+    c->h_adj_eq.assign(c->h_adj_ptr[c->n0], 0);
+    std::vector<int> pos(c->h_adj_ptr.begin(), c->h_adj_ptr.end() - 1);
+    for (int e = 0; e < c->nel_total; e++)
+        for (int q = 0; q < Q2; q++) c->h_adj_eq[pos[c->h_el0[(size_t)e * Q2 + q]]++] = e * Q2 + q;
+    return MIMSEM_OK;
+}
+
+template <class Args>
+void copy_basis(const mimsem_gpu_ctx* c, Args& a) {
+    std::memset(a.E, 0, sizeof(a.E));
+    std::memcpy(a.E, c->ejxi.data(), c->ejxi.size() * sizeof(double));
+}
+
+int check_ready(const mimsem_gpu_ctx* c, bool need_thick, int lev0, int nlev, int ld, int flags) {
+    if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    if (!c->have_basis || !c->have_topo || !c->have_geom) return fail(MIMSEM_ERR_STATE, "set_basis, set_topo and set_geom must precede an apply");
+    if (c->m != c->p) return fail(MIMSEM_ERR_UNSUPPORTED, "the sum-factorised kernels require quadrature order == element order");
+    if (nlev < 1 || ld < nlev || lev0 < 0) return fail(MIMSEM_ERR_ARG, "bad level range / leading dimension");
+    if (need_thick) {
+        const int last = (flags & MIMSEM_FIXED_LEVEL) ? lev0 : lev0 + nlev - 1;
+        if (c->nkT == 0) return fail(MIMSEM_ERR_STATE, "tpow > 0 needs set_thickness");
+        if (last >= c->nkT) return fail(MIMSEM_ERR_ARG, "level range exceeds the thickness table");
+    }
+    return MIMSEM_OK;
+}
+
+void fill_common(const mimsem_gpu_ctx* c, KArgs& a, int lev0, int nlev, int ld, double scale, int tpow, int flags) {
+    a.nel = c->nel_owned;
+    a.nlev = nlev;
+    a.ld = ld;
+    a.lev0 = lev0;
+    a.lev_stride = (flags & MIMSEM_FIXED_LEVEL) ? 0 : 1;
+    a.nkT = c->nkT;
+    a.tpow = tpow;
+    a.scale = scale;
+    a.el1x = c->d_el1x.p;
+    a.el1y = c->d_el1y.p;
+    a.el2 = c->d_el2.p;
+    a.elq = c->d_elq.p;
+    a.nbr = c->d_nbr.p;
+    a.eflags = c->d_eflags.p;
+    a.tinv = c->d_tinv.p;
+    a.c = nullptr;
+    copy_basis(c, a);
+}
+
+template <class F>
+int dispatch_p(int p, F f) {
+    switch (p) {
+        case 2: return f(std::integral_constant<int, 2>());
+        case 3: return f(std::integral_constant<int, 3>());
+        case 4: return f(std::integral_constant<int, 4>());
+        case 5: return f(std::integral_constant<int, 5>());
+        default: return fail(MIMSEM_ERR_UNSUPPORTED, "element order must be 2..5");
+    }
+}
+
+int finish_launch(mimsem_gpu_ctx* c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    c->launches++;
+    return MIMSEM_OK;
+}
+
+unsigned grid_for(int64_t threads, int block) { return (unsigned)((threads + block - 1) / block); }
+
+int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+             const double* h2, const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = with_h ? c->d_G1h.p : c->d_G1.p;
+    a.c = h2;
+    a.x = x;
+    a.y = y;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        if (with_h) k_apply_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        else k_apply_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "apply_M1");
+    });
+}
+
+int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+             const double* h2, const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = with_h ? c->d_W2h.p : c->d_W2.p;
+    a.c = h2;
+    a.x = x;
+    a.y = y;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        if (with_h) k_apply_m2<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        else k_apply_m2<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "apply_M2");
+    });
+}
+
+int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* u1,
+            const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = c->d_G1h.p;
+    a.c = u1;
+    a.x = x;
+    a.y = y;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        k_apply_k<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "apply_K");
+    });
+}
+
+int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+             const double* h2, const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    NodeArgs a;
+    a.n0 = c->n0;
+    a.nlev = nlev;
+    a.ld = ld;
+    a.lev0 = lev0;
+    a.lev_stride = (flags & MIMSEM_FIXED_LEVEL) ? 0 : 1;
+    a.nkT = c->nkT;
+    a.tpow = tpow;
+    a.scale = scale;
+    a.adj_ptr = c->d_adj_ptr.p;
+    a.adj_eq = c->d_adj_eq.p;
+    a.node_q = c->d_node_q.p;
+    a.el2 = c->d_el2.p;
+    a.D0 = c->d_D0.p;
+    a.wq = c->d_wq.p;
+    a.tinv = c->d_tinv.p;
+    a.c = h2;
+    a.x = x;
+    a.y = y;
+    copy_basis(c, a);
+    const int64_t threads = (int64_t)a.n0 * nlev;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        if (with_h) k_apply_m0<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        else k_apply_m0<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "apply_M0");
+    });
+}
+
+int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, cudaStream_t st) {
+    if (!c || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo must precede apply_incidence");
+    if (which < 0 || which > 3) return fail(MIMSEM_ERR_ARG, "incidence operator id must be 0..3");
+    if (nlev < 1 || ld < nlev) return fail(MIMSEM_ERR_ARG, "bad level count / leading dimension");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const DevEll& d = c->ell[which];
+    EllArgs a;
+    a.nrows = d.nrows_active;
+    a.width = d.width;
+    a.nlev = nlev;
+    a.ld = ld;
+    a.rows = d.use_rows ? d.rows.p : nullptr;
+    a.col = d.col.p;
+    a.sgn = d.sgn.p;
+    a.x = x;
+    a.y = y;
+    if (a.nrows == 0) return MIMSEM_OK;
+    k_apply_ell<<<grid_for(a.nrows * nlev, 256), 256, 0, st>>>(a);
+    return finish_launch(c, "apply_incidence");
+}
+
+int transpose(mimsem_gpu_ctx* c, bool to_columns, int64_t n, int nlev, int ld, const double* in, double* out, cudaStream_t st) {
+    if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    if (n < 1 || nlev < 1 || ld < nlev) return fail(MIMSEM_ERR_ARG, "bad transpose shape");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nlev + 31) / 32));
+    if (to_columns) k_transpose<true><<<grid, 256, 0, st>>>(n, nlev, ld, in, out);
+    else k_transpose<false><<<grid, 256, 0, st>>>(n, nlev, ld, in, out);
+    return finish_launch(c, "transpose");
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+
+extern "C" {
+
+int mimsem_gpu_create(int device, mimsem_gpu_ctx** out) {
+    if (!out) return fail(MIMSEM_ERR_ARG, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MIMSEM_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(MIMSEM_ERR_ARG, "device ordinal out of range");
+    CUDA_OK(cudaSetDevice(device));
+    mimsem_gpu_ctx* c = new mimsem_gpu_ctx;
+    c->device = device;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(MIMSEM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = c;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx) {
+    if (!ctx) return MIMSEM_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_basis(mimsem_gpu_ctx* c, int p, int m, const double* h_w, const double* h_ljxi, const double* h_ejxi) {
+    if (!c || !h_w || !h_ljxi || !h_ejxi) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (p < 1 || p > kMaxP || m < 1) return fail(MIMSEM_ERR_ARG, "unsupported order");
+    if (m != p) return fail(MIMSEM_ERR_UNSUPPORTED, "quadrature order must equal the element order (every BASELINE configuration)");
+    // with m == p the nodal table must be the identity (up to signed zeros / a few ulps in box/)
+    for (int q = 0; q <= m; q++)
+        for (int j = 0; j <= p; j++)
+            if (std::fabs(h_ljxi[q * (p + 1) + j] - (q == j ? 1.0 : 0.0)) > 1e-12)
+                return fail(MIMSEM_ERR_ARG, "ljxi is not the identity although m == p");
+    c->p = p;
+    c->m = m;
+    c->w.assign(h_w, h_w + m + 1);
+    c->ejxi.assign(h_ejxi, h_ejxi + (size_t)(m + 1) * p);
+    c->have_basis = true;
+    c->have_topo = c->have_geom = false;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0, int n1, int n2, int nq, int mode,
+                        const int* h_el0, const int* h_el1x, const int* h_el1y, const int* h_el2, const int* h_elq) {
+    if (!c || !h_el0 || !h_el1x || !h_el1y || !h_el2 || !h_elq) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (!c->have_basis) return fail(MIMSEM_ERR_STATE, "set_basis first");
+    if (nel_owned < 1 || nel_total < nel_owned || n0 < 1 || n1 < 1 || n2 < 1 || nq < 1 || mode < 0 || mode > 1)
+        return fail(MIMSEM_ERR_ARG, "bad sizes");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const int P = c->p, NP1 = P + 1;
+    c->nel_total = nel_total;
+    c->nel_owned = nel_owned;
+    c->n0 = n0;
+    c->n1 = n1;
+    c->n2 = n2;
+    c->nq = nq;
+    c->mode = mode;
+    c->h_el0.assign(h_el0, h_el0 + (size_t)nel_total * NP1 * NP1);
+    c->h_el1x.assign(h_el1x, h_el1x + (size_t)nel_total * P * NP1);
+    c->h_el1y.assign(h_el1y, h_el1y + (size_t)nel_total * P * NP1);
+    c->h_el2.assign(h_el2, h_el2 + (size_t)nel_total * P * P);
+    c->h_elq.assign(h_elq, h_elq + (size_t)nel_total * NP1 * NP1);
+    for (int v : c->h_el2)
+        if (v < 0 || v >= n2) return fail(MIMSEM_ERR_ARG, "set_topo: face index out of range");
+    for (int v : c->h_elq)
+        if (v < 0 || v >= nq) return fail(MIMSEM_ERR_ARG, "set_topo: quadrature-point index out of range");
+    if ((rc = build_neighbours(c))) return rc;
+    if ((rc = build_node_adjacency(c))) return rc;
+    if ((rc = build_incidence(c))) return rc;
+    CUDA_OK(c->d_el0.upload(c->h_el0));
+    CUDA_OK(c->d_el1x.upload(c->h_el1x));
+    CUDA_OK(c->d_el1y.upload(c->h_el1y));
+    CUDA_OK(c->d_el2.upload(c->h_el2));
+    CUDA_OK(c->d_elq.upload(c->h_elq));
+    CUDA_OK(c->d_nbr.upload(c->h_nbr));
+    CUDA_OK(c->d_eflags.upload(c->h_eflags));
+    CUDA_OK(c->d_adj_ptr.upload(c->h_adj_ptr));
+    CUDA_OK(c->d_adj_eq.upload(c->h_adj_eq));
+    CUDA_OK(c->d_node_q.upload(c->h_node_q));
+    c->have_topo = true;
+    c->have_geom = false;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_det) {
+    if (!c || !h_J || !h_det) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (!c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const int NP1 = c->p + 1, Q2 = NP1 * NP1;
+    const size_t npts = (size_t)c->nel_total * Q2;
+    std::vector<double> G1(npts * 3), G1h(npts * 3), W2(npts), W2h(npts), D0(c->n0, 0.0), wq(Q2);
+    for (int q = 0; q < Q2; q++) wq[q] = c->w[q % NP1] * c->w[q / NP1];   // Wii, eul/ElMats.cpp:177
+    for (size_t i = 0; i < npts; i++) {
+        const double* J = h_J + i * 4;
+        const double det = h_det[i];
+        if (!(det != 0.0)) return fail(MIMSEM_ERR_ARG, "set_geom: zero Jacobian determinant");
+        const double w = wq[i % Q2];
+        // metric of the H(div) Piola map, eul/Assembly.cpp:103-105
+        const double gaa = J[0] * J[0] + J[2] * J[2];
+        const double gab = J[0] * J[1] + J[2] * J[3];
+        const double gbb = J[1] * J[1] + J[3] * J[3];
+        const double wd = w / det, wdd = w / (det * det);
+        G1[i * 3 + 0] = gaa * wd;  G1[i * 3 + 1] = gab * wd;  G1[i * 3 + 2] = gbb * wd;
+        G1h[i * 3 + 0] = gaa * wdd; G1h[i * 3 + 1] = gab * wdd; G1h[i * 3 + 2] = gbb * wdd;
+        W2[i] = wd;
+        W2h[i] = wdd;
+        D0[c->h_el0[i]] += w * det;   // element order, as MatSetValues(ADD_VALUES) accumulates
+    }
+    CUDA_OK(c->d_G1.upload(G1));
+    CUDA_OK(c->d_G1h.upload(G1h));
+    CUDA_OK(c->d_W2.upload(W2));
+    CUDA_OK(c->d_W2h.upload(W2h));
+    CUDA_OK(c->d_D0.upload(D0));
+    CUDA_OK(c->d_wq.upload(wq));
+    c->have_geom = true;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_thickness(mimsem_gpu_ctx* c, int nk, const double* h_thick) {
+    if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    if (!c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    if (nk == 0) {
+        c->nkT = 0;
+        return MIMSEM_OK;
+    }
+    if (nk < 0 || !h_thick) return fail(MIMSEM_ERR_ARG, "bad thickness table");
+    std::vector<double> tinv((size_t)c->nq * nk);
+    for (int k = 0; k < nk; k++)
+        for (int q = 0; q < c->nq; q++) tinv[(size_t)q * nk + k] = 1.0 / h_thick[(size_t)k * c->nq + q];   // eul/Geom.cpp:761
+    CUDA_OK(c->d_tinv.upload(tinv));
+    c->nkT = nk;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_sizes(const mimsem_gpu_ctx* c, int64_t out[9]) {
+    if (!c || !out) return fail(MIMSEM_ERR_ARG, "null argument");
+    out[0] = c->nel_total; out[1] = c->nel_owned; out[2] = c->n0; out[3] = c->n1; out[4] = c->n2;
+    out[5] = c->nq; out[6] = c->nkT; out[7] = c->p; out[8] = c->m;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* c, int64_t n, int nlev, int ld, const double* in, double* out, void* stream) {
+    return transpose(c, true, n, nlev, ld, in, out, (cudaStream_t)stream);
+}
+int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* c, int64_t n, int nlev, int ld, const double* in, double* out, void* stream) {
+    return transpose(c, false, n, nlev, ld, in, out, (cudaStream_t)stream);
+}
+
+int mimsem_gpu_apply_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                        double* y, void* st) {
+    return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                         const double* x, double* y, void* st) {
+    if (!h2) return fail(MIMSEM_ERR_ARG, "null coefficient field");
+    return apply_m1(c, true, lev0, nlev, ld, scale, tpow, flags, h2, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M2(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                        double* y, void* st) {
+    return apply_m2(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M2h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                         const double* x, double* y, void* st) {
+    if (!h2) return fail(MIMSEM_ERR_ARG, "null coefficient field");
+    return apply_m2(c, true, lev0, nlev, ld, scale, tpow, flags, h2, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                        double* y, void* st) {
+    return apply_m0(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M0h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                         const double* x, double* y, void* st) {
+    if (!h2) return fail(MIMSEM_ERR_ARG, "null coefficient field");
+    return apply_m0(c, true, lev0, nlev, ld, scale, tpow, flags, h2, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_K(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* u1,
+                       const double* x, double* y, void* st) {
+    if (!u1) return fail(MIMSEM_ERR_ARG, "null coefficient field");
+    return apply_k(c, lev0, nlev, ld, scale, tpow, flags, u1, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_incidence(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, void* st) {
+    return apply_inc(c, which, nlev, ld, x, y, (cudaStream_t)st);
+}
+
+int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* c, int which, int64_t out_sizes[3], int64_t* indptr, int* indices, double* values) {
+    if (!c || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    if (which < 0 || which > 3) return fail(MIMSEM_ERR_ARG, "incidence operator id must be 0..3");
+    const HostCsr& m = c->csr[which];
+    if (out_sizes) {
+        out_sizes[0] = m.nrows;
+        out_sizes[1] = m.ncols;
+        out_sizes[2] = (int64_t)m.indices.size();
+    }
+    if (indptr) std::copy(m.indptr.begin(), m.indptr.end(), indptr);
+    if (indices) std::copy(m.indices.begin(), m.indices.end(), indices);
+    if (values) std::copy(m.values.begin(), m.values.end(), values);
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double scale, int tpow, int flags,
+                          const double* h_coeff, const double* h_x, double* h_y) {
+    if (!c || !h_x || !h_y) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (!c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    // input / output / coefficient spaces
+    int64_t nin, nout, ncoef = 0;
+    switch (op) {
+        case 0: case 3: nin = nout = c->n1; if (op == 3) ncoef = c->n2; break;
+        case 1: case 5: nin = nout = c->n2; if (op == 5) ncoef = c->n2; break;
+        case 2: case 6: nin = nout = c->n0; if (op == 6) ncoef = c->n2; break;
+        case 4: nin = c->n1; nout = c->n2; ncoef = c->n1; break;
+        case 10 + MIMSEM_E10: nin = c->n0; nout = c->n1; break;
+        case 10 + MIMSEM_E01: nin = c->n1; nout = c->n0; break;
+        case 10 + MIMSEM_E21: nin = c->n1; nout = c->n2; break;
+        case 10 + MIMSEM_E12: nin = c->n2; nout = c->n1; break;
+        default: return fail(MIMSEM_ERR_ARG, "unknown operator id");
+    }
+    if (ncoef && !h_coeff) return fail(MIMSEM_ERR_ARG, "this operator needs a coefficient field");
+    const int ld = nlev;
+    const size_t big = (size_t)std::max(std::max(nin, nout), ncoef) * nlev;
+    CUDA_OK(c->s_lev.resize(big));
+    CUDA_OK(c->s_x.resize((size_t)nin * nlev));
+    CUDA_OK(c->s_y.resize((size_t)nout * nlev));
+    if (ncoef) CUDA_OK(c->s_c.resize((size_t)ncoef * nlev));
+    cudaStream_t st = c->stream;
+    if (ncoef) {
+        CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_coeff, (size_t)ncoef * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = transpose(c, true, ncoef, nlev, ld, c->s_lev.p, c->s_c.p, st))) return rc;
+    }
+    CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_x, (size_t)nin * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = transpose(c, true, nin, nlev, ld, c->s_lev.p, c->s_x.p, st))) return rc;
+    // rows the operator does not write (halo rows in owner-computes mode) stay zero
+    CUDA_OK(cudaMemsetAsync(c->s_y.p, 0, (size_t)nout * nlev * sizeof(double), st));
+    switch (op) {
+        case 0: rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
+        case 3: rc = apply_m1(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
+        case 1: rc = apply_m2(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
+        case 5: rc = apply_m2(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
+        case 2: rc = apply_m0(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
+        case 6: rc = apply_m0(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
+        case 4: rc = apply_k(c, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
+        default: rc = apply_inc(c, op - 10, nlev, ld, c->s_x.p, c->s_y.p, st); break;
+    }
+    if (rc) return rc;
+    if ((rc = transpose(c, false, nout, nlev, ld, c->s_y.p, c->s_lev.p, st))) return rc;
+    CUDA_OK(cudaMemcpyAsync(h_y, c->s_lev.p, (size_t)nout * nlev * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return MIMSEM_OK;
+}
+
+int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Device-side data structures shared by the kernels and the host engine (sm_100a).
+#pragma once
+#include <cstdint>
+
+namespace mimsem {
+
+constexpr int kMaxP = 6;
+
+// Kernel arguments, passed by value: they live in the constant bank, so the (p+1) x p edge table
+// E and the quadrature weights are broadcast operands of the FP64 FMAs (no shared-memory or
+// global traffic for the basis).  The reference re-tabulates these inside every assemble call
+// (eul/Assembly.cpp:69-71).
+struct KArgs {
+    // work
+    int nel;            // elements to compute (owned)
+    int nlev;           // columns per field
+    int ld;             // leading dimension of the fields
+    int lev0;           // thickness level of column 0
+    int lev_stride;     // 1, or 0 when every column uses thickness level lev0
+    int nkT;            // leading dimension of the thickness table
+    int tpow;           // number of 1/thick factors per quadrature point (0..2)
+    double scale;
+    // topology (device pointers, local indices)
+    const int* el1x;
+    const int* el1y;
+    const int* el2;
+    const int* elq;
+    const int* nbr;               // [nel][2] west / south neighbour: elem | side<<29 | rev<<30, or -1
+    const unsigned char* eflags;  // [nel] bit0: write east side, bit1: write north side (partial-sum mode)
+    // geometry (device pointers)
+    const double* G;              // [nel_total][q2][3] or [nel_total][q2]
+    const double* tinv;           // [nq][nkT] inverse layer thickness, level fastest
+    // fields
+    const double* c;              // coefficient field (h2 or u1) or nullptr
+    const double* x;
+    double* y;
+    // basis
+    double E[(kMaxP + 1) * kMaxP];   // E[q*p + i] = e_i(x_q)
+};
+
+// Padded ELL incidence stencil: row r has entries (col[r*width+j], sgn[r*width+j]), col = -1 pads.
+struct EllArgs {
+    int64_t nrows;
+    int width;
+    int nlev, ld;
+    const int* rows;     // optional row list (nullptr: rows 0..nrows-1)
+    const int* col;
+    const signed char* sgn;
+    const double* x;
+    double* y;
+};
+
+// node -> (element, quadrature point) adjacency for the 0-form operators
+struct NodeArgs {
+    int n0;
+    int nlev, ld, lev0, lev_stride, nkT, tpow;
+    double scale;
+    const int* adj_ptr;   // [n0+1]
+    const int* adj_eq;    // elem*q2 + q
+    const int* node_q;    // [n0] quadrature-point index of the node (thickness lookup)
+    const int* el2;
+    const double* D0;     // [n0] sum_e w_q det
+    const double* wq;     // [q2] w_qx * w_qy
+    const double* tinv;
+    const double* c;      // h2 or nullptr
+    const double* x;
+    double* y;
+    double E[(kMaxP + 1) * kMaxP];
+};
+
+}  // namespace mimsem

@@ -1,0 +1,482 @@
+// Matrix-free, sum-factorised FP64 element kernels for sm_100a.
+//
+// Work decomposition: one thread per (element, vertical level), level fastest, over fields in
+// column layout f[dof*ld + k].  Consecutive lanes therefore touch consecutive addresses for
+// every DOF of the element (perfectly coalesced 8-byte accesses, runs of nlev*8 bytes), the
+// whole element contraction happens in registers (no shuffles, no shared memory), geometry and
+// index tables are warp-uniform broadcast loads amortised over the nlev levels of the launch,
+// and the edge basis table sits in the constant bank (kernel parameters).
+//
+// Shared degrees of freedom are summed by GATHER, not by atomics: an element owns its west,
+// south and interior edges (the reference's global numbering has exactly this ownership,
+// scr/Proc2.py:105-123); the contribution of the west / south neighbour to those edges only
+// needs that neighbour's east column / north row of quadrature points, which the owner
+// recomputes.  Results are therefore bit-reproducible and independent of the partition.
+//
+// Formula sheet (restated from the reference, m == p so the nodal table is the identity):
+//   ul0(qx,qy) = sum_iy E[qy][iy] xx(qx,iy)      ul1(qx,qy) = sum_ix E[qx][ix] xy(ix,qy)
+//   hl (qx,qy) = sum_iy E[qy][iy] sum_ix E[qx][ix] h(ix,iy)
+//   M1 : f = c (Gaa ul0 + Gab ul1 , Gab ul0 + Gbb ul1),  c = s w/det t^tpow [hl/det]
+//        y^x(ix,iy) = sum_qy E[qy][iy] f0(ix,qy) ;  y^y(ix,iy) = sum_qx E[qx][ix] f1(qx,iy)
+//        (eul/Assembly.cpp:99-131 Umat, :432-467 Uhmat; matrix-free twins :2144-2188, :2221-2268)
+//   M2 : y = W^T c W x,  c = s w/det t^tpow [rho_l/det]          (eul/Assembly.cpp:347-358, :1268-1285)
+//   K  : y = W^T (ka ul0(x) + kb ul1(x)),  (ka,kb) = 1/2 s t^2 w/det^2 G ul(u1)   (eul/Assembly.cpp:951-979)
+#pragma once
+#include "engine.cuh"
+
+namespace mimsem {
+
+template <int P>
+struct ElDim {
+    static constexpr int NP1 = P + 1;
+    static constexpr int N1E = P * (P + 1);
+    static constexpr int N2E = P * P;
+    static constexpr int Q2 = (P + 1) * (P + 1);
+};
+
+__device__ __forceinline__ double ldro(const double* p) { return __ldg(p); }
+
+// scale * (1/thick)^tpow at local quadrature point gq, column k
+__device__ __forceinline__ double thick_factor(const KArgs& a, int gq, int k) {
+    double f = a.scale;
+    if (a.tpow > 0) {
+        const double t = ldro(a.tinv + (size_t)gq * a.nkT + a.lev0 + k * a.lev_stride);
+        f *= t;
+        if (a.tpow > 1) f *= t;
+    }
+    return f;
+}
+
+// Contribution of neighbour element n to the P edges of one of its far sides:
+//   side 0: n's east column of x-normal edges  (quadrature points (P, qy))
+//   side 1: n's north row of y-normal edges    (quadrature points (qx, P))
+template <int P, bool WITH_H>
+__device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, bool rev, int k, double (&out)[P]) {
+    using D = ElDim<P>;
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    const int* __restrict__ nx = a.el1x + (size_t)n * D::N1E;
+    const int* __restrict__ ny = a.el1y + (size_t)n * D::N1E;
+    const int* __restrict__ nq = a.elq + (size_t)n * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)n * D::Q2 * 3;
+    double f[P + 1];
+    double hs[P];   // h contracted along the side-normal direction at the far abscissa
+    if (WITH_H) {
+        const double* __restrict__ h = a.c + k;
+        const int* __restrict__ n2 = a.el2 + (size_t)n * D::N2E;
+#pragma unroll
+        for (int i = 0; i < P; i++) hs[i] = 0.0;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++)
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                const double hv = ldro(h + (size_t)n2[iy * P + ix] * ld);
+                if (side == 0) hs[iy] += a.E[P * P + ix] * hv;   // E[P][ix]
+                else hs[ix] += a.E[P * P + iy] * hv;             // E[P][iy]
+            }
+    }
+    if (side == 0) {
+        double xe[P];
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) xe[iy] = ldro(x + (size_t)nx[iy * D::NP1 + P] * ld);
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xe[iy];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) ul1 += a.E[P * P + ix] * ldro(x + (size_t)ny[qy * P + ix] * ld);
+            const int q = qy * D::NP1 + P;
+            double c = thick_factor(a, nq[q], k);
+            if (WITH_H) {
+                double hl = 0.0;
+#pragma unroll
+                for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hs[iy];
+                c *= hl;
+            }
+            f[qy] = c * (G[q * 3 + 0] * ul0 + G[q * 3 + 1] * ul1);
+        }
+    } else {
+        double ye[P];
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) ye[ix] = ldro(x + (size_t)ny[P * P + ix] * ld);
+#pragma unroll
+        for (int qx = 0; qx <= P; qx++) {
+            double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * ye[ix];
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) ul0 += a.E[P * P + iy] * ldro(x + (size_t)nx[iy * D::NP1 + qx] * ld);
+            const int q = P * D::NP1 + qx;
+            double c = thick_factor(a, nq[q], k);
+            if (WITH_H) {
+                double hl = 0.0;
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) hl += a.E[qx * P + ix] * hs[ix];
+                c *= hl;
+            }
+            f[qx] = c * (G[q * 3 + 1] * ul0 + G[q * 3 + 2] * ul1);
+        }
+    }
+    double o[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q <= P; q++) s += a.E[q * P + i] * f[q];
+        o[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) out[i] = rev ? o[P - 1 - i] : o[i];
+}
+
+// y = M1 x   (WITH_H: M1(h) x with the 2-form coefficient a.c)
+template <int P, bool WITH_H>
+__global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.nel * a.nlev) return;
+    const int e = (int)(idx / a.nlev);
+    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    double* __restrict__ y = a.y + k;
+    const int* __restrict__ ex = a.el1x + (size_t)e * D::N1E;
+    const int* __restrict__ ey = a.el1y + (size_t)e * D::N1E;
+    const int* __restrict__ eq = a.elq + (size_t)e * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)e * D::Q2 * 3;
+
+    // own degrees of freedom
+    double xy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) xy[iy][ix] = ldro(x + (size_t)ey[iy * P + ix] * ld);
+    double xx[P][P + 1];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix <= P; ix++) xx[iy][ix] = ldro(x + (size_t)ex[iy * D::NP1 + ix] * ld);
+    double hx[P][P + 1];   // h contracted in x: hx[iy][qx]
+    if (WITH_H) {
+        const double* __restrict__ h = a.c + k;
+        const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double hv[P];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) hv[ix] = ldro(h + (size_t)e2[iy * P + ix] * ld);
+#pragma unroll
+            for (int qx = 0; qx <= P; qx++) {
+                double s = 0.0;
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * hv[ix];
+                hx[iy][qx] = s;
+            }
+        }
+    }
+
+    // neighbours' contributions to the west x-edges and south y-edges
+    double cw[P], cs[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) cw[i] = cs[i] = 0.0;
+    const int nw = a.nbr[2 * e + 0], ns = a.nbr[2 * e + 1];
+    if (nw >= 0) m1_far_side<P, WITH_H>(a, nw & 0x1fffffff, (nw >> 29) & 1, (nw >> 30) & 1, k, cw);
+    if (ns >= 0) m1_far_side<P, WITH_H>(a, ns & 0x1fffffff, (ns >> 29) & 1, (ns >> 30) & 1, k, cs);
+
+    const unsigned flags = a.eflags[e];
+    double yy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) yy[iy][ix] = 0.0;
+
+#pragma unroll
+    for (int qx = 0; qx <= P; qx++) {
+        double f0[P + 1];
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xx[iy][qx];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * xy[qy][ix];
+            const int q = qy * D::NP1 + qx;
+            double c = thick_factor(a, eq[q], k);
+            if (WITH_H) {
+                double hl = 0.0;
+#pragma unroll
+                for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hx[iy][qx];
+                c *= hl;
+            }
+            const double g0 = G[q * 3 + 0], g1 = G[q * 3 + 1], g2 = G[q * 3 + 2];
+            f0[qy] = c * (g0 * ul0 + g1 * ul1);
+            const double f1 = c * (g1 * ul0 + g2 * ul1);
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) yy[qy][ix] += a.E[qx * P + ix] * f1;
+        }
+        // x-normal edges of column ix = qx
+        if (qx < P || (flags & 1u)) {
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                double s = (qx == 0) ? cw[iy] : 0.0;
+#pragma unroll
+                for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
+                y[(size_t)ex[iy * D::NP1 + qx] * ld] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)ey[iy * P + ix] * ld] = yy[iy][ix] + (iy == 0 ? cs[ix] : 0.0);
+    if (flags & 2u) {
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)ey[P * P + ix] * ld] = yy[P][ix];
+    }
+}
+
+// y = M2 x   (WITH_H: M2(rho) x)
+template <int P, bool WITH_H>
+__global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.nel * a.nlev) return;
+    const int e = (int)(idx / a.nlev);
+    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    double* __restrict__ y = a.y + k;
+    const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
+    const int* __restrict__ eq = a.elq + (size_t)e * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)e * D::Q2;
+
+    double ax[P][P + 1];   // x contracted in x-direction: ax[iy][qx]
+    double rx[P][P + 1];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++) {
+        double hv[P], rv[P];
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) {
+            hv[ix] = ldro(x + (size_t)e2[iy * P + ix] * ld);
+            if (WITH_H) rv[ix] = ldro(a.c + k + (size_t)e2[iy * P + ix] * ld);
+        }
+#pragma unroll
+        for (int qx = 0; qx <= P; qx++) {
+            double s = 0.0, r = 0.0;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                s += a.E[qx * P + ix] * hv[ix];
+                if (WITH_H) r += a.E[qx * P + ix] * rv[ix];
+            }
+            ax[iy][qx] = s;
+            if (WITH_H) rx[iy][qx] = r;
+        }
+    }
+    double out[P][P];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) out[iy][ix] = 0.0;
+#pragma unroll
+    for (int qx = 0; qx <= P; qx++) {
+        double g[P + 1];
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double hl = 0.0, rl = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                hl += a.E[qy * P + iy] * ax[iy][qx];
+                if (WITH_H) rl += a.E[qy * P + iy] * rx[iy][qx];
+            }
+            const int q = qy * D::NP1 + qx;
+            double c = thick_factor(a, eq[q], k) * G[q];
+            if (WITH_H) c *= rl;
+            g[qy] = c * hl;
+        }
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double b = 0.0;
+#pragma unroll
+            for (int qy = 0; qy <= P; qy++) b += a.E[qy * P + iy] * g[qy];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) out[iy][ix] += a.E[qx * P + ix] * b;
+        }
+    }
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)e2[iy * P + ix] * ld] = out[iy][ix];
+}
+
+// y = K(u1) x : 1-form -> 2-form, coefficient a.c = u1 (1-form, same array indexing as x)
+template <int P>
+__global__ void __launch_bounds__(128) k_apply_k(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.nel * a.nlev) return;
+    const int e = (int)(idx / a.nlev);
+    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    const double* __restrict__ u = a.c + k;
+    double* __restrict__ y = a.y + k;
+    const int* __restrict__ ex = a.el1x + (size_t)e * D::N1E;
+    const int* __restrict__ ey = a.el1y + (size_t)e * D::N1E;
+    const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
+    const int* __restrict__ eq = a.elq + (size_t)e * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)e * D::Q2 * 3;
+
+    double xy[P + 1][P], uy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) {
+            const size_t o = (size_t)ey[iy * P + ix] * ld;
+            xy[iy][ix] = ldro(x + o);
+            uy[iy][ix] = ldro(u + o);
+        }
+    double out[P][P];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) out[iy][ix] = 0.0;
+#pragma unroll
+    for (int qx = 0; qx <= P; qx++) {
+        double xc[P], uc[P];
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            const size_t o = (size_t)ex[iy * D::NP1 + qx] * ld;
+            xc[iy] = ldro(x + o);
+            uc[iy] = ldro(u + o);
+        }
+        double g[P + 1];
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double x0 = 0.0, x1 = 0.0, a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                x0 += a.E[qy * P + iy] * xc[iy];
+                a0 += a.E[qy * P + iy] * uc[iy];
+            }
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                x1 += a.E[qx * P + ix] * xy[qy][ix];
+                a1 += a.E[qx * P + ix] * uy[qy][ix];
+            }
+            const int q = qy * D::NP1 + qx;
+            const double c = 0.5 * thick_factor(a, eq[q], k);
+            const double ka = G[q * 3 + 0] * a0 + G[q * 3 + 1] * a1;
+            const double kb = G[q * 3 + 1] * a0 + G[q * 3 + 2] * a1;
+            g[qy] = c * (ka * x0 + kb * x1);
+        }
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double b = 0.0;
+#pragma unroll
+            for (int qy = 0; qy <= P; qy++) b += a.E[qy * P + iy] * g[qy];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) out[iy][ix] += a.E[qx * P + ix] * b;
+        }
+    }
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)e2[iy * P + ix] * ld] = out[iy][ix];
+}
+
+// 0-form mass matrix.  With m == p the nodal tabulation is the identity, so M0 is diagonal:
+//   y_n = s t^tpow x_n sum_{(e,q) at n} w_q det_{e,q}                       (eul/Assembly.cpp:2021-2036)
+//   assemble_h: y_n = s t^2 x_n sum_{(e,q) at n} w_q hl^e_q(h)              (eul/Assembly.cpp:2067-2086)
+template <int P, bool WITH_H>
+__global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeArgs a) {
+    using D = ElDim<P>;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.n0 * a.nlev) return;
+    const int n = (int)(idx / a.nlev);
+    const int k = (int)(idx - (int64_t)n * a.nlev);
+    const size_t ld = a.ld;
+    double f = a.scale;
+    if (a.tpow > 0) {
+        const double t = ldro(a.tinv + (size_t)a.node_q[n] * a.nkT + a.lev0 + k * a.lev_stride);
+        f *= t;
+        if (a.tpow > 1) f *= t;
+    }
+    double d;
+    if (!WITH_H) {
+        d = a.D0[n];
+    } else {
+        d = 0.0;
+        const double* __restrict__ h = a.c + k;
+        for (int j = a.adj_ptr[n]; j < a.adj_ptr[n + 1]; j++) {
+            const int eqv = a.adj_eq[j];
+            const int e = eqv / D::Q2, q = eqv - e * D::Q2;
+            const int qx = q % D::NP1, qy = q / D::NP1;
+            const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
+            double hl = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                double s = 0.0;
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * ldro(h + (size_t)e2[iy * P + ix] * ld);
+                hl += a.E[qy * P + iy] * s;
+            }
+            d += a.wq[q] * hl;
+        }
+    }
+    a.y[(size_t)n * ld + k] = f * d * ldro(a.x + (size_t)n * ld + k);
+}
+
+// y[r][k] = sum_j sgn[r][j] x[col[r][j]][k]   (entries sorted by column, as a CSR SpMV would add them)
+__global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllArgs a) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= a.nrows * a.nlev) return;
+    const int64_t rr = idx / a.nlev;
+    const int k = (int)(idx - rr * a.nlev);
+    const int64_t r = a.rows ? a.rows[rr] : rr;
+    double s = 0.0;
+    for (int j = 0; j < a.width; j++) {
+        const int c = a.col[r * a.width + j];
+        if (c < 0) break;
+        const double v = ldro(a.x + (size_t)c * a.ld + k);
+        s += (a.sgn[r * a.width + j] > 0) ? v : -v;
+    }
+    a.y[(size_t)r * a.ld + k] = s;
+}
+
+// levels[k*n + dof] <-> columns[dof*ld + k] through a padded shared-memory tile
+template <bool TO_COLUMNS>
+__global__ void __launch_bounds__(256) k_transpose(int64_t n, int nlev, int ld, const double* __restrict__ in,
+                                                   double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int64_t d0 = (int64_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (TO_COLUMNS) {
+        for (int j = ty; j < 32; j += 8) {
+            const int k = k0 + j;
+            const int64_t d = d0 + tx;
+            if (k < nlev && d < n) tile[j][tx] = in[(size_t)k * n + d];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int64_t d = d0 + j;
+            const int k = k0 + tx;
+            if (k < nlev && d < n) out[(size_t)d * ld + k] = tile[tx][j];
+        }
+    } else {
+        for (int j = ty; j < 32; j += 8) {
+            const int64_t d = d0 + j;
+            const int k = k0 + tx;
+            if (k < nlev && d < n) tile[j][tx] = in[(size_t)d * ld + k];
+        }
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8) {
+            const int k = k0 + j;
+            const int64_t d = d0 + tx;
+            if (k < nlev && d < n) out[(size_t)k * n + d] = tile[tx][j];
+        }
+    }
+}
+
+}  // namespace mimsem

@@ -1,0 +1,187 @@
+"""Engine: ctypes wrapper of the mimsem_gpu_* device engine.  Device memory and streams come from
+torch (plumbing only); every numerical step is a kernel of libmimsem_gpu.so."""
+import ctypes as C
+
+import numpy as np
+
+from .lib import load_library, check, MimsemError, _dp, _ip, _lp, _vp
+from .mesh import Basis
+
+OPS = dict(M1=0, M2=1, M0=2, M1h=3, K=4, M2h=5, M0h=6, E10=10, E01=11, E21=12, E12=13)
+FIXED_LEVEL = 1
+
+
+def _np_ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Engine:
+    """One subdomain on one GPU.
+
+    Fields are torch float64 CUDA tensors in column layout, shape (ndof, nlev), contiguous
+    (element [dof, k] at dof*ld + k): see include/mimsem_gpu.h.
+    """
+
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise MimsemError("no CUDA device: mimsem_b200 has no CPU fallback")
+        self.torch = torch
+        self.L = load_library()
+        self.device = device
+        h = _vp()
+        check(self.L.mimsem_gpu_create(device, C.byref(h)))
+        self._h = h
+        self.nk = 0
+
+    @classmethod
+    def from_mesh(cls, mesh, device=0, thick=None):
+        """Whole global mesh as a single subdomain (owner-computes, no halo)."""
+        eng = cls(device)
+        b = Basis(mesh.p, mesh.m)
+        eng.set_basis(b)
+        eng.set_topo(mesh.el0, mesh.el1x, mesh.el1y, mesh.el2, mesh.elq, mesh.N0, mesh.N1, mesh.N2, mesh.NQ)
+        eng.set_geom(mesh.J, mesh.det)
+        if thick is not None:
+            eng.set_thickness(thick)
+        return eng
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.mimsem_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- setup
+    def set_basis(self, basis):
+        self.p, self.m = basis.p, basis.m
+        w = np.ascontiguousarray(basis.w)
+        l = np.ascontiguousarray(basis.ljxi)
+        e = np.ascontiguousarray(basis.ejxi)
+        check(self.L.mimsem_gpu_set_basis(self._h, basis.p, basis.m, _np_ptr(w, _dp), _np_ptr(l, _dp), _np_ptr(e, _dp)))
+
+    def set_topo(self, el0, el1x, el1y, el2, elq, n0, n1, n2, nq, nel_owned=None, mode=0):
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (el0, el1x, el1y, el2, elq)]
+        nel_total = arrs[0].shape[0]
+        nel_owned = nel_total if nel_owned is None else nel_owned
+        check(self.L.mimsem_gpu_set_topo(self._h, nel_total, nel_owned, n0, n1, n2, nq, mode,
+                                         *[_np_ptr(a, _ip) for a in arrs]))
+        self.n0, self.n1, self.n2, self.nq = n0, n1, n2, nq
+        self.nel_total, self.nel_owned = nel_total, nel_owned
+
+    def set_geom(self, J, det):
+        J = np.ascontiguousarray(J, dtype=np.float64)
+        det = np.ascontiguousarray(det, dtype=np.float64)
+        assert J.size == self.nel_total * (self.m + 1) ** 2 * 4 and det.size == self.nel_total * (self.m + 1) ** 2
+        check(self.L.mimsem_gpu_set_geom(self._h, _np_ptr(J, _dp), _np_ptr(det, _dp)))
+
+    def set_thickness(self, thick):
+        """thick[nk][nq] (level-major, as the reference's Geom::thick)."""
+        if thick is None:
+            check(self.L.mimsem_gpu_set_thickness(self._h, 0, None))
+            self.nk = 0
+            return
+        thick = np.ascontiguousarray(thick, dtype=np.float64)
+        assert thick.ndim == 2 and thick.shape[1] == self.nq, thick.shape
+        check(self.L.mimsem_gpu_set_thickness(self._h, thick.shape[0], _np_ptr(thick, _dp)))
+        self.nk = thick.shape[0]
+
+    # ---------------------------------------------------------------- helpers
+    def space_sizes(self, op):
+        n0, n1, n2 = self.n0, self.n1, self.n2
+        return {"M1": (n1, n1, 0), "M1h": (n1, n1, n2), "M2": (n2, n2, 0), "M2h": (n2, n2, n2), "M0": (n0, n0, 0),
+                "M0h": (n0, n0, n2), "K": (n1, n2, n1), "E10": (n0, n1, 0), "E01": (n1, n0, 0), "E21": (n1, n2, 0),
+                "E12": (n2, n1, 0)}[op]
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty(self, n, nlev):
+        return self.torch.empty((n, nlev), dtype=self.torch.float64, device="cuda:%d" % self.device)
+
+    def zeros(self, n, nlev):
+        return self.torch.zeros((n, nlev), dtype=self.torch.float64, device="cuda:%d" % self.device)
+
+    def _chk(self, t, n, nlev, name):
+        if t.dtype != self.torch.float64 or not t.is_cuda or not t.is_contiguous() or tuple(t.shape) != (n, nlev):
+            raise MimsemError("%s must be a contiguous float64 CUDA tensor of shape (%d, %d), got %s %s"
+                              % (name, n, nlev, tuple(t.shape), t.dtype))
+
+    def to_columns(self, levels):
+        """(nlev, n) level-major device tensor -> (n, nlev) column layout."""
+        nlev, n = levels.shape
+        out = self.empty(n, nlev)
+        check(self.L.mimsem_gpu_levels_to_columns(self._h, n, nlev, nlev, levels.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def to_levels(self, cols):
+        n, nlev = cols.shape
+        out = self.torch.empty((nlev, n), dtype=self.torch.float64, device=cols.device)
+        check(self.L.mimsem_gpu_columns_to_levels(self._h, n, nlev, nlev, cols.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    # ---------------------------------------------------------------- applies (device resident)
+    def apply(self, op, x, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0):
+        nin, nout, ncoef = self.space_sizes(op)
+        nlev = x.shape[1]
+        self._chk(x, nin, nlev, "x")
+        if out is None:
+            # rows a subdomain does not own are not written by the kernels
+            out = self.zeros(nout, nlev) if self.nel_owned != self.nel_total else self.empty(nout, nlev)
+        self._chk(out, nout, nlev, "out")
+        if ncoef:
+            if coeff is None:
+                raise MimsemError("operator %s needs a coefficient field" % op)
+            self._chk(coeff, ncoef, nlev, "coeff")
+        st = self._stream()
+        h, L = self._h, self.L
+        xp, yp = x.data_ptr(), out.data_ptr()
+        if op in ("M1", "M2", "M0"):
+            fn = getattr(L, "mimsem_gpu_apply_" + op)
+            check(fn(h, lev0, nlev, nlev, scale, tpow, flags, xp, yp, st))
+        elif op in ("M1h", "M2h", "M0h", "K"):
+            fn = getattr(L, "mimsem_gpu_apply_" + op)
+            check(fn(h, lev0, nlev, nlev, scale, tpow, flags, coeff.data_ptr(), xp, yp, st))
+        else:
+            check(L.mimsem_gpu_apply_incidence(h, OPS[op] - 10, nlev, nlev, xp, yp, st))
+        return out
+
+    # ---------------------------------------------------------------- end to end with host buffers
+    def apply_host(self, op, x, coeff=None, lev0=0, scale=1.0, tpow=0, flags=0, out=None):
+        """x: numpy (nlev, nin) in the reference's per-level layout; returns numpy (nlev, nout)."""
+        nin, nout, ncoef = self.space_sizes(op)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nlev = x.shape[0]
+        assert x.shape == (nlev, nin), x.shape
+        if out is None:
+            out = np.empty((nlev, nout))
+        cp = None
+        if ncoef:
+            coeff = np.ascontiguousarray(coeff, dtype=np.float64)
+            assert coeff.shape == (nlev, ncoef)
+            cp = _np_ptr(coeff, _dp)
+        check(self.L.mimsem_gpu_apply_host(self._h, OPS[op], lev0, nlev, scale, tpow, flags, cp, _np_ptr(x, _dp),
+                                           _np_ptr(out, _dp)))
+        return out
+
+    def incidence_csr(self, which):
+        """The +-1 stencil of E10/E01/E21/E12 as a scipy CSR matrix over local indices."""
+        import scipy.sparse as sp
+        w = OPS[which] - 10
+        sz = np.zeros(3, dtype=np.int64)
+        check(self.L.mimsem_gpu_incidence_csr(self._h, w, _np_ptr(sz, _lp), None, None, None))
+        indptr = np.zeros(sz[0] + 1, dtype=np.int64)
+        indices = np.zeros(sz[2], dtype=np.int32)
+        vals = np.zeros(sz[2])
+        check(self.L.mimsem_gpu_incidence_csr(self._h, w, _np_ptr(sz, _lp), _np_ptr(indptr, _lp), _np_ptr(indices, _ip),
+                                              _np_ptr(vals, _dp)))
+        return sp.csr_matrix((vals, indices, indptr), shape=(int(sz[0]), int(sz[1])))
+
+    @property
+    def launch_count(self):
+        return int(self.L.mimsem_gpu_launch_count(self._h))

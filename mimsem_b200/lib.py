@@ -1,0 +1,77 @@
+"""ctypes loader for libmimsem_gpu.so -- fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmimsem_gpu.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+# every symbol include/mimsem_gpu.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "mimsem_last_error": (C.c_char_p, []),
+    "mimsem_basis_gll": (C.c_int, [C.c_int, _dp, _dp]),
+    "mimsem_basis_tables": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
+    "mimsem_elmat": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp]),
+    "mimsem_topo_patch_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip]),
+    "mimsem_topo_patch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip]),
+    "mimsem_topo_write_input": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    "mimsem_mesh_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "mimsem_mesh_destroy": (None, [_vp]),
+    "mimsem_mesh_sizes": (C.c_int, [_vp, _lp]),
+    "mimsem_mesh_tables": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _ip]),
+    "mimsem_mesh_geometry": (C.c_int, [_vp, _dp, _dp]),
+    "mimsem_mesh_coords": (C.c_int, [_vp, _dp]),
+    "mimsem_gpu_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "mimsem_gpu_destroy": (C.c_int, [_vp]),
+    "mimsem_gpu_set_basis": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "mimsem_gpu_set_topo": (C.c_int, [_vp] + [C.c_int] * 7 + [_ip] * 5),
+    "mimsem_gpu_set_geom": (C.c_int, [_vp, _dp, _dp]),
+    "mimsem_gpu_set_thickness": (C.c_int, [_vp, C.c_int, _dp]),
+    "mimsem_gpu_sizes": (C.c_int, [_vp, _lp]),
+    "mimsem_gpu_levels_to_columns": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_columns_to_levels": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M0": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M1h": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M2h": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M0h": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_K": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_incidence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_incidence_csr": (C.c_int, [_vp, C.c_int, _lp, _lp, _ip, _dp]),
+    "mimsem_gpu_apply_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
+}
+
+
+class MimsemError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmimsem_gpu.so (built by mimsem_b200/csrc/Makefile or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MimsemError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MimsemError("mimsem error %d: %s" % (rc, load_library().mimsem_last_error().decode()))
