@@ -1,0 +1,92 @@
+"""CPU tests: the numpy oracle restatement (oracle/mimsem_oracle.py) is pinned against golden
+vectors produced by the reference's own sources (oracle/_ref; tests/golden/make_golden.py) and,
+when oracle/_ref is present, against a live run of the reference."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import TOL, golden, have_ref_lib, have_ref_mesh, ref_mesh_dir, rel_l2
+
+from oracle import mimsem_oracle as mo
+
+needs_mesh = pytest.mark.skipif(not have_ref_mesh("sphere", 3, 4, 6), reason="oracle/_ref/meshes not generated")
+
+
+def _csr(g, nm, shape):
+    return sp.csr_matrix((g[nm + "_data"], g[nm + "_indices"], g[nm + "_indptr"]), shape=shape)
+
+
+@needs_mesh
+def test_oracle_eul_vs_golden():
+    g = golden("ops_eul_sphere_p3_ne4.npz")
+    O = mo.Oracle(ref_mesh_dir("sphere", 3, 4, 6), 6, "sphere", "eul")
+    O.set_thick(g["thick"])
+    s = float(g["scale"])
+    nk = int(g["nk"])
+    assert rel_l2(np.concatenate(O.det), g["det"]) < 1e-14
+    for lev in range(nk):
+        assert rel_l2(O.umat(lev, s, 1) @ g["x1"][lev], g["y_Umat_vs1"][lev]) < TOL
+        assert rel_l2(O.umat(lev, s, 0) @ g["x1"][lev], g["y_Umat_vs0"][lev]) < TOL
+        assert rel_l2(O.wmat(lev, s, 1) @ g["x2"][lev], g["y_Wmat_vs1"][lev]) < TOL
+        assert rel_l2(O.pmat(lev, s) @ g["x0"][lev], g["y_Pmat"][lev]) < TOL
+        assert rel_l2(O.pmat(lev, s, h2=g["h2"][lev]) @ g["x0"][lev], g["y_Pmat_h"][lev]) < TOL
+        assert rel_l2(O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=1) @ g["x1"][lev], g["y_Uhmat_cv1"][lev]) < TOL
+        assert rel_l2(O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=0) @ g["x1"][lev], g["y_Uhmat_cv0"][lev]) < TOL
+        assert rel_l2(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1) @ g["x2"][lev], g["y_Whmat_vs1"][lev]) < TOL
+        assert rel_l2(O.wtqumat(g["u1"][lev], lev, s) @ g["x1"][lev], g["y_WtQUmat"][lev]) < TOL
+    E10, E01 = O.e10()
+    E21, E12 = O.e21()
+    for nm, A in (("E10", E10), ("E01", E01), ("E21", E21), ("E12", E12)):
+        assert abs(A - _csr(g, nm, A.shape)).max() == 0.0   # exact +-1 stencils
+    assert abs(E21 @ E10).max() == 0.0                      # E21 E10 = 0 as a matrix identity
+
+
+@needs_mesh
+def test_oracle_src_vs_golden():
+    g = golden("ops_src_sphere_p3_ne4.npz")
+    O = mo.Oracle(ref_mesh_dir("sphere", 3, 4, 6), 6, "sphere", "src")
+    assert rel_l2(O.umat() @ g["x1"][0], g["y_Umat"][0]) < TOL
+    assert rel_l2(O.wmat() @ g["x2"][0], g["y_Wmat"][0]) < TOL
+    assert rel_l2(O.pmat(tpow=0) @ g["x0"][0], g["y_Pmat"][0]) < TOL
+    assert rel_l2(O.umat(h2=g["h2"][0]) @ g["x1"][0], g["y_Uhmat"][0]) < TOL
+    assert rel_l2(O.wtqumat(g["u1"][0], tpow=0) @ g["x1"][0], g["y_WtQUmat"][0]) < TOL
+
+
+@pytest.mark.skipif(not have_ref_mesh("box", 3, 4, 1), reason="oracle/_ref/meshes not generated")
+def test_oracle_box_vs_golden():
+    g = golden("ops_box_p3_ne4.npz")
+    O = mo.Oracle(ref_mesh_dir("box", 3, 4, 1), 1, "box", "box")
+    O.set_thick(g["thick"])
+    s = float(g["scale"])
+    for lev in range(int(g["nk"])):
+        # box/: Umat/Wmat are built once with level-0 thickness (box/Assembly.cpp:44-45)
+        assert rel_l2(O.umat(0, s, 1) @ g["x1"][lev], g["y_Umat_M"][lev]) < TOL
+        assert rel_l2(O.umat(0, s, 0) @ g["x1"][lev], g["y_Umat_Mo"][lev]) < TOL
+        assert rel_l2(O.wmat(0, s, 1) @ g["x2"][lev], g["y_Wmat_M"][lev]) < TOL
+        assert rel_l2(O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=1) @ g["x1"][lev], g["y_Uhmat_cv1"][lev]) < TOL
+        assert rel_l2(O.wtqumat(g["u1"][lev], lev, s) @ g["x1"][lev], g["y_WtQUmat"][lev]) < TOL
+
+
+@pytest.mark.skipif(not (have_ref_lib("eul") and have_ref_mesh("sphere", 4, 2, 6)), reason="oracle/_ref not built")
+def test_oracle_vs_live_reference_p4():
+    """Live run of the reference's own sources (oracle/_ref) against the restatement, p = 4."""
+    from oracle import refbind as rb
+    md = ref_mesh_dir("sphere", 4, 2, 6)
+    R = rb.Reference("eul", md, 6, nk=2)
+    O = mo.Oracle(md, 6, "sphere", "eul")
+    rng = np.random.default_rng(7)
+    thick = rng.uniform(100, 200, (2, O.N0))
+    O.set_thick(thick)
+    for r in range(6):
+        R.set_thick(r, thick[:, R.loc(r, "locq")])
+    x = rng.uniform(-1, 1, O.N1)
+    h = rng.uniform(0.5, 1.5, O.N2)
+    assert rel_l2(O.umat(1, 1e8, 1) @ x, R.assemble("Umat", 1, 1e8, True) @ x) < TOL
+    assert rel_l2(O.umat(1, 1e8, 1, h2=h, tpow_h=1) @ x, R.assemble("Uhmat", 1, 1e8, True, c2=h) @ x) < TOL
+    assert rel_l2(O.wtqumat(x, 0, 1e8) @ x, R.assemble("WtQUmat", 0, 1e8, c1=x) @ x) < TOL
+    # the reference's own matrix-free twin (Uvec::assemble, eul/Assembly.cpp:2124-2196) agrees with its matrix
+    y, _ = R.uvec_apply(x, lev=1, scale=1e8)
+    assert rel_l2(y, R.assemble("Umat", 1, 1e8, True) @ x) < TOL
+    R.close()
