@@ -72,6 +72,10 @@ struct mimsem_gpu_ctx {
     std::vector<int> h_adj_ptr, h_adj_eq, h_node_q;
 
     DevBuf<int> d_el0, d_el1x, d_el1y, d_el2, d_elq, d_nbr, d_adj_ptr, d_adj_eq, d_node_q;
+    DevBuf<int> d_el1xT, d_elqT, d_far;      // line-task tables
+    DevBuf<double> d_Gc, d_Gr, d_Gch, d_Grh;
+    int n_far = 0;
+    int m1_variant = 1;                      // 1: line tasks (default), 0: one thread per element-level
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
     int nkT = 0;
@@ -345,6 +349,12 @@ void fill_common(const mimsem_gpu_ctx* c, KArgs& a, int lev0, int nlev, int ld, 
     a.eflags = c->d_eflags.p;
     a.tinv = c->d_tinv.p;
     a.c = nullptr;
+    a.el1xT = c->d_el1xT.p;
+    a.elqT = c->d_elqT.p;
+    a.Gc = a.Gr = nullptr;
+    const FastDiv fd = make_fastdiv((unsigned)nlev);
+    a.div_m = fd.m;
+    a.div_s = fd.s;
     copy_basis(c, a);
 }
 
@@ -380,11 +390,32 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.x = x;
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
+    if (c->m1_variant == 0) {
+        return dispatch_p(c->p, [&](auto P) {
+            constexpr int p = decltype(P)::value;
+            if (with_h) k_apply_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+            else k_apply_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+            return finish_launch(c, "apply_M1");
+        });
+    }
+    a.Gc = with_h ? c->d_Gch.p : c->d_Gc.p;
+    a.Gr = with_h ? c->d_Grh.p : c->d_Gr.p;
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
-        if (with_h) k_apply_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        else k_apply_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "apply_M1");
+        dim3 grid(grid_for(threads, 128), 2 * p);
+        if (with_h) k_apply_m1_lines<p, true, false><<<grid, 128, 0, st>>>(a);
+        else k_apply_m1_lines<p, false, false><<<grid, 128, 0, st>>>(a);
+        int rc2 = finish_launch(c, "apply_M1");
+        if (rc2 || c->n_far == 0) return rc2;
+        // partial-sum mode: far lines nobody else in the subdomain computes
+        KArgs b = a;
+        b.nel = c->n_far;
+        b.nbr = c->d_far.p;
+        const int64_t t2 = (int64_t)b.nel * nlev;
+        if (with_h) k_apply_m1_lines<p, true, true><<<grid_for(t2, 128), 128, 0, st>>>(b);
+        else k_apply_m1_lines<p, false, true><<<grid_for(t2, 128), 128, 0, st>>>(b);
+        return finish_launch(c, "apply_M1 far lines");
     });
 }
 
@@ -452,6 +483,11 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.x = x;
     a.y = y;
     copy_basis(c, a);
+    {
+        const FastDiv fd = make_fastdiv((unsigned)nlev);
+        a.div_m = fd.m;
+        a.div_s = fd.s;
+    }
     const int64_t threads = (int64_t)a.n0 * nlev;
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
@@ -478,6 +514,11 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     a.sgn = d.sgn.p;
     a.x = x;
     a.y = y;
+    {
+        const FastDiv fd = make_fastdiv((unsigned)nlev);
+        a.div_m = fd.m;
+        a.div_s = fd.s;
+    }
     if (a.nrows == 0) return MIMSEM_OK;
     k_apply_ell<<<grid_for(a.nrows * nlev, 256), 256, 0, st>>>(a);
     return finish_launch(c, "apply_incidence");
@@ -575,6 +616,27 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
     if ((rc = build_neighbours(c))) return rc;
     if ((rc = build_node_adjacency(c))) return rc;
     if ((rc = build_incidence(c))) return rc;
+    {
+        // column-major copies so that every GLL line of an element is contiguous (line-task kernels)
+        const int N1E = P * NP1, Q2 = NP1 * NP1;
+        std::vector<int> xT((size_t)nel_total * N1E), qT((size_t)nel_total * Q2), far;
+        for (int e = 0; e < nel_total; e++) {
+            for (int iy = 0; iy < P; iy++)
+                for (int ix = 0; ix <= P; ix++) xT[(size_t)e * N1E + ix * P + iy] = c->h_el1x[(size_t)e * N1E + iy * NP1 + ix];
+            for (int qy = 0; qy <= P; qy++)
+                for (int qx = 0; qx <= P; qx++) qT[(size_t)e * Q2 + qx * NP1 + qy] = c->h_elq[(size_t)e * Q2 + qy * NP1 + qx];
+        }
+        for (int e = 0; e < nel_owned; e++) {
+            if (c->h_eflags[e] & 1) far.push_back(e << 1);
+            if (c->h_eflags[e] & 2) far.push_back((e << 1) | 1);
+        }
+        c->n_far = (int)far.size();
+        CUDA_OK(c->d_el1xT.upload(xT));
+        CUDA_OK(c->d_elqT.upload(qT));
+        CUDA_OK(c->d_far.upload(far));
+        const char* v = getenv("MIMSEM_M1_VARIANT");
+        if (v) c->m1_variant = atoi(v);
+    }
     CUDA_OK(c->d_el0.upload(c->h_el0));
     CUDA_OK(c->d_el1x.upload(c->h_el1x));
     CUDA_OK(c->d_el1y.upload(c->h_el1y));
@@ -614,6 +676,23 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
         W2[i] = wd;
         W2h[i] = wdd;
         D0[c->h_el0[i]] += w * det;   // element order, as MatSetValues(ADD_VALUES) accumulates
+    }
+    {
+        // line-ordered copies of the metric: Gc[e][qx][qy] = (g0,g1), Gr[e][qy][qx] = (g1,g2)
+        std::vector<double> Gc(npts * 2), Gr(npts * 2), Gch(npts * 2), Grh(npts * 2);
+        for (size_t e = 0; e < (size_t)c->nel_total; e++)
+            for (int qy = 0; qy < NP1; qy++)
+                for (int qx = 0; qx < NP1; qx++) {
+                    const size_t i = e * Q2 + qy * NP1 + qx, ic = e * Q2 + qx * NP1 + qy;
+                    Gc[ic * 2 + 0] = G1[i * 3 + 0];   Gc[ic * 2 + 1] = G1[i * 3 + 1];
+                    Gr[i * 2 + 0] = G1[i * 3 + 1];    Gr[i * 2 + 1] = G1[i * 3 + 2];
+                    Gch[ic * 2 + 0] = G1h[i * 3 + 0]; Gch[ic * 2 + 1] = G1h[i * 3 + 1];
+                    Grh[i * 2 + 0] = G1h[i * 3 + 1];  Grh[i * 2 + 1] = G1h[i * 3 + 2];
+                }
+        CUDA_OK(c->d_Gc.upload(Gc));
+        CUDA_OK(c->d_Gr.upload(Gr));
+        CUDA_OK(c->d_Gch.upload(Gch));
+        CUDA_OK(c->d_Grh.upload(Grh));
     }
     CUDA_OK(c->d_G1.upload(G1));
     CUDA_OK(c->d_G1h.upload(G1h));

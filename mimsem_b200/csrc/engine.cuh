@@ -27,6 +27,12 @@ struct KArgs {
     const int* elq;
     const int* nbr;               // [nel][2] west / south neighbour: elem | side<<29 | rev<<30, or -1
     const unsigned char* eflags;  // [nel] bit0: write east side, bit1: write north side (partial-sum mode)
+    // line-task tables (transposed copies so that one GLL line is contiguous)
+    const int* el1xT;             // [nel][ix][iy]  x-normal edges, column-major
+    const int* elqT;              // [nel][qx][qy]  quadrature points, column-major
+    const double* Gc;             // [nel][qx][qy][2] = (g0, g1) of G, column-major   (x-line tasks)
+    const double* Gr;             // [nel][qy][qx][2] = (g1, g2) of G, row-major      (y-line tasks)
+    unsigned div_m, div_s;        // magic number / shift for idx / nlev
     // geometry (device pointers)
     const double* G;              // [nel_total][q2][3] or [nel_total][q2]
     const double* tinv;           // [nq][nkT] inverse layer thickness, level fastest
@@ -38,11 +44,31 @@ struct KArgs {
     double E[(kMaxP + 1) * kMaxP];   // E[q*p + i] = e_i(x_q)
 };
 
+// Division of a 32-bit index by a launch-constant divisor (Granlund-Montgomery):
+// q = (umulhi(m, n) + n) >> s  with  s = ceil(log2 d),  m = floor(2^32 (2^s - d) / d) + 1.
+struct FastDiv {
+    unsigned m = 0, s = 0;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    unsigned s = 0;
+    while ((1ull << s) < d) s++;
+    f.s = s;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, unsigned s) {
+    return (unsigned)(((unsigned long long)__umulhi(m, n) + n) >> s);
+}
+#endif
+
 // Padded ELL incidence stencil: row r has entries (col[r*width+j], sgn[r*width+j]), col = -1 pads.
 struct EllArgs {
     int64_t nrows;
     int width;
     int nlev, ld;
+    unsigned div_m, div_s;
     const int* rows;     // optional row list (nullptr: rows 0..nrows-1)
     const int* col;
     const signed char* sgn;
@@ -54,6 +80,7 @@ struct EllArgs {
 struct NodeArgs {
     int n0;
     int nlev, ld, lev0, lev_stride, nkT, tpow;
+    unsigned div_m, div_s;
     double scale;
     const int* adj_ptr;   // [n0+1]
     const int* adj_eq;    // elem*q2 + q

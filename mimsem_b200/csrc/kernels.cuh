@@ -134,10 +134,10 @@ __device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, boo
 template <int P, bool WITH_H>
 __global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs a) {
     using D = ElDim<P>;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.nel * a.nlev) return;
-    const int e = (int)(idx / a.nlev);
-    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     double* __restrict__ y = a.y + k;
@@ -236,14 +236,155 @@ __global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// M1 as independent GLL-line tasks (v1).
+//
+// The 2x2 block structure of M1 couples x- and y-edges only through the quadrature points, so the
+// P x-edge outputs of one GLL column (ix fixed) need exactly the P+1 quadrature points of that
+// column, and the P y-edge outputs of one GLL row (iy fixed) the P+1 points of that row:
+//   column i:  out[iy] = sum_qy E[qy][iy] c (Gaa ul0 + Gab ul1)(i,qy)
+//   row    i:  out[ix] = sum_qx E[qx][ix] c (Gab ul0 + Gbb ul1)(qx,i)
+// One thread handles one (element, line, level): ~24 loads, ~80 FP64 FMAs, ~40 registers, so an SM
+// keeps 40+ warps resident instead of 11 (the thread-per-element kernel was latency-bound by
+// occupancy, profiles/r01_m1_v0_thread_per_element.md).  The west-most column / south-most row
+// additionally gathers the neighbour's far line (i = P), exactly as before.
+template <int P, int DIR, bool WITH_H>
+__device__ __forceinline__ void m1_line(const KArgs& a, int n, int i, int k, double (&out)[P]) {
+    using D = ElDim<P>;
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    // line-local DOFs (the P edges normal to the line direction that sit ON the line's abscissa)
+    // and the (P+1) x P edges of the other family that the line's quadrature points interpolate
+    const int* __restrict__ iown = (DIR == 0) ? a.el1xT + (size_t)n * D::N1E + i * P      // xx(i, iy), iy = 0..P-1
+                                              : a.el1y + (size_t)n * D::N1E + i * P;      // xy(ix, i), ix = 0..P-1
+    const int* __restrict__ ioth = (DIR == 0) ? a.el1y + (size_t)n * D::N1E               // xy(ix, qy): [qy][ix]
+                                              : a.el1xT + (size_t)n * D::N1E;             // xx(qx, iy): [qx][iy]
+    const int* __restrict__ iq = (DIR == 0) ? a.elqT + (size_t)n * D::Q2 + i * D::NP1 : a.elq + (size_t)n * D::Q2 + i * D::NP1;
+    const double* __restrict__ G = ((DIR == 0) ? a.Gc : a.Gr) + ((size_t)n * D::Q2 + i * D::NP1) * 2;
+
+    double own[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) own[j] = ldro(x + (size_t)iown[j] * ld);
+    double hs[P];
+    if (WITH_H) {
+        // h contracted across the line at abscissa i: hs[j] = sum_t E[i][t] h(t, j) (DIR 0) / h(j, t) (DIR 1)
+        const double* __restrict__ h = a.c + k;
+        const int* __restrict__ n2 = a.el2 + (size_t)n * D::N2E;
+#pragma unroll
+        for (int j = 0; j < P; j++) hs[j] = 0.0;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++)
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                const double hv = ldro(h + (size_t)n2[iy * P + ix] * ld);
+                if (DIR == 0) hs[iy] += a.E[i * P + ix] * hv;
+                else hs[ix] += a.E[i * P + iy] * hv;
+            }
+    }
+    double f[P + 1];
+#pragma unroll
+    for (int q = 0; q <= P; q++) {
+        double ua = 0.0, ub = 0.0;   // along-line interpolation of `own`, across-line interpolation of `oth`
+#pragma unroll
+        for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
+#pragma unroll
+        for (int t = 0; t < P; t++) ub += a.E[i * P + t] * ldro(x + (size_t)ioth[q * P + t] * ld);
+        double c = thick_factor(a, iq[q], k);
+        if (WITH_H) {
+            double hl = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hs[j];
+            c *= hl;
+        }
+        // DIR 0: (g0,g1) = (Gaa,Gab), ua = ul0, ub = ul1 ; DIR 1: (g1,g2) = (Gab,Gbb), ub = ul0, ua = ul1
+        f[q] = (DIR == 0) ? c * (G[q * 2 + 0] * ua + G[q * 2 + 1] * ub) : c * (G[q * 2 + 0] * ub + G[q * 2 + 1] * ua);
+    }
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
+        out[j] = s;
+    }
+}
+
+// runtime line index -> compile-time E row (the table sits in the constant bank; a runtime row
+// index would turn every operand into an indexed constant load)
+template <int P, int DIR, bool WITH_H>
+__device__ __forceinline__ void m1_line_rt(const KArgs& a, int n, int i, int k, double (&out)[P]) {
+    // i is warp-uniform; dispatch keeps the E[i][*] operands immediate
+    switch (i) {
+        case 0: m1_line<P, DIR, WITH_H>(a, n, 0, k, out); break;
+        case 1: m1_line<P, DIR, WITH_H>(a, n, 1, k, out); break;
+        case 2: if (P >= 2) m1_line<P, DIR, WITH_H>(a, n, P >= 2 ? 2 : 0, k, out); break;
+        case 3: if (P >= 3) m1_line<P, DIR, WITH_H>(a, n, P >= 3 ? 3 : 0, k, out); break;
+        case 4: if (P >= 4) m1_line<P, DIR, WITH_H>(a, n, P >= 4 ? 4 : 0, k, out); break;
+        case 5: if (P >= 5) m1_line<P, DIR, WITH_H>(a, n, P >= 5 ? 5 : 0, k, out); break;
+        default: break;
+    }
+}
+
+// grid: x over (element, level) flattened with the level fastest, y over the 2P lines
+// (y < P: x-edge columns, y >= P: y-edge rows).  FAR = true launches only the far lines (i = P) of the
+// elements flagged in partial-sum mode (a.nbr then holds the flagged element list).
+template <int P, bool WITH_H, bool FAR>
+__global__ void __launch_bounds__(128) k_apply_m1_lines(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    const size_t ld = a.ld;
+    double* __restrict__ y = a.y + k;
+    double out[P];
+    if (FAR) {
+        // a.nbr = list of (element, dir) pairs whose far line nobody else in the subdomain computes
+        const int code = a.nbr[e];
+        e = code >> 1;
+        if ((code & 1) == 0) {
+            m1_line<P, 0, WITH_H>(a, e, P, k, out);
+            const int* __restrict__ io = a.el1xT + (size_t)e * D::N1E + P * P;
+#pragma unroll
+            for (int j = 0; j < P; j++) y[(size_t)io[j] * ld] = out[j];
+        } else {
+            m1_line<P, 1, WITH_H>(a, e, P, k, out);
+            const int* __restrict__ io = a.el1y + (size_t)e * D::N1E + P * P;
+#pragma unroll
+            for (int j = 0; j < P; j++) y[(size_t)io[j] * ld] = out[j];
+        }
+        return;
+    }
+    const int line = blockIdx.y;
+    const int dir = line >= P;
+    const int i = dir ? line - P : line;
+    if (!dir) m1_line_rt<P, 0, WITH_H>(a, e, i, k, out);
+    else m1_line_rt<P, 1, WITH_H>(a, e, i, k, out);
+    if (i == 0) {
+        const int nb = a.nbr[2 * e + dir];
+        if (nb >= 0) {
+            double far[P];
+            const int n = nb & 0x1fffffff;
+            if (((nb >> 29) & 1) == 0) m1_line<P, 0, WITH_H>(a, n, P, k, far);
+            else m1_line<P, 1, WITH_H>(a, n, P, k, far);
+            const bool rev = (nb >> 30) & 1;
+#pragma unroll
+            for (int j = 0; j < P; j++) out[j] += rev ? far[P - 1 - j] : far[j];
+        }
+    }
+    const int* __restrict__ io = dir ? a.el1y + (size_t)e * D::N1E + i * P : a.el1xT + (size_t)e * D::N1E + i * P;
+#pragma unroll
+    for (int j = 0; j < P; j++) y[(size_t)io[j] * ld] = out[j];
+}
+
 // y = M2 x   (WITH_H: M2(rho) x)
 template <int P, bool WITH_H>
 __global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs a) {
     using D = ElDim<P>;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.nel * a.nlev) return;
-    const int e = (int)(idx / a.nlev);
-    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     double* __restrict__ y = a.y + k;
@@ -313,10 +454,10 @@ __global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs 
 template <int P>
 __global__ void __launch_bounds__(128) k_apply_k(const __grid_constant__ KArgs a) {
     using D = ElDim<P>;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.nel * a.nlev) return;
-    const int e = (int)(idx / a.nlev);
-    const int k = (int)(idx - (int64_t)e * a.nlev);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     const double* __restrict__ u = a.c + k;
@@ -391,10 +532,10 @@ __global__ void __launch_bounds__(128) k_apply_k(const __grid_constant__ KArgs a
 template <int P, bool WITH_H>
 __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeArgs a) {
     using D = ElDim<P>;
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)a.n0 * a.nlev) return;
-    const int n = (int)(idx / a.nlev);
-    const int k = (int)(idx - (int64_t)n * a.nlev);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
+    const int n = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)n * (unsigned)a.nlev);
     const size_t ld = a.ld;
     double f = a.scale;
     if (a.tpow > 0) {
@@ -429,10 +570,10 @@ __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeAr
 
 // y[r][k] = sum_j sgn[r][j] x[col[r][j]][k]   (entries sorted by column, as a CSR SpMV would add them)
 __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllArgs a) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (idx >= a.nrows * a.nlev) return;
-    const int64_t rr = idx / a.nlev;
-    const int k = (int)(idx - rr * a.nlev);
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nrows * (unsigned)a.nlev) return;
+    const int64_t rr = fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)rr * (unsigned)a.nlev);
     const int64_t r = a.rows ? a.rows[rr] : rr;
     double s = 0.0;
     for (int j = 0; j < a.width; j++) {
