@@ -12,6 +12,7 @@
 #include "../../include/mimsem_gpu.h"
 #include "errors.hpp"
 #include "kernels.cuh"
+#include "tma_kernels.cuh"
 
 using namespace mimsem;
 
@@ -75,7 +76,15 @@ struct mimsem_gpu_ctx {
     DevBuf<int> d_el1xT, d_elqT, d_far;      // line-task tables
     DevBuf<double> d_Gc, d_Gr, d_Gch, d_Grh;
     int n_far = 0;
-    int m1_variant = 1;                      // 1: line tasks (default), 0: one thread per element-level
+    int m1_variant = 2;                      // 2: TMA tile kernel (default), 1: line tasks, 0: one thread per element-level
+    // TMA tile plan (owner-computes mode)
+    bool tma_ok = false;
+    std::vector<TileHdr> h_hdr;
+    DevBuf<TileHdr> d_hdr, d_hdr_h;
+    DevBuf<CopyEnt> d_cps, d_cps_h;
+    DevBuf<StoreEnt> d_stores;
+    DevBuf<int> d_st_ptr;
+    DevBuf<double> d_geo, d_geo_h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
     int nkT = 0;
@@ -313,6 +322,137 @@ int build_node_adjacency(mimsem_gpu_ctx* c) {
     return MIMSEM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// TMA tile plan: per owned element, the list of bulk copies that fills the tile's slots
+// (see M1Slots in engine.cuh) and the list of bulk stores of its owned edges.
+template <int P>
+int build_tma_plan_p(mimsem_gpu_ctx* c) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1, N1E = P * NP1, N2E = P * P, Q2 = NP1 * NP1;
+    std::vector<TileHdr> hdr(c->nel_owned), hdr_h(c->nel_owned);
+    std::vector<CopyEnt> cps, cps_h;
+    std::vector<StoreEnt> stores;
+    std::vector<int> st_ptr(c->nel_owned + 1, 0);
+    auto emit_runs = [](std::vector<std::pair<int, int>>& dof_slot, int kind, std::vector<CopyEnt>& out) {
+        // merge (dof, slot) pairs that advance together into runs
+        size_t i = 0;
+        int filled = 0;
+        while (i < dof_slot.size()) {
+            size_t j = i + 1;
+            while (j < dof_slot.size() && dof_slot[j].first == dof_slot[j - 1].first + 1 && dof_slot[j].second == dof_slot[j - 1].second + 1) j++;
+            out.push_back(CopyEnt{kind, dof_slot[i].first, dof_slot[i].second, (int)(j - i)});
+            filled += (int)(j - i);
+            i = j;
+        }
+        return filled;
+    };
+    for (int e = 0; e < c->nel_owned; e++) {
+        const int* ex = &c->h_el1x[(size_t)e * N1E];
+        const int* ey = &c->h_el1y[(size_t)e * N1E];
+        std::vector<std::pair<int, int>> xs, ts, hs;
+        // own block, in slot order
+        for (int iy = 0; iy < P; iy++)
+            for (int ix = 0; ix < P; ix++) {
+                xs.push_back({ex[iy * NP1 + ix], 2 * (iy * P + ix)});
+                xs.push_back({ey[iy * P + ix], 2 * (iy * P + ix) + 1});
+            }
+        for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + P], S::XE + iy});
+        for (int ix = 0; ix < P; ix++) xs.push_back({ey[P * P + ix], S::YN + ix});
+        int flags = 0;
+        int nbr_el[2] = {-1, -1};
+        for (int s = 0; s < 2; s++) {
+            const int nb = c->h_nbr[(size_t)e * 2 + s];
+            if (nb < 0) continue;
+            const int n = nb & 0x1fffffff, side = (nb >> 29) & 1, rev = (nb >> 30) & 1;
+            nbr_el[s] = n;
+            flags |= (s == 0 ? 1 : 4) | (rev ? (s == 0 ? 2 : 8) : 0) | (side ? (s == 0 ? 16 : 32) : 0);
+            const int OTH = s == 0 ? S::WOTH : S::SOTH;
+            for (int q = 0; q <= P; q++)
+                for (int t = 0; t < P; t++) {
+                    // far line = east column (side 0): other family = y-edges xy(ix=t, qy=q)
+                    // far line = north row  (side 1): other family = x-edges xx(qx=q, iy=t)
+                    const int dof = side == 0 ? c->h_el1y[(size_t)n * N1E + q * P + t] : c->h_el1x[(size_t)n * N1E + t * NP1 + q];
+                    xs.push_back({dof, OTH + q * P + t});
+                }
+        }
+        for (int q = 0; q < Q2; q++) ts.push_back({c->h_elq[(size_t)e * Q2 + q], S::T + q});
+        for (int j = 0; j < N2E; j++) hs.push_back({c->h_el2[(size_t)e * N2E + j], S::H + j});
+        for (int s = 0; s < 2; s++)
+            if (nbr_el[s] >= 0)
+                for (int j = 0; j < N2E; j++) hs.push_back({c->h_el2[(size_t)nbr_el[s] * N2E + j], (s == 0 ? S::HW : S::HS) + j});
+        // plain M1
+        TileHdr h;
+        h.cp_begin = (int)cps.size();
+        h.flags = flags;
+        cps.push_back(CopyEnt{3, e, 0, 1});
+        const int nx = emit_runs(xs, 0, cps);
+        const int nt = emit_runs(ts, 2, cps);
+        h.cp_count = (int)cps.size() - h.cp_begin;
+        h.nslots = nx | (nt << 16);
+        hdr[e] = h;
+        // M1(h)
+        h.cp_begin = (int)cps_h.size();
+        cps_h.push_back(CopyEnt{3, e, 0, 1});
+        emit_runs(xs, 0, cps_h);
+        const int nh = emit_runs(hs, 1, cps_h);
+        emit_runs(ts, 2, cps_h);
+        h.cp_count = (int)cps_h.size() - h.cp_begin;
+        h.nslots = (nx + nh) | (nt << 16);
+        hdr_h[e] = h;
+        // stores: owned block
+        std::vector<std::pair<int, int>> os;
+        for (int iy = 0; iy < P; iy++)
+            for (int ix = 0; ix < P; ix++) {
+                os.push_back({ex[iy * NP1 + ix], 2 * (iy * P + ix)});
+                os.push_back({ey[iy * P + ix], 2 * (iy * P + ix) + 1});
+            }
+        size_t i = 0;
+        while (i < os.size()) {
+            size_t j = i + 1;
+            while (j < os.size() && os[j].first == os[j - 1].first + 1 && os[j].second == os[j - 1].second + 1) j++;
+            stores.push_back(StoreEnt{os[i].second, os[i].first, (int)(j - i), 0});
+            i = j;
+        }
+        st_ptr[e + 1] = (int)stores.size();
+    }
+    c->h_hdr = hdr;
+    CUDA_OK(c->d_hdr.upload(hdr));
+    CUDA_OK(c->d_hdr_h.upload(hdr_h));
+    CUDA_OK(c->d_cps.upload(cps));
+    CUDA_OK(c->d_cps_h.upload(cps_h));
+    CUDA_OK(c->d_stores.upload(stores));
+    CUDA_OK(c->d_st_ptr.upload(st_ptr));
+    c->tma_ok = true;
+    return MIMSEM_OK;
+}
+
+// geometry records of the tile kernels: G[q][3], then the (c_own, c_oth) pairs of the west and south far lines
+template <int P>
+int build_tma_geo_p(mimsem_gpu_ctx* c, const std::vector<double>& G, DevBuf<double>& out) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1, Q2 = NP1 * NP1;
+    std::vector<double> geo((size_t)c->nel_owned * S::GEO, 0.0);
+    for (int e = 0; e < c->nel_owned; e++) {
+        double* g = &geo[(size_t)e * S::GEO];
+        for (int i = 0; i < Q2 * 3; i++) g[i] = G[(size_t)e * Q2 * 3 + i];
+        for (int s = 0; s < 2; s++) {
+            const int nb = c->h_nbr[(size_t)e * 2 + s];
+            if (nb < 0) continue;
+            const int n = nb & 0x1fffffff, side = (nb >> 29) & 1;
+            double* gf = g + (s == 0 ? S::GW : S::GS);
+            for (int q = 0; q <= P; q++) {
+                const size_t pt = (size_t)n * Q2 + (side == 0 ? q * NP1 + P : P * NP1 + q);
+                // east column: f = c (Gaa u_own + Gab u_oth) ; north row: f = c (Gbb u_own + Gab u_oth)
+                gf[q * 2 + 0] = side == 0 ? G[pt * 3 + 0] : G[pt * 3 + 2];
+                gf[q * 2 + 1] = G[pt * 3 + 1];
+            }
+        }
+    }
+    CUDA_OK(out.upload(geo));
+    return MIMSEM_OK;
+}
+
 template <class Args>
 void copy_basis(const mimsem_gpu_ctx* c, Args& a) {
     std::memset(a.E, 0, sizeof(a.E));
@@ -391,6 +531,35 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
+    // TMA tile kernel: needs 16-byte aligned, even-length level runs and one thread per level
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
+    const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
+    if (c->m1_variant == 2 && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
+        TArgs t;
+        t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
+        t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
+        t.scale = scale;
+        t.hdr = with_h ? c->d_hdr_h.p : c->d_hdr.p;
+        t.cps = with_h ? c->d_cps_h.p : c->d_cps.p;
+        t.st_ptr = c->d_st_ptr.p;
+        t.stores = c->d_stores.p;
+        t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;
+        t.x = x; t.c = h2; t.tinv = c->d_tinv.p; t.y = y;
+        copy_basis(c, t);
+        int rc3 = dispatch_p(c->p, [&](auto P) {
+            constexpr int p = decltype(P)::value;
+            using S = M1Slots<p>;
+            t.geo_doubles = S::GEO;
+            const size_t smem = 16 + ((size_t)S::GEO + (size_t)(with_h ? S::NS_H : S::NS) * nlev) * sizeof(double);
+            if (smem > 227 * 1024) return 1;   // fall through to the register kernels
+            auto kern = with_h ? k_apply_m1_tma<p, true> : k_apply_m1_tma<p, false>;
+            cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+            kern<<<c->nel_owned, nlev <= 32 ? 32 : 64, smem, st>>>(t);
+            return finish_launch(c, "apply_M1 (tma)");
+        });
+        if (rc3 != 1) return rc3;
+    }
     if (c->m1_variant == 0) {
         return dispatch_p(c->p, [&](auto P) {
             constexpr int p = decltype(P)::value;
@@ -637,6 +806,17 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         const char* v = getenv("MIMSEM_M1_VARIANT");
         if (v) c->m1_variant = atoi(v);
     }
+    c->tma_ok = false;
+    if (mode == 0) {
+        switch (P) {
+            case 2: rc = build_tma_plan_p<2>(c); break;
+            case 3: rc = build_tma_plan_p<3>(c); break;
+            case 4: rc = build_tma_plan_p<4>(c); break;
+            case 5: rc = build_tma_plan_p<5>(c); break;
+            default: rc = MIMSEM_OK;
+        }
+        if (rc) return rc;
+    }
     CUDA_OK(c->d_el0.upload(c->h_el0));
     CUDA_OK(c->d_el1x.upload(c->h_el1x));
     CUDA_OK(c->d_el1y.upload(c->h_el1y));
@@ -693,6 +873,15 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
         CUDA_OK(c->d_Gr.upload(Gr));
         CUDA_OK(c->d_Gch.upload(Gch));
         CUDA_OK(c->d_Grh.upload(Grh));
+    }
+    if (c->tma_ok) {
+        switch (c->p) {
+            case 2: rc = build_tma_geo_p<2>(c, G1, c->d_geo); if (!rc) rc = build_tma_geo_p<2>(c, G1h, c->d_geo_h); break;
+            case 3: rc = build_tma_geo_p<3>(c, G1, c->d_geo); if (!rc) rc = build_tma_geo_p<3>(c, G1h, c->d_geo_h); break;
+            case 4: rc = build_tma_geo_p<4>(c, G1, c->d_geo); if (!rc) rc = build_tma_geo_p<4>(c, G1h, c->d_geo_h); break;
+            case 5: rc = build_tma_geo_p<5>(c, G1, c->d_geo); if (!rc) rc = build_tma_geo_p<5>(c, G1h, c->d_geo_h); break;
+        }
+        if (rc) return rc;
     }
     CUDA_OK(c->d_G1.upload(G1));
     CUDA_OK(c->d_G1h.upload(G1h));

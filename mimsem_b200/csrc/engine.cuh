@@ -96,3 +96,76 @@ struct NodeArgs {
 };
 
 }  // namespace mimsem
+
+namespace mimsem {
+
+// ---------------------------------------------------------------------------------------------
+// TMA tile kernels: one CTA per element, all levels; every operand of the element-level
+// contraction is staged in shared memory by 1-D bulk async copies (cp.async.bulk, the TMA unit),
+// issued from a per-element copy list that the host builds once at set_topo.  All topology
+// irregularity (cubed-sphere seams, reversed sides, ghost elements) lives in that list; the
+// kernel itself addresses shared memory with compile-time slot numbers.
+//
+// Slot s of the tile holds nlev consecutive doubles (one value per level).  Slot map for M1:
+//   [0, 2P^2)            own edges in block order: x-edge (ix<P,iy) -> 2(iy P+ix), y-edge (ix,iy<P) -> 2(iy P+ix)+1
+//   XE  + iy             east column of x-edges xx(P,iy)            (owned by the east neighbour)
+//   YN  + ix             north row of y-edges   xy(ix,P)            (owned by the north neighbour)
+//   WOTH + q P + t       the west neighbour's other-family edges along its far line
+//   SOTH + q P + t       the south neighbour's other-family edges along its far line
+//   T + qy (P+1) + qx    inverse layer thickness at the element's quadrature points
+//   H, HW, HS (+P^2 each) 2-form coefficient of the element / west / south neighbour (M1h only)
+template <int P>
+struct M1Slots {
+    static constexpr int OWN = 0;
+    static constexpr int XE = 2 * P * P;
+    static constexpr int YN = XE + P;
+    static constexpr int WOTH = YN + P;
+    static constexpr int SOTH = WOTH + (P + 1) * P;
+    static constexpr int T = SOTH + (P + 1) * P;
+    static constexpr int NS = T + (P + 1) * (P + 1);
+    static constexpr int H = NS;
+    static constexpr int HW = H + P * P;
+    static constexpr int HS = HW + P * P;
+    static constexpr int NS_H = HS + P * P;
+    // geometry record (doubles): G[q][3], then (c_own, c_oth)[q] for the west and the south far line
+    static constexpr int GW = (P + 1) * (P + 1) * 3;
+    static constexpr int GS = GW + 2 * (P + 1);
+    static constexpr int GEO = ((GS + 2 * (P + 1)) + 1) / 2 * 2;
+};
+
+struct CopyEnt {      // 16 bytes
+    int kind;         // 0 x field, 1 coefficient field, 2 inverse thickness, 3 geometry record
+    int src;          // first DOF / quadrature point / element
+    int slot;         // first destination slot (kind 3: ignored)
+    int count;        // consecutive DOFs -> consecutive slots
+};
+
+struct TileHdr {      // 16 bytes
+    int cp_begin, cp_count;
+    int flags;        // bit0 has west nbr, bit1 west reversed, bit2 has south nbr, bit3 south reversed
+    int nslots;       // slots filled by the list (for the mbarrier transaction count)
+};
+
+struct StoreEnt {     // 16 bytes
+    int slot, dof, count, pad;
+};
+
+struct TArgs {
+    int nlev, ld, lev0, nkT, tpow;
+    int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
+    int contig_t;     // nkT == nlev
+    int geo_doubles;
+    double scale;
+    const TileHdr* hdr;
+    const CopyEnt* cps;
+    const int* st_ptr;        // [nel+1]
+    const StoreEnt* stores;
+    const double* geo;
+    const double* x;
+    const double* c;
+    const double* tinv;
+    double* y;
+    double E[(kMaxP + 1) * kMaxP];
+};
+
+}  // namespace mimsem

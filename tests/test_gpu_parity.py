@@ -45,7 +45,9 @@ def test_eul_operators_vs_reference_golden(fname, p, ne):
         y = _apply(eng, op, g[xk], coeff, scale=s, tpow=tpow)
         assert rel_l2(y, g[yk]) < TOL, (op, tpow, rel_l2(y, g[yk]))
         y1 = _apply_per_level(eng, op, g[xk], coeff, scale=s, tpow=tpow)
-        assert np.array_equal(y1, y), op   # batching over levels does not change a single bit
+        # one launch over all levels vs one launch per level (the MatShell pattern); the batched launch may take the
+        # TMA tile kernel and the single-column launch the register kernel: same arithmetic, different summation order
+        assert rel_l2(y1, y) < 1e-14, op
     assert eng.launch_count > 0
 
 
@@ -206,3 +208,23 @@ def test_error_paths():
         eng.apply("M1h", x)                 # missing coefficient
     with pytest.raises(mb.MimsemError):
         eng.apply("M1", x[:10].contiguous())
+
+
+@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40)])
+def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
+    """The TMA tile kernel (default), the line-task kernel and the thread-per-element kernel compute the
+    same M1 / M1(h) (identical up to FP summation order)."""
+    mesh = mb.Mesh(kind, p, ne)
+    thick = synthetic_thickness(mesh.xyz, nk, kind)
+    rng = np.random.default_rng(11)
+    f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+    res = {}
+    for variant in ("0", "1", "2"):
+        monkeypatch.setenv("MIMSEM_M1_VARIANT", variant)
+        eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
+        res[variant] = (_apply(eng, "M1", f["x1"], scale=1e8, tpow=1), _apply(eng, "M1h", f["x1"], f["h2"], scale=1e8, tpow=2),
+                        _apply(eng, "M1", f["x1"], scale=1.0, tpow=0))
+        eng.close()
+    for v in ("1", "2"):
+        for a, b in zip(res[v], res["0"]):
+            assert rel_l2(a, b) < 1e-14, (v, rel_l2(a, b))
