@@ -12,8 +12,9 @@
  *   mimsem_gpu_*                                     device engine (sm_100a CUDA)
  *
  * Device field layout ("column layout"): a k-level field over n degrees of freedom is the array
- *   f[dof * ld + k],   k = 0..nlev-1,   ld >= nlev,
- * i.e. DOF-major with the vertical level fastest.  The reference keeps one PETSc Vec per level
+ *   f[row(dof) * ld + k],   k = 0..nlev-1,   ld >= nlev,
+ * i.e. DOF-major with the vertical level fastest; row() is the identity for 0- and 2-forms and the
+ * engine's element-blocked edge order for 1-forms (mimsem_gpu_form_permutation).  The reference keeps one PETSc Vec per level
  * (`Vec velx[NK]`, eul/UMJS14.cpp:302-316); mimsem_gpu_levels_to_columns / _columns_to_levels
  * convert on the device.  A single-level apply (the MatShell adaptor) uses ld = 1.
  *
@@ -112,9 +113,16 @@ int mimsem_gpu_set_thickness(mimsem_gpu_ctx* ctx, int nk, const double* h_thick)
 /* out = {nel_total, nel_owned, n0, n1, n2, nq, nk, p, m} */
 int mimsem_gpu_sizes(const mimsem_gpu_ctx* ctx, int64_t out[9]);
 
-/* Layout helpers (device pointers): levels[k*n + dof]  <->  columns[dof*ld + k] */
-int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* ctx, int64_t n, int nlev, int ld, const double* d_levels, double* d_columns, void* stream);
-int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* ctx, int64_t n, int nlev, int ld, const double* d_columns, double* d_levels, void* stream);
+/* Layout conversion (device pointers) between the reference's per-level vectors in the caller's DOF
+ * numbering, levels[k*n + dof], and the engine's column layout columns[perm_space[dof]*ld + k].
+ * space = k of the k-form space (0 nodes, 1 edges, 2 faces); -1 = plain transpose without renumbering.
+ * 1-forms are stored element-blocked with x- and y-normal edges separated ("data layout in
+ * HBM"): every apply below expects and produces fields in this internal order. */
+int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* ctx, int space, int64_t n, int nlev, int ld, const double* d_levels, double* d_columns, void* stream);
+int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* ctx, int space, int64_t n, int nlev, int ld, const double* d_columns, double* d_levels, void* stream);
+/* perm[dof] = row of `dof` (caller numbering) in the engine's column layout, for callers that fill device
+ * fields themselves (host output, n_space ints). */
+int mimsem_gpu_form_permutation(const mimsem_gpu_ctx* ctx, int space, int* perm);
 
 /*
  * Operator applications.  All field pointers are DEVICE pointers in column layout with leading

@@ -67,7 +67,9 @@ struct mimsem_gpu_ctx {
     std::vector<double> w, ejxi;   // w[m+1], ejxi[(m+1)*p]
 
     int nel_total = 0, nel_owned = 0, n0 = 0, n1 = 0, n2 = 0, nq = 0, mode = 0;
-    std::vector<int> h_el0, h_el1x, h_el1y, h_el2, h_elq;
+    std::vector<int> h_el0, h_el1x, h_el1y, h_el2, h_elq;   // 1-form tables hold INTERNAL indices (perm1 applied)
+    std::vector<int> h_perm1;                                // external (caller) 1-form index -> internal
+    DevBuf<int> d_perm1;
     std::vector<int> h_nbr;
     std::vector<unsigned char> h_eflags;
     std::vector<int> h_adj_ptr, h_adj_eq, h_node_q;
@@ -227,17 +229,22 @@ void csr_from_triplets(int64_t nrows, int64_t ncols, std::vector<std::array<int6
     for (int64_t r = 0; r < nrows; r++) out.indptr[r + 1] += out.indptr[r];
 }
 
-int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows) {
+int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows, const std::vector<int>* rowperm,
+               const std::vector<int>* colperm) {
     int width = 0;
     for (int64_t r = 0; r < m.nrows; r++) width = std::max<int>(width, (int)(m.indptr[r + 1] - m.indptr[r]));
     width = std::max(width, 1);
     std::vector<int> col((size_t)m.nrows * width, -1);
     std::vector<signed char> sgn((size_t)m.nrows * width, 0);
-    for (int64_t r = 0; r < m.nrows; r++)
+    // entries keep the external column order (the order a CSR MatMult adds them in); only the storage
+    // positions move to the engine's internal numbering
+    for (int64_t r = 0; r < m.nrows; r++) {
+        const size_t ri = rowperm ? (size_t)(*rowperm)[r] : (size_t)r;
         for (int64_t k = m.indptr[r]; k < m.indptr[r + 1]; k++) {
-            col[(size_t)r * width + (k - m.indptr[r])] = m.indices[k];
-            sgn[(size_t)r * width + (k - m.indptr[r])] = m.values[k] > 0 ? 1 : -1;
+            col[ri * width + (k - m.indptr[r])] = colperm ? (*colperm)[m.indices[k]] : m.indices[k];
+            sgn[ri * width + (k - m.indptr[r])] = m.values[k] > 0 ? 1 : -1;
         }
+    }
     d.nrows = m.nrows;
     d.width = width;
     CUDA_OK(d.col.upload(col));
@@ -245,7 +252,11 @@ int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows) {
     if (rows) {
         d.use_rows = true;
         d.nrows_active = (int64_t)rows->size();
-        CUDA_OK(d.rows.upload(*rows));
+        std::vector<int> rr(*rows);
+        if (rowperm)
+            for (auto& v : rr) v = (*rowperm)[v];
+        std::sort(rr.begin(), rr.end());
+        CUDA_OK(d.rows.upload(rr));
     } else {
         d.use_rows = false;
         d.nrows_active = m.nrows;
@@ -296,10 +307,11 @@ int build_incidence(mimsem_gpu_ctx* c) {
     std::sort(rows21.begin(), rows21.end());
     const bool all = (c->nel_owned == c->nel_total);
     int rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E10], c->ell[MIMSEM_E10], all ? nullptr : &rows10))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E21], c->ell[MIMSEM_E21], all ? nullptr : &rows21))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E01], c->ell[MIMSEM_E01], nullptr))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E12], c->ell[MIMSEM_E12], nullptr))) return rc;
+    const std::vector<int>* pm = &c->h_perm1;
+    if ((rc = upload_ell(c->csr[MIMSEM_E10], c->ell[MIMSEM_E10], all ? nullptr : &rows10, pm, nullptr))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E21], c->ell[MIMSEM_E21], all ? nullptr : &rows21, nullptr, pm))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E01], c->ell[MIMSEM_E01], nullptr, nullptr, pm))) return rc;
+    if ((rc = upload_ell(c->csr[MIMSEM_E12], c->ell[MIMSEM_E12], nullptr, pm, nullptr))) return rc;
     return MIMSEM_OK;
 }
 
@@ -352,11 +364,10 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         const int* ey = &c->h_el1y[(size_t)e * N1E];
         std::vector<std::pair<int, int>> xs, ts, hs;
         // own block, in slot order
+        for (int ix = 0; ix < P; ix++)
+            for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + ix], S::OX + ix * P + iy});
         for (int iy = 0; iy < P; iy++)
-            for (int ix = 0; ix < P; ix++) {
-                xs.push_back({ex[iy * NP1 + ix], 2 * (iy * P + ix)});
-                xs.push_back({ey[iy * P + ix], 2 * (iy * P + ix) + 1});
-            }
+            for (int ix = 0; ix < P; ix++) xs.push_back({ey[iy * P + ix], S::OY + iy * P + ix});
         for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + P], S::XE + iy});
         for (int ix = 0; ix < P; ix++) xs.push_back({ey[P * P + ix], S::YN + ix});
         int flags = 0;
@@ -402,11 +413,10 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         hdr_h[e] = h;
         // stores: owned block
         std::vector<std::pair<int, int>> os;
+        for (int ix = 0; ix < P; ix++)
+            for (int iy = 0; iy < P; iy++) os.push_back({ex[iy * NP1 + ix], S::OX + ix * P + iy});
         for (int iy = 0; iy < P; iy++)
-            for (int ix = 0; ix < P; ix++) {
-                os.push_back({ex[iy * NP1 + ix], 2 * (iy * P + ix)});
-                os.push_back({ey[iy * P + ix], 2 * (iy * P + ix) + 1});
-            }
+            for (int ix = 0; ix < P; ix++) os.push_back({ey[iy * P + ix], S::OY + iy * P + ix});
         size_t i = 0;
         while (i < os.size()) {
             size_t j = i + 1;
@@ -693,14 +703,24 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     return finish_launch(c, "apply_incidence");
 }
 
-int transpose(mimsem_gpu_ctx* c, bool to_columns, int64_t n, int nlev, int ld, const double* in, double* out, cudaStream_t st) {
+int transpose(mimsem_gpu_ctx* c, bool to_columns, int space, int64_t n, int nlev, int ld, const double* in, double* out,
+              cudaStream_t st) {
     if (!c) return fail(MIMSEM_ERR_ARG, "null context");
     if (n < 1 || nlev < 1 || ld < nlev) return fail(MIMSEM_ERR_ARG, "bad transpose shape");
+    const int* perm = nullptr;
+    if (space == 1) {
+        if (!c->have_topo || n != c->n1) return fail(MIMSEM_ERR_ARG, "1-form layout conversion needs n == n1 after set_topo");
+        perm = c->d_perm1.p;
+    } else if (space == 0 || space == 2) {
+        if (c->have_topo && n != (space == 0 ? c->n0 : c->n2)) return fail(MIMSEM_ERR_ARG, "field length does not match the space");
+    } else if (space != -1) {
+        return fail(MIMSEM_ERR_ARG, "space must be 0, 1, 2 (k-forms) or -1 (no renumbering)");
+    }
     int rc = bind_device(c);
     if (rc) return rc;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nlev + 31) / 32));
-    if (to_columns) k_transpose<true><<<grid, 256, 0, st>>>(n, nlev, ld, in, out);
-    else k_transpose<false><<<grid, 256, 0, st>>>(n, nlev, ld, in, out);
+    if (to_columns) k_transpose<true><<<grid, 256, 0, st>>>(n, nlev, ld, perm, in, out);
+    else k_transpose<false><<<grid, 256, 0, st>>>(n, nlev, ld, perm, in, out);
     return finish_launch(c, "transpose");
 }
 
@@ -782,9 +802,40 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         if (v < 0 || v >= n2) return fail(MIMSEM_ERR_ARG, "set_topo: face index out of range");
     for (int v : c->h_elq)
         if (v < 0 || v >= nq) return fail(MIMSEM_ERR_ARG, "set_topo: quadrature-point index out of range");
+    for (int v : c->h_el1x)
+        if (v < 0 || v >= n1) return fail(MIMSEM_ERR_ARG, "set_topo: edge index out of range");
+    for (int v : c->h_el1y)
+        if (v < 0 || v >= n1) return fail(MIMSEM_ERR_ARG, "set_topo: edge index out of range");
+    {
+        // Internal 1-form numbering: element-blocked in local element order, each block = the element's
+        // west/interior x-edges column-major, then its south/interior y-edges row-major.  With it an
+        // element's own edges, a neighbour's west column, south row or whole edge family are each ONE
+        // contiguous run of memory, i.e. one TMA bulk copy.  (The reference's own numbering is
+        // element-blocked too, but interleaves x and y edges, scr/Proc2.py:105-123.)
+        const int N1E = P * NP1;
+        c->h_perm1.assign(n1, -1);
+        int next = 0;
+        for (int e = 0; e < nel_total; e++) {
+            for (int ix = 0; ix < P; ix++)
+                for (int iy = 0; iy < P; iy++) {
+                    int& d = c->h_perm1[c->h_el1x[(size_t)e * N1E + iy * NP1 + ix]];
+                    if (d < 0) d = next++;
+                }
+            for (int iy = 0; iy < P; iy++)
+                for (int ix = 0; ix < P; ix++) {
+                    int& d = c->h_perm1[c->h_el1y[(size_t)e * N1E + iy * P + ix]];
+                    if (d < 0) d = next++;
+                }
+        }
+        for (int i = 0; i < n1; i++)
+            if (c->h_perm1[i] < 0) c->h_perm1[i] = next++;
+        CUDA_OK(c->d_perm1.upload(c->h_perm1));
+    }
+    if ((rc = build_incidence(c))) return rc;   // external numbering (exported CSR), device stencils permuted
+    for (auto& v : c->h_el1x) v = c->h_perm1[v];
+    for (auto& v : c->h_el1y) v = c->h_perm1[v];
     if ((rc = build_neighbours(c))) return rc;
     if ((rc = build_node_adjacency(c))) return rc;
-    if ((rc = build_incidence(c))) return rc;
     {
         // column-major copies so that every GLL line of an element is contiguous (line-task kernels)
         const int N1E = P * NP1, Q2 = NP1 * NP1;
@@ -918,11 +969,25 @@ int mimsem_gpu_sizes(const mimsem_gpu_ctx* c, int64_t out[9]) {
     return MIMSEM_OK;
 }
 
-int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* c, int64_t n, int nlev, int ld, const double* in, double* out, void* stream) {
-    return transpose(c, true, n, nlev, ld, in, out, (cudaStream_t)stream);
+int mimsem_gpu_levels_to_columns(mimsem_gpu_ctx* c, int space, int64_t n, int nlev, int ld, const double* in, double* out,
+                                 void* stream) {
+    return transpose(c, true, space, n, nlev, ld, in, out, (cudaStream_t)stream);
 }
-int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* c, int64_t n, int nlev, int ld, const double* in, double* out, void* stream) {
-    return transpose(c, false, n, nlev, ld, in, out, (cudaStream_t)stream);
+int mimsem_gpu_columns_to_levels(mimsem_gpu_ctx* c, int space, int64_t n, int nlev, int ld, const double* in, double* out,
+                                 void* stream) {
+    return transpose(c, false, space, n, nlev, ld, in, out, (cudaStream_t)stream);
+}
+int mimsem_gpu_form_permutation(const mimsem_gpu_ctx* c, int space, int* perm) {
+    if (!c || !perm || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    if (space == 1) {
+        std::copy(c->h_perm1.begin(), c->h_perm1.end(), perm);
+    } else if (space == 0 || space == 2) {
+        const int n = space == 0 ? c->n0 : c->n2;
+        for (int i = 0; i < n; i++) perm[i] = i;
+    } else {
+        return fail(MIMSEM_ERR_ARG, "space must be 0, 1 or 2");
+    }
+    return MIMSEM_OK;
 }
 
 int mimsem_gpu_apply_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
@@ -983,18 +1048,23 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     int rc = bind_device(c);
     if (rc) return rc;
     // input / output / coefficient spaces
-    int64_t nin, nout, ncoef = 0;
+    int sin, sout, scoef = -1;   // k of the k-form spaces
     switch (op) {
-        case 0: case 3: nin = nout = c->n1; if (op == 3) ncoef = c->n2; break;
-        case 1: case 5: nin = nout = c->n2; if (op == 5) ncoef = c->n2; break;
-        case 2: case 6: nin = nout = c->n0; if (op == 6) ncoef = c->n2; break;
-        case 4: nin = c->n1; nout = c->n2; ncoef = c->n1; break;
-        case 10 + MIMSEM_E10: nin = c->n0; nout = c->n1; break;
-        case 10 + MIMSEM_E01: nin = c->n1; nout = c->n0; break;
-        case 10 + MIMSEM_E21: nin = c->n1; nout = c->n2; break;
-        case 10 + MIMSEM_E12: nin = c->n2; nout = c->n1; break;
+        case 0: sin = sout = 1; break;
+        case 3: sin = sout = 1; scoef = 2; break;
+        case 1: sin = sout = 2; break;
+        case 5: sin = sout = 2; scoef = 2; break;
+        case 2: sin = sout = 0; break;
+        case 6: sin = sout = 0; scoef = 2; break;
+        case 4: sin = 1; sout = 2; scoef = 1; break;
+        case 10 + MIMSEM_E10: sin = 0; sout = 1; break;
+        case 10 + MIMSEM_E01: sin = 1; sout = 0; break;
+        case 10 + MIMSEM_E21: sin = 1; sout = 2; break;
+        case 10 + MIMSEM_E12: sin = 2; sout = 1; break;
         default: return fail(MIMSEM_ERR_ARG, "unknown operator id");
     }
+    const int64_t nsp[3] = {c->n0, c->n1, c->n2};
+    const int64_t nin = nsp[sin], nout = nsp[sout], ncoef = scoef >= 0 ? nsp[scoef] : 0;
     if (ncoef && !h_coeff) return fail(MIMSEM_ERR_ARG, "this operator needs a coefficient field");
     const int ld = nlev;
     const size_t big = (size_t)std::max(std::max(nin, nout), ncoef) * nlev;
@@ -1005,10 +1075,10 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     cudaStream_t st = c->stream;
     if (ncoef) {
         CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_coeff, (size_t)ncoef * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
-        if ((rc = transpose(c, true, ncoef, nlev, ld, c->s_lev.p, c->s_c.p, st))) return rc;
+        if ((rc = transpose(c, true, scoef, ncoef, nlev, ld, c->s_lev.p, c->s_c.p, st))) return rc;
     }
     CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_x, (size_t)nin * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
-    if ((rc = transpose(c, true, nin, nlev, ld, c->s_lev.p, c->s_x.p, st))) return rc;
+    if ((rc = transpose(c, true, sin, nin, nlev, ld, c->s_lev.p, c->s_x.p, st))) return rc;
     // rows the operator does not write (halo rows in owner-computes mode) stay zero
     CUDA_OK(cudaMemsetAsync(c->s_y.p, 0, (size_t)nout * nlev * sizeof(double), st));
     switch (op) {
@@ -1022,7 +1092,7 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
         default: rc = apply_inc(c, op - 10, nlev, ld, c->s_x.p, c->s_y.p, st); break;
     }
     if (rc) return rc;
-    if ((rc = transpose(c, false, nout, nlev, ld, c->s_y.p, c->s_lev.p, st))) return rc;
+    if ((rc = transpose(c, false, sout, nout, nlev, ld, c->s_y.p, c->s_lev.p, st))) return rc;
     CUDA_OK(cudaMemcpyAsync(h_y, c->s_lev.p, (size_t)nout * nlev * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
     return MIMSEM_OK;

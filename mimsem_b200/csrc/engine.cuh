@@ -107,7 +107,9 @@ namespace mimsem {
 // kernel itself addresses shared memory with compile-time slot numbers.
 //
 // Slot s of the tile holds nlev consecutive doubles (one value per level).  Slot map for M1:
-//   [0, 2P^2)            own edges in block order: x-edge (ix<P,iy) -> 2(iy P+ix), y-edge (ix,iy<P) -> 2(iy P+ix)+1
+//   [0, 2P^2)            own edges in the engine's internal block order (== memory order, so the block is ONE
+//                        bulk copy): x-edge (ix<P,iy) -> OX + ix P + iy (column-major: the west column is
+//                        contiguous), y-edge (ix,iy<P) -> OY + iy P + ix (row-major: the south row is contiguous)
 //   XE  + iy             east column of x-edges xx(P,iy)            (owned by the east neighbour)
 //   YN  + ix             north row of y-edges   xy(ix,P)            (owned by the north neighbour)
 //   WOTH + q P + t       the west neighbour's other-family edges along its far line
@@ -116,7 +118,8 @@ namespace mimsem {
 //   H, HW, HS (+P^2 each) 2-form coefficient of the element / west / south neighbour (M1h only)
 template <int P>
 struct M1Slots {
-    static constexpr int OWN = 0;
+    static constexpr int OX = 0;
+    static constexpr int OY = P * P;
     static constexpr int XE = 2 * P * P;
     static constexpr int YN = XE + P;
     static constexpr int WOTH = YN + P;

@@ -585,10 +585,11 @@ __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllAr
     a.y[(size_t)r * a.ld + k] = s;
 }
 
-// levels[k*n + dof] <-> columns[dof*ld + k] through a padded shared-memory tile
+// levels[k*n + dof] <-> columns[perm[dof]*ld + k] through a padded shared-memory tile
+// (perm = the engine's internal numbering of the space, nullptr = identity)
 template <bool TO_COLUMNS>
-__global__ void __launch_bounds__(256) k_transpose(int64_t n, int nlev, int ld, const double* __restrict__ in,
-                                                   double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_transpose(int64_t n, int nlev, int ld, const int* __restrict__ perm,
+                                                   const double* __restrict__ in, double* __restrict__ out) {
     __shared__ double tile[32][33];
     const int64_t d0 = (int64_t)blockIdx.x * 32;
     const int k0 = blockIdx.y * 32;
@@ -603,13 +604,13 @@ __global__ void __launch_bounds__(256) k_transpose(int64_t n, int nlev, int ld, 
         for (int j = ty; j < 32; j += 8) {
             const int64_t d = d0 + j;
             const int k = k0 + tx;
-            if (k < nlev && d < n) out[(size_t)d * ld + k] = tile[tx][j];
+            if (k < nlev && d < n) out[(size_t)(perm ? perm[d] : d) * ld + k] = tile[tx][j];
         }
     } else {
         for (int j = ty; j < 32; j += 8) {
             const int64_t d = d0 + j;
             const int k = k0 + tx;
-            if (k < nlev && d < n) tile[j][tx] = in[(size_t)d * ld + k];
+            if (k < nlev && d < n) tile[j][tx] = in[(size_t)(perm ? perm[d] : d) * ld + k];
         }
         __syncthreads();
         for (int j = ty; j < 32; j += 8) {

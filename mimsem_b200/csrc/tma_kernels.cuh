@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
 #pragma unroll
             for (int j = 0; j < P; j++) {
                 const int mine = rev ? P - 1 - j : j;   // my iy (west) / ix (south)
-                // west: xx(0, iy) -> slot 2(iy P + 0) ; south: xy(ix, 0) -> slot 2 ix + 1
-                own[j] = rev ? (side == 0 ? SLOT(2 * ((P - 1 - j) * P)) : SLOT(2 * (P - 1 - j) + 1))
-                             : (side == 0 ? SLOT(2 * (j * P)) : SLOT(2 * j + 1));
+                // west: xx(0, iy) -> slot OX + iy ; south: xy(ix, 0) -> slot OY + ix
+                own[j] = rev ? (side == 0 ? SLOT(S::OX + (P - 1 - j)) : SLOT(S::OY + (P - 1 - j)))
+                             : (side == 0 ? SLOT(S::OX + j) : SLOT(S::OY + j));
                 (void)mine;
             }
             double hs[P];
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
 #pragma unroll
         for (int iy = 0; iy <= P; iy++)
 #pragma unroll
-            for (int ix = 0; ix < P; ix++) xy[iy][ix] = (iy < P) ? SLOT(2 * (iy * P + ix) + 1) : SLOT(S::YN + ix);
+            for (int ix = 0; ix < P; ix++) xy[iy][ix] = (iy < P) ? SLOT(S::OY + iy * P + ix) : SLOT(S::YN + ix);
         double hx[P][P + 1];
         if (WITH_H) {
 #pragma unroll
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
         for (int qx = 0; qx <= P; qx++) {
             double xc[P];
 #pragma unroll
-            for (int iy = 0; iy < P; iy++) xc[iy] = (qx < P) ? SLOT(2 * (iy * P + qx)) : SLOT(S::XE + iy);
+            for (int iy = 0; iy < P; iy++) xc[iy] = (qx < P) ? SLOT(S::OX + qx * P + iy) : SLOT(S::XE + iy);
             double f0[P + 1];
 #pragma unroll
             for (int qy = 0; qy <= P; qy++) {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
 #pragma unroll
                     for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
                     // the column's own x-edge slots were read above (xc) and by the west far line: overwrite in place
-                    SLOT(2 * (iy * P + qx)) = s;
+                    SLOT(S::OX + qx * P + iy) = s;
                 }
             }
         }
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
 #pragma unroll
         for (int iy = 0; iy < P; iy++)
 #pragma unroll
-            for (int ix = 0; ix < P; ix++) SLOT(2 * (iy * P + ix) + 1) = yy[iy][ix] + (iy == 0 ? cs[ix] : 0.0);
+            for (int ix = 0; ix < P; ix++) SLOT(S::OY + iy * P + ix) = yy[iy][ix] + (iy == 0 ? cs[ix] : 0.0);
 #undef SLOT
     }
     fence_async_smem();

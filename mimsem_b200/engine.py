@@ -112,18 +112,32 @@ class Engine:
             raise MimsemError("%s must be a contiguous float64 CUDA tensor of shape (%d, %d), got %s %s"
                               % (name, n, nlev, tuple(t.shape), t.dtype))
 
-    def to_columns(self, levels):
-        """(nlev, n) level-major device tensor -> (n, nlev) column layout."""
+    def to_columns(self, levels, space):
+        """(nlev, n) per-level device tensor in the caller's DOF numbering -> (n, nlev) engine column layout.
+        space = 0, 1, 2 for nodes / edges / faces (-1: plain transpose)."""
         nlev, n = levels.shape
         out = self.empty(n, nlev)
-        check(self.L.mimsem_gpu_levels_to_columns(self._h, n, nlev, nlev, levels.data_ptr(), out.data_ptr(), self._stream()))
+        check(self.L.mimsem_gpu_levels_to_columns(self._h, space, n, nlev, nlev, levels.data_ptr(), out.data_ptr(),
+                                                  self._stream()))
         return out
 
-    def to_levels(self, cols):
+    def to_levels(self, cols, space):
         n, nlev = cols.shape
         out = self.torch.empty((nlev, n), dtype=self.torch.float64, device=cols.device)
-        check(self.L.mimsem_gpu_columns_to_levels(self._h, n, nlev, nlev, cols.data_ptr(), out.data_ptr(), self._stream()))
+        check(self.L.mimsem_gpu_columns_to_levels(self._h, space, n, nlev, nlev, cols.data_ptr(), out.data_ptr(),
+                                                  self._stream()))
         return out
+
+    def permutation(self, space):
+        """row of each caller-numbered DOF in the engine's column layout."""
+        n = (self.n0, self.n1, self.n2)[space]
+        perm = np.zeros(n, dtype=np.int32)
+        check(self.L.mimsem_gpu_form_permutation(self._h, space, _np_ptr(perm, _ip)))
+        return perm
+
+    SPACES = {"M1": (1, 1, None), "M1h": (1, 1, 2), "M2": (2, 2, None), "M2h": (2, 2, 2), "M0": (0, 0, None),
+              "M0h": (0, 0, 2), "K": (1, 2, 1), "E10": (0, 1, None), "E01": (1, 0, None), "E21": (1, 2, None),
+              "E12": (2, 1, None)}
 
     # ---------------------------------------------------------------- applies (device resident)
     def apply(self, op, x, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0):

@@ -32,8 +32,9 @@ SIGNATURES = {
     "mimsem_gpu_set_geom": (C.c_int, [_vp, _dp, _dp]),
     "mimsem_gpu_set_thickness": (C.c_int, [_vp, C.c_int, _dp]),
     "mimsem_gpu_sizes": (C.c_int, [_vp, _lp]),
-    "mimsem_gpu_levels_to_columns": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
-    "mimsem_gpu_columns_to_levels": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_levels_to_columns": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_columns_to_levels": (C.c_int, [_vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_form_permutation": (C.c_int, [_vp, C.c_int, _ip]),
     "mimsem_gpu_apply_M1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M2": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M0": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -56,13 +56,13 @@ def synthetic_fields(rng, nk, N0, N1, N2, det_mean):
                 h2=rng.uniform(0.5, 1.5, (nk, N2)) * 1.0e4, u1=rng.uniform(-1, 1, (nk, N1)) * det_mean)
 
 
-def to_cols(engine, a):
-    """numpy (nlev, n) per-level array -> column-layout device tensor (n, nlev)."""
+def to_cols(engine, a, space):
+    """numpy (nlev, n) per-level array (reference numbering) -> engine column-layout device tensor (n, nlev)."""
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a)).to("cuda:%d" % engine.device)
-    return engine.to_columns(t)
+    return engine.to_columns(t, space)
 
 
-def to_np(engine, t):
-    """column-layout device tensor (n, nlev) -> numpy (nlev, n)."""
-    return engine.to_levels(t).cpu().numpy()
+def to_np(engine, t, space):
+    """engine column-layout device tensor (n, nlev) -> numpy (nlev, n) in the reference numbering."""
+    return engine.to_levels(t, space).cpu().numpy()

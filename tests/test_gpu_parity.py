@@ -19,8 +19,9 @@ def _engine(kind, p, ne, thick=None, signed=False):
 
 
 def _apply(eng, op, x, coeff=None, **kw):
-    c = None if coeff is None else to_cols(eng, coeff)
-    return to_np(eng, eng.apply(op, to_cols(eng, x), coeff=c, **kw))
+    sin, sout, sc = eng.SPACES[op]
+    c = None if coeff is None else to_cols(eng, coeff, sc)
+    return to_np(eng, eng.apply(op, to_cols(eng, x, sin), coeff=c, **kw), sout)
 
 
 def _apply_per_level(eng, op, x, coeff=None, **kw):
@@ -95,7 +96,7 @@ def test_incidence_bit_exact(fname, kind, p, ne):
         assert rel_l2(_apply(eng, nm, xf), (ref @ xf.T).T) < TOL
     # E21 E10 = 0: exact on integer data, composed on the device
     x0 = rng.integers(-1000, 1000, (2, mesh.N0)).astype(np.float64)
-    z = eng.apply("E21", eng.apply("E10", to_cols(eng, x0)))
+    z = eng.apply("E21", eng.apply("E10", to_cols(eng, x0, 0)))
     assert float(z.abs().max()) == 0.0
     assert abs(mats["E21"] @ mats["E10"]).max() == 0.0
 
@@ -192,10 +193,15 @@ def test_full_size_properties_c5():
 def test_layout_roundtrip():
     import torch
     mesh, eng = _engine("sphere", 3, 4)
-    a = torch.rand((7, mesh.N1), dtype=torch.float64, device="cuda:0")
-    c = eng.to_columns(a)
-    assert torch.equal(c, a.t().contiguous())
-    assert torch.equal(eng.to_levels(c), a)
+    for space, n in ((0, mesh.N0), (1, mesh.N1), (2, mesh.N2)):
+        a = torch.rand((7, n), dtype=torch.float64, device="cuda:0")
+        c = eng.to_columns(a, space)
+        perm = torch.from_numpy(eng.permutation(space).astype(np.int64)).cuda()
+        assert sorted(perm.tolist()) == list(range(n))
+        ref = torch.empty_like(c)
+        ref[perm] = a.t().contiguous()
+        assert torch.equal(c, ref)
+        assert torch.equal(eng.to_levels(c, space), a)
 
 
 def test_error_paths():
