@@ -549,6 +549,10 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
+        {
+            const char* dbg = getenv("MIMSEM_DEBUG");
+            t.debug = dbg ? atoi(dbg) : 0;
+        }
         t.hdr = with_h ? c->d_hdr_h.p : c->d_hdr.p;
         t.cps = with_h ? c->d_cps_h.p : c->d_cps.p;
         t.st_ptr = c->d_st_ptr.p;
@@ -562,10 +566,19 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             t.geo_doubles = S::GEO;
             const size_t smem = 16 + ((size_t)S::GEO + (size_t)(with_h ? S::NS_H : S::NS) * nlev) * sizeof(double);
             if (smem > 227 * 1024) return 1;   // fall through to the register kernels
-            auto kern = with_h ? k_apply_m1_tma<p, true> : k_apply_m1_tma<p, false>;
+            void (*kern)(const TArgs) = nullptr;
+            auto pick = [&](auto NLc) {
+                constexpr int NLv = decltype(NLc)::value;
+                kern = with_h ? k_apply_m1_tma<p, true, NLv> : k_apply_m1_tma<p, false, NLv>;
+            };
+            // compile-time level counts of the BASELINE configurations (C3: 30, C4: 40, C5: 60); anything else: runtime
+            if ((p == 3 || p == 4) && nlev == 60) pick(std::integral_constant<int, 60>());
+            else if (p == 3 && nlev == 30) pick(std::integral_constant<int, 30>());
+            else if (p == 3 && nlev == 40) pick(std::integral_constant<int, 40>());
+            else pick(std::integral_constant<int, 0>());
             cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-            kern<<<c->nel_owned, nlev <= 32 ? 32 : 64, smem, st>>>(t);
+            kern<<<c->nel_owned, 128, smem, st>>>(t);
             return finish_launch(c, "apply_M1 (tma)");
         });
         if (rc3 != 1) return rc3;

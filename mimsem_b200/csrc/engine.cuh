@@ -158,6 +158,7 @@ struct TArgs {
     int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
     int contig_t;     // nkT == nlev
     int geo_doubles;
+    int debug;        // bit0: skip the arithmetic (data-movement-only timing experiment, MIMSEM_DEBUG=1)
     double scale;
     const TileHdr* hdr;
     const CopyEnt* cps;

@@ -10,7 +10,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -39,9 +38,11 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void bulk_commit_wait_all() {
+// commit the bulk stores and wait until their shared-memory source has been read (the CTA may then exit;
+// global visibility is guaranteed at kernel completion)
+__device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -75,9 +76,78 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, 
     if (lane == 0) mbar_arrive_expect_tx(bar, nslots * slot_bytes + (unsigned)a.geo_doubles * 8u);
 }
 
-// y = M1 x (WITH_H: M1(h) x), one CTA per element, thread k = level k.
-template <int P, bool WITH_H>
-__global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TArgs a) {
+// Contribution of the west (SIDE 0) / south (SIDE 1) neighbour's far GLL line to my P shared edges.
+// REV: the neighbour numbers the shared edges in the opposite direction (rotated cubed-sphere seam).
+template <int P, bool WITH_H, int SIDE, bool REV, int NL>
+__device__ __forceinline__ void tile_far_line(const TArgs& a, const double* col, const double* geo, bool far_is_row,
+                                              double (&cfar)[P]) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1;
+    const int nl = NL ? NL : a.nlev;
+#define SLOT(s) col[(size_t)(s) * nl]
+    constexpr int OTH = SIDE == 0 ? S::WOTH : S::SOTH;
+    constexpr int OWN = SIDE == 0 ? S::OX : S::OY;   // west column xx(0,iy) -> OX+iy ; south row xy(ix,0) -> OY+ix
+    const double* gf = geo + (SIDE == 0 ? S::GW : S::GS);
+    double own[P];   // the shared edges in the neighbour's order
+#pragma unroll
+    for (int j = 0; j < P; j++) own[j] = SLOT(OWN + (REV ? P - 1 - j : j));
+    double hs[P];
+    if (WITH_H) {
+        // neighbour's h contracted across its far line (east column: over ix; north row: over iy)
+        constexpr int HN = SIDE == 0 ? S::HW : S::HS;
+#pragma unroll
+        for (int j = 0; j < P; j++) hs[j] = 0.0;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++)
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                const double hv = SLOT(HN + iy * P + ix);
+                if (!far_is_row) hs[iy] += a.E[P * P + ix] * hv;
+                else hs[ix] += a.E[P * P + iy] * hv;
+            }
+    }
+    double f[P + 1];
+#pragma unroll
+    for (int q = 0; q <= P; q++) {
+        double ua = 0.0, ub = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
+#pragma unroll
+        for (int t = 0; t < P; t++) ub += a.E[P * P + t] * SLOT(OTH + q * P + t);
+        // the far line's quadrature points are my own west column / south row points
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int qm = REV ? P - q : q;
+        double c = a.scale;
+        if (a.tpow > 0) {
+            const double t = SLOT(S::T + (SIDE == 0 ? qm * NP1 : qm));
+            c *= t;
+            if (a.tpow > 1) c *= t;
+        }
+        if (WITH_H) {
+            double hl = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hs[j];
+            c *= hl;
+        }
+        f[q] = c * (gf[q * 2 + 0] * ua + gf[q * 2 + 1] * ub);
+    }
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
+        cfar[REV ? P - 1 - j : j] = s;   // neighbour's edge j is my edge (REV ? P-1-j : j)
+    }
+#undef SLOT
+}
+
+// y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 parts x 64 level lanes:
+// part 0 computes the element's x-normal edges (GLL columns, plus the west neighbour's far line),
+// part 1 its y-normal edges (GLL rows, plus the south neighbour's far line).  NL = compile-time
+// number of levels (0: runtime) so that shared-memory operands use immediate offsets.
+template <int P, bool WITH_H, int NL>
+__global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TArgs a) {
     using S = M1Slots<P>;
     constexpr int NP1 = P + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -85,17 +155,27 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
     double* geo = reinterpret_cast<double*>(smem_raw + 16);
     double* tile = geo + S::GEO;
     const int e = blockIdx.x;
-    const int k = threadIdx.x;
-    if (k == 0) mbar_init(bar, 1);
+    const int part = threadIdx.x >> 6;
+    const int k = threadIdx.x & 63;
+    const int nl = NL ? NL : a.nlev;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_async_smem();
+    }
     __syncthreads();
-    if (k < 32) tile_load(a, e, bar, geo, tile);
+    if (threadIdx.x < 32) tile_load(a, e, bar, geo, tile);
     const int flags = a.hdr[e].flags;
     mbar_wait(bar, 0);
 
-    if (k < a.nlev) {
-        const int nl = a.nlev;
-        double* col = tile + k;
+    double out[P][P];
+    double* col = tile + k;
 #define SLOT(s) col[(size_t)(s) * nl]
+    if (a.debug & 1) {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+#pragma unroll
+            for (int j = 0; j < P; j++) out[i][j] = SLOT((part == 0 ? S::OX : S::OY) + i * P + j);
+    } else if (k < nl) {
         auto tf = [&](int q) {
             double f = a.scale;
             if (a.tpow > 0) {
@@ -105,163 +185,150 @@ __global__ void __launch_bounds__(64) k_apply_m1_tma(const __grid_constant__ TAr
             }
             return f;
         };
-        // west / south neighbours' far lines -> contributions to my west x-edges / south y-edges
-        double cw[P], cs[P];
+        double cfar[P];
 #pragma unroll
-        for (int j = 0; j < P; j++) cw[j] = cs[j] = 0.0;
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const bool has = flags & (side == 0 ? 1 : 4);
-            const bool rev = flags & (side == 0 ? 2 : 8);
-            if (!has) continue;
-            const int OTH = side == 0 ? S::WOTH : S::SOTH;
-            const double* gf = geo + (side == 0 ? S::GW : S::GS);
-            // the shared edges, in the neighbour's order
-            double own[P];
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                const int mine = rev ? P - 1 - j : j;   // my iy (west) / ix (south)
-                // west: xx(0, iy) -> slot OX + iy ; south: xy(ix, 0) -> slot OY + ix
-                own[j] = rev ? (side == 0 ? SLOT(S::OX + (P - 1 - j)) : SLOT(S::OY + (P - 1 - j)))
-                             : (side == 0 ? SLOT(S::OX + j) : SLOT(S::OY + j));
-                (void)mine;
+        for (int j = 0; j < P; j++) cfar[j] = 0.0;
+        if (part == 0) {
+            if (flags & 1) {
+                if (flags & 2) tile_far_line<P, WITH_H, 0, true, NL>(a, col, geo, flags & 16, cfar);
+                else tile_far_line<P, WITH_H, 0, false, NL>(a, col, geo, flags & 16, cfar);
             }
-            double hs[P];
+            // ---- x-normal edges: columns qx = 0..P-1 ----
+            double xy[P + 1][P];
+#pragma unroll
+            for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) xy[iy][ix] = (iy < P) ? SLOT(S::OY + iy * P + ix) : SLOT(S::YN + ix);
+            double hx[P][P];   // hx[iy][qx], qx < P
             if (WITH_H) {
-                // neighbour's h contracted across its far line: which index is "across" depends on whether the far
-                // line is its east column (contract ix) or its north row (contract iy): bit 4/5 of flags
-                const bool far_is_row = flags & (side == 0 ? 16 : 32);
-                const int HN = side == 0 ? S::HW : S::HS;
 #pragma unroll
-                for (int j = 0; j < P; j++) hs[j] = 0.0;
+                for (int iy = 0; iy < P; iy++) {
+                    double hv[P];
 #pragma unroll
-                for (int iy = 0; iy < P; iy++)
+                    for (int ix = 0; ix < P; ix++) hv[ix] = SLOT(S::H + iy * P + ix);
 #pragma unroll
-                    for (int ix = 0; ix < P; ix++) {
-                        const double hv = SLOT(HN + iy * P + ix);
-                        if (!far_is_row) hs[iy] += a.E[P * P + ix] * hv;
-                        else hs[ix] += a.E[P * P + iy] * hv;
+                    for (int qx = 0; qx < P; qx++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * hv[ix];
+                        hx[iy][qx] = s;
                     }
-            }
-            double f[P + 1];
-#pragma unroll
-            for (int q = 0; q <= P; q++) {
-                double ua = 0.0, ub = 0.0;
-#pragma unroll
-                for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
-#pragma unroll
-                for (int t = 0; t < P; t++) ub += a.E[P * P + t] * SLOT(OTH + q * P + t);
-                // the far line's quadrature points are my own west column / south row points
-                const int qm = rev ? P - q : q;
-                double c = tf(side == 0 ? qm * NP1 : qm);
-                if (WITH_H) {
-                    double hl = 0.0;
-#pragma unroll
-                    for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hs[j];
-                    c *= hl;
-                }
-                f[q] = c * (gf[q * 2 + 0] * ua + gf[q * 2 + 1] * ub);
-            }
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
-                // neighbour's edge j is my edge (rev ? P-1-j : j)
-                if (side == 0) {
-                    if (rev) cw[P - 1 - j] = s;
-                    else cw[j] = s;
-                } else {
-                    if (rev) cs[P - 1 - j] = s;
-                    else cs[j] = s;
                 }
             }
-        }
-
-        // own element
-        double xy[P + 1][P];
 #pragma unroll
-        for (int iy = 0; iy <= P; iy++)
+            for (int qx = 0; qx < P; qx++) {
+                double xc[P];
 #pragma unroll
-            for (int ix = 0; ix < P; ix++) xy[iy][ix] = (iy < P) ? SLOT(S::OY + iy * P + ix) : SLOT(S::YN + ix);
-        double hx[P][P + 1];
-        if (WITH_H) {
+                for (int iy = 0; iy < P; iy++) xc[iy] = SLOT(S::OX + qx * P + iy);
+                double f0[P + 1];
+#pragma unroll
+                for (int qy = 0; qy <= P; qy++) {
+                    double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+                    for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xc[iy];
+#pragma unroll
+                    for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * xy[qy][ix];
+                    const int q = qy * NP1 + qx;
+                    double c = tf(q);
+                    if (WITH_H) {
+                        double hl = 0.0;
+#pragma unroll
+                        for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hx[iy][qx];
+                        c *= hl;
+                    }
+                    f0[qy] = c * (geo[q * 3 + 0] * ul0 + geo[q * 3 + 1] * ul1);
+                }
+#pragma unroll
+                for (int iy = 0; iy < P; iy++) {
+                    double s = (qx == 0) ? cfar[iy] : 0.0;
+#pragma unroll
+                    for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
+                    out[qx][iy] = s;   // slot OX + qx P + iy
+                }
+            }
+        } else {
+            if (flags & 4) {
+                if (flags & 8) tile_far_line<P, WITH_H, 1, true, NL>(a, col, geo, flags & 32, cfar);
+                else tile_far_line<P, WITH_H, 1, false, NL>(a, col, geo, flags & 32, cfar);
+            }
+            // ---- y-normal edges: rows qy = 0..P-1 ----
+            double xx[P][P + 1];
 #pragma unroll
             for (int iy = 0; iy < P; iy++)
 #pragma unroll
+                for (int ix = 0; ix <= P; ix++) xx[iy][ix] = (ix < P) ? SLOT(S::OX + ix * P + iy) : SLOT(S::XE + iy);
+            double hy[P][P];   // hy[ix][qy], qy < P : h contracted in y
+            if (WITH_H) {
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) {
+                    double hv[P];
+#pragma unroll
+                    for (int iy = 0; iy < P; iy++) hv[iy] = SLOT(S::H + iy * P + ix);
+#pragma unroll
+                    for (int qy = 0; qy < P; qy++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int iy = 0; iy < P; iy++) s += a.E[qy * P + iy] * hv[iy];
+                        hy[ix][qy] = s;
+                    }
+                }
+            }
+#pragma unroll
+            for (int qy = 0; qy < P; qy++) {
+                double yr[P];
+#pragma unroll
+                for (int ix = 0; ix < P; ix++) yr[ix] = SLOT(S::OY + qy * P + ix);
+                double f1[P + 1];
+#pragma unroll
                 for (int qx = 0; qx <= P; qx++) {
-                    double s = 0.0;
+                    double ul0 = 0.0, ul1 = 0.0;
 #pragma unroll
-                    for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * SLOT(S::H + iy * P + ix);
-                    hx[iy][qx] = s;
+                    for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xx[iy][qx];
+#pragma unroll
+                    for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * yr[ix];
+                    const int q = qy * NP1 + qx;
+                    double c = tf(q);
+                    if (WITH_H) {
+                        double hl = 0.0;
+#pragma unroll
+                        for (int ix = 0; ix < P; ix++) hl += a.E[qx * P + ix] * hy[ix][qy];
+                        c *= hl;
+                    }
+                    f1[qx] = c * (geo[q * 3 + 1] * ul0 + geo[q * 3 + 2] * ul1);
                 }
-        }
-        double yy[P][P];
 #pragma unroll
-        for (int iy = 0; iy < P; iy++)
+                for (int ix = 0; ix < P; ix++) {
+                    double s = (qy == 0) ? cfar[ix] : 0.0;
 #pragma unroll
-            for (int ix = 0; ix < P; ix++) yy[iy][ix] = 0.0;
-#pragma unroll
-        for (int qx = 0; qx <= P; qx++) {
-            double xc[P];
-#pragma unroll
-            for (int iy = 0; iy < P; iy++) xc[iy] = (qx < P) ? SLOT(S::OX + qx * P + iy) : SLOT(S::XE + iy);
-            double f0[P + 1];
-#pragma unroll
-            for (int qy = 0; qy <= P; qy++) {
-                double ul0 = 0.0, ul1 = 0.0;
-#pragma unroll
-                for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xc[iy];
-#pragma unroll
-                for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * xy[qy][ix];
-                const int q = qy * NP1 + qx;
-                double c = tf(q);
-                if (WITH_H) {
-                    double hl = 0.0;
-#pragma unroll
-                    for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hx[iy][qx];
-                    c *= hl;
-                }
-                const double g0 = geo[q * 3 + 0], g1 = geo[q * 3 + 1], g2 = geo[q * 3 + 2];
-                f0[qy] = c * (g0 * ul0 + g1 * ul1);
-                if (qy < P) {
-                    const double f1 = c * (g1 * ul0 + g2 * ul1);
-#pragma unroll
-                    for (int ix = 0; ix < P; ix++) yy[qy][ix] += a.E[qx * P + ix] * f1;
-                }
-            }
-            if (qx < P) {
-#pragma unroll
-                for (int iy = 0; iy < P; iy++) {
-                    double s = (qx == 0) ? cw[iy] : 0.0;
-#pragma unroll
-                    for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
-                    // the column's own x-edge slots were read above (xc) and by the west far line: overwrite in place
-                    SLOT(S::OX + qx * P + iy) = s;
+                    for (int qx = 0; qx <= P; qx++) s += a.E[qx * P + ix] * f1[qx];
+                    out[qy][ix] = s;   // slot OY + qy P + ix
                 }
             }
         }
-        // results replace the inputs in the own-block slots (each thread only ever touches its own column)
-#pragma unroll
-        for (int iy = 0; iy < P; iy++)
-#pragma unroll
-            for (int ix = 0; ix < P; ix++) SLOT(S::OY + iy * P + ix) = yy[iy][ix] + (iy == 0 ? cs[ix] : 0.0);
-#undef SLOT
     }
+    __syncthreads();   // both parts have read every input slot: the own block can now be overwritten
+    if (k < nl) {
+        const int base = part == 0 ? S::OX : S::OY;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+#pragma unroll
+            for (int j = 0; j < P; j++) SLOT(base + i * P + j) = out[i][j];
+    }
+#undef SLOT
     fence_async_smem();
     __syncthreads();
     // bulk stores of the owned block
-    if (k < 32) {
-        const unsigned slot_bytes = (unsigned)a.nlev * 8u;
-        for (int si = a.st_ptr[e] + k; si < a.st_ptr[e + 1]; si += 32) {
+    if (threadIdx.x < 32) {
+        const unsigned slot_bytes = (unsigned)nl * 8u;
+        for (int si = a.st_ptr[e] + (int)threadIdx.x; si < a.st_ptr[e + 1]; si += 32) {
             const StoreEnt s = a.stores[si];
             double* dst = a.y + (size_t)s.dof * a.ld;
-            const double* src = tile + (size_t)s.slot * a.nlev;
+            const double* src = tile + (size_t)s.slot * nl;
             if (a.contig_x) bulk_s2g(dst, src, slot_bytes * s.count);
             else
-                for (int j = 0; j < s.count; j++) bulk_s2g(dst + (size_t)j * a.ld, src + (size_t)j * a.nlev, slot_bytes);
+                for (int j = 0; j < s.count; j++) bulk_s2g(dst + (size_t)j * a.ld, src + (size_t)j * nl, slot_bytes);
         }
-        bulk_commit_wait_all();
+        bulk_commit_wait_read();
     }
 }
 
