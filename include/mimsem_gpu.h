@@ -179,6 +179,16 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_s
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
                           const double* h_coeff, const double* h_x, double* h_y);
 
+/* Halo pack / unpack (device pointers; d_rows holds engine rows, i.e. values of mimsem_gpu_form_permutation):
+ *   gather : packed[i*nlev + k] = field[rows[i]*ld + k]        (send side of the ghost refresh)
+ *   scatter: field[rows[i]*ld + k] = packed[i*nlev + k]        (receive side)
+ * Together with an NCCL send/recv of the packed buffers these replace Topo's
+ * VecScatter(gtol_1 | gtol_0, INSERT_VALUES, SCATTER_FORWARD)  (eul/Topo.cpp:145-155, eul/Euler_2.cpp:1455-1456). */
+int mimsem_gpu_gather_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld, const int* d_rows, const double* d_field,
+                           double* d_packed, void* stream);
+int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld, const int* d_rows, const double* d_packed,
+                            double* d_field, void* stream);
+
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
 

@@ -1111,6 +1111,30 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     return MIMSEM_OK;
 }
 
+int mimsem_gpu_gather_rows(mimsem_gpu_ctx* c, int64_t nrows, int nlev, int ld, const int* d_rows, const double* d_field,
+                           double* d_packed, void* stream) {
+    if (!c || !d_rows || !d_field || !d_packed) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (nrows == 0) return MIMSEM_OK;
+    if (nrows < 0 || nlev < 1 || ld < nlev || nrows * nlev >= (1ll << 32)) return fail(MIMSEM_ERR_ARG, "bad pack shape");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const FastDiv fd = make_fastdiv((unsigned)nlev);
+    k_rows<true><<<grid_for(nrows * nlev, 256), 256, 0, (cudaStream_t)stream>>>(nrows, nlev, ld, fd.m, fd.s, d_rows, d_field, d_packed);
+    return finish_launch(c, "gather_rows");
+}
+
+int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* c, int64_t nrows, int nlev, int ld, const int* d_rows, const double* d_packed,
+                            double* d_field, void* stream) {
+    if (!c || !d_rows || !d_field || !d_packed) return fail(MIMSEM_ERR_ARG, "null argument");
+    if (nrows == 0) return MIMSEM_OK;
+    if (nrows < 0 || nlev < 1 || ld < nlev || nrows * nlev >= (1ll << 32)) return fail(MIMSEM_ERR_ARG, "bad unpack shape");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const FastDiv fd = make_fastdiv((unsigned)nlev);
+    k_rows<false><<<grid_for(nrows * nlev, 256), 256, 0, (cudaStream_t)stream>>>(nrows, nlev, ld, fd.m, fd.s, d_rows, d_packed, d_field);
+    return finish_launch(c, "scatter_rows");
+}
+
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* c) { return c ? c->launches : 0; }
 
 }  // extern "C"

@@ -585,6 +585,19 @@ __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllAr
     a.y[(size_t)r * a.ld + k] = s;
 }
 
+// Halo pack / unpack: packed[i*nlev + k] <-> field[rows[i]*ld + k]   (rows = ghost or send lists)
+template <bool GATHER>
+__global__ void __launch_bounds__(256) k_rows(int64_t nrows, int nlev, int ld, unsigned div_m, unsigned div_s,
+                                              const int* __restrict__ rows, const double* __restrict__ src,
+                                              double* __restrict__ dst) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)nrows * (unsigned)nlev) return;
+    const unsigned i = fastdiv(idx, div_m, div_s);
+    const unsigned k = idx - i * (unsigned)nlev;
+    if (GATHER) dst[idx] = src[(size_t)rows[i] * ld + k];
+    else dst[(size_t)rows[i] * ld + k] = src[idx];
+}
+
 // levels[k*n + dof] <-> columns[perm[dof]*ld + k] through a padded shared-memory tile
 // (perm = the engine's internal numbering of the space, nullptr = identity)
 template <bool TO_COLUMNS>

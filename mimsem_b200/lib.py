@@ -45,6 +45,8 @@ SIGNATURES = {
     "mimsem_gpu_apply_incidence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_incidence_csr": (C.c_int, [_vp, C.c_int, _lp, _lp, _ip, _dp]),
     "mimsem_gpu_apply_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "mimsem_gpu_gather_rows": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_scatter_rows": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
 }
 

@@ -1,0 +1,250 @@
+"""Multi-GPU: contiguous element-block partition of the canonical global mesh + ghost refresh.
+
+One process per GPU.  Rank g of G owns the contiguous element range [g*Nel/G, (g+1)*Nel/G) of the
+canonical numbering (element e = face*ne^2 + ey*ne + ex) -- free of the reference's 6*n^2 rank
+constraint (README.md:32, scr/Setup.py:25-29) -- and with it the edges and faces whose global ids
+fall into that element's block (scr/Proc2.py:105-123).  Operators are applied owner-computes: every
+rank holds, besides its owned elements, the west/south neighbour elements of its owned elements as
+read-only halo elements, so that outputs on owned DOFs are complete and need NO reduction.  What
+the reference does with VecScatter(gtol_1, ADD_VALUES, SCATTER_REVERSE) after its matrix-free
+assembly (eul/Assembly.cpp:2194-2195) and with the forward INSERT scatter before it
+(eul/Euler_2.cpp:1455-1456) collapses into ONE exchange: a ghost refresh of the INPUT field,
+implemented as pack kernel -> NCCL send/recv over NVLink (torch.distributed) -> unpack kernel.
+
+The partition logic is pure numpy (tested on CPU with world_size-2 gloo); only DistributedEngine
+touches the GPU.
+"""
+import numpy as np
+
+from .engine import Engine
+from .mesh import Basis
+
+
+def element_range(nel, rank, world):
+    return (rank * nel) // world, ((rank + 1) * nel) // world
+
+
+def owner_rank_of_element(e, nel, world):
+    """inverse of element_range (vectorised)"""
+    e = np.asarray(e, dtype=np.int64)
+    r = (e * world) // nel
+    # correct the integer-division edge cases
+    lo = (r * nel) // world
+    hi = ((r + 1) * nel) // world
+    r = np.where(e < lo, r - 1, np.where(e >= hi, r + 1, r))
+    return r
+
+
+def west_south_neighbours(mesh):
+    """nbr[e, 0] / nbr[e, 1]: the element across the west / south side of e (-1 if none)."""
+    if getattr(mesh, "_ws_nbr", None) is not None:
+        return mesh._ws_nbr
+    p, nel = mesh.p, mesh.nel
+    n1e = p * (p + 1)
+    dofs = np.concatenate([mesh.el1x.ravel(), mesh.el1y.ravel()]).astype(np.int64)
+    elem = np.concatenate([np.repeat(np.arange(nel), n1e), np.repeat(np.arange(nel), n1e)])
+    order = np.argsort(dofs, kind="stable")
+    ds, es = dofs[order], elem[order]
+    # every edge of a closed mesh is used by exactly two (element, slot) pairs
+    first = np.searchsorted(ds, np.arange(mesh.N1), side="left")
+    last = np.searchsorted(ds, np.arange(mesh.N1), side="right")
+    nbr = -np.ones((nel, 2), dtype=np.int64)
+    e_ids = np.arange(nel)
+    for side, d in ((0, mesh.el1x[:, 0].astype(np.int64)), (1, mesh.el1y[:, 0].astype(np.int64))):
+        a, b = es[first[d]], es[np.minimum(last[d] - 1, len(es) - 1)]
+        cnt = last[d] - first[d]
+        other = np.where(a == e_ids, b, a)
+        # a periodic one-element-wide mesh makes an element its own neighbour (both uses are e itself)
+        nbr[:, side] = np.where(cnt >= 2, other, -1)
+    mesh._ws_nbr = nbr
+    return nbr
+
+
+class Partition:
+    """Local view of rank `rank` of `world`: owned + halo elements, owned-first local DOF numbering,
+    ghost lists grouped by owner rank.  All index arrays are numpy int32/int64."""
+
+    def __init__(self, mesh, rank, world):
+        p = mesh.p
+        self.p, self.rank, self.world = p, rank, world
+        nel = mesh.nel
+        e0, e1 = element_range(nel, rank, world)
+        self.e0, self.e1 = e0, e1
+        owned = np.arange(e0, e1, dtype=np.int64)
+        nbr = west_south_neighbours(mesh)[e0:e1].ravel()
+        nbr = nbr[nbr >= 0]
+        halo = np.setdiff1d(np.unique(nbr), owned)
+        self.elements = np.concatenate([owned, halo])          # local element -> global element
+        self.nel_owned, self.nel_total = len(owned), len(owned) + len(halo)
+        L = self.elements
+        b1, b2 = 2 * p * p, p * p
+
+        def local_numbering(ids, block):
+            ids = np.unique(ids.astype(np.int64))
+            own = ids[(ids // block >= e0) & (ids // block < e1)] if block else ids
+            ghost = np.setdiff1d(ids, own) if block else ids[:0]
+            return np.concatenate([own, ghost]), len(own)
+
+        # 1-forms: edge g is owned by element g // (2 p^2); 2-forms: face g by element g // p^2
+        self.g1, self.n1_owned = local_numbering(np.concatenate([mesh.el1x[L].ravel(), mesh.el1y[L].ravel()]), b1)
+        self.g2, self.n2_owned = local_numbering(mesh.el2[L].ravel(), b2)
+        self.g0, _ = local_numbering(mesh.el0[L].ravel(), 0)
+        self.gq, _ = local_numbering(mesh.elq[L].ravel(), 0)
+        self.n0, self.n1, self.n2, self.nq = len(self.g0), len(self.g1), len(self.g2), len(self.gq)
+
+        def to_local(gids, table):
+            # gids = [owned ascending | ghost ascending]: search both halves
+            n_own = {id(self.g1): self.n1_owned, id(self.g2): self.n2_owned}.get(id(gids), len(gids))
+            t = table.astype(np.int64)
+            a = np.searchsorted(gids[:n_own], t)
+            a = np.minimum(a, max(n_own - 1, 0))
+            hit = (gids[:n_own][a] == t) if n_own else np.zeros(t.shape, bool)
+            if n_own < len(gids):
+                b = np.searchsorted(gids[n_own:], t)
+                b = np.minimum(b, len(gids) - n_own - 1)
+                out = np.where(hit, a, b + n_own)
+            else:
+                out = a
+            assert np.array_equal(gids[out], t)
+            return out.astype(np.int32)
+
+        self.el1x = to_local(self.g1, mesh.el1x[L])
+        self.el1y = to_local(self.g1, mesh.el1y[L])
+        self.el2 = to_local(self.g2, mesh.el2[L])
+        self.el0 = to_local(self.g0, mesh.el0[L])
+        self.elq = to_local(self.gq, mesh.elq[L])
+        # ghosts grouped by owner rank (ascending global id inside a group)
+        self.recv = {1: self._group(self.g1[self.n1_owned:], b1, nel, self.n1_owned),
+                     2: self._group(self.g2[self.n2_owned:], b2, nel, self.n2_owned)}
+
+    def _group(self, ghosts, block, nel, offset):
+        owner = owner_rank_of_element(ghosts // block, nel, self.world)
+        out = {}
+        for q in np.unique(owner):
+            sel = np.nonzero(owner == q)[0]
+            out[int(q)] = dict(local=(sel + offset).astype(np.int32), glob=ghosts[sel])
+        return out
+
+    def owned_global(self, space):
+        return {1: self.g1[:self.n1_owned], 2: self.g2[:self.n2_owned]}[space]
+
+
+def send_lists(mesh, rank, world):
+    """For every peer q: the LOCAL (owned) ids on `rank` that q holds as ghosts, in q's receive order.
+    Every rank can build every partition, so no index exchange is needed at setup."""
+    me = Partition(mesh, rank, world)
+    p = mesh.p
+    out = {1: {}, 2: {}}
+    for q in range(world):
+        if q == rank:
+            continue
+        other = Partition(mesh, q, world)
+        for space, block in ((1, 2 * p * p), (2, p * p)):
+            grp = other.recv[space].get(rank)
+            if grp is None:
+                continue
+            first = me.e0 * block
+            out[space][q] = (grp["glob"] - first).astype(np.int32)   # owned DOFs are numbered contiguously from e0*block
+    return me, out
+
+
+class DistributedEngine:
+    """Engine of one rank + the ghost-refresh plan.  Fields are local column-layout tensors with
+    n_space rows (owned rows are complete after an apply; ghost rows are refreshed by exchange())."""
+
+    SUPPORTED = ("M1", "M1h", "M2", "M2h", "K", "E21", "E12")
+
+    def __init__(self, mesh, thick, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = rank, world
+        self.part, sends = send_lists(mesh, rank, world)
+        P = self.part
+        eng = Engine(device)
+        eng.set_basis(Basis(mesh.p, mesh.m))
+        eng.set_topo(P.el0, P.el1x, P.el1y, P.el2, P.elq, P.n0, P.n1, P.n2, P.nq, nel_owned=P.nel_owned, mode=0)
+        eng.set_geom(mesh.J[P.elements], mesh.det[P.elements])
+        if thick is not None:
+            eng.set_thickness(np.ascontiguousarray(thick[:, P.gq]))
+        self.engine = eng
+        self.device = device
+        dev = "cuda:%d" % device
+        self.plan = {}
+        for space in (1, 2):
+            perm = eng.permutation(space).astype(np.int64)
+            peers = sorted(set(P.recv[space]) | set(sends[space]))
+            plan = []
+            for q in peers:
+                r = P.recv[space].get(q)
+                s = sends[space].get(q)
+                rrows = torch.from_numpy(perm[r["local"]].astype(np.int32)).to(dev) if r is not None else None
+                srows = torch.from_numpy(perm[s].astype(np.int32)).to(dev) if s is not None else None
+                plan.append((q, srows, rrows))
+            self.plan[space] = plan
+        self._bufs = {}
+
+    # sizes / plumbing shared with Engine
+    def space_sizes(self, op):
+        return self.engine.space_sizes(op)
+
+    @property
+    def launch_count(self):
+        return self.engine.launch_count
+
+    def halo_bytes(self, space, nlev):
+        return sum((0 if s is None else s.numel()) for _, s, _ in self.plan[space]) * nlev * 8
+
+    def exchange(self, field, space):
+        """Ghost refresh of a local field: pack -> NCCL send/recv -> unpack."""
+        eng, torch, dist = self.engine, self.torch, self.dist
+        nlev = field.shape[1]
+        st = eng._stream()
+        ops, unpack = [], []
+        for q, srows, rrows in self.plan[space]:
+            if srows is not None:
+                sb = self._buf(("s", space, q, nlev), srows.numel() * nlev, field.device)
+                eng.L.mimsem_gpu_gather_rows(eng._h, srows.numel(), nlev, nlev, srows.data_ptr(), field.data_ptr(), sb.data_ptr(), st)
+                ops.append(dist.P2POp(dist.isend, sb, q))
+            if rrows is not None:
+                rb = self._buf(("r", space, q, nlev), rrows.numel() * nlev, field.device)
+                ops.append(dist.P2POp(dist.irecv, rb, q))
+                unpack.append((rrows, rb))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for rrows, rb in unpack:
+            eng.L.mimsem_gpu_scatter_rows(eng._h, rrows.numel(), nlev, nlev, rrows.data_ptr(), rb.data_ptr(), field.data_ptr(), st)
+        return field
+
+    def _buf(self, key, n, device):
+        b = self._bufs.get(key)
+        if b is None or b.numel() < n:
+            b = self.torch.empty(n, dtype=self.torch.float64, device=device)
+            self._bufs[key] = b
+        return b[:n]
+
+    def apply(self, op, x, coeff=None, out=None, exchange=True, **kw):
+        if op not in self.SUPPORTED:
+            raise NotImplementedError("operator %s is not partitioned yet (0-form operators need node ownership)" % op)
+        sin, sout, sc = self.engine.SPACES[op]
+        if exchange:
+            self.exchange(x, sin)
+            if coeff is not None:
+                self.exchange(coeff, sc)
+        return self.engine.apply(op, x, coeff=coeff, out=out, **kw)
+
+    # test / IO helpers ------------------------------------------------------------------
+    def scatter_from_global(self, levels_global, space):
+        """numpy (nlev, N_space) global field -> local column tensor with owned AND ghost rows filled."""
+        g = {0: self.part.g0, 1: self.part.g1, 2: self.part.g2}[space]
+        loc = np.ascontiguousarray(levels_global[:, g])
+        t = self.torch.from_numpy(loc).to("cuda:%d" % self.device)
+        return self.engine.to_columns(t, space)
+
+    def owned_to_global(self, field, space, out_global):
+        """write the owned rows of a local column tensor into a numpy (nlev, N_space) global array"""
+        loc = self.engine.to_levels(field, space).cpu().numpy()
+        n_own = {1: self.part.n1_owned, 2: self.part.n2_owned}[space]
+        out_global[:, self.part.owned_global(space)] = loc[:, :n_own]
+        return out_global

@@ -234,3 +234,19 @@ def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
     for v in ("1", "2"):
         for a, b in zip(res[v], res["0"]):
             assert rel_l2(a, b) < 1e-14, (v, rel_l2(a, b))
+
+
+def test_multi_gpu_partitioned_apply():
+    """N>1: element-block partition + NCCL ghost refresh, bitwise equal to the single-GPU result (tests/mp_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (covered on CPU by tests/test_partition.py with gloo)")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,104 @@
+"""CPU tests of the N>1 host logic: element-block partition, owned-first local numbering, ghost lists,
+and the ghost refresh itself over a world_size-2 gloo group (no GPU, no CUDA library calls)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import mimsem_b200 as mb
+from mimsem_b200.parallel import Partition, element_range, owner_rank_of_element, send_lists, west_south_neighbours
+
+
+@pytest.mark.parametrize("kind,p,ne,world", [("sphere", 3, 4, 2), ("sphere", 3, 4, 8), ("sphere", 4, 2, 3), ("box", 3, 4, 2), ("box", 3, 4, 4)])
+def test_partition_covers_everything_once(kind, p, ne, world):
+    mesh = mb.Mesh(kind, p, ne)
+    seen1 = np.zeros(mesh.N1, int)
+    seen2 = np.zeros(mesh.N2, int)
+    for r in range(world):
+        P = Partition(mesh, r, world)
+        e0, e1 = element_range(mesh.nel, r, world)
+        assert np.array_equal(P.elements[:P.nel_owned], np.arange(e0, e1))
+        assert np.all(owner_rank_of_element(np.arange(e0, e1), mesh.nel, world) == r)
+        seen1[P.g1[:P.n1_owned]] += 1
+        seen2[P.g2[:P.n2_owned]] += 1
+        # local tables reproduce the global ones
+        assert np.array_equal(P.g1[P.el1x], mesh.el1x[P.elements])
+        assert np.array_equal(P.g1[P.el1y], mesh.el1y[P.elements])
+        assert np.array_equal(P.g2[P.el2], mesh.el2[P.elements])
+        assert np.array_equal(P.gq[P.elq], mesh.elq[P.elements])
+        # every west / south neighbour of an owned element is local (owner-computes needs no output reduction)
+        nb = west_south_neighbours(mesh)[e0:e1]
+        assert np.all(np.isin(nb[nb >= 0], P.elements))
+        # ghosts are owned by the rank the plan says
+        for space, block in ((1, 2 * p * p), (2, p * p)):
+            for q, grp in P.recv[space].items():
+                assert q != r
+                assert np.all(owner_rank_of_element(grp["glob"] // block, mesh.nel, world) == q)
+    assert np.all(seen1 == 1) and np.all(seen2 == 1)
+
+
+def test_send_lists_match_receive_lists():
+    mesh = mb.Mesh("sphere", 3, 4)
+    world = 4
+    parts, sends = zip(*[send_lists(mesh, r, world) for r in range(world)])
+    for r in range(world):
+        for space in (1, 2):
+            for q, grp in parts[r].recv[space].items():
+                s = sends[q][space][r]                       # what q sends to r, as q-local owned ids
+                assert np.array_equal(parts[q].owned_global(space)[s], grp["glob"])
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = mb.Mesh("sphere", 3, 4)
+        part, sends = send_lists(mesh, rank, world)
+        rng = np.random.default_rng(0)
+        ok = True
+        for space, N in ((1, mesh.N1), (2, mesh.N2)):
+            glob = rng.uniform(-1, 1, (N, 3))                 # same on every rank
+            g = {1: part.g1, 2: part.g2}[space]
+            n_own = {1: part.n1_owned, 2: part.n2_owned}[space]
+            loc = torch.zeros((len(g), 3), dtype=torch.float64)
+            loc[:n_own] = torch.from_numpy(glob[g[:n_own]])   # ghosts start as zero
+            ops, unpack = [], []
+            for peer in sorted(set(part.recv[space]) | set(sends[space])):
+                if peer in sends[space]:
+                    sb = loc[torch.from_numpy(sends[space][peer].astype(np.int64))].contiguous()
+                    ops.append(dist.P2POp(dist.isend, sb, peer))
+                if peer in part.recv[space]:
+                    rows = torch.from_numpy(part.recv[space][peer]["local"].astype(np.int64))
+                    rb = torch.empty((len(rows), 3), dtype=torch.float64)
+                    ops.append(dist.P2POp(dist.irecv, rb, peer))
+                    unpack.append((rows, rb))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for rows, rb in unpack:
+                loc[rows] = rb
+            ok = ok and bool(np.array_equal(loc.numpy(), glob[g]))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ghost_refresh_gloo_world2():
+    """The exchange plan, executed with gloo send/recv on CPU tensors, fills every ghost row with the owner's value."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
