@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -261,9 +262,24 @@ def main():
     if ncoef:
         cs = [torch.rand((ncoef, nk), dtype=torch.float64, device=dev, generator=g) + 0.5 for _ in range(RING)]
 
+    # the step (ghost refresh + kernels) is captured once per ring slot into a CUDA graph and replayed:
+    # at 4-8 GPUs a step is tens of microseconds, i.e. launch-bound without graphs
+    replays = None
+    if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
+        try:
+            replays = [eng.capture(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow)[0]
+                       for j in range(RING)]
+        except Exception as exc:  # fall back to eager launches
+            if rank == 0:
+                print("graph capture failed (%r); timing eager launches" % (exc,), file=sys.stderr)
+            replays = None
+
     def step(i):
         j = i % RING
-        eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow)
+        if replays is not None:
+            replays[j]()
+        else:
+            eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow)
 
     def barrier():
         if world > 1:
@@ -288,6 +304,12 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
+    if replays is not None:
+        # graph replays do not pass through the library's launch counter: count the kernels of one captured step
+        l0 = eng.launch_count
+        eng.apply(op, xs[0], coeff=None if cs is None else cs[0], out=ys[0], scale=SCALE, tpow=tpow)
+        torch.cuda.synchronize()
+        launches = (eng.launch_count - l0) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -340,7 +362,7 @@ def main():
                 "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; operator %s over all levels in one launch "
                                        "(Nel=%d, out DOF-levels=%d)" % (args.workload, variant, p, ne, ne, nk, op, mesh.nel, out_dofs),
                            "cache": "ring of %d distinct field sets, each field pair %.0f MB > 126 MB L2" % (RING, 16e-6 * nin * nk),
-                           "parallelism": "element-block x%d" % world},
+                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
                              "kernel_ms": kern_ms},

@@ -103,6 +103,10 @@ int mimsem_gpu_set_basis(mimsem_gpu_ctx* ctx, int p, int m, const double* h_w, c
 int mimsem_gpu_set_topo(mimsem_gpu_ctx* ctx, int nel_total, int nel_owned, int n0, int n1, int n2, int nq, int mode,
                         const int* h_el0, const int* h_el1x, const int* h_el1y, const int* h_el2, const int* h_elq);
 
+/* Declare which rows are ghosts (refreshed from other subdomains): caller indices >= n1_owned (1-forms) and
+ * >= n2_owned (2-forms).  Builds the INTERIOR / BOUNDARY element subsets; out_counts = {n_interior, n_boundary}. */
+int mimsem_gpu_set_ghosts(mimsem_gpu_ctx* ctx, int n1_owned, int n2_owned, int out_counts[2]);
+
 /* Geometry of the nel_total elements: J[nel][(m+1)^2][4], det[nel][(m+1)^2] (host pointers). */
 int mimsem_gpu_set_geom(mimsem_gpu_ctx* ctx, const double* h_J, const double* h_det);
 
@@ -143,6 +147,10 @@ int mimsem_gpu_form_permutation(const mimsem_gpu_ctx* ctx, int space, int* perm)
  * assembled once at level 0, box/Assembly.cpp:44-45).
  */
 #define MIMSEM_FIXED_LEVEL 1
+/* Element subsets for overlapping the ghost refresh with computation (after mimsem_gpu_set_ghosts):
+ * INTERIOR = owned elements that read no ghost row, BOUNDARY = the others.  Neither flag: all owned elements. */
+#define MIMSEM_SUBSET_INTERIOR 2
+#define MIMSEM_SUBSET_BOUNDARY 4
 
 int mimsem_gpu_apply_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                         const double* d_x, double* d_y, void* stream);

@@ -78,6 +78,10 @@ struct mimsem_gpu_ctx {
     DevBuf<int> d_el1xT, d_elqT, d_far;      // line-task tables
     DevBuf<double> d_Gc, d_Gr, d_Gch, d_Grh;
     int n_far = 0;
+    // element subsets (multi-GPU overlap): interior = owned elements that read no ghost row
+    DevBuf<int> d_elist_int, d_elist_bnd;
+    int n_int = 0, n_bnd = 0;
+    std::vector<int> h_el1x_ext, h_el1y_ext;   // caller numbering (before perm1), kept for set_ghosts
     int m1_variant = 2;                      // 2: TMA tile kernel (default), 1: line tasks, 0: one thread per element-level
     // TMA tile plan (owner-computes mode)
     bool tma_ok = false;
@@ -229,23 +233,31 @@ void csr_from_triplets(int64_t nrows, int64_t ncols, std::vector<std::array<int6
     for (int64_t r = 0; r < nrows; r++) out.indptr[r + 1] += out.indptr[r];
 }
 
-int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows, const std::vector<int>* rowperm,
-               const std::vector<int>* colperm) {
-    int width = 0;
-    for (int64_t r = 0; r < m.nrows; r++) width = std::max<int>(width, (int)(m.indptr[r + 1] - m.indptr[r]));
-    width = std::max(width, 1);
-    std::vector<int> col((size_t)m.nrows * width, -1);
-    std::vector<signed char> sgn((size_t)m.nrows * width, 0);
-    // entries keep the external column order (the order a CSR MatMult adds them in); only the storage
-    // positions move to the engine's internal numbering
-    for (int64_t r = 0; r < m.nrows; r++) {
-        const size_t ri = rowperm ? (size_t)(*rowperm)[r] : (size_t)r;
-        for (int64_t k = m.indptr[r]; k < m.indptr[r + 1]; k++) {
-            col[ri * width + (k - m.indptr[r])] = colperm ? (*colperm)[m.indices[k]] : m.indices[k];
-            sgn[ri * width + (k - m.indptr[r])] = m.values[k] > 0 ? 1 : -1;
-        }
+// Device stencil from (row, col, sign, key) entries.  The order in which a row's entries are ADDED is the
+// ascending `key`, chosen so that it does not depend on the local numbering (and hence not on the partition):
+// results are bitwise identical on 1 and on N GPUs.
+struct StencilEnt {
+    int64_t row, col;
+    int sign, key;
+};
+int upload_ell(int64_t nrows, std::vector<StencilEnt> ents, DevEll& d, const std::vector<int>* rows,
+               const std::vector<int>* rowperm, const std::vector<int>* colperm) {
+    std::stable_sort(ents.begin(), ents.end(), [](const StencilEnt& a, const StencilEnt& b) {
+        return a.row != b.row ? a.row < b.row : a.key < b.key;
+    });
+    std::vector<int> cnt(nrows, 0);
+    int width = 1;
+    for (auto& e : ents) width = std::max(width, ++cnt[e.row]);
+    std::vector<int> col((size_t)nrows * width, -1);
+    std::vector<signed char> sgn((size_t)nrows * width, 0);
+    std::fill(cnt.begin(), cnt.end(), 0);
+    for (auto& e : ents) {
+        const size_t ri = rowperm ? (size_t)(*rowperm)[e.row] : (size_t)e.row;
+        const int j = cnt[e.row]++;
+        col[ri * width + j] = colperm ? (*colperm)[e.col] : (int)e.col;
+        sgn[ri * width + j] = e.sign > 0 ? 1 : -1;
     }
-    d.nrows = m.nrows;
+    d.nrows = nrows;
     d.width = width;
     CUDA_OK(d.col.upload(col));
     CUDA_OK(d.sgn.upload(sgn));
@@ -259,7 +271,7 @@ int upload_ell(const HostCsr& m, DevEll& d, const std::vector<int>* rows, const 
         CUDA_OK(d.rows.upload(rr));
     } else {
         d.use_rows = false;
-        d.nrows_active = m.nrows;
+        d.nrows_active = nrows;
     }
     return MIMSEM_OK;
 }
@@ -299,6 +311,13 @@ int build_incidence(mimsem_gpu_ctx* c) {
     }
     for (auto& v : t10) t01.push_back({v[1], v[0], -v[2]});
     for (auto& v : t21) t12.push_back({v[1], v[0], -v[2]});
+    // device stencils: E10 / E21 add their entries in the reference's MatSetValues order (eul/Assembly.cpp:1133-1148,
+    // 1196-1205); E12 rows add the +1 face (the edge's owner side) before the -1 face; E01 rows by column.
+    std::vector<StencilEnt> s10, s21, s01, s12;
+    for (size_t i = 0; i < t10.size(); i++) s10.push_back({t10[i][0], t10[i][1], (int)t10[i][2], (int)(i & 1)});
+    for (size_t i = 0; i < t21.size(); i++) s21.push_back({t21[i][0], t21[i][1], (int)t21[i][2], (int)(i & 3)});
+    for (auto& v : t12) s12.push_back({v[0], v[1], (int)v[2], v[2] > 0 ? 0 : 1});
+    for (auto& v : t01) s01.push_back({v[0], v[1], (int)v[2], (int)v[1]});
     csr_from_triplets(c->n1, c->n0, t10, c->csr[MIMSEM_E10]);
     csr_from_triplets(c->n0, c->n1, t01, c->csr[MIMSEM_E01]);
     csr_from_triplets(c->n2, c->n1, t21, c->csr[MIMSEM_E21]);
@@ -308,10 +327,10 @@ int build_incidence(mimsem_gpu_ctx* c) {
     const bool all = (c->nel_owned == c->nel_total);
     int rc;
     const std::vector<int>* pm = &c->h_perm1;
-    if ((rc = upload_ell(c->csr[MIMSEM_E10], c->ell[MIMSEM_E10], all ? nullptr : &rows10, pm, nullptr))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E21], c->ell[MIMSEM_E21], all ? nullptr : &rows21, nullptr, pm))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E01], c->ell[MIMSEM_E01], nullptr, nullptr, pm))) return rc;
-    if ((rc = upload_ell(c->csr[MIMSEM_E12], c->ell[MIMSEM_E12], nullptr, pm, nullptr))) return rc;
+    if ((rc = upload_ell(c->n1, s10, c->ell[MIMSEM_E10], all ? nullptr : &rows10, pm, nullptr))) return rc;
+    if ((rc = upload_ell(c->n2, s21, c->ell[MIMSEM_E21], all ? nullptr : &rows21, nullptr, pm))) return rc;
+    if ((rc = upload_ell(c->n0, s01, c->ell[MIMSEM_E01], nullptr, nullptr, pm))) return rc;
+    if ((rc = upload_ell(c->n1, s12, c->ell[MIMSEM_E12], nullptr, pm, nullptr))) return rc;
     return MIMSEM_OK;
 }
 
@@ -471,6 +490,9 @@ void copy_basis(const mimsem_gpu_ctx* c, Args& a) {
 
 int check_ready(const mimsem_gpu_ctx* c, bool need_thick, int lev0, int nlev, int ld, int flags) {
     if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    if ((flags & (MIMSEM_SUBSET_INTERIOR | MIMSEM_SUBSET_BOUNDARY)) && c->n_int + c->n_bnd != c->nel_owned)
+        return fail(MIMSEM_ERR_STATE, "element subsets need mimsem_gpu_set_ghosts");
+    if ((flags & MIMSEM_SUBSET_INTERIOR) && (flags & MIMSEM_SUBSET_BOUNDARY)) return fail(MIMSEM_ERR_ARG, "choose one subset");
     if (!c->have_basis || !c->have_topo || !c->have_geom) return fail(MIMSEM_ERR_STATE, "set_basis, set_topo and set_geom must precede an apply");
     if (c->m != c->p) return fail(MIMSEM_ERR_UNSUPPORTED, "the sum-factorised kernels require quadrature order == element order");
     if (nlev < 1 || ld < nlev || lev0 < 0) return fail(MIMSEM_ERR_ARG, "bad level range / leading dimension");
@@ -484,6 +506,12 @@ int check_ready(const mimsem_gpu_ctx* c, bool need_thick, int lev0, int nlev, in
 
 void fill_common(const mimsem_gpu_ctx* c, KArgs& a, int lev0, int nlev, int ld, double scale, int tpow, int flags) {
     a.nel = c->nel_owned;
+    a.elist = nullptr;
+    if (flags & (MIMSEM_SUBSET_INTERIOR | MIMSEM_SUBSET_BOUNDARY)) {
+        const bool in = flags & MIMSEM_SUBSET_INTERIOR;
+        a.nel = in ? c->n_int : c->n_bnd;
+        a.elist = in ? c->d_elist_int.p : c->d_elist_bnd.p;
+    }
     a.nlev = nlev;
     a.ld = ld;
     a.lev0 = lev0;
@@ -541,6 +569,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
+    if (threads == 0) return MIMSEM_OK;
     // TMA tile kernel: needs 16-byte aligned, even-length level runs and one thread per level
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
     const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
@@ -553,6 +582,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             const char* dbg = getenv("MIMSEM_DEBUG");
             t.debug = dbg ? atoi(dbg) : 0;
         }
+        t.elist = a.elist;
         t.hdr = with_h ? c->d_hdr_h.p : c->d_hdr.p;
         t.cps = with_h ? c->d_cps_h.p : c->d_cps.p;
         t.st_ptr = c->d_st_ptr.p;
@@ -578,7 +608,8 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             else pick(std::integral_constant<int, 0>());
             cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-            kern<<<c->nel_owned, 128, smem, st>>>(t);
+            if (a.nel == 0) return (int)MIMSEM_OK;
+            kern<<<a.nel, 128, smem, st>>>(t);
             return finish_launch(c, "apply_M1 (tma)");
         });
         if (rc3 != 1) return rc3;
@@ -623,6 +654,7 @@ int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.x = x;
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads == 0) return MIMSEM_OK;
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
         if (with_h) k_apply_m2<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
@@ -643,6 +675,7 @@ int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpo
     a.x = x;
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads == 0) return MIMSEM_OK;
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
         k_apply_k<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
@@ -845,6 +878,9 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         CUDA_OK(c->d_perm1.upload(c->h_perm1));
     }
     if ((rc = build_incidence(c))) return rc;   // external numbering (exported CSR), device stencils permuted
+    c->h_el1x_ext = c->h_el1x;
+    c->h_el1y_ext = c->h_el1y;
+    c->n_int = c->n_bnd = 0;
     for (auto& v : c->h_el1x) v = c->h_perm1[v];
     for (auto& v : c->h_el1y) v = c->h_perm1[v];
     if ((rc = build_neighbours(c))) return rc;
@@ -893,6 +929,39 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
     CUDA_OK(c->d_node_q.upload(c->h_node_q));
     c->have_topo = true;
     c->have_geom = false;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_ghosts(mimsem_gpu_ctx* c, int n1_owned, int n2_owned, int out_counts[2]) {
+    if (!c || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    if (n1_owned < 0 || n1_owned > c->n1 || n2_owned < 0 || n2_owned > c->n2) return fail(MIMSEM_ERR_ARG, "bad owned counts");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const int P = c->p, N1E = P * (P + 1), N2E = P * P;
+    auto reads_ghost = [&](int e) {
+        for (int j = 0; j < N1E; j++)
+            if (c->h_el1x_ext[(size_t)e * N1E + j] >= n1_owned || c->h_el1y_ext[(size_t)e * N1E + j] >= n1_owned) return true;
+        for (int j = 0; j < N2E; j++)
+            if (c->h_el2[(size_t)e * N2E + j] >= n2_owned) return true;
+        return false;
+    };
+    std::vector<int> in, bd;
+    for (int e = 0; e < c->nel_owned; e++) {
+        bool g = reads_ghost(e);
+        for (int s = 0; s < 2 && !g; s++) {
+            const int nb = c->h_nbr[(size_t)e * 2 + s];
+            if (nb >= 0) g = reads_ghost(nb & 0x1fffffff);
+        }
+        (g ? bd : in).push_back(e);
+    }
+    c->n_int = (int)in.size();
+    c->n_bnd = (int)bd.size();
+    CUDA_OK(c->d_elist_int.upload(in));
+    CUDA_OK(c->d_elist_bnd.upload(bd));
+    if (out_counts) {
+        out_counts[0] = c->n_int;
+        out_counts[1] = c->n_bnd;
+    }
     return MIMSEM_OK;
 }
 

@@ -27,6 +27,7 @@ struct KArgs {
     const int* elq;
     const int* nbr;               // [nel][2] west / south neighbour: elem | side<<29 | rev<<30, or -1
     const unsigned char* eflags;  // [nel] bit0: write east side, bit1: write north side (partial-sum mode)
+    const int* elist;             // optional element subset (interior / boundary); nullptr: elements 0..nel-1
     // line-task tables (transposed copies so that one GLL line is contiguous)
     const int* el1xT;             // [nel][ix][iy]  x-normal edges, column-major
     const int* elqT;              // [nel][qx][qy]  quadrature points, column-major
@@ -160,6 +161,7 @@ struct TArgs {
     int geo_doubles;
     int debug;        // bit0: skip the arithmetic (data-movement-only timing experiment, MIMSEM_DEBUG=1)
     double scale;
+    const int* elist;         // optional element subset; nullptr: element = blockIdx.x
     const TileHdr* hdr;
     const CopyEnt* cps;
     const int* st_ptr;        // [nel+1]

@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs 
     using D = ElDim<P>;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
-    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
     const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (a.elist) e = a.elist[e];
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     double* __restrict__ y = a.y + k;
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(128) k_apply_m1_lines(const __grid_constant__ 
     if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
     int e = (int)fastdiv(idx, a.div_m, a.div_s);
     const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (!FAR && a.elist) e = a.elist[e];
     const size_t ld = a.ld;
     double* __restrict__ y = a.y + k;
     double out[P];
@@ -383,8 +385,9 @@ __global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs 
     using D = ElDim<P>;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
-    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
     const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (a.elist) e = a.elist[e];
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     double* __restrict__ y = a.y + k;
@@ -456,8 +459,9 @@ __global__ void __launch_bounds__(128) k_apply_k(const __grid_constant__ KArgs a
     using D = ElDim<P>;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
-    const int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
     const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (a.elist) e = a.elist[e];
     const size_t ld = a.ld;
     const double* __restrict__ x = a.x + k;
     const double* __restrict__ u = a.c + k;

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* geo = reinterpret_cast<double*>(smem_raw + 16);
     double* tile = geo + S::GEO;
-    const int e = blockIdx.x;
+    const int e = a.elist ? a.elist[blockIdx.x] : (int)blockIdx.x;
     const int part = threadIdx.x >> 6;
     const int k = threadIdx.x & 63;
     const int nl = NL ? NL : a.nlev;

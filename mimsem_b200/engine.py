@@ -9,6 +9,8 @@ from .mesh import Basis
 
 OPS = dict(M1=0, M2=1, M0=2, M1h=3, K=4, M2h=5, M0h=6, E10=10, E01=11, E21=12, E12=13)
 FIXED_LEVEL = 1
+SUBSET_INTERIOR = 2
+SUBSET_BOUNDARY = 4
 
 
 def _np_ptr(a, t):
@@ -73,6 +75,12 @@ class Engine:
                                          *[_np_ptr(a, _ip) for a in arrs]))
         self.n0, self.n1, self.n2, self.nq = n0, n1, n2, nq
         self.nel_total, self.nel_owned = nel_total, nel_owned
+
+    def set_ghosts(self, n1_owned, n2_owned):
+        """rows >= n*_owned (caller numbering) are ghosts; returns (n_interior, n_boundary) owned elements."""
+        cnt = np.zeros(2, dtype=np.int32)
+        check(self.L.mimsem_gpu_set_ghosts(self._h, n1_owned, n2_owned, _np_ptr(cnt, _ip)))
+        return int(cnt[0]), int(cnt[1])
 
     def set_geom(self, J, det):
         J = np.ascontiguousarray(J, dtype=np.float64)
@@ -164,6 +172,18 @@ class Engine:
         else:
             check(L.mimsem_gpu_apply_incidence(h, OPS[op] - 10, nlev, nlev, xp, yp, st))
         return out
+
+    def capture(self, op, x, coeff=None, out=None, **kw):
+        """Capture one apply into a CUDA graph; returns (replay, out)."""
+        torch = self.torch
+        if out is None:
+            out = self.empty(self.space_sizes(op)[1], x.shape[1])
+        self.apply(op, x, coeff=coeff, out=out, **kw)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.apply(op, x, coeff=coeff, out=out, **kw)
+        return graph.replay, out
 
     # ---------------------------------------------------------------- end to end with host buffers
     def apply_host(self, op, x, coeff=None, lev0=0, scale=1.0, tpow=0, flags=0, out=None):

@@ -16,7 +16,7 @@ touches the GPU.
 """
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, SUBSET_BOUNDARY, SUBSET_INTERIOR
 from .mesh import Basis
 
 
@@ -164,6 +164,7 @@ class DistributedEngine:
         eng = Engine(device)
         eng.set_basis(Basis(mesh.p, mesh.m))
         eng.set_topo(P.el0, P.el1x, P.el1y, P.el2, P.elq, P.n0, P.n1, P.n2, P.nq, nel_owned=P.nel_owned, mode=0)
+        self.n_interior, self.n_boundary = eng.set_ghosts(P.n1_owned, P.n2_owned)
         eng.set_geom(mesh.J[P.elements], mesh.det[P.elements])
         if thick is not None:
             eng.set_thickness(np.ascontiguousarray(thick[:, P.gq]))
@@ -183,6 +184,8 @@ class DistributedEngine:
                 plan.append((q, srows, rrows))
             self.plan[space] = plan
         self._bufs = {}
+        self.comm_stream = torch.cuda.Stream(device=device)
+        self.overlap = True
 
     # sizes / plumbing shared with Engine
     def space_sizes(self, op):
@@ -224,15 +227,66 @@ class DistributedEngine:
             self._bufs[key] = b
         return b[:n]
 
-    def apply(self, op, x, coeff=None, out=None, exchange=True, **kw):
+    # which inputs of an operator are read through ghost rows at all (2-forms are element-local)
+    NEEDS = {"M1": (True, False), "M1h": (True, True), "M2": (False, False), "M2h": (False, False), "K": (True, True),
+             "E21": (True, False), "E12": (True, False)}
+
+    def apply(self, op, x, coeff=None, out=None, exchange=True, flags=0, **kw):
+        """Ghost refresh of the inputs + local apply.  For the element kernels the refresh runs on a side stream
+        while the interior elements (no ghost reads) are computed; boundary elements follow once it has landed."""
         if op not in self.SUPPORTED:
             raise NotImplementedError("operator %s is not partitioned yet (0-form operators need node ownership)" % op)
+        torch = self.torch
         sin, sout, sc = self.engine.SPACES[op]
-        if exchange:
-            self.exchange(x, sin)
-            if coeff is not None:
+        need_x, need_c = self.NEEDS[op]
+        do_x = exchange and need_x
+        do_c = exchange and need_c and coeff is not None
+        if out is None:
+            out = self.engine.zeros(self.engine.space_sizes(op)[1], x.shape[1])
+        if not (do_x or do_c):
+            return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
+        overlap = self.overlap and op in ("M1", "M1h", "K") and self.n_interior > 0
+        if not overlap:
+            if do_x:
+                self.exchange(x, sin)
+            if do_c:
                 self.exchange(coeff, sc)
-        return self.engine.apply(op, x, coeff=coeff, out=out, **kw)
+            return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            if do_x:
+                self.exchange(x, sin)
+            if do_c:
+                self.exchange(coeff, sc)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_INTERIOR, **kw)
+        main.wait_event(done)
+        self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_BOUNDARY, **kw)
+        return out
+
+    def capture(self, op, x, coeff=None, out=None, **kw):
+        """Capture one full step (pack, NCCL ghost refresh, unpack, interior and boundary kernels) into a CUDA
+        graph -- the launch-bound inner loop of a time step -- and return (replay, out).  All ranks must capture
+        and replay the same sequence."""
+        torch = self.torch
+        if out is None:
+            out = self.engine.zeros(self.engine.space_sizes(op)[1], x.shape[1])
+        # warm up outside the capture (allocates the pack buffers, creates NCCL channels)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.apply(op, x, coeff=coeff, out=out, **kw)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.apply(op, x, coeff=coeff, out=out, **kw)
+        return graph.replay, out
 
     # test / IO helpers ------------------------------------------------------------------
     def scatter_from_global(self, levels_global, space):
