@@ -329,6 +329,86 @@ void sphere_jacobian(const double* const c[4], double lon, double lat, double x1
 
 }  // namespace
 
+void patch_geometry(MeshKind kind, int m, int nelx, int ne_side, double radius, double lx, bool signed_det,
+                    std::vector<double>& xl, std::vector<double>& J, std::vector<double>& det, std::vector<double>* lonlat_out) {
+    const int mp1 = m + 1, nqe = mp1 * mp1;
+    const size_t nel = (size_t)nelx * nelx;
+    J.assign(nel * nqe * 4, 0.0);
+    det.assign(nel * nqe, 0.0);
+    if (kind == MESH_BOX) {
+        // box/Geom.cpp:132-143: constant diagonal Jacobian, half an element width
+        const double h = 0.5 * lx / ne_side;
+        for (size_t e = 0; e < nel; e++)
+            for (int k = 0; k < nqe; k++) {
+                double* Jq = &J[(e * nqe + k) * 4];
+                Jq[0] = h; Jq[1] = 0.0; Jq[2] = 0.0; Jq[3] = h;
+                det[e * nqe + k] = std::fabs(h * h);
+            }
+        return;
+    }
+    std::vector<double> qx, qw;
+    gll_rule(m, qx, qw);
+    // Sphere.  The reference keeps, per rank, a private copy of its quadrature points' coordinates,
+    // re-projects every non-corner point of every element from the element's corners
+    // (eul/Geom.cpp:682-724; element loop order ey, ex; shared points keep the last writer's value)
+    // and only then evaluates the Jacobians (eul/Geom.cpp:726-741).
+    const int nxq = m * nelx, nq1 = nxq + 1;
+    std::vector<double> lon((size_t)nq1 * nq1), lat((size_t)nq1 * nq1);
+    for (int i = 0; i < nq1 * nq1; i++) {
+        lon[i] = std::atan2(xl[(size_t)i * 3 + 1], xl[(size_t)i * 3 + 0]);
+        lat[i] = std::asin(xl[(size_t)i * 3 + 2] / radius);
+    }
+    auto corner_ids = [&](int ex, int ey, int* id) {
+        id[0] = (ey * m) * nq1 + ex * m;
+        id[1] = (ey * m) * nq1 + ex * m + m;
+        id[2] = (ey * m + m) * nq1 + ex * m + m;
+        id[3] = (ey * m + m) * nq1 + ex * m;
+    };
+    for (int ey = 0; ey < nelx; ey++)
+        for (int ex = 0; ex < nelx; ex++) {
+            int id[4];
+            corner_ids(ex, ey, id);
+            const double* c[4] = {&xl[(size_t)id[0] * 3], &xl[(size_t)id[1] * 3], &xl[(size_t)id[2] * 3], &xl[(size_t)id[3] * 3]};
+            for (int qy = 0; qy <= m; qy++)
+                for (int qxi = 0; qxi <= m; qxi++) {
+                    if ((qxi == 0 || qxi == m) && (qy == 0 || qy == m)) continue;
+                    const double x1 = qx[qxi], x2 = qx[qy];
+                    const double wgt[4] = {(1.0 - x1) * (1.0 - x2), (1.0 + x1) * (1.0 - x2), (1.0 + x1) * (1.0 + x2),
+                                           (1.0 - x1) * (1.0 + x2)};
+                    double r[3];
+                    for (int a = 0; a < 3; a++)
+                        r[a] = 0.25 * (wgt[0] * c[0][a] + wgt[1] * c[1][a] + wgt[2] * c[2][a] + wgt[3] * c[3][a]);
+                    const double mag = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                    const int k = (ey * m + qy) * nq1 + ex * m + qxi;
+                    for (int a = 0; a < 3; a++) xl[(size_t)k * 3 + a] = radius * r[a] / mag;
+                    lon[k] = std::atan2(xl[(size_t)k * 3 + 1], xl[(size_t)k * 3 + 0]);
+                    lat[k] = std::asin(xl[(size_t)k * 3 + 2] / radius);
+                }
+        }
+    for (int ey = 0; ey < nelx; ey++)
+        for (int ex = 0; ex < nelx; ex++) {
+            const size_t e = (size_t)ey * nelx + ex;
+            int id[4];
+            corner_ids(ex, ey, id);
+            const double* c[4] = {&xl[(size_t)id[0] * 3], &xl[(size_t)id[1] * 3], &xl[(size_t)id[2] * 3], &xl[(size_t)id[3] * 3]};
+            for (int qy = 0; qy <= m; qy++)
+                for (int qxi = 0; qxi <= m; qxi++) {
+                    const int k = (ey * m + qy) * nq1 + ex * m + qxi;
+                    double* Jq = &J[(e * nqe + qy * mp1 + qxi) * 4];
+                    sphere_jacobian(c, lon[k], lat[k], qx[qxi], qx[qy], radius, Jq);
+                    const double d = Jq[0] * Jq[3] - Jq[1] * Jq[2];
+                    det[e * nqe + qy * mp1 + qxi] = signed_det ? d : std::fabs(d);
+                }
+        }
+    if (lonlat_out) {
+        lonlat_out->resize((size_t)nq1 * nq1 * 2);
+        for (int i = 0; i < nq1 * nq1; i++) {
+            (*lonlat_out)[(size_t)i * 2] = lon[i];
+            (*lonlat_out)[(size_t)i * 2 + 1] = lat[i];
+        }
+    }
+}
+
 bool build_global_mesh(MeshKind kind, int p, int m, int ne, bool signed_det, GlobalMesh& g, std::string* err) {
     const int nfaces = (kind == MESH_SPHERE) ? 6 : 1;
     const int nprocs = nfaces;   // canonical numbering: one patch per face
@@ -389,74 +469,14 @@ bool build_global_mesh(MeshKind kind, int p, int m, int ne, bool signed_det, Glo
                         g.elq[e * nqe + iy * mp1 + ix] = q.loc0[(ey * m + iy) * (nxq + 1) + ex * m + ix];
             }
 
-        if (kind == MESH_BOX) {
-            // box/Geom.cpp:132-143: constant diagonal Jacobian, half an element width
-            const double h = 0.5 * g.lx / ne;
-            for (size_t e = 0; e < (size_t)ne * ne; e++)
-                for (int k = 0; k < nqe; k++) {
-                    double* J = &g.J[(e * nqe + k) * 4];
-                    J[0] = h; J[1] = 0.0; J[2] = 0.0; J[3] = h;
-                    g.det[e * nqe + k] = std::fabs(h * h);
-                }
-            continue;
-        }
-
-        // Sphere.  The reference keeps, per rank, a private copy of its quadrature points'
-        // coordinates, re-projects every non-corner point of every element from the element's
-        // corners (eul/Geom.cpp:682-724; element loop order ey, ex; shared points keep the last
-        // writer's value) and only then evaluates the Jacobians (eul/Geom.cpp:726-741).
-        const int nq1 = nxq + 1;
-        std::vector<double> xl((size_t)nq1 * nq1 * 3), lon((size_t)nq1 * nq1), lat((size_t)nq1 * nq1);
-        for (int i = 0; i < nq1 * nq1; i++) {
-            const double* c = &g.xyz[(size_t)q.loc0[i] * 3];
-            xl[(size_t)i * 3 + 0] = c[0];
-            xl[(size_t)i * 3 + 1] = c[1];
-            xl[(size_t)i * 3 + 2] = c[2];
-            lon[i] = std::atan2(c[1], c[0]);
-            lat[i] = std::asin(c[2] / g.radius);
-        }
-        auto corner_ids = [&](int ex, int ey, int* id) {
-            id[0] = (ey * m) * nq1 + ex * m;
-            id[1] = (ey * m) * nq1 + ex * m + m;
-            id[2] = (ey * m + m) * nq1 + ex * m + m;
-            id[3] = (ey * m + m) * nq1 + ex * m;
-        };
-        for (int ey = 0; ey < ne; ey++)
-            for (int ex = 0; ex < ne; ex++) {
-                int id[4];
-                corner_ids(ex, ey, id);
-                const double* c[4] = {&xl[(size_t)id[0] * 3], &xl[(size_t)id[1] * 3], &xl[(size_t)id[2] * 3], &xl[(size_t)id[3] * 3]};
-                for (int qy = 0; qy <= m; qy++)
-                    for (int qxi = 0; qxi <= m; qxi++) {
-                        if ((qxi == 0 || qxi == m) && (qy == 0 || qy == m)) continue;
-                        const double x1 = qx[qxi], x2 = qx[qy];
-                        const double wgt[4] = {(1.0 - x1) * (1.0 - x2), (1.0 + x1) * (1.0 - x2), (1.0 + x1) * (1.0 + x2),
-                                               (1.0 - x1) * (1.0 + x2)};
-                        double r[3];
-                        for (int a = 0; a < 3; a++)
-                            r[a] = 0.25 * (wgt[0] * c[0][a] + wgt[1] * c[1][a] + wgt[2] * c[2][a] + wgt[3] * c[3][a]);
-                        const double mag = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-                        const int k = (ey * m + qy) * nq1 + ex * m + qxi;
-                        for (int a = 0; a < 3; a++) xl[(size_t)k * 3 + a] = g.radius * r[a] / mag;
-                        lon[k] = std::atan2(xl[(size_t)k * 3 + 1], xl[(size_t)k * 3 + 0]);
-                        lat[k] = std::asin(xl[(size_t)k * 3 + 2] / g.radius);
-                    }
-            }
-        for (int ey = 0; ey < ne; ey++)
-            for (int ex = 0; ex < ne; ex++) {
-                const size_t e = (size_t)f * ne * ne + (size_t)ey * ne + ex;
-                int id[4];
-                corner_ids(ex, ey, id);
-                const double* c[4] = {&xl[(size_t)id[0] * 3], &xl[(size_t)id[1] * 3], &xl[(size_t)id[2] * 3], &xl[(size_t)id[3] * 3]};
-                for (int qy = 0; qy <= m; qy++)
-                    for (int qxi = 0; qxi <= m; qxi++) {
-                        const int k = (ey * m + qy) * nq1 + ex * m + qxi;
-                        double* J = &g.J[(e * nqe + qy * mp1 + qxi) * 4];
-                        sphere_jacobian(c, lon[k], lat[k], qx[qxi], qx[qy], g.radius, J);
-                        const double d = J[0] * J[3] - J[1] * J[2];
-                        g.det[e * nqe + qy * mp1 + qxi] = signed_det ? d : std::fabs(d);
-                    }
-            }
+        // per-patch geometry exactly as one reference rank computes it (canonical numbering: patch == face)
+        std::vector<double> xl((size_t)(nxq + 1) * (nxq + 1) * 3), Jp, dp;
+        for (int i = 0; i < (nxq + 1) * (nxq + 1); i++)
+            for (int a = 0; a < 3; a++) xl[(size_t)i * 3 + a] = g.xyz[(size_t)q.loc0[i] * 3 + a];
+        patch_geometry(kind, m, ne, ne, g.radius, g.lx, signed_det, xl, Jp, dp, NULL);
+        const size_t e0 = (size_t)f * ne * ne;
+        std::copy(Jp.begin(), Jp.end(), g.J.begin() + e0 * nqe * 4);
+        std::copy(dp.begin(), dp.end(), g.det.begin() + e0 * nqe);
     }
     return true;
 }

@@ -57,6 +57,13 @@ struct GlobalMesh {
 
 bool build_global_mesh(MeshKind kind, int p, int m, int ne, bool signed_det, GlobalMesh& out, std::string* err);
 
+// Geometry of one reference rank's patch from the coordinates of its quadrature points (what Geom reads from
+// geom_RRRR.txt, local row-major (m*nelx+1)^2 grid): the per-element re-projection of eul/Geom.cpp:682-724 (xl is
+// updated in place, like Geom::x) followed by the Jacobians of eul/Geom.cpp:245-326 (box: box/Geom.cpp:132-143,
+// ne_side = elements per box side).  J[nel][(m+1)^2][4], det[nel][(m+1)^2], optional (lon, lat) per point.
+void patch_geometry(MeshKind kind, int m, int nelx, int ne_side, double radius, double lx, bool signed_det,
+                    std::vector<double>& xl, std::vector<double>& J, std::vector<double>& det, std::vector<double>* lonlat_out);
+
 // Node coordinates in global numbering, restating scr/Geom2.py:10-277 / scr/GeomBox.py:9-74.
 void sphere_node_coords(int order, int ne, double radius, std::vector<double>& xyz);
 void box_node_coords(int order, int ne, double lx, std::vector<double>& xyz);

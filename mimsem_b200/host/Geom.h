@@ -1,0 +1,57 @@
+// Host mirror of the reference's Geom (eul/Geom.h:1-56): coordinates, Jacobians, determinants, layer
+// thicknesses and the DOF -> quadrature-point interpolations, with the reference's member names.
+// Field writers (write0/1/2, HDF5) are outside the hot path and not provided.
+#ifndef MIMSEM_HOST_GEOM_H
+#define MIMSEM_HOST_GEOM_H
+
+#include "Basis.h"
+#include "Topo.h"
+
+typedef double(TopogFunc)(double* xi);
+typedef double(LevelFunc)(double* xi, int ki);
+
+class Geom {
+    public:
+        Geom(Topo* _topo, int _nk);          // eul/, box/
+        Geom(Topo* _topo);                   // src/  (signed determinant, no levels)
+        ~Geom();
+        int pi;
+        int nl;            // number of local quadrature points
+        int nk;
+        int nDofsX;        // quadrature points per patch side - 1
+        int nDofs0G;
+        int n0, n0l;
+        int* loc0;         // global ids of the local quadrature points (quads_RRRR.txt)
+        int* inds0_l;
+        int* inds0_g;
+        double** x;        // [nl][3]
+        double** s;        // [nl][2]  (lon, lat)
+        double** det;      // [nel][mp12]
+        double**** J;      // [nel][mp12][2][2]
+        double* topog;
+        double** levs;     // [nk+1][n0]
+        double** thick;    // [nk][n0]
+        double** thickInv; // [nk][n0]
+        Topo* topo;
+        GaussLobatto* quad;
+        LagrangeNode* node;
+        LagrangeEdge* edge;
+        void interp0(int ex, int ey, int px, int py, double* vec, double* val);
+        void interp1_l(int ex, int ey, int px, int py, double* vec, double* val);
+        void interp2_l(int ex, int ey, int px, int py, double* vec, double* val);
+        void interp1_g(int ex, int ey, int px, int py, double* vec, double* val);
+        void interp2_g(int ex, int ey, int px, int py, double* vec, double* val);
+        void initTopog(TopogFunc* ft, LevelFunc* fl);
+        int* elInds0_l(int ex, int ey);
+        int* elInds0_g(int ex, int ey);
+        // flat copies for the device engine
+        const double* flatJ() const { return Jflat; }
+        const double* flatDet() const { return detflat; }
+        unsigned long thick_version;   // bumped by initTopog so that operators re-upload the table
+    private:
+        void build(bool signed_det);
+        double* Jflat;
+        double* detflat;
+};
+
+#endif

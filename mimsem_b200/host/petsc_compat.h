@@ -1,0 +1,73 @@
+// Minimal PETSc / MPI compatibility layer for building the host classes WITHOUT PETSc.
+//
+// When PETSc is available, compile with -DMIMSEM_HAVE_PETSC: this header then just includes <petsc.h>
+// and the adaptor uses the real MATSHELL / Vec / VecScatter.  Otherwise the subset below provides the
+// same entry points with the documented PETSc semantics for ONE process that plays R "ranks" in
+// lockstep phases (the current rank is set with PetscCompatSetRank): the k-th VecCreateMPI call of
+// every rank refers to the same global vector, exactly as a collective call does under MPI.
+// This is product code (the host mirror needs *a* PETSc to compile against); it is independent of the
+// oracle's shim under oracle/shim/, which exists to compile the reference's sources.
+#ifndef MIMSEM_PETSC_COMPAT_H
+#define MIMSEM_PETSC_COMPAT_H
+
+#ifdef MIMSEM_HAVE_PETSC
+#include <petsc.h>
+#else
+
+#include <stddef.h>
+
+typedef double PetscScalar;
+typedef double PetscReal;
+typedef int PetscInt;
+typedef int PetscErrorCode;
+typedef int MPI_Comm;
+#define MPI_COMM_WORLD 1
+#define MPI_COMM_SELF 2
+#define PETSC_NULL NULL
+#define PETSC_DECIDE (-1)
+
+typedef enum { NOT_SET_VALUES = 0, INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
+typedef enum { SCATTER_FORWARD = 0, SCATTER_REVERSE = 1 } ScatterMode;
+typedef enum { PETSC_COPY_VALUES = 0, PETSC_OWN_POINTER = 1, PETSC_USE_POINTER = 2 } PetscCopyMode;
+typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_DESTROY = 60 } MatOperation;
+
+typedef struct _mimsem_Vec* Vec;
+typedef struct _mimsem_Mat* Mat;
+typedef struct _mimsem_IS* IS;
+typedef struct _mimsem_VecScatter* VecScatter;
+
+/* which of the R in-process ranks is executing (compat only) */
+void PetscCompatSetRank(int rank, int size);
+/* forget every global vector (between independent tests) */
+void PetscCompatReset(void);
+
+int MPI_Comm_rank(MPI_Comm comm, int* rank);
+int MPI_Comm_size(MPI_Comm comm, int* size);
+
+PetscErrorCode ISCreateGeneral(MPI_Comm comm, PetscInt n, const PetscInt idx[], PetscCopyMode mode, IS* is);
+PetscErrorCode ISCreateStride(MPI_Comm comm, PetscInt n, PetscInt first, PetscInt step, IS* is);
+PetscErrorCode ISDestroy(IS* is);
+
+PetscErrorCode VecCreateSeq(MPI_Comm comm, PetscInt n, Vec* v);
+PetscErrorCode VecCreateMPI(MPI_Comm comm, PetscInt n, PetscInt N, Vec* v);
+PetscErrorCode VecDestroy(Vec* v);
+PetscErrorCode VecZeroEntries(Vec v);
+PetscErrorCode VecGetArray(Vec v, PetscScalar** a);         /* the rank's owned slice */
+PetscErrorCode VecRestoreArray(Vec v, PetscScalar** a);
+PetscErrorCode VecGetLocalSize(Vec v, PetscInt* n);
+PetscErrorCode VecGetSize(Vec v, PetscInt* N);
+PetscErrorCode VecGetOwnershipRange(Vec v, PetscInt* lo, PetscInt* hi);
+
+PetscErrorCode VecScatterCreate(Vec x, IS ix, Vec y, IS iy, VecScatter* sc);
+PetscErrorCode VecScatterBegin(VecScatter sc, Vec x, Vec y, InsertMode addv, ScatterMode mode);
+PetscErrorCode VecScatterEnd(VecScatter sc, Vec x, Vec y, InsertMode addv, ScatterMode mode);
+PetscErrorCode VecScatterDestroy(VecScatter* sc);
+
+PetscErrorCode MatCreateShell(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt M, PetscInt N, void* ctx, Mat* A);
+PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void));
+PetscErrorCode MatShellGetContext(Mat A, void* ctx);
+PetscErrorCode MatMult(Mat A, Vec x, Vec y);
+PetscErrorCode MatDestroy(Mat* A);
+
+#endif /* MIMSEM_HAVE_PETSC */
+#endif
