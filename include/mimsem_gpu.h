@@ -197,6 +197,28 @@ int mimsem_gpu_gather_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld,
 int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld, const int* d_rows, const double* d_packed,
                             double* d_field, void* stream);
 
+/*
+ * Peer-to-peer ghost refresh over NVLink, without NCCL on the data path (the kernel is fused with its collective:
+ * the push kernel stores into the peer's memory).  Buffers that peers write into are allocated with
+ * mimsem_gpu_ipc_alloc (cudaMalloc + IPC handle, 64 bytes, to be exchanged by the caller's process-group plumbing)
+ * and mapped on the peers with mimsem_gpu_ipc_open.  d_peers is a device array of `npeers` records
+ *   { const int* rows; int nrows; int pad; double* inbox; long long inbox_parity_stride;
+ *     unsigned long long* signal; const unsigned long long* wait; }                        (48 bytes each)
+ * push: rows = owned rows to send, inbox/signal = the PEER's inbox region and flag for this rank, wait = the ack
+ *       the peer writes into this rank's memory;
+ * pull: rows = ghost rows to fill, inbox/wait = this rank's inbox region and flag for the peer, signal = the ack
+ *       on the peer.  d_epoch is a device counter, one for the pushes and one for the pulls of a space, advanced by
+ *       every call, so a captured CUDA graph can be replayed and several fields can be in flight;
+ * d_err is set to 1 if a peer never answered (the kernels give up after ~2 s instead of hanging the GPU).
+ */
+int mimsem_gpu_ipc_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** d_ptr, unsigned char handle[64]);
+int mimsem_gpu_ipc_open(mimsem_gpu_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int mimsem_gpu_ipc_close(mimsem_gpu_ctx* ctx, void* d_ptr, int owned);
+int mimsem_gpu_halo_push(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, const double* d_field,
+                         void* d_epoch, int* d_err, void* stream);
+int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, double* d_field, void* d_epoch,
+                         int* d_err, void* stream);
+
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
 

@@ -98,6 +98,7 @@ struct mimsem_gpu_ctx {
     HostCsr csr[4];
     DevEll ell[4];
 
+    DevBuf<unsigned> d_halo_counters;   // [2][64] finished-CTA counters of the p2p halo kernels (push, pull)
     // staging for the host-buffer entry point
     DevBuf<double> s_lev, s_x, s_y, s_c;
     cudaStream_t stream = nullptr;
@@ -1202,6 +1203,78 @@ int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* c, int64_t nrows, int nlev, int ld, 
     const FastDiv fd = make_fastdiv((unsigned)nlev);
     k_rows<false><<<grid_for(nrows * nlev, 256), 256, 0, (cudaStream_t)stream>>>(nrows, nlev, ld, fd.m, fd.s, d_rows, d_packed, d_field);
     return finish_launch(c, "scatter_rows");
+}
+
+int mimsem_gpu_ipc_alloc(mimsem_gpu_ctx* c, int64_t bytes, void** d_ptr, unsigned char handle[64]) {
+    if (!c || !d_ptr || !handle || bytes < 1) return fail(MIMSEM_ERR_ARG, "bad argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaMalloc(d_ptr, (size_t)bytes));
+    CUDA_OK(cudaMemset(*d_ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, *d_ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle, &h, 64);
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_ipc_open(mimsem_gpu_ctx* c, const unsigned char handle[64], void** d_ptr) {
+    if (!c || !d_ptr || !handle) return fail(MIMSEM_ERR_ARG, "bad argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    CUDA_OK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_ipc_close(mimsem_gpu_ctx* c, void* d_ptr, int owned) {
+    if (!c || !d_ptr) return MIMSEM_OK;
+    cudaSetDevice(c->device);
+    if (owned) cudaFree(d_ptr);
+    else cudaIpcCloseMemHandle(d_ptr);
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_halo_push(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, const double* d_field,
+                         void* d_epoch, int* d_err, void* stream) {
+    if (!c || !d_epoch || (npeers > 0 && (!d_peers || !d_field || !d_err))) return fail(MIMSEM_ERR_ARG, "null argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    if (npeers > 64) return fail(MIMSEM_ERR_ARG, "at most 64 halo peers");
+    if (!c->d_halo_counters.p) {
+        CUDA_OK(c->d_halo_counters.resize(256));
+        CUDA_OK(cudaMemset(c->d_halo_counters.p, 0, 256 * sizeof(unsigned)));
+    }
+    if (npeers > 0) {
+        k_halo<true><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld,
+                                                                             const_cast<double*>(d_field),
+                                                                             (const unsigned long long*)d_epoch,
+                                                                             c->d_halo_counters.p + (((uintptr_t)d_epoch >> 3) & 1) * 128, d_err);
+        if ((rc = finish_launch(c, "halo_push"))) return rc;
+    }
+    k_epoch_inc<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_epoch);
+    return finish_launch(c, "halo epoch");
+}
+
+int mimsem_gpu_halo_pull(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, double* d_field, void* d_epoch,
+                         int* d_err, void* stream) {
+    if (!c || !d_epoch || (npeers > 0 && (!d_peers || !d_field || !d_err))) return fail(MIMSEM_ERR_ARG, "null argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    if (npeers > 64) return fail(MIMSEM_ERR_ARG, "at most 64 halo peers");
+    if (!c->d_halo_counters.p) {
+        CUDA_OK(c->d_halo_counters.resize(256));
+        CUDA_OK(cudaMemset(c->d_halo_counters.p, 0, 256 * sizeof(unsigned)));
+    }
+    if (npeers > 0) {
+        k_halo<false><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld, d_field,
+                                                                              (const unsigned long long*)d_epoch,
+                                                                              c->d_halo_counters.p + 64 + (((uintptr_t)d_epoch >> 3) & 1) * 128, d_err);
+        if ((rc = finish_launch(c, "halo_pull"))) return rc;
+    }
+    k_epoch_inc<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_epoch);
+    return finish_launch(c, "halo epoch");
 }
 
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* c) { return c ? c->launches : 0; }

@@ -64,6 +64,20 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, unsigned s) 
 }
 #endif
 
+// Peer-to-peer halo exchange (no NCCL on the data path): the sender's kernel stores its boundary rows
+// straight into the receiver's inbox over NVLink and then raises a flag there; the receiver's kernel waits on the
+// flag, scatters the inbox into its ghost rows and acknowledges.  Epoch counters live in device memory so the
+// whole step (push, interior kernel, pull, boundary kernel) replays as one CUDA graph.
+struct HaloPeer {
+    const int* rows;          // local rows to send (push) / ghost rows to fill (pull)
+    int nrows;
+    int pad;
+    double* inbox;            // push: the PEER's inbox region for me (peer address); pull: my inbox region for this peer
+    long long inbox_parity_stride;   // doubles between the two parity buffers
+    unsigned long long* signal;      // push: flag on the peer (I write) ; pull: ack on the peer (I write)
+    const unsigned long long* wait;  // push: ack from the peer (peer writes, local memory) ; pull: flag from the peer
+};
+
 // Padded ELL incidence stencil: row r has entries (col[r*width+j], sgn[r*width+j]), col = -1 pads.
 struct EllArgs {
     int64_t nrows;

@@ -589,6 +589,64 @@ __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllAr
     a.y[(size_t)r * a.ld + k] = s;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *p >= want; gives up after ~4e9 cycles (a dead peer must not hang the GPU) and records the failure
+__device__ __forceinline__ void spin_until(const unsigned long long* p, unsigned long long want, int* err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(err, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+// PUSH (HALO_NB CTAs per send peer): field rows -> the peer's inbox; the last CTA to finish raises the peer's flag
+// to the new epoch.  PULL (HALO_NB CTAs per receive peer): wait for the peer's flag, inbox -> ghost rows; the last
+// CTA acknowledges.  counters[peer] counts finished CTAs (reset by the last one).
+constexpr int HALO_NB = 96;
+template <bool PUSH>
+__global__ void __launch_bounds__(256) k_halo(const HaloPeer* __restrict__ peers, int nlev, int ld, double* field,
+                                               const unsigned long long* __restrict__ epoch, unsigned* counters, int* err) {
+    const HaloPeer p = peers[blockIdx.x];
+    const unsigned long long e = *epoch + 1;
+    double* box = p.inbox + (e & 1) * p.inbox_parity_stride;
+    if (threadIdx.x == 0) {
+        // PUSH: the receiver must have consumed the buffer of epoch e-2 (same parity) ; PULL: the data of epoch e must have landed
+        if (PUSH) {
+            if (e > 2) spin_until(p.wait, e - 2, err);
+        } else {
+            spin_until(p.wait, e, err);
+        }
+    }
+    __syncthreads();
+    const int total = p.nrows * nlev;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += gridDim.y * blockDim.x) {
+        const int r = i / nlev, k = i - r * nlev;
+        if (PUSH) box[i] = field[(size_t)p.rows[r] * ld + k];
+        else field[(size_t)p.rows[r] * ld + k] = box[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned done = atomicAdd(&counters[blockIdx.x], 1u);
+        if (done == gridDim.y - 1) {
+            counters[blockIdx.x] = 0;
+            __threadfence_system();
+            st_release_sys(p.signal, e);
+        }
+    }
+}
+__global__ void k_epoch_inc(unsigned long long* epoch) { *epoch += 1; }
+
 // Halo pack / unpack: packed[i*nlev + k] <-> field[rows[i]*ld + k]   (rows = ghost or send lists)
 template <bool GATHER>
 __global__ void __launch_bounds__(256) k_rows(int64_t nrows, int nlev, int ld, unsigned div_m, unsigned div_s,

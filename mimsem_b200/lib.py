@@ -48,6 +48,11 @@ SIGNATURES = {
     "mimsem_gpu_apply_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),
     "mimsem_gpu_gather_rows": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_scatter_rows": (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_ipc_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp), C.c_char_p]),
+    "mimsem_gpu_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "mimsem_gpu_ipc_close": (C.c_int, [_vp, _vp, C.c_int]),
+    "mimsem_gpu_halo_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_halo_pull": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
 }
 

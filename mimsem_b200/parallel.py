@@ -184,8 +184,106 @@ class DistributedEngine:
                 plan.append((q, srows, rrows))
             self.plan[space] = plan
         self._bufs = {}
-        self.comm_stream = torch.cuda.Stream(device=device)
+        self.comm_stream = torch.cuda.Stream(device=device, priority=-1)   # halo kernels get SM slots ahead of the bulk kernel
         self.overlap = True
+        self.nk_max = 1 if thick is None else int(thick.shape[0])
+        self.p2p = None
+        self.graph_safe = False
+        import os
+        if world > 1 and os.environ.get("MIMSEM_HALO", "p2p") == "p2p":
+            self._setup_p2p(P, sends)
+
+    # ---------------------------------------------------------------- peer-to-peer halo (no NCCL on the data path)
+    MAXP = 16
+
+    def _setup_p2p(self, P, sends):
+        """Allocate this rank's inbox / flag buffer, exchange IPC handles and layouts (control plane: torch.distributed
+        object collectives), map every peer's buffer and build the push / pull descriptor arrays."""
+        import ctypes as C
+        torch, dist, eng = self.torch, self.dist, self.engine
+        MAXP, nk = self.MAXP, self.nk_max
+        spaces = (1, 2)
+        recv_peers = {s: sorted(P.recv[s]) for s in spaces}
+        send_peers = {s: sorted(sends[s]) for s in spaces}
+        assert all(len(v) <= MAXP for v in list(recv_peers.values()) + list(send_peers.values()))
+        hdr_bytes = 4 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP]
+        layout = {}                                    # (space, peer) -> (slot, inbox offset in bytes, nrows)
+        off = hdr_bytes
+        for si, s in enumerate(spaces):
+            for slot, q in enumerate(recv_peers[s]):
+                n = len(P.recv[s][q]["local"])
+                layout[(s, q)] = (slot, off, n)
+                off += 2 * n * nk * 8
+        total = max(off, hdr_bytes + 16)
+        base = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        from .lib import check
+        check(eng.L.mimsem_gpu_ipc_alloc(eng._h, total, C.byref(base), handle))
+        mine = dict(handle=handle.raw, layout=layout, send_slot={(s, q): i for s in spaces for i, q in enumerate(send_peers[s])})
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        peer_base = {}
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            if any(q in recv_peers[s] or q in send_peers[s] for s in spaces):
+                ptr = C.c_void_p()
+                check(eng.L.mimsem_gpu_ipc_open(eng._h, everyone[q]["handle"], C.byref(ptr)))
+                peer_base[q] = ptr.value
+        dt = np.dtype([("rows", "<u8"), ("nrows", "<i4"), ("pad", "<i4"), ("inbox", "<u8"), ("stride", "<i8"), ("signal", "<u8"),
+                       ("wait", "<u8")])
+        assert dt.itemsize == 48
+        dev = "cuda:%d" % self.device
+        my = base.value
+        keep = []
+        plans = {}
+        for si, s in enumerate(spaces):
+            perm = eng.permutation(s).astype(np.int64)
+            push = np.zeros(len(send_peers[s]), dtype=dt)
+            for i, q in enumerate(send_peers[s]):
+                rows = torch.from_numpy(perm[sends[s][q]].astype(np.int32)).to(dev)
+                keep.append(rows)
+                slot_on_q, off_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
+                assert n_on_q == rows.numel()
+                push[i] = (rows.data_ptr(), rows.numel(), 0, peer_base[q] + off_on_q, n_on_q * nk,
+                           peer_base[q] + (si * MAXP + slot_on_q) * 8,            # flag on q
+                           my + (2 * MAXP + si * MAXP + i) * 8)                    # ack from q, in my memory
+            pull = np.zeros(len(recv_peers[s]), dtype=dt)
+            for i, q in enumerate(recv_peers[s]):
+                rows = torch.from_numpy(perm[P.recv[s][q]["local"]].astype(np.int32)).to(dev)
+                keep.append(rows)
+                slot, off_b, n = layout[(s, q)]
+                ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
+                pull[i] = (rows.data_ptr(), n, 0, my + off_b, n * nk,
+                           peer_base[q] + (2 * MAXP + si * MAXP + ack_slot_on_q) * 8,   # ack on q
+                           my + (si * MAXP + slot) * 8)                                # flag from q, in my memory
+            dpush = torch.from_numpy(push.view(np.uint8).copy()).to(dev)
+            dpull = torch.from_numpy(pull.view(np.uint8).copy()).to(dev)
+            epochs = torch.zeros(2, dtype=torch.int64, device=dev)   # [push counter, pull counter]
+            plans[s] = (len(push), dpush, len(pull), dpull, epochs)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.p2p = dict(plans=plans, err=err, keep=keep, base=base, peer_base=peer_base)
+        self.graph_safe = True
+        torch.cuda.synchronize(self.device)
+        dist.barrier()   # every inbox is allocated and zeroed before anybody pushes
+
+    def halo_error(self):
+        """True if a p2p exchange timed out waiting for a peer."""
+        return bool(self.p2p is not None and int(self.p2p["err"].item()) != 0)
+
+    def push(self, field, space):
+        npush, dpush, _, _, epochs = self.p2p["plans"][space]
+        eng = self.engine
+        from .lib import check
+        check(eng.L.mimsem_gpu_halo_push(eng._h, npush, dpush.data_ptr(), field.shape[1], field.shape[1], field.data_ptr(),
+                                         epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
+
+    def pull(self, field, space):
+        _, _, npull, dpull, epochs = self.p2p["plans"][space]
+        eng = self.engine
+        from .lib import check
+        check(eng.L.mimsem_gpu_halo_pull(eng._h, npull, dpull.data_ptr(), field.shape[1], field.shape[1], field.data_ptr(),
+                                         epochs.data_ptr() + 8, self.p2p["err"].data_ptr(), eng._stream()))
 
     # sizes / plumbing shared with Engine
     def space_sizes(self, op):
@@ -199,7 +297,13 @@ class DistributedEngine:
         return sum((0 if s is None else s.numel()) for _, s, _ in self.plan[space]) * nlev * 8
 
     def exchange(self, field, space):
-        """Ghost refresh of a local field: pack -> NCCL send/recv -> unpack."""
+        """Ghost refresh of a local field.  p2p mode: push kernel (stores into the peers' inboxes) + pull kernel;
+        otherwise pack -> NCCL send/recv -> unpack."""
+        if self.p2p is not None:
+            assert field.shape[1] <= self.nk_max
+            self.push(field, space)
+            self.pull(field, space)
+            return field
         eng, torch, dist = self.engine, self.torch, self.dist
         nlev = field.shape[1]
         st = eng._stream()
@@ -246,6 +350,29 @@ class DistributedEngine:
         if not (do_x or do_c):
             return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
         overlap = self.overlap and op in ("M1", "M1h", "K") and self.n_interior > 0
+        if overlap and self.p2p is not None:
+            # side stream: push kernels (store into the peers' inboxes over NVLink) and pull kernels (wait for the
+            # peers' flags, fill my ghost rows); main stream: interior elements meanwhile, boundary elements after
+            main = torch.cuda.current_stream(self.device)
+            side = self.comm_stream
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                if do_x:
+                    self.push(x, sin)
+                if do_c:
+                    self.push(coeff, sc)
+                if do_x:
+                    self.pull(x, sin)
+                if do_c:
+                    self.pull(coeff, sc)
+                done = torch.cuda.Event()
+                done.record(side)
+            self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_INTERIOR, **kw)
+            main.wait_event(done)
+            self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_BOUNDARY, **kw)
+            return out
         if not overlap:
             if do_x:
                 self.exchange(x, sin)

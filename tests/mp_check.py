@@ -67,6 +67,8 @@ def main():
                         failures.append((what, op, "golden", rel_l2(yg, g[key])))
         if rank == 0:
             print("case", what, kind, p, ne, nk, "world", world, "halo bytes/rank (1-form)", deng.halo_bytes(1, f["x1"].shape[0]), flush=True)
+        if deng.halo_error():
+            failures.append(("halo timeout", rank))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
