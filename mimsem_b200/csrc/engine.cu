@@ -85,9 +85,8 @@ struct mimsem_gpu_ctx {
     int m1_variant = 2;                      // 2: TMA tile kernel (default), 1: line tasks, 0: one thread per element-level
     // TMA tile plan (owner-computes mode)
     bool tma_ok = false;
-    std::vector<TileHdr> h_hdr;
-    DevBuf<TileHdr> d_hdr, d_hdr_h;
-    DevBuf<CopyEnt> d_cps, d_cps_h;
+    DevBuf<TileHdr> d_recs, d_recs_h;   // fixed-stride tile records: header + rec_ents copy entries
+    int rec_ents = 0, rec_ents_h = 0;
     DevBuf<StoreEnt> d_stores;
     DevBuf<int> d_st_ptr;
     DevBuf<double> d_geo, d_geo_h;
@@ -414,21 +413,21 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
                 for (int j = 0; j < N2E; j++) hs.push_back({c->h_el2[(size_t)nbr_el[s] * N2E + j], (s == 0 ? S::HW : S::HS) + j});
         // plain M1
         TileHdr h;
-        h.cp_begin = (int)cps.size();
+        h.st_dof = (int)cps.size();   // parked: begin of this element's entries (replaced by the store row in pack())
         h.flags = flags;
         cps.push_back(CopyEnt{3, e, 0, 1});
         const int nx = emit_runs(xs, 0, cps);
         const int nt = emit_runs(ts, 2, cps);
-        h.cp_count = (int)cps.size() - h.cp_begin;
+        h.cp_count = (int)cps.size() - h.st_dof;
         h.nslots = nx | (nt << 16);
         hdr[e] = h;
         // M1(h)
-        h.cp_begin = (int)cps_h.size();
+        h.st_dof = (int)cps_h.size();
         cps_h.push_back(CopyEnt{3, e, 0, 1});
         emit_runs(xs, 0, cps_h);
         const int nh = emit_runs(hs, 1, cps_h);
         emit_runs(ts, 2, cps_h);
-        h.cp_count = (int)cps_h.size() - h.cp_begin;
+        h.cp_count = (int)cps_h.size() - h.st_dof;
         h.nslots = (nx + nh) | (nt << 16);
         hdr_h[e] = h;
         // stores: owned block
@@ -446,11 +445,26 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         }
         st_ptr[e + 1] = (int)stores.size();
     }
-    c->h_hdr = hdr;
-    CUDA_OK(c->d_hdr.upload(hdr));
-    CUDA_OK(c->d_hdr_h.upload(hdr_h));
-    CUDA_OK(c->d_cps.upload(cps));
-    CUDA_OK(c->d_cps_h.upload(cps_h));
+    // pack into fixed-stride records
+    auto pack = [&](const std::vector<TileHdr>& hd, const std::vector<CopyEnt>& cp, int& nents, DevBuf<TileHdr>& out) -> cudaError_t {
+        nents = 1;
+        for (auto& h : hd) nents = std::max(nents, h.cp_count);
+        static_assert(sizeof(TileHdr) == 16 && sizeof(CopyEnt) == 16, "16-byte records");
+        std::vector<TileHdr> rec((size_t)hd.size() * (1 + nents));
+        std::memset(rec.data(), 0, rec.size() * sizeof(TileHdr));
+        for (size_t e = 0; e < hd.size(); e++) {
+            TileHdr h = hd[e];
+            const int begin = h.st_dof;   // cp_begin was parked here by the builder
+            // owned block contiguous in slot order?
+            h.st_dof = (st_ptr[e + 1] - st_ptr[e] == 1 && stores[st_ptr[e]].slot == 0 && stores[st_ptr[e]].count == 2 * P * P)
+                           ? stores[st_ptr[e]].dof : -1;
+            rec[e * (1 + nents)] = h;
+            std::memcpy(&rec[e * (1 + nents) + 1], &cp[begin], (size_t)h.cp_count * sizeof(CopyEnt));
+        }
+        return out.upload(rec);
+    };
+    CUDA_OK(pack(hdr, cps, c->rec_ents, c->d_recs));
+    CUDA_OK(pack(hdr_h, cps_h, c->rec_ents_h, c->d_recs_h));
     CUDA_OK(c->d_stores.upload(stores));
     CUDA_OK(c->d_st_ptr.upload(st_ptr));
     c->tma_ok = true;
@@ -582,10 +596,17 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         {
             const char* dbg = getenv("MIMSEM_DEBUG");
             t.debug = dbg ? atoi(dbg) : 0;
+            const char* pa = getenv("MIMSEM_PREFETCH");
+            t.prefetch_ahead = pa ? atoi(pa) : 592;   // ~ the number of CTAs resident on 148 SMs x 4
+            t.prefetch_own_slots = 2 * c->p * c->p;
+            const char* lo = getenv("MIMSEM_DEBUG_LO");
+            const char* hi = getenv("MIMSEM_DEBUG_HI");
+            t.debug_slot_lo = lo ? atoi(lo) : 0;
+            t.debug_slot_hi = hi ? atoi(hi) : 0;
         }
         t.elist = a.elist;
-        t.hdr = with_h ? c->d_hdr_h.p : c->d_hdr.p;
-        t.cps = with_h ? c->d_cps_h.p : c->d_cps.p;
+        t.recs = with_h ? c->d_recs_h.p : c->d_recs.p;
+        t.rec_ents = with_h ? c->rec_ents_h : c->rec_ents;
         t.st_ptr = c->d_st_ptr.p;
         t.stores = c->d_stores.p;
         t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;

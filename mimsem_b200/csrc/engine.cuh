@@ -158,8 +158,11 @@ struct CopyEnt {      // 16 bytes
     int count;        // consecutive DOFs -> consecutive slots
 };
 
+// Per-element tile record in global memory: one header followed by rec_ents copy entries (fixed stride), so
+// that lane l fetches its entry with ONE load whose address depends only on the element number.
 struct TileHdr {      // 16 bytes
-    int cp_begin, cp_count;
+    int st_dof;       // first output row of the element's owned block (-1: use the general store list)
+    int cp_count;
     int flags;        // bit0 has west nbr, bit1 west reversed, bit2 has south nbr, bit3 south reversed
     int nslots;       // slots filled by the list (for the mbarrier transaction count)
 };
@@ -173,11 +176,14 @@ struct TArgs {
     int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
     int contig_t;     // nkT == nlev
     int geo_doubles;
+    int prefetch_ahead;       // L2-prefetch the tile this many CTAs ahead (0: off)
+    int prefetch_own_slots;   // x-field slots below this number are the element's own block
+    int debug_slot_lo, debug_slot_hi;   // bit1 of debug: skip x-field copies into slots [lo, hi) (traffic experiment)
     int debug;        // bit0: skip the arithmetic (data-movement-only timing experiment, MIMSEM_DEBUG=1)
     double scale;
     const int* elist;         // optional element subset; nullptr: element = blockIdx.x
-    const TileHdr* hdr;
-    const CopyEnt* cps;
+    const TileHdr* recs;      // [nel][1 + rec_ents] 16-byte words: header, then the copy entries
+    int rec_ents;
     const int* st_ptr;        // [nel+1]
     const StoreEnt* stores;
     const double* geo;

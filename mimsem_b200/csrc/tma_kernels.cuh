@@ -44,17 +44,30 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// ask the TMA unit to pull a range into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Stage one tile: warp 0 walks the element's copy list (one entry per lane and round)
 __device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, double* geo, double* tile) {
-    const TileHdr h = a.hdr[e];
+    const TileHdr* rec = a.recs + (size_t)e * (1 + a.rec_ents);
+    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + 1);
     const int lane = threadIdx.x;
+    // header and this lane's first entry are fetched together (no dependent load on the critical path)
+    const TileHdr h = rec[0];
+    CopyEnt first = ents[lane < a.rec_ents ? lane : 0];
     const unsigned slot_bytes = (unsigned)a.nlev * 8u;
     const bool with_t = a.tpow > 0;
+    int skipped = 0;
     for (int ci = lane; ci < h.cp_count; ci += 32) {
-        const CopyEnt c = a.cps[h.cp_begin + ci];
+        const CopyEnt c = (ci == lane) ? first : ents[ci];
         if (c.kind == 2 && !with_t) continue;
+        if ((a.debug & 2) && c.kind == 0 && c.slot >= a.debug_slot_lo && c.slot < a.debug_slot_hi) {   // traffic experiment only
+            skipped += c.count;
+            continue;
+        }
         if (c.kind == 3) {
             bulk_g2s(geo, a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u, bar);
         } else if (c.kind == 2) {
@@ -72,7 +85,11 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, 
         }
     }
     // nslots = slots filled by x / coefficient entries (low 16 bits) and by thickness entries (high 16 bits)
-    const unsigned nslots = (unsigned)(h.nslots & 0xffff) + (with_t ? (unsigned)(h.nslots >> 16) : 0u);
+    unsigned nslots = (unsigned)(h.nslots & 0xffff) + (with_t ? (unsigned)(h.nslots >> 16) : 0u);
+    if (a.debug & 2) {
+        for (int o = 16; o > 0; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+        nslots -= (unsigned)skipped;
+    }
     if (lane == 0) mbar_arrive_expect_tx(bar, nslots * slot_bytes + (unsigned)a.geo_doubles * 8u);
 }
 
@@ -142,6 +159,25 @@ __device__ __forceinline__ void tile_far_line(const TArgs& a, const double* col,
 #undef SLOT
 }
 
+// L2 prefetch of the DRAM-unique part of a LATER tile (its own edge block and its thickness rows): by the time that
+// tile's CTA starts, its bulk loads hit L2, which takes the HBM latency out of the per-tile critical path.
+__device__ __forceinline__ void tile_prefetch(const TArgs& a, int e) {
+    const TileHdr* rec = a.recs + (size_t)e * (1 + a.rec_ents);
+    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + 1);
+    const TileHdr h = rec[0];
+    const int lane = threadIdx.x & 31;
+    const unsigned slot_bytes = (unsigned)a.nlev * 8u;
+    const int own_slots = a.prefetch_own_slots;
+    for (int ci = lane; ci < h.cp_count; ci += 32) {
+        const CopyEnt c = ents[ci];
+        if (c.kind == 2 && a.tpow > 0 && a.contig_t) {
+            bulk_prefetch_l2(a.tinv + (size_t)c.src * a.nkT + a.lev0, slot_bytes * c.count);
+        } else if ((c.kind == 0 && c.slot < own_slots && a.contig_x) || (c.kind == 1 && a.contig_x)) {
+            bulk_prefetch_l2((c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld, slot_bytes * c.count);
+        }
+    }
+}
+
 // y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 parts x 64 level lanes:
 // part 0 computes the element's x-normal edges (GLL columns, plus the west neighbour's far line),
 // part 1 its y-normal edges (GLL rows, plus the south neighbour's far line).  NL = compile-time
@@ -164,7 +200,12 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
     }
     __syncthreads();
     if (threadIdx.x < 32) tile_load(a, e, bar, geo, tile);
-    const int flags = a.hdr[e].flags;
+    else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && (int)blockIdx.x + a.prefetch_ahead < (int)gridDim.x) {
+        const int bn = blockIdx.x + a.prefetch_ahead;
+        tile_prefetch(a, a.elist ? a.elist[bn] : bn);
+    }
+    const TileHdr hd = a.recs[(size_t)e * (1 + a.rec_ents)];
+    const int flags = hd.flags;
     mbar_wait(bar, 0);
 
     double out[P][P];
@@ -306,30 +347,31 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
             }
         }
     }
-    __syncthreads();   // both parts have read every input slot: the own block can now be overwritten
-    if (k < nl) {
+    // Results go straight from registers to global memory (lanes = levels: coalesced 8-byte stores); the CTA
+    // can retire without a shared-memory round trip or a bulk-store wait.  Output rows come from the store list.
+    if (k < nl && !(a.debug & 4)) {
         const int base = part == 0 ? S::OX : S::OY;
+        if (hd.st_dof >= 0) {
+            // the usual case: the element's 2P^2 owned rows are one contiguous run in slot order
+            double* __restrict__ y = a.y + (size_t)(hd.st_dof + base) * a.ld + k;
 #pragma unroll
-        for (int i = 0; i < P; i++)
+            for (int i = 0; i < P; i++)
 #pragma unroll
-            for (int j = 0; j < P; j++) SLOT(base + i * P + j) = out[i][j];
+                for (int j = 0; j < P; j++) y[(size_t)(i * P + j) * a.ld] = out[i][j];
+        } else {
+            for (int si = a.st_ptr[e]; si < a.st_ptr[e + 1]; si++) {
+                const StoreEnt st = a.stores[si];
+#pragma unroll
+                for (int i = 0; i < P; i++)
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        const int slot = base + i * P + j;
+                        if (slot >= st.slot && slot < st.slot + st.count) a.y[(size_t)(st.dof + slot - st.slot) * a.ld + k] = out[i][j];
+                    }
+            }
+        }
     }
 #undef SLOT
-    fence_async_smem();
-    __syncthreads();
-    // bulk stores of the owned block
-    if (threadIdx.x < 32) {
-        const unsigned slot_bytes = (unsigned)nl * 8u;
-        for (int si = a.st_ptr[e] + (int)threadIdx.x; si < a.st_ptr[e + 1]; si += 32) {
-            const StoreEnt s = a.stores[si];
-            double* dst = a.y + (size_t)s.dof * a.ld;
-            const double* src = tile + (size_t)s.slot * nl;
-            if (a.contig_x) bulk_s2g(dst, src, slot_bytes * s.count);
-            else
-                for (int j = 0; j < s.count; j++) bulk_s2g(dst + (size_t)j * a.ld, src + (size_t)j * nl, slot_bytes);
-        }
-        bulk_commit_wait_read();
-    }
 }
 
 }  // namespace mimsem
