@@ -365,13 +365,18 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
     std::vector<CopyEnt> cps, cps_h;
     std::vector<StoreEnt> stores;
     std::vector<int> st_ptr(c->nel_owned + 1, 0);
-    auto emit_runs = [](std::vector<std::pair<int, int>>& dof_slot, int kind, std::vector<CopyEnt>& out) {
+    // bulk copies longer than max_run slots are split so that several lanes / TMA requests work on them in parallel
+    int max_run = 64;
+    if (const char* mr = getenv("MIMSEM_MAXRUN")) max_run = std::max(1, atoi(mr));
+    auto emit_runs = [max_run](std::vector<std::pair<int, int>>& dof_slot, int kind, std::vector<CopyEnt>& out) {
         // merge (dof, slot) pairs that advance together into runs
         size_t i = 0;
         int filled = 0;
         while (i < dof_slot.size()) {
             size_t j = i + 1;
-            while (j < dof_slot.size() && dof_slot[j].first == dof_slot[j - 1].first + 1 && dof_slot[j].second == dof_slot[j - 1].second + 1) j++;
+            while (j < dof_slot.size() && (int)(j - i) < max_run && dof_slot[j].first == dof_slot[j - 1].first + 1 &&
+                   dof_slot[j].second == dof_slot[j - 1].second + 1)
+                j++;
             out.push_back(CopyEnt{kind, dof_slot[i].first, dof_slot[i].second, (int)(j - i)});
             filled += (int)(j - i);
             i = j;
@@ -446,6 +451,7 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         st_ptr[e + 1] = (int)stores.size();
     }
     // pack into fixed-stride records
+    bool all_contig = true;
     auto pack = [&](const std::vector<TileHdr>& hd, const std::vector<CopyEnt>& cp, int& nents, DevBuf<TileHdr>& out) -> cudaError_t {
         nents = 1;
         for (auto& h : hd) nents = std::max(nents, h.cp_count);
@@ -458,6 +464,7 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
             // owned block contiguous in slot order?
             h.st_dof = (st_ptr[e + 1] - st_ptr[e] == 1 && stores[st_ptr[e]].slot == 0 && stores[st_ptr[e]].count == 2 * P * P)
                            ? stores[st_ptr[e]].dof : -1;
+            if (h.st_dof < 0) all_contig = false;
             rec[e * (1 + nents)] = h;
             std::memcpy(&rec[e * (1 + nents) + 1], &cp[begin], (size_t)h.cp_count * sizeof(CopyEnt));
         }
@@ -467,7 +474,7 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
     CUDA_OK(pack(hdr_h, cps_h, c->rec_ents_h, c->d_recs_h));
     CUDA_OK(c->d_stores.upload(stores));
     CUDA_OK(c->d_st_ptr.upload(st_ptr));
-    c->tma_ok = true;
+    c->tma_ok = all_contig;   // the tile kernel stores the owned block as one run of rows
     return MIMSEM_OK;
 }
 
@@ -596,8 +603,10 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         {
             const char* dbg = getenv("MIMSEM_DEBUG");
             t.debug = dbg ? atoi(dbg) : 0;
+            const char* dt = getenv("MIMSEM_DBG_TIMES");   // address of a device buffer, set by the diagnostic script
+            t.dbg_times = dt ? (long long*)strtoull(dt, NULL, 0) : NULL;
             const char* pa = getenv("MIMSEM_PREFETCH");
-            t.prefetch_ahead = pa ? atoi(pa) : 592;   // ~ the number of CTAs resident on 148 SMs x 4
+            t.prefetch_ahead = pa ? atoi(pa) : 296;   // ~ the number of CTAs resident on 148 SMs x 4
             t.prefetch_own_slots = 2 * c->p * c->p;
             const char* lo = getenv("MIMSEM_DEBUG_LO");
             const char* hi = getenv("MIMSEM_DEBUG_HI");
@@ -631,7 +640,15 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
             if (a.nel == 0) return (int)MIMSEM_OK;
-            kern<<<a.nel, 128, smem, st>>>(t);
+            // persistent grid: as many CTAs as fit (shared memory bound), each loops over tiles
+            int nsm = 148, per_sm = 1;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+            const char* pg = getenv("MIMSEM_PERSISTENT");
+            const bool persistent = pg && atoi(pg) != 0;   // measured equal to one CTA per tile on C5; off by default
+            t.ntiles = a.nel;
+            const int grid = persistent ? std::min(a.nel, nsm * std::max(per_sm, 1)) : a.nel;
+            kern<<<grid, 128, smem, st>>>(t);
             return finish_launch(c, "apply_M1 (tma)");
         });
         if (rc3 != 1) return rc3;

@@ -176,6 +176,8 @@ struct TArgs {
     int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
     int contig_t;     // nkT == nlev
     int geo_doubles;
+    long long* dbg_times;     // optional [grid][6] phase timestamps (globaltimer ns) for latency breakdowns; nullptr: off
+    int ntiles;               // tiles (elements) of this launch; the grid is persistent
     int prefetch_ahead;       // L2-prefetch the tile this many CTAs ahead (0: off)
     int prefetch_own_slots;   // x-field slots below this number are the element's own block
     int debug_slot_lo, debug_slot_hi;   // bit1 of debug: skip x-field copies into slots [lo, hi) (traffic experiment)

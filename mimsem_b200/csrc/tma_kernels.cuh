@@ -6,6 +6,12 @@
 
 namespace mimsem {
 
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_T(i) do { if (a.dbg_times && threadIdx.x == 64) a.dbg_times[(size_t)tile_i * 6 + (i)] = gtime_ns(); } while (0)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -170,7 +176,9 @@ __device__ __forceinline__ void tile_prefetch(const TArgs& a, int e) {
     const int own_slots = a.prefetch_own_slots;
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = ents[ci];
-        if (c.kind == 2 && a.tpow > 0 && a.contig_t) {
+        if (c.kind == 3) {
+            bulk_prefetch_l2(a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u);
+        } else if (c.kind == 2 && a.tpow > 0 && a.contig_t) {
             bulk_prefetch_l2(a.tinv + (size_t)c.src * a.nkT + a.lev0, slot_bytes * c.count);
         } else if ((c.kind == 0 && c.slot < own_slots && a.contig_x) || (c.kind == 1 && a.contig_x)) {
             bulk_prefetch_l2((c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld, slot_bytes * c.count);
@@ -178,19 +186,123 @@ __device__ __forceinline__ void tile_prefetch(const TArgs& a, int e) {
     }
 }
 
-// y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 parts x 64 level lanes:
-// part 0 computes the element's x-normal edges (GLL columns, plus the west neighbour's far line),
-// part 1 its y-normal edges (GLL rows, plus the south neighbour's far line).  NL = compile-time
-// number of levels (0: runtime) so that shared-memory operands use immediate offsets.
+// One warp-pair's share of an element tile: DIR 0 = x-normal edges of GLL columns [LO,HI), DIR 1 = y-normal edges of
+// GLL rows [LO,HI); HALF 0 additionally gathers the west (DIR 0) / south (DIR 1) neighbour's far line.
+template <int P, bool WITH_H, int NL, int DIR, int HALF>
+__device__ __forceinline__ void tile_compute(const TArgs& a, const double* col, const double* geo, int flags, int st_dof, int k) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1;
+    // HALF 2 = all lines of the direction (two warp-pairs per tile: the configuration that measured fastest)
+    constexpr int LO = HALF == 1 ? (P + 1) / 2 : 0;
+    constexpr int HI = HALF == 0 ? (P + 1) / 2 : P;
+    constexpr int NLN = HI - LO > 0 ? HI - LO : 1;
+    const int nl = NL ? NL : a.nlev;
+#define SLOT(s) col[(size_t)(s) * nl]
+    auto tf = [&](int q) {
+        double f = a.scale;
+        if (a.tpow > 0) {
+            const double t = SLOT(S::T + q);
+            f *= t;
+            if (a.tpow > 1) f *= t;
+        }
+        return f;
+    };
+    double cfar[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) cfar[j] = 0.0;
+    if (HALF != 1) {
+        const int has = DIR == 0 ? 1 : 4, rv = DIR == 0 ? 2 : 8, row = DIR == 0 ? 16 : 32;
+        if (flags & has) {
+            if (flags & rv) tile_far_line<P, WITH_H, DIR, true, NL>(a, col, geo, flags & row, cfar);
+            else tile_far_line<P, WITH_H, DIR, false, NL>(a, col, geo, flags & row, cfar);
+        }
+    }
+    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (DIR 0) / xx(qx=q, iy=t) (DIR 1) are read from shared memory at
+    // their point of use (keeping all (P+1)P of them in registers would halve the number of resident CTAs)
+#define OTH_SMEM(q, t) ((DIR == 0) ? ((q) < P ? SLOT(S::OY + (q) * P + (t)) : SLOT(S::YN + (t))) : ((q) < P ? SLOT(S::OX + (q) * P + (t)) : SLOT(S::XE + (t))))
+    // with two warp-pairs per tile the (P+1)P values are used P times each: keep them in registers
+    constexpr bool OTH_REGS = (HALF == 2);
+    double othr[OTH_REGS ? P + 1 : 1][OTH_REGS ? P : 1];
+    if (OTH_REGS) {
+#pragma unroll
+        for (int q = 0; q <= P; q++)
+#pragma unroll
+            for (int t = 0; t < P; t++) othr[OTH_REGS ? q : 0][OTH_REGS ? t : 0] = OTH_SMEM(q, t);
+    }
+#define OTH(q, t) (OTH_REGS ? othr[OTH_REGS ? (q) : 0][OTH_REGS ? (t) : 0] : OTH_SMEM(q, t))
+    double hc[NLN][P];   // h contracted across the line direction: hc[line][j]
+    if (WITH_H) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            double hv[P];
+#pragma unroll
+            for (int t = 0; t < P; t++) hv[t] = (DIR == 0) ? SLOT(S::H + j * P + t) : SLOT(S::H + t * P + j);   // h(ix=t,iy=j) / h(ix=j,iy=t)
+#pragma unroll
+            for (int ln = LO; ln < HI; ln++) {
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t < P; t++) s += a.E[ln * P + t] * hv[t];
+                hc[ln - LO][j] = s;
+            }
+        }
+    }
+    double out[NLN][P];
+#pragma unroll
+    for (int ln = LO; ln < HI; ln++) {
+        // edges ON the line: xx(ln, iy) (DIR 0) / xy(ix, ln) (DIR 1)
+        double own[P];
+#pragma unroll
+        for (int j = 0; j < P; j++) own[j] = SLOT((DIR == 0 ? S::OX : S::OY) + ln * P + j);
+        double f[P + 1];
+#pragma unroll
+        for (int q = 0; q <= P; q++) {
+            double ua = 0.0, ub = 0.0;   // along-line interpolation of own, across-line interpolation of oth
+#pragma unroll
+            for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
+#pragma unroll
+            for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * OTH(q, t);
+            const int qq = (DIR == 0) ? q * NP1 + ln : ln * NP1 + q;
+            double c = tf(qq);
+            if (WITH_H) {
+                double hl = 0.0;
+#pragma unroll
+                for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hc[ln - LO][j];
+                c *= hl;
+            }
+            // DIR 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; DIR 1: f1 = c (Gab ul0 + Gbb ul1), ul1 = ua
+            f[q] = (DIR == 0) ? c * (geo[qq * 3 + 0] * ua + geo[qq * 3 + 1] * ub) : c * (geo[qq * 3 + 1] * ub + geo[qq * 3 + 2] * ua);
+        }
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            double s = (ln == 0) ? cfar[j] : 0.0;
+#pragma unroll
+            for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
+            out[ln - LO][j] = s;
+        }
+    }
+    // results straight from registers to global memory (lanes = levels: coalesced 8-byte stores)
+    if (st_dof >= 0) {
+        double* __restrict__ y = a.y + (size_t)(st_dof + (DIR == 0 ? S::OX : S::OY) + LO * P) * a.ld + k;
+#pragma unroll
+        for (int i = 0; i < HI - LO; i++)
+#pragma unroll
+            for (int j = 0; j < P; j++) y[(size_t)(i * P + j) * a.ld] = out[i][j];
+    }
+#undef OTH
+#undef OTH_SMEM
+#undef SLOT
+}
+
+// y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 warp-pairs (x-normal / y-normal edges) x 64 level
+// lanes.  (A 4-warp-pair split -- direction x half of the lines -- was measured slower: 165 vs 121 us on C5.)
+// NL = compile-time number of levels (0: runtime) so that shared-memory operands use immediate offsets.
 template <int P, bool WITH_H, int NL>
 __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TArgs a) {
     using S = M1Slots<P>;
-    constexpr int NP1 = P + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* geo = reinterpret_cast<double*>(smem_raw + 16);
     double* tile = geo + S::GEO;
-    const int e = a.elist ? a.elist[blockIdx.x] : (int)blockIdx.x;
     const int part = threadIdx.x >> 6;
     const int k = threadIdx.x & 63;
     const int nl = NL ? NL : a.nlev;
@@ -199,179 +311,35 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
         fence_async_smem();
     }
     __syncthreads();
-    if (threadIdx.x < 32) tile_load(a, e, bar, geo, tile);
-    else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && (int)blockIdx.x + a.prefetch_ahead < (int)gridDim.x) {
-        const int bn = blockIdx.x + a.prefetch_ahead;
-        tile_prefetch(a, a.elist ? a.elist[bn] : bn);
-    }
-    const TileHdr hd = a.recs[(size_t)e * (1 + a.rec_ents)];
-    const int flags = hd.flags;
-    mbar_wait(bar, 0);
-
-    double out[P][P];
-    double* col = tile + k;
-#define SLOT(s) col[(size_t)(s) * nl]
-    if (a.debug & 1) {
-#pragma unroll
-        for (int i = 0; i < P; i++)
-#pragma unroll
-            for (int j = 0; j < P; j++) out[i][j] = SLOT((part == 0 ? S::OX : S::OY) + i * P + j);
-    } else if (k < nl) {
-        auto tf = [&](int q) {
-            double f = a.scale;
-            if (a.tpow > 0) {
-                const double t = SLOT(S::T + q);
-                f *= t;
-                if (a.tpow > 1) f *= t;
-            }
-            return f;
-        };
-        double cfar[P];
-#pragma unroll
-        for (int j = 0; j < P; j++) cfar[j] = 0.0;
-        if (part == 0) {
-            if (flags & 1) {
-                if (flags & 2) tile_far_line<P, WITH_H, 0, true, NL>(a, col, geo, flags & 16, cfar);
-                else tile_far_line<P, WITH_H, 0, false, NL>(a, col, geo, flags & 16, cfar);
-            }
-            // ---- x-normal edges: columns qx = 0..P-1 ----
-            double xy[P + 1][P];
-#pragma unroll
-            for (int iy = 0; iy <= P; iy++)
-#pragma unroll
-                for (int ix = 0; ix < P; ix++) xy[iy][ix] = (iy < P) ? SLOT(S::OY + iy * P + ix) : SLOT(S::YN + ix);
-            double hx[P][P];   // hx[iy][qx], qx < P
-            if (WITH_H) {
-#pragma unroll
-                for (int iy = 0; iy < P; iy++) {
-                    double hv[P];
-#pragma unroll
-                    for (int ix = 0; ix < P; ix++) hv[ix] = SLOT(S::H + iy * P + ix);
-#pragma unroll
-                    for (int qx = 0; qx < P; qx++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * hv[ix];
-                        hx[iy][qx] = s;
-                    }
-                }
-            }
-#pragma unroll
-            for (int qx = 0; qx < P; qx++) {
-                double xc[P];
-#pragma unroll
-                for (int iy = 0; iy < P; iy++) xc[iy] = SLOT(S::OX + qx * P + iy);
-                double f0[P + 1];
-#pragma unroll
-                for (int qy = 0; qy <= P; qy++) {
-                    double ul0 = 0.0, ul1 = 0.0;
-#pragma unroll
-                    for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xc[iy];
-#pragma unroll
-                    for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * xy[qy][ix];
-                    const int q = qy * NP1 + qx;
-                    double c = tf(q);
-                    if (WITH_H) {
-                        double hl = 0.0;
-#pragma unroll
-                        for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hx[iy][qx];
-                        c *= hl;
-                    }
-                    f0[qy] = c * (geo[q * 3 + 0] * ul0 + geo[q * 3 + 1] * ul1);
-                }
-#pragma unroll
-                for (int iy = 0; iy < P; iy++) {
-                    double s = (qx == 0) ? cfar[iy] : 0.0;
-#pragma unroll
-                    for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
-                    out[qx][iy] = s;   // slot OX + qx P + iy
-                }
-            }
-        } else {
-            if (flags & 4) {
-                if (flags & 8) tile_far_line<P, WITH_H, 1, true, NL>(a, col, geo, flags & 32, cfar);
-                else tile_far_line<P, WITH_H, 1, false, NL>(a, col, geo, flags & 32, cfar);
-            }
-            // ---- y-normal edges: rows qy = 0..P-1 ----
-            double xx[P][P + 1];
-#pragma unroll
-            for (int iy = 0; iy < P; iy++)
-#pragma unroll
-                for (int ix = 0; ix <= P; ix++) xx[iy][ix] = (ix < P) ? SLOT(S::OX + ix * P + iy) : SLOT(S::XE + iy);
-            double hy[P][P];   // hy[ix][qy], qy < P : h contracted in y
-            if (WITH_H) {
-#pragma unroll
-                for (int ix = 0; ix < P; ix++) {
-                    double hv[P];
-#pragma unroll
-                    for (int iy = 0; iy < P; iy++) hv[iy] = SLOT(S::H + iy * P + ix);
-#pragma unroll
-                    for (int qy = 0; qy < P; qy++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int iy = 0; iy < P; iy++) s += a.E[qy * P + iy] * hv[iy];
-                        hy[ix][qy] = s;
-                    }
-                }
-            }
-#pragma unroll
-            for (int qy = 0; qy < P; qy++) {
-                double yr[P];
-#pragma unroll
-                for (int ix = 0; ix < P; ix++) yr[ix] = SLOT(S::OY + qy * P + ix);
-                double f1[P + 1];
-#pragma unroll
-                for (int qx = 0; qx <= P; qx++) {
-                    double ul0 = 0.0, ul1 = 0.0;
-#pragma unroll
-                    for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xx[iy][qx];
-#pragma unroll
-                    for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * yr[ix];
-                    const int q = qy * NP1 + qx;
-                    double c = tf(q);
-                    if (WITH_H) {
-                        double hl = 0.0;
-#pragma unroll
-                        for (int ix = 0; ix < P; ix++) hl += a.E[qx * P + ix] * hy[ix][qy];
-                        c *= hl;
-                    }
-                    f1[qx] = c * (geo[q * 3 + 1] * ul0 + geo[q * 3 + 2] * ul1);
-                }
-#pragma unroll
-                for (int ix = 0; ix < P; ix++) {
-                    double s = (qy == 0) ? cfar[ix] : 0.0;
-#pragma unroll
-                    for (int qx = 0; qx <= P; qx++) s += a.E[qx * P + ix] * f1[qx];
-                    out[qy][ix] = s;   // slot OY + qy P + ix
-                }
+    // optionally persistent: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    unsigned phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < a.ntiles; tile_i += gridDim.x, phase ^= 1) {
+        const int e = a.elist ? a.elist[tile_i] : tile_i;
+        DBG_T(0);
+        if (threadIdx.x < 32) tile_load(a, e, bar, geo, tile);
+        else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && tile_i + a.prefetch_ahead < a.ntiles) {
+            const int bn = tile_i + a.prefetch_ahead;
+            tile_prefetch(a, a.elist ? a.elist[bn] : bn);
+        }
+        const TileHdr hd = a.recs[(size_t)e * (1 + a.rec_ents)];
+        DBG_T(1);
+        mbar_wait(bar, phase);
+        DBG_T(2);
+        if (k < nl && !(a.debug & 1)) {
+            const double* col = tile + k;
+            if (hd.st_dof < 0) {
+                // owned rows not contiguous (generic numbering): not produced by this library's own plans
+                if (threadIdx.x == 0 && blockIdx.x == 0) printf("mimsem: non-contiguous owned block is not supported by the TMA kernel\n");
+            } else if (part == 0) {
+                tile_compute<P, WITH_H, NL, 0, 2>(a, col, geo, hd.flags, hd.st_dof, k);
+            } else {
+                tile_compute<P, WITH_H, NL, 1, 2>(a, col, geo, hd.flags, hd.st_dof, k);
             }
         }
+        DBG_T(3);
+        DBG_T(4);
+        if (gridDim.x < (unsigned)a.ntiles) __syncthreads();   // persistent: the next tile's bulk loads overwrite the buffer
     }
-    // Results go straight from registers to global memory (lanes = levels: coalesced 8-byte stores); the CTA
-    // can retire without a shared-memory round trip or a bulk-store wait.  Output rows come from the store list.
-    if (k < nl && !(a.debug & 4)) {
-        const int base = part == 0 ? S::OX : S::OY;
-        if (hd.st_dof >= 0) {
-            // the usual case: the element's 2P^2 owned rows are one contiguous run in slot order
-            double* __restrict__ y = a.y + (size_t)(hd.st_dof + base) * a.ld + k;
-#pragma unroll
-            for (int i = 0; i < P; i++)
-#pragma unroll
-                for (int j = 0; j < P; j++) y[(size_t)(i * P + j) * a.ld] = out[i][j];
-        } else {
-            for (int si = a.st_ptr[e]; si < a.st_ptr[e + 1]; si++) {
-                const StoreEnt st = a.stores[si];
-#pragma unroll
-                for (int i = 0; i < P; i++)
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        const int slot = base + i * P + j;
-                        if (slot >= st.slot && slot < st.slot + st.count) a.y[(size_t)(st.dof + slot - st.slot) * a.ld + k] = out[i][j];
-                    }
-            }
-        }
-    }
-#undef SLOT
 }
 
 }  // namespace mimsem
