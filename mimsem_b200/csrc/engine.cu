@@ -99,8 +99,9 @@ struct mimsem_gpu_ctx {
 
     DevBuf<unsigned> d_halo_counters;   // [2][64] finished-CTA counters of the p2p halo kernels (push, pull)
     // staging for the host-buffer entry point
-    DevBuf<double> s_lev, s_x, s_y, s_c;
-    cudaStream_t stream = nullptr;
+    DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[2], s_out2[2], s_x2[2], s_y2[2], s_c2[2];
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_host[3] = {nullptr, nullptr, nullptr};
 
     int64_t launches = 0;
 };
@@ -840,6 +841,9 @@ int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx) {
     if (!ctx) return MIMSEM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int b = 0; b < 3; b++)
+        if (ctx->ev_host[b]) cudaEventDestroy(ctx->ev_host[b]);
     delete ctx;
     return MIMSEM_OK;
 }
@@ -1187,34 +1191,58 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     const int64_t nsp[3] = {c->n0, c->n1, c->n2};
     const int64_t nin = nsp[sin], nout = nsp[sout], ncoef = scoef >= 0 ? nsp[scoef] : 0;
     if (ncoef && !h_coeff) return fail(MIMSEM_ERR_ARG, "this operator needs a coefficient field");
+    // Pipeline over chunks of levels (levels are independent): while chunk c is being computed, chunk c+1 is on
+    // its way in and chunk c-1 on its way out; two streams ping-pong so that both PCIe directions stay busy.
     const int ld = nlev;
-    const size_t big = (size_t)std::max(std::max(nin, nout), ncoef) * nlev;
-    CUDA_OK(c->s_lev.resize(big));
-    CUDA_OK(c->s_x.resize((size_t)nin * nlev));
-    CUDA_OK(c->s_y.resize((size_t)nout * nlev));
-    if (ncoef) CUDA_OK(c->s_c.resize((size_t)ncoef * nlev));
-    cudaStream_t st = c->stream;
-    if (ncoef) {
-        CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_coeff, (size_t)ncoef * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
-        if ((rc = transpose(c, true, scoef, ncoef, nlev, ld, c->s_lev.p, c->s_c.p, st))) return rc;
+    int CH = 12;
+    if (const char* ch = getenv("MIMSEM_HOST_CHUNK")) CH = std::max(1, atoi(ch));
+    if (CH % 2) CH++;
+    CH = std::min(CH, nlev);
+    const int nchunk = (nlev + CH - 1) / CH;
+    const size_t big = (size_t)std::max(std::max(nin, nout), ncoef) * CH;
+    for (int b = 0; b < 2; b++) {
+        CUDA_OK(c->s_lev2[b].resize(big));
+        CUDA_OK(c->s_out2[b].resize((size_t)nout * CH));
     }
-    CUDA_OK(cudaMemcpyAsync(c->s_lev.p, h_x, (size_t)nin * nlev * sizeof(double), cudaMemcpyHostToDevice, st));
-    if ((rc = transpose(c, true, sin, nin, nlev, ld, c->s_lev.p, c->s_x.p, st))) return rc;
-    // rows the operator does not write (halo rows in owner-computes mode) stay zero
-    CUDA_OK(cudaMemsetAsync(c->s_y.p, 0, (size_t)nout * nlev * sizeof(double), st));
-    switch (op) {
-        case 0: rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
-        case 3: rc = apply_m1(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
-        case 1: rc = apply_m2(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
-        case 5: rc = apply_m2(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
-        case 2: rc = apply_m0(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, c->s_x.p, c->s_y.p, st); break;
-        case 6: rc = apply_m0(c, true, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
-        case 4: rc = apply_k(c, lev0, nlev, ld, scale, tpow, flags, c->s_c.p, c->s_x.p, c->s_y.p, st); break;
-        default: rc = apply_inc(c, op - 10, nlev, ld, c->s_x.p, c->s_y.p, st); break;
+    for (int b = 0; b < 2; b++) {
+        CUDA_OK(c->s_x2[b].resize((size_t)nin * CH));
+        CUDA_OK(c->s_y2[b].resize((size_t)nout * CH));
+        if (ncoef) CUDA_OK(c->s_c2[b].resize((size_t)ncoef * CH));
     }
-    if (rc) return rc;
-    if ((rc = transpose(c, false, sout, nout, nlev, ld, c->s_y.p, c->s_lev.p, st))) return rc;
-    CUDA_OK(cudaMemcpyAsync(h_y, c->s_lev.p, (size_t)nout * nlev * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!c->stream2) CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    cudaStream_t sts[2] = {c->stream, c->stream2};
+    for (int ck = 0; ck < nchunk; ck++) {
+        cudaStream_t st = sts[ck & 1];
+        const int b = ck & 1;
+        const int k0 = ck * CH, nl = std::min(CH, nlev - k0);
+        // each chunk lives in its own column-layout buffers with leading dimension nl (contiguous DOF runs)
+        if (ncoef) {
+            CUDA_OK(cudaMemcpyAsync(c->s_lev2[b].p, h_coeff + (size_t)k0 * ncoef, (size_t)ncoef * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+            if ((rc = transpose(c, true, scoef, ncoef, nl, nl, c->s_lev2[b].p, c->s_c2[b].p, st))) return rc;
+        }
+        CUDA_OK(cudaMemcpyAsync(c->s_lev2[b].p, h_x + (size_t)k0 * nin, (size_t)nin * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = transpose(c, true, sin, nin, nl, nl, c->s_lev2[b].p, c->s_x2[b].p, st))) return rc;
+        // rows the operator does not write (halo rows in owner-computes mode) stay zero
+        CUDA_OK(cudaMemsetAsync(c->s_y2[b].p, 0, (size_t)nout * nl * sizeof(double), st));
+        const double* xc = c->s_x2[b].p;
+        const double* cc = ncoef ? c->s_c2[b].p : nullptr;
+        double* yc = c->s_y2[b].p;
+        switch (op) {
+            case 0: rc = apply_m1(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 3: rc = apply_m1(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 1: rc = apply_m2(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 5: rc = apply_m2(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 2: rc = apply_m0(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 6: rc = apply_m0(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 4: rc = apply_k(c, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
+        }
+        if (rc) return rc;
+        if ((rc = transpose(c, false, sout, nout, nl, nl, yc, c->s_out2[b].p, st))) return rc;
+        CUDA_OK(cudaMemcpyAsync(h_y + (size_t)k0 * nout, c->s_out2[b].p, (size_t)nout * nl * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(sts[1]));
+    cudaStream_t st = sts[0];
     CUDA_OK(cudaStreamSynchronize(st));
     return MIMSEM_OK;
 }
