@@ -753,6 +753,16 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         a.div_m = fd.m;
         a.div_s = fd.s;
     }
+    const bool vec2 = !with_h && nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+                      (tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0));
+    if (vec2) {
+        a.nlev = nlev / 2;
+        const FastDiv fd = make_fastdiv((unsigned)a.nlev);
+        a.div_m = fd.m;
+        a.div_s = fd.s;
+        k_apply_m0_vec2<<<grid_for((int64_t)a.n0 * a.nlev, 256), 256, 0, st>>>(a);
+        return finish_launch(c, "apply_M0");
+    }
     const int64_t threads = (int64_t)a.n0 * nlev;
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
@@ -785,7 +795,16 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
         a.div_s = fd.s;
     }
     if (a.nrows == 0) return MIMSEM_OK;
-    k_apply_ell<<<grid_for(a.nrows * nlev, 256), 256, 0, st>>>(a);
+    if (a.width > 4) return fail(MIMSEM_ERR_UNSUPPORTED, "incidence stencil wider than 4");
+    if (nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+        a.nlev = nlev / 2;
+        const FastDiv fd2 = make_fastdiv((unsigned)a.nlev);
+        a.div_m = fd2.m;
+        a.div_s = fd2.s;
+        k_apply_ell<2><<<grid_for(a.nrows * a.nlev, 256), 256, 0, st>>>(a);
+        return finish_launch(c, "apply_incidence");
+    }
+    k_apply_ell<1><<<grid_for(a.nrows * nlev, 256), 256, 0, st>>>(a);
     return finish_launch(c, "apply_incidence");
 }
 

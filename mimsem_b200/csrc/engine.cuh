@@ -71,8 +71,8 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned m, unsigned s) 
 struct HaloPeer {
     const int* rows;          // local rows to send (push) / ghost rows to fill (pull)
     int nrows;
-    int pad;
-    double* inbox;            // push: the PEER's inbox region for me (peer address); pull: my inbox region for this peer
+    int row0;                 // first inbox row of this peer's share (inbox rows are packed with stride nlev)
+    double* inbox;            // push: the PEER's inbox of this space (peer address); pull: my inbox of this space
     long long inbox_parity_stride;   // doubles between the two parity buffers
     unsigned long long* signal;      // push: flag on the peer (I write) ; pull: ack on the peer (I write)
     const unsigned long long* wait;  // push: ack from the peer (peer writes, local memory) ; pull: flag from the peer
@@ -152,8 +152,8 @@ struct M1Slots {
 };
 
 struct CopyEnt {      // 16 bytes
-    int kind;         // 0 x field, 1 coefficient field, 2 inverse thickness, 3 geometry record
-    int src;          // first DOF / quadrature point / element
+    int kind;         // 0 x field, 1 coefficient field, 2 inverse thickness, 3 geometry record, 4 x field from the halo inbox
+    int src;          // first DOF / quadrature point / element / inbox row
     int slot;         // first destination slot (kind 3: ignored)
     int count;        // consecutive DOFs -> consecutive slots
 };
@@ -171,7 +171,27 @@ struct StoreEnt {     // 16 bytes
     int slot, dof, count, pad;
 };
 
+// Ghost refresh fused into the tile kernel (multi-GPU): the first push_ctas CTAs of the grid store this rank's
+// boundary rows into the peers' inboxes over NVLink and raise the peers' flags; tiles [0, n_int) read no ghost row;
+// tiles >= n_int wait for the flags of this epoch and then stage their ghost rows straight from the inbox (copy-list
+// kind 4) -- no pull kernel, no ghost rows in x.  The last CTA to finish acknowledges the inbox to the peers and
+// advances the device-side epoch, so the launch replays inside a CUDA graph.
+struct HaloFused {
+    int npush, npull;
+    int push_ctas;
+    int n_int;                       // tiles below this index never touch the inbox
+    const HaloPeer* push;
+    const HaloPeer* pull;
+    const double* inbox;             // my inbox of the x field's space, parity 0
+    long long parity_stride;         // doubles between the two parity copies
+    unsigned long long* epoch;
+    unsigned* counters;              // [1 + npush]: finished CTAs of the launch, finished push CTAs per peer
+    int* err;
+};
+
 struct TArgs {
+    int halo_on;
+    HaloFused halo;
     int nlev, ld, lev0, nkT, tpow;
     int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
     int contig_t;     // nkT == nlev

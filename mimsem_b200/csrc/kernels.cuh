@@ -572,21 +572,63 @@ __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeAr
     a.y[(size_t)n * ld + k] = f * d * ldro(a.x + (size_t)n * ld + k);
 }
 
-// y[r][k] = sum_j sgn[r][j] x[col[r][j]][k]   (entries sorted by column, as a CSR SpMV would add them)
+// M0 without a coefficient field, two levels per thread (16-byte accesses); a.nlev counts level pairs
+__global__ void __launch_bounds__(256) k_apply_m0_vec2(const __grid_constant__ NodeArgs a) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
+    const int n = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)n * (unsigned)a.nlev) * 2;
+    const double2 x = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)n * a.ld + k));
+    double2 f = make_double2(a.scale, a.scale);
+    if (a.tpow > 0) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(a.tinv + (size_t)a.node_q[n] * a.nkT + a.lev0 + k));
+        f.x *= t.x; f.y *= t.y;
+        if (a.tpow > 1) { f.x *= t.x; f.y *= t.y; }
+    }
+    const double d = a.D0[n];
+    *reinterpret_cast<double2*>(a.y + (size_t)n * a.ld + k) = make_double2(f.x * d * x.x, f.y * d * x.y);
+}
+
+// y[r][k] = sum_j sgn[r][j] x[col[r][j]][k]   (entries in a partition-invariant order, see upload_ell)
+// VEC = 2: two consecutive levels per thread through 16-byte accesses (nlev, ld even, 16-byte aligned fields);
+// a.nlev then counts level PAIRS.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllArgs a) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.nrows * (unsigned)a.nlev) return;
     const int64_t rr = fastdiv(idx, a.div_m, a.div_s);
-    const int k = (int)(idx - (unsigned)rr * (unsigned)a.nlev);
+    const int k = (int)(idx - (unsigned)rr * (unsigned)a.nlev) * VEC;
     const int64_t r = a.rows ? a.rows[rr] : rr;
-    double s = 0.0;
-    for (int j = 0; j < a.width; j++) {
-        const int c = a.col[r * a.width + j];
-        if (c < 0) break;
-        const double v = ldro(a.x + (size_t)c * a.ld + k);
-        s += (a.sgn[r * a.width + j] > 0) ? v : -v;
+    int cols[4];
+    signed char sg[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        cols[j] = j < a.width ? a.col[r * a.width + j] : -1;
+        sg[j] = j < a.width ? a.sgn[r * a.width + j] : 0;
     }
-    a.y[(size_t)r * a.ld + k] = s;
+    if (VEC == 2) {
+        double2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cols[j] >= 0) v[j] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)cols[j] * a.ld + k));
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cols[j] >= 0) {
+                s.x += sg[j] > 0 ? v[j].x : -v[j].x;
+                s.y += sg[j] > 0 ? v[j].y : -v[j].y;
+            }
+        *reinterpret_cast<double2*>(a.y + (size_t)r * a.ld + k) = s;
+    } else {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cols[j] >= 0) {
+                const double v = ldro(a.x + (size_t)cols[j] * a.ld + k);
+                s += sg[j] > 0 ? v : -v;
+            }
+        a.y[(size_t)r * a.ld + k] = s;
+    }
 }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
