@@ -254,7 +254,8 @@ def main():
 
     # ring of distinct field sets: every step reads and writes buffers that were last touched
     # >= RING-1 steps ago; one field pair (0.42 GB on C5) already exceeds the 126 MB L2
-    RING = 3
+    # (at N GPUs the per-rank slice shrinks, so the ring grows until it covers >= 4x the 126 MB L2)
+    RING = max(3, -(-4 * 126_000_000 // (16 * nin * nk)))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.rand((nin, nk), dtype=torch.float64, device=dev, generator=g) * 2 - 1 for _ in range(RING)]
     ys = [torch.empty((nout, nk), dtype=torch.float64, device=dev) for _ in range(RING)]

@@ -167,6 +167,22 @@ int mimsem_gpu_apply_M0h(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double
 int mimsem_gpu_apply_K(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                        const double* d_u1, const double* d_x, double* d_y, void* stream);
 
+/*
+ * Rotational term and the potential-vorticity-upwinded operators of the shallow-water solver (BASELINE config 2):
+ *   RotMat::assemble(q0)                  -> apply_R      (src tpow = 0; eul/box (q0,lev,scale): tpow = 2)
+ *                                            src/Assembly.cpp:1346-1395, eul/Assembly.cpp:1030-1083, box/Assembly.cpp:826-880
+ *   RotMat_up::assemble(q0, ul, fac, dt)  -> apply_R_up   (tau = fac*dt)                    src/Assembly.cpp:1784-1853
+ *   Phmat::assemble_up(ul, hl, fac, dt)   -> apply_M0h_up (tau = fac*dt)                    src/Assembly.cpp:499-567
+ * d_q0: 0-form coefficient (node rows), d_u1: 1-form advecting velocity (engine edge rows), d_h2: 2-form depth.
+ * The trial basis is evaluated at the departure points xi_q - tau J^-1 u_g(xi_q) (LagrangeNode::eval_q).
+ */
+int mimsem_gpu_apply_R(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                       const double* d_q0, const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_R_up(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                          const double* d_q0, const double* d_u1, double tau, const double* d_x, double* d_y, void* stream);
+int mimsem_gpu_apply_M0h_up(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                            const double* d_h2, const double* d_u1, double tau, const double* d_x, double* d_y, void* stream);
+
 /* Incidence operators (exact +-1 stencils), E10mat/E21mat of eul/Assembly.cpp:1102-1226:
  * which = 0 E10 (0-form -> 1-form), 1 E01 = -E10^T, 2 E21 (1-form -> 2-form), 3 E12 = -E21^T. */
 #define MIMSEM_E10 0
@@ -186,6 +202,10 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_s
  */
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
                           const double* h_coeff, const double* h_x, double* h_y);
+/* The same with the operators of BASELINE config 2: op 7 R (h_coeff = q0), 8 R_up (h_coeff = q0, h_u1, tau),
+ * 9 M0h_up (h_coeff = h2, h_u1, tau); every other op ignores h_u1 and tau. */
+int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
+                             const double* h_coeff, const double* h_u1, double tau, const double* h_x, double* h_y);
 
 /* Halo pack / unpack (device pointers; d_rows holds engine rows, i.e. values of mimsem_gpu_form_permutation):
  *   gather : packed[i*nlev + k] = field[rows[i]*ld + k]        (send side of the ghost refresh)
@@ -202,9 +222,10 @@ int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld
  * the push kernel stores into the peer's memory).  Buffers that peers write into are allocated with
  * mimsem_gpu_ipc_alloc (cudaMalloc + IPC handle, 64 bytes, to be exchanged by the caller's process-group plumbing)
  * and mapped on the peers with mimsem_gpu_ipc_open.  d_peers is a device array of `npeers` records
- *   { const int* rows; int nrows; int pad; double* inbox; long long inbox_parity_stride;
+ *   { const int* rows; int nrows; int row0; double* inbox; long long inbox_parity_stride;
  *     unsigned long long* signal; const unsigned long long* wait; }                        (48 bytes each)
- * push: rows = owned rows to send, inbox/signal = the PEER's inbox region and flag for this rank, wait = the ack
+ * Inbox rows are packed with stride nlev; a peer's share starts at row `row0` of the space's inbox.
+ * push: rows = owned rows to send, inbox/signal = the PEER's inbox of the space and flag for this rank, wait = the ack
  *       the peer writes into this rank's memory;
  * pull: rows = ghost rows to fill, inbox/wait = this rank's inbox region and flag for the peer, signal = the ack
  *       on the peer.  d_epoch is a device counter, one for the pushes and one for the pulls of a space, advanced by
@@ -218,6 +239,24 @@ int mimsem_gpu_halo_push(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, i
                          void* d_epoch, int* d_err, void* stream);
 int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, double* d_field, void* d_epoch,
                          int* d_err, void* stream);
+
+/*
+ * M1 apply FUSED with the ghost refresh of its input (one launch per step and GPU; replaces the
+ * VecScatter(gtol_1, INSERT_VALUES, SCATTER_FORWARD) + Umat MatMult + VecScatter(ADD_VALUES, SCATTER_REVERSE)
+ * sequence of eul/Euler_2.cpp:1455-1456, eul/Assembly.cpp:2194-2195).  The first `push_ctas` CTAs of the grid store
+ * this rank's boundary rows into the peers' inboxes over NVLink and raise their flags; interior element tiles run
+ * meanwhile; boundary tiles (ordered last) wait for the flags and stage their ghost rows straight from the inbox
+ * by TMA; the last CTA acknowledges the inbox and advances the device-side epoch (CUDA-graph replayable).
+ * Requires mimsem_gpu_set_ghosts, ld == nlev (even, <= 64) and inbox rows in ghost order:
+ * inbox row i holds caller row n1_owned + i (d_push[].row0 = first row of each peer's share).
+ * d_push / d_pull as for mimsem_gpu_halo_push / _pull; d_inbox = this rank's inbox (parity 0), the second parity
+ * copy parity_stride doubles later; d_epoch = the space's two epoch counters {push, pull} (both advanced, so this
+ * call can be mixed with push / pull pairs).  Ghost rows of d_x itself are neither read nor written.
+ */
+int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                             const double* d_x, double* d_y, int npush, const void* d_push, int npull, const void* d_pull,
+                             const double* d_inbox, int64_t parity_stride, int push_ctas, void* d_epoch, int* d_err,
+                             void* stream);
 
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);

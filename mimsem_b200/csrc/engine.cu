@@ -87,11 +87,24 @@ struct mimsem_gpu_ctx {
     bool tma_ok = false;
     DevBuf<TileHdr> d_recs, d_recs_h;   // fixed-stride tile records: header + rec_ents copy entries
     int rec_ents = 0, rec_ents_h = 0;
+    // fused ghost refresh (set_ghosts): records whose ghost rows are staged from the halo inbox; tiles ordered
+    // interior first, boundary last
+    DevBuf<TileHdr> d_recs_halo;
+    int rec_ents_halo = 0;
+    bool halo_plan_ok = false;
+    DevBuf<int> d_elist_all;
+    bool elist_all_identity = false;   // the caller already stores interior elements first (no indirection needed)
+    DevBuf<unsigned> d_fused_counters;
+    DevBuf<TileHdr> d_recs_k;           // K (WtQUmat) tile records
+    int rec_ents_k = 0;
+    bool k_plan_ok = false;
     DevBuf<StoreEnt> d_stores;
     DevBuf<int> d_st_ptr;
     DevBuf<double> d_geo, d_geo_h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
+    DevBuf<double> d_J4, d_det, d_Wr;   // raw Jacobians for the upwinded operators, signed quadrature weight of R(q)
+    std::vector<double> xn;             // GLL nodes of order p
     int nkT = 0;
 
     HostCsr csr[4];
@@ -99,7 +112,7 @@ struct mimsem_gpu_ctx {
 
     DevBuf<unsigned> d_halo_counters;   // [2][64] finished-CTA counters of the p2p halo kernels (push, pull)
     // staging for the host-buffer entry point
-    DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[2], s_out2[2], s_x2[2], s_y2[2], s_c2[2];
+    DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[2], s_out2[2], s_x2[2], s_y2[2], s_c2[2], s_u2[2];
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_host[3] = {nullptr, nullptr, nullptr};
 
@@ -358,9 +371,16 @@ int build_node_adjacency(mimsem_gpu_ctx* c) {
 // ------------------------------------------------------------------------------------------
 // TMA tile plan: per owned element, the list of bulk copies that fills the tile's slots
 // (see M1Slots in engine.cuh) and the list of bulk stores of its owned edges.
+// ghost_from >= 0 builds only the fused-halo variant of the plain-M1 records: x rows whose CALLER index is
+// >= ghost_from are staged from inbox row (caller index - ghost_from) instead (copy kind 4).
 template <int P>
-int build_tma_plan_p(mimsem_gpu_ctx* c) {
+int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
     using S = M1Slots<P>;
+    std::vector<int> inv1;
+    if (ghost_from >= 0) {
+        inv1.assign(c->n1, 0);
+        for (int i = 0; i < c->n1; i++) inv1[c->h_perm1[i]] = i;
+    }
     constexpr int NP1 = P + 1, N1E = P * NP1, N2E = P * P, Q2 = NP1 * NP1;
     std::vector<TileHdr> hdr(c->nel_owned), hdr_h(c->nel_owned);
     std::vector<CopyEnt> cps, cps_h;
@@ -422,7 +442,18 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         h.st_dof = (int)cps.size();   // parked: begin of this element's entries (replaced by the store row in pack())
         h.flags = flags;
         cps.push_back(CopyEnt{3, e, 0, 1});
-        const int nx = emit_runs(xs, 0, cps);
+        int nx;
+        if (ghost_from >= 0) {
+            std::vector<std::pair<int, int>> xo, xg;
+            for (auto& ds : xs) {
+                const int ext = inv1[ds.first];
+                if (ext >= ghost_from) xg.push_back({ext - ghost_from, ds.second});
+                else xo.push_back(ds);
+            }
+            nx = emit_runs(xo, 0, cps) + emit_runs(xg, 4, cps);
+        } else {
+            nx = emit_runs(xs, 0, cps);
+        }
         const int nt = emit_runs(ts, 2, cps);
         h.cp_count = (int)cps.size() - h.st_dof;
         h.nslots = nx | (nt << 16);
@@ -471,11 +502,72 @@ int build_tma_plan_p(mimsem_gpu_ctx* c) {
         }
         return out.upload(rec);
     };
+    if (ghost_from >= 0) {
+        CUDA_OK(pack(hdr, cps, c->rec_ents_halo, c->d_recs_halo));
+        c->halo_plan_ok = all_contig;
+        return MIMSEM_OK;
+    }
     CUDA_OK(pack(hdr, cps, c->rec_ents, c->d_recs));
     CUDA_OK(pack(hdr_h, cps_h, c->rec_ents_h, c->d_recs_h));
     CUDA_OK(c->d_stores.upload(stores));
     CUDA_OK(c->d_st_ptr.upload(st_ptr));
     c->tma_ok = all_contig;   // the tile kernel stores the owned block as one run of rows
+    return MIMSEM_OK;
+}
+
+// Tile records of the K kernel (KSlots): x and u1 edges of the element, thickness; output = the element's faces.
+template <int P>
+int build_k_plan_p(mimsem_gpu_ctx* c) {
+    using S = KSlots<P>;
+    constexpr int NP1 = P + 1, N1E = P * NP1, N2E = P * P, Q2 = NP1 * NP1;
+    std::vector<TileHdr> rec;
+    std::vector<std::vector<CopyEnt>> ents(c->nel_owned);
+    std::vector<TileHdr> hdr(c->nel_owned);
+    bool ok = true;
+    int nents = 1;
+    for (int e = 0; e < c->nel_owned; e++) {
+        const int* ex = &c->h_el1x[(size_t)e * N1E];
+        const int* ey = &c->h_el1y[(size_t)e * N1E];
+        std::vector<std::pair<int, int>> xs, ts;
+        for (int ix = 0; ix < P; ix++)
+            for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + ix], S::OX + ix * P + iy});
+        for (int iy = 0; iy < P; iy++)
+            for (int ix = 0; ix < P; ix++) xs.push_back({ey[iy * P + ix], S::OY + iy * P + ix});
+        for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + P], S::XE + iy});
+        for (int ix = 0; ix < P; ix++) xs.push_back({ey[P * P + ix], S::YN + ix});
+        for (int q = 0; q < Q2; q++) ts.push_back({c->h_elq[(size_t)e * Q2 + q], S::T + q});
+        auto runs = [&](const std::vector<std::pair<int, int>>& ds, int kind, int slot_off) {
+            size_t i = 0;
+            while (i < ds.size()) {
+                size_t j = i + 1;
+                while (j < ds.size() && ds[j].first == ds[j - 1].first + 1 && ds[j].second == ds[j - 1].second + 1) j++;
+                ents[e].push_back(CopyEnt{kind, ds[i].first, ds[i].second + slot_off, (int)(j - i)});
+                i = j;
+            }
+        };
+        ents[e].push_back(CopyEnt{3, e, 0, 1});
+        runs(xs, 0, 0);
+        runs(xs, 1, S::U0);
+        runs(ts, 2, 0);
+        const int* e2 = &c->h_el2[(size_t)e * N2E];
+        for (int j = 0; j < N2E; j++)
+            if (e2[j] != e2[0] + j) ok = false;
+        TileHdr h;
+        h.st_dof = e2[0];
+        h.cp_count = (int)ents[e].size();
+        h.flags = 0;
+        h.nslots = (int)(2 * xs.size()) | ((int)ts.size() << 16);
+        hdr[e] = h;
+        nents = std::max(nents, h.cp_count);
+    }
+    rec.assign((size_t)c->nel_owned * (1 + nents), TileHdr{0, 0, 0, 0});
+    for (int e = 0; e < c->nel_owned; e++) {
+        rec[(size_t)e * (1 + nents)] = hdr[e];
+        std::memcpy(&rec[(size_t)e * (1 + nents) + 1], ents[e].data(), ents[e].size() * sizeof(CopyEnt));
+    }
+    CUDA_OK(c->d_recs_k.upload(rec));
+    c->rec_ents_k = nents;
+    c->k_plan_ok = ok;
     return MIMSEM_OK;
 }
 
@@ -580,7 +672,7 @@ int finish_launch(mimsem_gpu_ctx* c, const char* what) {
 unsigned grid_for(int64_t threads, int block) { return (unsigned)((threads + block - 1) / block); }
 
 int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
-             const double* h2, const double* x, double* y, cudaStream_t st) {
+             const double* h2, const double* x, double* y, cudaStream_t st, const HaloFused* hf = nullptr) {
     int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
     if (rc) return rc;
     if ((rc = bind_device(c))) return rc;
@@ -596,8 +688,16 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     // TMA tile kernel: needs 16-byte aligned, even-length level runs and one thread per level
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
     const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
-    if (c->m1_variant == 2 && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
+    const bool tma_path = c->m1_variant == 2 && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64;
+    if (hf) {
+        if (with_h || !tma_path || !c->halo_plan_ok || a.elist || ld != nlev)
+            return fail(MIMSEM_ERR_UNSUPPORTED, "fused ghost refresh needs the TMA tile path (plain M1, all owned elements, even nlev == ld <= 64, set_ghosts)");
+        if (hf->npush > 64 || hf->npull > 32) return fail(MIMSEM_ERR_ARG, "too many halo peers");
+    }
+    if (tma_path) {
         TArgs t;
+        t.halo_on = 0;
+        std::memset(&t.halo, 0, sizeof(t.halo));
         t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
@@ -622,6 +722,21 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;
         t.x = x; t.c = h2; t.tinv = c->d_tinv.p; t.y = y;
         copy_basis(c, t);
+        int push_ctas = 0;
+        if (hf) {
+            if (!c->d_fused_counters.p) {
+                CUDA_OK(c->d_fused_counters.resize(80));
+                CUDA_OK(cudaMemset(c->d_fused_counters.p, 0, 80 * sizeof(unsigned)));
+            }
+            t.halo_on = 1;
+            t.halo = *hf;
+            t.halo.n_int = c->n_int;
+            t.halo.counters = c->d_fused_counters.p;
+            t.elist = c->elist_all_identity ? nullptr : c->d_elist_all.p;
+            t.recs = c->d_recs_halo.p;
+            t.rec_ents = c->rec_ents_halo;
+            push_ctas = t.halo.push_ctas = hf->npush > 0 ? std::max(1, std::min(296, hf->push_ctas)) : 0;
+        }
         int rc3 = dispatch_p(c->p, [&](auto P) {
             constexpr int p = decltype(P)::value;
             using S = M1Slots<p>;
@@ -631,7 +746,8 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             void (*kern)(const TArgs) = nullptr;
             auto pick = [&](auto NLc) {
                 constexpr int NLv = decltype(NLc)::value;
-                kern = with_h ? k_apply_m1_tma<p, true, NLv> : k_apply_m1_tma<p, false, NLv>;
+                if (hf) kern = k_apply_m1_tma<p, false, NLv, true>;
+                else kern = with_h ? k_apply_m1_tma<p, true, NLv, false> : k_apply_m1_tma<p, false, NLv, false>;
             };
             // compile-time level counts of the BASELINE configurations (C3: 30, C4: 40, C5: 60); anything else: runtime
             if ((p == 3 || p == 4) && nlev == 60) pick(std::integral_constant<int, 60>());
@@ -648,7 +764,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             const char* pg = getenv("MIMSEM_PERSISTENT");
             const bool persistent = pg && atoi(pg) != 0;   // measured equal to one CTA per tile on C5; off by default
             t.ntiles = a.nel;
-            const int grid = persistent ? std::min(a.nel, nsm * std::max(per_sm, 1)) : a.nel;
+            const int grid = (persistent && !hf ? std::min(a.nel, nsm * std::max(per_sm, 1)) : a.nel) + push_ctas;
             kern<<<grid, 128, smem, st>>>(t);
             return finish_launch(c, "apply_M1 (tma)");
         });
@@ -716,6 +832,43 @@ int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpo
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads == 0) return MIMSEM_OK;
+    // TMA tile kernel (same eligibility as M1's)
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)u1 % 16 == 0);
+    const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
+    const char* kv = getenv("MIMSEM_K_VARIANT");
+    if ((!kv || atoi(kv) != 0) && c->k_plan_ok && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
+        TArgs t;
+        std::memset(&t, 0, sizeof(t));
+        t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
+        t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
+        t.scale = scale;
+        const char* pa = getenv("MIMSEM_PREFETCH");
+        t.prefetch_ahead = pa ? atoi(pa) : 296;
+        t.prefetch_own_slots = 2 * c->p * c->p + 2 * c->p;
+        t.elist = a.elist;
+        t.recs = c->d_recs_k.p;
+        t.rec_ents = c->rec_ents_k;
+        t.geo = c->d_geo_h.p;
+        t.x = x; t.c = u1; t.tinv = c->d_tinv.p; t.y = y;
+        t.ntiles = a.nel;
+        copy_basis(c, t);
+        int rc3 = dispatch_p(c->p, [&](auto P) {
+            constexpr int p = decltype(P)::value;
+            t.geo_doubles = M1Slots<p>::GEO;
+            const size_t smem = 16 + ((size_t)M1Slots<p>::GEO + (size_t)KSlots<p>::NS * nlev) * sizeof(double);
+            if (smem > 227 * 1024) return 1;
+            void (*kern)(const TArgs) = nullptr;
+            if ((p == 3 || p == 4) && nlev == 60) kern = k_apply_k_tma<p, 60>;
+            else if (p == 3 && nlev == 30) kern = k_apply_k_tma<p, 30>;
+            else if (p == 3 && nlev == 40) kern = k_apply_k_tma<p, 40>;
+            else kern = k_apply_k_tma<p, 0>;
+            cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+            kern<<<a.nel, 128, smem, st>>>(t);
+            return finish_launch(c, "apply_K (tma)");
+        });
+        if (rc3 != 1) return rc3;
+    }
     return dispatch_p(c->p, [&](auto P) {
         constexpr int p = decltype(P)::value;
         k_apply_k<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
@@ -769,6 +922,84 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         if (with_h) k_apply_m0<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
         else k_apply_m0<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
         return finish_launch(c, "apply_M0");
+    });
+}
+
+// RotMat::assemble(q0) / RotMat_up::assemble(q0, ul, fac, dt) + MatMult
+int apply_rot(mimsem_gpu_ctx* c, bool up, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* q0,
+              const double* u1, double tau, const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!q0 || !x || !y || (up && !u1)) return fail(MIMSEM_ERR_ARG, "null field");
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = nullptr;
+    a.x = x;
+    a.y = y;
+    a.el0 = c->d_el0.p;
+    a.q0 = q0;
+    a.u1 = u1;
+    a.J4 = c->d_J4.p;
+    a.det = c->d_det.p;
+    a.Wr = c->d_Wr.p;
+    a.tau = tau;
+    for (int i = 0; i <= kMaxP; i++) a.xn[i] = i <= c->p ? c->xn[i] : 0.0;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
+    if (threads == 0) return MIMSEM_OK;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        if (up) k_apply_rot<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        else k_apply_rot<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, up ? "apply_R_up" : "apply_R");
+    });
+}
+
+// Phmat::assemble_up(ul, hl, fac, dt) + MatMult
+int apply_m0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                 const double* u1, double tau, const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!h2 || !u1 || !x || !y) return fail(MIMSEM_ERR_ARG, "null field");
+    if (c->nel_owned != c->nel_total) return fail(MIMSEM_ERR_UNSUPPORTED, "0-form operators are not partitioned");
+    NodeArgs a;
+    a.n0 = c->n0;
+    a.nlev = nlev;
+    a.ld = ld;
+    a.lev0 = lev0;
+    a.lev_stride = (flags & MIMSEM_FIXED_LEVEL) ? 0 : 1;
+    a.nkT = c->nkT;
+    a.tpow = tpow;
+    a.scale = scale;
+    a.adj_ptr = c->d_adj_ptr.p;
+    a.adj_eq = c->d_adj_eq.p;
+    a.node_q = c->d_node_q.p;
+    a.el2 = c->d_el2.p;
+    a.D0 = c->d_D0.p;
+    a.wq = c->d_wq.p;
+    a.tinv = c->d_tinv.p;
+    a.c = h2;
+    a.x = x;
+    a.y = y;
+    a.el0 = c->d_el0.p;
+    a.el1x = c->d_el1x.p;
+    a.el1y = c->d_el1y.p;
+    a.u1 = u1;
+    a.J4 = c->d_J4.p;
+    a.det = c->d_det.p;
+    a.tau = tau;
+    for (int i = 0; i <= kMaxP; i++) a.xn[i] = i <= c->p ? c->xn[i] : 0.0;
+    copy_basis(c, a);
+    const FastDiv fd = make_fastdiv((unsigned)nlev);
+    a.div_m = fd.m;
+    a.div_s = fd.s;
+    const int64_t threads = (int64_t)a.n0 * nlev;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        k_apply_m0h_up<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "apply_M0h_up");
     });
 }
 
@@ -880,6 +1111,11 @@ int mimsem_gpu_set_basis(mimsem_gpu_ctx* c, int p, int m, const double* h_w, con
     c->m = m;
     c->w.assign(h_w, h_w + m + 1);
     c->ejxi.assign(h_ejxi, h_ejxi + (size_t)(m + 1) * p);
+    {
+        c->xn.assign(p + 1, 0.0);
+        std::vector<double> wtmp(p + 1);
+        if (mimsem_basis_gll(p, c->xn.data(), wtmp.data()) != MIMSEM_OK) return MIMSEM_ERR_ARG;
+    }
     c->have_basis = true;
     c->have_topo = c->have_geom = false;
     return MIMSEM_OK;
@@ -979,6 +1215,15 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         }
         if (rc) return rc;
     }
+    c->k_plan_ok = false;
+    switch (P) {
+        case 2: rc = build_k_plan_p<2>(c); break;
+        case 3: rc = build_k_plan_p<3>(c); break;
+        case 4: rc = build_k_plan_p<4>(c); break;
+        case 5: rc = build_k_plan_p<5>(c); break;
+        default: rc = MIMSEM_OK;
+    }
+    if (rc) return rc;
     CUDA_OK(c->d_el0.upload(c->h_el0));
     CUDA_OK(c->d_el1x.upload(c->h_el1x));
     CUDA_OK(c->d_el1y.upload(c->h_el1y));
@@ -1020,6 +1265,25 @@ int mimsem_gpu_set_ghosts(mimsem_gpu_ctx* c, int n1_owned, int n2_owned, int out
     c->n_bnd = (int)bd.size();
     CUDA_OK(c->d_elist_int.upload(in));
     CUDA_OK(c->d_elist_bnd.upload(bd));
+    {
+        std::vector<int> all(in);
+        all.insert(all.end(), bd.begin(), bd.end());
+        CUDA_OK(c->d_elist_all.upload(all));
+        c->elist_all_identity = true;
+        for (size_t i = 0; i < all.size(); i++)
+            if (all[i] != (int)i) c->elist_all_identity = false;
+    }
+    c->halo_plan_ok = false;
+    if (c->mode == 0 && c->tma_ok) {
+        switch (P) {
+            case 2: rc = build_tma_plan_p<2>(c, n1_owned); break;
+            case 3: rc = build_tma_plan_p<3>(c, n1_owned); break;
+            case 4: rc = build_tma_plan_p<4>(c, n1_owned); break;
+            case 5: rc = build_tma_plan_p<5>(c, n1_owned); break;
+            default: rc = MIMSEM_OK;
+        }
+        if (rc) return rc;
+    }
     if (out_counts) {
         out_counts[0] = c->n_int;
         out_counts[1] = c->n_bnd;
@@ -1084,6 +1348,14 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
     CUDA_OK(c->d_W2h.upload(W2h));
     CUDA_OK(c->d_D0.upload(D0));
     CUDA_OK(c->d_wq.upload(wq));
+    {
+        std::vector<double> J4(h_J, h_J + npts * 4), dt(h_det, h_det + npts), Wr(npts);
+        // RotMat: (-/+)(J00 J11 - J01 J10) w / det   (src/Assembly.cpp:1369-1370)
+        for (size_t i = 0; i < npts; i++) Wr[i] = (h_J[i * 4 + 0] * h_J[i * 4 + 3] - h_J[i * 4 + 1] * h_J[i * 4 + 2]) * wq[i % Q2] / h_det[i];
+        CUDA_OK(c->d_J4.upload(J4));
+        CUDA_OK(c->d_det.upload(dt));
+        CUDA_OK(c->d_Wr.upload(Wr));
+    }
     c->have_geom = true;
     return MIMSEM_OK;
 }
@@ -1138,6 +1410,24 @@ int mimsem_gpu_apply_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sc
                         double* y, void* st) {
     return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
 }
+int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                             double* y, int npush, const void* d_push, int npull, const void* d_pull, const double* d_inbox,
+                             int64_t parity_stride, int push_ctas, void* d_epoch, int* d_err, void* st) {
+    if (!c || !d_epoch || !d_err || (npush > 0 && !d_push) || (npull > 0 && (!d_pull || !d_inbox)))
+        return fail(MIMSEM_ERR_ARG, "null argument");
+    HaloFused hf;
+    std::memset(&hf, 0, sizeof(hf));
+    hf.npush = npush;
+    hf.npull = npull;
+    hf.push_ctas = push_ctas;
+    hf.push = (const HaloPeer*)d_push;
+    hf.pull = (const HaloPeer*)d_pull;
+    hf.inbox = d_inbox;
+    hf.parity_stride = parity_stride;
+    hf.epoch = (unsigned long long*)d_epoch;
+    hf.err = d_err;
+    return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st, &hf);
+}
 int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
                          const double* x, double* y, void* st) {
     if (!h2) return fail(MIMSEM_ERR_ARG, "null coefficient field");
@@ -1166,6 +1456,18 @@ int mimsem_gpu_apply_K(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sca
     if (!u1) return fail(MIMSEM_ERR_ARG, "null coefficient field");
     return apply_k(c, lev0, nlev, ld, scale, tpow, flags, u1, x, y, (cudaStream_t)st);
 }
+int mimsem_gpu_apply_R(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* q0,
+                       const double* x, double* y, void* st) {
+    return apply_rot(c, false, lev0, nlev, ld, scale, tpow, flags, q0, nullptr, 0.0, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_R_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* q0,
+                          const double* u1, double tau, const double* x, double* y, void* st) {
+    return apply_rot(c, true, lev0, nlev, ld, scale, tpow, flags, q0, u1, tau, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_M0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                            const double* u1, double tau, const double* x, double* y, void* st) {
+    return apply_m0h_up(c, lev0, nlev, ld, scale, tpow, flags, h2, u1, tau, x, y, (cudaStream_t)st);
+}
 int mimsem_gpu_apply_incidence(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, void* st) {
     return apply_inc(c, which, nlev, ld, x, y, (cudaStream_t)st);
 }
@@ -1187,6 +1489,11 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* c, int which, int64_t out_siz
 
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double scale, int tpow, int flags,
                           const double* h_coeff, const double* h_x, double* h_y) {
+    return mimsem_gpu_apply_host_up(c, op, lev0, nlev, scale, tpow, flags, h_coeff, nullptr, 0.0, h_x, h_y);
+}
+
+int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double scale, int tpow, int flags,
+                             const double* h_coeff, const double* h_u1, double tau, const double* h_x, double* h_y) {
     if (!c || !h_x || !h_y) return fail(MIMSEM_ERR_ARG, "null argument");
     if (!c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
     int rc = bind_device(c);
@@ -1201,6 +1508,8 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
         case 2: sin = sout = 0; break;
         case 6: sin = sout = 0; scoef = 2; break;
         case 4: sin = 1; sout = 2; scoef = 1; break;
+        case 7: case 8: sin = sout = 1; scoef = 0; break;   // R(q0), R_up(q0, u1)
+        case 9: sin = sout = 0; scoef = 2; break;           // M0h_up(h2, u1)
         case 10 + MIMSEM_E10: sin = 0; sout = 1; break;
         case 10 + MIMSEM_E01: sin = 1; sout = 0; break;
         case 10 + MIMSEM_E21: sin = 1; sout = 2; break;
@@ -1210,6 +1519,8 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     const int64_t nsp[3] = {c->n0, c->n1, c->n2};
     const int64_t nin = nsp[sin], nout = nsp[sout], ncoef = scoef >= 0 ? nsp[scoef] : 0;
     if (ncoef && !h_coeff) return fail(MIMSEM_ERR_ARG, "this operator needs a coefficient field");
+    const bool need_u = (op == 8 || op == 9);
+    if (need_u && !h_u1) return fail(MIMSEM_ERR_ARG, "this operator needs the advecting velocity");
     // Pipeline over chunks of levels (levels are independent): while chunk c is being computed, chunk c+1 is on
     // its way in and chunk c-1 on its way out; two streams ping-pong so that both PCIe directions stay busy.
     const int ld = nlev;
@@ -1218,7 +1529,7 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
     if (CH % 2) CH++;
     CH = std::min(CH, nlev);
     const int nchunk = (nlev + CH - 1) / CH;
-    const size_t big = (size_t)std::max(std::max(nin, nout), ncoef) * CH;
+    const size_t big = (size_t)std::max(std::max(std::max(nin, nout), ncoef), need_u ? (int64_t)c->n1 : (int64_t)0) * CH;
     for (int b = 0; b < 2; b++) {
         CUDA_OK(c->s_lev2[b].resize(big));
         CUDA_OK(c->s_out2[b].resize((size_t)nout * CH));
@@ -1227,6 +1538,7 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
         CUDA_OK(c->s_x2[b].resize((size_t)nin * CH));
         CUDA_OK(c->s_y2[b].resize((size_t)nout * CH));
         if (ncoef) CUDA_OK(c->s_c2[b].resize((size_t)ncoef * CH));
+        if (need_u) CUDA_OK(c->s_u2[b].resize((size_t)c->n1 * CH));
     }
     if (!c->stream2) CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     cudaStream_t sts[2] = {c->stream, c->stream2};
@@ -1238,6 +1550,10 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
         if (ncoef) {
             CUDA_OK(cudaMemcpyAsync(c->s_lev2[b].p, h_coeff + (size_t)k0 * ncoef, (size_t)ncoef * nl * sizeof(double), cudaMemcpyHostToDevice, st));
             if ((rc = transpose(c, true, scoef, ncoef, nl, nl, c->s_lev2[b].p, c->s_c2[b].p, st))) return rc;
+        }
+        if (need_u) {
+            CUDA_OK(cudaMemcpyAsync(c->s_lev2[b].p, h_u1 + (size_t)k0 * c->n1, (size_t)c->n1 * nl * sizeof(double), cudaMemcpyHostToDevice, st));
+            if ((rc = transpose(c, true, 1, c->n1, nl, nl, c->s_lev2[b].p, c->s_u2[b].p, st))) return rc;
         }
         CUDA_OK(cudaMemcpyAsync(c->s_lev2[b].p, h_x + (size_t)k0 * nin, (size_t)nin * nl * sizeof(double), cudaMemcpyHostToDevice, st));
         if ((rc = transpose(c, true, sin, nin, nl, nl, c->s_lev2[b].p, c->s_x2[b].p, st))) return rc;
@@ -1254,6 +1570,9 @@ int mimsem_gpu_apply_host(mimsem_gpu_ctx* c, int op, int lev0, int nlev, double 
             case 2: rc = apply_m0(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
             case 6: rc = apply_m0(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
             case 4: rc = apply_k(c, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 7: rc = apply_rot(c, false, lev0 + k0, nl, nl, scale, tpow, flags, cc, nullptr, 0.0, xc, yc, st); break;
+            case 8: rc = apply_rot(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
+            case 9: rc = apply_m0h_up(c, lev0 + k0, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
             default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
         }
         if (rc) return rc;

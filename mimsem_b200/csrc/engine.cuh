@@ -43,6 +43,15 @@ struct KArgs {
     double* y;
     // basis
     double E[(kMaxP + 1) * kMaxP];   // E[q*p + i] = e_i(x_q)
+    // rotational / upwinded operators (RotMat, RotMat_up, Phmat::assemble_up; src/Assembly.cpp:1346-1395, 1784-1853, 499-567)
+    const int* el0;               // [nel_total][(p+1)^2] element -> node
+    const double* q0;             // 0-form coefficient (potential vorticity), column layout
+    const double* u1;             // 1-form advecting velocity (upwinded variants), column layout
+    const double* J4;             // [nel_total][q2][4] Jacobian J00 J01 J10 J11
+    const double* det;            // [nel_total][q2]
+    const double* Wr;             // [nel_total][q2] w_q * (J00 J11 - J01 J10) / det   (= +-w_q)
+    double tau;                   // upwinding time scale fac*dt
+    double xn[kMaxP + 1];         // GLL nodes
 };
 
 // Division of a 32-bit index by a launch-constant divisor (Granlund-Montgomery):
@@ -108,6 +117,15 @@ struct NodeArgs {
     const double* x;
     double* y;
     double E[(kMaxP + 1) * kMaxP];
+    // Phmat::assemble_up
+    const int* el0;
+    const int* el1x;
+    const int* el1y;
+    const double* u1;
+    const double* J4;
+    const double* det;
+    double tau;
+    double xn[kMaxP + 1];
 };
 
 }  // namespace mimsem
@@ -149,6 +167,19 @@ struct M1Slots {
     static constexpr int GW = (P + 1) * (P + 1) * 3;
     static constexpr int GS = GW + 2 * (P + 1);
     static constexpr int GEO = ((GS + 2 * (P + 1)) + 1) / 2 * 2;
+};
+
+// Slot map of the K (WtQUmat) tile: the element's x edges as in M1Slots, the same block again for the velocity
+// coefficient u1, then the inverse thickness; element-local (no neighbour data).  The geometry record is M1(h)'s.
+template <int P>
+struct KSlots {
+    static constexpr int OX = 0;
+    static constexpr int OY = P * P;
+    static constexpr int XE = 2 * P * P;
+    static constexpr int YN = XE + P;
+    static constexpr int U0 = YN + P;            // u1 block: same layout, offset U0
+    static constexpr int T = 2 * U0;
+    static constexpr int NS = T + (P + 1) * (P + 1);
 };
 
 struct CopyEnt {      // 16 bytes

@@ -379,6 +379,233 @@ __global__ void __launch_bounds__(128) k_apply_m1_lines(const __grid_constant__ 
     for (int j = 0; j < P; j++) y[(size_t)io[j] * ld] = out[j];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rotational term R(q) and its potential-vorticity-upwinded variant (BASELINE config 2).
+//   RotMat::assemble(q0)             y^x = U^T [-c ul1(x)],  y^y = V^T [+c ul0(x)],  c = s t^tpow w sigma q_q
+//   RotMat_up::assemble(q0,ul,fac,dt) the same with q_q replaced by the element's nodal interpolant of q0 at the
+//                                    departure point xi_q - tau J^-1 u_g(xi_q), tau = fac dt
+// (src/Assembly.cpp:1346-1395, 1784-1853; eul/Assembly.cpp:1030-1083 adds t^2 and scale; sigma = det J / |det|).
+// One thread per (element, level), structured like k_apply_m1: shared edges by gather from the west / south neighbour.
+
+// Lagrange polynomials through the GLL nodes at x (LagrangeNode::eval_q, src/Basis.cpp:183-190)
+template <int P>
+__device__ __forceinline__ void lagrange_at(const double* xn, double x, double (&l)[P + 1]) {
+#pragma unroll
+    for (int i = 0; i <= P; i++) {
+        double y = 1.0;
+#pragma unroll
+        for (int j = 0; j <= P; j++)
+            if (j != i) y *= (x - xn[j]) / (xn[i] - xn[j]);
+        l[i] = y;
+    }
+}
+
+// departure point of quadrature point (qx,qy) of element n given the local velocity components there
+template <int P, class A>
+__device__ __forceinline__ void departure_basis(const A& a, int n, int qx, int qy, double ul0, double ul1, double (&lx)[P + 1],
+                                                double (&ly)[P + 1]) {
+    constexpr int Q2 = (P + 1) * (P + 1);
+    const int q = qy * (P + 1) + qx;
+    const double* __restrict__ J = a.J4 + ((size_t)n * Q2 + q) * 4;
+    const double det = a.det[(size_t)n * Q2 + q];
+    // interp1_g (src/Geom.cpp:302-313), then J^-1 (src/Assembly.cpp:1815-1816)
+    const double ux0 = (J[0] * ul0 + J[1] * ul1) / det;
+    const double ux1 = (J[2] * ul0 + J[3] * ul1) / det;
+    const double v0 = +J[3] * ux0 / det - J[1] * ux1 / det;
+    const double v1 = -J[2] * ux0 / det + J[0] * ux1 / det;
+    lagrange_at<P>(a.xn, a.xn[qx] - a.tau * v0, lx);
+    lagrange_at<P>(a.xn, a.xn[qy] - a.tau * v1, ly);
+}
+
+// potential vorticity seen by quadrature point (qx,qy) of element n, column k
+template <int P, bool UP>
+__device__ __forceinline__ double rot_vort(const KArgs& a, int n, int qx, int qy, int k) {
+    using D = ElDim<P>;
+    const int* __restrict__ n0 = a.el0 + (size_t)n * D::Q2;
+    const size_t ld = a.ld;
+    if (!UP) return ldro(a.q0 + (size_t)n0[qy * D::NP1 + qx] * ld + k);
+    const double* __restrict__ u = a.u1 + k;
+    const int* __restrict__ nx = a.el1x + (size_t)n * D::N1E;
+    const int* __restrict__ ny = a.el1y + (size_t)n * D::N1E;
+    double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+    for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * ldro(u + (size_t)nx[iy * D::NP1 + qx] * ld);
+#pragma unroll
+    for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * ldro(u + (size_t)ny[qy * P + ix] * ld);
+    double lx[P + 1], ly[P + 1];
+    departure_basis<P>(a, n, qx, qy, ul0, ul1, lx, ly);
+    double v = 0.0;
+#pragma unroll
+    for (int jy = 0; jy <= P; jy++)
+#pragma unroll
+        for (int jx = 0; jx <= P; jx++) v += ldro(a.q0 + (size_t)n0[jy * D::NP1 + jx] * ld + k) * lx[jx] * ly[jy];
+    return v;
+}
+
+// neighbour n's contribution to the P edges of its far side (side 0: east column of x-edges, 1: north row of y-edges)
+template <int P, bool UP>
+__device__ __forceinline__ void rot_far_side(const KArgs& a, int n, int side, bool rev, int k, double (&out)[P]) {
+    using D = ElDim<P>;
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    const int* __restrict__ nx = a.el1x + (size_t)n * D::N1E;
+    const int* __restrict__ ny = a.el1y + (size_t)n * D::N1E;
+    const int* __restrict__ nq = a.elq + (size_t)n * D::Q2;
+    double f[P + 1];
+#pragma unroll
+    for (int t = 0; t <= P; t++) {
+        const int qx = side == 0 ? P : t, qy = side == 0 ? t : P;
+        const int q = qy * D::NP1 + qx;
+        const double c = thick_factor(a, nq[q], k) * a.Wr[(size_t)n * D::Q2 + q] * rot_vort<P, UP>(a, n, qx, qy, k);
+        if (side == 0) {
+            double ul1 = 0.0;   // east column x-edges receive -c ul1
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * ldro(x + (size_t)ny[qy * P + ix] * ld);
+            f[t] = -c * ul1;
+        } else {
+            double ul0 = 0.0;   // north row y-edges receive +c ul0
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * ldro(x + (size_t)nx[iy * D::NP1 + qx] * ld);
+            f[t] = c * ul0;
+        }
+    }
+    double o[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t <= P; t++) s += a.E[t * P + i] * f[t];
+        o[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) out[i] = rev ? o[P - 1 - i] : o[i];
+}
+
+template <int P, bool UP>
+__global__ void __launch_bounds__(128) k_apply_rot(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (a.elist) e = a.elist[e];
+    const size_t ld = a.ld;
+    const double* __restrict__ x = a.x + k;
+    double* __restrict__ y = a.y + k;
+    const int* __restrict__ ex = a.el1x + (size_t)e * D::N1E;
+    const int* __restrict__ ey = a.el1y + (size_t)e * D::N1E;
+    const int* __restrict__ eq = a.elq + (size_t)e * D::Q2;
+    double xy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) xy[iy][ix] = ldro(x + (size_t)ey[iy * P + ix] * ld);
+    double xx[P][P + 1];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix <= P; ix++) xx[iy][ix] = ldro(x + (size_t)ex[iy * D::NP1 + ix] * ld);
+    double cw[P], cs[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) cw[i] = cs[i] = 0.0;
+    const int nw = a.nbr[2 * e + 0], ns = a.nbr[2 * e + 1];
+    if (nw >= 0) rot_far_side<P, UP>(a, nw & 0x1fffffff, (nw >> 29) & 1, (nw >> 30) & 1, k, cw);
+    if (ns >= 0) rot_far_side<P, UP>(a, ns & 0x1fffffff, (ns >> 29) & 1, (ns >> 30) & 1, k, cs);
+    const unsigned flags = a.eflags[e];
+    double yy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) yy[iy][ix] = 0.0;
+#pragma unroll
+    for (int qx = 0; qx <= P; qx++) {
+        double f0[P + 1];
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double ul0 = 0.0, ul1 = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * xx[iy][qx];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * xy[qy][ix];
+            const int q = qy * D::NP1 + qx;
+            const double c = thick_factor(a, eq[q], k) * a.Wr[(size_t)e * D::Q2 + q] * rot_vort<P, UP>(a, e, qx, qy, k);
+            f0[qy] = -c * ul1;
+            const double f1 = c * ul0;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) yy[qy][ix] += a.E[qx * P + ix] * f1;
+        }
+        if (qx < P || (flags & 1u)) {
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                double s = (qx == 0) ? cw[iy] : 0.0;
+#pragma unroll
+                for (int qy = 0; qy <= P; qy++) s += a.E[qy * P + iy] * f0[qy];
+                y[(size_t)ex[iy * D::NP1 + qx] * ld] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)ey[iy * P + ix] * ld] = yy[iy][ix] + (iy == 0 ? cs[ix] : 0.0);
+    if (flags & 2u) {
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) y[(size_t)ey[P * P + ix] * ld] = yy[P][ix];
+    }
+}
+
+// Phmat::assemble_up(ul, hl, fac, dt) followed by MatMult (src/Assembly.cpp:499-567): with m == p the test basis is
+// nodal, so row n collects, from every (element, quadrature point) at the node,
+//   y_n = sum_{(e,q) at n} w_q hl^e_q(h) * [element e's nodal interpolant of x at xi_q - tau J^-1 u_g(xi_q)].
+// One thread per (node, level).
+template <int P>
+__global__ void __launch_bounds__(128) k_apply_m0h_up(const __grid_constant__ NodeArgs a) {
+    using D = ElDim<P>;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
+    const int n = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)n * (unsigned)a.nlev);
+    const size_t ld = a.ld;
+    double f = a.scale;
+    if (a.tpow > 0) {
+        const double t = ldro(a.tinv + (size_t)a.node_q[n] * a.nkT + a.lev0 + k * a.lev_stride);
+        f *= t;
+        if (a.tpow > 1) f *= t;
+    }
+    const double* __restrict__ h = a.c + k;
+    const double* __restrict__ u = a.u1 + k;
+    double acc = 0.0;
+    for (int j = a.adj_ptr[n]; j < a.adj_ptr[n + 1]; j++) {
+        const int eqv = a.adj_eq[j];
+        const int e = eqv / D::Q2, q = eqv - e * D::Q2;
+        const int qx = q % D::NP1, qy = q / D::NP1;
+        const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
+        const int* __restrict__ e0 = a.el0 + (size_t)e * D::Q2;
+        const int* __restrict__ ex = a.el1x + (size_t)e * D::N1E;
+        const int* __restrict__ ey = a.el1y + (size_t)e * D::N1E;
+        double hl = 0.0;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double s = 0.0;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * ldro(h + (size_t)e2[iy * P + ix] * ld);
+            hl += a.E[qy * P + iy] * s;
+        }
+        double ul0 = 0.0, ul1 = 0.0;
+        for (int iy = 0; iy < P; iy++) ul0 += a.E[qy * P + iy] * ldro(u + (size_t)ex[iy * D::NP1 + qx] * ld);
+        for (int ix = 0; ix < P; ix++) ul1 += a.E[qx * P + ix] * ldro(u + (size_t)ey[qy * P + ix] * ld);
+        double lx[P + 1], ly[P + 1];
+        departure_basis<P>(a, e, qx, qy, ul0, ul1, lx, ly);
+        double v = 0.0;
+#pragma unroll
+        for (int jy = 0; jy <= P; jy++)
+#pragma unroll
+            for (int jx = 0; jx <= P; jx++) v += ldro(a.x + (size_t)e0[jy * D::NP1 + jx] * ld + k) * lx[jx] * ly[jy];
+        acc += a.wq[q] * hl * v;
+    }
+    a.y[(size_t)n * ld + k] = f * acc;
+}
+
 // y = M2 x   (WITH_H: M2(rho) x)
 template <int P, bool WITH_H>
 __global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs a) {
@@ -640,7 +867,7 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // spin until *p >= want; gives up after ~4e9 cycles (a dead peer must not hang the GPU) and records the failure
-__device__ __forceinline__ void spin_until(const unsigned long long* p, unsigned long long want, int* err) {
+__device__ __noinline__ void spin_until(const unsigned long long* p, unsigned long long want, int* err) {
     const long long t0 = clock64();
     while (ld_acquire_sys(p) < want) {
         if (clock64() - t0 > 4000000000ll) {
@@ -660,7 +887,7 @@ __global__ void __launch_bounds__(256) k_halo(const HaloPeer* __restrict__ peers
                                                const unsigned long long* __restrict__ epoch, unsigned* counters, int* err) {
     const HaloPeer p = peers[blockIdx.x];
     const unsigned long long e = *epoch + 1;
-    double* box = p.inbox + (e & 1) * p.inbox_parity_stride;
+    double* box = p.inbox + (e & 1) * p.inbox_parity_stride + (size_t)p.row0 * nlev;
     if (threadIdx.x == 0) {
         // PUSH: the receiver must have consumed the buffer of epoch e-2 (same parity) ; PULL: the data of epoch e must have landed
         if (PUSH) {

@@ -3,6 +3,7 @@
 #include <cstdint>
 
 #include "engine.cuh"
+#include "kernels.cuh"
 
 namespace mimsem {
 
@@ -54,10 +55,78 @@ __device__ __forceinline__ void bulk_commit_wait_read() {
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Push role of the fused ghost refresh: CTA b of push_ctas copies its share of every peer's rows into that peer's
+// inbox (16-byte accesses, lanes along the levels) and the last CTA to finish a peer raises that peer's flag.
+__device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long epoch) {
+    const HaloFused& h = a.halo;
+    // the peer must have consumed the inbox copy of epoch - 2 (same parity)
+    if (epoch > 2)
+        for (int p = threadIdx.x; p < h.npush; p += blockDim.x) spin_until(h.push[p].wait, epoch - 2, h.err);
+    __syncthreads();
+    const int nl2 = a.nlev >> 1;
+    for (int p = 0; p < h.npush; p++) {
+        const HaloPeer pp = h.push[p];
+        const int r0 = (int)(((long long)pp.nrows * blockIdx.x) / h.push_ctas);
+        const int r1 = (int)(((long long)pp.nrows * (blockIdx.x + 1)) / h.push_ctas);
+        double2* box = reinterpret_cast<double2*>(pp.inbox + (epoch & 1ull) * pp.inbox_parity_stride + (size_t)pp.row0 * a.nlev);
+        const int total = (a.debug & 4) ? 0 : (r1 - r0) * nl2;   // debug bit 2: signal without copying (timing experiment)
+        // four independent 16-byte loads in flight per thread before the peer stores (the copy is latency-bound)
+        constexpr int U = 4;
+        for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+            double2 v[U];
+            size_t dst[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = base + u * blockDim.x;
+                if (i < total) {
+                    const int r = r0 + i / nl2, k2 = i - (r - r0) * nl2;
+                    v[u] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)pp.rows[r] * a.ld) + k2);
+                    dst[u] = (size_t)r * nl2 + k2;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (base + u * (int)blockDim.x < total) box[dst[u]] = v[u];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < h.npush; p++) {
+            const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
+            if (done == (unsigned)h.push_ctas - 1) {
+                h.counters[1 + p] = 0;
+                __threadfence_system();
+                st_release_sys(h.push[p].signal, epoch);
+            }
+        }
+    }
+}
+
+// Every CTA of a fused launch ends here; the last one acknowledges the inbox of this epoch to the peers (all bulk
+// loads from it have completed) and advances the epoch for the next launch / graph replay.
+__device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long epoch) {
+    // only the push CTAs and the boundary tiles take part (interior tiles neither read the epoch nor touch the inbox)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&a.halo.counters[0], 1u);
+        if (done == (unsigned)(a.halo.push_ctas + a.ntiles - a.halo.n_int) - 1) {
+            a.halo.counters[0] = 0;
+            for (int i = 0; i < a.halo.npull; i++) st_release_sys(a.halo.pull[i].signal, epoch);
+            a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
+            a.halo.epoch[1] = epoch;
+            __threadfence();
+        }
+    }
+}
+
 // Stage one tile: warp 0 walks the element's copy list (one entry per lane and round)
-__device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, double* geo, double* tile) {
+template <bool HALO>
+__device__ __forceinline__ void tile_load(const TArgs& a, int e, int tile_i, unsigned long long epoch, uint64_t* bar, double* geo,
+                                          double* tile) {
     const TileHdr* rec = a.recs + (size_t)e * (1 + a.rec_ents);
     const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + 1);
     const int lane = threadIdx.x;
@@ -67,6 +136,15 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, 
     const unsigned slot_bytes = (unsigned)a.nlev * 8u;
     const bool with_t = a.tpow > 0;
     int skipped = 0;
+    const double* inbox = nullptr;
+    if (HALO && tile_i >= a.halo.n_int) {
+        // boundary tile: the peers' rows of this epoch must have landed in my inbox (lane i watches peer i)
+        if (!(a.debug & 8))   // debug bit 3: do not wait for the peers (timing experiment)
+            for (int i = lane; i < a.halo.npull; i += 32) spin_until(a.halo.pull[i].wait, epoch, a.halo.err);
+        __syncwarp();
+        fence_async_all();   // the peers' generic-proxy stores are read by the async proxy (TMA) below
+        inbox = a.halo.inbox + (epoch & 1ull) * a.halo.parity_stride;
+    }
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = (ci == lane) ? first : ents[ci];
         if (c.kind == 2 && !with_t) continue;
@@ -76,6 +154,9 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, uint64_t* bar, 
         }
         if (c.kind == 3) {
             bulk_g2s(geo, a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u, bar);
+        } else if (HALO && c.kind == 4) {
+            // ghost rows of x, straight from the inbox (rows packed with stride nlev)
+            bulk_g2s(tile + (size_t)c.slot * a.nlev, inbox + (size_t)c.src * a.nlev, slot_bytes * c.count, bar);
         } else if (c.kind == 2) {
             const double* src = a.tinv + (size_t)c.src * a.nkT + a.lev0;
             double* dst = tile + (size_t)c.slot * a.nlev;
@@ -296,7 +377,9 @@ __device__ __forceinline__ void tile_compute(const TArgs& a, const double* col, 
 // y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 warp-pairs (x-normal / y-normal edges) x 64 level
 // lanes.  (A 4-warp-pair split -- direction x half of the lines -- was measured slower: 165 vs 121 us on C5.)
 // NL = compile-time number of levels (0: runtime) so that shared-memory operands use immediate offsets.
-template <int P, bool WITH_H, int NL>
+// HALO: ghost refresh fused into the launch (see HaloFused); a separate instantiation so that the single-GPU kernel
+// carries none of its code.
+template <int P, bool WITH_H, int NL, bool HALO>
 __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TArgs a) {
     using S = M1Slots<P>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -306,17 +389,30 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
     const int part = threadIdx.x >> 6;
     const int k = threadIdx.x & 63;
     const int nl = NL ? NL : a.nlev;
+    unsigned long long epoch = 0;
+    int first_tile = blockIdx.x, tile_stride = gridDim.x;
+    if (HALO) {
+        if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) epoch = *a.halo.epoch + 1;
+        if ((int)blockIdx.x < a.halo.push_ctas) {
+            halo_push_role(a, epoch);
+            halo_cta_done(a, epoch);
+            return;
+        }
+        first_tile -= a.halo.push_ctas;
+        tile_stride -= a.halo.push_ctas;
+    }
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_async_smem();
     }
     __syncthreads();
-    // optionally persistent: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    // optionally persistent: tiles first_tile, first_tile + tile_stride, ...
+    const int tile_end = a.ntiles;
     unsigned phase = 0;
-    for (int tile_i = blockIdx.x; tile_i < a.ntiles; tile_i += gridDim.x, phase ^= 1) {
+    for (int tile_i = first_tile; tile_i < tile_end; tile_i += tile_stride, phase ^= 1) {
         const int e = a.elist ? a.elist[tile_i] : tile_i;
         DBG_T(0);
-        if (threadIdx.x < 32) tile_load(a, e, bar, geo, tile);
+        if (threadIdx.x < 32) tile_load<HALO>(a, e, tile_i, epoch, bar, geo, tile);
         else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && tile_i + a.prefetch_ahead < a.ntiles) {
             const int bn = tile_i + a.prefetch_ahead;
             tile_prefetch(a, a.elist ? a.elist[bn] : bn);
@@ -338,7 +434,130 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
         }
         DBG_T(3);
         DBG_T(4);
-        if (gridDim.x < (unsigned)a.ntiles) __syncthreads();   // persistent: the next tile's bulk loads overwrite the buffer
+        if (tile_i + tile_stride < tile_end) __syncthreads();   // the next tile's bulk loads overwrite the buffer
+    }
+    if (HALO && first_tile >= a.halo.n_int) halo_cta_done(a, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = K(u1) x (WtQUmat, eul/Assembly.cpp:933-986): 1-form -> 2-form, element-local.  One CTA per element, 128 threads =
+// 2 parts x 64 level lanes; part 0 takes the quadrature columns qx < (P+1)/2, part 1 the rest; the two partial
+// P x P results are exchanged through the (by then dead) thickness slots and each part stores half of the rows.
+template <int P, int NL, int PART>
+__device__ __forceinline__ void k_tile_compute(const TArgs& a, const double* col, const double* geo, double (&out)[P][P]) {
+    using S = KSlots<P>;
+    constexpr int NP1 = P + 1;
+    constexpr int Q0 = PART == 0 ? 0 : NP1 / 2, Q1 = PART == 0 ? NP1 / 2 : NP1;
+    const int nl = NL ? NL : a.nlev;
+#define SLOT(s) col[(size_t)(s) * nl]
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) out[iy][ix] = 0.0;
+#pragma unroll
+    for (int qx = Q0; qx < Q1; qx++) {
+        double xc[P], uc[P];
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            const int s = qx < P ? S::OX + qx * P + iy : S::XE + iy;
+            xc[iy] = SLOT(s);
+            uc[iy] = SLOT(S::U0 + s);
+        }
+        double g[NP1];
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double x0 = 0.0, x1 = 0.0, a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) {
+                x0 += a.E[qy * P + iy] * xc[iy];
+                a0 += a.E[qy * P + iy] * uc[iy];
+            }
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) {
+                const int s = qy < P ? S::OY + qy * P + ix : S::YN + ix;
+                x1 += a.E[qx * P + ix] * SLOT(s);
+                a1 += a.E[qx * P + ix] * SLOT(S::U0 + s);
+            }
+            const int q = qy * NP1 + qx;
+            double f = a.scale;
+            if (a.tpow > 0) {
+                const double t = SLOT(S::T + q);
+                f *= t;
+                if (a.tpow > 1) f *= t;
+            }
+            const double c = 0.5 * f;
+            const double ka = geo[q * 3 + 0] * a0 + geo[q * 3 + 1] * a1;
+            const double kb = geo[q * 3 + 1] * a0 + geo[q * 3 + 2] * a1;
+            g[qy] = c * (ka * x0 + kb * x1);
+        }
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double b = 0.0;
+#pragma unroll
+            for (int qy = 0; qy <= P; qy++) b += a.E[qy * P + iy] * g[qy];
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) out[iy][ix] += a.E[qx * P + ix] * b;
+        }
+    }
+#undef SLOT
+}
+
+template <int P, int NL>
+__global__ void __launch_bounds__(128, (P <= 4 ? 4 : 2)) k_apply_k_tma(const __grid_constant__ TArgs a) {
+    using S = KSlots<P>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* geo = reinterpret_cast<double*>(smem_raw + 16);
+    double* tile = geo + M1Slots<P>::GEO;
+    const int part = threadIdx.x >> 6;
+    const int k = threadIdx.x & 63;
+    const int nl = NL ? NL : a.nlev;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_async_smem();
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    for (int tile_i = blockIdx.x; tile_i < a.ntiles; tile_i += gridDim.x, phase ^= 1) {
+        const int e = a.elist ? a.elist[tile_i] : tile_i;
+        if (threadIdx.x < 32) tile_load<false>(a, e, tile_i, 0ull, bar, geo, tile);
+        else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && tile_i + a.prefetch_ahead < a.ntiles) {
+            const int bn = tile_i + a.prefetch_ahead;
+            tile_prefetch(a, a.elist ? a.elist[bn] : bn);
+        }
+        const TileHdr hd = a.recs[(size_t)e * (1 + a.rec_ents)];
+        mbar_wait(bar, phase);
+        const bool active = k < nl;
+        double* col = tile + k;
+        double out[P][P];
+        if (active) {
+            if (part == 0) k_tile_compute<P, NL, 0>(a, col, geo, out);
+            else k_tile_compute<P, NL, 1>(a, col, geo, out);
+        }
+        __syncthreads();   // every read of the tile is done: the thickness slots become the exchange buffer
+        constexpr int H0 = P / 2;   // part 0 finishes rows [0, H0), part 1 rows [H0, P)
+        if (active) {
+            // hand the rows the OTHER part finishes over to it (slot = row-major face index)
+#pragma unroll
+            for (int iy = 0; iy < P; iy++)
+#pragma unroll
+                for (int ix = 0; ix < P; ix++)
+                    if ((iy < H0) != (part == 0)) col[(size_t)(S::T + iy * P + ix) * nl] = out[iy][ix];
+        }
+        __syncthreads();
+        if (active) {
+            double* __restrict__ y = a.y + (size_t)hd.st_dof * a.ld + k;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++)
+#pragma unroll
+                for (int ix = 0; ix < P; ix++)
+                    if ((iy < H0) == (part == 0)) {
+                        // part 0's share (low qx) is always the first addend: the result does not depend on the part
+                        const double o = col[(size_t)(S::T + iy * P + ix) * nl];
+                        y[(size_t)(iy * P + ix) * a.ld] = part == 0 ? out[iy][ix] + o : o + out[iy][ix];
+                    }
+        }
+        if (gridDim.x < (unsigned)a.ntiles) __syncthreads();
     }
 }
 

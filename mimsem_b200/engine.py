@@ -102,6 +102,10 @@ class Engine:
     # ---------------------------------------------------------------- helpers
     def space_sizes(self, op):
         n0, n1, n2 = self.n0, self.n1, self.n2
+        if op in ("R", "R_up"):
+            return (n1, n1, n0)
+        if op == "M0h_up":
+            return (n0, n0, n2)
         return {"M1": (n1, n1, 0), "M1h": (n1, n1, n2), "M2": (n2, n2, 0), "M2h": (n2, n2, n2), "M0": (n0, n0, 0),
                 "M0h": (n0, n0, n2), "K": (n1, n2, n1), "E10": (n0, n1, 0), "E01": (n1, n0, 0), "E21": (n1, n2, 0),
                 "E12": (n2, n1, 0)}[op]
@@ -145,10 +149,12 @@ class Engine:
 
     SPACES = {"M1": (1, 1, None), "M1h": (1, 1, 2), "M2": (2, 2, None), "M2h": (2, 2, 2), "M0": (0, 0, None),
               "M0h": (0, 0, 2), "K": (1, 2, 1), "E10": (0, 1, None), "E01": (1, 0, None), "E21": (1, 2, None),
-              "E12": (2, 1, None)}
+              "E12": (2, 1, None), "R": (1, 1, 0), "R_up": (1, 1, 0), "M0h_up": (0, 0, 2)}
 
     # ---------------------------------------------------------------- applies (device resident)
-    def apply(self, op, x, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0):
+    def apply(self, op, x, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0, u1=None, tau=0.0):
+        """R / R_up / M0h_up (RotMat, RotMat_up, Phmat::assemble_up): coeff = q0 (0-form) resp. h2 (2-form),
+        u1 = advecting 1-form velocity, tau = fac*dt."""
         nin, nout, ncoef = self.space_sizes(op)
         nlev = x.shape[1]
         self._chk(x, nin, nlev, "x")
@@ -163,7 +169,15 @@ class Engine:
         st = self._stream()
         h, L = self._h, self.L
         xp, yp = x.data_ptr(), out.data_ptr()
-        if op in ("M1", "M2", "M0"):
+        if op in ("R_up", "M0h_up"):
+            if u1 is None:
+                raise MimsemError("operator %s needs the advecting velocity u1" % op)
+            self._chk(u1, self.n1, nlev, "u1")
+            fn = getattr(L, "mimsem_gpu_apply_" + op)
+            check(fn(h, lev0, nlev, nlev, scale, tpow, flags, coeff.data_ptr(), u1.data_ptr(), tau, xp, yp, st))
+        elif op == "R":
+            check(L.mimsem_gpu_apply_R(h, lev0, nlev, nlev, scale, tpow, flags, coeff.data_ptr(), xp, yp, st))
+        elif op in ("M1", "M2", "M0"):
             fn = getattr(L, "mimsem_gpu_apply_" + op)
             check(fn(h, lev0, nlev, nlev, scale, tpow, flags, xp, yp, st))
         elif op in ("M1h", "M2h", "M0h", "K"):

@@ -95,6 +95,8 @@ struct MimsemShell {
     int lev = 0, tpow = 0, flags = 0;
     double scale = 1.0;
     std::vector<double> coeff;   // coefficient field in the rank-local numbering, copied at assemble() time
+    std::vector<double> u1;      // advecting velocity of the upwinded operators (ghosted local 1-form)
+    double tau = 0.0;            // fac*dt
     Vec xl = NULL, yl = NULL;    // ghosted local work vectors
     Mat mat = NULL;
 };
@@ -129,7 +131,8 @@ PetscErrorCode shell_mult(Mat A, Vec x, Vec y) {
     if (s->sout == 2) VecGetArray(y, &ya);
     else VecGetArray(s->yl, &ya);
     // 2. the CUDA kernels (single level: one column)
-    if (mimsem_gpu_apply_host(p->ctx, s->op, s->lev, 1, s->scale, s->tpow, s->flags, s->coeff.empty() ? NULL : s->coeff.data(), xa, ya))
+    if (mimsem_gpu_apply_host_up(p->ctx, s->op, s->lev, 1, s->scale, s->tpow, s->flags, s->coeff.empty() ? NULL : s->coeff.data(),
+                                 s->u1.empty() ? NULL : s->u1.data(), s->tau, xa, ya))
         die("mimsem_gpu_apply_host");
     if (s->sin == 2) VecRestoreArray(x, &xa);
     else VecRestoreArray(s->xl, &xa);
@@ -175,7 +178,7 @@ void copy_coeff(MimsemShell* s, Vec v, int n) {
     VecRestoreArray(v, &a);
 }
 
-enum { OP_M1 = 0, OP_M2 = 1, OP_M0 = 2, OP_M1H = 3, OP_K = 4, OP_M2H = 5, OP_M0H = 6, OP_INC = 10 };
+enum { OP_M1 = 0, OP_M2 = 1, OP_M0 = 2, OP_M1H = 3, OP_K = 4, OP_M2H = 5, OP_M0H = 6, OP_R = 7, OP_R_UP = 8, OP_M0H_UP = 9, OP_INC = 10 };
 
 }  // namespace
 
@@ -262,6 +265,67 @@ void WtQUmat::assemble(Vec u1, int lev, double scale) {   // eul/Assembly.cpp:93
     sh->lev = lev;
     sh->scale = scale;
     sh->tpow = 2;
+}
+
+RotMat::RotMat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    attach(topo, geom);
+    sh = make_shell(topo, OP_R, 1, 1, &M);
+}
+RotMat::~RotMat() { free_shell(sh, &M); }
+void RotMat::assemble(Vec q0, int lev, double scale) {   // eul/Assembly.cpp:1030-1083: vort/thick and Qab/thick
+    copy_coeff(sh, q0, topo->n0);
+    sh->lev = lev;
+    sh->scale = scale;
+    sh->tpow = 2;
+}
+void RotMat::assemble(Vec q0) {   // src/Assembly.cpp:1346-1395
+    copy_coeff(sh, q0, topo->n0);
+    sh->lev = 0;
+    sh->scale = 1.0;
+    sh->tpow = 0;
+}
+
+RotMat_up::RotMat_up(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    attach(topo, geom);
+    sh = make_shell(topo, OP_R_UP, 1, 1, &M);
+}
+RotMat_up::~RotMat_up() { free_shell(sh, &M); }
+void RotMat_up::assemble(Vec q0, Vec ul, double tau, double dt) {   // src/Assembly.cpp:1784-1853: tau_eff = tau*dt (:1818)
+    copy_coeff(sh, q0, topo->n0);
+    PetscScalar* a;
+    VecGetArray(ul, &a);
+    sh->u1.assign(a, a + topo->n1);
+    VecRestoreArray(ul, &a);
+    sh->tau = tau * dt;
+    sh->lev = 0;
+    sh->scale = 1.0;
+    sh->tpow = 0;
+}
+
+Phmat::Phmat(Topo* _topo, Geom* _geom, LagrangeNode* _node) : topo(_topo), geom(_geom), node(_node) {
+    attach(topo, geom);
+    sh = make_shell(topo, OP_M0H, 0, 0, &M);
+}
+Phmat::~Phmat() { free_shell(sh, &M); }
+void Phmat::assemble(Vec h2) {   // src/Assembly.cpp:396-442
+    sh->op = OP_M0H;
+    copy_coeff(sh, h2, topo->n2);
+    sh->u1.clear();
+    sh->lev = 0;
+    sh->scale = 1.0;
+    sh->tpow = 0;
+}
+void Phmat::assemble_up(Vec ul, Vec hl, double fac, double dt) {   // src/Assembly.cpp:499-567
+    sh->op = OP_M0H_UP;
+    copy_coeff(sh, hl, topo->n2);
+    PetscScalar* a;
+    VecGetArray(ul, &a);
+    sh->u1.assign(a, a + topo->n1);
+    VecRestoreArray(ul, &a);
+    sh->tau = fac * dt;
+    sh->lev = 0;
+    sh->scale = 1.0;
+    sh->tpow = 0;
 }
 
 E10mat::E10mat(Topo* _topo) : topo(_topo) {

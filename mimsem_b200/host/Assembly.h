@@ -12,8 +12,10 @@
 // petsc_compat.h where PETSc is unavailable.
 //
 // Signatures follow eul/ (the 3-D code).  src/ has the same classes without the level / scale arguments
-// (src/Assembly.h:11, 23, 34, 77, 153) and box/ builds Umat/Wmat once in the constructor
-// (box/Assembly.h:9-25); thin wrappers for those variants are in Assembly_variants.h.
+// (src/Assembly.h:11, 23, 34, 77, 153): an eul-signature call with scale 1 on a Geom without layers is
+// that operator; the classes that exist ONLY in src/ and carry BASELINE config 2's potential-vorticity
+// upwinding (Phmat::assemble_up, RotMat_up) are mirrored below with their src/ signatures.  box/ builds
+// Umat/Wmat once in the constructor (box/Assembly.h:9-25), i.e. assemble(0, SCALE, true) here.
 #ifndef MIMSEM_HOST_ASSEMBLY_H
 #define MIMSEM_HOST_ASSEMBLY_H
 
@@ -98,6 +100,44 @@ class WtQUmat {
         Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
         Mat M;
         void assemble(Vec u1, int lev, double scale);   // u1: ghosted local 1-form (VecCreateSeq(topo->n1))
+    private:
+        MimsemShell* sh;
+};
+
+// rotational term: 1-form mass matrix weighted by a 0-form             eul/Assembly.h:148-170
+class RotMat {
+    public:
+        RotMat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~RotMat();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(Vec q0, int lev, double scale);   // q0: ghosted local 0-form; eul/Assembly.cpp:1030-1083
+        void assemble(Vec q0);                          // src/Assembly.cpp:1346-1395 (no layers, scale 1)
+    private:
+        MimsemShell* sh;
+};
+
+// rotational term with the potential vorticity upwinded along the velocity      src/Assembly.h:227-250
+class RotMat_up {
+    public:
+        RotMat_up(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~RotMat_up();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(Vec q0, Vec ul, double tau, double dt);   // src/Assembly.cpp:1784-1853; q0, ul ghosted local
+    private:
+        MimsemShell* sh;
+};
+
+// 0-form mass matrix weighted by a 2-form, optionally with the trial space upwinded      src/Assembly.h:37-49
+class Phmat {
+    public:
+        Phmat(Topo* _topo, Geom* _geom, LagrangeNode* _node);
+        ~Phmat();
+        Topo* topo; Geom* geom; LagrangeNode* node;
+        Mat M;
+        void assemble(Vec h2);                                      // src/Assembly.cpp:396-442
+        void assemble_up(Vec ul, Vec hl, double fac, double dt);    // src/Assembly.cpp:499-567
     private:
         MimsemShell* sh;
 };

@@ -74,37 +74,64 @@ class Partition:
         nbr = west_south_neighbours(mesh)[e0:e1].ravel()
         nbr = nbr[nbr >= 0]
         halo = np.setdiff1d(np.unique(nbr), owned)
+        # owned elements that read no row owned elsewhere (interior) come first, the others (boundary) last: the
+        # engine's interior / boundary subsets are then index ranges, and the fused ghost-refresh kernel walks the
+        # elements in storage order (same rule as mimsem_gpu_set_ghosts)
+        b1_, b2_ = 2 * p * p, p * p
+        def foreign(e):
+            d1 = np.concatenate([mesh.el1x[e], mesh.el1y[e]], axis=1).astype(np.int64) // b1_
+            d2 = mesh.el2[e].astype(np.int64) // b2_
+            return ((d1 < e0) | (d1 >= e1)).any(axis=1) | ((d2 < e0) | (d2 >= e1)).any(axis=1)
+        bnd = foreign(owned)
+        ws_own = west_south_neighbours(mesh)[e0:e1]
+        for side in (0, 1):
+            n = ws_own[:, side]
+            ok = n >= 0
+            bnd[ok] |= foreign(n[ok])
+        owned = np.concatenate([owned[~bnd], owned[bnd]])
+        self.n_interior = int((~bnd).sum())
         self.elements = np.concatenate([owned, halo])          # local element -> global element
         self.nel_owned, self.nel_total = len(owned), len(owned) + len(halo)
         L = self.elements
         b1, b2 = 2 * p * p, p * p
 
-        def local_numbering(ids, block):
+        def local_numbering(ids, block, needed=None):
             ids = np.unique(ids.astype(np.int64))
             own = ids[(ids // block >= e0) & (ids // block < e1)] if block else ids
             ghost = np.setdiff1d(ids, own) if block else ids[:0]
-            return np.concatenate([own, ghost]), len(own)
+            if needed is not None:
+                # ghosts some kernel actually reads come first (they are the ones exchanged), the rest after
+                need = np.intersect1d(ghost, needed)
+                ghost = np.concatenate([need, np.setdiff1d(ghost, need)])
+                return np.concatenate([own, ghost]), len(own), len(need)
+            return np.concatenate([own, ghost]), len(own), len(ghost)
+
+        # 1-form rows the kernels read: every edge of an owned element and, of a west / south halo element, the
+        # edge family ACROSS its far line (all y-normal edges behind an east column, all x-normal edges behind a
+        # north row -- the WOTH / SOTH slots of the tile kernel); the halo element's remaining edges are never read
+        ws = west_south_neighbours(mesh)
+        need = [mesh.el1x[e0:e1].ravel(), mesh.el1y[e0:e1].ravel()]
+        for side, shared in ((0, mesh.el1x[e0:e1, 0]), (1, mesh.el1y[e0:e1, 0])):
+            n = ws[e0:e1, side]
+            ok = n >= 0
+            nn, sh = n[ok], shared[ok].astype(np.int64)
+            far_is_east = (mesh.el1x[nn].astype(np.int64) == sh[:, None]).any(axis=1)
+            need.append(mesh.el1y[nn[far_is_east]].ravel())
+            need.append(mesh.el1x[nn[~far_is_east]].ravel())
+        needed1 = np.unique(np.concatenate(need).astype(np.int64))
 
         # 1-forms: edge g is owned by element g // (2 p^2); 2-forms: face g by element g // p^2
-        self.g1, self.n1_owned = local_numbering(np.concatenate([mesh.el1x[L].ravel(), mesh.el1y[L].ravel()]), b1)
-        self.g2, self.n2_owned = local_numbering(mesh.el2[L].ravel(), b2)
-        self.g0, _ = local_numbering(mesh.el0[L].ravel(), 0)
-        self.gq, _ = local_numbering(mesh.elq[L].ravel(), 0)
+        self.g1, self.n1_owned, n1_need = local_numbering(np.concatenate([mesh.el1x[L].ravel(), mesh.el1y[L].ravel()]), b1, needed1)
+        self.n1_halo = self.n1_owned + n1_need          # rows [n1_owned, n1_halo) are refreshed from their owners
+        self.g2, self.n2_owned, _ = local_numbering(mesh.el2[L].ravel(), b2)
+        self.g0, _, _ = local_numbering(mesh.el0[L].ravel(), 0)
+        self.gq, _, _ = local_numbering(mesh.elq[L].ravel(), 0)
         self.n0, self.n1, self.n2, self.nq = len(self.g0), len(self.g1), len(self.g2), len(self.gq)
 
         def to_local(gids, table):
-            # gids = [owned ascending | ghost ascending]: search both halves
-            n_own = {id(self.g1): self.n1_owned, id(self.g2): self.n2_owned}.get(id(gids), len(gids))
+            order = np.argsort(gids, kind="stable")
             t = table.astype(np.int64)
-            a = np.searchsorted(gids[:n_own], t)
-            a = np.minimum(a, max(n_own - 1, 0))
-            hit = (gids[:n_own][a] == t) if n_own else np.zeros(t.shape, bool)
-            if n_own < len(gids):
-                b = np.searchsorted(gids[n_own:], t)
-                b = np.minimum(b, len(gids) - n_own - 1)
-                out = np.where(hit, a, b + n_own)
-            else:
-                out = a
+            out = order[np.searchsorted(gids[order], t)]
             assert np.array_equal(gids[out], t)
             return out.astype(np.int32)
 
@@ -114,7 +141,7 @@ class Partition:
         self.el0 = to_local(self.g0, mesh.el0[L])
         self.elq = to_local(self.gq, mesh.elq[L])
         # ghosts grouped by owner rank (ascending global id inside a group)
-        self.recv = {1: self._group(self.g1[self.n1_owned:], b1, nel, self.n1_owned),
+        self.recv = {1: self._group(self.g1[self.n1_owned:self.n1_halo], b1, nel, self.n1_owned),
                      2: self._group(self.g2[self.n2_owned:], b2, nel, self.n2_owned)}
 
     def _group(self, ghosts, block, nel, offset):
@@ -165,6 +192,7 @@ class DistributedEngine:
         eng.set_basis(Basis(mesh.p, mesh.m))
         eng.set_topo(P.el0, P.el1x, P.el1y, P.el2, P.elq, P.n0, P.n1, P.n2, P.nq, nel_owned=P.nel_owned, mode=0)
         self.n_interior, self.n_boundary = eng.set_ghosts(P.n1_owned, P.n2_owned)
+        assert self.n_interior == P.n_interior, "partition and engine disagree on the interior / boundary split"
         eng.set_geom(mesh.J[P.elements], mesh.det[P.elements])
         if thick is not None:
             eng.set_thickness(np.ascontiguousarray(thick[:, P.gq]))
@@ -189,7 +217,9 @@ class DistributedEngine:
         self.nk_max = 1 if thick is None else int(thick.shape[0])
         self.p2p = None
         self.graph_safe = False
+        self._inbox = {}
         import os
+        self.fused = os.environ.get("MIMSEM_FUSED_HALO", "1") != "0"
         if world > 1 and os.environ.get("MIMSEM_HALO", "p2p") == "p2p":
             self._setup_p2p(P, sends)
 
@@ -207,19 +237,28 @@ class DistributedEngine:
         send_peers = {s: sorted(sends[s]) for s in spaces}
         assert all(len(v) <= MAXP for v in list(recv_peers.values()) + list(send_peers.values()))
         hdr_bytes = 4 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP]
-        layout = {}                                    # (space, peer) -> (slot, inbox offset in bytes, nrows)
+        # inbox of a space: [2 parities][ghost rows of the space, in ghost order][nk]; a peer's share is the run of
+        # rows it owns (ghosts are sorted by global id, owners hold contiguous id ranges)
+        layout = {}                                    # (space, peer) -> (slot, first inbox row, nrows)
+        region = {}                                    # space -> (offset in bytes, total ghost rows)
         off = hdr_bytes
         for si, s in enumerate(spaces):
+            n_own = {1: P.n1_owned, 2: P.n2_owned}[s]
+            row = 0
             for slot, q in enumerate(recv_peers[s]):
-                n = len(P.recv[s][q]["local"])
-                layout[(s, q)] = (slot, off, n)
-                off += 2 * n * nk * 8
+                loc = P.recv[s][q]["local"].astype(np.int64)
+                assert np.array_equal(loc, n_own + row + np.arange(len(loc))), "ghost rows of a peer must be one run"
+                layout[(s, q)] = (slot, row, len(loc))
+                row += len(loc)
+            region[s] = (off, row)
+            off += 2 * row * nk * 8
         total = max(off, hdr_bytes + 16)
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
         from .lib import check
         check(eng.L.mimsem_gpu_ipc_alloc(eng._h, total, C.byref(base), handle))
-        mine = dict(handle=handle.raw, layout=layout, send_slot={(s, q): i for s in spaces for i, q in enumerate(send_peers[s])})
+        mine = dict(handle=handle.raw, layout=layout, region=region,
+                    send_slot={(s, q): i for s in spaces for i, q in enumerate(send_peers[s])})
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
         peer_base = {}
@@ -230,7 +269,7 @@ class DistributedEngine:
                 ptr = C.c_void_p()
                 check(eng.L.mimsem_gpu_ipc_open(eng._h, everyone[q]["handle"], C.byref(ptr)))
                 peer_base[q] = ptr.value
-        dt = np.dtype([("rows", "<u8"), ("nrows", "<i4"), ("pad", "<i4"), ("inbox", "<u8"), ("stride", "<i8"), ("signal", "<u8"),
+        dt = np.dtype([("rows", "<u8"), ("nrows", "<i4"), ("row0", "<i4"), ("inbox", "<u8"), ("stride", "<i8"), ("signal", "<u8"),
                        ("wait", "<u8")])
         assert dt.itemsize == 48
         dev = "cuda:%d" % self.device
@@ -243,24 +282,27 @@ class DistributedEngine:
             for i, q in enumerate(send_peers[s]):
                 rows = torch.from_numpy(perm[sends[s][q]].astype(np.int32)).to(dev)
                 keep.append(rows)
-                slot_on_q, off_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
+                slot_on_q, row0_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
+                off_on_q, nghost_on_q = everyone[q]["region"][s]
                 assert n_on_q == rows.numel()
-                push[i] = (rows.data_ptr(), rows.numel(), 0, peer_base[q] + off_on_q, n_on_q * nk,
+                push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, nghost_on_q * nk,
                            peer_base[q] + (si * MAXP + slot_on_q) * 8,            # flag on q
                            my + (2 * MAXP + si * MAXP + i) * 8)                    # ack from q, in my memory
             pull = np.zeros(len(recv_peers[s]), dtype=dt)
+            off_b, nghost = region[s]
             for i, q in enumerate(recv_peers[s]):
                 rows = torch.from_numpy(perm[P.recv[s][q]["local"]].astype(np.int32)).to(dev)
                 keep.append(rows)
-                slot, off_b, n = layout[(s, q)]
+                slot, row0, n = layout[(s, q)]
                 ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
-                pull[i] = (rows.data_ptr(), n, 0, my + off_b, n * nk,
+                pull[i] = (rows.data_ptr(), n, row0, my + off_b, nghost * nk,
                            peer_base[q] + (2 * MAXP + si * MAXP + ack_slot_on_q) * 8,   # ack on q
                            my + (si * MAXP + slot) * 8)                                # flag from q, in my memory
             dpush = torch.from_numpy(push.view(np.uint8).copy()).to(dev)
             dpull = torch.from_numpy(pull.view(np.uint8).copy()).to(dev)
             epochs = torch.zeros(2, dtype=torch.int64, device=dev)   # [push counter, pull counter]
             plans[s] = (len(push), dpush, len(pull), dpull, epochs)
+            self._inbox[s] = (my + off_b, nghost * nk, int(sum(int(r["nrows"]) for r in push)))
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = dict(plans=plans, err=err, keep=keep, base=base, peer_base=peer_base)
         self.graph_safe = True
@@ -349,6 +391,8 @@ class DistributedEngine:
             out = self.engine.zeros(self.engine.space_sizes(op)[1], x.shape[1])
         if not (do_x or do_c):
             return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
+        if op == "M1" and self.p2p is not None and self.fused and self._fused_ok(x, kw):
+            return self._apply_m1_fused(x, out, flags, **kw)
         overlap = self.overlap and op in ("M1", "M1h", "K") and self.n_interior > 0
         if overlap and self.p2p is not None:
             # side stream: push kernels (store into the peers' inboxes over NVLink) and pull kernels (wait for the
@@ -393,6 +437,25 @@ class DistributedEngine:
         self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_INTERIOR, **kw)
         main.wait_event(done)
         self.engine.apply(op, x, coeff=coeff, out=out, flags=flags | SUBSET_BOUNDARY, **kw)
+        return out
+
+    def _fused_ok(self, x, kw):
+        nlev = x.shape[1]
+        return nlev % 2 == 0 and nlev <= 64 and nlev <= self.nk_max and self.engine.p >= 2
+
+    def _apply_m1_fused(self, x, out, flags, lev0=0, scale=1.0, tpow=0):
+        """ONE launch: push CTAs + interior tiles + boundary tiles that stage their ghost rows from the inbox
+        (mimsem_gpu_apply_M1_halo).  Shares the epoch / flag / ack words of the 1-form space with push()/pull():
+        both epoch counters advance together so the two mechanisms can be mixed."""
+        from .lib import check
+        eng = self.engine
+        npush, dpush, npull, dpull, epochs = self.p2p["plans"][1]
+        inbox, stride, push_rows = self._inbox[1]
+        nlev = x.shape[1]
+        push_ctas = max(8, min(64, push_rows // 48))     # few CTAs: their fixed cost (flag wait, system fence) is paid per CTA
+        check(eng.L.mimsem_gpu_apply_M1_halo(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(),
+                                             npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, push_ctas,
+                                             epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
         return out
 
     def capture(self, op, x, coeff=None, out=None, **kw):

@@ -408,6 +408,66 @@ class Oracle:
             self._add(e2, e1y, np.einsum("qi,eq,qj->eij", W, Qab, V), trip)
         return self._csr(trip, (self.N2, self.N1))
 
+    def _departure_tables(self, r, u1, tau):
+        """lx[e,q,j], ly[e,q,j]: LagrangeNode::eval_q at xi_q - tau J^-1 u_g(xi_q)
+        (src/Assembly.cpp:531-541 in Phmat::assemble_up, :1811-1820 in RotMat_up::assemble)."""
+        U, V = self.em["U"], self.em["V"]
+        J, det = self.J[r], self.det[r]
+        _, e1x, e1y, _ = self.inds[r]
+        mp1, np1 = self.m + 1, self.p + 1
+        ul0 = u1[e1x] @ U.T                                            # interp1_l
+        ul1 = u1[e1y] @ V.T
+        ux0 = (J[:, :, 0, 0] * ul0 + J[:, :, 0, 1] * ul1) / det        # interp1_g, src/Geom.cpp:302-313
+        ux1 = (J[:, :, 1, 0] * ul0 + J[:, :, 1, 1] * ul1) / det
+        v0 = +J[:, :, 1, 1] * ux0 / det - J[:, :, 0, 1] * ux1 / det    # ux2, src/Assembly.cpp:532-533
+        v1 = -J[:, :, 1, 0] * ux0 / det + J[:, :, 0, 0] * ux1 / det
+        xq = self.em["qx"]
+        xn = gauss_lobatto(self.p)[0]
+        q = np.arange(mp1 * mp1)
+        ptx = xq[q % mp1][None, :] - tau * v0
+        pty = xq[q // mp1][None, :] - tau * v1
+        lx = np.stack([lagrange_eval_q(xn, ptx, j) for j in range(np1)], axis=-1)
+        ly = np.stack([lagrange_eval_q(xn, pty, j) for j in range(np1)], axis=-1)
+        return lx, ly
+
+    def rotmat(self, q0, lev=0, scale=1.0, tpow=0, u1=None, tau=0.0):
+        """RotMat::assemble (src/Assembly.cpp:1346-1395; eul/Assembly.cpp:1030-1083 with tpow=2 and scale);
+        with u1: RotMat_up::assemble (src/Assembly.cpp:1784-1853), tau = fac*dt."""
+        U, V, P, Q = self.em["U"], self.em["V"], self.em["P"], self.em["Q"]
+        np1 = self.p + 1
+        trip = []
+        for r in range(self.nprocs):
+            J, det = self.J[r], self.det[r]
+            e0, e1x, e1y, _ = self.inds[r]
+            if u1 is None:
+                vort = q0[e0] @ P.T                                    # interp0
+            else:
+                lx, ly = self._departure_tables(r, u1, tau)
+                jj = np.arange(np1 * np1)
+                vort = np.einsum("ej,eqj->eq", q0[e0], lx[:, :, jj % np1] * ly[:, :, jj // np1])
+            if tpow:
+                vort = vort * self._tinv(r, lev) ** tpow
+            dj = J[:, :, 0, 0] * J[:, :, 1, 1] - J[:, :, 0, 1] * J[:, :, 1, 0]
+            Qab = vort * (-dj) * Q[None, :] * (scale / det)
+            Qba = vort * (+dj) * Q[None, :] * (scale / det)
+            self._add(e1x, e1y, np.einsum("qi,eq,qj->eij", U, Qab, V), trip)
+            self._add(e1y, e1x, np.einsum("qi,eq,qj->eij", V, Qba, U), trip)
+        return self._csr(trip, (self.N1, self.N1))
+
+    def phmat_up(self, u1, h2, tau):
+        """Phmat::assemble_up(ul, hl, fac, dt) (src/Assembly.cpp:499-567), tau = fac*dt."""
+        P, W, Q = self.em["P"], self.em["W"], self.em["Q"]
+        np1 = self.p + 1
+        trip = []
+        for r in range(self.nprocs):
+            e0, _, _, e2 = self.inds[r]
+            lx, ly = self._departure_tables(r, u1, tau)
+            hx = h2[e2] @ W.T                                          # interp2_l (no determinant)
+            jj = np.arange(np1 * np1)
+            QP = (hx * Q[None, :])[:, :, None] * lx[:, :, jj % np1] * ly[:, :, jj // np1]
+            self._add(e0, e0, np.einsum("qi,eqj->eij", P, QP), trip)
+        return self._csr(trip, (self.N0, self.N0))
+
     def e10(self):
         """E10mat::E10mat, eul/Assembly.cpp:1102-1162 (INSERT_VALUES); returns (E10, E01 = -E10^T)."""
         p = self.p

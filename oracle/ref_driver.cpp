@@ -403,6 +403,11 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
                 A->assemble(v1, lev, scale);
                 keep[rk] = A->M->t; delete A; break;
             }
+            case OP_ROTMAT: {
+                RotMat* A = new RotMat(topo, geom, o.node, o.edge);
+                A->assemble(v0, lev, scale);
+                keep[rk] = A->M->t; delete A; break;
+            }
 #endif
             case OP_E10: case OP_E01: {
                 E10mat* A = new E10mat(topo);

@@ -86,6 +86,11 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
     h2 = rng.uniform(0.5, 1.5, (nk, N2)) * 1.0e4
     u1 = rng.uniform(-1, 1, (nk, N1)) * float(np.mean(out["det"]))
     out.update(x1=x1, x2=x2, x0=x0, h2=h2, u1=u1)
+    # drawn AFTER every earlier field so that the older vectors of the fixture are unchanged
+    q0 = rng.uniform(-1, 1, (nk, N0)) * 1.0e-4          # potential vorticity
+    u1_up = u1 * 1.0e-3                                  # advecting velocity: departure points move ~0.1 element widths
+    up_fac, up_dt = 0.5, 300.0                           # UP_TAU (src/SWEqn_Picard.cpp:30) and a time step
+    out.update(q0=q0, u1_up=u1_up, up_fac=up_fac, up_dt=up_dt)
 
     def run(op, x, **kw):
         ys = []
@@ -105,18 +110,23 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
         out["y_Uhmat_cv0"] = run("Uhmat", x1, flag=False, c2=h2)
         out["y_Whmat_vs1"] = run("Whmat", x2, flag=True, c2=h2)
         out["y_WtQUmat"] = run("WtQUmat", x1, c1=u1)
+        out["y_RotMat"] = run("RotMat", x1, c0=q0)
     elif variant == "src":
         out["y_Umat"] = run("Umat", x1)
         out["y_Wmat"] = run("Wmat", x2)
         out["y_Pmat"] = run("Pmat", x0)
         out["y_Uhmat"] = run("Uhmat", x1, c2=h2)
         out["y_WtQUmat"] = run("WtQUmat", x1, c1=u1)
+        out["y_RotMat"] = run("RotMat", x1, c0=q0)
+        out["y_RotMat_up"] = run("RotMat_up", x1, c0=q0, c1=u1_up, tau=up_fac, dt=up_dt)
+        out["y_Phmat_up"] = run("Phmat_up", x0, c1=u1_up, c2=h2, tau=up_fac, dt=up_dt)
     else:  # box: Umat/Wmat are assembled once at level 0 in the ctor (box/Assembly.cpp:44-45, 171-172)
         out["y_Umat_M"] = run("Umat", x1, flag=True)
         out["y_Umat_Mo"] = run("Umat", x1, flag=False)
         out["y_Wmat_M"] = run("Wmat", x2, flag=True)
         out["y_Uhmat_cv1"] = run("Uhmat", x1, flag=True, c2=h2)
         out["y_WtQUmat"] = run("WtQUmat", x1, c1=u1)
+        out["y_RotMat"] = run("RotMat", x1, c0=q0)
     for nm in ("E10", "E01", "E21", "E12"):
         A = R.assemble(nm)
         out["%s_indptr" % nm] = A.indptr.astype(np.int64)

@@ -18,9 +18,11 @@ def _engine(kind, p, ne, thick=None, signed=False):
     return mesh, mb.Engine.from_mesh(mesh, 0, thick=thick)
 
 
-def _apply(eng, op, x, coeff=None, **kw):
+def _apply(eng, op, x, coeff=None, u1=None, **kw):
     sin, sout, sc = eng.SPACES[op]
     c = None if coeff is None else to_cols(eng, coeff, sc)
+    if u1 is not None:
+        kw["u1"] = to_cols(eng, u1, 1)
     return to_np(eng, eng.apply(op, to_cols(eng, x, sin), coeff=c, **kw), sout)
 
 
@@ -40,7 +42,8 @@ def test_eul_operators_vs_reference_golden(fname, p, ne):
     s = float(g["scale"])
     cases = [("M1", "x1", None, 1, "y_Umat_vs1"), ("M1", "x1", None, 0, "y_Umat_vs0"), ("M2", "x2", None, 1, "y_Wmat_vs1"),
              ("M0", "x0", None, 1, "y_Pmat"), ("M0h", "x0", "h2", 2, "y_Pmat_h"), ("M1h", "x1", "h2", 2, "y_Uhmat_cv1"),
-             ("M1h", "x1", "h2", 1, "y_Uhmat_cv0"), ("M2h", "x2", "h2", 2, "y_Whmat_vs1"), ("K", "x1", "u1", 2, "y_WtQUmat")]
+             ("M1h", "x1", "h2", 1, "y_Uhmat_cv0"), ("M2h", "x2", "h2", 2, "y_Whmat_vs1"), ("K", "x1", "u1", 2, "y_WtQUmat"),
+             ("R", "x1", "q0", 2, "y_RotMat")]
     for op, xk, ck, tpow, yk in cases:
         coeff = None if ck is None else g[ck]
         y = _apply(eng, op, g[xk], coeff, scale=s, tpow=tpow)
@@ -59,6 +62,17 @@ def test_src_operators_vs_reference_golden():
                            ("M1h", "x1", "h2", "y_Uhmat"), ("K", "x1", "u1", "y_WtQUmat")]:
         y = _apply(eng, op, g[xk], None if ck is None else g[ck], scale=1.0, tpow=0)
         assert rel_l2(y, g[yk]) < TOL, (op, rel_l2(y, g[yk]))
+    # BASELINE config 2: rotational term and the potential-vorticity-upwinded operators
+    tau = float(g["up_fac"]) * float(g["up_dt"])
+    y = _apply(eng, "R", g["x1"], g["q0"])
+    assert rel_l2(y, g["y_RotMat"]) < TOL, rel_l2(y, g["y_RotMat"])
+    y = _apply(eng, "R_up", g["x1"], g["q0"], u1=g["u1_up"], tau=tau)
+    assert rel_l2(y, g["y_RotMat_up"]) < TOL, rel_l2(y, g["y_RotMat_up"])
+    y = _apply(eng, "M0h_up", g["x0"], g["h2"], u1=g["u1_up"], tau=tau)
+    assert rel_l2(y, g["y_Phmat_up"]) < TOL, rel_l2(y, g["y_Phmat_up"])
+    # tau = 0 reduces the upwinded operators to the plain ones
+    assert rel_l2(_apply(eng, "R_up", g["x1"], g["q0"], u1=g["u1_up"], tau=0.0), g["y_RotMat"]) < TOL
+    assert rel_l2(_apply(eng, "M0h_up", g["x0"], g["h2"], u1=g["u1_up"], tau=0.0), _apply(eng, "M0h", g["x0"], g["h2"])) < TOL
 
 
 def test_box_operators_vs_reference_golden():
@@ -72,6 +86,7 @@ def test_box_operators_vs_reference_golden():
     assert rel_l2(_apply(eng, "M2", g["x2"], scale=s, tpow=1, flags=FL), g["y_Wmat_M"]) < TOL
     assert rel_l2(_apply(eng, "M1h", g["x1"], g["h2"], scale=s, tpow=2), g["y_Uhmat_cv1"]) < TOL
     assert rel_l2(_apply(eng, "K", g["x1"], g["u1"], scale=s, tpow=2), g["y_WtQUmat"]) < TOL
+    assert rel_l2(_apply(eng, "R", g["x1"], g["q0"], scale=s, tpow=2), g["y_RotMat"]) < TOL
 
 
 @pytest.mark.parametrize("fname,kind,p,ne", [("ops_eul_sphere_p3_ne4.npz", "sphere", 3, 4),
@@ -234,6 +249,26 @@ def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
     for v in ("1", "2"):
         for a, b in zip(res[v], res["0"]):
             assert rel_l2(a, b) < 1e-14, (v, rel_l2(a, b))
+
+
+@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
+                                          ("sphere", 5, 2, 20)])
+def test_k_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
+    """K (WtQUmat): the TMA tile kernel (default) and the thread-per-element-level kernel agree up to FP summation order."""
+    mesh = mb.Mesh(kind, p, ne)
+    thick = synthetic_thickness(mesh.xyz, nk, kind)
+    rng = np.random.default_rng(12)
+    f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+    res = {}
+    for variant in ("0", "1"):
+        monkeypatch.setenv("MIMSEM_K_VARIANT", variant)
+        eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
+        l0 = eng.launch_count
+        res[variant] = (_apply(eng, "K", f["x1"], f["u1"], scale=1e8, tpow=2), _apply(eng, "K", f["x1"], f["u1"], scale=1.0, tpow=0))
+        assert eng.launch_count > l0
+        eng.close()
+    for a, b in zip(res["1"], res["0"]):
+        assert rel_l2(a, b) < 1e-14, rel_l2(a, b)
 
 
 def test_multi_gpu_partitioned_apply():

@@ -89,3 +89,30 @@ def test_host_classes_24_ranks_vs_oracle(tmp_path):
     E21, E12 = O.e21()
     assert rel_l2(res["E01"], (E01 @ g["x1"].T).T) < TOL and rel_l2(res["E12"], (E12 @ g["x2"].T).T) < TOL
     assert rel_l2(res["E10"], (E10 @ g["x0"].T).T) < TOL and rel_l2(res["E21"], (E21 @ g["x1"].T).T) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("from_files", [False, True])
+def test_host_src_upwinded_classes_vs_reference_golden(tmp_path, from_files):
+    """BASELINE config 2: RotMat, RotMat_up and Phmat::assemble / assemble_up with the reference's src/ signatures
+    (src/Assembly.h:37-49, 227-250), 6 emulated ranks, against vectors produced by the reference's own sources."""
+    _build()
+    g = golden("ops_src_sphere_p3_ne4.npz")
+    meshdir = "-"
+    if from_files:
+        if not have_ref_mesh("sphere", 3, 4, 6):
+            pytest.skip("reference-generated mesh files not present")
+        meshdir = ref_mesh_dir("sphere", 3, 4, 6)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([g[k][0] for k in ("x1", "x0", "h2", "q0", "u1_up")]).astype("<f8").tofile(fin)
+    r = subprocess.run([BIN + "_src", meshdir, "3", "4", "6", repr(float(g["up_fac"])), repr(float(g["up_dt"])), fin, fout],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_apply_src ok" in r.stdout, r.stdout + r.stderr
+    out = np.fromfile(fout, dtype="<f8")
+    N0, N1 = int(g["N0"]), int(g["N1"])
+    assert out.size == 2 * N1 + 2 * N0
+    y_R, y_Rup, y_Ph, y_Phup = out[:N1], out[N1:2 * N1], out[2 * N1:2 * N1 + N0], out[2 * N1 + N0:]
+    assert rel_l2(y_R, g["y_RotMat"][0]) < TOL, rel_l2(y_R, g["y_RotMat"][0])
+    assert rel_l2(y_Rup, g["y_RotMat_up"][0]) < TOL, rel_l2(y_Rup, g["y_RotMat_up"][0])
+    assert rel_l2(y_Phup, g["y_Phmat_up"][0]) < TOL, rel_l2(y_Phup, g["y_Phmat_up"][0])
+    assert rel_l2(y_Ph, y_Phup) > 1e-6      # the upwinding changes the operator

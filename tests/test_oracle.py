@@ -36,6 +36,7 @@ def test_oracle_eul_vs_golden():
         assert rel_l2(O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=0) @ g["x1"][lev], g["y_Uhmat_cv0"][lev]) < TOL
         assert rel_l2(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1) @ g["x2"][lev], g["y_Whmat_vs1"][lev]) < TOL
         assert rel_l2(O.wtqumat(g["u1"][lev], lev, s) @ g["x1"][lev], g["y_WtQUmat"][lev]) < TOL
+        assert rel_l2(O.rotmat(g["q0"][lev], lev, s, 2) @ g["x1"][lev], g["y_RotMat"][lev]) < TOL
     E10, E01 = O.e10()
     E21, E12 = O.e21()
     for nm, A in (("E10", E10), ("E01", E01), ("E21", E21), ("E12", E12)):
@@ -52,6 +53,13 @@ def test_oracle_src_vs_golden():
     assert rel_l2(O.pmat(tpow=0) @ g["x0"][0], g["y_Pmat"][0]) < TOL
     assert rel_l2(O.umat(h2=g["h2"][0]) @ g["x1"][0], g["y_Uhmat"][0]) < TOL
     assert rel_l2(O.wtqumat(g["u1"][0], tpow=0) @ g["x1"][0], g["y_WtQUmat"][0]) < TOL
+    # rotational term and the PV-upwinded operators of BASELINE config 2 (src/Assembly.cpp:1346-1395, 1784-1853, 499-567)
+    tau = float(g["up_fac"]) * float(g["up_dt"])
+    assert rel_l2(O.rotmat(g["q0"][0]) @ g["x1"][0], g["y_RotMat"][0]) < TOL
+    assert rel_l2(O.rotmat(g["q0"][0], u1=g["u1_up"][0], tau=tau) @ g["x1"][0], g["y_RotMat_up"][0]) < TOL
+    assert rel_l2(O.phmat_up(g["u1_up"][0], g["h2"][0], tau) @ g["x0"][0], g["y_Phmat_up"][0]) < TOL
+    # the upwinding is not a no-op on these inputs
+    assert rel_l2(g["y_RotMat_up"][0], g["y_RotMat"][0]) > 1e-3
 
 
 @pytest.mark.skipif(not have_ref_mesh("box", 3, 4, 1), reason="oracle/_ref/meshes not generated")
@@ -67,6 +75,7 @@ def test_oracle_box_vs_golden():
         assert rel_l2(O.wmat(0, s, 1) @ g["x2"][lev], g["y_Wmat_M"][lev]) < TOL
         assert rel_l2(O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=1) @ g["x1"][lev], g["y_Uhmat_cv1"][lev]) < TOL
         assert rel_l2(O.wtqumat(g["u1"][lev], lev, s) @ g["x1"][lev], g["y_WtQUmat"][lev]) < TOL
+        assert rel_l2(O.rotmat(g["q0"][lev], lev, s, 2) @ g["x1"][lev], g["y_RotMat"][lev]) < TOL
 
 
 @pytest.mark.skipif(not (have_ref_lib("eul") and have_ref_mesh("sphere", 4, 2, 6)), reason="oracle/_ref not built")
