@@ -255,7 +255,9 @@ def main():
     # ring of distinct field sets: every step reads and writes buffers that were last touched
     # >= RING-1 steps ago; one field pair (0.42 GB on C5) already exceeds the 126 MB L2
     # (at N GPUs the per-rank slice shrinks, so the ring grows until it covers >= 4x the 126 MB L2)
-    RING = max(3, -(-4 * 126_000_000 // (16 * nin * nk)))
+    # computed from GLOBAL sizes: every rank must capture and replay the same number of steps (the ghost refresh is collective)
+    n_glob = {"M1": mesh.N1, "M1h": mesh.N1, "K": mesh.N1, "E21": mesh.N1, "M2": mesh.N2, "E12": mesh.N2, "M0": mesh.N0}[op]
+    RING = max(3, -(-4 * 126_000_000 // (16 * (n_glob // world) * nk)))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.rand((nin, nk), dtype=torch.float64, device=dev, generator=g) * 2 - 1 for _ in range(RING)]
     ys = [torch.empty((nout, nk), dtype=torch.float64, device=dev) for _ in range(RING)]
@@ -328,7 +330,10 @@ def main():
 
     # end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
+        # N > 1: every rank passes its ghosted local vector (the reference's VecCreateSeq(topo->n1) convention), so the
+        # host call needs no exchange; the aggregate is all ranks' owned output DOFs over the slowest rank's time
+        heng = eng if world == 1 else eng.engine
         hx = torch.empty((nk, nin), dtype=torch.float64).pin_memory()
         hx.uniform_(-1, 1)
         hy = torch.empty((nk, nout), dtype=torch.float64).pin_memory()
@@ -338,16 +343,26 @@ def main():
             hc.uniform_(0.5, 1.5)
         n_e2e = max(3, min(args.steps, 10))
         for _ in range(2):
-            eng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
-        torch.cuda.synchronize()
+            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
+        barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            eng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
+            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": out_dofs / dt / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * nk * (nin + ncoef),
-               "d2h_bytes_per_step": 8 * nk * nout, "ms_per_step": dt * 1e3,
-               "api": "mimsem_gpu_apply_host (per-level host layout in, per-level host layout out)"}
+        h2d, d2h = 8 * nk * (nin + ncoef), 8 * nk * nout
+        if world > 1:
+            import torch.distributed as dist
+            tt = torch.tensor([dt, -float(h2d), -float(d2h)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+            tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb)
+            h2d, d2h = int(tb[0]), int(tb[1])
+        e2e = {"value": out_dofs / dt / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
+               "api": "mimsem_gpu_apply_host (per-level host layout in, per-level host layout out)" +
+                      ("" if world == 1 else "; one call per rank on its ghosted local vectors, bytes summed over ranks")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -356,13 +371,15 @@ def main():
         except Exception as exc:  # the checker must never take the measurement down
             cpu = {"error": repr(exc)}
 
+    if world > 1 and eng.halo_error():
+        raise SystemExit("rank %d: a peer-to-peer ghost refresh timed out (ranks out of step?) -- the measurement is void" % rank)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; operator %s over all levels in one launch "
                                        "(Nel=%d, out DOF-levels=%d)" % (args.workload, variant, p, ne, ne, nk, op, mesh.nel, out_dofs),
-                           "cache": "ring of %d distinct field sets, each field pair %.0f MB > 126 MB L2" % (RING, 16e-6 * nin * nk),
+                           "cache": "ring of %d distinct field sets per GPU (%.0f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
                            "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,

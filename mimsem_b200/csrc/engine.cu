@@ -692,7 +692,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     if (hf) {
         if (with_h || !tma_path || !c->halo_plan_ok || a.elist || ld != nlev)
             return fail(MIMSEM_ERR_UNSUPPORTED, "fused ghost refresh needs the TMA tile path (plain M1, all owned elements, even nlev == ld <= 64, set_ghosts)");
-        if (hf->npush > 64 || hf->npull > 32) return fail(MIMSEM_ERR_ARG, "too many halo peers");
+        if (hf->npush > kMaxPushPeers || hf->npull > 32) return fail(MIMSEM_ERR_ARG, "too many halo peers");
     }
     if (tma_path) {
         TArgs t;

@@ -60,50 +60,74 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // Push role of the fused ghost refresh: CTA b of push_ctas copies its share of every peer's rows into that peer's
 // inbox (16-byte accesses, lanes along the levels) and the last CTA to finish a peer raises that peer's flag.
+#define DBG_PUSH(i) do { if (a.dbg_times && threadIdx.x == 0) a.dbg_times[(size_t)(a.ntiles + blockIdx.x) * 6 + (i)] = gtime_ns(); } while (0)
+// Push role of the fused ghost refresh.  The rows of all peers form one flat list that is split evenly over the push
+// CTAs (a CTA's share may straddle peers), sized so that a CTA moves its share in a single pass: every thread has up to
+// four independent 16-byte loads in flight, then stores them into the peers' inboxes over NVLink.  The copy is
+// latency-bound (index load -> HBM load -> remote store -> system fence), hence many small CTAs rather than few big ones.
+constexpr int kMaxPushPeers = 16;
 __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long epoch) {
     const HaloFused& h = a.halo;
-    // the peer must have consumed the inbox copy of epoch - 2 (same parity)
-    if (epoch > 2)
-        for (int p = threadIdx.x; p < h.npush; p += blockDim.x) spin_until(h.push[p].wait, epoch - 2, h.err);
-    __syncthreads();
-    const int nl2 = a.nlev >> 1;
-    for (int p = 0; p < h.npush; p++) {
-        const HaloPeer pp = h.push[p];
-        const int r0 = (int)(((long long)pp.nrows * blockIdx.x) / h.push_ctas);
-        const int r1 = (int)(((long long)pp.nrows * (blockIdx.x + 1)) / h.push_ctas);
-        double2* box = reinterpret_cast<double2*>(pp.inbox + (epoch & 1ull) * pp.inbox_parity_stride + (size_t)pp.row0 * a.nlev);
-        const int total = (a.debug & 4) ? 0 : (r1 - r0) * nl2;   // debug bit 2: signal without copying (timing experiment)
-        // four independent 16-byte loads in flight per thread before the peer stores (the copy is latency-bound)
-        constexpr int U = 4;
-        for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
-            double2 v[U];
-            size_t dst[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = base + u * blockDim.x;
-                if (i < total) {
-                    const int r = r0 + i / nl2, k2 = i - (r - r0) * nl2;
-                    v[u] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)pp.rows[r] * a.ld) + k2);
-                    dst[u] = (size_t)r * nl2 + k2;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++)
-                if (base + u * (int)blockDim.x < total) box[dst[u]] = v[u];
-        }
+    __shared__ HaloPeer peers[kMaxPushPeers];
+    __shared__ int pre[kMaxPushPeers + 1];
+    DBG_PUSH(0);
+    if (threadIdx.x < h.npush) {
+        peers[threadIdx.x] = h.push[threadIdx.x];
+        // the peer must have consumed the inbox copy of epoch - 2 (same parity)
+        if (epoch > 2) spin_until(h.push[threadIdx.x].wait, epoch - 2, h.err);
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        int acc = 0;
         for (int p = 0; p < h.npush; p++) {
-            const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
-            if (done == (unsigned)h.push_ctas - 1) {
-                h.counters[1 + p] = 0;
-                __threadfence_system();
-                st_release_sys(h.push[p].signal, epoch);
+            pre[p] = acc;
+            acc += peers[p].nrows;
+        }
+        pre[h.npush] = acc;
+    }
+    __syncthreads();
+    DBG_PUSH(1);
+    const int nl2 = a.nlev >> 1;
+    const int R = pre[h.npush];
+    const int f0 = (int)(((long long)R * blockIdx.x) / h.push_ctas);
+    const int f1 = (int)(((long long)R * (blockIdx.x + 1)) / h.push_ctas);
+    const int total = (a.debug & 4) ? 0 : (f1 - f0) * nl2;   // debug bit 2: signal without copying (timing experiment)
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+        double2 v[U];
+        double2* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * blockDim.x;
+            dst[u] = nullptr;
+            if (i < total) {
+                const int f = f0 + i / nl2, k2 = i - (f - f0) * nl2;
+                int p = 0;
+                while (f >= pre[p + 1]) p++;
+                const int r = f - pre[p];
+                const HaloPeer& pp = peers[p];
+                v[u] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)pp.rows[r] * a.ld) + k2);
+                dst[u] = reinterpret_cast<double2*>(pp.inbox + (epoch & 1ull) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev) + k2;
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (dst[u]) *dst[u] = v[u];
     }
+    DBG_PUSH(2);
+    __threadfence_system();
+    __syncthreads();
+    DBG_PUSH(3);
+    if (threadIdx.x < h.npush) {
+        const int p = threadIdx.x;
+        const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
+        if (done == (unsigned)h.push_ctas - 1) {
+            h.counters[1 + p] = 0;
+            __threadfence_system();
+            st_release_sys(peers[p].signal, epoch);
+        }
+    }
+    DBG_PUSH(4);
 }
 
 // Every CTA of a fused launch ends here; the last one acknowledges the inbox of this epoch to the peers (all bulk
@@ -123,6 +147,18 @@ __device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long ep
     }
 }
 
+// Boundary tile, warp 0: wait until every peer's rows of this epoch have landed (lane i watches peer i) and return the
+// inbox copy to stage from.  Out of line: cold code stays out of the tile loop.
+__device__ __noinline__ const double* halo_wait_peers(const TArgs& a, unsigned long long epoch, int lane) {
+    if (!(a.debug & 8)) {   // debug bit 3: do not wait for the peers (timing experiment)
+#pragma unroll 1
+        for (int i = lane; i < a.halo.npull; i += 32) spin_until(a.halo.pull[i].wait, epoch, a.halo.err);
+    }
+    __syncwarp();
+    fence_async_all();   // the peers' generic-proxy stores are read by the async proxy (TMA) next
+    return a.halo.inbox + (epoch & 1ull) * a.halo.parity_stride;
+}
+
 // Stage one tile: warp 0 walks the element's copy list (one entry per lane and round)
 template <bool HALO>
 __device__ __forceinline__ void tile_load(const TArgs& a, int e, int tile_i, unsigned long long epoch, uint64_t* bar, double* geo,
@@ -139,11 +175,7 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, int tile_i, uns
     const double* inbox = nullptr;
     if (HALO && tile_i >= a.halo.n_int) {
         // boundary tile: the peers' rows of this epoch must have landed in my inbox (lane i watches peer i)
-        if (!(a.debug & 8))   // debug bit 3: do not wait for the peers (timing experiment)
-            for (int i = lane; i < a.halo.npull; i += 32) spin_until(a.halo.pull[i].wait, epoch, a.halo.err);
-        __syncwarp();
-        fence_async_all();   // the peers' generic-proxy stores are read by the async proxy (TMA) below
-        inbox = a.halo.inbox + (epoch & 1ull) * a.halo.parity_stride;
+        inbox = halo_wait_peers(a, epoch, lane);
     }
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = (ci == lane) ? first : ents[ci];

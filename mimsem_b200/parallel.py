@@ -452,7 +452,7 @@ class DistributedEngine:
         npush, dpush, npull, dpull, epochs = self.p2p["plans"][1]
         inbox, stride, push_rows = self._inbox[1]
         nlev = x.shape[1]
-        push_ctas = max(8, min(64, push_rows // 48))     # few CTAs: their fixed cost (flag wait, system fence) is paid per CTA
+        push_ctas = max(1, min(148, push_rows // 16))    # ~16 rows per CTA: one pass with four loads in flight per thread
         check(eng.L.mimsem_gpu_apply_M1_halo(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(),
                                              npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, push_ctas,
                                              epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
