@@ -58,6 +58,15 @@ def algorithmic_bytes(op, nel, q2, N0, N1, N2, NQ, nk):
     raise ValueError(op)
 
 
+def ncu_traffic(workload, op):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload][op]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -382,7 +391,8 @@ def main():
                            "cache": "ring of %d distinct field sets per GPU (%.0f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
                            "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
+                             "traffic": (ncu_traffic(args.workload, op) if world == 1 else None), "traffic_source": "ncu --set full capture, profiles/r01_traffic.json",
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
                              "kernel_ms": kern_ms},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))

@@ -21,6 +21,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -162,10 +165,10 @@ __device__ __noinline__ const double* halo_wait_peers(const TArgs& a, unsigned l
 // Stage one tile: warp 0 walks the element's copy list (one entry per lane and round)
 template <bool HALO>
 __device__ __forceinline__ void tile_load(const TArgs& a, int e, int tile_i, unsigned long long epoch, uint64_t* bar, double* geo,
-                                          double* tile) {
+                                          double* tile, int lane_in = -1) {
     const TileHdr* rec = a.recs + (size_t)e * (1 + a.rec_ents);
     const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + 1);
-    const int lane = threadIdx.x;
+    const int lane = lane_in >= 0 ? lane_in : (int)threadIdx.x;
     // header and this lane's first entry are fetched together (no dependent load on the critical path)
     const TileHdr h = rec[0];
     CopyEnt first = ents[lane < a.rec_ents ? lane : 0];
@@ -306,8 +309,8 @@ __device__ __forceinline__ void tile_compute(const TArgs& a, const double* col, 
     using S = M1Slots<P>;
     constexpr int NP1 = P + 1;
     // HALF 2 = all lines of the direction (two warp-pairs per tile: the configuration that measured fastest)
-    constexpr int LO = HALF == 1 ? (P + 1) / 2 : 0;
-    constexpr int HI = HALF == 0 ? (P + 1) / 2 : P;
+    constexpr int LO = HALF == 1 ? P / 2 : 0;
+    constexpr int HI = HALF == 0 ? P / 2 : P;
     constexpr int NLN = HI - LO > 0 ? HI - LO : 1;
     const int nl = NL ? NL : a.nlev;
 #define SLOT(s) col[(size_t)(s) * nl]
@@ -444,14 +447,16 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
     for (int tile_i = first_tile; tile_i < tile_end; tile_i += tile_stride, phase ^= 1) {
         const int e = a.elist ? a.elist[tile_i] : tile_i;
         DBG_T(0);
-        if (threadIdx.x < 32) tile_load<HALO>(a, e, tile_i, epoch, bar, geo, tile);
+        if (a.debug & 16) {
+            // timing experiment: contraction + stores on whatever the shared memory holds (no copies, no wait)
+        } else if (threadIdx.x < 32) tile_load<HALO>(a, e, tile_i, epoch, bar, geo, tile);
         else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && tile_i + a.prefetch_ahead < a.ntiles) {
             const int bn = tile_i + a.prefetch_ahead;
             tile_prefetch(a, a.elist ? a.elist[bn] : bn);
         }
         const TileHdr hd = a.recs[(size_t)e * (1 + a.rec_ents)];
         DBG_T(1);
-        mbar_wait(bar, phase);
+        if (!(a.debug & 16)) mbar_wait(bar, phase);
         DBG_T(2);
         if (k < nl && !(a.debug & 1)) {
             const double* col = tile + k;
