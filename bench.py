@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lockstep", action="store_true", help="N > 1: push and consume the ghost rows in the same launch (no pipelining over the ring)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -274,12 +275,35 @@ def main():
     if ncoef:
         cs = [torch.rand((ncoef, nk), dtype=torch.float64, device=dev, generator=g) + 0.5 for _ in range(RING)]
 
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # kernels of this library per step (graph replays bypass the library's launch counter)
+    l0 = eng.launch_count
+    eng.apply(op, xs[0], coeff=None if cs is None else cs[0], out=ys[0], scale=SCALE, tpow=tpow)
+    barrier()
+    launches_per_step = eng.launch_count - l0
+
+    # N > 1, M1: the ghost refresh is software-pipelined over the ring of independent inputs -- the launch of step i
+    # pushes the boundary rows of step i+1's input and consumes what step i-1 pushed (one push + one apply per step,
+    # as without pipelining; only the dependency distance changes).  --lockstep pushes and consumes in the same launch.
+    pipelined = world > 1 and op == "M1" and not args.lockstep and getattr(eng, "p2p", None) is not None and eng.fused
+    nxt = (lambda j: {"x_next": xs[(j + 1) % RING]}) if pipelined else (lambda j: {})
+    if pipelined:
+        eng.prologue_push(xs[0])
+        barrier()
+
     # the step (ghost refresh + kernels) is captured once per ring slot into a CUDA graph and replayed:
     # at 4-8 GPUs a step is tens of microseconds, i.e. launch-bound without graphs
     replays = None
     if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
         try:
-            replays = [eng.capture(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow)[0]
+            # (each capture warms up with two real applies of its slot; after the last slot the pipeline holds the
+            #  boundary rows of xs[0], the input of the first step)
+            replays = [eng.capture(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow, **nxt(j))[0]
                        for j in range(RING)]
         except Exception as exc:  # fall back to eager launches
             if rank == 0:
@@ -291,14 +315,9 @@ def main():
         if replays is not None:
             replays[j]()
         else:
-            eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow)
+            eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow, **nxt(j))
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    barrier()
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -317,11 +336,7 @@ def main():
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
     if replays is not None:
-        # graph replays do not pass through the library's launch counter: count the kernels of one captured step
-        l0 = eng.launch_count
-        eng.apply(op, xs[0], coeff=None if cs is None else cs[0], out=ys[0], scale=SCALE, tpow=tpow)
-        torch.cuda.synchronize()
-        launches = (eng.launch_count - l0) * args.steps
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -389,7 +404,10 @@ def main():
                 "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; operator %s over all levels in one launch "
                                        "(Nel=%d, out DOF-levels=%d)" % (args.workload, variant, p, ne, ne, nk, op, mesh.nel, out_dofs),
                            "cache": "ring of %d distinct field sets per GPU (%.0f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
-                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None},
+                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None,
+                           "ghost_refresh": ("none (1 GPU)" if world == 1 else
+                                             ("fused into the M1 launch over NVLink peer memory; push of step i+1's input overlapped with step i (ring of independent inputs)"
+                                              if pipelined else "fused into the M1 launch over NVLink peer memory; push and consume in the same launch"))},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (ncu_traffic(args.workload, op) if world == 1 else None), "traffic_source": "ncu --set full capture, profiles/r01_traffic.json",
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,

@@ -183,6 +183,25 @@ int mimsem_gpu_apply_R_up(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, doubl
 int mimsem_gpu_apply_M0h_up(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                             const double* d_h2, const double* d_u1, double tau, const double* d_x, double* d_y, void* stream);
 
+/*
+ * Mass-matrix solves -- the step that follows almost every apply in the reference:
+ *   KSPSolve(ksp1, b, x) with GMRES + element-block Jacobi on M1  -> solve_M1   eul/HorizSolve.cpp:77-84, 224, 310, 322
+ *   KSPSolve(ksp0, b, x) on M0                                    -> solve_M0   eul/HorizSolve.cpp:87-96, 246, 490
+ * M1 is symmetric positive definite: solve_M1 runs a diagonally preconditioned conjugate-gradient iteration with the
+ * matrix-free M1 kernel as the operator, batched over the nlev levels (each level is its own system with its own step
+ * lengths; a converged level stops moving).  Stops when every level has |b - M1 x| <= rtol |b| or after maxit
+ * iterations; *iters = iterations performed, *relres = the worst level's relative residual (either may be NULL).
+ * The arguments before d_b are those of the apply that defines the matrix.  Whole mesh on one GPU only.
+ * M0 is diagonal when the quadrature order equals the element order, so solve_M0 is a pointwise division.
+ * diag_M1 returns the diagonal of M1 (MatGetDiagonal for a Jacobi-preconditioned KSP on the MatShell).
+ */
+int mimsem_gpu_solve_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                        const double* d_b, double* d_x, double rtol, int maxit, int* iters, double* relres, void* stream);
+int mimsem_gpu_solve_M0(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                        const double* d_b, double* d_x, void* stream);
+int mimsem_gpu_diag_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
+                       double* d_diag, void* stream);
+
 /* Incidence operators (exact +-1 stencils), E10mat/E21mat of eul/Assembly.cpp:1102-1226:
  * which = 0 E10 (0-form -> 1-form), 1 E01 = -E10^T, 2 E21 (1-form -> 2-form), 3 E12 = -E21^T. */
 #define MIMSEM_E10 0
@@ -249,14 +268,22 @@ int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, i
  * by TMA; the last CTA acknowledges the inbox and advances the device-side epoch (CUDA-graph replayable).
  * Requires mimsem_gpu_set_ghosts, ld == nlev (even, <= 64) and inbox rows in ghost order:
  * inbox row i holds caller row n1_owned + i (d_push[].row0 = first row of each peer's share).
- * d_push / d_pull as for mimsem_gpu_halo_push / _pull; d_inbox = this rank's inbox (parity 0), the second parity
- * copy parity_stride doubles later; d_epoch = the space's two epoch counters {push, pull} (both advanced, so this
+ * d_push / d_pull as for mimsem_gpu_halo_push / _pull; d_inbox = this rank's inbox, `nbuf` copies (2..4, the same on
+ * every rank) parity_stride doubles apart, data epoch e in copy e % nbuf (3 copies let a pipelined push proceed
+ * without waiting for the consumer of the current epoch); d_epoch = the space's two epoch counters {push, pull} (both advanced, so this
  * call can be mixed with push / pull pairs).  Ghost rows of d_x itself are neither read nor written.
+ *
+ * Software pipelining over INDEPENDENT applies (several fields per time step, a ring of right-hand sides): mode 1
+ * pushes the boundary rows of d_x_push -- the input of the NEXT call -- while this call's boundary tiles consume
+ * what the previous call pushed, which takes the NVLink round trip of the push off the critical path of a step.  A
+ * pipelined sequence starts with one mode-2 call (push d_x_push only; nothing is applied, the epoch is unchanged)
+ * and ends with one mode-3 call (consume only, push nothing); every rank must use the same mode in the same call.
+ * mode 0 (d_x_push ignored): push and consume in one call.
  */
 int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
-                             const double* d_x, double* d_y, int npush, const void* d_push, int npull, const void* d_pull,
-                             const double* d_inbox, int64_t parity_stride, int push_ctas, void* d_epoch, int* d_err,
-                             void* stream);
+                             const double* d_x, double* d_y, const double* d_x_push, int mode, int npush, const void* d_push,
+                             int npull, const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf,
+                             int push_ctas, void* d_epoch, int* d_err, void* stream);
 
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);

@@ -103,6 +103,7 @@ struct mimsem_gpu_ctx {
     DevBuf<double> d_geo, d_geo_h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
+    DevBuf<double> cg_r, cg_p, cg_q, cg_dinv, cg_partial, cg_scal;   // work space of mimsem_gpu_solve_M1
     DevBuf<double> d_J4, d_det, d_Wr;   // raw Jacobians for the upwinded operators, signed quadrature weight of R(q)
     std::vector<double> xn;             // GLL nodes of order p
     int nkT = 0;
@@ -730,7 +731,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             }
             t.halo_on = 1;
             t.halo = *hf;
-            t.halo.n_int = c->n_int;
+            t.halo.n_int = hf->push_only ? 0 : c->n_int;
             t.halo.counters = c->d_fused_counters.p;
             t.elist = c->elist_all_identity ? nullptr : c->d_elist_all.p;
             t.recs = c->d_recs_halo.p;
@@ -764,6 +765,12 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             const char* pg = getenv("MIMSEM_PERSISTENT");
             const bool persistent = pg && atoi(pg) != 0;   // measured equal to one CTA per tile on C5; off by default
             t.ntiles = a.nel;
+            if (hf && hf->push_only) {
+                if (push_ctas == 0) return (int)MIMSEM_OK;
+                t.ntiles = 0;
+                kern<<<push_ctas, 128, smem, st>>>(t);
+                return finish_launch(c, "halo push (prologue)");
+            }
             const int grid = (persistent && !hf ? std::min(a.nel, nsm * std::max(per_sm, 1)) : a.nel) + push_ctas;
             kern<<<grid, 128, smem, st>>>(t);
             return finish_launch(c, "apply_M1 (tma)");
@@ -1001,6 +1008,119 @@ int apply_m0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, in
         k_apply_m0h_up<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
         return finish_launch(c, "apply_M0h_up");
     });
+}
+
+// diag(M1) (invert: its reciprocal) for the same arguments as apply_m1
+int diag_m1(mimsem_gpu_ctx* c, bool invert, int lev0, int nlev, int ld, double scale, int tpow, int flags, double* d, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!d) return fail(MIMSEM_ERR_ARG, "null output");
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = c->d_G1.p;
+    a.x = nullptr;
+    a.y = d;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads == 0) return MIMSEM_OK;
+    return dispatch_p(c->p, [&](auto P) {
+        constexpr int p = decltype(P)::value;
+        if (invert) k_diag_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        else k_diag_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
+        return finish_launch(c, "diag_M1");
+    });
+}
+
+// x = M1^-1 b by Jacobi-preconditioned CG, all levels at once (per-level step lengths)
+int solve_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
+             double rtol, int maxit, int* iters, double* relres, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!b || !x) return fail(MIMSEM_ERR_ARG, "null field");
+    if (c->mode != 0 || c->nel_owned != c->nel_total)
+        return fail(MIMSEM_ERR_UNSUPPORTED, "solve_M1 works on a whole mesh in owner-computes mode (the dot products are not partitioned yet)");
+    if (nlev > 64) return fail(MIMSEM_ERR_UNSUPPORTED, "solve_M1: at most 64 levels per call");
+    if (flags & (MIMSEM_SUBSET_INTERIOR | MIMSEM_SUBSET_BOUNDARY)) return fail(MIMSEM_ERR_ARG, "solve_M1 takes no element subset");
+    if (!(rtol > 0.0) || maxit < 1) return fail(MIMSEM_ERR_ARG, "bad tolerance / iteration limit");
+    const size_t nfield = (size_t)c->n1 * ld;
+    CgArgs g;
+    g.nrows = c->n1;
+    g.nlev = nlev;
+    g.ld = ld;
+    g.nblocks = (int)((c->n1 + CG_ROWS - 1) / CG_ROWS);
+    CUDA_OK(c->cg_r.resize(nfield));
+    CUDA_OK(c->cg_p.resize(nfield));
+    CUDA_OK(c->cg_q.resize(nfield));
+    CUDA_OK(c->cg_dinv.resize(nfield));
+    CUDA_OK(c->cg_partial.resize((size_t)3 * g.nblocks * 64));
+    CUDA_OK(c->cg_scal.resize(8 * 64));
+    CUDA_OK(cudaMemsetAsync(c->cg_scal.p, 0, 8 * 64 * sizeof(double), st));
+    g.x = x; g.r = c->cg_r.p; g.p = c->cg_p.p; g.q = c->cg_q.p; g.dinv = c->cg_dinv.p; g.b = b;
+    g.partial = c->cg_partial.p;
+    g.scal = c->cg_scal.p;
+    g.tol2 = rtol * rtol;
+    if ((rc = diag_m1(c, true, lev0, nlev, ld, scale, tpow, flags, c->cg_dinv.p, st))) return rc;
+    k_cg_step<0><<<g.nblocks, 256, 0, st>>>(g);
+    k_cg_finish<0><<<1, 64, 0, st>>>(g);
+    c->launches += 2;
+    std::vector<double> h(8 * 64);
+    int it = 0;
+    double worst = 0.0;
+    const int check_every = 4;
+    bool done = false;
+    while (!done) {
+        for (int j = 0; j < check_every && it < maxit; j++, it++) {
+            if ((rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, g.p, c->cg_q.p, st))) return rc;
+            k_cg_step<1><<<g.nblocks, 256, 0, st>>>(g);
+            k_cg_finish<1><<<1, 64, 0, st>>>(g);
+            k_cg_step<2><<<g.nblocks, 256, 0, st>>>(g);
+            k_cg_finish<2><<<1, 64, 0, st>>>(g);
+            k_cg_step<3><<<g.nblocks, 256, 0, st>>>(g);
+            c->launches += 5;
+        }
+        CUDA_OK(cudaMemcpyAsync(h.data(), c->cg_scal.p, 8 * 64 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+        done = true;
+        worst = 0.0;
+        for (int k = 0; k < nlev; k++) {
+            const double bb = h[3 * 64 + k], rr = h[2 * 64 + k];
+            if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
+            if (h[7 * 64 + k] == 0.0) done = false;
+        }
+        if (it >= maxit) done = true;
+    }
+    CUDA_OK(cudaGetLastError());
+    if (iters) *iters = it;
+    if (relres) *relres = worst;
+    return MIMSEM_OK;
+}
+
+int solve_m0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!b || !x) return fail(MIMSEM_ERR_ARG, "null field");
+    NodeArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.n0 = c->n0;
+    a.nlev = nlev;
+    a.ld = ld;
+    a.lev0 = lev0;
+    a.lev_stride = (flags & MIMSEM_FIXED_LEVEL) ? 0 : 1;
+    a.nkT = c->nkT;
+    a.tpow = tpow;
+    a.scale = scale;
+    a.node_q = c->d_node_q.p;
+    a.D0 = c->d_D0.p;
+    a.tinv = c->d_tinv.p;
+    a.x = b;
+    a.y = x;
+    const FastDiv fd = make_fastdiv((unsigned)nlev);
+    a.div_m = fd.m;
+    a.div_s = fd.s;
+    k_solve_m0<<<grid_for((int64_t)a.n0 * nlev, 256), 256, 0, st>>>(a);
+    return finish_launch(c, "solve_M0");
 }
 
 int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, cudaStream_t st) {
@@ -1411,8 +1531,12 @@ int mimsem_gpu_apply_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sc
     return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
 }
 int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
-                             double* y, int npush, const void* d_push, int npull, const void* d_pull, const double* d_inbox,
-                             int64_t parity_stride, int push_ctas, void* d_epoch, int* d_err, void* st) {
+                             double* y, const double* x_push, int mode, int npush, const void* d_push, int npull,
+                             const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf, int push_ctas,
+                             void* d_epoch, int* d_err, void* st) {
+    if (nbuf < 2 || nbuf > 4) return fail(MIMSEM_ERR_ARG, "the inbox has 2..4 copies");
+    if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && !x_push)) return fail(MIMSEM_ERR_ARG, "bad pipelining mode / missing field to push");
+    if (mode == 3) npush = 0;   // last call of a pipelined sequence: consume what the previous call pushed, push nothing
     if (!c || !d_epoch || !d_err || (npush > 0 && !d_push) || (npull > 0 && (!d_pull || !d_inbox)))
         return fail(MIMSEM_ERR_ARG, "null argument");
     HaloFused hf;
@@ -1424,8 +1548,12 @@ int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, doub
     hf.pull = (const HaloPeer*)d_pull;
     hf.inbox = d_inbox;
     hf.parity_stride = parity_stride;
+    hf.nbuf = nbuf;
     hf.epoch = (unsigned long long*)d_epoch;
     hf.err = d_err;
+    hf.x_push = mode == 0 ? x : x_push;
+    hf.lead = mode == 1 ? 1 : 0;
+    hf.push_only = mode == 2 ? 1 : 0;
     return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st, &hf);
 }
 int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
@@ -1467,6 +1595,17 @@ int mimsem_gpu_apply_R_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double 
 int mimsem_gpu_apply_M0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
                             const double* u1, double tau, const double* x, double* y, void* st) {
     return apply_m0h_up(c, lev0, nlev, ld, scale, tpow, flags, h2, u1, tau, x, y, (cudaStream_t)st);
+}
+int mimsem_gpu_solve_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
+                        double rtol, int maxit, int* iters, double* relres, void* st) {
+    return solve_m1(c, lev0, nlev, ld, scale, tpow, flags, b, x, rtol, maxit, iters, relres, (cudaStream_t)st);
+}
+int mimsem_gpu_solve_M0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
+                        void* st) {
+    return solve_m0(c, lev0, nlev, ld, scale, tpow, flags, b, x, (cudaStream_t)st);
+}
+int mimsem_gpu_diag_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, double* d, void* st) {
+    return diag_m1(c, false, lev0, nlev, ld, scale, tpow, flags, d, (cudaStream_t)st);
 }
 int mimsem_gpu_apply_incidence(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, void* st) {
     return apply_inc(c, which, nlev, ld, x, y, (cudaStream_t)st);

@@ -214,10 +214,16 @@ struct HaloFused {
     const HaloPeer* push;
     const HaloPeer* pull;
     const double* inbox;             // my inbox of the x field's space, parity 0
-    long long parity_stride;         // doubles between the two parity copies
+    long long parity_stride;         // doubles between consecutive inbox copies
     unsigned long long* epoch;
     unsigned* counters;              // [1 + npush]: finished CTAs of the launch, finished push CTAs per peer
     int* err;
+    // software pipelining over independent applies: with lead = 1 the push CTAs send the boundary rows of the NEXT
+    // call's input (x_push, data epoch e+1) while this call's boundary tiles consume what the previous call pushed
+    const double* x_push;            // field whose boundary rows are pushed (lead 0: the input itself)
+    int lead;                        // 0 or 1
+    int nbuf;                        // inbox copies (2, or 3 so that a pipelined push never waits for the current consumer)
+    int push_only;                   // prologue of a pipelined sequence: push data epoch e+1... nothing else, epoch unchanged
 };
 
 struct TArgs {

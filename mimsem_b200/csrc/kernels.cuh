@@ -606,6 +606,172 @@ __global__ void __launch_bounds__(128) k_apply_m0h_up(const __grid_constant__ No
     a.y[(size_t)n * ld + k] = f * acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mass-matrix solves (KSPSolve(ksp1, ...) after almost every apply, eul/HorizSolve.cpp:77-96, 224, 310).
+// M1 is symmetric positive definite, so the reference's GMRES + element-block Jacobi is replaced by a
+// diagonally preconditioned conjugate-gradient iteration, batched over the levels (every level is its own system,
+// so alpha and beta are per-level vectors) with the matrix-free M1 kernel as the operator.
+
+// diag(M1) for the element's owned edges: y^x(ix,iy) = sum_qy E[qy][iy]^2 c Gaa (ix,qy) (+ west neighbour's far line),
+//                                         y^y(ix,iy) = sum_qx E[qx][ix]^2 c Gbb (qx,iy) (+ south neighbour's far line)
+template <int P>
+__device__ __forceinline__ void m1_diag_far(const KArgs& a, int n, int side, bool rev, int k, double (&out)[P]) {
+    using D = ElDim<P>;
+    const int* __restrict__ nq = a.elq + (size_t)n * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)n * D::Q2 * 3;
+    double o[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) o[i] = 0.0;
+#pragma unroll
+    for (int t = 0; t <= P; t++) {
+        const int q = side == 0 ? t * D::NP1 + P : P * D::NP1 + t;
+        const double c = thick_factor(a, nq[q], k) * (side == 0 ? G[q * 3 + 0] : G[q * 3 + 2]);
+#pragma unroll
+        for (int i = 0; i < P; i++) o[i] += a.E[t * P + i] * a.E[t * P + i] * c;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++) out[i] = rev ? o[P - 1 - i] : o[i];
+}
+
+// INVERT: store 1 / diag (the preconditioner)
+template <int P, bool INVERT>
+__global__ void __launch_bounds__(128) k_diag_m1(const __grid_constant__ KArgs a) {
+    using D = ElDim<P>;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.nel * (unsigned)a.nlev) return;
+    int e = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)e * (unsigned)a.nlev);
+    if (a.elist) e = a.elist[e];
+    const size_t ld = a.ld;
+    double* __restrict__ y = a.y + k;
+    const int* __restrict__ ex = a.el1x + (size_t)e * D::N1E;
+    const int* __restrict__ ey = a.el1y + (size_t)e * D::N1E;
+    const int* __restrict__ eq = a.elq + (size_t)e * D::Q2;
+    const double* __restrict__ G = a.G + (size_t)e * D::Q2 * 3;
+    double cw[P], cs[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) cw[i] = cs[i] = 0.0;
+    const int nw = a.nbr[2 * e + 0], ns = a.nbr[2 * e + 1];
+    if (nw >= 0) m1_diag_far<P>(a, nw & 0x1fffffff, (nw >> 29) & 1, (nw >> 30) & 1, k, cw);
+    if (ns >= 0) m1_diag_far<P>(a, ns & 0x1fffffff, (ns >> 29) & 1, (ns >> 30) & 1, k, cs);
+    const unsigned flags = a.eflags[e];
+    double dx[P][P + 1], dy[P + 1][P];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix <= P; ix++) dx[iy][ix] = (ix == 0) ? cw[iy] : 0.0;
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) dy[iy][ix] = (iy == 0) ? cs[ix] : 0.0;
+#pragma unroll
+    for (int qy = 0; qy <= P; qy++)
+#pragma unroll
+        for (int qx = 0; qx <= P; qx++) {
+            const int q = qy * D::NP1 + qx;
+            const double c = thick_factor(a, eq[q], k);
+            const double caa = c * G[q * 3 + 0], cbb = c * G[q * 3 + 2];
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) dx[iy][qx] += a.E[qy * P + iy] * a.E[qy * P + iy] * caa;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) dy[qy][ix] += a.E[qx * P + ix] * a.E[qx * P + ix] * cbb;
+        }
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix <= P; ix++)
+            if (ix < P || (flags & 1u)) y[(size_t)ex[iy * D::NP1 + ix] * ld] = INVERT ? 1.0 / dx[iy][ix] : dx[iy][ix];
+#pragma unroll
+    for (int iy = 0; iy <= P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++)
+            if (iy < P || (flags & 2u)) y[(size_t)ey[iy * P + ix] * ld] = INVERT ? 1.0 / dy[iy][ix] : dy[iy][ix];
+}
+
+// Batched CG building blocks.  Fields are [rows][ld] with lanes along the levels; every reduction is per level and
+// deterministic: a block sums 256 rows into partial[block][k], k_cg_finish adds the partials in block order.
+constexpr int CG_ROWS = 256;
+struct CgArgs {
+    int64_t nrows;
+    int nlev, ld, nblocks;
+    double* x; double* r; double* p; const double* q; const double* dinv; const double* b;
+    double* partial;      // [3][nblocks][64]
+    double* scal;         // [8][64]: 0 rz, 1 pq, 2 rr, 3 bb, 4 rz_new, 5 alpha, 6 beta, 7 frozen (converged levels)
+    double tol2;
+};
+
+__device__ __forceinline__ void cg_block_reduce(double v0, double v1, double v2, double* partial, int nblocks, int nsums) {
+    __shared__ double red[3][4][64];
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    red[0][g][k] = v0; red[1][g][k] = v1; red[2][g][k] = v2;
+    __syncthreads();
+    if (g == 0) {
+        for (int s = 0; s < nsums; s++)
+            partial[((size_t)s * nblocks + blockIdx.x) * 64 + k] = ((red[s][0][k] + red[s][1][k]) + red[s][2][k]) + red[s][3][k];
+    }
+}
+
+// MODE 0: r = b, x = 0, z = dinv r, p = z; sums rz, bb, rr.   MODE 1: sums pq.
+// MODE 2: alpha = rz/pq; x += alpha p; r -= alpha q; sums rz_new (r . dinv r), rr.   MODE 3: beta = rz_new/rz; p = dinv r + beta p.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_cg_step(const __grid_constant__ CgArgs a) {
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int64_t r0 = (int64_t)blockIdx.x * CG_ROWS;
+    const int64_t r1 = r0 + CG_ROWS < a.nrows ? r0 + CG_ROWS : a.nrows;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (k < a.nlev) {
+        double alpha = 0.0, beta = 0.0;
+        if (MODE == 2) alpha = a.scal[5 * 64 + k];
+        if (MODE == 3) beta = a.scal[6 * 64 + k];
+        for (int64_t row = r0 + g; row < r1; row += 4) {
+            const size_t i = (size_t)row * a.ld + k;
+            if (MODE == 0) {
+                const double bv = a.b[i], z = a.dinv[i] * bv;
+                a.x[i] = 0.0; a.r[i] = bv; a.p[i] = z;
+                s0 += bv * z; s1 += bv * bv; s2 += bv * bv;
+            } else if (MODE == 1) {
+                s0 += a.p[i] * a.q[i];
+            } else if (MODE == 2) {
+                a.x[i] += alpha * a.p[i];
+                const double rv = a.r[i] - alpha * a.q[i];
+                a.r[i] = rv;
+                s0 += rv * (a.dinv[i] * rv); s1 += rv * rv;
+            } else {
+                a.p[i] = a.dinv[i] * a.r[i] + beta * a.p[i];
+            }
+        }
+    }
+    if (MODE != 3) cg_block_reduce(s0, s1, s2, a.partial, a.nblocks, MODE == 0 ? 3 : (MODE == 1 ? 1 : 2));
+}
+
+// one thread per level: add the block partials in order and update the per-level scalars
+template <int MODE>
+__global__ void k_cg_finish(const __grid_constant__ CgArgs a) {
+    const int k = threadIdx.x;
+    if (k >= a.nlev) return;
+    double s[3] = {0.0, 0.0, 0.0};
+    const int nsums = MODE == 0 ? 3 : (MODE == 1 ? 1 : 2);
+    for (int j = 0; j < nsums; j++)
+        for (int bI = 0; bI < a.nblocks; bI++) s[j] += a.partial[((size_t)j * a.nblocks + bI) * 64 + k];
+    double* S = a.scal;
+    if (MODE == 0) {
+        S[0 * 64 + k] = s[0]; S[3 * 64 + k] = s[1]; S[2 * 64 + k] = s[2];
+        S[7 * 64 + k] = (s[1] == 0.0) ? 1.0 : 0.0;                    // zero right-hand side: x = 0 is the solution
+    } else if (MODE == 1) {
+        S[1 * 64 + k] = s[0];
+        const bool frozen = S[7 * 64 + k] != 0.0 || s[0] <= 0.0;
+        S[5 * 64 + k] = frozen ? 0.0 : S[0 * 64 + k] / s[0];          // alpha
+    } else {
+        const bool frozen = S[7 * 64 + k] != 0.0;
+        S[6 * 64 + k] = (frozen || S[0 * 64 + k] == 0.0) ? 0.0 : s[0] / S[0 * 64 + k];   // beta = rz_new / rz
+        if (!frozen) {
+            S[0 * 64 + k] = s[0];
+            S[2 * 64 + k] = s[1];
+            if (s[1] <= a.tol2 * S[3 * 64 + k]) S[7 * 64 + k] = 1.0;   // converged: this level stops moving
+        }
+    }
+}
+
 // y = M2 x   (WITH_H: M2(rho) x)
 template <int P, bool WITH_H>
 __global__ void __launch_bounds__(128) k_apply_m2(const __grid_constant__ KArgs a) {
@@ -797,6 +963,22 @@ __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeAr
         }
     }
     a.y[(size_t)n * ld + k] = f * d * ldro(a.x + (size_t)n * ld + k);
+}
+
+// x = M0^-1 b: M0 is diagonal when the quadrature order equals the element order (KSPSolve(ksp0, ...) of
+// eul/HorizSolve.cpp:87-96, 246 becomes a pointwise division)
+__global__ void __launch_bounds__(256) k_solve_m0(const __grid_constant__ NodeArgs a) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
+    const int n = (int)fastdiv(idx, a.div_m, a.div_s);
+    const int k = (int)(idx - (unsigned)n * (unsigned)a.nlev);
+    double f = a.scale;
+    if (a.tpow > 0) {
+        const double t = ldro(a.tinv + (size_t)a.node_q[n] * a.nkT + a.lev0 + k * a.lev_stride);
+        f *= t;
+        if (a.tpow > 1) f *= t;
+    }
+    a.y[(size_t)n * a.ld + k] = ldro(a.x + (size_t)n * a.ld + k) / (f * a.D0[n]);
 }
 
 // M0 without a coefficient field, two levels per thread (16-byte accesses); a.nlev counts level pairs

@@ -76,8 +76,8 @@ __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long e
     DBG_PUSH(0);
     if (threadIdx.x < h.npush) {
         peers[threadIdx.x] = h.push[threadIdx.x];
-        // the peer must have consumed the inbox copy of epoch - 2 (same parity)
-        if (epoch > 2) spin_until(h.push[threadIdx.x].wait, epoch - 2, h.err);
+        // the peer must have consumed the inbox copy of epoch - nbuf (the one this push overwrites)
+        if (epoch > (unsigned long long)h.nbuf) spin_until(h.push[threadIdx.x].wait, epoch - h.nbuf, h.err);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -109,8 +109,8 @@ __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long e
                 while (f >= pre[p + 1]) p++;
                 const int r = f - pre[p];
                 const HaloPeer& pp = peers[p];
-                v[u] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)pp.rows[r] * a.ld) + k2);
-                dst[u] = reinterpret_cast<double2*>(pp.inbox + (epoch & 1ull) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev) + k2;
+                v[u] = __ldg(reinterpret_cast<const double2*>(h.x_push + (size_t)pp.rows[r] * a.ld) + k2);
+                dst[u] = reinterpret_cast<double2*>(pp.inbox + (epoch % h.nbuf) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev) + k2;
             }
         }
 #pragma unroll
@@ -118,11 +118,12 @@ __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long e
             if (dst[u]) *dst[u] = v[u];
     }
     DBG_PUSH(2);
-    __threadfence_system();
+    // the CTA barrier orders every thread's stores before the npush threads below; their system-scope fences are
+    // cumulative, so only they (not all 128 threads) pay the NVLink round trip
     __syncthreads();
-    DBG_PUSH(3);
     if (threadIdx.x < h.npush) {
         const int p = threadIdx.x;
+        __threadfence_system();
         const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
         if (done == (unsigned)h.push_ctas - 1) {
             h.counters[1 + p] = 0;
@@ -130,6 +131,7 @@ __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long e
             st_release_sys(peers[p].signal, epoch);
         }
     }
+    DBG_PUSH(3);
     DBG_PUSH(4);
 }
 
@@ -137,16 +139,21 @@ __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long e
 // loads from it have completed) and advances the epoch for the next launch / graph replay.
 __device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long epoch) {
     // only the push CTAs and the boundary tiles take part (interior tiles neither read the epoch nor touch the inbox)
+    __shared__ int last;
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned done = atomicAdd(&a.halo.counters[0], 1u);
-        if (done == (unsigned)(a.halo.push_ctas + a.ntiles - a.halo.n_int) - 1) {
-            a.halo.counters[0] = 0;
-            for (int i = 0; i < a.halo.npull; i++) st_release_sys(a.halo.pull[i].signal, epoch);
-            a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
-            a.halo.epoch[1] = epoch;
-            __threadfence();
-        }
+        last = (done == (unsigned)(a.halo.push_ctas + a.ntiles - a.halo.n_int) - 1) ? 1 : 0;
+        if (last) a.halo.counters[0] = 0;
+    }
+    __syncthreads();
+    if (!last || a.halo.push_only) return;
+    // one thread per peer: the release stores cross NVLink concurrently (a serial loop costs a round trip per peer)
+    if ((int)threadIdx.x < a.halo.npull) st_release_sys(a.halo.pull[threadIdx.x].signal, epoch);
+    if (threadIdx.x == 0) {
+        a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
+        a.halo.epoch[1] = epoch;
+        __threadfence();
     }
 }
 
@@ -159,7 +166,7 @@ __device__ __noinline__ const double* halo_wait_peers(const TArgs& a, unsigned l
     }
     __syncwarp();
     fence_async_all();   // the peers' generic-proxy stores are read by the async proxy (TMA) next
-    return a.halo.inbox + (epoch & 1ull) * a.halo.parity_stride;
+    return a.halo.inbox + (epoch % a.halo.nbuf) * a.halo.parity_stride;
 }
 
 // Stage one tile: warp 0 walks the element's copy list (one entry per lane and round)
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(128) k_apply_m1_tma(const __grid_constant__ TA
     if (HALO) {
         if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) epoch = *a.halo.epoch + 1;
         if ((int)blockIdx.x < a.halo.push_ctas) {
-            halo_push_role(a, epoch);
+            halo_push_role(a, epoch + (unsigned long long)a.halo.lead);   // data epoch of the pushed field
             halo_cta_done(a, epoch);
             return;
         }

@@ -187,6 +187,34 @@ class Engine:
             check(L.mimsem_gpu_apply_incidence(h, OPS[op] - 10, nlev, nlev, xp, yp, st))
         return out
 
+    # ---------------------------------------------------------------- mass-matrix solves
+    def solve(self, op, b, out=None, lev0=0, scale=1.0, tpow=0, flags=0, rtol=1e-13, maxit=200):
+        """x = M^-1 b for op in ("M1", "M0") with the matrix that apply(op, ..., same arguments) applies.
+        Returns (x, iterations, worst relative residual); M0 is diagonal (0 iterations)."""
+        n = self.n1 if op == "M1" else self.n0
+        nlev = b.shape[1]
+        self._chk(b, n, nlev, "b")
+        if out is None:
+            out = self.empty(n, nlev)
+        self._chk(out, n, nlev, "out")
+        if op == "M0":
+            check(self.L.mimsem_gpu_solve_M0(self._h, lev0, nlev, nlev, scale, tpow, flags, b.data_ptr(), out.data_ptr(), self._stream()))
+            return out, 0, 0.0
+        if op != "M1":
+            raise MimsemError("solve: operator must be M1 or M0")
+        it = C.c_int(0)
+        rr = C.c_double(0.0)
+        check(self.L.mimsem_gpu_solve_M1(self._h, lev0, nlev, nlev, scale, tpow, flags, b.data_ptr(), out.data_ptr(), rtol, maxit,
+                                         C.byref(it), C.byref(rr), self._stream()))
+        return out, it.value, rr.value
+
+    def diag(self, op, nlev, lev0=0, scale=1.0, tpow=0, flags=0):
+        if op != "M1":
+            raise MimsemError("diag: only M1")
+        out = self.zeros(self.n1, nlev)
+        check(self.L.mimsem_gpu_diag_M1(self._h, lev0, nlev, nlev, scale, tpow, flags, out.data_ptr(), self._stream()))
+        return out
+
     def capture(self, op, x, coeff=None, out=None, **kw):
         """Capture one apply into a CUDA graph; returns (replay, out)."""
         torch = self.torch

@@ -46,6 +46,10 @@ SIGNATURES = {
     "mimsem_gpu_apply_R": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_apply_R_up": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M0h_up": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp]),
+    "mimsem_gpu_solve_M1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
+                                      _ip, _dp, _vp]),
+    "mimsem_gpu_solve_M0": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_diag_M1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp]),
     "mimsem_gpu_apply_incidence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_incidence_csr": (C.c_int, [_vp, C.c_int, _lp, _lp, _ip, _dp]),
     "mimsem_gpu_apply_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),
@@ -57,8 +61,8 @@ SIGNATURES = {
     "mimsem_gpu_ipc_close": (C.c_int, [_vp, _vp, C.c_int]),
     "mimsem_gpu_halo_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_halo_pull": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
-    "mimsem_gpu_apply_M1_halo": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp,
-                                           C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M1_halo": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
+                                           C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
 }
 

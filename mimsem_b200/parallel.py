@@ -225,6 +225,7 @@ class DistributedEngine:
 
     # ---------------------------------------------------------------- peer-to-peer halo (no NCCL on the data path)
     MAXP = 16
+    NBUF = 3      # inbox copies per space (the push / pull kernels use the first two, the fused M1 launch all three)
 
     def _setup_p2p(self, P, sends):
         """Allocate this rank's inbox / flag buffer, exchange IPC handles and layouts (control plane: torch.distributed
@@ -237,7 +238,7 @@ class DistributedEngine:
         send_peers = {s: sorted(sends[s]) for s in spaces}
         assert all(len(v) <= MAXP for v in list(recv_peers.values()) + list(send_peers.values()))
         hdr_bytes = 4 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP]
-        # inbox of a space: [2 parities][ghost rows of the space, in ghost order][nk]; a peer's share is the run of
+        # inbox of a space: [NBUF copies][ghost rows of the space, in ghost order][nk]; a peer's share is the run of
         # rows it owns (ghosts are sorted by global id, owners hold contiguous id ranges)
         layout = {}                                    # (space, peer) -> (slot, first inbox row, nrows)
         region = {}                                    # space -> (offset in bytes, total ghost rows)
@@ -251,7 +252,7 @@ class DistributedEngine:
                 layout[(s, q)] = (slot, row, len(loc))
                 row += len(loc)
             region[s] = (off, row)
-            off += 2 * row * nk * 8
+            off += self.NBUF * row * nk * 8
         total = max(off, hdr_bytes + 16)
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
@@ -377,9 +378,12 @@ class DistributedEngine:
     NEEDS = {"M1": (True, False), "M1h": (True, True), "M2": (False, False), "M2h": (False, False), "K": (True, True),
              "E21": (True, False), "E12": (True, False)}
 
-    def apply(self, op, x, coeff=None, out=None, exchange=True, flags=0, **kw):
+    def apply(self, op, x, coeff=None, out=None, exchange=True, flags=0, x_next=None, pipeline_last=False, **kw):
         """Ghost refresh of the inputs + local apply.  For the element kernels the refresh runs on a side stream
-        while the interior elements (no ghost reads) are computed; boundary elements follow once it has landed."""
+        while the interior elements (no ghost reads) are computed; boundary elements follow once it has landed.
+        x_next (fused M1 only): software pipelining over independent applies -- this call pushes the boundary rows of
+        x_next, the input of the NEXT call, and consumes what the previous call (or prologue_push) sent for x;
+        pipeline_last=True ends such a sequence (consume only)."""
         if op not in self.SUPPORTED:
             raise NotImplementedError("operator %s is not partitioned yet (0-form operators need node ownership)" % op)
         torch = self.torch
@@ -392,7 +396,9 @@ class DistributedEngine:
         if not (do_x or do_c):
             return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
         if op == "M1" and self.p2p is not None and self.fused and self._fused_ok(x, kw):
-            return self._apply_m1_fused(x, out, flags, **kw)
+            return self._apply_m1_fused(x, out, flags, x_next=x_next, mode=3 if pipeline_last else None, **kw)
+        if x_next is not None or pipeline_last:
+            raise NotImplementedError("pipelined ghost refresh needs the fused M1 path")
         overlap = self.overlap and op in ("M1", "M1h", "K") and self.n_interior > 0
         if overlap and self.p2p is not None:
             # side stream: push kernels (store into the peers' inboxes over NVLink) and pull kernels (wait for the
@@ -443,7 +449,13 @@ class DistributedEngine:
         nlev = x.shape[1]
         return nlev % 2 == 0 and nlev <= 64 and nlev <= self.nk_max and self.engine.p >= 2
 
-    def _apply_m1_fused(self, x, out, flags, lev0=0, scale=1.0, tpow=0):
+    def prologue_push(self, x):
+        """Start a pipelined sequence: push the boundary rows of x (the first input) without applying anything.
+        Collective; the caller must make sure every rank has finished it (stream sync + barrier) before the first
+        pipelined apply if an earlier sequence already raised the flags of this epoch."""
+        self._apply_m1_fused(x, x, 0, x_next=x, mode=2)
+
+    def _apply_m1_fused(self, x, out, flags, lev0=0, scale=1.0, tpow=0, x_next=None, mode=None):
         """ONE launch: push CTAs + interior tiles + boundary tiles that stage their ghost rows from the inbox
         (mimsem_gpu_apply_M1_halo).  Shares the epoch / flag / ack words of the 1-form space with push()/pull():
         both epoch counters advance together so the two mechanisms can be mixed."""
@@ -453,8 +465,11 @@ class DistributedEngine:
         inbox, stride, push_rows = self._inbox[1]
         nlev = x.shape[1]
         push_ctas = max(1, min(148, push_rows // 16))    # ~16 rows per CTA: one pass with four loads in flight per thread
-        check(eng.L.mimsem_gpu_apply_M1_halo(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(),
-                                             npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, push_ctas,
+        if mode is None:
+            mode = 0 if x_next is None else 1
+        xp = x.data_ptr() if x_next is None else x_next.data_ptr()
+        check(eng.L.mimsem_gpu_apply_M1_halo(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(), xp, mode,
+                                             npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, self.NBUF, push_ctas,
                                              epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
         return out
 

@@ -65,6 +65,37 @@ def main():
                     key = {"M1": "y_Umat_vs1", "M1h": "y_Uhmat_cv1", "M2": "y_Wmat_vs1", "M2h": "y_Whmat_vs1", "K": "y_WtQUmat"}.get(op)
                     if key and rel_l2(yg, g[key]) >= TOL:
                         failures.append((what, op, "golden", rel_l2(yg, g[key])))
+        # software-pipelined ghost refresh (fused M1): prologue, then each apply pushes the NEXT input
+        if deng.p2p is not None and deng.fused and nk % 2 == 0:
+            xa = deng.scatter_from_global(f["x1"], 1)
+            xb = deng.scatter_from_global(f["x1"][::-1].copy() * 0.5, 1)
+            perm1 = torch.from_numpy(deng.engine.permutation(1).astype(np.int64)).cuda()
+            xa[perm1[deng.part.n1_owned:]] = 0.0
+            xb[perm1[deng.part.n1_owned:]] = 0.0
+            torch.cuda.synchronize(); dist.barrier()
+            deng.prologue_push(xa)
+            torch.cuda.synchronize(); dist.barrier()
+            outs = [deng.apply("M1", xa, x_next=xb, scale=1e8, tpow=1), deng.apply("M1", xb, x_next=xa, scale=1e8, tpow=1),
+                    deng.apply("M1", xa, pipeline_last=True, scale=1e8, tpow=1)]
+            for yl, xg in zip(outs, (f["x1"], f["x1"][::-1].copy() * 0.5, f["x1"])):
+                yg = np.zeros((nk, mesh.N1))
+                deng.owned_to_global(yl, 1, yg)
+                t = torch.from_numpy(yg).cuda()
+                dist.all_reduce(t)
+                if rank == 0:
+                    ys = to_np(single, single.apply("M1", to_cols(single, xg, 1), scale=1e8, tpow=1), 1)
+                    if not np.array_equal(t.cpu().numpy(), ys):
+                        failures.append((what, kind, p, ne, "pipelined M1 differs from single GPU", rel_l2(t.cpu().numpy(), ys)))
+            # back in the ordinary mode: push and consume in one call
+            yl = deng.apply("M1", xb, scale=1e8, tpow=1)
+            yg = np.zeros((nk, mesh.N1))
+            deng.owned_to_global(yl, 1, yg)
+            t = torch.from_numpy(yg).cuda()
+            dist.all_reduce(t)
+            if rank == 0:
+                ys = to_np(single, single.apply("M1", to_cols(single, f["x1"][::-1].copy() * 0.5, 1), scale=1e8, tpow=1), 1)
+                if not np.array_equal(t.cpu().numpy(), ys):
+                    failures.append((what, kind, p, ne, "M1 after a pipelined sequence differs from single GPU"))
         if rank == 0:
             print("case", what, kind, p, ne, nk, "world", world, "halo bytes/rank (1-form)", deng.halo_bytes(1, f["x1"].shape[0]), flush=True)
         if deng.halo_error():

@@ -271,6 +271,57 @@ def test_k_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
         assert rel_l2(a, b) < 1e-14, rel_l2(a, b)
 
 
+def test_mass_matrix_solves_vs_reference_matrix():
+    """KSPSolve(ksp1 | ksp0) on the mass matrices.  The device CG (M1) and the pointwise M0 solve
+    against a sparse direct solve with the REFERENCE's assembled matrices (numpy restatement, pinned to the reference's
+    golden vectors in tests/test_oracle.py), p = 3, 4x4 elements per face, 3 levels (odd: register kernels) and the
+    same mesh with 4 levels (even: TMA tile kernel inside the iteration)."""
+    import scipy.sparse.linalg as spla
+    import tempfile
+    import os
+    from oracle import mimsem_oracle as mo
+    g = golden("ops_eul_sphere_p3_ne4.npz")
+    s = float(g["scale"])
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "input"))
+        mb.write_input("sphere", 3, 4, 6, os.path.join(tmp, "input"))
+        O = mo.Oracle(tmp, 6, "sphere", "eul")
+        for nk in (3, 4):
+            thick = np.concatenate([g["thick"], g["thick"][:1] * 1.7])[:nk]
+            O.set_thick(thick)
+            mesh, eng = _engine("sphere", 3, 4, thick=thick)
+            rng = np.random.default_rng(21)
+            b1 = rng.uniform(-1, 1, (nk, mesh.N1))
+            b0 = rng.uniform(-1, 1, (nk, mesh.N0))
+            x1, its, rr = eng.solve("M1", to_cols(eng, b1, 1), scale=s, tpow=1, rtol=1e-14, maxit=300)
+            assert its < 300 and rr <= 1e-13, (its, rr)
+            x1 = to_np(eng, x1, 1)
+            x0 = to_np(eng, eng.solve("M0", to_cols(eng, b0, 0), scale=s, tpow=1)[0], 0)
+            d1 = to_np(eng, eng.diag("M1", nk, scale=s, tpow=1), 1)
+            for lev in range(nk):
+                A1 = O.umat(lev, s, 1).tocsc()
+                assert rel_l2(x1[lev], spla.spsolve(A1, b1[lev])) < 1e-11, (nk, lev)
+                assert rel_l2(d1[lev], A1.diagonal()) < TOL
+                A0 = O.pmat(lev, s).tocsc()
+                assert rel_l2(x0[lev], spla.spsolve(A0, b0[lev])) < TOL
+            eng.close()
+
+
+def test_mass_matrix_solve_c5_roundtrip():
+    """C5 (p=4, 48x48 per face, 60 levels): x -> M1 x -> solve recovers x; iteration count stays mesh-independent."""
+    import torch
+    p, ne, nk = 4, 48, 60
+    mesh = mb.Mesh("sphere", p, ne)
+    eng = mb.Engine.from_mesh(mesh, 0, thick=synthetic_thickness(mesh.xyz, nk))
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    x = torch.rand((mesh.N1, nk), dtype=torch.float64, device="cuda:0", generator=gen) * 2 - 1
+    b = eng.apply("M1", x, scale=1e8, tpow=1)
+    xs, its, rr = eng.solve("M1", b, scale=1e8, tpow=1, rtol=1e-13, maxit=200)
+    assert its < 200 and rr <= 1e-12, (its, rr)
+    err = float((xs - x).norm() / x.norm())
+    assert err < 1e-10, err
+
+
 def test_multi_gpu_partitioned_apply():
     """N>1: element-block partition + NCCL ghost refresh, bitwise equal to the single-GPU result (tests/mp_check.py)."""
     import subprocess
