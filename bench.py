@@ -31,6 +31,10 @@ WORKLOADS = {
     "C5": ("sphere", 4, 48, 60, "eul"),
     "C3": ("sphere", 3, 12, 30, "eul"),
     "C4": ("box", 3, 20, 40, "box"),
+    # 1/2, 1/4 and 1/8 of C5's elements on ONE GPU (no exchange): the granularity ceiling of strong scaling
+    "C5_half": ("sphere", 4, 34, 60, "eul"),
+    "C5_quarter": ("sphere", 4, 24, 60, "eul"),
+    "C5_eighth": ("sphere", 4, 17, 60, "eul"),
 }
 SCALE = 1.0e8
 METRIC = "GDOF/s FP64 horizontal operator apply"
