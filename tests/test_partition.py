@@ -38,6 +38,37 @@ def test_partition_covers_everything_once(kind, p, ne, world):
     assert np.all(seen1 == 1) and np.all(seen2 == 1)
 
 
+@pytest.mark.parametrize("kind,p,ne,world", [("sphere", 3, 4, 2), ("sphere", 3, 4, 8), ("sphere", 4, 2, 3), ("box", 3, 4, 4)])
+def test_exchanged_rows_cover_everything_the_kernels_read(kind, p, ne, world):
+    """Only the ghost rows in [n1_owned, n1_halo) are refreshed.  Re-derive, from the mesh tables alone, every 1-form row
+    the M1 tile plan of an owned element stages (own edges, east column, north row, and the other edge family of the west /
+    south neighbour across its far line) and check that each is owned or refreshed; and that the interior elements,
+    stored first, read no foreign row at all."""
+    mesh = mb.Mesh(kind, p, ne)
+    ws = west_south_neighbours(mesh)
+    b1, b2 = 2 * p * p, p * p
+    for r in range(world):
+        P = Partition(mesh, r, world)
+        refreshed = set(P.g1[:P.n1_halo].tolist())
+        owned2 = set(P.g2[:P.n2_owned].tolist()) | {int(g) for q in P.recv[2].values() for g in q["glob"]}
+        for le in range(P.nel_owned):
+            e = int(P.elements[le])
+            reads = set(mesh.el1x[e].tolist()) | set(mesh.el1y[e].tolist())
+            faces = set(mesh.el2[e].tolist())
+            for side, shared in ((0, int(mesh.el1x[e, 0])), (1, int(mesh.el1y[e, 0]))):
+                n = int(ws[e, side])
+                if n < 0:
+                    continue
+                reads |= set(mesh.el1y[n].tolist()) if shared in set(mesh.el1x[n].tolist()) else set(mesh.el1x[n].tolist())
+                faces |= set(mesh.el2[n].tolist())          # M1(h): the neighbour's coefficient block
+            assert reads <= refreshed, (r, e, sorted(reads - refreshed)[:5])
+            assert faces <= owned2
+            if le < P.n_interior:
+                assert all(P.e0 <= d // b1 < P.e1 for d in reads) and all(P.e0 <= f // b2 < P.e1 for f in faces)
+        # the exchange is smaller than "every edge of every halo element"
+        assert P.n1_halo <= P.n1
+
+
 def test_send_lists_match_receive_lists():
     mesh = mb.Mesh("sphere", 3, 4)
     world = 4
