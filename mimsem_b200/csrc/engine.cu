@@ -1147,7 +1147,17 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     }
     if (a.nrows == 0) return MIMSEM_OK;
     if (a.width > 4) return fail(MIMSEM_ERR_UNSUPPORTED, "incidence stencil wider than 4");
-    if (nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+    const char* ev = getenv("MIMSEM_ELL_VEC");
+    const int vmax = ev ? atoi(ev) : 4;
+    if (vmax >= 4 && nlev % 4 == 0 && ld % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+        a.nlev = nlev / 4;
+        const FastDiv fd4 = make_fastdiv((unsigned)a.nlev);
+        a.div_m = fd4.m;
+        a.div_s = fd4.s;
+        k_apply_ell<4><<<grid_for(a.nrows * a.nlev, 256), 256, 0, st>>>(a);
+        return finish_launch(c, "apply_incidence");
+    }
+    if (vmax >= 2 && nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
         a.nlev = nlev / 2;
         const FastDiv fd2 = make_fastdiv((unsigned)a.nlev);
         a.div_m = fd2.m;

@@ -999,8 +999,9 @@ __global__ void __launch_bounds__(256) k_apply_m0_vec2(const __grid_constant__ N
 }
 
 // y[r][k] = sum_j sgn[r][j] x[col[r][j]][k]   (entries in a partition-invariant order, see upload_ell)
-// VEC = 2: two consecutive levels per thread through 16-byte accesses (nlev, ld even, 16-byte aligned fields);
-// a.nlev then counts level PAIRS.
+// VEC = 2 / 4: two / four consecutive levels per thread through 16-byte accesses (nlev, ld multiples of VEC, 16-byte
+// aligned fields); a.nlev then counts level GROUPS.  The kernels are bound by instruction issue per thread (index
+// loads, address arithmetic), not by HBM, so fewer, fatter threads are faster.
 template <int VEC>
 __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllArgs a) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1015,19 +1016,31 @@ __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllAr
         cols[j] = j < a.width ? a.col[r * a.width + j] : -1;
         sg[j] = j < a.width ? a.sgn[r * a.width + j] : 0;
     }
-    if (VEC == 2) {
-        double2 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (cols[j] >= 0) v[j] = __ldg(reinterpret_cast<const double2*>(a.x + (size_t)cols[j] * a.ld + k));
-        double2 s = make_double2(0.0, 0.0);
+    if (VEC >= 2) {
+        constexpr int NV = VEC >= 2 ? VEC / 2 : 1;
+        double2 v[4][NV];
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (cols[j] >= 0) {
-                s.x += sg[j] > 0 ? v[j].x : -v[j].x;
-                s.y += sg[j] > 0 ? v[j].y : -v[j].y;
+                const double2* src = reinterpret_cast<const double2*>(a.x + (size_t)cols[j] * a.ld + k);
+#pragma unroll
+                for (int u = 0; u < NV; u++) v[j][u] = __ldg(src + u);
             }
-        *reinterpret_cast<double2*>(a.y + (size_t)r * a.ld + k) = s;
+        double2 s[NV];
+#pragma unroll
+        for (int u = 0; u < NV; u++) s[u] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cols[j] >= 0) {
+#pragma unroll
+                for (int u = 0; u < NV; u++) {
+                    s[u].x += sg[j] > 0 ? v[j][u].x : -v[j][u].x;
+                    s[u].y += sg[j] > 0 ? v[j][u].y : -v[j][u].y;
+                }
+            }
+        double2* dst = reinterpret_cast<double2*>(a.y + (size_t)r * a.ld + k);
+#pragma unroll
+        for (int u = 0; u < NV; u++) dst[u] = s[u];
     } else {
         double s = 0.0;
 #pragma unroll

@@ -109,6 +109,10 @@ def test_incidence_bit_exact(fname, kind, p, ne):
         assert np.array_equal(y, (ref @ x.T).T), nm
         xf = rng.uniform(-1, 1, (3, A.shape[1]))
         assert rel_l2(_apply(eng, nm, xf), (ref @ xf.T).T) < TOL
+        # 2 and 8 levels take the 16-byte kernels (two / four levels per thread): still exact on integer data
+        for nl in (2, 8):
+            xi = rng.integers(-1000, 1000, (nl, A.shape[1])).astype(np.float64)
+            assert np.array_equal(_apply(eng, nm, xi), (ref @ xi.T).T), (nm, nl)
     # E21 E10 = 0: exact on integer data, composed on the device
     x0 = rng.integers(-1000, 1000, (2, mesh.N0)).astype(np.float64)
     z = eng.apply("E21", eng.apply("E10", to_cols(eng, x0, 0)))
