@@ -129,15 +129,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_mesh_dir(kind, p, ne, tmp_root):
+def reference_ranks(kind, ne, cores):
+    """The reference runs one MPI rank per patch: 6 n^2 ranks on the sphere (n^2 in the box) with n dividing the elements
+    per side (README.md:32 of the reference).  Use as many as the host has cores for (at most 96), at least one patch per face."""
+    best = 6 if kind == "sphere" else 1
+    for n in range(1, ne + 1):
+        if ne % n:
+            continue
+        r = (6 if kind == "sphere" else 1) * n * n
+        if r <= min(cores, 96):
+            best = max(best, r)
+    return best
+
+
+def reference_mesh_dir(kind, p, ne, tmp_root, nprocs=None):
     """input/ directory for the reference's sources: the reference-generated one when it travelled with
     the repo, else written by the product's own writer (bit-identical maps, coordinates to 1e-15)."""
-    nprocs = 6 if kind == "sphere" else 1
+    if nprocs is None:
+        nprocs = 6 if kind == "sphere" else 1
     d = os.path.join(ROOT, "oracle", "_ref", "meshes", "%s_p%d_ne%d_np%d" % (kind, p, ne, nprocs))
     if os.path.isdir(os.path.join(d, "input")):
         return d, nprocs, "reference-generated"
     import mimsem_b200 as mb
-    d = os.path.join(tmp_root, "mesh_%s_p%d_ne%d" % (kind, p, ne))
+    d = os.path.join(tmp_root, "mesh_%s_p%d_ne%d_np%d" % (kind, p, ne, nprocs))
     os.makedirs(os.path.join(d, "input"), exist_ok=True)
     mb.write_input(kind, p, ne, nprocs, os.path.join(d, "input"))
     return d, nprocs, "written by mimsem_topo_write_input"
@@ -155,8 +169,9 @@ def cpu_reference_sample(workload, nlev_sample, budget_s, seed=0):
     if not rb.available(variant):
         return None
     tmp = tempfile.mkdtemp(prefix="mimsem_bench_")
-    md, nprocs, how = reference_mesh_dir(kind, p, ne, tmp)
-    cores = min(os.cpu_count() or 1, nprocs)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    md, nprocs, how = reference_mesh_dir(kind, p, ne, tmp, reference_ranks(kind, ne, ncpu))
+    cores = min(ncpu, nprocs)
     R = rb.Reference(variant, md, nprocs, nk=nk, nthreads=cores)
     mesh = mb.Mesh(kind, p, ne)
     thick = synthetic_thickness(mesh.xyz, nk, kind)
@@ -186,8 +201,8 @@ def cpu_reference_sample(workload, nlev_sample, budget_s, seed=0):
     # it is NOT charged to the reference (reported in `sample` only)
     total = t_asm + t_mv
     return {"value": dofs / total / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "reference",
-            "sample": "%s: Umat::assemble + MatMult for %d of %d levels (reference sources via PETSc shim, %d rank threads; "
-                      "mesh %s); assemble %.2fs, SpMV %.3fs counted; shim CSR merge %.2fs not counted" % (workload, done, nk, cores, how, t_asm, t_mv, t_mrg),
+            "sample": "%s: Umat::assemble + MatMult for %d of %d levels (reference sources via PETSc shim, %d emulated MPI ranks on %d "
+                      "threads; mesh %s); assemble %.2fs, SpMV %.3fs counted; shim CSR merge %.2fs not counted" % (workload, done, nk, nprocs, cores, how, t_asm, t_mv, t_mrg),
             "matmult_only_gdofs": dofs / t_mv / 1e9,
             "matrix_free_twin_gdofs": (R.N1 / t_mf / 1e9) if t_mf else None}
 
