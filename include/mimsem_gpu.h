@@ -141,6 +141,9 @@ int mimsem_gpu_form_permutation(const mimsem_gpu_ctx* ctx, int space, int* perm)
  *   Uhmat::assemble(h2,lev,const_vert,scale)    -> apply_M1h (tpow = 1 + const_vert)     eul/Assembly.cpp:416-474
  *   Whmat::assemble(rho,lev,scale,vs_rho)       -> apply_M2h (tpow = 1 + vs_rho)         eul/Assembly.cpp:1243-1299
  *   WtQUmat::assemble(u1,lev,scale)             -> apply_K  (tpow = 2)                   eul/Assembly.cpp:933-986
+ *   Ut_mat::assemble(lev,scale)                 -> apply_M1 (tpow = 1, MIMSEM_THICK_MEAN) eul/Assembly.cpp:1338-1388
+ *   Ut_mat::assemble_h(lev,scale,rho)           -> apply_M1h (tpow = 0)                  eul/Assembly.cpp:1390-1440
+ *   WtQdUdz_mat::assemble(u1,scale)             -> apply_K  (tpow = 0, 2*scale)          eul/Assembly.cpp:1581-1640
  *   src/ variants (no thickness)                -> the same with tpow = 0                src/Assembly.cpp:30-124 ...
  * followed, in each case, by the MatMult the reference performs on the assembled matrix.
  * flags: MIMSEM_FIXED_LEVEL uses thickness level lev0 for every column (box/: Umat and Wmat are
@@ -151,6 +154,9 @@ int mimsem_gpu_form_permutation(const mimsem_gpu_ctx* ctx, int space, int* perm)
  * INTERIOR = owned elements that read no ghost row, BOUNDARY = the others.  Neither flag: all owned elements. */
 #define MIMSEM_SUBSET_INTERIOR 2
 #define MIMSEM_SUBSET_BOUNDARY 4
+/* apply_M1 only: each thickness factor is the MEAN THICKNESS of levels lev and lev+1 instead of the inverse thickness
+ * of level lev -- Ut_mat::assemble(lev, scale) is apply_M1 with tpow = 1 and this flag (eul/Assembly.cpp:1338-1388). */
+#define MIMSEM_THICK_MEAN 8
 
 int mimsem_gpu_apply_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                         const double* d_x, double* d_y, void* stream);

@@ -103,6 +103,7 @@ struct mimsem_gpu_ctx {
     DevBuf<double> d_geo, d_geo_h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
+    DevBuf<double> d_tmean;   // [nq][nkT]: mean thickness of levels k and k+1 (Ut_mat::assemble), selected by MIMSEM_THICK_MEAN
     DevBuf<double> cg_r, cg_p, cg_q, cg_dinv, cg_partial, cg_scal;   // work space of mimsem_gpu_solve_M1
     DevBuf<double> d_J4, d_det, d_Wr;   // raw Jacobians for the upwinded operators, signed quadrature weight of R(q)
     std::vector<double> xn;             // GLL nodes of order p
@@ -641,7 +642,7 @@ void fill_common(const mimsem_gpu_ctx* c, KArgs& a, int lev0, int nlev, int ld, 
     a.elq = c->d_elq.p;
     a.nbr = c->d_nbr.p;
     a.eflags = c->d_eflags.p;
-    a.tinv = c->d_tinv.p;
+    a.tinv = (flags & MIMSEM_THICK_MEAN) ? c->d_tmean.p : c->d_tinv.p;
     a.c = nullptr;
     a.el1xT = c->d_el1xT.p;
     a.elqT = c->d_elqT.p;
@@ -721,7 +722,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.st_ptr = c->d_st_ptr.p;
         t.stores = c->d_stores.p;
         t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;
-        t.x = x; t.c = h2; t.tinv = c->d_tinv.p; t.y = y;
+        t.x = x; t.c = h2; t.tinv = a.tinv; t.y = y;
         copy_basis(c, t);
         int push_ctas = 0;
         if (hf) {
@@ -1504,6 +1505,18 @@ int mimsem_gpu_set_thickness(mimsem_gpu_ctx* c, int nk, const double* h_thick) {
     for (int k = 0; k < nk; k++)
         for (int q = 0; q < c->nq; q++) tinv[(size_t)q * nk + k] = 1.0 / h_thick[(size_t)k * c->nq + q];   // eul/Geom.cpp:761
     CUDA_OK(c->d_tinv.upload(tinv));
+    {
+        // 0.5 (thick[k] + thick[k+1]) per point (eul/Assembly.cpp:1362-1364); the last level has no upper neighbour and
+        // keeps its own thickness so that the table has the same shape as the inverse-thickness one
+        std::vector<double> tm((size_t)c->nq * nk);
+        for (int k = 0; k < nk; k++)
+            for (int q = 0; q < c->nq; q++) {
+                const double t0 = h_thick[(size_t)k * c->nq + q];
+                const double t1 = k + 1 < nk ? h_thick[(size_t)(k + 1) * c->nq + q] : t0;
+                tm[(size_t)q * nk + k] = 0.5 * (t0 + t1);
+            }
+        CUDA_OK(c->d_tmean.upload(tm));
+    }
     c->nkT = nk;
     return MIMSEM_OK;
 }

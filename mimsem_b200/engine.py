@@ -9,6 +9,7 @@ from .mesh import Basis
 
 OPS = dict(M1=0, M2=1, M0=2, M1h=3, K=4, M2h=5, M0h=6, E10=10, E01=11, E21=12, E12=13)
 FIXED_LEVEL = 1
+THICK_MEAN = 8       # apply_M1: thickness factor = mean thickness of levels lev, lev+1 (Ut_mat::assemble)
 SUBSET_INTERIOR = 2
 SUBSET_BOUNDARY = 4
 

@@ -328,6 +328,40 @@ void Phmat::assemble_up(Vec ul, Vec hl, double fac, double dt) {   // src/Assemb
     sh->tpow = 0;
 }
 
+Ut_mat::Ut_mat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    attach(topo, geom);
+    sh = make_shell(topo, OP_M1, 1, 1, &M);
+}
+Ut_mat::~Ut_mat() { free_shell(sh, &M); }
+void Ut_mat::assemble(int lev, double scale) {   // eul/Assembly.cpp:1338-1388: Umat times 0.5 (thick[lev] + thick[lev+1])
+    sh->op = OP_M1;
+    sh->coeff.clear();
+    sh->lev = lev;
+    sh->scale = scale;
+    sh->tpow = 1;
+    sh->flags = MIMSEM_THICK_MEAN;
+}
+void Ut_mat::assemble_h(int lev, double scale, Vec rho) {   // eul/Assembly.cpp:1390-1440: Uhmat without its 1/thick factors
+    sh->op = OP_M1H;
+    copy_coeff(sh, rho, topo->n2);
+    sh->lev = lev;
+    sh->scale = scale;
+    sh->tpow = 0;
+    sh->flags = 0;
+}
+
+WtQdUdz_mat::WtQdUdz_mat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    attach(topo, geom);
+    sh = make_shell(topo, OP_K, 1, 2, &M);
+}
+WtQdUdz_mat::~WtQdUdz_mat() { free_shell(sh, &M); }
+void WtQdUdz_mat::assemble(Vec u1, double scale) {   // eul/Assembly.cpp:1581-1640: WtQUmat without the 1/2 and the 1/thick^2
+    copy_coeff(sh, u1, topo->n1);
+    sh->lev = 0;
+    sh->scale = 2.0 * scale;
+    sh->tpow = 0;
+}
+
 E10mat::E10mat(Topo* _topo) : topo(_topo) {
     sh10 = make_shell(topo, OP_INC + MIMSEM_E10, 0, 1, &E10);
     sh01 = make_shell(topo, OP_INC + MIMSEM_E01, 1, 0, &E01);

@@ -142,6 +142,31 @@ class Phmat {
         MimsemShell* sh;
 };
 
+// 1-form mass matrix of the horizontal-vorticity terms                  eul/Assembly.h:201-229
+class Ut_mat {
+    public:
+        Ut_mat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~Ut_mat();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(int lev, double scale);              // weighted by the mean thickness of levels lev, lev+1 (eul/Assembly.cpp:1338-1388)
+        void assemble_h(int lev, double scale, Vec rho);   // weighted by rho, no thickness factor (eul/Assembly.cpp:1390-1440)
+    private:
+        MimsemShell* sh;
+};
+
+// vertical-momentum vorticity term, 1-form -> 2-form                    eul/Assembly.h:257-280
+class WtQdUdz_mat {
+    public:
+        WtQdUdz_mat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~WtQdUdz_mat();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(Vec u1, double scale);               // u1: ghosted local 1-form (eul/Assembly.cpp:1581-1640)
+    private:
+        MimsemShell* sh;
+};
+
 // edge-node incidence and its negative transpose                       eul/Assembly.h:171-177
 class E10mat {
     public:

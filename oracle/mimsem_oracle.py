@@ -468,6 +468,38 @@ class Oracle:
             self._add(e0, e0, np.einsum("qi,eqj->eij", P, QP), trip)
         return self._csr(trip, (self.N0, self.N0))
 
+    # ---- operators of the horizontal-vorticity / vertical-momentum terms ----------------
+    def ut_mat(self, lev, scale=1.0):
+        """Ut_mat::assemble(lev, scale) (eul/Assembly.cpp:1338-1388): the 1-form mass matrix weighted by the mean
+        thickness of levels lev and lev+1 (NOT its inverse)."""
+        U, V, Q = self.em["U"], self.em["V"], self.em["Q"]
+        trip = []
+        for r in range(self.nprocs):
+            gaa, gab, gbb = self._metric(r)
+            tavg = 0.5 * (1.0 / self._tinv(r, lev) + 1.0 / self._tinv(r, lev + 1))
+            c = Q[None, :] * (scale / self.det[r]) * tavg
+            _, e1x, e1y, _ = self.inds[r]
+            self._add(e1x, e1x, np.einsum("qi,eq,qj->eij", U, gaa * c, U), trip)
+            self._add(e1x, e1y, np.einsum("qi,eq,qj->eij", U, gab * c, V), trip)
+            self._add(e1y, e1x, np.einsum("qi,eq,qj->eij", V, gab * c, U), trip)
+            self._add(e1y, e1y, np.einsum("qi,eq,qj->eij", V, gbb * c, V), trip)
+        return self._csr(trip, (self.N1, self.N1))
+
+    def ut_mat_h(self, rho, scale=1.0):
+        """Ut_mat::assemble_h(lev, scale, rho) (eul/Assembly.cpp:1390-1440): no thickness factor at all, i.e. exactly
+        Uhmat without its 1/thick factors -- umat(h2=rho) with tpow = tpow_h = 0 (the device's apply_M1h with tpow 0)."""
+        return self.umat(0, scale, 0, h2=rho, tpow_h=0)
+
+    def wtqdudz_mat(self, u1, scale=1.0):
+        """WtQdUdz_mat::assemble(u1, scale) (eul/Assembly.cpp:1581-1640): W^T diag((u_g . J[:,a]) w scale/det) [U V], i.e.
+        WtQUmat without the factor 1/2 and without the thickness factors = 2 x wtqumat(tpow = 0) (apply_K, tpow 0)."""
+        return 2.0 * self.wtqumat(u1, 0, scale, tpow=0)
+
+    def utqwmat(self, u1, scale=1.0):
+        """UtQWmat::assemble(u1, scale) (eul/Assembly.cpp:1490-1538): [U V]^T diag(...) W with interp1_g_t == interp1_g
+        (eul/Geom.cpp:392-406), i.e. the transpose of WtQdUdz_mat."""
+        return self.wtqdudz_mat(u1, scale).T.tocsr()
+
     def e10(self):
         """E10mat::E10mat, eul/Assembly.cpp:1102-1162 (INSERT_VALUES); returns (E10, E01 = -E10^T)."""
         p = self.p

@@ -258,7 +258,9 @@ void ref_set_thick(void* hv, int rank, const double* thick) {
 enum {
     OP_UMAT = 0, OP_WMAT = 1, OP_PMAT = 2, OP_UHMAT = 3, OP_WTQUMAT = 4,
     OP_E10 = 5, OP_E01 = 6, OP_E21 = 7, OP_E12 = 8, OP_PMAT_H = 9, OP_WHMAT = 10, OP_ROTMAT = 11,
-    OP_PHMAT_UP = 12, OP_ROTMAT_UP = 13
+    OP_PHMAT_UP = 12, OP_ROTMAT_UP = 13,
+    /* eul/: operators of the horizontal-vorticity / vertical-momentum terms */
+    OP_UT_MAT = 14, OP_UT_MAT_H = 15, OP_UTQWMAT = 16, OP_WTQDUDZ = 17
 };
 
 /*
@@ -337,6 +339,26 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
             case OP_ROTMAT: {
                 RotMat* A = new RotMat(topo, geom, o.node, o.edge);
                 A->assemble(v0, lev, scale);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_UT_MAT: {
+                Ut_mat* A = new Ut_mat(topo, geom, o.node, o.edge);
+                A->assemble(lev, scale);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_UT_MAT_H: {
+                Ut_mat* A = new Ut_mat(topo, geom, o.node, o.edge);
+                A->assemble_h(lev, scale, v2);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_UTQWMAT: {
+                UtQWmat* A = new UtQWmat(topo, geom, o.node, o.edge);
+                A->assemble(v1, scale);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_WTQDUDZ: {
+                WtQdUdz_mat* A = new WtQdUdz_mat(topo, geom, o.node, o.edge);
+                A->assemble(v1, scale);
                 keep[rk] = A->M->t; delete A; break;
             }
 #elif defined(REF_SRC)
@@ -428,7 +450,9 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
     double t1 = now();
     Topo* t = h->r[0].topo;
     switch (op) {
-        case OP_UMAT: case OP_UHMAT: case OP_ROTMAT: case OP_ROTMAT_UP: nrows = ncols = t->nDofs1G; break;
+        case OP_UMAT: case OP_UHMAT: case OP_ROTMAT: case OP_ROTMAT_UP: case OP_UT_MAT: case OP_UT_MAT_H: nrows = ncols = t->nDofs1G; break;
+        case OP_WTQDUDZ: nrows = t->nDofs2G; ncols = t->nDofs1G; break;
+        case OP_UTQWMAT: nrows = t->nDofs1G; ncols = t->nDofs2G; break;
         case OP_WMAT: case OP_WHMAT: nrows = ncols = t->nDofs2G; break;
         case OP_PMAT: case OP_PMAT_H: case OP_PHMAT_UP: nrows = ncols = t->nDofs0G; break;
         case OP_WTQUMAT: case OP_E21: nrows = t->nDofs2G; ncols = t->nDofs1G; break;

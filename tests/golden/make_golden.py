@@ -111,6 +111,11 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
         out["y_Whmat_vs1"] = run("Whmat", x2, flag=True, c2=h2)
         out["y_WtQUmat"] = run("WtQUmat", x1, c1=u1)
         out["y_RotMat"] = run("RotMat", x1, c0=q0)
+        # operators of the horizontal-vorticity / vertical-momentum terms
+        out["y_Ut_mat"] = np.array([R.assemble("Ut_mat", lev=lev, scale=scale) @ x1[lev] for lev in range(nk - 1)])
+        out["y_Ut_mat_h"] = run("Ut_mat_h", x1, c2=h2)
+        out["y_WtQdUdz_mat"] = run("WtQdUdz_mat", x1, c1=u1)
+        out["y_UtQWmat"] = run("UtQWmat", x2, c1=u1)
     elif variant == "src":
         out["y_Umat"] = run("Umat", x1)
         out["y_Wmat"] = run("Wmat", x2)

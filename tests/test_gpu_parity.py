@@ -326,6 +326,26 @@ def test_mass_matrix_solve_c5_roundtrip():
     assert err < 1e-10, err
 
 
+@pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
+def test_vorticity_term_operators_vs_reference_golden(fname, p, ne):
+    """SURVEY section 8f-2, the operators that map onto kernels the device already has (identities pinned against the
+    reference in tests/test_oracle.py): Ut_mat::assemble(lev, scale) = M1 with the mean thickness of levels lev, lev+1;
+    Ut_mat::assemble_h(lev, scale, rho) = M1(h) without thickness factors; WtQdUdz_mat::assemble(u1, scale) = 2 K(u1)
+    without thickness factors (eul/Assembly.cpp:1338-1440, 1581-1640)."""
+    g = golden(fname)
+    mesh, eng = _engine("sphere", p, ne, thick=g["thick"])
+    s = float(g["scale"])
+    nk = int(g["nk"])
+    y = _apply(eng, "M1h", g["x1"], g["h2"], scale=s, tpow=0)
+    assert rel_l2(y, g["y_Ut_mat_h"]) < TOL, rel_l2(y, g["y_Ut_mat_h"])
+    y = _apply(eng, "K", g["x1"], g["u1"], scale=2.0 * s, tpow=0)
+    assert rel_l2(y, g["y_WtQdUdz_mat"]) < TOL, rel_l2(y, g["y_WtQdUdz_mat"])
+    y = _apply(eng, "M1", g["x1"], scale=s, tpow=1, flags=mb.engine.THICK_MEAN)
+    assert rel_l2(y[:nk - 1], g["y_Ut_mat"]) < TOL, rel_l2(y[:nk - 1], g["y_Ut_mat"])
+    y1 = _apply_per_level(eng, "M1", g["x1"][:nk - 1], scale=s, tpow=1, flags=mb.engine.THICK_MEAN)
+    assert rel_l2(y1, g["y_Ut_mat"]) < TOL
+
+
 def test_multi_gpu_partitioned_apply():
     """N>1: element-block partition + NCCL ghost refresh, bitwise equal to the single-GPU result (tests/mp_check.py)."""
     import subprocess

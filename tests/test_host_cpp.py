@@ -116,3 +116,28 @@ def test_host_src_upwinded_classes_vs_reference_golden(tmp_path, from_files):
     assert rel_l2(y_Rup, g["y_RotMat_up"][0]) < TOL, rel_l2(y_Rup, g["y_RotMat_up"][0])
     assert rel_l2(y_Phup, g["y_Phmat_up"][0]) < TOL, rel_l2(y_Phup, g["y_Phmat_up"][0])
     assert rel_l2(y_Ph, y_Phup) > 1e-6      # the upwinding changes the operator
+
+
+@pytest.mark.gpu
+def test_host_vorticity_term_classes_vs_reference_golden(tmp_path):
+    """Ut_mat (assemble, assemble_h) and WtQdUdz_mat with the reference's eul/ signatures (eul/Assembly.h:201-229, 257-280),
+    6 emulated ranks, against vectors produced by the reference's own sources."""
+    _build()
+    g = golden("ops_eul_sphere_p3_ne4.npz")
+    nk = int(g["nk"])
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([g[k].ravel() for k in ("thick", "x1", "h2", "u1")]).astype("<f8").tofile(fin)
+    r = subprocess.run([BIN + "_vort", "-", "3", "4", "6", str(nk), fin, fout], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_apply_vort ok" in r.stdout, r.stdout + r.stderr
+    out = np.fromfile(fout, dtype="<f8")
+    N1, N2 = int(g["N1"]), int(g["N2"])
+    o = 0
+    for lev in range(nk):
+        if lev < nk - 1:
+            assert rel_l2(out[o:o + N1], g["y_Ut_mat"][lev]) < TOL, ("Ut_mat", lev)
+            o += N1
+        assert rel_l2(out[o:o + N1], g["y_Ut_mat_h"][lev]) < TOL, ("Ut_mat_h", lev)
+        o += N1
+        assert rel_l2(out[o:o + N2], g["y_WtQdUdz_mat"][lev]) < TOL, ("WtQdUdz_mat", lev)
+        o += N2
+    assert o == out.size

@@ -37,6 +37,14 @@ def test_oracle_eul_vs_golden():
         assert rel_l2(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1) @ g["x2"][lev], g["y_Whmat_vs1"][lev]) < TOL
         assert rel_l2(O.wtqumat(g["u1"][lev], lev, s) @ g["x1"][lev], g["y_WtQUmat"][lev]) < TOL
         assert rel_l2(O.rotmat(g["q0"][lev], lev, s, 2) @ g["x1"][lev], g["y_RotMat"][lev]) < TOL
+        # SURVEY section 8f-2 operators, stated through the ones the device already has:
+        #   Ut_mat::assemble_h == Uhmat without thickness factors, WtQdUdz_mat == 2 WtQUmat without thickness factors,
+        #   UtQWmat == WtQdUdz_mat^T, Ut_mat::assemble == Umat weighted by the mean thickness of two levels
+        assert rel_l2(O.ut_mat_h(g["h2"][lev], s) @ g["x1"][lev], g["y_Ut_mat_h"][lev]) < TOL
+        assert rel_l2(O.wtqdudz_mat(g["u1"][lev], s) @ g["x1"][lev], g["y_WtQdUdz_mat"][lev]) < TOL
+        assert rel_l2(O.utqwmat(g["u1"][lev], s) @ g["x2"][lev], g["y_UtQWmat"][lev]) < TOL
+        if lev < nk - 1:
+            assert rel_l2(O.ut_mat(lev, s) @ g["x1"][lev], g["y_Ut_mat"][lev]) < TOL
     E10, E01 = O.e10()
     E21, E12 = O.e21()
     for nm, A in (("E10", E10), ("E01", E01), ("E21", E21), ("E12", E12)):
