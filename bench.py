@@ -8,7 +8,14 @@ BASELINE.json configs[4] ("eul/ baroclinic scaling p=4, 48x48 elems/face, 60 lev
 BASELINE shape that is HBM-bound and the one the metric's roofline target
 is stated on; it fits one GPU (0.42 GB per field pair).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--op M1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op M1] [--workload C5] [--lockstep] [--impl reference]
+
+N > 1 (under torchrun, one rank per GPU): the one C5 mesh is split into contiguous element blocks (strong scaling); the
+ghost refresh is fused into the M1 launch over NVLink peer memory and, by default, software-pipelined over the ring of
+independent inputs (the launch of step i pushes the boundary rows of step i+1's input); --lockstep pushes and consumes
+in the same launch.  --impl reference times the reference's own CPU path (oracle/_ref) with as many emulated MPI ranks
+as the host has cores for.  --workload C5_half | C5_quarter | C5_eighth: one GPU, no exchange, 1/2 .. 1/8 of the
+elements (the granularity ceiling of strong scaling, profiles/r01_session2_summary.md section 8).
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys.
 """
