@@ -101,7 +101,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -363,6 +363,7 @@ def main():
     launches = eng.launch_count - launches0
     if replays is not None:
         launches = launches_per_step * args.steps
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -412,12 +413,6 @@ def main():
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3,
                "api": "mimsem_gpu_apply_host (per-level host layout in, per-level host layout out)" +
                       ("" if world == 1 else "; one call per rank on its ghosted local vectors, bytes summed over ranks")}
-
-    # the device-timed region lasts a few milliseconds, less than one nvidia-smi period: the sampler keeps running through the
-    # end-to-end region (same kernels, plus the copies) so that the clock record has samples under load
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = "device-timed region + end-to-end region, nvidia-smi every 25 ms"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
