@@ -107,3 +107,24 @@ def test_oracle_vs_live_reference_p4():
     y, _ = R.uvec_apply(x, lev=1, scale=1e8)
     assert rel_l2(y, R.assemble("Umat", 1, 1e8, True) @ x) < TOL
     R.close()
+
+
+@pytest.mark.skipif(not (have_ref_lib("src") and have_ref_mesh("sphere", 4, 2, 6)), reason="oracle/_ref not built")
+def test_oracle_upwinded_operators_vs_live_reference_p4():
+    """BASELINE config 2's operators at p = 4: live run of the reference's src/ sources against the restatement
+    (RotMat, RotMat_up, Phmat::assemble_up; src/Assembly.cpp:1346-1395, 1784-1853, 499-567)."""
+    from oracle import refbind as rb
+    md = ref_mesh_dir("sphere", 4, 2, 6)
+    R = rb.Reference("src", md, 6, nk=1)
+    O = mo.Oracle(md, 6, "sphere", "src")
+    rng = np.random.default_rng(17)
+    q0 = rng.uniform(-1, 1, O.N0) * 1e-4
+    u1 = rng.uniform(-1, 1, O.N1) * float(np.mean(np.abs(np.concatenate(O.det)))) * 1e-3
+    h2 = rng.uniform(0.5, 1.5, O.N2) * 1e4
+    x1 = rng.uniform(-1, 1, O.N1)
+    x0 = rng.uniform(-1, 1, O.N0)
+    fac, dt = 0.5, 300.0
+    assert rel_l2(O.rotmat(q0) @ x1, R.assemble("RotMat", c0=q0) @ x1) < TOL
+    assert rel_l2(O.rotmat(q0, u1=u1, tau=fac * dt) @ x1, R.assemble("RotMat_up", c0=q0, c1=u1, tau=fac, dt=dt) @ x1) < TOL
+    assert rel_l2(O.phmat_up(u1, h2, fac * dt) @ x0, R.assemble("Phmat_up", c1=u1, c2=h2, tau=fac, dt=dt) @ x0) < TOL
+    R.close()
