@@ -44,6 +44,7 @@ WORKLOADS = {
     "C5_eighth": ("sphere", 4, 17, 60, "eul"),
 }
 SCALE = 1.0e8
+TPOW = {"M1": 1, "M1h": 2, "M2": 1, "M0": 1, "K": 2, "E21": 0, "E12": 0, "E10": 0, "E01": 0, "M2h": 2, "M0h": 2}
 METRIC = "GDOF/s FP64 horizontal operator apply"
 
 
@@ -256,6 +257,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine tuning knob (mimsem_gpu_set_option), e.g. --opt m1_min_blocks=5; recorded in config")
     ap.add_argument("--lockstep", action="store_true", help="N > 1: push and consume the ghost rows in the same launch (no pipelining over the ring)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -284,9 +287,12 @@ def main():
         eng = DistributedEngine(mesh, thick, rank, world, local)
     else:
         eng = mb.Engine.from_mesh(mesh, local, thick=thick)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        (eng if world == 1 else eng.engine).set_option(name, int(val))
     op = args.op
     nin, nout, ncoef = eng.space_sizes(op)
-    tpow = {"M1": 1, "M1h": 2, "M2": 1, "M0": 1, "K": 2, "E21": 0, "E12": 0}[op]
+    tpow = TPOW[op]
 
     # ring of distinct field sets: every step reads and writes buffers that were last touched
     # >= RING-1 steps ago; one field pair (0.42 GB on C5) already exceeds the 126 MB L2
@@ -430,7 +436,7 @@ def main():
                 "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; operator %s over all levels in one launch "
                                        "(Nel=%d, out DOF-levels=%d)" % (args.workload, variant, p, ne, ne, nk, op, mesh.nel, out_dofs),
                            "cache": "ring of %d distinct field sets per GPU (%.0f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
-                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None,
+                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None, "options": args.opt,
                            "ghost_refresh": ("none (1 GPU)" if world == 1 else
                                              ("fused into the M1 launch over NVLink peer memory; push of step i+1's input overlapped with step i (ring of independent inputs)"
                                               if pipelined else "fused into the M1 launch over NVLink peer memory; push and consume in the same launch"))},

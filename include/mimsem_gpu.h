@@ -87,6 +87,13 @@ typedef struct mimsem_gpu_ctx mimsem_gpu_ctx;
 
 int mimsem_gpu_create(int device, mimsem_gpu_ctx** out);
 int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx);
+/* Tuning / test knobs of a context (never read from the environment on a launch path; mimsem_gpu_create consults
+ * MIMSEM_M1_VARIANT, MIMSEM_K_VARIANT, MIMSEM_ELL_VEC, MIMSEM_PREFETCH, MIMSEM_M1_MINB, MIMSEM_HOST_CHUNK once):
+ *   "m1_variant" 2 tile kernel (default) | 1 line tasks | 0 thread per element-level;  "k_variant" 1 tile | 0 registers;
+ *   "ell_vec" 4 | 2 | 1 levels per thread of the incidence kernels;  "prefetch_ahead" L2 prefetch distance in tiles;
+ *   "m1_min_blocks" register-budget variant of the M1 tile kernel;  "host_chunk" levels per stage of apply_host;
+ *   "halo_max_levels" levels per ghost row the caller's halo inboxes hold (0 = unchecked). */
+int mimsem_gpu_set_option(mimsem_gpu_ctx* ctx, const char* name, long long value);
 
 /* Basis tables (host pointers): quadrature weights w[m+1], ljxi[(m+1)(p+1)], ejxi[(m+1)p].
  * The sum-factorised kernels require m == p, where ljxi is the identity. */
@@ -256,14 +263,18 @@ int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* ctx, int64_t nrows, int nlev, int ld
  *       on the peer.  d_epoch is a device counter, one for the pushes and one for the pulls of a space, advanced by
  *       every call, so a captured CUDA graph can be replayed and several fields can be in flight;
  * d_err is set to 1 if a peer never answered (the kernels give up after ~2 s instead of hanging the GPU).
+ * nbuf = inbox copies of the space (2..4, inbox_parity_stride doubles apart): data epoch e lives in copy e % nbuf and a push
+ * of epoch e waits for the acknowledgement of epoch e - nbuf -- the SAME rule as mimsem_gpu_apply_M1_halo, so that the
+ * two mechanisms can be mixed on one space without a host synchronisation in between.  Whoever allocates the inboxes
+ * declares their capacity with mimsem_gpu_set_option(ctx, "halo_max_levels", n); calls with nlev > n are rejected.
  */
 int mimsem_gpu_ipc_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** d_ptr, unsigned char handle[64]);
 int mimsem_gpu_ipc_open(mimsem_gpu_ctx* ctx, const unsigned char handle[64], void** d_ptr);
 int mimsem_gpu_ipc_close(mimsem_gpu_ctx* ctx, void* d_ptr, int owned);
-int mimsem_gpu_halo_push(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, const double* d_field,
+int mimsem_gpu_halo_push(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, int nbuf, const double* d_field,
                          void* d_epoch, int* d_err, void* stream);
-int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, double* d_field, void* d_epoch,
-                         int* d_err, void* stream);
+int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, int nlev, int ld, int nbuf, double* d_field,
+                         void* d_epoch, int* d_err, void* stream);
 
 /*
  * M1 apply FUSED with the ghost refresh of its input (one launch per step and GPU; replaces the

@@ -12,7 +12,7 @@
 #include "../../include/mimsem_gpu.h"
 #include "errors.hpp"
 #include "kernels.cuh"
-#include "tma_kernels.cuh"
+#include "launch.hpp"
 
 using namespace mimsem;
 
@@ -82,24 +82,33 @@ struct mimsem_gpu_ctx {
     DevBuf<int> d_elist_int, d_elist_bnd;
     int n_int = 0, n_bnd = 0;
     std::vector<int> h_el1x_ext, h_el1y_ext;   // caller numbering (before perm1), kept for set_ghosts
+    // tuning / test knobs: read from the environment ONCE at mimsem_gpu_create, or set with mimsem_gpu_set_option
     int m1_variant = 2;                      // 2: TMA tile kernel (default), 1: line tasks, 0: one thread per element-level
+    int k_variant = 1;                       // 1: TMA tile kernel (default), 0: one thread per element-level
+    int ell_vec = 4;                         // widest level group of the incidence kernels (4, 2, 1)
+    int prefetch_ahead = 444;                // L2 prefetch distance of the tile kernels in tiles (0: off)
+    int m1_min_blocks = 0;                   // register-budget variant of the M1 tile kernel (0: default)
+    int host_chunk = 12;                     // levels per pipeline stage of mimsem_gpu_apply_host
+    int halo_max_levels = 0;                 // levels per ghost row the caller's halo inboxes were allocated for (0: unknown)
+#ifdef MIMSEM_DIAG
+    int diag_debug = 0;
+    long long* diag_times = nullptr;
+#endif
     // TMA tile plan (owner-computes mode)
-    bool tma_ok = false;
-    DevBuf<TileHdr> d_recs, d_recs_h;   // fixed-stride tile records: header + rec_ents copy entries
-    int rec_ents = 0, rec_ents_h = 0;
+    bool tma_ok = false, tma_h_ok = false;
+    DevBuf<TileHdr> d_recs, d_recs_h;   // fixed-stride tile records (see TileHdr)
+    int rec_stride = 0, rec_stride_h = 0, rec_list = 0, rec_list_h = 0;
     // fused ghost refresh (set_ghosts): records whose ghost rows are staged from the halo inbox; tiles ordered
     // interior first, boundary last
     DevBuf<TileHdr> d_recs_halo;
-    int rec_ents_halo = 0;
+    int rec_stride_halo = 0, rec_list_halo = 0;
     bool halo_plan_ok = false;
     DevBuf<int> d_elist_all;
     bool elist_all_identity = false;   // the caller already stores interior elements first (no indirection needed)
     DevBuf<unsigned> d_fused_counters;
     DevBuf<TileHdr> d_recs_k;           // K (WtQUmat) tile records
-    int rec_ents_k = 0;
+    int rec_stride_k = 0;
     bool k_plan_ok = false;
-    DevBuf<StoreEnt> d_stores;
-    DevBuf<int> d_st_ptr;
     DevBuf<double> d_geo, d_geo_h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
@@ -373,8 +382,9 @@ int build_node_adjacency(mimsem_gpu_ctx* c) {
 // ------------------------------------------------------------------------------------------
 // TMA tile plan: per owned element, the list of bulk copies that fills the tile's slots
 // (see M1Slots in engine.cuh) and the list of bulk stores of its owned edges.
-// ghost_from >= 0 builds only the fused-halo variant of the plain-M1 records: x rows whose CALLER index is
-// >= ghost_from are staged from inbox row (caller index - ghost_from) instead (copy kind 4).
+// Tile records of the M1 / M1(h) kernel.  ghost_from >= 0 builds only the fused-halo variant of the plain-M1 records:
+// x rows whose CALLER index is >= ghost_from are read from inbox row (caller index - ghost_from) instead (copy kind 4
+// for staged slots, negative entries of the explicit far-row list for the far lines).
 template <int P>
 int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
     using S = M1Slots<P>;
@@ -383,30 +393,32 @@ int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
         inv1.assign(c->n1, 0);
         for (int i = 0; i < c->n1; i++) inv1[c->h_perm1[i]] = i;
     }
-    constexpr int NP1 = P + 1, N1E = P * NP1, N2E = P * P, Q2 = NP1 * NP1;
-    std::vector<TileHdr> hdr(c->nel_owned), hdr_h(c->nel_owned);
-    std::vector<CopyEnt> cps, cps_h;
-    std::vector<StoreEnt> stores;
-    std::vector<int> st_ptr(c->nel_owned + 1, 0);
-    // bulk copies longer than max_run slots are split so that several lanes / TMA requests work on them in parallel
-    int max_run = 64;
-    if (const char* mr = getenv("MIMSEM_MAXRUN")) max_run = std::max(1, atoi(mr));
-    auto emit_runs = [max_run](std::vector<std::pair<int, int>>& dof_slot, int kind, std::vector<CopyEnt>& out) {
+    constexpr int NP1 = P + 1, N1E = P * NP1, N2E = P * P, Q2 = NP1 * NP1, NF = NP1 * P;
+    struct Rec {
+        TileHdr h;
+        TileFar f;
+        TileFarH fh;
+        std::vector<CopyEnt> cp, cp_h;
+        int nslots_h;
+        int list[2][NF];
+    };
+    std::vector<Rec> recs(c->nel_owned);
+    auto emit_runs = [](std::vector<std::pair<int, int>>& dof_slot, int kind, std::vector<CopyEnt>& out) {
         // merge (dof, slot) pairs that advance together into runs
         size_t i = 0;
         int filled = 0;
         while (i < dof_slot.size()) {
             size_t j = i + 1;
-            while (j < dof_slot.size() && (int)(j - i) < max_run && dof_slot[j].first == dof_slot[j - 1].first + 1 &&
-                   dof_slot[j].second == dof_slot[j - 1].second + 1)
-                j++;
+            while (j < dof_slot.size() && dof_slot[j].first == dof_slot[j - 1].first + 1 && dof_slot[j].second == dof_slot[j - 1].second + 1) j++;
             out.push_back(CopyEnt{kind, dof_slot[i].first, dof_slot[i].second, (int)(j - i)});
             filled += (int)(j - i);
             i = j;
         }
         return filled;
     };
+    bool all_contig = true, h_contig = true, any_list = false;
     for (int e = 0; e < c->nel_owned; e++) {
+        Rec& r = recs[e];
         const int* ex = &c->h_el1x[(size_t)e * N1E];
         const int* ey = &c->h_el1y[(size_t)e * N1E];
         std::vector<std::pair<int, int>> xs, ts, hs;
@@ -415,35 +427,61 @@ int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
             for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + ix], S::OX + ix * P + iy});
         for (int iy = 0; iy < P; iy++)
             for (int ix = 0; ix < P; ix++) xs.push_back({ey[iy * P + ix], S::OY + iy * P + ix});
+        // the kernel stores the owned block as one run of rows starting at st_dof
+        for (size_t i = 1; i < xs.size(); i++)
+            if (xs[i].first != xs[0].first + (int)i) all_contig = false;
+        r.h.st_dof = xs[0].first;
         for (int iy = 0; iy < P; iy++) xs.push_back({ex[iy * NP1 + P], S::XE + iy});
         for (int ix = 0; ix < P; ix++) xs.push_back({ey[P * P + ix], S::YN + ix});
         int flags = 0;
-        int nbr_el[2] = {-1, -1};
+        r.f = TileFar{0, 0, 0, 0};
+        r.fh = TileFarH{0, 0, 0, 0};
         for (int s = 0; s < 2; s++) {
+            for (int i = 0; i < NF; i++) r.list[s][i] = 0;
             const int nb = c->h_nbr[(size_t)e * 2 + s];
             if (nb < 0) continue;
             const int n = nb & 0x1fffffff, side = (nb >> 29) & 1, rev = (nb >> 30) & 1;
-            nbr_el[s] = n;
-            flags |= (s == 0 ? 1 : 4) | (rev ? (s == 0 ? 2 : 8) : 0) | (side ? (s == 0 ? 16 : 32) : 0);
-            const int OTH = s == 0 ? S::WOTH : S::SOTH;
+            flags |= (s == 0 ? TF_HAS_W : TF_HAS_S) | (rev ? (s == 0 ? TF_REV_W : TF_REV_S) : 0) | (side ? (s == 0 ? TF_ROW_W : TF_ROW_S) : 0);
+            // far line = east column (side 0): other family = y-edges xy(ix=t, qy=q)
+            // far line = north row  (side 1): other family = x-edges xx(qx=q, iy=t)
+            int rows[NF];
+            bool ghost = false;
             for (int q = 0; q <= P; q++)
                 for (int t = 0; t < P; t++) {
-                    // far line = east column (side 0): other family = y-edges xy(ix=t, qy=q)
-                    // far line = north row  (side 1): other family = x-edges xx(qx=q, iy=t)
                     const int dof = side == 0 ? c->h_el1y[(size_t)n * N1E + q * P + t] : c->h_el1x[(size_t)n * N1E + t * NP1 + q];
-                    xs.push_back({dof, OTH + q * P + t});
+                    rows[q * P + t] = dof;
+                    if (ghost_from >= 0 && inv1[dof] >= ghost_from) ghost = true;
                 }
+            bool run16 = true, asc4 = true, desc4 = true;
+            for (int i = 1; i < P * P; i++)
+                if (rows[i] != rows[0] + i) run16 = false;
+            for (int t = 1; t < P; t++) {
+                if (rows[P * P + t] != rows[P * P] + t) asc4 = false;
+                if (rows[P * P + t] != rows[P * P] - t) desc4 = false;
+            }
+            if (!ghost && run16 && (asc4 || desc4)) {
+                (s == 0 ? r.f.w16 : r.f.s16) = rows[0];
+                (s == 0 ? r.f.w4 : r.f.s4) = rows[P * P];
+                if (!asc4) flags |= (s == 0 ? TF_W4_DESC : TF_S4_DESC);
+            } else {
+                flags |= (s == 0 ? TF_LIST_W : TF_LIST_S);
+                any_list = true;
+                for (int i = 0; i < NF; i++) {
+                    const int ext = ghost_from >= 0 ? inv1[rows[i]] : -1;
+                    r.list[s][i] = (ghost_from >= 0 && ext >= ghost_from) ? -(ext - ghost_from) - 1 : rows[i];
+                }
+            }
+            // neighbour's 2-form block (M1h)
+            const int* e2 = &c->h_el2[(size_t)n * N2E];
+            for (int j = 1; j < N2E; j++)
+                if (e2[j] != e2[0] + j) h_contig = false;
+            (s == 0 ? r.fh.hw : r.fh.hs) = e2[0];
         }
         for (int q = 0; q < Q2; q++) ts.push_back({c->h_elq[(size_t)e * Q2 + q], S::T + q});
         for (int j = 0; j < N2E; j++) hs.push_back({c->h_el2[(size_t)e * N2E + j], S::H + j});
-        for (int s = 0; s < 2; s++)
-            if (nbr_el[s] >= 0)
-                for (int j = 0; j < N2E; j++) hs.push_back({c->h_el2[(size_t)nbr_el[s] * N2E + j], (s == 0 ? S::HW : S::HS) + j});
+        r.h.flags = flags;
         // plain M1
-        TileHdr h;
-        h.st_dof = (int)cps.size();   // parked: begin of this element's entries (replaced by the store row in pack())
-        h.flags = flags;
-        cps.push_back(CopyEnt{3, e, 0, 1});
+        r.cp.push_back(CopyEnt{3, e, 0, 1});
         int nx;
         if (ghost_from >= 0) {
             std::vector<std::pair<int, int>> xo, xg;
@@ -452,68 +490,56 @@ int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
                 if (ext >= ghost_from) xg.push_back({ext - ghost_from, ds.second});
                 else xo.push_back(ds);
             }
-            nx = emit_runs(xo, 0, cps) + emit_runs(xg, 4, cps);
+            nx = emit_runs(xo, 0, r.cp) + emit_runs(xg, 4, r.cp);
         } else {
-            nx = emit_runs(xs, 0, cps);
+            nx = emit_runs(xs, 0, r.cp);
         }
-        const int nt = emit_runs(ts, 2, cps);
-        h.cp_count = (int)cps.size() - h.st_dof;
-        h.nslots = nx | (nt << 16);
-        hdr[e] = h;
+        const int nt = emit_runs(ts, 2, r.cp);
+        r.h.cp_count = (int)r.cp.size();
+        r.h.nslots = nx | (nt << 16);
         // M1(h)
-        h.st_dof = (int)cps_h.size();
-        cps_h.push_back(CopyEnt{3, e, 0, 1});
-        emit_runs(xs, 0, cps_h);
-        const int nh = emit_runs(hs, 1, cps_h);
-        emit_runs(ts, 2, cps_h);
-        h.cp_count = (int)cps_h.size() - h.st_dof;
-        h.nslots = (nx + nh) | (nt << 16);
-        hdr_h[e] = h;
-        // stores: owned block
-        std::vector<std::pair<int, int>> os;
-        for (int ix = 0; ix < P; ix++)
-            for (int iy = 0; iy < P; iy++) os.push_back({ex[iy * NP1 + ix], S::OX + ix * P + iy});
-        for (int iy = 0; iy < P; iy++)
-            for (int ix = 0; ix < P; ix++) os.push_back({ey[iy * P + ix], S::OY + iy * P + ix});
-        size_t i = 0;
-        while (i < os.size()) {
-            size_t j = i + 1;
-            while (j < os.size() && os[j].first == os[j - 1].first + 1 && os[j].second == os[j - 1].second + 1) j++;
-            stores.push_back(StoreEnt{os[i].second, os[i].first, (int)(j - i), 0});
-            i = j;
-        }
-        st_ptr[e + 1] = (int)stores.size();
+        r.cp_h.push_back(CopyEnt{3, e, 0, 1});
+        emit_runs(xs, 0, r.cp_h);
+        const int nh = emit_runs(hs, 1, r.cp_h);
+        emit_runs(ts, 2, r.cp_h);
+        r.nslots_h = (nx + nh) | (nt << 16);
     }
-    // pack into fixed-stride records
-    bool all_contig = true;
-    auto pack = [&](const std::vector<TileHdr>& hd, const std::vector<CopyEnt>& cp, int& nents, DevBuf<TileHdr>& out) -> cudaError_t {
+    // pack into fixed-stride records: header words, copy entries, explicit far-row lists (only if some tile needs one)
+    static_assert(sizeof(TileHdr) == 16 && sizeof(CopyEnt) == 16 && sizeof(TileFar) == 16 && sizeof(TileFarH) == 16, "16-byte records");
+    constexpr int LIST_WORDS = (2 * NF * 4 + 15) / 16;
+    auto pack = [&](bool with_h, int& nents, int& stride, int& list_off, DevBuf<TileHdr>& out) -> cudaError_t {
         nents = 1;
-        for (auto& h : hd) nents = std::max(nents, h.cp_count);
-        static_assert(sizeof(TileHdr) == 16 && sizeof(CopyEnt) == 16, "16-byte records");
-        std::vector<TileHdr> rec((size_t)hd.size() * (1 + nents));
+        for (auto& r : recs) nents = std::max(nents, (int)(with_h ? r.cp_h.size() : r.cp.size()));
+        list_off = any_list ? kRecHdr + nents : 0;
+        stride = kRecHdr + nents + (any_list ? LIST_WORDS : 0);
+        std::vector<TileHdr> rec((size_t)recs.size() * stride);
         std::memset(rec.data(), 0, rec.size() * sizeof(TileHdr));
-        for (size_t e = 0; e < hd.size(); e++) {
-            TileHdr h = hd[e];
-            const int begin = h.st_dof;   // cp_begin was parked here by the builder
-            // owned block contiguous in slot order?
-            h.st_dof = (st_ptr[e + 1] - st_ptr[e] == 1 && stores[st_ptr[e]].slot == 0 && stores[st_ptr[e]].count == 2 * P * P)
-                           ? stores[st_ptr[e]].dof : -1;
-            if (h.st_dof < 0) all_contig = false;
-            rec[e * (1 + nents)] = h;
-            std::memcpy(&rec[e * (1 + nents) + 1], &cp[begin], (size_t)h.cp_count * sizeof(CopyEnt));
+        for (size_t e = 0; e < recs.size(); e++) {
+            const Rec& r = recs[e];
+            TileHdr* w = &rec[e * stride];
+            w[0] = r.h;
+            const std::vector<CopyEnt>& cp = with_h ? r.cp_h : r.cp;
+            if (with_h) {
+                w[0].cp_count = (int)cp.size();
+                w[0].nslots = r.nslots_h;
+            }
+            std::memcpy(&w[1], &r.f, 16);
+            std::memcpy(&w[2], &r.fh, 16);
+            std::memcpy(&w[kRecHdr], cp.data(), cp.size() * sizeof(CopyEnt));
+            if (any_list) std::memcpy(&w[list_off], &r.list[0][0], 2 * NF * sizeof(int));
         }
         return out.upload(rec);
     };
+    int nents = 0;
     if (ghost_from >= 0) {
-        CUDA_OK(pack(hdr, cps, c->rec_ents_halo, c->d_recs_halo));
+        CUDA_OK(pack(false, nents, c->rec_stride_halo, c->rec_list_halo, c->d_recs_halo));
         c->halo_plan_ok = all_contig;
         return MIMSEM_OK;
     }
-    CUDA_OK(pack(hdr, cps, c->rec_ents, c->d_recs));
-    CUDA_OK(pack(hdr_h, cps_h, c->rec_ents_h, c->d_recs_h));
-    CUDA_OK(c->d_stores.upload(stores));
-    CUDA_OK(c->d_st_ptr.upload(st_ptr));
-    c->tma_ok = all_contig;   // the tile kernel stores the owned block as one run of rows
+    CUDA_OK(pack(false, nents, c->rec_stride, c->rec_list, c->d_recs));
+    CUDA_OK(pack(true, nents, c->rec_stride_h, c->rec_list_h, c->d_recs_h));
+    c->tma_ok = all_contig;
+    c->tma_h_ok = all_contig && h_contig;
     return MIMSEM_OK;
 }
 
@@ -568,7 +594,7 @@ int build_k_plan_p(mimsem_gpu_ctx* c) {
         std::memcpy(&rec[(size_t)e * (1 + nents) + 1], ents[e].data(), ents[e].size() * sizeof(CopyEnt));
     }
     CUDA_OK(c->d_recs_k.upload(rec));
-    c->rec_ents_k = nents;
+    c->rec_stride_k = 1 + nents;
     c->k_plan_ok = ok;
     return MIMSEM_OK;
 }
@@ -690,7 +716,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     // TMA tile kernel: needs 16-byte aligned, even-length level runs and one thread per level
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
     const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
-    const bool tma_path = c->m1_variant == 2 && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64;
+    const bool tma_path = c->m1_variant == 2 && (with_h ? c->tma_h_ok : c->tma_ok) && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64;
     if (hf) {
         if (with_h || !tma_path || !c->halo_plan_ok || a.elist || ld != nlev)
             return fail(MIMSEM_ERR_UNSUPPORTED, "fused ghost refresh needs the TMA tile path (plain M1, all owned elements, even nlev == ld <= 64, set_ghosts)");
@@ -698,33 +724,21 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     }
     if (tma_path) {
         TArgs t;
-        t.halo_on = 0;
-        std::memset(&t.halo, 0, sizeof(t.halo));
+        std::memset(&t, 0, sizeof(t));
         t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
-        {
-            const char* dbg = getenv("MIMSEM_DEBUG");
-            t.debug = dbg ? atoi(dbg) : 0;
-            const char* dt = getenv("MIMSEM_DBG_TIMES");   // address of a device buffer, set by the diagnostic script
-            t.dbg_times = dt ? (long long*)strtoull(dt, NULL, 0) : NULL;
-            const char* pa = getenv("MIMSEM_PREFETCH");
-            t.prefetch_ahead = pa ? atoi(pa) : 296;   // ~ the number of CTAs resident on 148 SMs x 4
-            t.prefetch_own_slots = 2 * c->p * c->p;
-            const char* lo = getenv("MIMSEM_DEBUG_LO");
-            const char* hi = getenv("MIMSEM_DEBUG_HI");
-            t.debug_slot_lo = lo ? atoi(lo) : 0;
-            t.debug_slot_hi = hi ? atoi(hi) : 0;
-        }
+        t.prefetch_ahead = c->prefetch_ahead;
+        t.prefetch_own_slots = 2 * c->p * c->p;
         t.elist = a.elist;
         t.recs = with_h ? c->d_recs_h.p : c->d_recs.p;
-        t.rec_ents = with_h ? c->rec_ents_h : c->rec_ents;
-        t.st_ptr = c->d_st_ptr.p;
-        t.stores = c->d_stores.p;
+        t.rec_stride = with_h ? c->rec_stride_h : c->rec_stride;
+        t.rec_list = with_h ? c->rec_list_h : c->rec_list;
+        t.rec_hdr = kRecHdr;
         t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;
         t.x = x; t.c = h2; t.tinv = a.tinv; t.y = y;
         copy_basis(c, t);
-        int push_ctas = 0;
+        M1TileLaunch l{c->p, with_h, hf != nullptr, a.nel, 0, false, c->m1_min_blocks};
         if (hf) {
             if (!c->d_fused_counters.p) {
                 CUDA_OK(c->d_fused_counters.resize(80));
@@ -736,74 +750,39 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             t.halo.counters = c->d_fused_counters.p;
             t.elist = c->elist_all_identity ? nullptr : c->d_elist_all.p;
             t.recs = c->d_recs_halo.p;
-            t.rec_ents = c->rec_ents_halo;
-            push_ctas = t.halo.push_ctas = hf->npush > 0 ? std::max(1, std::min(296, hf->push_ctas)) : 0;
+            t.rec_stride = c->rec_stride_halo;
+            t.rec_list = c->rec_list_halo;
+            l.push_ctas = t.halo.push_ctas = hf->npush > 0 ? std::max(1, std::min(296, hf->push_ctas)) : 0;
+            l.push_only = hf->push_only != 0;
         }
-        int rc3 = dispatch_p(c->p, [&](auto P) {
-            constexpr int p = decltype(P)::value;
-            using S = M1Slots<p>;
-            t.geo_doubles = S::GEO;
-            const size_t smem = 16 + ((size_t)S::GEO + (size_t)(with_h ? S::NS_H : S::NS) * nlev) * sizeof(double);
-            if (smem > 227 * 1024) return 1;   // fall through to the register kernels
-            void (*kern)(const TArgs) = nullptr;
-            auto pick = [&](auto NLc) {
-                constexpr int NLv = decltype(NLc)::value;
-                if (hf) kern = k_apply_m1_tma<p, false, NLv, true>;
-                else kern = with_h ? k_apply_m1_tma<p, true, NLv, false> : k_apply_m1_tma<p, false, NLv, false>;
-            };
-            // compile-time level counts of the BASELINE configurations (C3: 30, C4: 40, C5: 60); anything else: runtime
-            if ((p == 3 || p == 4) && nlev == 60) pick(std::integral_constant<int, 60>());
-            else if (p == 3 && nlev == 30) pick(std::integral_constant<int, 30>());
-            else if (p == 3 && nlev == 40) pick(std::integral_constant<int, 40>());
-            else pick(std::integral_constant<int, 0>());
-            cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-            if (a.nel == 0) return (int)MIMSEM_OK;
-            // persistent grid: as many CTAs as fit (shared memory bound), each loops over tiles
-            int nsm = 148, per_sm = 1;
-            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
-            const char* pg = getenv("MIMSEM_PERSISTENT");
-            const bool persistent = pg && atoi(pg) != 0;   // measured equal to one CTA per tile on C5; off by default
-            t.ntiles = a.nel;
-            if (hf && hf->push_only) {
-                if (push_ctas == 0) return (int)MIMSEM_OK;
-                t.ntiles = 0;
-                kern<<<push_ctas, 128, smem, st>>>(t);
-                return finish_launch(c, "halo push (prologue)");
-            }
-            const int grid = (persistent && !hf ? std::min(a.nel, nsm * std::max(per_sm, 1)) : a.nel) + push_ctas;
-            kern<<<grid, 128, smem, st>>>(t);
-            return finish_launch(c, "apply_M1 (tma)");
-        });
-        if (rc3 != 1) return rc3;
+#ifdef MIMSEM_DIAG
+        t.debug = c->diag_debug;
+        t.dbg_times = c->diag_times;
+#endif
+        std::string err;
+        const int rc3 = launch_m1_tile(l, t, st, &err);
+        if (rc3 < 0) return fail(MIMSEM_ERR_CUDA, err);
+        if (rc3 == 0) {
+            if (l.push_only && l.push_ctas == 0) return MIMSEM_OK;
+            return finish_launch(c, l.push_only ? "halo push (prologue)" : "apply_M1 (tile)");
+        }
+        if (hf) return fail(MIMSEM_ERR_UNSUPPORTED, "fused ghost refresh: the tile does not fit in shared memory");
     }
     if (c->m1_variant == 0) {
-        return dispatch_p(c->p, [&](auto P) {
-            constexpr int p = decltype(P)::value;
-            if (with_h) k_apply_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-            else k_apply_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-            return finish_launch(c, "apply_M1");
-        });
+        launch_m1_regs(c->p, with_h, a, grid_for(threads, 128), st);
+        return finish_launch(c, "apply_M1");
     }
     a.Gc = with_h ? c->d_Gch.p : c->d_Gc.p;
     a.Gr = with_h ? c->d_Grh.p : c->d_Gr.p;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        dim3 grid(grid_for(threads, 128), 2 * p);
-        if (with_h) k_apply_m1_lines<p, true, false><<<grid, 128, 0, st>>>(a);
-        else k_apply_m1_lines<p, false, false><<<grid, 128, 0, st>>>(a);
-        int rc2 = finish_launch(c, "apply_M1");
-        if (rc2 || c->n_far == 0) return rc2;
-        // partial-sum mode: far lines nobody else in the subdomain computes
-        KArgs b = a;
-        b.nel = c->n_far;
-        b.nbr = c->d_far.p;
-        const int64_t t2 = (int64_t)b.nel * nlev;
-        if (with_h) k_apply_m1_lines<p, true, true><<<grid_for(t2, 128), 128, 0, st>>>(b);
-        else k_apply_m1_lines<p, false, true><<<grid_for(t2, 128), 128, 0, st>>>(b);
-        return finish_launch(c, "apply_M1 far lines");
-    });
+    launch_m1_lines(c->p, with_h, false, a, dim3(grid_for(threads, 128), 2 * c->p), st);
+    int rc2 = finish_launch(c, "apply_M1");
+    if (rc2 || c->n_far == 0) return rc2;
+    // partial-sum mode: far lines nobody else in the subdomain computes
+    KArgs b = a;
+    b.nel = c->n_far;
+    b.nbr = c->d_far.p;
+    launch_m1_lines(c->p, with_h, true, b, dim3(grid_for((int64_t)b.nel * nlev, 128)), st);
+    return finish_launch(c, "apply_M1 far lines");
 }
 
 int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
@@ -819,12 +798,8 @@ int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads == 0) return MIMSEM_OK;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        if (with_h) k_apply_m2<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        else k_apply_m2<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "apply_M2");
-    });
+    launch_m2(c->p, with_h, a, grid_for(threads, 128), st);
+    return finish_launch(c, "apply_M2");
 }
 
 int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* u1,
@@ -843,45 +818,28 @@ int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpo
     // TMA tile kernel (same eligibility as M1's)
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)u1 % 16 == 0);
     const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
-    const char* kv = getenv("MIMSEM_K_VARIANT");
-    if ((!kv || atoi(kv) != 0) && c->k_plan_ok && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
+    if (c->k_variant != 0 && c->k_plan_ok && c->tma_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
         TArgs t;
         std::memset(&t, 0, sizeof(t));
         t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
-        const char* pa = getenv("MIMSEM_PREFETCH");
-        t.prefetch_ahead = pa ? atoi(pa) : 296;
+        t.prefetch_ahead = c->prefetch_ahead;
         t.prefetch_own_slots = 2 * c->p * c->p + 2 * c->p;
         t.elist = a.elist;
         t.recs = c->d_recs_k.p;
-        t.rec_ents = c->rec_ents_k;
+        t.rec_stride = c->rec_stride_k;
+        t.rec_hdr = 1;
         t.geo = c->d_geo_h.p;
-        t.x = x; t.c = u1; t.tinv = c->d_tinv.p; t.y = y;
-        t.ntiles = a.nel;
+        t.x = x; t.c = u1; t.tinv = a.tinv; t.y = y;
         copy_basis(c, t);
-        int rc3 = dispatch_p(c->p, [&](auto P) {
-            constexpr int p = decltype(P)::value;
-            t.geo_doubles = M1Slots<p>::GEO;
-            const size_t smem = 16 + ((size_t)M1Slots<p>::GEO + (size_t)KSlots<p>::NS * nlev) * sizeof(double);
-            if (smem > 227 * 1024) return 1;
-            void (*kern)(const TArgs) = nullptr;
-            if ((p == 3 || p == 4) && nlev == 60) kern = k_apply_k_tma<p, 60>;
-            else if (p == 3 && nlev == 30) kern = k_apply_k_tma<p, 30>;
-            else if (p == 3 && nlev == 40) kern = k_apply_k_tma<p, 40>;
-            else kern = k_apply_k_tma<p, 0>;
-            cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (ce != cudaSuccess) return fail(MIMSEM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-            kern<<<a.nel, 128, smem, st>>>(t);
-            return finish_launch(c, "apply_K (tma)");
-        });
-        if (rc3 != 1) return rc3;
+        std::string err;
+        const int rc3 = launch_k_tile(c->p, t, a.nel, st, &err);
+        if (rc3 < 0) return fail(MIMSEM_ERR_CUDA, err);
+        if (rc3 == 0) return finish_launch(c, "apply_K (tile)");
     }
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        k_apply_k<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "apply_K");
-    });
+    launch_k_regs(c->p, a, grid_for(threads, 128), st);
+    return finish_launch(c, "apply_K");
 }
 
 int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
@@ -925,12 +883,8 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         return finish_launch(c, "apply_M0");
     }
     const int64_t threads = (int64_t)a.n0 * nlev;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        if (with_h) k_apply_m0<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        else k_apply_m0<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "apply_M0");
-    });
+    launch_m0(c->p, with_h, a, grid_for(threads, 128), st);
+    return finish_launch(c, "apply_M0");
 }
 
 // RotMat::assemble(q0) / RotMat_up::assemble(q0, ul, fac, dt) + MatMult
@@ -956,12 +910,8 @@ int apply_rot(mimsem_gpu_ctx* c, bool up, int lev0, int nlev, int ld, double sca
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
     if (threads == 0) return MIMSEM_OK;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        if (up) k_apply_rot<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        else k_apply_rot<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, up ? "apply_R_up" : "apply_R");
-    });
+    launch_rot(c->p, up, a, grid_for(threads, 128), st);
+    return finish_launch(c, up ? "apply_R_up" : "apply_R");
 }
 
 // Phmat::assemble_up(ul, hl, fac, dt) + MatMult
@@ -1004,11 +954,8 @@ int apply_m0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, in
     a.div_m = fd.m;
     a.div_s = fd.s;
     const int64_t threads = (int64_t)a.n0 * nlev;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        k_apply_m0h_up<p><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "apply_M0h_up");
-    });
+    launch_m0h_up(c->p, a, grid_for(threads, 128), st);
+    return finish_launch(c, "apply_M0h_up");
 }
 
 // diag(M1) (invert: its reciprocal) for the same arguments as apply_m1
@@ -1024,12 +971,8 @@ int diag_m1(mimsem_gpu_ctx* c, bool invert, int lev0, int nlev, int ld, double s
     a.y = d;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads == 0) return MIMSEM_OK;
-    return dispatch_p(c->p, [&](auto P) {
-        constexpr int p = decltype(P)::value;
-        if (invert) k_diag_m1<p, true><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        else k_diag_m1<p, false><<<grid_for(threads, 128), 128, 0, st>>>(a);
-        return finish_launch(c, "diag_M1");
-    });
+    launch_diag_m1(c->p, invert, a, grid_for(threads, 128), st);
+    return finish_launch(c, "diag_M1");
 }
 
 // x = M1^-1 b by Jacobi-preconditioned CG, all levels at once (per-level step lengths)
@@ -1148,8 +1091,7 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     }
     if (a.nrows == 0) return MIMSEM_OK;
     if (a.width > 4) return fail(MIMSEM_ERR_UNSUPPORTED, "incidence stencil wider than 4");
-    const char* ev = getenv("MIMSEM_ELL_VEC");
-    const int vmax = ev ? atoi(ev) : 4;
+    const int vmax = c->ell_vec;
     if (vmax >= 4 && nlev % 4 == 0 && ld % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
         a.nlev = nlev / 4;
         const FastDiv fd4 = make_fastdiv((unsigned)a.nlev);
@@ -1196,6 +1138,15 @@ int transpose(mimsem_gpu_ctx* c, bool to_columns, int space, int64_t n, int nlev
 // ==========================================================================================
 // C ABI
 
+// the inbox of a space holds halo_max_levels levels per ghost row (declared by whoever allocated it)
+static int check_halo_levels(const mimsem_gpu_ctx* c, int nlev, int ld, int nbuf) {
+    if (nlev < 1 || ld < nlev) return fail(MIMSEM_ERR_ARG, "halo exchange: bad level count / leading dimension");
+    if (nbuf < 2 || nbuf > 4) return fail(MIMSEM_ERR_ARG, "the inbox has 2..4 copies");
+    if (c->halo_max_levels > 0 && nlev > c->halo_max_levels)
+        return fail(MIMSEM_ERR_ARG, "halo exchange: more levels than the inbox was allocated for (option halo_max_levels)");
+    return MIMSEM_OK;
+}
+
 extern "C" {
 
 int mimsem_gpu_create(int device, mimsem_gpu_ctx** out) {
@@ -1214,7 +1165,31 @@ int mimsem_gpu_create(int device, mimsem_gpu_ctx** out) {
         delete c;
         return fail(MIMSEM_ERR_CUDA, cudaGetErrorString(e));
     }
+    // test / tuning knobs: the environment is consulted here, once -- never on a launch path
+    static const char* const names[] = {"m1_variant", "k_variant", "ell_vec", "prefetch_ahead", "m1_min_blocks", "host_chunk"};
+    static const char* const envs[] = {"MIMSEM_M1_VARIANT", "MIMSEM_K_VARIANT", "MIMSEM_ELL_VEC", "MIMSEM_PREFETCH", "MIMSEM_M1_MINB", "MIMSEM_HOST_CHUNK"};
+    for (int i = 0; i < 6; i++)
+        if (const char* v = getenv(envs[i])) mimsem_gpu_set_option(c, names[i], atoll(v));
     *out = c;
+    return MIMSEM_OK;
+}
+
+int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) {
+    if (!c || !name) return fail(MIMSEM_ERR_ARG, "null argument");
+    const std::string n(name);
+    const int v = (int)value;
+    if (n == "m1_variant" && v >= 0 && v <= 2) c->m1_variant = v;
+    else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
+    else if (n == "ell_vec" && (v == 1 || v == 2 || v == 4)) c->ell_vec = v;
+    else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
+    else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
+    else if (n == "host_chunk" && v >= 1) c->host_chunk = v;
+    else if (n == "halo_max_levels" && v >= 0) c->halo_max_levels = v;
+#ifdef MIMSEM_DIAG
+    else if (n == "diag_debug") c->diag_debug = v;
+    else if (n == "diag_times") c->diag_times = (long long*)value;
+#endif
+    else return fail(MIMSEM_ERR_ARG, "unknown option or value out of range: " + n);
     return MIMSEM_OK;
 }
 
@@ -1332,8 +1307,6 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         CUDA_OK(c->d_el1xT.upload(xT));
         CUDA_OK(c->d_elqT.upload(qT));
         CUDA_OK(c->d_far.upload(far));
-        const char* v = getenv("MIMSEM_M1_VARIANT");
-        if (v) c->m1_variant = atoi(v);
     }
     c->tma_ok = false;
     if (mode == 0) {
@@ -1557,7 +1530,10 @@ int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, doub
                              double* y, const double* x_push, int mode, int npush, const void* d_push, int npull,
                              const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf, int push_ctas,
                              void* d_epoch, int* d_err, void* st) {
-    if (nbuf < 2 || nbuf > 4) return fail(MIMSEM_ERR_ARG, "the inbox has 2..4 copies");
+    if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    if (int rcl = check_halo_levels(c, nlev, ld, nbuf)) return rcl;
+    // bulk copies and 16-byte stores address the inbox copies: every copy must start on a 16-byte boundary
+    if (parity_stride % 2 != 0 || (uintptr_t)d_inbox % 16 != 0) return fail(MIMSEM_ERR_ARG, "fused ghost refresh: inbox copies must be 16-byte aligned (even stride)");
     if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && !x_push)) return fail(MIMSEM_ERR_ARG, "bad pipelining mode / missing field to push");
     if (mode == 3) npush = 0;   // last call of a pipelined sequence: consume what the previous call pushed, push nothing
     if (!c || !d_epoch || !d_err || (npush > 0 && !d_push) || (npull > 0 && (!d_pull || !d_inbox)))
@@ -1686,8 +1662,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
     // Pipeline over chunks of levels (levels are independent): while chunk c is being computed, chunk c+1 is on
     // its way in and chunk c-1 on its way out; two streams ping-pong so that both PCIe directions stay busy.
     const int ld = nlev;
-    int CH = 12;
-    if (const char* ch = getenv("MIMSEM_HOST_CHUNK")) CH = std::max(1, atoi(ch));
+    int CH = std::max(1, c->host_chunk);
     if (CH % 2) CH++;
     CH = std::min(CH, nlev);
     const int nchunk = (nlev + CH - 1) / CH;
@@ -1724,17 +1699,19 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         const double* xc = c->s_x2[b].p;
         const double* cc = ncoef ? c->s_c2[b].p : nullptr;
         double* yc = c->s_y2[b].p;
+        // MIMSEM_FIXED_LEVEL: every column of every chunk uses thickness level lev0 (box/Assembly.cpp:44-45)
+        const int levk = (flags & MIMSEM_FIXED_LEVEL) ? lev0 : lev0 + k0;
         switch (op) {
-            case 0: rc = apply_m1(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
-            case 3: rc = apply_m1(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
-            case 1: rc = apply_m2(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
-            case 5: rc = apply_m2(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
-            case 2: rc = apply_m0(c, false, lev0 + k0, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
-            case 6: rc = apply_m0(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
-            case 4: rc = apply_k(c, lev0 + k0, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
-            case 7: rc = apply_rot(c, false, lev0 + k0, nl, nl, scale, tpow, flags, cc, nullptr, 0.0, xc, yc, st); break;
-            case 8: rc = apply_rot(c, true, lev0 + k0, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
-            case 9: rc = apply_m0h_up(c, lev0 + k0, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
+            case 0: rc = apply_m1(c, false, levk, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 3: rc = apply_m1(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 1: rc = apply_m2(c, false, levk, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 5: rc = apply_m2(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 2: rc = apply_m0(c, false, levk, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 6: rc = apply_m0(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 4: rc = apply_k(c, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 7: rc = apply_rot(c, false, levk, nl, nl, scale, tpow, flags, cc, nullptr, 0.0, xc, yc, st); break;
+            case 8: rc = apply_rot(c, true, levk, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
+            case 9: rc = apply_m0h_up(c, levk, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
             default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
         }
         if (rc) return rc;
@@ -1802,18 +1779,19 @@ int mimsem_gpu_ipc_close(mimsem_gpu_ctx* c, void* d_ptr, int owned) {
     return MIMSEM_OK;
 }
 
-int mimsem_gpu_halo_push(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, const double* d_field,
+int mimsem_gpu_halo_push(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, int nbuf, const double* d_field,
                          void* d_epoch, int* d_err, void* stream) {
     if (!c || !d_epoch || (npeers > 0 && (!d_peers || !d_field || !d_err))) return fail(MIMSEM_ERR_ARG, "null argument");
-    int rc = bind_device(c);
+    int rc = check_halo_levels(c, nlev, ld, nbuf);
     if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
     if (npeers > 64) return fail(MIMSEM_ERR_ARG, "at most 64 halo peers");
     if (!c->d_halo_counters.p) {
         CUDA_OK(c->d_halo_counters.resize(256));
         CUDA_OK(cudaMemset(c->d_halo_counters.p, 0, 256 * sizeof(unsigned)));
     }
     if (npeers > 0) {
-        k_halo<true><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld,
+        k_halo<true><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld, nbuf,
                                                                              const_cast<double*>(d_field),
                                                                              (const unsigned long long*)d_epoch,
                                                                              c->d_halo_counters.p + (((uintptr_t)d_epoch >> 3) & 1) * 128, d_err);
@@ -1823,18 +1801,19 @@ int mimsem_gpu_halo_push(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int
     return finish_launch(c, "halo epoch");
 }
 
-int mimsem_gpu_halo_pull(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, double* d_field, void* d_epoch,
+int mimsem_gpu_halo_pull(mimsem_gpu_ctx* c, int npeers, const void* d_peers, int nlev, int ld, int nbuf, double* d_field, void* d_epoch,
                          int* d_err, void* stream) {
     if (!c || !d_epoch || (npeers > 0 && (!d_peers || !d_field || !d_err))) return fail(MIMSEM_ERR_ARG, "null argument");
-    int rc = bind_device(c);
+    int rc = check_halo_levels(c, nlev, ld, nbuf);
     if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
     if (npeers > 64) return fail(MIMSEM_ERR_ARG, "at most 64 halo peers");
     if (!c->d_halo_counters.p) {
         CUDA_OK(c->d_halo_counters.resize(256));
         CUDA_OK(cudaMemset(c->d_halo_counters.p, 0, 256 * sizeof(unsigned)));
     }
     if (npeers > 0) {
-        k_halo<false><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld, d_field,
+        k_halo<false><<<dim3(npeers, HALO_NB), 256, 0, (cudaStream_t)stream>>>((const HaloPeer*)d_peers, nlev, ld, nbuf, d_field,
                                                                               (const unsigned long long*)d_epoch,
                                                                               c->d_halo_counters.p + 64 + (((uintptr_t)d_epoch >> 3) & 1) * 128, d_err);
         if ((rc = finish_launch(c, "halo_pull"))) return rc;

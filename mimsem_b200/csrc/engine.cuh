@@ -133,11 +133,16 @@ struct NodeArgs {
 namespace mimsem {
 
 // ---------------------------------------------------------------------------------------------
-// TMA tile kernels: one CTA per element, all levels; every operand of the element-level
-// contraction is staged in shared memory by 1-D bulk async copies (cp.async.bulk, the TMA unit),
-// issued from a per-element copy list that the host builds once at set_topo.  All topology
-// irregularity (cubed-sphere seams, reversed sides, ghost elements) lives in that list; the
-// kernel itself addresses shared memory with compile-time slot numbers.
+// TMA tile kernels: one CTA per element, all levels.  The operands every thread of the tile reads many times
+// (the element's own edges, its east column / north row, the inverse thickness, the 2-form coefficient) are
+// staged in shared memory by 1-D bulk async copies (cp.async.bulk, the TMA unit) issued from a per-element
+// copy list that the host builds once at set_topo; the operands that are read ONCE per tile -- the west / south
+// neighbour's edge family behind its far line (and its 2-form coefficient for M1(h)) -- are loaded straight into
+// registers (lanes = levels: coalesced) while the bulk copies are in flight and reduced to P+1 (resp. P) values per
+// thread.  Keeping them out of shared memory cuts the tile from 105 to 65 slots (M1, p = 4: 31 KB instead of 50 KB),
+// which is what bounds the number of resident tiles per SM.  All topology irregularity (cubed-sphere seams,
+// reversed sides, ghost elements) lives in the per-element record; the kernel itself addresses shared memory with
+// compile-time slot numbers.
 //
 // Slot s of the tile holds nlev consecutive doubles (one value per level).  Slot map for M1:
 //   [0, 2P^2)            own edges in the engine's internal block order (== memory order, so the block is ONE
@@ -145,24 +150,18 @@ namespace mimsem {
 //                        contiguous), y-edge (ix,iy<P) -> OY + iy P + ix (row-major: the south row is contiguous)
 //   XE  + iy             east column of x-edges xx(P,iy)            (owned by the east neighbour)
 //   YN  + ix             north row of y-edges   xy(ix,P)            (owned by the north neighbour)
-//   WOTH + q P + t       the west neighbour's other-family edges along its far line
-//   SOTH + q P + t       the south neighbour's other-family edges along its far line
 //   T + qy (P+1) + qx    inverse layer thickness at the element's quadrature points
-//   H, HW, HS (+P^2 each) 2-form coefficient of the element / west / south neighbour (M1h only)
+//   H  (+P^2)            2-form coefficient of the element (M1h only)
 template <int P>
 struct M1Slots {
     static constexpr int OX = 0;
     static constexpr int OY = P * P;
     static constexpr int XE = 2 * P * P;
     static constexpr int YN = XE + P;
-    static constexpr int WOTH = YN + P;
-    static constexpr int SOTH = WOTH + (P + 1) * P;
-    static constexpr int T = SOTH + (P + 1) * P;
+    static constexpr int T = YN + P;
     static constexpr int NS = T + (P + 1) * (P + 1);
     static constexpr int H = NS;
-    static constexpr int HW = H + P * P;
-    static constexpr int HS = HW + P * P;
-    static constexpr int NS_H = HS + P * P;
+    static constexpr int NS_H = H + P * P;
     // geometry record (doubles): G[q][3], then (c_own, c_oth)[q] for the west and the south far line
     static constexpr int GW = (P + 1) * (P + 1) * 3;
     static constexpr int GS = GW + 2 * (P + 1);
@@ -189,17 +188,28 @@ struct CopyEnt {      // 16 bytes
     int count;        // consecutive DOFs -> consecutive slots
 };
 
-// Per-element tile record in global memory: one header followed by rec_ents copy entries (fixed stride), so
-// that lane l fetches its entry with ONE load whose address depends only on the element number.
-struct TileHdr {      // 16 bytes
-    int st_dof;       // first output row of the element's owned block (-1: use the general store list)
+// Per-element tile record in global memory: kRecHdr 16-byte header words, then rec_ents copy entries, then (only in
+// plans that need it) 2 x (P+1)P explicit far-line rows; fixed stride, so that lane l fetches its entry with ONE load
+// whose address depends only on the element number.
+struct TileHdr {      // word 0
+    int st_dof;       // first output row of the element's owned block
     int cp_count;
-    int flags;        // bit0 has west nbr, bit1 west reversed, bit2 has south nbr, bit3 south reversed
-    int nslots;       // slots filled by the list (for the mbarrier transaction count)
+    int flags;        // TF_* bits
+    int nslots;       // slots filled by the list (for the mbarrier transaction count): x/coefficient | thickness << 16
 };
-
-struct StoreEnt {     // 16 bytes
-    int slot, dof, count, pad;
+struct TileFar {      // word 1: first rows of the far-line runs of the x field.  OTH(q,t), q <= P, t < P:
+    int w16, w4;      //   west neighbour:  q < P -> row w16 + q P + t ; q == P -> row w4 +- t  (TF_W4_DESC)
+    int s16, s4;      //   south neighbour: likewise
+};
+struct TileFarH {     // word 2
+    int hw, hs;       // first row of the west / south neighbour's 2-form block (M1h)
+    int pad0, pad1;
+};
+constexpr int kRecHdr = 3;
+enum : int {
+    TF_HAS_W = 1, TF_REV_W = 2, TF_HAS_S = 4, TF_REV_S = 8, TF_ROW_W = 16, TF_ROW_S = 32,   // ROW: the far line is a north row
+    TF_W4_DESC = 64, TF_S4_DESC = 128,      // the 4-run is stored in descending row order
+    TF_LIST_W = 256, TF_LIST_S = 512        // explicit row list instead of runs (entries < 0: inbox row -(r)-1)
 };
 
 // Ghost refresh fused into the tile kernel (multi-GPU): the first push_ctas CTAs of the grid store this rank's
@@ -207,6 +217,7 @@ struct StoreEnt {     // 16 bytes
 // tiles >= n_int wait for the flags of this epoch and then stage their ghost rows straight from the inbox (copy-list
 // kind 4) -- no pull kernel, no ghost rows in x.  The last CTA to finish acknowledges the inbox to the peers and
 // advances the device-side epoch, so the launch replays inside a CUDA graph.
+constexpr int kMaxPushPeers = 16;   // push descriptors staged in shared memory by the push role
 struct HaloFused {
     int npush, npull;
     int push_ctas;
@@ -233,24 +244,25 @@ struct TArgs {
     int contig_x;     // ld == nlev: a run of DOFs is one contiguous copy
     int contig_t;     // nkT == nlev
     int geo_doubles;
-    long long* dbg_times;     // optional [grid][6] phase timestamps (globaltimer ns) for latency breakdowns; nullptr: off
-    int ntiles;               // tiles (elements) of this launch; the grid is persistent
+    int ntiles;               // tiles (elements) of this launch
     int prefetch_ahead;       // L2-prefetch the tile this many CTAs ahead (0: off)
     int prefetch_own_slots;   // x-field slots below this number are the element's own block
-    int debug_slot_lo, debug_slot_hi;   // bit1 of debug: skip x-field copies into slots [lo, hi) (traffic experiment)
-    int debug;        // bit0: skip the arithmetic (data-movement-only timing experiment, MIMSEM_DEBUG=1)
     double scale;
     const int* elist;         // optional element subset; nullptr: element = blockIdx.x
-    const TileHdr* recs;      // [nel][1 + rec_ents] 16-byte words: header, then the copy entries
-    int rec_ents;
-    const int* st_ptr;        // [nel+1]
-    const StoreEnt* stores;
+    const TileHdr* recs;      // [nel][rec_stride] 16-byte words: kRecHdr header words (K tile: 1), copy entries, far-row list
+    int rec_stride;           // words per record
+    int rec_hdr;              // header words before the copy entries
+    int rec_list;             // word offset of the explicit far-row list (0: the plan has none)
     const double* geo;
     const double* x;
     const double* c;
     const double* tinv;
     double* y;
     double E[(kMaxP + 1) * kMaxP];
+#ifdef MIMSEM_DIAG
+    long long* dbg_times;     // [grid][6] phase timestamps (globaltimer ns), diagnostics build only
+    int debug;                // bit0 skip arithmetic, bit4 skip copies (phase-isolation timing experiments)
+#endif
 };
 
 }  // namespace mimsem

@@ -23,6 +23,7 @@
 //   K  : y = W^T (ka ul0(x) + kb ul1(x)),  (ka,kb) = 1/2 s t^2 w/det^2 G ul(u1)   (eul/Assembly.cpp:951-979)
 #pragma once
 #include "engine.cuh"
+#include "p2p_sync.cuh"
 
 namespace mimsem {
 
@@ -967,7 +968,7 @@ __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeAr
 
 // x = M0^-1 b: M0 is diagonal when the quadrature order equals the element order (KSPSolve(ksp0, ...) of
 // eul/HorizSolve.cpp:87-96, 246 becomes a pointwise division)
-__global__ void __launch_bounds__(256) k_solve_m0(const __grid_constant__ NodeArgs a) {
+static __global__ void __launch_bounds__(256) k_solve_m0(const __grid_constant__ NodeArgs a) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
     const int n = (int)fastdiv(idx, a.div_m, a.div_s);
@@ -982,7 +983,7 @@ __global__ void __launch_bounds__(256) k_solve_m0(const __grid_constant__ NodeAr
 }
 
 // M0 without a coefficient field, two levels per thread (16-byte accesses); a.nlev counts level pairs
-__global__ void __launch_bounds__(256) k_apply_m0_vec2(const __grid_constant__ NodeArgs a) {
+static __global__ void __launch_bounds__(256) k_apply_m0_vec2(const __grid_constant__ NodeArgs a) {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (unsigned)a.n0 * (unsigned)a.nlev) return;
     const int n = (int)fastdiv(idx, a.div_m, a.div_s);
@@ -1053,40 +1054,22 @@ __global__ void __launch_bounds__(256) k_apply_ell(const __grid_constant__ EllAr
     }
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// spin until *p >= want; gives up after ~4e9 cycles (a dead peer must not hang the GPU) and records the failure
-__device__ __noinline__ void spin_until(const unsigned long long* p, unsigned long long want, int* err) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(p) < want) {
-        if (clock64() - t0 > 4000000000ll) {
-            atomicExch(err, 1);
-            break;
-        }
-        __nanosleep(64);
-    }
-}
-
 // PUSH (HALO_NB CTAs per send peer): field rows -> the peer's inbox; the last CTA to finish raises the peer's flag
 // to the new epoch.  PULL (HALO_NB CTAs per receive peer): wait for the peer's flag, inbox -> ghost rows; the last
 // CTA acknowledges.  counters[peer] counts finished CTAs (reset by the last one).
 constexpr int HALO_NB = 96;
 template <bool PUSH>
-__global__ void __launch_bounds__(256) k_halo(const HaloPeer* __restrict__ peers, int nlev, int ld, double* field,
+__global__ void __launch_bounds__(256) k_halo(const HaloPeer* __restrict__ peers, int nlev, int ld, int nbuf, double* field,
                                                const unsigned long long* __restrict__ epoch, unsigned* counters, int* err) {
     const HaloPeer p = peers[blockIdx.x];
     const unsigned long long e = *epoch + 1;
-    double* box = p.inbox + (e & 1) * p.inbox_parity_stride + (size_t)p.row0 * nlev;
+    // ONE buffering rule for this kernel and the fused M1 launch (they share inbox, flags and epochs of a space):
+    // data epoch e lives in inbox copy e % nbuf; a push of epoch e waits for the acknowledgement of epoch e - nbuf
+    double* box = p.inbox + (e % (unsigned long long)nbuf) * p.inbox_parity_stride + (size_t)p.row0 * nlev;
     if (threadIdx.x == 0) {
-        // PUSH: the receiver must have consumed the buffer of epoch e-2 (same parity) ; PULL: the data of epoch e must have landed
+        // PUSH: the receiver must have consumed the copy this push overwrites ; PULL: the data of epoch e must have landed
         if (PUSH) {
-            if (e > 2) spin_until(p.wait, e - 2, err);
+            if (e > (unsigned long long)nbuf) spin_until(p.wait, e - nbuf, err);
         } else {
             spin_until(p.wait, e, err);
         }
@@ -1109,7 +1092,7 @@ __global__ void __launch_bounds__(256) k_halo(const HaloPeer* __restrict__ peers
         }
     }
 }
-__global__ void k_epoch_inc(unsigned long long* epoch) { *epoch += 1; }
+static __global__ void k_epoch_inc(unsigned long long* epoch) { *epoch += 1; }
 
 // Halo pack / unpack: packed[i*nlev + k] <-> field[rows[i]*ld + k]   (rows = ghost or send lists)
 template <bool GATHER>

@@ -1,0 +1,374 @@
+// y = M1 x and y = M1(h) x as a TMA-staged tile kernel (Umat / Uhmat / Ut_mat, eul/Assembly.cpp:51-153, 416-474,
+// 1338-1440), optionally fused with the peer-to-peer ghost refresh of its input (HaloFused, engine.cuh).
+#pragma once
+#include "tile_common.cuh"
+
+namespace mimsem {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused ghost refresh, push role.  The rows of all peers form one flat list that is split evenly over the push CTAs (a
+// CTA's share may straddle peers), sized so that a CTA moves its share in a single pass: every thread has up to four
+// independent 16-byte loads in flight, then stores them into the peers' inboxes over NVLink.  The copy is
+// latency-bound (index load -> HBM load -> remote store -> system fence), hence many small CTAs rather than few big ones.
+static __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long long epoch) {
+    const HaloFused& h = a.halo;
+    __shared__ HaloPeer peers[kMaxPushPeers];
+    __shared__ int pre[kMaxPushPeers + 1];
+    if (threadIdx.x < h.npush) {
+        peers[threadIdx.x] = h.push[threadIdx.x];
+        // the peer must have consumed the inbox copy of epoch - nbuf (the one this push overwrites)
+        if (epoch > (unsigned long long)h.nbuf) spin_until(h.push[threadIdx.x].wait, epoch - h.nbuf, h.err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int p = 0; p < h.npush; p++) {
+            pre[p] = acc;
+            acc += peers[p].nrows;
+        }
+        pre[h.npush] = acc;
+    }
+    __syncthreads();
+    const int nl2 = a.nlev >> 1;
+    const int R = pre[h.npush];
+    const int f0 = (int)(((long long)R * blockIdx.x) / h.push_ctas);
+    const int f1 = (int)(((long long)R * (blockIdx.x + 1)) / h.push_ctas);
+    const int total = (f1 - f0) * nl2;
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+        double2 v[U];
+        double2* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * blockDim.x;
+            dst[u] = nullptr;
+            if (i < total) {
+                const int f = f0 + i / nl2, k2 = i - (f - f0) * nl2;
+                int p = 0;
+                while (f >= pre[p + 1]) p++;
+                const int r = f - pre[p];
+                const HaloPeer& pp = peers[p];
+                v[u] = __ldg(reinterpret_cast<const double2*>(h.x_push + (size_t)pp.rows[r] * a.ld) + k2);
+                dst[u] = reinterpret_cast<double2*>(pp.inbox + (epoch % h.nbuf) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev) + k2;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (dst[u]) *dst[u] = v[u];
+    }
+    // the CTA barrier orders every thread's stores before the npush threads below; their system-scope fences are
+    // cumulative, so only they (not all 128 threads) pay the NVLink round trip
+    __syncthreads();
+    if (threadIdx.x < h.npush) {
+        const int p = threadIdx.x;
+        __threadfence_system();
+        const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
+        if (done == (unsigned)h.push_ctas - 1) {
+            h.counters[1 + p] = 0;
+            __threadfence_system();
+            st_release_sys(peers[p].signal, epoch);
+        }
+    }
+}
+
+// Every push CTA and every boundary tile of a fused launch ends here; the last one acknowledges the inbox of this epoch
+// to the peers (all reads from it have completed) and advances the epoch for the next launch / graph replay.
+static __device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long epoch) {
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&a.halo.counters[0], 1u);
+        last = (done == (unsigned)(a.halo.push_ctas + a.ntiles - a.halo.n_int) - 1) ? 1 : 0;
+        if (last) a.halo.counters[0] = 0;
+    }
+    __syncthreads();
+    if (!last || a.halo.push_only) return;
+    // one thread per peer: the release stores cross NVLink concurrently (a serial loop costs a round trip per peer)
+    if ((int)threadIdx.x < a.halo.npull) st_release_sys(a.halo.pull[threadIdx.x].signal, epoch);
+    if (threadIdx.x == 0) {
+        a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
+        a.halo.epoch[1] = epoch;
+        __threadfence();
+    }
+}
+
+// Boundary tile, warp 0: wait until every peer's rows of this epoch have landed (lane i watches peer i).
+// Out of line: cold code stays out of the tile body.
+static __device__ __noinline__ void halo_wait_peers(const TArgs& a, unsigned long long epoch, int lane) {
+#pragma unroll 1
+    for (int i = lane; i < a.halo.npull; i += 32) spin_until(a.halo.pull[i].wait, epoch, a.halo.err);
+    __syncwarp();
+    fence_async_all();   // the peers' generic-proxy stores are read by the async proxy (TMA) next
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Far-line operands, straight from global memory into registers (side 0: the west neighbour behind my west column,
+// side 1: the south neighbour behind my south row).  Of the neighbour's other edge family oth(q,t) only its
+// interpolation onto the far line is needed,  ubf[q] = sum_t E[P][t] oth(q,t)  (and of its 2-form coefficient only
+// hs[j] = sum_t E[P][t] h(t across, j along)), so (P+1)P + P^2 loads collapse into 2P+1 registers that stay live
+// across the wait for the bulk copies.  Lanes are levels: every load is a coalesced run of the row.
+template <int P, bool WITH_H, bool HALO>
+__device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, int flags, int side, const double* inbox, int k,
+                                          double (&ubf)[P + 1], double (&hs)[P]) {
+    const int has = side ? TF_HAS_S : TF_HAS_W;
+#pragma unroll
+    for (int q = 0; q <= P; q++) ubf[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; j++) hs[j] = 0.0;
+    if (!(flags & has)) return;
+    double oth[P + 1][P];
+    if (flags & (side ? TF_LIST_S : TF_LIST_W)) {
+        // explicit rows (ghost rows of a fused launch live in the inbox; generic numberings)
+        const int* list = reinterpret_cast<const int*>(rec + a.rec_list) + side * (P + 1) * P;
+#pragma unroll
+        for (int q = 0; q <= P; q++)
+#pragma unroll
+            for (int t = 0; t < P; t++) {
+                const int r = list[q * P + t];
+                if (HALO && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+                else oth[q][t] = a.x[(size_t)r * a.ld + k];
+            }
+    } else {
+        const TileFar fr = *reinterpret_cast<const TileFar*>(rec + 1);
+        const double* b16 = a.x + (size_t)(side ? fr.s16 : fr.w16) * a.ld + k;
+        const double* b4 = a.x + (size_t)(side ? fr.s4 : fr.w4) * a.ld + k;
+        const long long st4 = (flags & (side ? TF_S4_DESC : TF_W4_DESC)) ? -(long long)a.ld : (long long)a.ld;
+#pragma unroll
+        for (int q = 0; q < P; q++)
+#pragma unroll
+            for (int t = 0; t < P; t++) oth[q][t] = b16[(size_t)(q * P + t) * a.ld];
+#pragma unroll
+        for (int t = 0; t < P; t++) oth[P][t] = b4[t * st4];
+    }
+    double hv[WITH_H ? P : 1][WITH_H ? P : 1];
+    if (WITH_H) {
+        const TileFarH fh = *reinterpret_cast<const TileFarH*>(rec + 2);
+        const double* hb = a.c + (size_t)(side ? fh.hs : fh.hw) * a.ld + k;
+#pragma unroll
+        for (int iy = 0; iy < P; iy++)
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) hv[WITH_H ? iy : 0][WITH_H ? ix : 0] = hb[(size_t)(iy * P + ix) * a.ld];
+    }
+#pragma unroll
+    for (int q = 0; q <= P; q++) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < P; t++) s += a.E[P * P + t] * oth[q][t];
+        ubf[q] = s;
+    }
+    if (WITH_H) {
+        // neighbour's h contracted across its far line (east column: over ix; north row: over iy)
+        const bool far_is_row = flags & (side ? TF_ROW_S : TF_ROW_W);
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < P; t++) s += a.E[P * P + t] * (far_is_row ? hv[WITH_H ? t : 0][WITH_H ? j : 0] : hv[WITH_H ? j : 0][WITH_H ? t : 0]);
+            hs[j] = s;
+        }
+    }
+}
+
+// Contribution of the neighbour's far GLL line to my P shared edges (one routine for both sides and both orientations:
+// side and `rev` only select shared-memory strides).  rev: the neighbour numbers the shared edges in the opposite
+// direction (rotated cubed-sphere seam).
+template <int P, bool WITH_H, int NL>
+__device__ __forceinline__ void far_line(const TArgs& a, const double* col, const double* geo, int flags, int side,
+                                         const double (&ubf)[P + 1], const double (&hs)[P], double (&cfar)[P]) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1;
+    const int nl = NL ? NL : a.nlev;
+#pragma unroll
+    for (int j = 0; j < P; j++) cfar[j] = 0.0;
+    if (!(flags & (side ? TF_HAS_S : TF_HAS_W))) return;
+    const bool rev = flags & (side ? TF_REV_S : TF_REV_W);
+    // the shared edges in the neighbour's order: my west column xx(0,iy) = OX + iy, my south row xy(ix,0) = OY + ix
+    const double* ownp = col + (size_t)((side ? S::OY : S::OX) + (rev ? P - 1 : 0)) * nl;
+    const int ostep = rev ? -nl : nl;
+    // the far line's quadrature points are my own west column (T + q (P+1)) / south row (T + q) points
+    const int tq = side ? 1 : NP1;
+    const double* tp = col + (size_t)(S::T + (rev ? P * tq : 0)) * nl;
+    const int tstep = (rev ? -tq : tq) * nl;
+    const double* gf = geo + (side ? S::GS : S::GW);
+    double own[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) own[j] = ownp[j * ostep];
+    double f[P + 1];
+#pragma unroll
+    for (int q = 0; q <= P; q++) {
+        double ua = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
+        double c = a.scale;
+        if (a.tpow > 0) {
+            const double t = tp[q * tstep];
+            c *= t;
+            if (a.tpow > 1) c *= t;
+        }
+        if (WITH_H) {
+            double hl = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hs[j];
+            c *= hl;
+        }
+        f[q] = c * (gf[q * 2 + 0] * ua + gf[q * 2 + 1] * ubf[q]);
+    }
+    double s[P];
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q <= P; q++) v += a.E[q * P + j] * f[q];
+        s[j] = v;
+    }
+    // the neighbour's edge j is my edge (rev ? P-1-j : j)
+#pragma unroll
+    for (int j = 0; j < P; j++) cfar[j] = rev ? s[P - 1 - j] : s[j];
+}
+
+// One warp-pair's share of an element tile: DIR 0 = the x-normal edges of GLL columns 0..P-1, DIR 1 = the y-normal edges
+// of GLL rows 0..P-1; line 0 additionally receives the neighbour's far-line contribution cfar.  Each line is stored as
+// soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
+template <int P, bool WITH_H, int NL, int DIR>
+__device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, const double (&cfar)[P], double* __restrict__ y) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1;
+    const int nl = NL ? NL : a.nlev;
+#define SLOT(s) col[(size_t)(s) * nl]
+    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (DIR 0) / xx(qx=q, iy=t) (DIR 1): used P times each, kept in registers
+    double othr[P + 1][P];
+#pragma unroll
+    for (int q = 0; q <= P; q++)
+#pragma unroll
+        for (int t = 0; t < P; t++)
+            othr[q][t] = (DIR == 0) ? (q < P ? SLOT(S::OY + q * P + t) : SLOT(S::YN + t)) : (q < P ? SLOT(S::OX + q * P + t) : SLOT(S::XE + t));
+#pragma unroll
+    for (int ln = 0; ln < P; ln++) {
+        // edges ON the line: xx(ln, iy) (DIR 0) / xy(ix, ln) (DIR 1)
+        double own[P];
+#pragma unroll
+        for (int j = 0; j < P; j++) own[j] = SLOT((DIR == 0 ? S::OX : S::OY) + ln * P + j);
+        double hc[WITH_H ? P : 1];   // h contracted across the line direction
+        if (WITH_H) {
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t < P; t++) s += a.E[ln * P + t] * ((DIR == 0) ? SLOT(S::H + j * P + t) : SLOT(S::H + t * P + j));   // h(ix=t,iy=j) / h(ix=j,iy=t)
+                hc[WITH_H ? j : 0] = s;
+            }
+        }
+        double f[P + 1];
+#pragma unroll
+        for (int q = 0; q <= P; q++) {
+            double ua = 0.0, ub = 0.0;   // along-line interpolation of own, across-line interpolation of oth
+#pragma unroll
+            for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
+#pragma unroll
+            for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * othr[q][t];
+            const int qq = (DIR == 0) ? q * NP1 + ln : ln * NP1 + q;
+            double c = a.scale;
+            if (a.tpow > 0) {
+                const double t = SLOT(S::T + qq);
+                c *= t;
+                if (a.tpow > 1) c *= t;
+            }
+            if (WITH_H) {
+                double hl = 0.0;
+#pragma unroll
+                for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hc[WITH_H ? j : 0];
+                c *= hl;
+            }
+            // DIR 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; DIR 1: f1 = c (Gab ul0 + Gbb ul1), ul1 = ua
+            f[q] = (DIR == 0) ? c * (geo[qq * 3 + 0] * ua + geo[qq * 3 + 1] * ub) : c * (geo[qq * 3 + 1] * ub + geo[qq * 3 + 2] * ua);
+        }
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            double s = (ln == 0) ? cfar[j] : 0.0;
+#pragma unroll
+            for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
+            y[(size_t)(ln * P + j) * a.ld] = s;
+        }
+    }
+#undef SLOT
+}
+
+// y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 warp-pairs (x-normal / y-normal edges) x 64 level
+// lanes.  NL = compile-time number of levels (0: runtime) so that shared-memory operands use immediate offsets.
+// HALO: ghost refresh fused into the launch (see HaloFused); a separate instantiation so that the single-GPU kernel
+// carries none of its code.  MINB = resident CTAs per SM the register allocation is budgeted for.
+template <int P, bool WITH_H, int NL, bool HALO, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_constant__ TArgs a) {
+    using S = M1Slots<P>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* geo = reinterpret_cast<double*>(smem_raw + 16);
+    double* tile = geo + S::GEO;
+    const int part = threadIdx.x >> 6;
+    const int k = threadIdx.x & 63;
+    const int nl = NL ? NL : a.nlev;
+    unsigned long long epoch = 0;
+    int first_tile = blockIdx.x, tile_stride = gridDim.x;
+    if (HALO) {
+        if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) epoch = *a.halo.epoch + 1;
+        if ((int)blockIdx.x < a.halo.push_ctas) {
+            halo_push_role(a, epoch + (unsigned long long)a.halo.lead);   // data epoch of the pushed field
+            halo_cta_done(a, epoch);
+            return;
+        }
+        first_tile -= a.halo.push_ctas;
+        tile_stride -= a.halo.push_ctas;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_async_smem();
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    for (int tile_i = first_tile; tile_i < a.ntiles; tile_i += tile_stride, phase ^= 1) {
+        const int e = a.elist ? a.elist[tile_i] : tile_i;
+        const TileHdr* rec = tile_record(a, e);
+        const TileHdr hd = rec[0];
+        DBG_T(0);
+        const double* inbox = nullptr;
+        if (HALO && tile_i >= a.halo.n_int) {
+            // boundary tile: the peers' rows of this epoch must have landed in my inbox before anybody reads it
+            if (threadIdx.x < 32) halo_wait_peers(a, epoch, threadIdx.x);
+            __syncthreads();
+            inbox = a.halo.inbox + (epoch % a.halo.nbuf) * a.halo.parity_stride;
+        }
+#ifdef MIMSEM_DIAG
+        if (!(a.debug & 16))
+#endif
+        {
+            if (threadIdx.x < 32) tile_load(a, e, inbox, bar, geo, tile);
+            else if (threadIdx.x < 64 && a.prefetch_ahead > 0 && tile_i + a.prefetch_ahead < a.ntiles) {
+                const int bn = tile_i + a.prefetch_ahead;
+                tile_prefetch(a, a.elist ? a.elist[bn] : bn);
+            }
+        }
+        double ubf[P + 1], hs[P];
+        if (k < nl) far_fetch<P, WITH_H, HALO>(a, rec, hd.flags, part, inbox, k, ubf, hs);
+        DBG_T(1);
+#ifdef MIMSEM_DIAG
+        if (!(a.debug & 16))
+#endif
+        mbar_wait(bar, phase);
+        DBG_T(2);
+#ifdef MIMSEM_DIAG
+        if (!(a.debug & 1))
+#endif
+        if (k < nl) {
+            const double* col = tile + k;
+            double cfar[P];
+            far_line<P, WITH_H, NL>(a, col, geo, hd.flags, part, ubf, hs, cfar);
+            if (part == 0) tile_lines<P, WITH_H, NL, 0>(a, col, geo, cfar, a.y + (size_t)(hd.st_dof + S::OX) * a.ld + k);
+            else tile_lines<P, WITH_H, NL, 1>(a, col, geo, cfar, a.y + (size_t)(hd.st_dof + S::OY) * a.ld + k);
+        }
+        DBG_T(3);
+        if (tile_i + tile_stride < a.ntiles) __syncthreads();   // the next tile's bulk loads overwrite the buffer
+    }
+    if (HALO && first_tile >= a.halo.n_int) halo_cta_done(a, epoch);
+}
+
+}  // namespace mimsem

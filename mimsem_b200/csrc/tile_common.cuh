@@ -1,0 +1,119 @@
+// Shared pieces of the TMA-staged tile kernels (sm_100a): PTX wrappers, the copy-list walker, the L2 prefetcher.
+// See the comment above M1Slots in engine.cuh.
+#pragma once
+#include <cstdint>
+
+#include "engine.cuh"
+#include "p2p_sync.cuh"
+
+namespace mimsem {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared 1-D bulk copy (TMA), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// ask the TMA unit to pull a range into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifdef MIMSEM_DIAG
+__device__ __forceinline__ long long gtime_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_T(i) do { if (a.dbg_times && threadIdx.x == 64) a.dbg_times[(size_t)tile_i * 6 + (i)] = gtime_ns(); } while (0)
+#else
+#define DBG_T(i) do { } while (0)
+#endif
+
+__device__ __forceinline__ const TileHdr* tile_record(const TArgs& a, int e) { return a.recs + (size_t)e * a.rec_stride; }
+
+// Stage one tile: one warp walks the element's copy list (one entry per lane and round).  `inbox` = the halo inbox copy
+// of this epoch (kind-4 entries), or nullptr.
+__device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* inbox, uint64_t* bar, double* geo, double* tile) {
+    const TileHdr* rec = tile_record(a, e);
+    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr);
+    const int lane = (int)threadIdx.x & 31;
+    const int nents = a.rec_stride - a.rec_hdr;
+    // header and this lane's first entry are fetched together (no dependent load on the critical path)
+    const TileHdr h = rec[0];
+    const CopyEnt first = ents[lane < nents ? lane : 0];
+    const unsigned slot_bytes = (unsigned)a.nlev * 8u;
+    const bool with_t = a.tpow > 0;
+    for (int ci = lane; ci < h.cp_count; ci += 32) {
+        const CopyEnt c = (ci == lane) ? first : ents[ci];
+        if (c.kind == 2 && !with_t) continue;
+        if (c.kind == 3) {
+            bulk_g2s(geo, a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u, bar);
+        } else if (c.kind == 4) {
+            // ghost rows of x, straight from the inbox (rows packed with stride nlev)
+            bulk_g2s(tile + (size_t)c.slot * a.nlev, inbox + (size_t)c.src * a.nlev, slot_bytes * c.count, bar);
+        } else if (c.kind == 2) {
+            const double* src = a.tinv + (size_t)c.src * a.nkT + a.lev0;
+            double* dst = tile + (size_t)c.slot * a.nlev;
+            if (a.contig_t) bulk_g2s(dst, src, slot_bytes * c.count, bar);
+            else
+                for (int j = 0; j < c.count; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * a.nkT, slot_bytes, bar);
+        } else {
+            const double* src = (c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld;
+            double* dst = tile + (size_t)c.slot * a.nlev;
+            if (a.contig_x) bulk_g2s(dst, src, slot_bytes * c.count, bar);
+            else
+                for (int j = 0; j < c.count; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * a.ld, slot_bytes, bar);
+        }
+    }
+    // nslots = slots filled by x / coefficient entries (low 16 bits) and by thickness entries (high 16 bits)
+    const unsigned nslots = (unsigned)(h.nslots & 0xffff) + (with_t ? (unsigned)(h.nslots >> 16) : 0u);
+    if (lane == 0) mbar_arrive_expect_tx(bar, nslots * slot_bytes + (unsigned)a.geo_doubles * 8u);
+}
+
+// L2 prefetch of the DRAM-unique part of a LATER tile (its record, its own edge block, its coefficient and thickness
+// rows): by the time that tile's CTA starts, its bulk loads hit L2, which takes the HBM latency out of the per-tile
+// critical path.
+__device__ __forceinline__ void tile_prefetch(const TArgs& a, int e) {
+    const TileHdr* rec = tile_record(a, e);
+    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr);
+    const TileHdr h = rec[0];
+    const int lane = threadIdx.x & 31;
+    const unsigned slot_bytes = (unsigned)a.nlev * 8u;
+    const int own_slots = a.prefetch_own_slots;
+    for (int ci = lane; ci < h.cp_count; ci += 32) {
+        const CopyEnt c = ents[ci];
+        if (c.kind == 3) {
+            bulk_prefetch_l2(a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u);
+        } else if (c.kind == 2 && a.tpow > 0 && a.contig_t) {
+            bulk_prefetch_l2(a.tinv + (size_t)c.src * a.nkT + a.lev0, slot_bytes * c.count);
+        } else if ((c.kind == 0 && c.slot < own_slots && a.contig_x) || (c.kind == 1 && a.contig_x)) {
+            bulk_prefetch_l2((c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld, slot_bytes * c.count);
+        }
+    }
+}
+
+}  // namespace mimsem

@@ -49,6 +49,10 @@ class Engine:
             eng.set_thickness(thick)
         return eng
 
+    def set_option(self, name, value):
+        """tuning / test knob of this context (include/mimsem_gpu.h: mimsem_gpu_set_option)"""
+        check(self.L.mimsem_gpu_set_option(self._h, name.encode(), int(value)))
+
     def close(self):
         if getattr(self, "_h", None):
             self.L.mimsem_gpu_destroy(self._h)

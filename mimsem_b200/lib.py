@@ -27,6 +27,7 @@ SIGNATURES = {
     "mimsem_mesh_coords": (C.c_int, [_vp, _dp]),
     "mimsem_gpu_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "mimsem_gpu_destroy": (C.c_int, [_vp]),
+    "mimsem_gpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_longlong]),
     "mimsem_gpu_set_basis": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp]),
     "mimsem_gpu_set_topo": (C.c_int, [_vp] + [C.c_int] * 7 + [_ip] * 5),
     "mimsem_gpu_set_geom": (C.c_int, [_vp, _dp, _dp]),
@@ -59,8 +60,8 @@ SIGNATURES = {
     "mimsem_gpu_ipc_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp), C.c_char_p]),
     "mimsem_gpu_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "mimsem_gpu_ipc_close": (C.c_int, [_vp, _vp, C.c_int]),
-    "mimsem_gpu_halo_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
-    "mimsem_gpu_halo_pull": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_halo_push": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "mimsem_gpu_halo_pull": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M1_halo": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
                                            C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),

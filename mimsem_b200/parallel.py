@@ -181,7 +181,7 @@ class DistributedEngine:
 
     SUPPORTED = ("M1", "M1h", "M2", "M2h", "K", "E21", "E12")
 
-    def __init__(self, mesh, thick, rank, world, device):
+    def __init__(self, mesh, thick, rank, world, device, max_levels=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -214,7 +214,9 @@ class DistributedEngine:
         self._bufs = {}
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1)   # halo kernels get SM slots ahead of the bulk kernel
         self.overlap = True
-        self.nk_max = 1 if thick is None else int(thick.shape[0])
+        # levels per ghost row the halo inboxes are allocated for: explicit, else the thickness table's, else 1
+        self.nk_max = int(max_levels) if max_levels else (1 if thick is None else int(thick.shape[0]))
+        eng.set_option("halo_max_levels", self.nk_max)
         self.p2p = None
         self.graph_safe = False
         self._inbox = {}
@@ -225,7 +227,7 @@ class DistributedEngine:
 
     # ---------------------------------------------------------------- peer-to-peer halo (no NCCL on the data path)
     MAXP = 16
-    NBUF = 3      # inbox copies per space (the push / pull kernels use the first two, the fused M1 launch all three)
+    NBUF = 3      # inbox copies per space; the push / pull kernels and the fused M1 launch follow the same rule (epoch e -> copy e % NBUF)
 
     def _setup_p2p(self, P, sends):
         """Allocate this rank's inbox / flag buffer, exchange IPC handles and layouts (control plane: torch.distributed
@@ -251,8 +253,10 @@ class DistributedEngine:
                 assert np.array_equal(loc, n_own + row + np.arange(len(loc))), "ghost rows of a peer must be one run"
                 layout[(s, q)] = (slot, row, len(loc))
                 row += len(loc)
-            region[s] = (off, row)
-            off += self.NBUF * row * nk * 8
+            # per-copy stride in doubles, rounded up to an even number: every inbox copy starts 16-byte aligned
+            stride = row * nk + ((row * nk) & 1)
+            region[s] = (off, row, stride)
+            off += self.NBUF * stride * 8
         total = max(off, hdr_bytes + 16)
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
@@ -284,26 +288,26 @@ class DistributedEngine:
                 rows = torch.from_numpy(perm[sends[s][q]].astype(np.int32)).to(dev)
                 keep.append(rows)
                 slot_on_q, row0_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
-                off_on_q, nghost_on_q = everyone[q]["region"][s]
+                off_on_q, nghost_on_q, stride_on_q = everyone[q]["region"][s]
                 assert n_on_q == rows.numel()
-                push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, nghost_on_q * nk,
+                push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, stride_on_q,
                            peer_base[q] + (si * MAXP + slot_on_q) * 8,            # flag on q
                            my + (2 * MAXP + si * MAXP + i) * 8)                    # ack from q, in my memory
             pull = np.zeros(len(recv_peers[s]), dtype=dt)
-            off_b, nghost = region[s]
+            off_b, nghost, stride_b = region[s]
             for i, q in enumerate(recv_peers[s]):
                 rows = torch.from_numpy(perm[P.recv[s][q]["local"]].astype(np.int32)).to(dev)
                 keep.append(rows)
                 slot, row0, n = layout[(s, q)]
                 ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
-                pull[i] = (rows.data_ptr(), n, row0, my + off_b, nghost * nk,
+                pull[i] = (rows.data_ptr(), n, row0, my + off_b, stride_b,
                            peer_base[q] + (2 * MAXP + si * MAXP + ack_slot_on_q) * 8,   # ack on q
                            my + (si * MAXP + slot) * 8)                                # flag from q, in my memory
             dpush = torch.from_numpy(push.view(np.uint8).copy()).to(dev)
             dpull = torch.from_numpy(pull.view(np.uint8).copy()).to(dev)
             epochs = torch.zeros(2, dtype=torch.int64, device=dev)   # [push counter, pull counter]
             plans[s] = (len(push), dpush, len(pull), dpull, epochs)
-            self._inbox[s] = (my + off_b, nghost * nk, int(sum(int(r["nrows"]) for r in push)))
+            self._inbox[s] = (my + off_b, stride_b, int(sum(int(r["nrows"]) for r in push)))
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = dict(plans=plans, err=err, keep=keep, base=base, peer_base=peer_base)
         self.graph_safe = True
@@ -314,18 +318,26 @@ class DistributedEngine:
         """True if a p2p exchange timed out waiting for a peer."""
         return bool(self.p2p is not None and int(self.p2p["err"].item()) != 0)
 
+    def _check_levels(self, field):
+        if field.shape[1] > self.nk_max:
+            from .lib import MimsemError
+            raise MimsemError("ghost refresh of %d levels, but the halo inboxes hold %d (DistributedEngine(max_levels=...))"
+                              % (field.shape[1], self.nk_max))
+
     def push(self, field, space):
+        self._check_levels(field)
         npush, dpush, _, _, epochs = self.p2p["plans"][space]
         eng = self.engine
         from .lib import check
-        check(eng.L.mimsem_gpu_halo_push(eng._h, npush, dpush.data_ptr(), field.shape[1], field.shape[1], field.data_ptr(),
+        check(eng.L.mimsem_gpu_halo_push(eng._h, npush, dpush.data_ptr(), field.shape[1], field.shape[1], self.NBUF, field.data_ptr(),
                                          epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
 
     def pull(self, field, space):
+        self._check_levels(field)
         _, _, npull, dpull, epochs = self.p2p["plans"][space]
         eng = self.engine
         from .lib import check
-        check(eng.L.mimsem_gpu_halo_pull(eng._h, npull, dpull.data_ptr(), field.shape[1], field.shape[1], field.data_ptr(),
+        check(eng.L.mimsem_gpu_halo_pull(eng._h, npull, dpull.data_ptr(), field.shape[1], field.shape[1], self.NBUF, field.data_ptr(),
                                          epochs.data_ptr() + 8, self.p2p["err"].data_ptr(), eng._stream()))
 
     # sizes / plumbing shared with Engine
@@ -343,7 +355,6 @@ class DistributedEngine:
         """Ghost refresh of a local field.  p2p mode: push kernel (stores into the peers' inboxes) + pull kernel;
         otherwise pack -> NCCL send/recv -> unpack."""
         if self.p2p is not None:
-            assert field.shape[1] <= self.nk_max
             self.push(field, space)
             self.pull(field, space)
             return field

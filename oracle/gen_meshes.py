@@ -36,7 +36,8 @@ STANDARD = [
     ("box", 3, 4, 4),
     ("box", 3, 20, 1),      # C4 (box bubble)
 ]
-BIG = [("sphere", 4, 48, 6)]  # C5
+# C5, with the rank counts the CPU-baseline arm of bench.py picks for 6..23, 24..53, 54..95 and >= 96 host threads
+BIG = [("sphere", 4, 48, 6), ("sphere", 4, 48, 24), ("sphere", 4, 48, 54), ("sphere", 4, 48, 96)]
 
 
 def mesh_name(kind, p, ne, nprocs):

@@ -157,6 +157,93 @@ def test_umjs14_shape_vs_oracle(tmp_path):
     assert np.array_equal(eng.apply_host("E21", f["x1"]), _apply(eng, "E21", f["x1"]))
 
 
+def _oracle(tmp_path, kind, p, ne, nprocs, variant):
+    """numpy restatement of the reference's assemble path (O2, pinned to the reference itself in tests/test_oracle.py)
+    on mesh files written by the product's own writer (bit-identical to the reference's, tests/test_host.py)."""
+    from oracle import mimsem_oracle as mo
+    d = tmp_path / "input"
+    d.mkdir()
+    mb.write_input(kind, p, ne, nprocs, str(d))
+    return mo.Oracle(str(tmp_path), nprocs, kind, variant)
+
+
+def test_c5_benchmark_shape_vs_oracle(tmp_path):
+    """C5 = the configuration bench.py quotes (eul p=4, 48x48 elements per face, 60 levels): the kernels the bench
+    times -- k_apply_m1_tile<4,*,60,*>, k_apply_k_tma<4,60>, M2, M0 -- against the oracle's assembled matrices on levels
+    0, 29 and 59, relative L2 <= 1e-12."""
+    p, ne, nk = 4, 48, 60
+    mesh = mb.Mesh("sphere", p, ne)
+    thick = synthetic_thickness(mesh.xyz, nk)
+    eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
+    O = _oracle(tmp_path, "sphere", p, ne, 6, "eul")
+    O.set_thick(thick)
+    rng = np.random.default_rng(0)
+    f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+    s = 1.0e8
+    l0 = eng.launch_count
+    yM1 = _apply(eng, "M1", f["x1"], scale=s, tpow=1)
+    yM1h = _apply(eng, "M1h", f["x1"], f["h2"], scale=s, tpow=2)
+    yK = _apply(eng, "K", f["x1"], f["u1"], scale=s, tpow=2)
+    yM2 = _apply(eng, "M2", f["x2"], scale=s, tpow=1)
+    yM0 = _apply(eng, "M0", f["x0"], scale=s, tpow=1)
+    assert eng.launch_count > l0
+    for lev in (0, 29, 59):
+        assert rel_l2(yM1[lev], O.umat(lev, s, 1) @ f["x1"][lev]) < TOL, ("M1", lev)
+        assert rel_l2(yM1h[lev], O.umat(lev, s, 1, h2=f["h2"][lev], tpow_h=1) @ f["x1"][lev]) < TOL, ("M1h", lev)
+        assert rel_l2(yK[lev], O.wtqumat(f["u1"][lev], lev, s) @ f["x1"][lev]) < TOL, ("K", lev)
+        assert rel_l2(yM2[lev], O.wmat(lev, s, 1) @ f["x2"][lev]) < TOL, ("M2", lev)
+        assert rel_l2(yM0[lev], O.pmat(lev, s) @ f["x0"][lev]) < TOL, ("M0", lev)
+
+
+def test_c4_box_shape_vs_oracle(tmp_path):
+    """C4: box/ p=3, 20x20 elements, 40 levels, including the level-0 thickness of box Umat / Wmat (MIMSEM_FIXED_LEVEL)."""
+    p, ne, nk = 3, 20, 40
+    mesh = mb.Mesh("box", p, ne)
+    thick = synthetic_thickness(mesh.xyz, nk, "box")
+    eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
+    O = _oracle(tmp_path, "box", p, ne, 1, "box")
+    O.set_thick(thick)
+    rng = np.random.default_rng(1)
+    f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+    q0 = rng.uniform(-1, 1, (nk, mesh.N0)) * 1e-4
+    s = 1.0e8
+    FL = mb.engine.FIXED_LEVEL
+    yM = _apply(eng, "M1", f["x1"], scale=s, tpow=1, flags=FL)
+    yMo = _apply(eng, "M1", f["x1"], scale=s, tpow=0)
+    yW = _apply(eng, "M2", f["x2"], scale=s, tpow=1, flags=FL)
+    yF = _apply(eng, "M1h", f["x1"], f["h2"], scale=s, tpow=2)
+    yK = _apply(eng, "K", f["x1"], f["u1"], scale=s, tpow=2)
+    yR = _apply(eng, "R", f["x1"], q0, scale=s, tpow=2)
+    # host-buffer entry point with more levels than one pipeline chunk under MIMSEM_FIXED_LEVEL
+    assert np.array_equal(eng.apply_host("M1", f["x1"], scale=s, tpow=1, flags=FL), yM)
+    for lev in (0, 19, 39):
+        assert rel_l2(yM[lev], O.umat(0, s, 1) @ f["x1"][lev]) < TOL, ("Umat.M", lev)
+        assert rel_l2(yMo[lev], O.umat(0, s, 0) @ f["x1"][lev]) < TOL, ("Umat.Mo", lev)
+        assert rel_l2(yW[lev], O.wmat(0, s, 1) @ f["x2"][lev]) < TOL, ("Wmat.M", lev)
+        assert rel_l2(yF[lev], O.umat(lev, s, 1, h2=f["h2"][lev], tpow_h=1) @ f["x1"][lev]) < TOL, ("Uhmat", lev)
+        assert rel_l2(yK[lev], O.wtqumat(f["u1"][lev], lev, s) @ f["x1"][lev]) < TOL, ("WtQUmat", lev)
+        assert rel_l2(yR[lev], O.rotmat(q0[lev], lev, s, 2) @ f["x1"][lev]) < TOL, ("RotMat", lev)
+
+
+def test_c2_galewsky_shape_vs_oracle(tmp_path):
+    """C2: src/ p=3, 16x16 elements per face, one level: Uhmat, WtQUmat and the PV-upwinded RotMat_up / Phmat::assemble_up."""
+    p, ne = 3, 16
+    mesh = mb.Mesh("sphere", p, ne, signed_det=True)
+    eng = mb.Engine.from_mesh(mesh, 0)
+    O = _oracle(tmp_path, "sphere", p, ne, 6, "src")
+    rng = np.random.default_rng(2)
+    dm = float(np.abs(mesh.det).mean())
+    f = synthetic_fields(rng, 1, mesh.N0, mesh.N1, mesh.N2, dm)
+    q0 = rng.uniform(-1, 1, (1, mesh.N0)) * 1e-4
+    u_up = rng.uniform(-1, 1, (1, mesh.N1)) * dm * 1e-3
+    tau = 0.5 * 300.0
+    assert rel_l2(_apply(eng, "M1h", f["x1"], f["h2"])[0], O.umat(h2=f["h2"][0]) @ f["x1"][0]) < TOL
+    assert rel_l2(_apply(eng, "K", f["x1"], f["u1"])[0], O.wtqumat(f["u1"][0], tpow=0) @ f["x1"][0]) < TOL
+    assert rel_l2(_apply(eng, "R", f["x1"], q0)[0], O.rotmat(q0[0]) @ f["x1"][0]) < TOL
+    assert rel_l2(_apply(eng, "R_up", f["x1"], q0, u1=u_up, tau=tau)[0], O.rotmat(q0[0], u1=u_up[0], tau=tau) @ f["x1"][0]) < TOL
+    assert rel_l2(_apply(eng, "M0h_up", f["x0"], f["h2"], u1=u_up, tau=tau)[0], O.phmat_up(u_up[0], f["h2"][0], tau) @ f["x0"][0]) < TOL
+
+
 def test_full_size_properties_c5():
     """C5: eul p=4, 48x48 elements/face, 60 levels (26.5 M 1-form DOF-levels) -- properties that need no oracle."""
     import torch
