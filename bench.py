@@ -8,14 +8,19 @@ BASELINE.json configs[4] ("eul/ baroclinic scaling p=4, 48x48 elems/face, 60 lev
 BASELINE shape that is HBM-bound and the one the metric's roofline target
 is stated on; it fits one GPU (0.42 GB per field pair).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--op M1] [--workload C5] [--lockstep] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--op M1] [--workload C5] [--chain] [--pipelined] [--impl reference]
 
-N > 1 (under torchrun, one rank per GPU): the one C5 mesh is split into contiguous element blocks (strong scaling); the
-ghost refresh is fused into the M1 launch over NVLink peer memory and, by default, software-pipelined over the ring of
-independent inputs (the launch of step i pushes the boundary rows of step i+1's input); --lockstep pushes and consumes
-in the same launch.  --impl reference times the reference's own CPU path (oracle/_ref) with as many emulated MPI ranks
-as the host has cores for.  --workload C5_half | C5_quarter | C5_eighth: one GPU, no exchange, 1/2 .. 1/8 of the
-elements (the granularity ceiling of strong scaling, profiles/r01_session2_summary.md section 8).
+N > 1 (under torchrun, one rank per GPU): the one C5 mesh is split into contiguous element blocks (STRONG scaling); the
+ghost refresh is fused into the M1 launch over NVLink peer memory.  The timed mode is LOCKSTEP -- every launch pushes
+the boundary rows of its own input and consumes them, which is what a dependent sequence of applies (a solver
+iteration) does; the software-pipelined mode (the launch of step i pushes the rows of step i+1's independent input) is
+timed afterwards and reported as the extra field "pipelined".  Before anything is timed, the N-GPU output of step 0 is
+compared BITWISE with a single-GPU apply of the gathered input on rank 0; no number is printed if they differ.
+--impl reference times the reference's own CPU path (oracle/_ref) with as many emulated MPI ranks as the host has
+cores for; it imports nothing of the product.  --workload C1..C4: the other BASELINE shapes (L2-resident, launch-bound);
+--chain times the diagnose chain (4 x Uhmat apply + E21) of one time step under ONE CUDA graph instead of a single
+operator.  --workload C5_half | C5_quarter | C5_eighth: one GPU, no exchange, 1/2 .. 1/8 of the elements (the
+granularity ceiling of strong scaling).
 
 Prints ONE JSON line (rank 0).  See the task contract for the keys.
 """
@@ -35,24 +40,29 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 WORKLOADS = {
     # name: (kind, p, ne, nk, variant)
-    "C5": ("sphere", 4, 48, 60, "eul"),
+    "C1": ("sphere", 3, 4, 1, "src"),
+    "C2": ("sphere", 3, 16, 1, "src"),
     "C3": ("sphere", 3, 12, 30, "eul"),
     "C4": ("box", 3, 20, 40, "box"),
+    "C5": ("sphere", 4, 48, 60, "eul"),
     # 1/2, 1/4 and 1/8 of C5's elements on ONE GPU (no exchange): the granularity ceiling of strong scaling
     "C5_half": ("sphere", 4, 34, 60, "eul"),
     "C5_quarter": ("sphere", 4, 24, 60, "eul"),
     "C5_eighth": ("sphere", 4, 17, 60, "eul"),
 }
 SCALE = 1.0e8
-TPOW = {"M1": 1, "M1h": 2, "M2": 1, "M0": 1, "K": 2, "E21": 0, "E12": 0, "E10": 0, "E01": 0, "M2h": 2, "M0h": 2}
+TPOW = {"M1": 1, "M1h": 2, "M2": 1, "M0": 1, "K": 2, "E21": 0, "E12": 0, "E10": 0, "E01": 0, "M2h": 2, "M0h": 2, "R": 2,
+        "R_up": 0, "M0h_up": 0}
+OPS = ["M1", "M1h", "M2", "M0", "K", "E21", "E12", "E10", "E01", "R_up", "M0h_up"]
 METRIC = "GDOF/s FP64 horizontal operator apply"
+UP_TAU = 0.5 * 300.0   # src/SWEqn_Picard.cpp:30 UP_TAU times a 300 s step
 
 
-def algorithmic_bytes(op, nel, q2, N0, N1, N2, NQ, nk):
+def algorithmic_bytes(op, nel, q2, N0, N1, N2, NQ, nk, thickness=True):
     """Compulsory HBM traffic of one launch: every input and output DOF once, the
-    per-point inverse thickness once per unique quadrature point per level, coefficient fields once,
-    the pre-scaled geometry once per (element, quadrature point)."""
-    thick = 8 * NQ * nk
+    per-point inverse thickness once per unique quadrature point per level (3-D only), coefficient fields once,
+    the pre-scaled geometry once per (element, quadrature point).  Returns (bytes, output DOF-levels)."""
+    thick = 8 * NQ * nk if thickness else 0
     if op == "M1":
         return 8 * N1 * nk * 2 + thick + 24 * nel * q2, N1 * nk
     if op == "M1h":
@@ -67,16 +77,26 @@ def algorithmic_bytes(op, nel, q2, N0, N1, N2, NQ, nk):
         return 8 * N1 * nk + 8 * N2 * nk, N2 * nk
     if op == "E12":
         return 8 * N2 * nk + 8 * N1 * nk, N1 * nk
+    if op == "E10":
+        return 8 * N0 * nk + 8 * N1 * nk, N1 * nk
+    if op == "E01":
+        return 8 * N1 * nk + 8 * N0 * nk, N0 * nk
+    if op == "R_up":    # x, y, u1 (1-forms), q0 (0-form), J (4) + det + signed weight per (element, point)
+        return 8 * N1 * nk * 3 + 8 * N0 * nk + thick + 48 * nel * q2, N1 * nk
+    if op == "M0h_up":  # x, y (0-forms), h2 (2-form), u1 (1-form), J (4) + det per (element, point)
+        return 8 * N0 * nk * 2 + 8 * N2 * nk + 8 * N1 * nk + thick + 40 * nel * q2, N0 * nk
     raise ValueError(op)
 
 
 def ncu_traffic(workload, op):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r01_traffic.json), or None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[workload][op]
-        return t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r0*_traffic.json), or None."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[workload][op]
+            return t["dram_bytes_read"] + t["dram_bytes_write"], "ncu --set full capture, profiles/" + name
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -122,20 +142,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own sources (oracle/_ref), nothing of the product
 
 def reference_ranks(kind, ne, cores):
     """The reference runs one MPI rank per patch: 6 n^2 ranks on the sphere (n^2 in the box) with n dividing the elements
@@ -150,48 +174,43 @@ def reference_ranks(kind, ne, cores):
     return best
 
 
-def reference_mesh_dir(kind, p, ne, tmp_root, nprocs=None):
-    """input/ directory for the reference's sources: the reference-generated one when it travelled with
-    the repo, else written by the product's own writer (bit-identical maps, coordinates to 1e-15)."""
-    if nprocs is None:
-        nprocs = 6 if kind == "sphere" else 1
-    d = os.path.join(ROOT, "oracle", "_ref", "meshes", "%s_p%d_ne%d_np%d" % (kind, p, ne, nprocs))
-    if os.path.isdir(os.path.join(d, "input")):
-        return d, nprocs, "reference-generated"
-    import mimsem_b200 as mb
-    d = os.path.join(tmp_root, "mesh_%s_p%d_ne%d_np%d" % (kind, p, ne, nprocs))
-    os.makedirs(os.path.join(d, "input"), exist_ok=True)
-    mb.write_input(kind, p, ne, nprocs, os.path.join(d, "input"))
-    return d, nprocs, "written by mimsem_topo_write_input"
+def reference_mesh_dir(kind, p, ne, nprocs):
+    """input/ directory written by the reference's OWN generator scripts (oracle/gen_meshes.py, travels in oracle/_ref);
+    falls back to fewer ranks if that rank count was not generated.  Returns (dir, nprocs) or (None, None)."""
+    base = 6 if kind == "sphere" else 1
+    cands = sorted({nprocs, base} | {base * n * n for n in range(1, 12) if base * n * n <= nprocs}, reverse=True)
+    for np_ in cands:
+        d = os.path.join(ROOT, "oracle", "_ref", "meshes", "%s_p%d_ne%d_np%d" % (kind, p, ne, np_))
+        if os.path.isdir(os.path.join(d, "input")):
+            return d, np_
+    return None, None
 
 
 def cpu_reference_sample(workload, nlev_sample, budget_s, seed=0):
     """Time the reference's own CPU path (oracle/_ref: its unmodified sources behind the PETSc shim) on a
     bounded sample of the workload: Umat::assemble + MatMult for `nlev_sample` levels, one emulated MPI
-    rank per cube face on its own host thread."""
-    import tempfile
+    rank per patch, each on its own host thread.  Meshes, coordinates and geometry are the reference's own."""
     from helpers import synthetic_thickness
     from oracle import refbind as rb
-    import mimsem_b200 as mb
     kind, p, ne, nk, variant = WORKLOADS[workload]
     if not rb.available(variant):
         return None
-    tmp = tempfile.mkdtemp(prefix="mimsem_bench_")
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    md, nprocs, how = reference_mesh_dir(kind, p, ne, tmp, reference_ranks(kind, ne, ncpu))
+    md, nprocs = reference_mesh_dir(kind, p, ne, reference_ranks(kind, ne, ncpu))
+    if md is None:
+        return None
     cores = min(ncpu, nprocs)
     R = rb.Reference(variant, md, nprocs, nk=nk, nthreads=cores)
-    mesh = mb.Mesh(kind, p, ne)
-    thick = synthetic_thickness(mesh.xyz, nk, kind)
-    for r in range(nprocs):
-        R.set_thick(r, thick[:, R.loc(r, "locq" if variant == "eul" else "loc0")])
+    if variant != "src":
+        for r in range(nprocs):
+            R.set_thick(r, synthetic_thickness(R.coords(r), nk, kind))   # the reference's own Geom::x of that rank
     rng = np.random.default_rng(seed)
     x = rng.uniform(-1, 1, R.N1)
     t_asm = t_mrg = t_mv = 0.0
     done = 0
     t0 = time.time()
-    for lev in range(nlev_sample):
-        a, m = R.assemble_only("Umat", lev=lev, scale=SCALE, flag=True)
+    for lev in range(min(nlev_sample, nk)):
+        a, m = R.assemble_only("Umat", lev=lev, scale=SCALE if variant != "src" else 1.0, flag=True)
         _, s = R.spmv(x, nthreads=cores)
         t_asm += a
         t_mrg += m
@@ -210,7 +229,8 @@ def cpu_reference_sample(workload, nlev_sample, budget_s, seed=0):
     total = t_asm + t_mv
     return {"value": dofs / total / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "reference",
             "sample": "%s: Umat::assemble + MatMult for %d of %d levels (reference sources via PETSc shim, %d emulated MPI ranks on %d "
-                      "threads; mesh %s); assemble %.2fs, SpMV %.3fs counted; shim CSR merge %.2fs not counted" % (workload, done, nk, nprocs, cores, how, t_asm, t_mv, t_mrg),
+                      "threads; mesh, coordinates and Jacobians from the reference's own scripts and Geom); assemble %.2fs, SpMV %.3fs counted; "
+                      "shim CSR merge %.2fs not counted" % (workload, done, nk, nprocs, cores, t_asm, t_mv, t_mrg),
             "matmult_only_gdofs": dofs / t_mv / 1e9,
             "matrix_free_twin_gdofs": (R.N1 / t_mf / 1e9) if t_mf else None}
 
@@ -221,7 +241,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     kind, p, ne, nk, variant = WORKLOADS[args.workload]
-    per_step_levels = 2
+    per_step_levels = min(2, nk)
     times = []
     res = None
     for it in range(args.warmup + args.steps):
@@ -235,15 +255,51 @@ def run_reference_arm(args):
         if time.time() - t0 > 60 and it >= args.warmup:
             break
     v = float(np.mean(times))
-    N1 = 12 * (p * ne) ** 2
+    N1 = (12 if kind == "sphere" else 2) * (p * ne) ** 2
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": len(times),
             "warmup": args.warmup, "ms_per_step": 1e3 * (N1 * per_step_levels / 1e9) / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s eul/ p=%d %dx%d elems/face %d levels, operator Umat (M1) apply; each step = assemble+MatMult "
-                                   "for %d levels" % (args.workload, p, ne, ne, nk, per_step_levels)},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s %s/ p=%d %dx%d elems/face %d levels, operator Umat (M1) apply; each step = assemble+MatMult "
+                                   "for %d levels" % (args.workload, variant, p, ne, ne, nk, per_step_levels)},
             "cpu_baseline": {"kind": res["kind"], "cores": res["cores"], "sample": res["sample"], "value": v, "unit": "GDOF/s"},
             "e2e": {"value": v, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+
+def parity_vs_one_gpu(eng, mesh, thick, op, x, coeff, y, kw, rank, world, local):
+    """N-GPU correctness at the size the numbers are quoted on: gather the owned rows of the input, the coefficient and
+    the N-GPU output; rank 0 applies the operator to the gathered input on ONE GPU and compares bit for bit."""
+    import torch
+    import torch.distributed as dist
+    import mimsem_b200 as mb
+    sin, sout, sc = eng.engine.SPACES[op]
+    nk = x.shape[1]
+    sizes = {0: mesh.N0, 1: mesh.N1, 2: mesh.N2}
+
+    def gather(field, space):
+        g = np.zeros((nk, sizes[space]))
+        eng.owned_to_global(field, space, g)
+        t = torch.from_numpy(g).to("cuda:%d" % local)
+        dist.all_reduce(t)          # every DOF has exactly one owner: a sum of one value and zeros
+        return t
+
+    xg = gather(x, sin)
+    cg = gather(coeff, sc) if coeff is not None else None
+    yg = gather(y, sout)
+    ok = True
+    if rank == 0:
+        single = mb.Engine.from_mesh(mesh, local, thick=thick)
+        y1 = single.to_levels(single.apply(op, single.to_columns(xg, sin), coeff=None if cg is None else single.to_columns(cg, sc), **kw), sout)
+        ok = bool(torch.equal(y1, yg))
+        single.close()
+        del single, y1
+    flag = torch.tensor([1 if ok else 0], device="cuda:%d" % local)
+    dist.broadcast(flag, 0)
+    del xg, cg, yg
+    torch.cuda.empty_cache()
+    return bool(flag.item())
 
 
 def main():
@@ -252,14 +308,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mimsem_b200")
-    ap.add_argument("--op", default="M1", choices=["M1", "M1h", "M2", "M0", "K", "E21", "E12"])
+    ap.add_argument("--op", default="M1", choices=OPS)
     ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
+    ap.add_argument("--chain", action="store_true", help="time the diagnose chain (4 x M1h + E21) under one CUDA graph instead of --op")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bitwise comparison with a single-GPU apply")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="engine tuning knob (mimsem_gpu_set_option), e.g. --opt m1_min_blocks=5; recorded in config")
-    ap.add_argument("--lockstep", action="store_true", help="N > 1: push and consume the ghost rows in the same launch (no pipelining over the ring)")
+    ap.add_argument("--pipelined", action="store_true",
+                    help="N > 1: time ONLY the software-pipelined ghost refresh (independent inputs) as the headline")
+    ap.add_argument("--lockstep", action="store_true", help="(default since round 2; kept for old command lines)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -280,8 +341,10 @@ def main():
     dev = "cuda:%d" % local
 
     kind, p, ne, nk, variant = WORKLOADS[args.workload]
-    mesh = mb.Mesh(kind, p, ne)
-    thick = synthetic_thickness(mesh.xyz, nk, kind)
+    flat = variant == "src"              # 2-D shallow water: no thickness, unit scale, signed det J
+    mesh = mb.Mesh(kind, p, ne, signed_det=flat)
+    thick = None if flat else synthetic_thickness(mesh.xyz, nk, kind)
+    scale = 1.0 if flat else SCALE
     if world > 1:
         from mimsem_b200.parallel import DistributedEngine
         eng = DistributedEngine(mesh, thick, rank, world, local)
@@ -290,22 +353,38 @@ def main():
     for kv in args.opt:
         name, val = kv.split("=")
         (eng if world == 1 else eng.engine).set_option(name, int(val))
-    op = args.op
+    op = "M1h" if args.chain else args.op
+    if world > 1 and (args.chain or op not in eng.SUPPORTED):
+        raise SystemExit("operator %s is not available on more than one GPU" % ("chain" if args.chain else op))
     nin, nout, ncoef = eng.space_sizes(op)
-    tpow = TPOW[op]
+    tpow = 0 if flat else TPOW[op]
+    need_u = op in ("R_up", "M0h_up")
+    n1_local = eng.space_sizes("M1")[0]
 
     # ring of distinct field sets: every step reads and writes buffers that were last touched
     # >= RING-1 steps ago; one field pair (0.42 GB on C5) already exceeds the 126 MB L2
     # (at N GPUs the per-rank slice shrinks, so the ring grows until it covers >= 4x the 126 MB L2)
     # computed from GLOBAL sizes: every rank must capture and replay the same number of steps (the ghost refresh is collective)
-    n_glob = {"M1": mesh.N1, "M1h": mesh.N1, "K": mesh.N1, "E21": mesh.N1, "M2": mesh.N2, "E12": mesh.N2, "M0": mesh.N0}[op]
-    RING = max(3, -(-4 * 126_000_000 // (16 * (n_glob // world) * nk)))
+    n_glob = max(mesh.N1 if op not in ("M2", "M0") else (mesh.N2 if op == "M2" else mesh.N0), 1)
+    RING = min(64, max(3, -(-4 * 126_000_000 // (16 * max(n_glob // world, 1) * nk))))
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     xs = [torch.rand((nin, nk), dtype=torch.float64, device=dev, generator=g) * 2 - 1 for _ in range(RING)]
     ys = [torch.empty((nout, nk), dtype=torch.float64, device=dev) for _ in range(RING)]
     cs = None
     if ncoef:
         cs = [torch.rand((ncoef, nk), dtype=torch.float64, device=dev, generator=g) + 0.5 for _ in range(RING)]
+    us = None
+    if need_u:
+        umag = float(np.abs(mesh.det).mean()) * 1e-3
+        us = [(torch.rand((n1_local, nk), dtype=torch.float64, device=dev, generator=g) * 2 - 1) * umag for _ in range(RING)]
+    chain_extra = None
+    if args.chain:
+        # the other three (coefficient, field) pairs of one diagnose step and the divergence of the first flux
+        n2 = eng.space_sizes("E21")[1]
+        chain_extra = [([torch.rand((nin, nk), dtype=torch.float64, device=dev, generator=g) for _ in range(3)],
+                        [torch.rand((ncoef, nk), dtype=torch.float64, device=dev, generator=g) + 0.5 for _ in range(3)],
+                        [torch.empty((nout, nk), dtype=torch.float64, device=dev) for _ in range(3)],
+                        torch.empty((n2, nk), dtype=torch.float64, device=dev)) for _ in range(RING)]
 
     def barrier():
         if world > 1:
@@ -313,80 +392,138 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def kw_of(j):
+        if op.startswith("E"):
+            return {}
+        kw = dict(scale=scale, tpow=tpow)
+        if need_u:
+            kw.update(u1=us[j], tau=UP_TAU)
+        return kw
+
+    def apply_slot(j, **extra):
+        eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], **kw_of(j), **extra)
+        if args.chain:
+            fx, fc, fy, dv = chain_extra[j]
+            for i in range(3):
+                eng.apply(op, fx[i], coeff=fc[i], out=fy[i], **kw_of(j))
+            eng.apply("E21", ys[j], out=dv)
+
     # kernels of this library per step (graph replays bypass the library's launch counter)
     l0 = eng.launch_count
-    eng.apply(op, xs[0], coeff=None if cs is None else cs[0], out=ys[0], scale=SCALE, tpow=tpow)
+    apply_slot(0)
     barrier()
     launches_per_step = eng.launch_count - l0
 
-    # N > 1, M1: the ghost refresh is software-pipelined over the ring of independent inputs -- the launch of step i
-    # pushes the boundary rows of step i+1's input and consumes what step i-1 pushed (one push + one apply per step,
-    # as without pipelining; only the dependency distance changes).  --lockstep pushes and consumes in the same launch.
-    pipelined = world > 1 and op == "M1" and not args.lockstep and getattr(eng, "p2p", None) is not None and eng.fused
-    nxt = (lambda j: {"x_next": xs[(j + 1) % RING]}) if pipelined else (lambda j: {})
-    if pipelined:
-        eng.prologue_push(xs[0])
+    # N > 1: the N-GPU result of this very configuration must equal the single-GPU result bit for bit
+    parity = None
+    if world > 1 and not args.no_parity:
+        ok = parity_vs_one_gpu(eng, mesh, thick, op, xs[0], None if cs is None else cs[0], ys[0], kw_of(0), rank, world, local)
+        parity = {"bitwise_vs_1gpu": ok, "what": "owned rows of step 0's output on %d GPUs vs a one-GPU apply of the gathered input (rank 0), %s %s"
+                                                 % (world, args.workload, op)}
+        if not ok:
+            raise SystemExit("rank %d: the %d-GPU output differs from the single-GPU output -- refusing to print a number" % (rank, world))
+
+    fused = world > 1 and op == "M1" and getattr(eng, "p2p", None) is not None and eng.fused
+
+    def measure(pipelined):
+        """W warm-up + K timed steps (CUDA-graph replays of the captured step, one graph per ring slot)."""
+        nxt = (lambda j: {"x_next": xs[(j + 1) % RING]}) if pipelined else (lambda j: {})
+        if pipelined:
+            eng.prologue_push(xs[0])
+            barrier()
+        replays = None
+        if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
+            try:
+                # (each capture warms up with real applies of its slot; after the last slot a pipelined sequence
+                #  holds the boundary rows of xs[0], the input of the first step)
+                if world == 1:
+                    replays = []
+                    for j in range(RING):
+                        apply_slot(j)
+                        torch.cuda.synchronize()
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr):
+                            apply_slot(j)
+                        replays.append(gr.replay)
+                else:
+                    replays = [eng.capture(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], **kw_of(j), **nxt(j))[0]
+                               for j in range(RING)]
+            except Exception as exc:  # fall back to eager launches
+                if rank == 0:
+                    print("graph capture failed (%r); timing eager launches" % (exc,), file=sys.stderr)
+                replays = None
+
+        def step(i):
+            j = i % RING
+            if replays is not None:
+                replays[j]()
+            else:
+                apply_slot(j, **nxt(j))
+
         barrier()
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        l_before = eng.launch_count
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record()
+        barrier()
+        total_ms = ev[0].elapsed_time(ev[-1])
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+        launches = launches_per_step * args.steps if replays is not None else eng.launch_count - l_before
+        # sustained leg: the same step replayed back to back for about 1 s (clocks settle, power rises); the count is
+        # a multiple of the ring so that a pipelined sequence ends where it began
+        sustained_ms = None
+        if not args.no_sustained:
+            n_sus = int(max(args.steps, min(100000, 1.0e3 / max(total_ms / args.steps, 1e-3))))
+            n_sus = -(-n_sus // RING) * RING
+            first = args.warmup + args.steps
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for i in range(n_sus):
+                step(first + i)
+            e1.record()
+            barrier()
+            sustained_ms = (e0.elapsed_time(e1) / n_sus, n_sus)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([total_ms, sustained_ms[0] if sustained_ms else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t[0])
+            if sustained_ms:
+                sustained_ms = (float(t[1]), sustained_ms[1])
+        return total_ms / args.steps, float(np.mean(per)), launches, sustained_ms, replays is not None
 
-    # the step (ghost refresh + kernels) is captured once per ring slot into a CUDA graph and replayed:
-    # at 4-8 GPUs a step is tens of microseconds, i.e. launch-bound without graphs
-    replays = None
-    if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
-        try:
-            # (each capture warms up with two real applies of its slot; after the last slot the pipeline holds the
-            #  boundary rows of xs[0], the input of the first step)
-            replays = [eng.capture(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow, **nxt(j))[0]
-                       for j in range(RING)]
-        except Exception as exc:  # fall back to eager launches
-            if rank == 0:
-                print("graph capture failed (%r); timing eager launches" % (exc,), file=sys.stderr)
-            replays = None
-
-    def step(i):
-        j = i % RING
-        if replays is not None:
-            replays[j]()
-        else:
-            eng.apply(op, xs[j], coeff=None if cs is None else cs[j], out=ys[j], scale=SCALE, tpow=tpow, **nxt(j))
-
-    barrier()
-    for i in range(args.warmup):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = eng.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-        ev[i + 1].record()
-    barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    launches = eng.launch_count - launches0
-    if replays is not None:
-        launches = launches_per_step * args.steps
+    headline_pipelined = bool(args.pipelined and fused)
+    ms_per_step, kern_ms, launches, sustained, graphed = measure(headline_pipelined)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t[0])
-    ms_per_step = total_ms / args.steps
+    second = None
+    if fused and not headline_pipelined:
+        barrier()
+        second = measure(True)[0]
 
     q2 = (p + 1) ** 2
-    alg_bytes, out_dofs = algorithmic_bytes(op, mesh.nel, q2, mesh.N0, mesh.N1, mesh.N2, mesh.NQ, nk)
+    if args.chain:
+        a1, d1 = algorithmic_bytes("M1h", mesh.nel, q2, mesh.N0, mesh.N1, mesh.N2, mesh.NQ, nk, thickness=not flat)
+        a2, d2 = algorithmic_bytes("E21", mesh.nel, q2, mesh.N0, mesh.N1, mesh.N2, mesh.NQ, nk, thickness=not flat)
+        alg_bytes, out_dofs = 4 * a1 + a2, 4 * d1 + d2
+    else:
+        alg_bytes, out_dofs = algorithmic_bytes(op, mesh.nel, q2, mesh.N0, mesh.N1, mesh.N2, mesh.NQ, nk, thickness=not flat)
     value = out_dofs / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    kern_ms = float(np.mean(per_launch_ms))
     achieved = (alg_bytes / world) / (kern_ms * 1e-3) / 1e9
 
     # end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.chain and not need_u:
         # N > 1: every rank passes its ghosted local vector (the reference's VecCreateSeq(topo->n1) convention), so the
         # host call needs no exchange; the aggregate is all ranks' owned output DOFs over the slowest rank's time
         heng = eng if world == 1 else eng.engine
@@ -398,18 +535,19 @@ def main():
             hc = torch.empty((nk, ncoef), dtype=torch.float64).pin_memory()
             hc.uniform_(0.5, 1.5)
         n_e2e = max(3, min(args.steps, 10))
+        hkw = {} if op.startswith("E") else dict(scale=scale, tpow=tpow)
         for _ in range(2):
-            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
+            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), out=hy.numpy(), **hkw)
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), scale=SCALE, tpow=tpow, out=hy.numpy())
+            heng.apply_host(op, hx.numpy(), coeff=None if hc is None else hc.numpy(), out=hy.numpy(), **hkw)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n_e2e
         h2d, d2h = 8 * nk * (nin + ncoef), 8 * nk * nout
         if world > 1:
             import torch.distributed as dist
-            tt = torch.tensor([dt, -float(h2d), -float(d2h)], dtype=torch.float64, device=dev)
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt[0])
             tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
@@ -430,21 +568,37 @@ def main():
     if world > 1 and eng.halo_error():
         raise SystemExit("rank %d: a peer-to-peer ghost refresh timed out (ranks out of step?) -- the measurement is void" % rank)
     if rank == 0:
+        what = "diagnose chain: 4 x M1h (Uhmat) + E21 under one CUDA graph" if args.chain else "operator %s over all levels in one launch" % op
+        traffic, traffic_src = ncu_traffic(args.workload, "chain" if args.chain else op) if world == 1 else (None, None)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / world, "kernel_ms": kern_ms}
+        if sustained:
+            roof["sustained_frac"] = (alg_bytes / world) / (sustained[0] * 1e-3) / 1e9 / peak
+            roof["sustained_ms"] = sustained[0]
+            roof["sustained_steps"] = sustained[1]
+        mode = "none (1 GPU)"
+        if world > 1:
+            if fused:
+                mode = "fused into the M1 launch over NVLink peer memory; " + (
+                    "push of step i+1's input overlapped with step i (ring of independent inputs)" if headline_pipelined
+                    else "lockstep: push and consume in the same launch (dependent applies)")
+            else:
+                mode = "push / pull kernels over NVLink peer memory on a side stream"
         line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; operator %s over all levels in one launch "
-                                       "(Nel=%d, out DOF-levels=%d)" % (args.workload, variant, p, ne, ne, nk, op, mesh.nel, out_dofs),
-                           "cache": "ring of %d distinct field sets per GPU (%.0f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
-                           "parallelism": "element-block x%d" % world, "cuda_graph": replays is not None, "options": args.opt,
-                           "ghost_refresh": ("none (1 GPU)" if world == 1 else
-                                             ("fused into the M1 launch over NVLink peer memory; push of step i+1's input overlapped with step i (ring of independent inputs)"
-                                              if pipelined else "fused into the M1 launch over NVLink peer memory; push and consume in the same launch"))},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": (ncu_traffic(args.workload, op) if world == 1 else None), "traffic_source": "ncu --set full capture, profiles/r01_traffic.json",
-                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
-                             "kernel_ms": kern_ms},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; %s (Nel=%d, out DOF-levels=%d)"
+                                       % (args.workload, variant, p, ne, ne, nk, what, mesh.nel, out_dofs),
+                           "cache": "ring of %d distinct field sets per GPU (%.1f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
+                           "parallelism": "element-block x%d" % world, "cuda_graph": graphed, "options": args.opt,
+                           "ghost_refresh": mode},
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if parity is not None:
+            line["parity_check"] = parity
+        if second is not None:
+            line["pipelined"] = {"value": out_dofs / (second * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": second,
+                                 "note": "ghost rows of step i+1's INDEPENDENT input pushed during step i; not the headline"}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
