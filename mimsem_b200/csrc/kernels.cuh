@@ -963,7 +963,8 @@ __global__ void __launch_bounds__(128) k_apply_m0(const __grid_constant__ NodeAr
             d += a.wq[q] * hl;
         }
     }
-    a.y[(size_t)n * ld + k] = f * d * ldro(a.x + (size_t)n * ld + k);
+    // x == nullptr: the diagonal itself (Pvec::assemble, Phvec::assemble, eul/Assembly.cpp:602-628, 652-681)
+    a.y[(size_t)n * ld + k] = f * d * (a.x ? ldro(a.x + (size_t)n * ld + k) : 1.0);
 }
 
 // x = M0^-1 b: M0 is diagonal when the quadrature order equals the element order (KSPSolve(ksp0, ...) of
@@ -1105,6 +1106,39 @@ __global__ void __launch_bounds__(256) k_rows(int64_t nrows, int nlev, int ld, u
     const unsigned k = idx - i * (unsigned)nlev;
     if (GATHER) dst[idx] = src[(size_t)rows[i] * ld + k];
     else dst[(size_t)rows[i] * ld + k] = src[idx];
+}
+
+// L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): 2-form fields between the engine's column layout
+// cols[el2[e][i]*ld + k] and the reference's per-element vertical vectors vert[e][k*p2 + i] (vz[ei] of size nk*p2, all
+// elements back to back).  A pure relabelling -- bit exact -- through a padded shared-memory tile, one CTA per element,
+// so that both sides are accessed in runs.
+template <bool TO_VERT>
+__global__ void __launch_bounds__(256) k_l2vecs(int p2, int nlev, int ld, const int* __restrict__ el2, const double* __restrict__ in,
+                                                double* __restrict__ out) {
+    extern __shared__ double l2tile[];   // [nlev][p2 + 1]
+    const int e = blockIdx.x, n = p2 * nlev, pad = p2 + 1;
+    const int* __restrict__ rows = el2 + (size_t)e * p2;
+    if (TO_VERT) {
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int i = idx / nlev, k = idx - i * nlev;
+            l2tile[k * pad + i] = in[(size_t)rows[i] * ld + k];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int k = idx / p2, i = idx - k * p2;
+            out[(size_t)e * n + idx] = l2tile[k * pad + i];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int k = idx / p2, i = idx - k * p2;
+            l2tile[k * pad + i] = in[(size_t)e * n + idx];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+            const int i = idx / nlev, k = idx - i * nlev;
+            out[(size_t)rows[i] * ld + k] = l2tile[k * pad + i];
+        }
+    }
 }
 
 // levels[k*n + dof] <-> columns[perm[dof]*ld + k] through a padded shared-memory tile
