@@ -215,6 +215,33 @@ int mimsem_gpu_solve_M0(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double 
 int mimsem_gpu_diag_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                        double* d_diag, void* stream);
 
+/*
+ * Remaining coefficient operators of the vorticity / forcing terms:
+ *   Pvec::assemble(lev, scale)            -> diag_M0 (d_h2 = NULL, tpow = 1): M0 is diagonal when m == p, so the lumped
+ *                                            0-form mass "vector" IS its diagonal            eul/Assembly.cpp:602-628
+ *   Phvec::assemble(hl, lev, scale)       -> diag_M0 (d_h2 = hl, tpow = 2)                   eul/Assembly.cpp:652-681
+ *   WmatInv::assemble(lev, scale)         -> solve_M2 (d_h2 = NULL, tpow = 1): the 2-form mass matrix is block diagonal,
+ *   WhmatInv::assemble(rho, lev, scale)      one p^2 x p^2 SPD block per element; the reference inverts each block
+ *                                            (Gauss-Jordan) and MatMults, here every block is tabulated, Cholesky-factorised
+ *                                            and solved in shared memory                     eul/Assembly.cpp:1658-1800
+ *   UtQWmat::assemble(u1, scale)          -> apply_UtQW: 2-form -> 1-form; equals Uhmat(h2 := x2) applied to u1 without
+ *                                            thickness factors (and WtQdUdz_mat^T)           eul/Assembly.cpp:1462-1538
+ */
+int mimsem_gpu_diag_M0(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_h2,
+                       double* d_diag, void* stream);
+int mimsem_gpu_solve_M2(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_h2,
+                        const double* d_b, double* d_x, void* stream);
+int mimsem_gpu_apply_UtQW(mimsem_gpu_ctx* ctx, int nlev, int ld, double scale, const double* d_u1, const double* d_x2, double* d_y1,
+                          void* stream);
+
+/*
+ * L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101) for device-resident 2-form fields: between the engine's
+ * column layout cols[face*ld + k] and the reference's per-element vertical vectors, all owned elements back to back,
+ * vert[e*(nlev*p^2) + k*p^2 + i]  (== vz[e] of size nk*p^2, face = Topo::elInds2_l(e)[i]).  A relabelling: bit exact.
+ */
+int mimsem_gpu_columns_to_vertical(mimsem_gpu_ctx* ctx, int nlev, int ld, const double* d_cols, double* d_vert, void* stream);
+int mimsem_gpu_vertical_to_columns(mimsem_gpu_ctx* ctx, int nlev, int ld, const double* d_vert, double* d_cols, void* stream);
+
 /* Incidence operators (exact +-1 stencils), E10mat/E21mat of eul/Assembly.cpp:1102-1226:
  * which = 0 E10 (0-form -> 1-form), 1 E01 = -E10^T, 2 E21 (1-form -> 2-form), 3 E12 = -E21^T. */
 #define MIMSEM_E10 0

@@ -109,7 +109,7 @@ struct mimsem_gpu_ctx {
     DevBuf<TileHdr> d_recs_k;           // K (WtQUmat) tile records
     int rec_stride_k = 0;
     bool k_plan_ok = false;
-    DevBuf<double> d_geo, d_geo_h;
+    DevBuf<double> d_geo, d_geo_h, d_geo_k;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
     DevBuf<double> d_tmean;   // [nq][nkT]: mean thickness of levels k and k+1 (Ut_mat::assemble), selected by MIMSEM_THICK_MEAN
@@ -599,7 +599,8 @@ int build_k_plan_p(mimsem_gpu_ctx* c) {
     return MIMSEM_OK;
 }
 
-// geometry records of the tile kernels: G[q][3], then the (c_own, c_oth) pairs of the west and south far lines
+// geometry records of the M1 tile kernel: gl[part][line][q] = (g_own, g_oth) of the element's own lines, then the
+// (g_own, g_oth) pairs of the west and south far lines (M1Slots)
 template <int P>
 int build_tma_geo_p(mimsem_gpu_ctx* c, const std::vector<double>& G, DevBuf<double>& out) {
     using S = M1Slots<P>;
@@ -607,7 +608,18 @@ int build_tma_geo_p(mimsem_gpu_ctx* c, const std::vector<double>& G, DevBuf<doub
     std::vector<double> geo((size_t)c->nel_owned * S::GEO, 0.0);
     for (int e = 0; e < c->nel_owned; e++) {
         double* g = &geo[(size_t)e * S::GEO];
-        for (int i = 0; i < Q2 * 3; i++) g[i] = G[(size_t)e * Q2 * 3 + i];
+        const double* Ge = &G[(size_t)e * Q2 * 3];
+        for (int ln = 0; ln < P; ln++)
+            for (int q = 0; q <= P; q++) {
+                // part 0: x-line ln = GLL column qx = ln, points qy = q: f0 = c (Gaa ul0 + Gab ul1)
+                const int q0 = q * NP1 + ln;
+                g[S::GL + (ln * NP1 + q) * 2 + 0] = Ge[q0 * 3 + 0];
+                g[S::GL + (ln * NP1 + q) * 2 + 1] = Ge[q0 * 3 + 1];
+                // part 1: y-line ln = GLL row qy = ln, points qx = q: f1 = c (Gbb ul1 + Gab ul0)
+                const int q1 = ln * NP1 + q;
+                g[S::GL + P * NP1 * 2 + (ln * NP1 + q) * 2 + 0] = Ge[q1 * 3 + 2];
+                g[S::GL + P * NP1 * 2 + (ln * NP1 + q) * 2 + 1] = Ge[q1 * 3 + 1];
+            }
         for (int s = 0; s < 2; s++) {
             const int nb = c->h_nbr[(size_t)e * 2 + s];
             if (nb < 0) continue;
@@ -621,6 +633,16 @@ int build_tma_geo_p(mimsem_gpu_ctx* c, const std::vector<double>& G, DevBuf<doub
             }
         }
     }
+    CUDA_OK(out.upload(geo));
+    return MIMSEM_OK;
+}
+
+// geometry records of the K tile kernel: G[q][3] of the element, padded to an even number of doubles
+int build_k_geo(mimsem_gpu_ctx* c, const std::vector<double>& G, DevBuf<double>& out) {
+    const int Q2 = (c->p + 1) * (c->p + 1), GK = (Q2 * 3 + 1) / 2 * 2;
+    std::vector<double> geo((size_t)c->nel_owned * GK, 0.0);
+    for (int e = 0; e < c->nel_owned; e++)
+        for (int i = 0; i < Q2 * 3; i++) geo[(size_t)e * GK + i] = G[(size_t)e * Q2 * 3 + i];
     CUDA_OK(out.upload(geo));
     return MIMSEM_OK;
 }
@@ -830,7 +852,7 @@ int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpo
         t.recs = c->d_recs_k.p;
         t.rec_stride = c->rec_stride_k;
         t.rec_hdr = 1;
-        t.geo = c->d_geo_h.p;
+        t.geo = c->d_geo_k.p;
         t.x = x; t.c = u1; t.tinv = a.tinv; t.y = y;
         copy_basis(c, t);
         std::string err;
@@ -872,7 +894,7 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         a.div_m = fd.m;
         a.div_s = fd.s;
     }
-    const bool vec2 = !with_h && nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+    const bool vec2 = x && !with_h && nlev % 2 == 0 && ld % 2 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
                       (tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0));
     if (vec2) {
         a.nlev = nlev / 2;
@@ -1110,6 +1132,40 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     }
     k_apply_ell<1><<<grid_for(a.nrows * nlev, 256), 256, 0, st>>>(a);
     return finish_launch(c, "apply_incidence");
+}
+
+// x = M2^-1 b (WITH_H: M2(rho)^-1 b), element-local dense solves
+int solve_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+             const double* b, double* x, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!b || !x || (with_h && !h2)) return fail(MIMSEM_ERR_ARG, "null field");
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = with_h ? c->d_W2h.p : c->d_W2.p;
+    a.c = h2;
+    a.x = b;
+    a.y = x;
+    if ((int64_t)a.nel * nlev == 0) return MIMSEM_OK;
+    std::string err;
+    if (launch_solve_m2(c->p, with_h, a, st, &err) < 0) return fail(MIMSEM_ERR_CUDA, err);
+    return finish_launch(c, "solve_M2");
+}
+
+// L2Vecs::HorizToVert / VertToHoriz on device-resident 2-form fields
+int l2vecs(mimsem_gpu_ctx* c, bool to_vert, int nlev, int ld, const double* in, double* out, cudaStream_t st) {
+    if (!c || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
+    if (!in || !out) return fail(MIMSEM_ERR_ARG, "null field");
+    if (nlev < 1 || ld < nlev) return fail(MIMSEM_ERR_ARG, "bad level count / leading dimension");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const int p2 = c->p * c->p;
+    const size_t smem = (size_t)nlev * (p2 + 1) * sizeof(double);
+    if (smem > 48 * 1024) return fail(MIMSEM_ERR_UNSUPPORTED, "L2Vecs relabelling: more than 48 KB per element column");
+    if (to_vert) k_l2vecs<true><<<c->nel_owned, 256, smem, st>>>(p2, nlev, ld, c->d_el2.p, in, out);
+    else k_l2vecs<false><<<c->nel_owned, 256, smem, st>>>(p2, nlev, ld, c->d_el2.p, in, out);
+    return finish_launch(c, "L2Vecs relabel");
 }
 
 int transpose(mimsem_gpu_ctx* c, bool to_columns, int space, int64_t n, int nlev, int ld, const double* in, double* out,
@@ -1445,6 +1501,7 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
             case 5: rc = build_tma_geo_p<5>(c, G1, c->d_geo); if (!rc) rc = build_tma_geo_p<5>(c, G1h, c->d_geo_h); break;
         }
         if (rc) return rc;
+        if ((rc = build_k_geo(c, G1h, c->d_geo_k))) return rc;
     }
     CUDA_OK(c->d_G1.upload(G1));
     CUDA_OK(c->d_G1h.upload(G1h));
@@ -1605,6 +1662,26 @@ int mimsem_gpu_solve_M0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sc
 }
 int mimsem_gpu_diag_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, double* d, void* st) {
     return diag_m1(c, false, lev0, nlev, ld, scale, tpow, flags, d, (cudaStream_t)st);
+}
+int mimsem_gpu_diag_M0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2, double* d,
+                       void* st) {
+    if (!d) return fail(MIMSEM_ERR_ARG, "null output");
+    return apply_m0(c, h2 != nullptr, lev0, nlev, ld, scale, tpow, flags, h2, nullptr, d, (cudaStream_t)st);
+}
+int mimsem_gpu_solve_M2(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
+                        const double* b, double* x, void* st) {
+    return solve_m2(c, h2 != nullptr, lev0, nlev, ld, scale, tpow, flags, h2, b, x, (cudaStream_t)st);
+}
+int mimsem_gpu_apply_UtQW(mimsem_gpu_ctx* c, int nlev, int ld, double scale, const double* u1, const double* x2, double* y1, void* st) {
+    // UtQWmat(u1) x2 == Uhmat(h2 := x2) u1 without thickness factors: the form is bilinear in (2-form, 1-form)
+    if (!u1 || !x2) return fail(MIMSEM_ERR_ARG, "null field");
+    return apply_m1(c, true, 0, nlev, ld, scale, 0, 0, x2, u1, y1, (cudaStream_t)st);
+}
+int mimsem_gpu_columns_to_vertical(mimsem_gpu_ctx* c, int nlev, int ld, const double* cols, double* vert, void* st) {
+    return l2vecs(c, true, nlev, ld, cols, vert, (cudaStream_t)st);
+}
+int mimsem_gpu_vertical_to_columns(mimsem_gpu_ctx* c, int nlev, int ld, const double* vert, double* cols, void* st) {
+    return l2vecs(c, false, nlev, ld, vert, cols, (cudaStream_t)st);
 }
 int mimsem_gpu_apply_incidence(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, double* y, void* st) {
     return apply_inc(c, which, nlev, ld, x, y, (cudaStream_t)st);

@@ -162,10 +162,15 @@ struct M1Slots {
     static constexpr int NS = T + (P + 1) * (P + 1);
     static constexpr int H = NS;
     static constexpr int NS_H = H + P * P;
-    // geometry record (doubles): G[q][3], then (c_own, c_oth)[q] for the west and the south far line
-    static constexpr int GW = (P + 1) * (P + 1) * 3;
+    // geometry record (doubles): per part (x-lines, y-lines) gl[part][line][q] = (g_own, g_oth), then (g_own, g_oth)[q] of
+    // the west and the south far line.  (The K tile kernel shares the record type but reads G[q][3] at offset 0: its
+    // records are built separately, see build_tile_geo.)
+    static constexpr int GL = 0;
+    static constexpr int GW = 2 * P * (P + 1) * 2;
     static constexpr int GS = GW + 2 * (P + 1);
     static constexpr int GEO = ((GS + 2 * (P + 1)) + 1) / 2 * 2;
+    // K tile: plain G[q][3]
+    static constexpr int GEO_K = (((P + 1) * (P + 1) * 3) + 1) / 2 * 2;
 };
 
 // Slot map of the K (WtQUmat) tile: the element's x edges as in M1Slots, the same block again for the velocity

@@ -8,8 +8,8 @@ int launch_k_tile(int p, TArgs& t, int nel, cudaStream_t st, std::string* err) {
     int rc = 1;
     for_p(p, [&](auto Pc) {
         constexpr int P = decltype(Pc)::value;
-        t.geo_doubles = M1Slots<P>::GEO;
-        const size_t smem = 16 + ((size_t)M1Slots<P>::GEO + (size_t)KSlots<P>::NS * t.nlev) * sizeof(double);
+        t.geo_doubles = M1Slots<P>::GEO_K;
+        const size_t smem = 16 + ((size_t)M1Slots<P>::GEO_K + (size_t)KSlots<P>::NS * t.nlev) * sizeof(double);
         if (smem > 227 * 1024) return;
         void (*kern)(const TArgs) = nullptr;
         if ((P == 3 || P == 4) && t.nlev == 60) kern = k_apply_k_tma<P, 60>;

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128, (P <= 4 ? 4 : 2)) k_apply_k_tma(const __g
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
     double* geo = reinterpret_cast<double*>(smem_raw + 16);
-    double* tile = geo + M1Slots<P>::GEO;
+    double* tile = geo + M1Slots<P>::GEO_K;
     const int part = threadIdx.x >> 6;
     const int k = threadIdx.x & 63;
     const int nl = NL ? NL : a.nlev;

@@ -27,6 +27,7 @@ void launch_m1_regs(int p, bool with_h, const KArgs& a, unsigned grid, cudaStrea
 void launch_m1_lines(int p, bool with_h, bool far, const KArgs& a, dim3 grid, cudaStream_t st);
 void launch_diag_m1(int p, bool invert, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m2(int p, bool with_h, const KArgs& a, unsigned grid, cudaStream_t st);
+int launch_solve_m2(int p, bool with_h, const KArgs& a, cudaStream_t st, std::string* err);
 void launch_k_regs(int p, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_rot(int p, bool up, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m0h_up(int p, const NodeArgs& a, unsigned grid, cudaStream_t st);

@@ -31,7 +31,12 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         if (smem > 227 * 1024) return;
         void (*kern)(const TArgs) = nullptr;
         if (l.halo) kern = pick_nl<P, false, true, default_minb<P, false>()>(t.nlev);
-        else if (l.with_h) kern = pick_nl<P, true, false, default_minb<P, true>()>(t.nlev);
+        else if (l.with_h) {
+            kern = pick_nl<P, true, false, default_minb<P, true>()>(t.nlev);
+            if constexpr (P == 4) {
+                if (l.min_blocks == 5) kern = pick_nl<P, true, false, 5>(t.nlev);
+            }
+        }
         else {
             kern = pick_nl<P, false, false, default_minb<P, false>()>(t.nlev);
             if constexpr (P == 4) {   // register-budget variants kept for tuning runs (mimsem_gpu_set_option "m1_min_blocks")

@@ -116,30 +116,33 @@ __device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, in
 #pragma unroll
     for (int j = 0; j < P; j++) hs[j] = 0.0;
     if (!(flags & has)) return;
-    double oth[P + 1][P];
+    // rows of oth(q,t): two runs (the neighbour's own block, then the far row / column owned by ITS neighbour), or an
+    // explicit list (ghost rows of a fused launch live in the inbox: entries < 0; generic numberings)
+    constexpr int NF = (P + 1) * P;
+    int rows[NF];
     if (flags & (side ? TF_LIST_S : TF_LIST_W)) {
-        // explicit rows (ghost rows of a fused launch live in the inbox; generic numberings)
-        const int* list = reinterpret_cast<const int*>(rec + a.rec_list) + side * (P + 1) * P;
+        const int* list = reinterpret_cast<const int*>(rec + a.rec_list) + side * NF;
 #pragma unroll
-        for (int q = 0; q <= P; q++)
-#pragma unroll
-            for (int t = 0; t < P; t++) {
-                const int r = list[q * P + t];
-                if (HALO && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
-                else oth[q][t] = a.x[(size_t)r * a.ld + k];
-            }
+        for (int i = 0; i < NF; i++) rows[i] = list[i];
     } else {
         const TileFar fr = *reinterpret_cast<const TileFar*>(rec + 1);
-        const double* b16 = a.x + (size_t)(side ? fr.s16 : fr.w16) * a.ld + k;
-        const double* b4 = a.x + (size_t)(side ? fr.s4 : fr.w4) * a.ld + k;
-        const long long st4 = (flags & (side ? TF_S4_DESC : TF_W4_DESC)) ? -(long long)a.ld : (long long)a.ld;
+        const int r16 = side ? fr.s16 : fr.w16, r4 = side ? fr.s4 : fr.w4;
+        const int st4 = (flags & (side ? TF_S4_DESC : TF_W4_DESC)) ? -1 : 1;
 #pragma unroll
-        for (int q = 0; q < P; q++)
+        for (int i = 0; i < P * P; i++) rows[i] = r16 + i;
 #pragma unroll
-            for (int t = 0; t < P; t++) oth[q][t] = b16[(size_t)(q * P + t) * a.ld];
-#pragma unroll
-        for (int t = 0; t < P; t++) oth[P][t] = b4[t * st4];
+        for (int t = 0; t < P; t++) rows[P * P + t] = r4 + t * st4;
     }
+    double oth[P + 1][P];
+    const double* xk = a.x + k;
+#pragma unroll
+    for (int q = 0; q <= P; q++)
+#pragma unroll
+        for (int t = 0; t < P; t++) {
+            const int r = rows[q * P + t];
+            if (HALO && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+            else oth[q][t] = xk[(size_t)r * a.ld];
+        }
     double hv[WITH_H ? P : 1][WITH_H ? P : 1];
     if (WITH_H) {
         const TileFarH fh = *reinterpret_cast<const TileFarH*>(rec + 2);
@@ -226,35 +229,47 @@ __device__ __forceinline__ void far_line(const TArgs& a, const double* col, cons
     for (int j = 0; j < P; j++) cfar[j] = rev ? s[P - 1 - j] : s[j];
 }
 
-// One warp-pair's share of an element tile: DIR 0 = the x-normal edges of GLL columns 0..P-1, DIR 1 = the y-normal edges
-// of GLL rows 0..P-1; line 0 additionally receives the neighbour's far-line contribution cfar.  Each line is stored as
-// soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
-template <int P, bool WITH_H, int NL, int DIR>
-__device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, const double (&cfar)[P], double* __restrict__ y) {
+// One warp-pair's share of an element tile: part 0 = the x-normal edges of GLL columns 0..P-1, part 1 = the y-normal
+// edges of GLL rows 0..P-1; line 0 additionally receives the neighbour's far-line contribution cfar.  ONE code path
+// serves both directions -- `part` only selects base pointers and two shared-memory strides -- so that all four warps
+// of a tile run the same instructions (the unrolled contraction of one direction is ~12 KB of SASS; two copies did
+// not fit the 32 KB instruction cache and 14 % of the warp samples were waiting for instructions).  The geometry
+// record is laid out per part for this, gl[part][line][q] = (g_own, g_oth):
+//   part 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; part 1: f1 = c (Gbb ul1 + Gab ul0), ul1 = ua.
+// Each line is stored as soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
+template <int P, bool WITH_H, int NL>
+__device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, int part, const double (&cfar)[P],
+                                           double* __restrict__ y) {
     using S = M1Slots<P>;
     constexpr int NP1 = P + 1;
     const int nl = NL ? NL : a.nlev;
-#define SLOT(s) col[(size_t)(s) * nl]
-    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (DIR 0) / xx(qx=q, iy=t) (DIR 1): used P times each, kept in registers
+    const double* ownp = col + (size_t)(part ? S::OY : S::OX) * nl;      // edges ON line ln: ownp[(ln P + j) nl]
+    const double* oth16 = col + (size_t)(part ? S::OX : S::OY) * nl;     // the other family: oth(q < P, t) = oth16[(q P + t) nl]
+    const double* oth4 = col + (size_t)(part ? S::XE : S::YN) * nl;      //                   oth(P, t)     = oth4[t nl]
+    const double* tp = col + (size_t)S::T * nl;                          // thickness at point (line ln, q): tp[q sq + ln sl]
+    const int sq = (part ? 1 : NP1) * nl, sl = (part ? NP1 : 1) * nl;
+    const double* gl = geo + S::GL + part * (P * NP1 * 2);
+    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (part 0) / xx(qx=q, iy=t) (part 1): used P times each, kept in registers
     double othr[P + 1][P];
 #pragma unroll
     for (int q = 0; q <= P; q++)
 #pragma unroll
-        for (int t = 0; t < P; t++)
-            othr[q][t] = (DIR == 0) ? (q < P ? SLOT(S::OY + q * P + t) : SLOT(S::YN + t)) : (q < P ? SLOT(S::OX + q * P + t) : SLOT(S::XE + t));
+        for (int t = 0; t < P; t++) othr[q][t] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
 #pragma unroll
     for (int ln = 0; ln < P; ln++) {
-        // edges ON the line: xx(ln, iy) (DIR 0) / xy(ix, ln) (DIR 1)
         double own[P];
 #pragma unroll
-        for (int j = 0; j < P; j++) own[j] = SLOT((DIR == 0 ? S::OX : S::OY) + ln * P + j);
+        for (int j = 0; j < P; j++) own[j] = ownp[(size_t)(ln * P + j) * nl];
         double hc[WITH_H ? P : 1];   // h contracted across the line direction
         if (WITH_H) {
+            // h(ix = t, iy = j) for part 0, h(ix = j, iy = t) for part 1: slot H + j sj + t st
+            const double* hp = col + (size_t)S::H * nl;
+            const int sj = (part ? 1 : P) * nl, st = (part ? P : 1) * nl;
 #pragma unroll
             for (int j = 0; j < P; j++) {
                 double s = 0.0;
 #pragma unroll
-                for (int t = 0; t < P; t++) s += a.E[ln * P + t] * ((DIR == 0) ? SLOT(S::H + j * P + t) : SLOT(S::H + t * P + j));   // h(ix=t,iy=j) / h(ix=j,iy=t)
+                for (int t = 0; t < P; t++) s += a.E[ln * P + t] * hp[j * sj + t * st];
                 hc[WITH_H ? j : 0] = s;
             }
         }
@@ -266,10 +281,9 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
             for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
 #pragma unroll
             for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * othr[q][t];
-            const int qq = (DIR == 0) ? q * NP1 + ln : ln * NP1 + q;
             double c = a.scale;
             if (a.tpow > 0) {
-                const double t = SLOT(S::T + qq);
+                const double t = tp[q * sq + ln * sl];
                 c *= t;
                 if (a.tpow > 1) c *= t;
             }
@@ -279,8 +293,7 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
                 for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hc[WITH_H ? j : 0];
                 c *= hl;
             }
-            // DIR 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; DIR 1: f1 = c (Gab ul0 + Gbb ul1), ul1 = ua
-            f[q] = (DIR == 0) ? c * (geo[qq * 3 + 0] * ua + geo[qq * 3 + 1] * ub) : c * (geo[qq * 3 + 1] * ub + geo[qq * 3 + 2] * ua);
+            f[q] = c * (gl[(ln * NP1 + q) * 2 + 0] * ua + gl[(ln * NP1 + q) * 2 + 1] * ub);
         }
 #pragma unroll
         for (int j = 0; j < P; j++) {
@@ -290,7 +303,6 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
             y[(size_t)(ln * P + j) * a.ld] = s;
         }
     }
-#undef SLOT
 }
 
 // y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 warp-pairs (x-normal / y-normal edges) x 64 level
@@ -362,8 +374,7 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
             const double* col = tile + k;
             double cfar[P];
             far_line<P, WITH_H, NL>(a, col, geo, hd.flags, part, ubf, hs, cfar);
-            if (part == 0) tile_lines<P, WITH_H, NL, 0>(a, col, geo, cfar, a.y + (size_t)(hd.st_dof + S::OX) * a.ld + k);
-            else tile_lines<P, WITH_H, NL, 1>(a, col, geo, cfar, a.y + (size_t)(hd.st_dof + S::OY) * a.ld + k);
+            tile_lines<P, WITH_H, NL>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
         }
         DBG_T(3);
         if (tile_i + tile_stride < a.ntiles) __syncthreads();   // the next tile's bulk loads overwrite the buffer

@@ -70,24 +70,30 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* i
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = (ci == lane) ? first : ents[ci];
         if (c.kind == 2 && !with_t) continue;
+        // one copy site for every kind (the walker is cold code on one warp; keep its footprint small): a run of
+        // `count` rows is ONE bulk copy when the rows are packed (row stride == nlev), else one copy per row
+        const double* src;
+        double* dst = tile + (size_t)c.slot * a.nlev;
+        size_t sstride = (size_t)a.nlev;
+        bool packed = true;
         if (c.kind == 3) {
-            bulk_g2s(geo, a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u, bar);
+            src = a.geo + (size_t)c.src * a.geo_doubles;
+            dst = geo;
         } else if (c.kind == 4) {
-            // ghost rows of x, straight from the inbox (rows packed with stride nlev)
-            bulk_g2s(tile + (size_t)c.slot * a.nlev, inbox + (size_t)c.src * a.nlev, slot_bytes * c.count, bar);
+            src = inbox + (size_t)c.src * a.nlev;   // ghost rows of x, straight from the inbox (rows packed with stride nlev)
         } else if (c.kind == 2) {
-            const double* src = a.tinv + (size_t)c.src * a.nkT + a.lev0;
-            double* dst = tile + (size_t)c.slot * a.nlev;
-            if (a.contig_t) bulk_g2s(dst, src, slot_bytes * c.count, bar);
-            else
-                for (int j = 0; j < c.count; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * a.nkT, slot_bytes, bar);
+            src = a.tinv + (size_t)c.src * a.nkT + a.lev0;
+            sstride = (size_t)a.nkT;
+            packed = a.contig_t;
         } else {
-            const double* src = (c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld;
-            double* dst = tile + (size_t)c.slot * a.nlev;
-            if (a.contig_x) bulk_g2s(dst, src, slot_bytes * c.count, bar);
-            else
-                for (int j = 0; j < c.count; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * a.ld, slot_bytes, bar);
+            src = (c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld;
+            sstride = (size_t)a.ld;
+            packed = a.contig_x;
         }
+        const int n = packed ? 1 : c.count;
+        const unsigned bytes = c.kind == 3 ? (unsigned)a.geo_doubles * 8u : (packed ? slot_bytes * (unsigned)c.count : slot_bytes);
+#pragma unroll 1
+        for (int j = 0; j < n; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * sstride, bytes, bar);
     }
     // nslots = slots filled by x / coefficient entries (low 16 bits) and by thickness entries (high 16 bits)
     const unsigned nslots = (unsigned)(h.nslots & 0xffff) + (with_t ? (unsigned)(h.nslots >> 16) : 0u);
@@ -106,13 +112,17 @@ __device__ __forceinline__ void tile_prefetch(const TArgs& a, int e) {
     const int own_slots = a.prefetch_own_slots;
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = ents[ci];
+        const double* src = nullptr;
+        unsigned bytes = slot_bytes * (unsigned)c.count;
         if (c.kind == 3) {
-            bulk_prefetch_l2(a.geo + (size_t)c.src * a.geo_doubles, (unsigned)a.geo_doubles * 8u);
-        } else if (c.kind == 2 && a.tpow > 0 && a.contig_t) {
-            bulk_prefetch_l2(a.tinv + (size_t)c.src * a.nkT + a.lev0, slot_bytes * c.count);
-        } else if ((c.kind == 0 && c.slot < own_slots && a.contig_x) || (c.kind == 1 && a.contig_x)) {
-            bulk_prefetch_l2((c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld, slot_bytes * c.count);
+            src = a.geo + (size_t)c.src * a.geo_doubles;
+            bytes = (unsigned)a.geo_doubles * 8u;
+        } else if (c.kind == 2) {
+            if (a.tpow > 0 && a.contig_t) src = a.tinv + (size_t)c.src * a.nkT + a.lev0;
+        } else if (a.contig_x && ((c.kind == 0 && c.slot < own_slots) || c.kind == 1)) {
+            src = (c.kind == 0 ? a.x : a.c) + (size_t)c.src * a.ld;
         }
+        if (src) bulk_prefetch_l2(src, bytes);
     }
 }
 

@@ -111,6 +111,8 @@ class Engine:
             return (n1, n1, n0)
         if op == "M0h_up":
             return (n0, n0, n2)
+        if op == "UtQW":
+            return (n2, n1, n1)
         return {"M1": (n1, n1, 0), "M1h": (n1, n1, n2), "M2": (n2, n2, 0), "M2h": (n2, n2, n2), "M0": (n0, n0, 0),
                 "M0h": (n0, n0, n2), "K": (n1, n2, n1), "E10": (n0, n1, 0), "E01": (n1, n0, 0), "E21": (n1, n2, 0),
                 "E12": (n2, n1, 0)}[op]
@@ -154,7 +156,7 @@ class Engine:
 
     SPACES = {"M1": (1, 1, None), "M1h": (1, 1, 2), "M2": (2, 2, None), "M2h": (2, 2, 2), "M0": (0, 0, None),
               "M0h": (0, 0, 2), "K": (1, 2, 1), "E10": (0, 1, None), "E01": (1, 0, None), "E21": (1, 2, None),
-              "E12": (2, 1, None), "R": (1, 1, 0), "R_up": (1, 1, 0), "M0h_up": (0, 0, 2)}
+              "E12": (2, 1, None), "R": (1, 1, 0), "R_up": (1, 1, 0), "M0h_up": (0, 0, 2), "UtQW": (2, 1, 1)}
 
     # ---------------------------------------------------------------- applies (device resident)
     def apply(self, op, x, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0, u1=None, tau=0.0):
@@ -180,6 +182,9 @@ class Engine:
             self._chk(u1, self.n1, nlev, "u1")
             fn = getattr(L, "mimsem_gpu_apply_" + op)
             check(fn(h, lev0, nlev, nlev, scale, tpow, flags, coeff.data_ptr(), u1.data_ptr(), tau, xp, yp, st))
+        elif op == "UtQW":
+            # UtQWmat::assemble(u1, scale) + MatMult: coeff = u1 (1-form), x = 2-form
+            check(L.mimsem_gpu_apply_UtQW(h, nlev, nlev, scale, coeff.data_ptr(), xp, yp, st))
         elif op == "R":
             check(L.mimsem_gpu_apply_R(h, lev0, nlev, nlev, scale, tpow, flags, coeff.data_ptr(), xp, yp, st))
         elif op in ("M1", "M2", "M0"):
@@ -202,6 +207,9 @@ class Engine:
         if out is None:
             out = self.empty(n, nlev)
         self._chk(out, n, nlev, "out")
+        if op in ("M2", "M2h"):
+            # WmatInv / WhmatInv: element-local dense solves
+            raise MimsemError("use solve_m2")
         if op == "M0":
             check(self.L.mimsem_gpu_solve_M0(self._h, lev0, nlev, nlev, scale, tpow, flags, b.data_ptr(), out.data_ptr(), self._stream()))
             return out, 0, 0.0
@@ -213,11 +221,47 @@ class Engine:
                                          C.byref(it), C.byref(rr), self._stream()))
         return out, it.value, rr.value
 
-    def diag(self, op, nlev, lev0=0, scale=1.0, tpow=0, flags=0):
+    def diag(self, op, nlev, lev0=0, scale=1.0, tpow=0, flags=0, coeff=None):
+        """diagonal of M1, or of M0 / M0(h) (= Pvec::assemble / Phvec::assemble: the lumped 0-form mass vector)."""
+        if op in ("M0", "M0h"):
+            out = self.zeros(self.n0, nlev)
+            if op == "M0h":
+                self._chk(coeff, self.n2, nlev, "coeff")
+            check(self.L.mimsem_gpu_diag_M0(self._h, lev0, nlev, nlev, scale, tpow, flags, None if op == "M0" else coeff.data_ptr(),
+                                            out.data_ptr(), self._stream()))
+            return out
         if op != "M1":
-            raise MimsemError("diag: only M1")
+            raise MimsemError("diag: M1, M0 or M0h")
         out = self.zeros(self.n1, nlev)
         check(self.L.mimsem_gpu_diag_M1(self._h, lev0, nlev, nlev, scale, tpow, flags, out.data_ptr(), self._stream()))
+        return out
+
+    def solve_m2(self, b, coeff=None, out=None, lev0=0, scale=1.0, tpow=0, flags=0):
+        """x = M2^-1 b (coeff: M2(rho)^-1 b) -- WmatInv / WhmatInv::assemble + MatMult (eul/Assembly.cpp:1658-1800)."""
+        nlev = b.shape[1]
+        self._chk(b, self.n2, nlev, "b")
+        if out is None:
+            out = self.zeros(self.n2, nlev) if self.nel_owned != self.nel_total else self.empty(self.n2, nlev)
+        if coeff is not None:
+            self._chk(coeff, self.n2, nlev, "coeff")
+        check(self.L.mimsem_gpu_solve_M2(self._h, lev0, nlev, nlev, scale, tpow, flags, None if coeff is None else coeff.data_ptr(),
+                                         b.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def to_vertical(self, cols):
+        """L2Vecs::HorizToVert: (n2, nlev) column layout -> (nel_owned, nlev * p^2) per-element vertical vectors."""
+        nlev = cols.shape[1]
+        self._chk(cols, self.n2, nlev, "cols")
+        out = self.torch.empty((self.nel_owned, nlev * self.p * self.p), dtype=self.torch.float64, device=cols.device)
+        check(self.L.mimsem_gpu_columns_to_vertical(self._h, nlev, nlev, cols.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def from_vertical(self, vert, out=None):
+        """L2Vecs::VertToHoriz: (nel_owned, nlev * p^2) -> (n2, nlev) column layout."""
+        nlev = vert.shape[1] // (self.p * self.p)
+        if out is None:
+            out = self.zeros(self.n2, nlev)
+        check(self.L.mimsem_gpu_vertical_to_columns(self._h, nlev, nlev, vert.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def capture(self, op, x, coeff=None, out=None, **kw):

@@ -433,6 +433,51 @@ def test_vorticity_term_operators_vs_reference_golden(fname, p, ne):
     assert rel_l2(y1, g["y_Ut_mat"]) < TOL
 
 
+@pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
+def test_remaining_coefficient_operators(fname, p, ne, tmp_path):
+    """SURVEY section 8f-2: UtQWmat (golden vector of the reference), Pvec / Phvec (= the diagonal of Pmat / Pmat::assemble_h,
+    eul/Assembly.cpp:602-681) and WmatInv / WhmatInv (element-block inverse of Wmat / Whmat, eul/Assembly.cpp:1658-1800)
+    against the oracle's assembled matrices."""
+    import scipy.sparse.linalg as spla
+    g = golden(fname)
+    mesh, eng = _engine("sphere", p, ne, thick=g["thick"])
+    s = float(g["scale"])
+    nk = int(g["nk"])
+    y = _apply(eng, "UtQW", g["x2"], g["u1"], scale=s)
+    assert rel_l2(y, g["y_UtQWmat"]) < TOL, rel_l2(y, g["y_UtQWmat"])
+    O = _oracle(tmp_path, "sphere", p, ne, 6, "eul")
+    O.set_thick(g["thick"])
+    dP = to_np(eng, eng.diag("M0", nk, scale=s, tpow=1), 0)
+    dPh = to_np(eng, eng.diag("M0h", nk, scale=s, tpow=2, coeff=to_cols(eng, g["h2"], 2)), 0)
+    xw = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), scale=s, tpow=1), 2)
+    xwh = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), coeff=to_cols(eng, g["h2"], 2), scale=s, tpow=2), 2)
+    for lev in range(nk):
+        P0 = O.pmat(lev, s)
+        assert abs(P0 - sp.diags(P0.diagonal())).max() < 1e-9 * abs(P0).max()      # m == p: Pmat is diagonal, Pvec its diagonal
+        assert rel_l2(dP[lev], P0.diagonal()) < TOL
+        assert rel_l2(dPh[lev], O.pmat(lev, s, h2=g["h2"][lev]).diagonal()) < TOL
+        assert rel_l2(xw[lev], spla.spsolve(O.wmat(lev, s, 1).tocsc(), g["x2"][lev])) < TOL, ("WmatInv", lev)
+        assert rel_l2(xwh[lev], spla.spsolve(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < TOL, ("WhmatInv", lev)
+
+
+@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 4, 30), ("sphere", 4, 3, 60), ("box", 3, 5, 7)])
+def test_l2vecs_relabelling_bit_exact(kind, p, ne, nk):
+    """L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): vz[e][k*p^2 + i] = vh[k][elInds2_l(e)[i]], bit for bit."""
+    import torch
+    mesh, eng = _engine(kind, p, ne)
+    rng = np.random.default_rng(9)
+    vh = rng.uniform(-1, 1, (nk, mesh.N2))
+    vz = np.zeros((mesh.nel, nk * p * p))
+    for e in range(mesh.nel):                       # the reference's loop, restated
+        for k in range(nk):
+            vz[e, k * p * p:(k + 1) * p * p] = vh[k, mesh.el2[e]]
+    cols = to_cols(eng, vh, 2)
+    got = eng.to_vertical(cols)
+    assert np.array_equal(got.cpu().numpy(), vz)
+    back = eng.from_vertical(torch.from_numpy(vz).cuda())
+    assert np.array_equal(to_np(eng, back, 2), vh)
+
+
 def test_multi_gpu_partitioned_apply():
     """N>1: element-block partition + NCCL ghost refresh, bitwise equal to the single-GPU result (tests/mp_check.py)."""
     import subprocess
