@@ -329,6 +329,20 @@ int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, do
                              int npull, const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf,
                              int push_ctas, void* d_epoch, int* d_err, void* stream);
 
+/*
+ * The same with the IN-BAND hand-over of the ghost rows: a pushed value travels as one 16-byte cell
+ * { lo32(value), epoch32, hi32(value), epoch32 } that validates itself, so the sender needs no system fence and no flag
+ * after the copy and the receiver's boundary tiles poll the cells they read (ordinary loads instead of TMA for those
+ * rows).  d_inbox_cells = this rank's inbox of 16-byte cells, [nbuf][ghost rows][nlev], cell_stride cells between
+ * copies; d_push[].inbox / .inbox_parity_stride address the PEER's cell inbox in the same units.  d_push[].wait and
+ * d_pull[].signal carry the acknowledgements as before; d_push[].signal and d_pull[].wait are unused.  The cell
+ * inbox, its acknowledgement words and d_epoch must not be shared with mimsem_gpu_halo_push / _pull.
+ */
+int mimsem_gpu_apply_M1_halo_ll(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_x,
+                                double* d_y, const double* d_x_push, int mode, int npush, const void* d_push, int npull,
+                                const void* d_pull, const void* d_inbox_cells, int64_t cell_stride, int nbuf, int push_ctas,
+                                void* d_epoch, int* d_err, void* stream);
+
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
 

@@ -482,7 +482,7 @@ int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
         r.h.flags = flags;
         // plain M1
         r.cp.push_back(CopyEnt{3, e, 0, 1});
-        int nx;
+        int nx, ng = 0;
         if (ghost_from >= 0) {
             std::vector<std::pair<int, int>> xo, xg;
             for (auto& ds : xs) {
@@ -490,19 +490,22 @@ int build_tma_plan_p(mimsem_gpu_ctx* c, int ghost_from = -1) {
                 if (ext >= ghost_from) xg.push_back({ext - ghost_from, ds.second});
                 else xo.push_back(ds);
             }
-            nx = emit_runs(xo, 0, r.cp) + emit_runs(xg, 4, r.cp);
+            nx = emit_runs(xo, 0, r.cp);
+            r.fh.first4 = (int)r.cp.size();
+            ng = emit_runs(xg, 4, r.cp);
+            r.fh.n4 = (int)r.cp.size() - r.fh.first4;
         } else {
             nx = emit_runs(xs, 0, r.cp);
         }
         const int nt = emit_runs(ts, 2, r.cp);
         r.h.cp_count = (int)r.cp.size();
-        r.h.nslots = nx | (nt << 16);
+        r.h.nslots = nx | (ng << 12) | (nt << 20);
         // M1(h)
         r.cp_h.push_back(CopyEnt{3, e, 0, 1});
         emit_runs(xs, 0, r.cp_h);
         const int nh = emit_runs(hs, 1, r.cp_h);
         emit_runs(ts, 2, r.cp_h);
-        r.nslots_h = (nx + nh) | (nt << 16);
+        r.nslots_h = (nx + nh) | (nt << 20);
     }
     // pack into fixed-stride records: header words, copy entries, explicit far-row lists (only if some tile needs one)
     static_assert(sizeof(TileHdr) == 16 && sizeof(CopyEnt) == 16 && sizeof(TileFar) == 16 && sizeof(TileFarH) == 16, "16-byte records");
@@ -584,7 +587,7 @@ int build_k_plan_p(mimsem_gpu_ctx* c) {
         h.st_dof = e2[0];
         h.cp_count = (int)ents[e].size();
         h.flags = 0;
-        h.nslots = (int)(2 * xs.size()) | ((int)ts.size() << 16);
+        h.nslots = (int)(2 * xs.size()) | ((int)ts.size() << 20);
         hdr[e] = h;
         nents = std::max(nents, h.cp_count);
     }
@@ -760,7 +763,8 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.geo = with_h ? c->d_geo_h.p : c->d_geo.p;
         t.x = x; t.c = h2; t.tinv = a.tinv; t.y = y;
         copy_basis(c, t);
-        M1TileLaunch l{c->p, with_h, hf != nullptr, a.nel, 0, false, c->m1_min_blocks};
+        for (size_t i = 0; i < sizeof(t.E) / sizeof(double); i++) t.Es[i] = scale * t.E[i];
+        M1TileLaunch l{c->p, with_h, hf ? (hf->ll ? 2 : 1) : 0, a.nel, 0, false, c->m1_min_blocks};
         if (hf) {
             if (!c->d_fused_counters.p) {
                 CUDA_OK(c->d_fused_counters.resize(80));
@@ -1583,14 +1587,14 @@ int mimsem_gpu_apply_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sc
                         double* y, void* st) {
     return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
 }
-int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+static int apply_m1_halo_impl(int ll, mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
                              double* y, const double* x_push, int mode, int npush, const void* d_push, int npull,
                              const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf, int push_ctas,
                              void* d_epoch, int* d_err, void* st) {
     if (!c) return fail(MIMSEM_ERR_ARG, "null context");
     if (int rcl = check_halo_levels(c, nlev, ld, nbuf)) return rcl;
     // bulk copies and 16-byte stores address the inbox copies: every copy must start on a 16-byte boundary
-    if (parity_stride % 2 != 0 || (uintptr_t)d_inbox % 16 != 0) return fail(MIMSEM_ERR_ARG, "fused ghost refresh: inbox copies must be 16-byte aligned (even stride)");
+    if ((!ll && parity_stride % 2 != 0) || (uintptr_t)d_inbox % 16 != 0) return fail(MIMSEM_ERR_ARG, "fused ghost refresh: inbox copies must be 16-byte aligned (even stride)");
     if (mode < 0 || mode > 3 || ((mode == 1 || mode == 2) && !x_push)) return fail(MIMSEM_ERR_ARG, "bad pipelining mode / missing field to push");
     if (mode == 3) npush = 0;   // last call of a pipelined sequence: consume what the previous call pushed, push nothing
     if (!c || !d_epoch || !d_err || (npush > 0 && !d_push) || (npull > 0 && (!d_pull || !d_inbox)))
@@ -1605,12 +1609,27 @@ int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, doub
     hf.inbox = d_inbox;
     hf.parity_stride = parity_stride;
     hf.nbuf = nbuf;
+    hf.ll = ll;
     hf.epoch = (unsigned long long*)d_epoch;
     hf.err = d_err;
     hf.x_push = mode == 0 ? x : x_push;
     hf.lead = mode == 1 ? 1 : 0;
     hf.push_only = mode == 2 ? 1 : 0;
     return apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st, &hf);
+}
+int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                             double* y, const double* x_push, int mode, int npush, const void* d_push, int npull,
+                             const void* d_pull, const double* d_inbox, int64_t parity_stride, int nbuf, int push_ctas,
+                             void* d_epoch, int* d_err, void* st) {
+    return apply_m1_halo_impl(0, c, lev0, nlev, ld, scale, tpow, flags, x, y, x_push, mode, npush, d_push, npull, d_pull, d_inbox,
+                              parity_stride, nbuf, push_ctas, d_epoch, d_err, st);
+}
+int mimsem_gpu_apply_M1_halo_ll(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
+                                double* y, const double* x_push, int mode, int npush, const void* d_push, int npull,
+                                const void* d_pull, const void* d_inbox_cells, int64_t cell_stride, int nbuf, int push_ctas,
+                                void* d_epoch, int* d_err, void* st) {
+    return apply_m1_halo_impl(1, c, lev0, nlev, ld, scale, tpow, flags, x, y, x_push, mode, npush, d_push, npull, d_pull,
+                              (const double*)d_inbox_cells, cell_stride, nbuf, push_ctas, d_epoch, d_err, st);
 }
 int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* h2,
                          const double* x, double* y, void* st) {

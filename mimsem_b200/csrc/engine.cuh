@@ -200,7 +200,8 @@ struct TileHdr {      // word 0
     int st_dof;       // first output row of the element's owned block
     int cp_count;
     int flags;        // TF_* bits
-    int nslots;       // slots filled by the list (for the mbarrier transaction count): x/coefficient | thickness << 16
+    int nslots;       // slots filled by the list (for the mbarrier transaction count):
+                      //   x / coefficient rows | ghost rows staged from the halo inbox << 12 | thickness << 20
 };
 struct TileFar {      // word 1: first rows of the far-line runs of the x field.  OTH(q,t), q <= P, t < P:
     int w16, w4;      //   west neighbour:  q < P -> row w16 + q P + t ; q == P -> row w4 +- t  (TF_W4_DESC)
@@ -208,7 +209,7 @@ struct TileFar {      // word 1: first rows of the far-line runs of the x field.
 };
 struct TileFarH {     // word 2
     int hw, hs;       // first row of the west / south neighbour's 2-form block (M1h)
-    int pad0, pad1;
+    int n4, first4;   // copy entries [first4, first4 + n4) are the kind-4 ones (ghost rows staged from the halo inbox)
 };
 constexpr int kRecHdr = 3;
 enum : int {
@@ -236,6 +237,7 @@ struct HaloFused {
     int* err;
     // software pipelining over independent applies: with lead = 1 the push CTAs send the boundary rows of the NEXT
     // call's input (x_push, data epoch e+1) while this call's boundary tiles consume what the previous call pushed
+    int ll;                          // 1: in-band protocol -- inbox cells are 16 bytes {lo, epoch, hi, epoch}, strides count cells
     const double* x_push;            // field whose boundary rows are pushed (lead 0: the input itself)
     int lead;                        // 0 or 1
     int nbuf;                        // inbox copies (2, or 3 so that a pipelined push never waits for the current consumer)
@@ -264,6 +266,7 @@ struct TArgs {
     const double* tinv;
     double* y;
     double E[(kMaxP + 1) * kMaxP];
+    double Es[(kMaxP + 1) * kMaxP];   // scale * E: the operator's scale factor rides on the last contraction (M1 tile kernel)
 #ifdef MIMSEM_DIAG
     long long* dbg_times;     // [grid][6] phase timestamps (globaltimer ns), diagnostics build only
     int debug;                // bit0 skip arithmetic, bit4 skip copies (phase-isolation timing experiments)

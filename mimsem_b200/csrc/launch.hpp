@@ -13,7 +13,7 @@ namespace mimsem {
 struct M1TileLaunch {
     int p;
     bool with_h;
-    bool halo;
+    int halo;           // 0: none, 1: fused ghost refresh with flags, 2: with in-band (LL) cells
     int nel;            // tiles
     int push_ctas;      // fused ghost refresh: CTAs of the push role (0: none)
     bool push_only;     // prologue of a pipelined sequence

@@ -6,13 +6,15 @@ namespace mimsem {
 
 namespace {
 
-template <int P, bool WITH_H, bool HALO, int MINB>
-void (*pick_nl(int nlev))(const TArgs) {
-    // compile-time level counts of the BASELINE configurations (C3: 30, C4: 40, C5: 60); anything else: runtime
-    if ((P == 3 || P == 4) && nlev == 60) return k_apply_m1_tile<P, WITH_H, 60, HALO, MINB>;
-    if (P == 3 && nlev == 30) return k_apply_m1_tile<P, WITH_H, 30, HALO, MINB>;
-    if (P == 3 && nlev == 40) return k_apply_m1_tile<P, WITH_H, 40, HALO, MINB>;
-    return k_apply_m1_tile<P, WITH_H, 0, HALO, MINB>;
+template <int P, bool WITH_H, int HALO, int MINB>
+void (*pick_nl(int nlev, int tpow))(const TArgs) {
+    // compile-time level counts of the BASELINE configurations (C3: 30, C4: 40, C5: 60) together with the number of
+    // thickness factors their Umat (1) / Uhmat (2) applies use; anything else: runtime
+    constexpr int TP = WITH_H ? 2 : 1;
+    if ((P == 3 || P == 4) && nlev == 60) return tpow == TP ? k_apply_m1_tile<P, WITH_H, 60, HALO, MINB, TP> : k_apply_m1_tile<P, WITH_H, 60, HALO, MINB, -1>;
+    if (P == 3 && nlev == 30) return tpow == TP ? k_apply_m1_tile<P, WITH_H, 30, HALO, MINB, TP> : k_apply_m1_tile<P, WITH_H, 30, HALO, MINB, -1>;
+    if (P == 3 && nlev == 40) return tpow == TP ? k_apply_m1_tile<P, WITH_H, 40, HALO, MINB, TP> : k_apply_m1_tile<P, WITH_H, 40, HALO, MINB, -1>;
+    return k_apply_m1_tile<P, WITH_H, 0, HALO, MINB, -1>;
 }
 
 // register budget: CTAs per SM the shared-memory footprint allows at the BASELINE shapes
@@ -30,18 +32,19 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         const size_t smem = 16 + ((size_t)S::GEO + (size_t)(l.with_h ? S::NS_H : S::NS) * t.nlev) * sizeof(double);
         if (smem > 227 * 1024) return;
         void (*kern)(const TArgs) = nullptr;
-        if (l.halo) kern = pick_nl<P, false, true, default_minb<P, false>()>(t.nlev);
+        if (l.halo == 2) kern = pick_nl<P, false, 2, default_minb<P, false>()>(t.nlev, t.tpow);
+        else if (l.halo) kern = pick_nl<P, false, 1, default_minb<P, false>()>(t.nlev, t.tpow);
         else if (l.with_h) {
-            kern = pick_nl<P, true, false, default_minb<P, true>()>(t.nlev);
+            kern = pick_nl<P, true, 0, default_minb<P, true>()>(t.nlev, t.tpow);
             if constexpr (P == 4) {
-                if (l.min_blocks == 5) kern = pick_nl<P, true, false, 5>(t.nlev);
+                if (l.min_blocks == 5) kern = pick_nl<P, true, 0, 5>(t.nlev, t.tpow);
             }
         }
         else {
-            kern = pick_nl<P, false, false, default_minb<P, false>()>(t.nlev);
+            kern = pick_nl<P, false, 0, default_minb<P, false>()>(t.nlev, t.tpow);
             if constexpr (P == 4) {   // register-budget variants kept for tuning runs (mimsem_gpu_set_option "m1_min_blocks")
-                if (l.min_blocks == 4) kern = pick_nl<P, false, false, 4>(t.nlev);
-                if (l.min_blocks == 6) kern = pick_nl<P, false, false, 6>(t.nlev);
+                if (l.min_blocks == 4) kern = pick_nl<P, false, 0, 4>(t.nlev, t.tpow);
+                if (l.min_blocks == 6) kern = pick_nl<P, false, 0, 6>(t.nlev, t.tpow);
             }
         }
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

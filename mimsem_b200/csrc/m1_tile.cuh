@@ -71,6 +71,93 @@ static __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// In-band ("LL") variant of the fused ghost refresh.  A pushed value travels as ONE 16-byte cell
+//   { lo32(value), epoch32, hi32(value), epoch32 }
+// so that the data validates itself: the receiver polls the cell until both flag words carry the epoch it expects
+// (each 8-byte half is written atomically, so a torn cell is never mistaken for a complete one).  Nothing else is
+// needed to hand the rows over -- no system fence after the copy, no per-peer flag, no counter of finished push
+// CTAs -- which takes the push off the critical path of a step: the rows are visible one NVLink traversal after
+// the stores were issued instead of 15-20 us into the launch.  The inbox is never reset: cells of the copy that is
+// overwritten (data epoch e - nbuf) carry a different epoch.  Cost: twice the NVLink bytes (still < 2 MB per rank
+// and step on C5 at 8 GPUs) and no TMA on the receiving side (the consumer unpacks cells with ordinary loads).
+__device__ __forceinline__ void ll_store(uint4* cell, double v, unsigned ep) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)b), "r"(ep), "r"((unsigned)(b >> 32)), "r"(ep)
+                 : "memory");
+}
+// poll a cell until it carries epoch `ep`; gives up after ~2 s (a dead peer must not hang the GPU) and records the failure
+__device__ __forceinline__ double ll_load(const uint4* cell, unsigned ep, int* err) {
+    unsigned x, f0, y, f1;
+    long long t0 = 0;
+    for (unsigned spin = 0;; spin++) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(cell) : "memory");
+        if (f0 == ep && f1 == ep) break;
+        if ((spin & 1023u) == 1023u) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ll) {
+                atomicExch(err, 1);
+                break;
+            }
+        }
+    }
+    return __longlong_as_double((long long)(((unsigned long long)y << 32) | (unsigned long long)x));
+}
+
+static __device__ __noinline__ void halo_push_role_ll(const TArgs& a, unsigned long long epoch) {
+    const HaloFused& h = a.halo;
+    __shared__ HaloPeer peers[kMaxPushPeers];
+    __shared__ int pre[kMaxPushPeers + 1];
+    if (threadIdx.x < h.npush) {
+        peers[threadIdx.x] = h.push[threadIdx.x];
+        // the peer must have consumed the inbox copy of epoch - nbuf (the one this push overwrites)
+        if (epoch > (unsigned long long)h.nbuf) spin_until(h.push[threadIdx.x].wait, epoch - h.nbuf, h.err);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int p = 0; p < h.npush; p++) {
+            pre[p] = acc;
+            acc += peers[p].nrows;
+        }
+        pre[h.npush] = acc;
+    }
+    __syncthreads();
+    const int nl2 = a.nlev >> 1;
+    const int R = pre[h.npush];
+    const int f0 = (int)(((long long)R * blockIdx.x) / h.push_ctas);
+    const int f1 = (int)(((long long)R * (blockIdx.x + 1)) / h.push_ctas);
+    const int total = (f1 - f0) * nl2;
+    const unsigned ep = (unsigned)epoch;
+    constexpr int U = 4;
+    for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
+        double2 v[U];
+        uint4* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = base + u * blockDim.x;
+            dst[u] = nullptr;
+            if (i < total) {
+                const int f = f0 + i / nl2, k2 = i - (f - f0) * nl2;
+                int p = 0;
+                while (f >= pre[p + 1]) p++;
+                const int r = f - pre[p];
+                const HaloPeer& pp = peers[p];
+                v[u] = __ldg(reinterpret_cast<const double2*>(h.x_push + (size_t)pp.rows[r] * a.ld) + k2);
+                // LL inbox of the peer: 16-byte cells, [copy][row][level]
+                dst[u] = reinterpret_cast<uint4*>(pp.inbox) + (epoch % h.nbuf) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev + 2 * k2;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (dst[u]) {
+                ll_store(dst[u], v[u].x, ep);
+                ll_store(dst[u] + 1, v[u].y, ep);
+            }
+    }
+}
+
 // Every push CTA and every boundary tile of a fused launch ends here; the last one acknowledges the inbox of this epoch
 // to the peers (all reads from it have completed) and advances the epoch for the next launch / graph replay.
 static __device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long epoch) {
@@ -107,8 +194,8 @@ static __device__ __noinline__ void halo_wait_peers(const TArgs& a, unsigned lon
 // interpolation onto the far line is needed,  ubf[q] = sum_t E[P][t] oth(q,t)  (and of its 2-form coefficient only
 // hs[j] = sum_t E[P][t] h(t across, j along)), so (P+1)P + P^2 loads collapse into 2P+1 registers that stay live
 // across the wait for the bulk copies.  Lanes are levels: every load is a coalesced run of the row.
-template <int P, bool WITH_H, bool HALO>
-__device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, int flags, int side, const double* inbox, int k,
+template <int P, bool WITH_H, int HALO>
+__device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, int flags, int side, const double* inbox, unsigned ep, int k,
                                           double (&ubf)[P + 1], double (&hs)[P]) {
     const int has = side ? TF_HAS_S : TF_HAS_W;
 #pragma unroll
@@ -140,7 +227,8 @@ __device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, in
 #pragma unroll
         for (int t = 0; t < P; t++) {
             const int r = rows[q * P + t];
-            if (HALO && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+            if (HALO == 1 && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+            else if (HALO == 2 && r < 0) oth[q][t] = ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(-r - 1) * a.nlev + k, ep, a.halo.err);
             else oth[q][t] = xk[(size_t)r * a.ld];
         }
     double hv[WITH_H ? P : 1][WITH_H ? P : 1];
@@ -175,7 +263,7 @@ __device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, in
 // Contribution of the neighbour's far GLL line to my P shared edges (one routine for both sides and both orientations:
 // side and `rev` only select shared-memory strides).  rev: the neighbour numbers the shared edges in the opposite
 // direction (rotated cubed-sphere seam).
-template <int P, bool WITH_H, int NL>
+template <int P, bool WITH_H, int NL, int TPOW>
 __device__ __forceinline__ void far_line(const TArgs& a, const double* col, const double* geo, int flags, int side,
                                          const double (&ubf)[P + 1], const double (&hs)[P], double (&cfar)[P]) {
     using S = M1Slots<P>;
@@ -202,31 +290,77 @@ __device__ __forceinline__ void far_line(const TArgs& a, const double* col, cons
         double ua = 0.0;
 #pragma unroll
         for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
-        double c = a.scale;
-        if (a.tpow > 0) {
+        // (the operator's scale factor rides on the final contraction: a.Es = scale * E)
+        double g = gf[q * 2 + 0] * ua + gf[q * 2 + 1] * ubf[q];
+        const int tpw = TPOW >= 0 ? TPOW : a.tpow;
+        if (tpw > 0) {
             const double t = tp[q * tstep];
-            c *= t;
-            if (a.tpow > 1) c *= t;
+            g *= t;
+            if (tpw > 1) g *= t;
         }
         if (WITH_H) {
             double hl = 0.0;
 #pragma unroll
             for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hs[j];
-            c *= hl;
+            g *= hl;
         }
-        f[q] = c * (gf[q * 2 + 0] * ua + gf[q * 2 + 1] * ubf[q]);
+        f[q] = g;
     }
     double s[P];
 #pragma unroll
     for (int j = 0; j < P; j++) {
         double v = 0.0;
 #pragma unroll
-        for (int q = 0; q <= P; q++) v += a.E[q * P + j] * f[q];
+        for (int q = 0; q <= P; q++) v += a.Es[q * P + j] * f[q];
         s[j] = v;
     }
     // the neighbour's edge j is my edge (rev ? P-1-j : j)
 #pragma unroll
     for (int j = 0; j < P; j++) cfar[j] = rev ? s[P - 1 - j] : s[j];
+}
+
+// M1(h): the point factor t^tpow * hl(q), hl = the element's 2-form coefficient interpolated to the quadrature point
+// (interp2_g without its 1/det, which sits in the geometry record), is the same for both edge directions.  The two
+// warp-pairs of a tile tabulate it ONCE -- part 0 the GLL columns qx < SPLIT, part 1 the others, sum-factorised --
+// and leave it in the thickness slots, so that the line contraction below is exactly the plain M1 one (one multiply per
+// point, no coefficient data in registers).  Runs between two CTA barriers, after the far lines have read the raw
+// thickness of the west column / south row.
+template <int P, int NL, int TPOW>
+__device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part) {
+    using S = M1Slots<P>;
+    constexpr int NP1 = P + 1, SPLIT = (NP1 + 1) / 2;
+    const int nl = NL ? NL : a.nlev;
+    const int tpw = TPOW >= 0 ? TPOW : a.tpow;
+    double hv[P][P];
+#pragma unroll
+    for (int iy = 0; iy < P; iy++)
+#pragma unroll
+        for (int ix = 0; ix < P; ix++) hv[iy][ix] = col[(size_t)(S::H + iy * P + ix) * nl];
+#pragma unroll
+    for (int qx = 0; qx <= P; qx++) {
+        if ((qx < SPLIT) != (part == 0)) continue;
+        double ax[P];
+#pragma unroll
+        for (int iy = 0; iy < P; iy++) {
+            double s = 0.0;
+#pragma unroll
+            for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * hv[iy][ix];
+            ax[iy] = s;
+        }
+#pragma unroll
+        for (int qy = 0; qy <= P; qy++) {
+            double hl = 0.0;
+#pragma unroll
+            for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * ax[iy];
+            double* tq = col + (size_t)(S::T + qy * NP1 + qx) * nl;
+            if (tpw > 0) {
+                const double t = *tq;
+                hl *= t;
+                if (tpw > 1) hl *= t;
+            }
+            *tq = hl;
+        }
+    }
 }
 
 // One warp-pair's share of an element tile: part 0 = the x-normal edges of GLL columns 0..P-1, part 1 = the y-normal
@@ -237,7 +371,7 @@ __device__ __forceinline__ void far_line(const TArgs& a, const double* col, cons
 // record is laid out per part for this, gl[part][line][q] = (g_own, g_oth):
 //   part 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; part 1: f1 = c (Gbb ul1 + Gab ul0), ul1 = ua.
 // Each line is stored as soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
-template <int P, bool WITH_H, int NL>
+template <int P, bool WITH_H, int NL, int TPOW>
 __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, int part, const double (&cfar)[P],
                                            double* __restrict__ y) {
     using S = M1Slots<P>;
@@ -260,19 +394,6 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
         double own[P];
 #pragma unroll
         for (int j = 0; j < P; j++) own[j] = ownp[(size_t)(ln * P + j) * nl];
-        double hc[WITH_H ? P : 1];   // h contracted across the line direction
-        if (WITH_H) {
-            // h(ix = t, iy = j) for part 0, h(ix = j, iy = t) for part 1: slot H + j sj + t st
-            const double* hp = col + (size_t)S::H * nl;
-            const int sj = (part ? 1 : P) * nl, st = (part ? P : 1) * nl;
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                double s = 0.0;
-#pragma unroll
-                for (int t = 0; t < P; t++) s += a.E[ln * P + t] * hp[j * sj + t * st];
-                hc[WITH_H ? j : 0] = s;
-            }
-        }
         double f[P + 1];
 #pragma unroll
         for (int q = 0; q <= P; q++) {
@@ -281,25 +402,24 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
             for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
 #pragma unroll
             for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * othr[q][t];
-            double c = a.scale;
-            if (a.tpow > 0) {
-                const double t = tp[q * sq + ln * sl];
-                c *= t;
-                if (a.tpow > 1) c *= t;
-            }
+            double g = gl[(ln * NP1 + q) * 2 + 0] * ua + gl[(ln * NP1 + q) * 2 + 1] * ub;
             if (WITH_H) {
-                double hl = 0.0;
-#pragma unroll
-                for (int j = 0; j < P; j++) hl += a.E[q * P + j] * hc[WITH_H ? j : 0];
-                c *= hl;
+                g *= tp[q * sq + ln * sl];   // h_prepass left t^tpow * hl(q) in the thickness slot
+            } else {
+                const int tpw = TPOW >= 0 ? TPOW : a.tpow;
+                if (tpw > 0) {
+                    const double t = tp[q * sq + ln * sl];
+                    g *= t;
+                    if (tpw > 1) g *= t;
+                }
             }
-            f[q] = c * (gl[(ln * NP1 + q) * 2 + 0] * ua + gl[(ln * NP1 + q) * 2 + 1] * ub);
+            f[q] = g;
         }
 #pragma unroll
         for (int j = 0; j < P; j++) {
             double s = (ln == 0) ? cfar[j] : 0.0;
 #pragma unroll
-            for (int q = 0; q <= P; q++) s += a.E[q * P + j] * f[q];
+            for (int q = 0; q <= P; q++) s += a.Es[q * P + j] * f[q];
             y[(size_t)(ln * P + j) * a.ld] = s;
         }
     }
@@ -307,9 +427,11 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
 
 // y = M1 x (WITH_H: M1(h) x).  One CTA per element; 128 threads = 2 warp-pairs (x-normal / y-normal edges) x 64 level
 // lanes.  NL = compile-time number of levels (0: runtime) so that shared-memory operands use immediate offsets.
-// HALO: ghost refresh fused into the launch (see HaloFused); a separate instantiation so that the single-GPU kernel
-// carries none of its code.  MINB = resident CTAs per SM the register allocation is budgeted for.
-template <int P, bool WITH_H, int NL, bool HALO, int MINB>
+// HALO: ghost refresh fused into the launch (see HaloFused; 1 = flag protocol, 2 = in-band LL cells); separate
+// instantiations so that the single-GPU kernel
+// carries none of its code.  MINB = resident CTAs per SM the register allocation is budgeted for.  TPOW = compile-time
+// number of thickness factors (-1: runtime) for the BASELINE shapes.
+template <int P, bool WITH_H, int NL, int HALO, int MINB, int TPOW>
 __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_constant__ TArgs a) {
     using S = M1Slots<P>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -324,7 +446,9 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
     if (HALO) {
         if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) epoch = *a.halo.epoch + 1;
         if ((int)blockIdx.x < a.halo.push_ctas) {
-            halo_push_role(a, epoch + (unsigned long long)a.halo.lead);   // data epoch of the pushed field
+            // data epoch of the pushed field = epoch + lead
+            if (HALO == 2) halo_push_role_ll(a, epoch + (unsigned long long)a.halo.lead);
+            else halo_push_role(a, epoch + (unsigned long long)a.halo.lead);
             halo_cta_done(a, epoch);
             return;
         }
@@ -344,10 +468,15 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
         DBG_T(0);
         const double* inbox = nullptr;
         if (HALO && tile_i >= a.halo.n_int) {
-            // boundary tile: the peers' rows of this epoch must have landed in my inbox before anybody reads it
-            if (threadIdx.x < 32) halo_wait_peers(a, epoch, threadIdx.x);
-            __syncthreads();
-            inbox = a.halo.inbox + (epoch % a.halo.nbuf) * a.halo.parity_stride;
+            if (HALO == 1) {
+                // boundary tile: the peers' rows of this epoch must have landed in my inbox before anybody reads it
+                if (threadIdx.x < 32) halo_wait_peers(a, epoch, threadIdx.x);
+                __syncthreads();
+                inbox = a.halo.inbox + (epoch % a.halo.nbuf) * a.halo.parity_stride;
+            } else {
+                // LL: cells validate themselves; parity_stride counts 16-byte cells (= 2 doubles)
+                inbox = a.halo.inbox + (epoch % a.halo.nbuf) * a.halo.parity_stride * 2;
+            }
         }
 #ifdef MIMSEM_DIAG
         if (!(a.debug & 16))
@@ -360,7 +489,22 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
             }
         }
         double ubf[P + 1], hs[P];
-        if (k < nl) far_fetch<P, WITH_H, HALO>(a, rec, hd.flags, part, inbox, k, ubf, hs);
+        if (k < nl) far_fetch<P, WITH_H, HALO>(a, rec, hd.flags, part, inbox, (unsigned)epoch, k, ubf, hs);
+        if (HALO == 2 && inbox) {
+            // ghost rows that are STAGED (east column / north row owned elsewhere): unpack their cells into the tile
+            // slots with ordinary loads (the copy-list walker skips kind-4 entries in this mode); rows alternate
+            // between the two warp-pairs, lanes are levels
+            const TileFarH fh = *reinterpret_cast<const TileFarH*>(rec + 2);
+            const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr);
+            if (k < nl)
+                for (int ci = fh.first4; ci < fh.first4 + fh.n4; ci++) {
+                    const CopyEnt c = ents[ci];
+                    for (int j = part; j < c.count; j += 2)
+                        tile[(size_t)(c.slot + j) * nl + k] =
+                            ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(c.src + j) * a.nlev + k, (unsigned)epoch, a.halo.err);
+                }
+            __syncthreads();   // generic-proxy writes of one warp-pair are read by the other
+        }
         DBG_T(1);
 #ifdef MIMSEM_DIAG
         if (!(a.debug & 16))
@@ -370,11 +514,17 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
 #ifdef MIMSEM_DIAG
         if (!(a.debug & 1))
 #endif
-        if (k < nl) {
-            const double* col = tile + k;
+        {
+            const bool active = k < nl;   // level lanes beyond nlev only take part in the barriers
+            double* col = tile + k;
             double cfar[P];
-            far_line<P, WITH_H, NL>(a, col, geo, hd.flags, part, ubf, hs, cfar);
-            tile_lines<P, WITH_H, NL>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
+            if (active) far_line<P, WITH_H, NL, TPOW>(a, col, geo, hd.flags, part, ubf, hs, cfar);
+            if (WITH_H) {
+                __syncthreads();   // the far lines have read the raw thickness of the west column / south row
+                if (active) h_prepass<P, NL, TPOW>(a, col, part);
+                __syncthreads();
+            }
+            if (active) tile_lines<P, WITH_H, NL, TPOW>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
         }
         DBG_T(3);
         if (tile_i + tile_stride < a.ntiles) __syncthreads();   // the next tile's bulk loads overwrite the buffer

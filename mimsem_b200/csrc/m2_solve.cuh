@@ -2,7 +2,7 @@
 // (eul/Assembly.cpp:1658-1722, 1730-1800).  The 2-form mass matrix is block diagonal -- one p^2 x p^2 symmetric positive
 // definite block  B = W^T diag(c) W  per element and level -- and the reference inverts every block with Gauss-Jordan
 // elimination (LinAlg Inv).  Here one thread owns one (element, level) pair: it tabulates the lower triangle of its block
-// in shared memory (entry-major, lanes = levels: conflict free), factorises it in place (Cholesky) and solves; the block
+// in shared memory (entry-major, lanes = levels: conflict free), factorises it in place (L D L^T) and solves; the block
 // never exists in global memory.  The tabulation exploits the tensor structure of W:
 //   B[(iy,ix),(jy,jx)] = sum_qy E[qy][iy] E[qy][jy] ( sum_qx E[qx][ix] E[qx][jx] c[qy][qx] ).
 #pragma once
@@ -97,28 +97,39 @@ __global__ void __launch_bounds__(32) k_solve_m2(const __grid_constant__ KArgs a
             B[(size_t)(i * (i + 1) / 2 + j) * L] = s;
         }
     }
-    // in-place Cholesky B = L L^T (row-oriented), diagonal stored inverted
+    // in-place B = L D L^T (unit lower L below the diagonal, 1/D on it); no square roots, so a block that is not positive
+    // definite (a coefficient whose interpolant changes sign) still factorises as long as no pivot vanishes
     for (int i = 0; i < N; i++) {
         const int ri = i * (i + 1) / 2;
-        for (int j = 0; j <= i; j++) {
+        // row i holds W_it = L_it D_t until the row is finished
+        for (int j = 0; j < i; j++) {
             const int rj = j * (j + 1) / 2;
             double s = B[(size_t)(ri + j) * L];
             for (int t = 0; t < j; t++) s -= B[(size_t)(ri + t) * L] * B[(size_t)(rj + t) * L];
-            B[(size_t)(ri + j) * L] = (j < i) ? s * B[(size_t)(rj + j) * L] : 1.0 / sqrt(s);
+            B[(size_t)(ri + j) * L] = s;
         }
+        double d = B[(size_t)(ri + i) * L];
+        for (int t = 0; t < i; t++) {
+            const double w = B[(size_t)(ri + t) * L];
+            const double l = w * B[(size_t)(t * (t + 1) / 2 + t) * L];   // L_it = W_it / D_t
+            d -= w * l;
+            B[(size_t)(ri + t) * L] = l;
+        }
+        B[(size_t)(ri + i) * L] = 1.0 / d;
     }
-    // forward and backward substitution
+    // L z = b, z /= D, L^T x = z
     for (int i = 0; i < N; i++) R[(size_t)i * L] = ldro(a.x + k + (size_t)e2[i] * ld);
     for (int i = 0; i < N; i++) {
         const int ri = i * (i + 1) / 2;
         double s = R[(size_t)i * L];
         for (int t = 0; t < i; t++) s -= B[(size_t)(ri + t) * L] * R[(size_t)t * L];
-        R[(size_t)i * L] = s * B[(size_t)(ri + i) * L];
+        R[(size_t)i * L] = s;
     }
+    for (int i = 0; i < N; i++) R[(size_t)i * L] *= B[(size_t)(i * (i + 1) / 2 + i) * L];
     for (int i = N - 1; i >= 0; i--) {
         double s = R[(size_t)i * L];
         for (int t = i + 1; t < N; t++) s -= B[(size_t)(t * (t + 1) / 2 + i) * L] * R[(size_t)t * L];
-        R[(size_t)i * L] = s * B[(size_t)(i * (i + 1) / 2 + i) * L];
+        R[(size_t)i * L] = s;
     }
     for (int i = 0; i < N; i++) a.y[k + (size_t)e2[i] * ld] = R[(size_t)i * L];
 }

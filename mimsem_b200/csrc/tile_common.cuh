@@ -70,6 +70,7 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* i
     for (int ci = lane; ci < h.cp_count; ci += 32) {
         const CopyEnt c = (ci == lane) ? first : ents[ci];
         if (c.kind == 2 && !with_t) continue;
+        if (c.kind == 4 && a.halo.ll) continue;   // in-band protocol: unpacked by the tile's threads, not by TMA
         // one copy site for every kind (the walker is cold code on one warp; keep its footprint small): a run of
         // `count` rows is ONE bulk copy when the rows are packed (row stride == nlev), else one copy per row
         const double* src;
@@ -95,8 +96,9 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* i
 #pragma unroll 1
         for (int j = 0; j < n; j++) bulk_g2s(dst + (size_t)j * a.nlev, src + (size_t)j * sstride, bytes, bar);
     }
-    // nslots = slots filled by x / coefficient entries (low 16 bits) and by thickness entries (high 16 bits)
-    const unsigned nslots = (unsigned)(h.nslots & 0xffff) + (with_t ? (unsigned)(h.nslots >> 16) : 0u);
+    // bytes the TMA unit will deliver (the LL protocol unpacks ghost slots with ordinary loads instead)
+    const unsigned nslots = (unsigned)(h.nslots & 0xfff) + (a.halo.ll ? 0u : (unsigned)((h.nslots >> 12) & 0xff)) +
+                            (with_t ? (unsigned)(h.nslots >> 20) : 0u);
     if (lane == 0) mbar_arrive_expect_tx(bar, nslots * slot_bytes + (unsigned)a.geo_doubles * 8u);
 }
 

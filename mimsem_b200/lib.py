@@ -69,6 +69,8 @@ SIGNATURES = {
     "mimsem_gpu_halo_pull": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M1_halo": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
                                            C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_apply_M1_halo_ll": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
+                                              C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
 }
 

@@ -450,14 +450,20 @@ def test_remaining_coefficient_operators(fname, p, ne, tmp_path):
     dP = to_np(eng, eng.diag("M0", nk, scale=s, tpow=1), 0)
     dPh = to_np(eng, eng.diag("M0h", nk, scale=s, tpow=2, coeff=to_cols(eng, g["h2"], 2)), 0)
     xw = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), scale=s, tpow=1), 2)
-    xwh = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), coeff=to_cols(eng, g["h2"], 2), scale=s, tpow=2), 2)
+    # a density-like coefficient (positive interpolant: the blocks are SPD as in the model) ...
+    rho = 1.0e4 * (1.0 + 0.1 * np.random.default_rng(4).uniform(-1, 1, g["h2"].shape))
+    xwh = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), coeff=to_cols(eng, rho, 2), scale=s, tpow=2), 2)
+    # ... and the golden file's rough one (U(0.5, 1.5) per DOF: some blocks are indefinite; the reference inverts them with
+    # full pivoting, eul/LinAlg.cpp:186-260, the device factorisation does not pivot)
+    xwr = to_np(eng, eng.solve_m2(to_cols(eng, g["x2"], 2), coeff=to_cols(eng, g["h2"], 2), scale=s, tpow=2), 2)
     for lev in range(nk):
         P0 = O.pmat(lev, s)
         assert abs(P0 - sp.diags(P0.diagonal())).max() < 1e-9 * abs(P0).max()      # m == p: Pmat is diagonal, Pvec its diagonal
         assert rel_l2(dP[lev], P0.diagonal()) < TOL
         assert rel_l2(dPh[lev], O.pmat(lev, s, h2=g["h2"][lev]).diagonal()) < TOL
         assert rel_l2(xw[lev], spla.spsolve(O.wmat(lev, s, 1).tocsc(), g["x2"][lev])) < TOL, ("WmatInv", lev)
-        assert rel_l2(xwh[lev], spla.spsolve(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < TOL, ("WhmatInv", lev)
+        assert rel_l2(xwh[lev], spla.spsolve(O.wmat(lev, s, 1, rho=rho[lev], tpow_rho=1).tocsc(), g["x2"][lev])) < TOL, ("WhmatInv", lev)
+        assert rel_l2(xwr[lev], spla.spsolve(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < 1e-8, ("WhmatInv, rough", lev)
 
 
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 4, 30), ("sphere", 4, 3, 60), ("box", 3, 5, 7)])
