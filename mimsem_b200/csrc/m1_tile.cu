@@ -19,7 +19,7 @@ void (*pick_nl(int nlev, int tpow))(const TArgs) {
 
 // register budget: CTAs per SM the shared-memory footprint allows at the BASELINE shapes
 template <int P, bool WITH_H>
-constexpr int default_minb() { return P <= 3 ? (WITH_H ? 5 : 6) : (P == 4 ? (WITH_H ? 4 : 5) : 3); }
+constexpr int default_minb() { return P <= 3 ? (WITH_H ? 5 : 6) : (P == 4 ? 4 : 3); }
 
 }  // namespace
 
@@ -43,7 +43,7 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         else {
             kern = pick_nl<P, false, 0, default_minb<P, false>()>(t.nlev, t.tpow);
             if constexpr (P == 4) {   // register-budget variants kept for tuning runs (mimsem_gpu_set_option "m1_min_blocks")
-                if (l.min_blocks == 4) kern = pick_nl<P, false, 0, 4>(t.nlev, t.tpow);
+                if (l.min_blocks == 5) kern = pick_nl<P, false, 0, 5>(t.nlev, t.tpow);
                 if (l.min_blocks == 6) kern = pick_nl<P, false, 0, 6>(t.nlev, t.tpow);
             }
         }

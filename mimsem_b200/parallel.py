@@ -222,6 +222,8 @@ class DistributedEngine:
         self._inbox = {}
         import os
         self.fused = os.environ.get("MIMSEM_FUSED_HALO", "1") != "0"
+        # fused M1: hand the ghost rows over in self-validating 16-byte cells (no fence, no flag) instead of data + flag
+        self.ll = os.environ.get("MIMSEM_HALO_LL", "1") != "0"
         if world > 1 and os.environ.get("MIMSEM_HALO", "p2p") == "p2p":
             self._setup_p2p(P, sends)
 
@@ -239,7 +241,7 @@ class DistributedEngine:
         recv_peers = {s: sorted(P.recv[s]) for s in spaces}
         send_peers = {s: sorted(sends[s]) for s in spaces}
         assert all(len(v) <= MAXP for v in list(recv_peers.values()) + list(send_peers.values()))
-        hdr_bytes = 4 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP]
+        hdr_bytes = 5 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP], acks of the in-band (LL) 1-form inbox [MAXP]
         # inbox of a space: [NBUF copies][ghost rows of the space, in ghost order][nk]; a peer's share is the run of
         # rows it owns (ghosts are sorted by global id, owners hold contiguous id ranges)
         layout = {}                                    # (space, peer) -> (slot, first inbox row, nrows)
@@ -257,12 +259,17 @@ class DistributedEngine:
             stride = row * nk + ((row * nk) & 1)
             region[s] = (off, row, stride)
             off += self.NBUF * stride * 8
+        # in-band (LL) inbox of the 1-form space for the fused M1 launch: [NBUF][ghost rows][nk] 16-byte cells
+        off = (off + 15) // 16 * 16
+        ll_cells = region[1][1] * nk
+        ll_region = (off, ll_cells)
+        off += self.NBUF * ll_cells * 16
         total = max(off, hdr_bytes + 16)
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
         from .lib import check
         check(eng.L.mimsem_gpu_ipc_alloc(eng._h, total, C.byref(base), handle))
-        mine = dict(handle=handle.raw, layout=layout, region=region,
+        mine = dict(handle=handle.raw, layout=layout, region=region, ll_region=ll_region,
                     send_slot={(s, q): i for s in spaces for i, q in enumerate(send_peers[s])})
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
@@ -308,6 +315,24 @@ class DistributedEngine:
             epochs = torch.zeros(2, dtype=torch.int64, device=dev)   # [push counter, pull counter]
             plans[s] = (len(push), dpush, len(pull), dpull, epochs)
             self._inbox[s] = (my + off_b, stride_b, int(sum(int(r["nrows"]) for r in push)))
+        # descriptors of the in-band protocol (1-forms only): same rows, the peers' cell inboxes, separate ack words
+        s = 1
+        perm = eng.permutation(s).astype(np.int64)
+        push = np.zeros(len(send_peers[s]), dtype=dt)
+        for i, q in enumerate(send_peers[s]):
+            rows = torch.from_numpy(perm[sends[s][q]].astype(np.int32)).to(dev)
+            keep.append(rows)
+            slot_on_q, row0_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
+            off_on_q, cells_on_q = everyone[q]["ll_region"]
+            push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, cells_on_q, 0, my + (4 * MAXP + i) * 8)
+        pull = np.zeros(len(recv_peers[s]), dtype=dt)
+        for i, q in enumerate(recv_peers[s]):
+            slot, row0, n = layout[(s, q)]
+            ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
+            pull[i] = (0, n, row0, my + ll_region[0], ll_region[1], peer_base[q] + (4 * MAXP + ack_slot_on_q) * 8, 0)
+        self._ll = dict(npush=len(push), dpush=torch.from_numpy(push.view(np.uint8).copy()).to(dev), npull=len(pull),
+                        dpull=torch.from_numpy(pull.view(np.uint8).copy()).to(dev), epochs=torch.zeros(2, dtype=torch.int64, device=dev),
+                        inbox=my + ll_region[0], stride=ll_region[1], push_rows=int(sum(int(r["nrows"]) for r in push)))
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = dict(plans=plans, err=err, keep=keep, base=base, peer_base=peer_base)
         self.graph_safe = True
@@ -479,6 +504,14 @@ class DistributedEngine:
         if mode is None:
             mode = 0 if x_next is None else 1
         xp = x.data_ptr() if x_next is None else x_next.data_ptr()
+        if self.ll:
+            L = self._ll
+            push_ctas = max(1, min(148, L["push_rows"] // 16))
+            check(eng.L.mimsem_gpu_apply_M1_halo_ll(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(), xp, mode,
+                                                    L["npush"], L["dpush"].data_ptr(), L["npull"], L["dpull"].data_ptr(), L["inbox"],
+                                                    L["stride"], self.NBUF, push_ctas, L["epochs"].data_ptr(),
+                                                    self.p2p["err"].data_ptr(), eng._stream()))
+            return out
         check(eng.L.mimsem_gpu_apply_M1_halo(eng._h, lev0, nlev, nlev, scale, tpow, flags, x.data_ptr(), out.data_ptr(), xp, mode,
                                              npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, self.NBUF, push_ctas,
                                              epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))

@@ -96,6 +96,28 @@ def main():
                 ys = to_np(single, single.apply("M1", to_cols(single, f["x1"][::-1].copy() * 0.5, 1), scale=1e8, tpow=1), 1)
                 if not np.array_equal(t.cpu().numpy(), ys):
                     failures.append((what, kind, p, ne, "M1 after a pipelined sequence differs from single GPU"))
+        # back-to-back M1 (fused launch) and K (push / pull kernels) on the SAME 1-form space with no host synchronisation
+        # in between: the two ghost-refresh mechanisms must not overwrite each other's inbox copies
+        if deng.p2p is not None and nk % 2 == 0:
+            x1 = deng.scatter_from_global(f["x1"], 1)
+            u1 = deng.scatter_from_global(f["u1"], 1)
+            perm1 = torch.from_numpy(deng.engine.permutation(1).astype(np.int64)).cuda()
+            x1[perm1[deng.part.n1_owned:]] = 0.0
+            u1[perm1[deng.part.n1_owned:]] = 0.0
+            for it in range(12):
+                ya = deng.apply("M1", x1, scale=1e8, tpow=1)
+                yb = deng.apply("K", x1, coeff=u1, scale=1e8, tpow=2)
+            for yl, op, sp_ in ((ya, "M1", 1), (yb, "K", 2)):
+                N = {1: mesh.N1, 2: mesh.N2}[sp_]
+                yg = np.zeros((nk, N))
+                deng.owned_to_global(yl, sp_, yg)
+                tt = torch.from_numpy(yg).cuda()
+                dist.all_reduce(tt)
+                if rank == 0:
+                    cs = to_cols(single, f["u1"], 1) if op == "K" else None
+                    ys = to_np(single, single.apply(op, to_cols(single, f["x1"], 1), coeff=cs, scale=1e8, tpow=1 if op == "M1" else 2), sp_)
+                    if not np.array_equal(tt.cpu().numpy(), ys):
+                        failures.append((what, kind, p, ne, "back-to-back M1 / K: %s differs from single GPU" % op))
         if rank == 0:
             print("case", what, kind, p, ne, nk, "world", world, "halo bytes/rank (1-form)", deng.halo_bytes(1, f["x1"].shape[0]), flush=True)
         if deng.halo_error():

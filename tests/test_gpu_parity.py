@@ -496,5 +496,7 @@ def test_multi_gpu_partitioned_apply():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mp_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "MP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # both hand-over protocols of the fused M1 launch: in-band 16-byte cells (default) and data + flag
+    for ll in ("1", "0"):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MIMSEM_HALO_LL=ll))
+        assert r.returncode == 0 and "MP_CHECK OK" in r.stdout, (ll, r.stdout[-2000:] + r.stderr[-2000:])
