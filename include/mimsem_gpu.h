@@ -256,7 +256,9 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_s
 /*
  * End-to-end convenience with HOST buffers in the reference's per-level layout
  * (levels[k*n + dof]): copies in, converts, applies, converts back and copies out on the
- * engine's own streams.  op: 0 M1, 1 M2, 2 M0, 3 M1h, 4 K, 5 M2h, 6 M0h, 10+which incidence.
+ * engine's own streams.  op: 0 M1, 1 M2, 2 M0, 3 M1h, 4 K, 5 M2h, 6 M0h, 10+which incidence, 14 UtQW (h_coeff = u1, h_x the
+ * 2-form), 15 / 16 diagonal of M0 / M0(h) (Pvec / Phvec; h_x is read but ignored), 17 / 18 M2^-1 / M2(rho)^-1 (WmatInv / WhmatInv),
+ * 19 diagonal of M1 (MatGetDiagonal of the Umat shell).
  * h_coeff may be NULL for operators without a coefficient field.
  */
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,

@@ -1748,6 +1748,12 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         case 10 + MIMSEM_E01: sin = 1; sout = 0; break;
         case 10 + MIMSEM_E21: sin = 1; sout = 2; break;
         case 10 + MIMSEM_E12: sin = 2; sout = 1; break;
+        case 14: sin = 2; sout = 1; scoef = 1; break;       // UtQW(u1) x2
+        case 15: sin = sout = 0; break;                     // diag M0 (Pvec): h_x is ignored
+        case 16: sin = sout = 0; scoef = 2; break;          // diag M0(h) (Phvec): h_x is ignored
+        case 17: sin = sout = 2; break;                     // M2^-1 (WmatInv)
+        case 18: sin = sout = 2; scoef = 2; break;          // M2(rho)^-1 (WhmatInv)
+        case 19: sin = sout = 1; break;                     // diag M1 (MatGetDiagonal of the Umat shell): h_x is ignored
         default: return fail(MIMSEM_ERR_ARG, "unknown operator id");
     }
     const int64_t nsp[3] = {c->n0, c->n1, c->n2};
@@ -1808,6 +1814,12 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
             case 7: rc = apply_rot(c, false, levk, nl, nl, scale, tpow, flags, cc, nullptr, 0.0, xc, yc, st); break;
             case 8: rc = apply_rot(c, true, levk, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
             case 9: rc = apply_m0h_up(c, levk, nl, nl, scale, tpow, flags, cc, c->s_u2[b].p, tau, xc, yc, st); break;
+            case 14: rc = apply_m1(c, true, 0, nl, nl, scale, 0, 0, xc, cc, yc, st); break;   // Uhmat(h2 := x2) u1, no thickness
+            case 15: rc = apply_m0(c, false, levk, nl, nl, scale, tpow, flags, nullptr, nullptr, yc, st); break;
+            case 16: rc = apply_m0(c, true, levk, nl, nl, scale, tpow, flags, cc, nullptr, yc, st); break;
+            case 17: rc = solve_m2(c, false, levk, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
+            case 18: rc = solve_m2(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
+            case 19: rc = diag_m1(c, false, levk, nl, nl, scale, tpow, flags, yc, st); break;
             default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
         }
         if (rc) return rc;

@@ -11,11 +11,11 @@
 // eul/Assembly.cpp:2124-2196).  Compile with -DMIMSEM_HAVE_PETSC against real PETSc, or against
 // petsc_compat.h where PETSc is unavailable.
 //
-// Signatures follow eul/ (the 3-D code).  src/ has the same classes without the level / scale arguments
-// (src/Assembly.h:11, 23, 34, 77, 153): an eul-signature call with scale 1 on a Geom without layers is
-// that operator; the classes that exist ONLY in src/ and carry BASELINE config 2's potential-vorticity
-// upwinding (Phmat::assemble_up, RotMat_up) are mirrored below with their src/ signatures.  box/ builds
-// Umat/Wmat once in the constructor (box/Assembly.h:9-25), i.e. assemble(0, SCALE, true) here.
+// ONE header serves the three directories of the reference: the eul/ (3-D) signatures, the src/ (2-D shallow water)
+// overloads without level / scale arguments (src/Assembly.h:11, 23, 34, 77, 153) and the box/ members (box/Assembly.h:9-25:
+// Umat and Wmat carry a second matrix `Mo` and are built once, in the constructor, with the level-0 thickness -- the
+// constructors do that when the Topo is a box).  The classes that exist only in src/ and carry BASELINE config 2's
+// potential-vorticity upwinding (Phmat::assemble_up, RotMat_up) have their src/ signatures.
 #ifndef MIMSEM_HOST_ASSEMBLY_H
 #define MIMSEM_HOST_ASSEMBLY_H
 
@@ -37,9 +37,12 @@ class Umat {
         Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
         Mat M;
         Mat MT;    // unused by the live reference code (assemble_up only), kept NULL
-        void assemble(int lev, double scale, bool vert_scale);
+        Mat Mo;    // box/: the mass matrix without the vertical scaling (box/Assembly.h:13); NULL elsewhere
+        void assemble(int lev, double scale, bool vert_scale);   // eul/Assembly.cpp:51-153
+        void assemble();                                         // src/Assembly.cpp:30-124 (no layers, scale 1)
     private:
         MimsemShell* sh;
+        MimsemShell* sho;
 };
 
 // 2-form mass matrix                                                   eul/Assembly.h:17-28
@@ -49,9 +52,12 @@ class Wmat {
         ~Wmat();
         Topo* topo; Geom* geom; LagrangeEdge* e;
         Mat M;
-        void assemble(int lev, double scale, bool vert_scale);
+        Mat Mo;    // box/Assembly.h:25
+        void assemble(int lev, double scale, bool vert_scale);   // eul/Assembly.cpp:311-373
+        void assemble();                                         // src/Assembly.cpp:260-309
     private:
         MimsemShell* sh;
+        MimsemShell* sho;
 };
 
 // 0-form mass matrix                                                   eul/Assembly.h:333-347
@@ -63,6 +69,7 @@ class Pmat {
         Mat M;
         void assemble(int lev, double scale);
         void assemble_h(int lev, double scale, Vec h2);
+        void assemble();                                         // src/Assembly.cpp:324-372
     private:
         MimsemShell* sh;
 };
@@ -76,6 +83,7 @@ class Uhmat {
         Mat M;
         Mat MT;
         void assemble(Vec h2, int lev, bool const_vert, double scale);
+        void assemble(Vec h2);                                   // src/Assembly.cpp:675-734
     private:
         MimsemShell* sh;
 };
@@ -100,6 +108,7 @@ class WtQUmat {
         Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
         Mat M;
         void assemble(Vec u1, int lev, double scale);   // u1: ghosted local 1-form (VecCreateSeq(topo->n1))
+        void assemble(Vec u1);                          // src/Assembly.cpp:1172-1218
     private:
         MimsemShell* sh;
 };
@@ -165,6 +174,102 @@ class WtQdUdz_mat {
         void assemble(Vec u1, double scale);               // u1: ghosted local 1-form (eul/Assembly.cpp:1581-1640)
     private:
         MimsemShell* sh;
+};
+
+// vertical-vorticity term of the horizontal momentum equation, 2-form -> 1-form (= WtQdUdz_mat^T)   eul/Assembly.h:231-255
+class UtQWmat {
+    public:
+        UtQWmat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~UtQWmat();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(Vec u1, double scale);               // u1: ghosted local 1-form (eul/Assembly.cpp:1490-1538)
+    private:
+        MimsemShell* sh;
+};
+
+// element-block inverse of the 2-form mass matrix                      eul/Assembly.h:282-303
+class WmatInv {
+    public:
+        WmatInv(Topo* _topo, Geom* _geom, LagrangeEdge* _e);
+        ~WmatInv();
+        Topo* topo; Geom* geom; LagrangeEdge* e;
+        Mat M;
+        void assemble(int lev, double scale);              // eul/Assembly.cpp:1673-1722
+    private:
+        MimsemShell* sh;
+};
+class WhmatInv {
+    public:
+        WhmatInv(Topo* _topo, Geom* _geom, LagrangeEdge* _e);
+        ~WhmatInv();
+        Topo* topo; Geom* geom; LagrangeEdge* e;
+        Mat M;
+        void assemble(Vec rho, int lev, double scale);     // eul/Assembly.cpp:1744-1800
+    private:
+        MimsemShell* sh;
+};
+
+// lumped 0-form mass "vectors": the diagonal of Pmat / Pmat::assemble_h (exact when m == p)      eul/Assembly.h:61-87
+class Pvec {
+    public:
+        Pvec(Topo* _topo, Geom* _geom, LagrangeNode* _l);
+        ~Pvec();
+        Topo* topo; Geom* geom; LagrangeNode* l;
+        Vec vl;
+        Vec vg;
+        void assemble(int lev, double scale);              // eul/Assembly.cpp:602-628
+};
+class Phvec {
+    public:
+        Phvec(Topo* _topo, Geom* _geom, LagrangeNode* _l);
+        ~Phvec();
+        Topo* topo; Geom* geom; LagrangeNode* l;
+        Vec vl;
+        Vec vg;
+        void assemble(Vec hl, int lev, double scale);      // eul/Assembly.cpp:652-681
+};
+
+// quadrature-point values -> 0-form (start-up only: the Coriolis vector, eul/HorizSolve.cpp:141-151); host loop
+class PtQmat {
+    public:
+        PtQmat(Topo* _topo, Geom* _geom, LagrangeNode* _l);
+        ~PtQmat();
+        Topo* topo; Geom* geom; LagrangeNode* l;
+        Mat M;
+        void assemble();                                   // eul/Assembly.cpp:758-800: a no-op here, the shell is matrix-free
+    private:
+        Vec xl, yl;
+};
+
+// matrix-free twins: the action of the 1-form mass matrix (optionally weighted by a 2-form) on a ghosted local
+// velocity, accumulated in the ghosted local vector vl; vg = reverse ADD scatter of vl      eul/Assembly.h:350-369
+class Uvec {
+    public:
+        Uvec(Topo* _topo, Geom* _geom, LagrangeNode* _node, LagrangeEdge* _edge);
+        ~Uvec();
+        Topo* topo; Geom* geom; LagrangeNode* node; LagrangeEdge* edge;
+        Vec vl;
+        Vec vg;
+        void assemble(int lev, double scale, bool vert_scale, Vec vel);                                 // eul/Assembly.cpp:2124-2196
+        void assemble_hu(int lev, double scale, Vec vel, Vec rho, bool zero_and_scatter, double fac);   // eul/Assembly.cpp:2198-2279
+        void assemble_hu(int lev, double scale, bool vert_scale, Vec vel, Vec rho);                     // box/Assembly.cpp:2862-2925
+    private:
+        void accumulate(int op, int lev, double scale, int tpow, Vec vel, Vec rho);
+};
+
+// 2-form twins                                                           eul/Assembly.h:371-384
+class Wvec {
+    public:
+        Wvec(Topo* _topo, Geom* _geom, LagrangeEdge* _edge);
+        ~Wvec();
+        Topo* topo; Geom* geom; LagrangeEdge* edge;
+        Vec vg;
+        void assemble(int lev, double scale, bool vert_scale, Vec rho);    // vg = M2 rho              eul/Assembly.cpp:2441-2495
+        // vg = WtQUmat(vel2) vel1 -- the kinetic-energy form the reference's routine means to evaluate (its own loop is
+        // dead code in eul/ and mis-indexes in box/)                            eul/Assembly.cpp:2497-2545
+        void assemble_K(int lev, double scale, Vec vel1, Vec vel2);
+        void assemble_K(int lev, double scale, bool vert_scale, Vec vel1, Vec vel2);                    // box/Assembly.cpp:3047-3095
 };
 
 // edge-node incidence and its negative transpose                       eul/Assembly.h:171-177

@@ -66,6 +66,16 @@ void Geom::build(bool signed_det) {
     nDofs0G = (int)q.N0;
     loc0 = new int[n0];
     for (int i = 0; i < n0; i++) loc0[i] = q.loc0[i];
+    {
+        Vec vl, vg;
+        ISCreateGeneral(MPI_COMM_WORLD, n0, loc0, PETSC_COPY_VALUES, &is_g_0);
+        ISCreateStride(MPI_COMM_SELF, n0, 0, 1, &is_l_0);
+        VecCreateSeq(MPI_COMM_SELF, n0, &vl);
+        VecCreateMPI(MPI_COMM_WORLD, n0l, nDofs0G, &vg);
+        VecScatterCreate(vg, is_g_0, vl, is_l_0, &gtol_0);
+        VecDestroy(&vl);
+        VecDestroy(&vg);
+    }
     inds0_l = new int[(m + 1) * (m + 1)];
     inds0_g = new int[(m + 1) * (m + 1)];
 
@@ -125,6 +135,9 @@ Geom::~Geom() {
     delete[] x;
     delete[] s;
     delete[] loc0;
+    ISDestroy(&is_l_0);
+    ISDestroy(&is_g_0);
+    VecScatterDestroy(&gtol_0);
     delete[] inds0_l;
     delete[] inds0_g;
     delete[] topog;

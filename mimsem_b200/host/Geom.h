@@ -33,6 +33,8 @@ class Geom {
         double** thick;    // [nk][n0]
         double** thickInv; // [nk][n0]
         Topo* topo;
+        IS is_l_0, is_g_0;
+        VecScatter gtol_0;   // quadrature-point vectors: global (MPI) <-> ghosted local (eul/Geom.cpp:107-113)
         GaussLobatto* quad;
         LagrangeNode* node;
         LagrangeEdge* edge;

@@ -2,6 +2,7 @@
 #ifndef MIMSEM_HAVE_PETSC
 #include "petsc_compat.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +47,19 @@ struct _mimsem_Mat {
     void* ctx;
     PetscErrorCode (*mult)(Mat, Vec, Vec);
     PetscErrorCode (*destroy)(Mat);
+    PetscErrorCode (*getdiag)(Mat, Vec);
+};
+struct _mimsem_PC {
+    const char* type;
+    PetscErrorCode (*apply)(PC, Vec, Vec);
+    void* ctx;
+    int blocks;
+};
+struct _mimsem_KSP {
+    Mat A, P;
+    double rtol, abstol;
+    int maxits, its;
+    _mimsem_PC pc;
 };
 
 void PetscCompatSetRank(int rank, int size) {
@@ -175,11 +189,13 @@ PetscErrorCode MatCreateShell(MPI_Comm, PetscInt, PetscInt, PetscInt, PetscInt, 
     (*A)->ctx = ctx;
     (*A)->mult = NULL;
     (*A)->destroy = NULL;
+    (*A)->getdiag = NULL;
     return 0;
 }
 PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void)) {
     if (op == MATOP_MULT) A->mult = (PetscErrorCode(*)(Mat, Vec, Vec))f;
     else if (op == MATOP_DESTROY) A->destroy = (PetscErrorCode(*)(Mat))f;
+    else if (op == MATOP_GET_DIAGONAL) A->getdiag = (PetscErrorCode(*)(Mat, Vec))f;
     else return 56;   /* PETSC_ERR_SUP */
     return 0;
 }
@@ -191,6 +207,159 @@ PetscErrorCode MatDestroy(Mat* A) {
         delete *A;
     }
     *A = NULL;
+    return 0;
+}
+PetscErrorCode MatGetDiagonal(Mat A, Vec d) { return A->getdiag ? A->getdiag(A, d) : 56; }
+
+// ---------------------------------------------------------------------------------------------- vector algebra
+static double* own_of(Vec v) { return v->mpi ? v->g->a.data() + rstart_of(v) : v->local.data(); }
+static void settle(Vec v) { if (v->mpi) v->g->flush(); }
+PetscErrorCode VecSet(Vec v, PetscScalar a) {
+    settle(v);
+    double* p = own_of(v);
+    for (int i = 0; i < v->n; i++) p[i] = a;
+    return 0;
+}
+PetscErrorCode VecCopy(Vec x, Vec y) {
+    settle(x); settle(y);
+    std::memcpy(own_of(y), own_of(x), sizeof(double) * x->n);
+    return 0;
+}
+PetscErrorCode VecDuplicate(Vec x, Vec* y) { return x->mpi ? VecCreateMPI(MPI_COMM_WORLD, x->n, x->N, y) : VecCreateSeq(MPI_COMM_SELF, x->n, y); }
+PetscErrorCode VecScale(Vec v, PetscScalar a) {
+    settle(v);
+    double* p = own_of(v);
+    for (int i = 0; i < v->n; i++) p[i] *= a;
+    return 0;
+}
+PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x) {
+    settle(x); settle(y);
+    double* py = own_of(y);
+    const double* px = own_of(x);
+    for (int i = 0; i < y->n; i++) py[i] += a * px[i];
+    return 0;
+}
+PetscErrorCode VecAYPX(Vec y, PetscScalar a, Vec x) {
+    settle(x); settle(y);
+    double* py = own_of(y);
+    const double* px = own_of(x);
+    for (int i = 0; i < y->n; i++) py[i] = px[i] + a * py[i];
+    return 0;
+}
+PetscErrorCode VecPointwiseMult(Vec w, Vec x, Vec y) {
+    settle(x); settle(y); settle(w);
+    double* pw = own_of(w);
+    const double *px = own_of(x), *py = own_of(y);
+    for (int i = 0; i < w->n; i++) pw[i] = px[i] * py[i];
+    return 0;
+}
+PetscErrorCode VecPointwiseDivide(Vec w, Vec x, Vec y) {
+    settle(x); settle(y); settle(w);
+    double* pw = own_of(w);
+    const double *px = own_of(x), *py = own_of(y);
+    for (int i = 0; i < w->n; i++) pw[i] = px[i] / py[i];
+    return 0;
+}
+// reductions are collective: over the whole vector (every in-process rank has finished its phase when one of them asks)
+PetscErrorCode VecDot(Vec x, Vec y, PetscScalar* val) {
+    settle(x); settle(y);
+    const double *px = x->mpi ? x->g->a.data() : x->local.data(), *py = y->mpi ? y->g->a.data() : y->local.data();
+    double s = 0.0;
+    for (int i = 0; i < x->N; i++) s += px[i] * py[i];
+    *val = s;
+    return 0;
+}
+PetscErrorCode VecNorm(Vec x, NormType t, PetscReal* val) {
+    settle(x);
+    const double* px = x->mpi ? x->g->a.data() : x->local.data();
+    double s = 0.0;
+    for (int i = 0; i < x->N; i++) {
+        const double a = std::fabs(px[i]);
+        if (t == NORM_1) s += a;
+        else if (t == NORM_INFINITY) s = a > s ? a : s;
+        else s += a * a;
+    }
+    *val = (t == NORM_1 || t == NORM_INFINITY) ? s : std::sqrt(s);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- KSP (one rank)
+PetscErrorCode KSPCreate(MPI_Comm, KSP* ksp) {
+    KSP k = new _mimsem_KSP;
+    k->A = k->P = NULL;
+    k->rtol = 1.0e-5;   // PETSc's defaults
+    k->abstol = 1.0e-50;
+    k->maxits = 10000;
+    k->its = 0;
+    k->pc.type = PCJACOBI;
+    k->pc.apply = NULL;
+    k->pc.ctx = NULL;
+    k->pc.blocks = 0;
+    *ksp = k;
+    return 0;
+}
+PetscErrorCode KSPDestroy(KSP* ksp) { delete *ksp; *ksp = NULL; return 0; }
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P) { ksp->A = A; ksp->P = P; return 0; }
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal, PetscInt maxits) {
+    if (rtol != PETSC_DEFAULT) ksp->rtol = rtol;
+    if (abstol != PETSC_DEFAULT) ksp->abstol = abstol;
+    if (maxits != PETSC_DEFAULT) ksp->maxits = maxits;
+    return 0;
+}
+PetscErrorCode KSPSetType(KSP, KSPType) { return 0; }
+PetscErrorCode KSPSetOptionsPrefix(KSP, const char*) { return 0; }
+PetscErrorCode KSPSetFromOptions(KSP) { return 0; }
+PetscErrorCode KSPGetPC(KSP ksp, PC* pc) { *pc = &ksp->pc; return 0; }
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt* its) { *its = ksp->its; return 0; }
+PetscErrorCode PCSetType(PC pc, PCType type) { pc->type = type; return 0; }
+PetscErrorCode PCBJacobiSetTotalBlocks(PC pc, PetscInt blocks, const PetscInt*) { pc->blocks = blocks; return 0; }
+PetscErrorCode PCShellSetApply(PC pc, PetscErrorCode (*apply)(PC, Vec, Vec)) { pc->apply = apply; return 0; }
+PetscErrorCode PCShellSetContext(PC pc, void* ctx) { pc->ctx = ctx; return 0; }
+PetscErrorCode PCShellGetContext(PC pc, void* ctx) { *(void**)ctx = pc->ctx; return 0; }
+
+// preconditioned conjugate gradients on the (symmetric positive definite) shell operator
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
+    if (g_size != 1) {
+        std::fprintf(stderr, "petsc_compat: KSPSolve needs real PETSc when more than one rank is played in-process\n");
+        std::abort();
+    }
+    Vec r, z, p, q, d = NULL;
+    VecDuplicate(b, &r); VecDuplicate(b, &z); VecDuplicate(b, &p); VecDuplicate(b, &q);
+    const bool shell_pc = ksp->pc.apply != NULL;
+    if (!shell_pc && ksp->P && ksp->P->getdiag) {
+        VecDuplicate(b, &d);
+        MatGetDiagonal(ksp->P, d);
+    }
+    auto precond = [&](Vec in, Vec out) {
+        if (shell_pc) ksp->pc.apply(&ksp->pc, in, out);
+        else if (d) VecPointwiseDivide(out, in, d);
+        else VecCopy(in, out);
+    };
+    double bn, rn, rz, rz_new, pq;
+    VecNorm(b, NORM_2, &bn);
+    MatMult(ksp->A, x, q);             // nonzero initial guess, as PETSc's KSPSolve with the caller's x
+    VecCopy(b, r);
+    VecAXPY(r, -1.0, q);
+    precond(r, z);
+    VecCopy(z, p);
+    VecDot(r, z, &rz);
+    ksp->its = 0;
+    VecNorm(r, NORM_2, &rn);
+    while (rn > ksp->rtol * bn && rn > ksp->abstol && ksp->its < ksp->maxits) {
+        MatMult(ksp->A, p, q);
+        VecDot(p, q, &pq);
+        const double alpha = rz / pq;
+        VecAXPY(x, alpha, p);
+        VecAXPY(r, -alpha, q);
+        precond(r, z);
+        VecDot(r, z, &rz_new);
+        VecAYPX(p, rz_new / rz, z);
+        rz = rz_new;
+        VecNorm(r, NORM_2, &rn);
+        ksp->its++;
+    }
+    VecDestroy(&r); VecDestroy(&z); VecDestroy(&p); VecDestroy(&q);
+    if (d) VecDestroy(&d);
     return 0;
 }
 #endif

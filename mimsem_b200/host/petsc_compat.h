@@ -14,7 +14,9 @@
 #include <petsc.h>
 #else
 
+#include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 typedef double PetscScalar;
 typedef double PetscReal;
@@ -29,12 +31,24 @@ typedef int MPI_Comm;
 typedef enum { NOT_SET_VALUES = 0, INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
 typedef enum { SCATTER_FORWARD = 0, SCATTER_REVERSE = 1 } ScatterMode;
 typedef enum { PETSC_COPY_VALUES = 0, PETSC_OWN_POINTER = 1, PETSC_USE_POINTER = 2 } PetscCopyMode;
-typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_DESTROY = 60 } MatOperation;
+typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_GET_DIAGONAL = 17, MATOP_DESTROY = 60 } MatOperation;
+typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
+#define PETSC_DEFAULT (-2)
+typedef const char* KSPType;
+typedef const char* PCType;
+#define KSPGMRES "gmres"
+#define KSPCG "cg"
+#define PCBJACOBI "bjacobi"
+#define PCJACOBI "jacobi"
+#define PCSHELL "shell"
+#define PCNONE "none"
 
 typedef struct _mimsem_Vec* Vec;
 typedef struct _mimsem_Mat* Mat;
 typedef struct _mimsem_IS* IS;
 typedef struct _mimsem_VecScatter* VecScatter;
+typedef struct _mimsem_KSP* KSP;
+typedef struct _mimsem_PC* PC;
 
 /* which of the R in-process ranks is executing (compat only) */
 void PetscCompatSetRank(int rank, int size);
@@ -58,6 +72,18 @@ PetscErrorCode VecGetLocalSize(Vec v, PetscInt* n);
 PetscErrorCode VecGetSize(Vec v, PetscInt* N);
 PetscErrorCode VecGetOwnershipRange(Vec v, PetscInt* lo, PetscInt* hi);
 
+/* vector algebra on the calling rank's owned slice; VecDot / VecNorm reduce over the WHOLE vector (a collective) */
+PetscErrorCode VecSet(Vec v, PetscScalar a);
+PetscErrorCode VecCopy(Vec x, Vec y);
+PetscErrorCode VecDuplicate(Vec x, Vec* y);
+PetscErrorCode VecScale(Vec v, PetscScalar a);
+PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x);              /* y += a x */
+PetscErrorCode VecAYPX(Vec y, PetscScalar a, Vec x);              /* y = x + a y */
+PetscErrorCode VecDot(Vec x, Vec y, PetscScalar* val);
+PetscErrorCode VecNorm(Vec x, NormType t, PetscReal* val);
+PetscErrorCode VecPointwiseMult(Vec w, Vec x, Vec y);             /* w = x .* y */
+PetscErrorCode VecPointwiseDivide(Vec w, Vec x, Vec y);           /* w = x ./ y */
+
 PetscErrorCode VecScatterCreate(Vec x, IS ix, Vec y, IS iy, VecScatter* sc);
 PetscErrorCode VecScatterBegin(VecScatter sc, Vec x, Vec y, InsertMode addv, ScatterMode mode);
 PetscErrorCode VecScatterEnd(VecScatter sc, Vec x, Vec y, InsertMode addv, ScatterMode mode);
@@ -68,6 +94,27 @@ PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void));
 PetscErrorCode MatShellGetContext(Mat A, void* ctx);
 PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatDestroy(Mat* A);
+PetscErrorCode MatGetDiagonal(Mat A, Vec d);                      /* MATOP_GET_DIAGONAL of the shell */
+
+/* Krylov solver on a shell operator.  Without PETSc this is a (diagonally preconditioned, when the shell offers
+ * MATOP_GET_DIAGONAL, or PCSHELL-preconditioned) conjugate-gradient iteration for ONE rank -- the operators of the hot
+ * path are symmetric positive definite mass matrices; GMRES / block-Jacobi requests are accepted and mapped onto it.
+ * With several in-process ranks KSPSolve is not available (a collective cannot be played rank after rank). */
+PetscErrorCode KSPCreate(MPI_Comm comm, KSP* ksp);
+PetscErrorCode KSPDestroy(KSP* ksp);
+PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P);
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt maxits);
+PetscErrorCode KSPSetType(KSP ksp, KSPType type);
+PetscErrorCode KSPSetOptionsPrefix(KSP ksp, const char* prefix);
+PetscErrorCode KSPSetFromOptions(KSP ksp);
+PetscErrorCode KSPGetPC(KSP ksp, PC* pc);
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x);
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt* its);
+PetscErrorCode PCSetType(PC pc, PCType type);
+PetscErrorCode PCBJacobiSetTotalBlocks(PC pc, PetscInt blocks, const PetscInt lens[]);
+PetscErrorCode PCShellSetApply(PC pc, PetscErrorCode (*apply)(PC, Vec, Vec));
+PetscErrorCode PCShellSetContext(PC pc, void* ctx);
+PetscErrorCode PCShellGetContext(PC pc, void* ctx);
 
 #endif /* MIMSEM_HAVE_PETSC */
 #endif

@@ -536,6 +536,46 @@ double ref_uvec_apply(void* hv, int lev, double scale, int vert_scale, const dou
     }
     return now() - t0;
 }
+
+/*
+ * The reference's own matrix-free twin of the flux form, exactly as eul/HorizSolve.cpp:298-306 drives it: per rank
+ * Uvec::assemble_hu(lev, scale, u_a, h_a, false, fac_a) for nterms (velocity, density, factor) triples accumulated in
+ * the rank's ghosted local vector vl, then the reverse ADD scatter -- merged here over the emulated ranks.
+ * u[t] are global 1-form vectors (gathered through loc1), h[t] global 2-form vectors (each rank reads its owned block).
+ */
+double ref_uvec_assemble_hu(void* hv, int lev, double scale, int nterms, const double* u, const double* h2, const double* fac,
+                            double* y, int nthreads) {
+    Ref* h = (Ref*)hv;
+    Topo* t0p = h->r[0].topo;
+    const long N1 = t0p->nDofs1G, N2 = t0p->nDofs2G;
+    std::vector<std::vector<double> > part(h->nranks);
+    double t0 = now();
+    for_ranks(h, nthreads, [&](int rk) {
+        RankObjs& o = h->r[rk];
+        Topo* topo = o.topo;
+        Uvec* A = new Uvec(topo, o.geom, o.node, o.edge);
+        VecZeroEntries(A->vl);
+        VecZeroEntries(A->vg);
+        for (int t = 0; t < nterms; t++) {
+            Vec v1, r2;
+            VecCreateSeq(MPI_COMM_SELF, topo->n1, &v1);
+            VecCreateSeq(MPI_COMM_SELF, topo->n2, &r2);
+            for (int i = 0; i < topo->n1; i++) v1->a[i] = u[(size_t)t * N1 + topo->loc1[i]];
+            for (int i = 0; i < topo->n2; i++) r2->a[i] = h2[(size_t)t * N2 + (size_t)topo->pi * topo->n2 + i];   // faces: global = local + pi n2
+            A->assemble_hu(lev, scale, v1, r2, false, fac[t]);
+            VecDestroy(&v1);
+            VecDestroy(&r2);
+        }
+        part[rk].assign(A->vl->a, A->vl->a + topo->n1);
+        delete A;
+    });
+    for (long i = 0; i < N1; i++) y[i] = 0.0;
+    for (int rk = 0; rk < h->nranks; rk++) {
+        Topo* topo = h->r[rk].topo;
+        for (int i = 0; i < topo->n1; i++) y[topo->loc1[i]] += part[rk][i];
+    }
+    return now() - t0;
+}
 #endif
 
 }  // extern "C"

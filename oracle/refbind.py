@@ -63,6 +63,8 @@ class Reference:
         if variant == "eul":
             L.ref_uvec_apply.restype = C.c_double
             L.ref_uvec_apply.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, C.c_int]
+            L.ref_uvec_assemble_hu.restype = C.c_double
+            L.ref_uvec_assemble_hu.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, _dp, _dp, C.c_int]
         self.nthreads = nthreads or min(os.cpu_count() or 1, nranks)
         self.nranks = nranks
         self.nk = nk
@@ -168,3 +170,14 @@ class Reference:
         y = np.zeros(self.N1)
         s = self.lib.ref_uvec_apply(self.h, lev, scale, int(bool(vert_scale)), _d(x), _d(y), self.nthreads)
         return y, s
+
+    def uvec_assemble_hu(self, us, hs, facs, lev=0, scale=1.0):
+        """The reference's own Uvec::assemble_hu accumulated over (velocity, density, factor) triples and scattered
+        (eul/Assembly.cpp:2198-2279, driven as eul/HorizSolve.cpp:298-306 does); eul only.  Returns the global 1-form."""
+        us = np.ascontiguousarray(us, dtype=np.float64)
+        hs = np.ascontiguousarray(hs, dtype=np.float64)
+        facs = np.ascontiguousarray(facs, dtype=np.float64)
+        assert us.shape == (len(facs), self.N1) and hs.shape == (len(facs), self.N2)
+        y = np.zeros(self.N1)
+        self.lib.ref_uvec_assemble_hu(self.h, lev, scale, len(facs), _d(us), _d(hs), _d(facs), _d(y), self.nthreads)
+        return y

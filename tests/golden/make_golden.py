@@ -91,6 +91,10 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
     u1_up = u1 * 1.0e-3                                  # advecting velocity: departure points move ~0.1 element widths
     up_fac, up_dt = 0.5, 300.0                           # UP_TAU (src/SWEqn_Picard.cpp:30) and a time step
     out.update(q0=q0, u1_up=u1_up, up_fac=up_fac, up_dt=up_dt)
+    # second velocity / density of the flux diagnostic (drawn last, see above)
+    x1b = rng.uniform(-1, 1, (nk, N1))
+    h2b = rng.uniform(0.5, 1.5, (nk, N2)) * 1.0e4
+    out.update(x1b=x1b, h2b=h2b)
 
     def run(op, x, **kw):
         ys = []
@@ -116,6 +120,11 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
         out["y_Ut_mat_h"] = run("Ut_mat_h", x1, c2=h2)
         out["y_WtQdUdz_mat"] = run("WtQdUdz_mat", x1, c1=u1)
         out["y_UtQWmat"] = run("UtQWmat", x2, c1=u1)
+        # the reference's own matrix-free twin, driven as diagnose_fluxes does (eul/HorizSolve.cpp:298-306):
+        # vl = sum of assemble_hu(u_a, h_b, fac), then the reverse ADD scatter
+        out["y_Uvec_hu"] = np.array([R.uvec_assemble_hu([x1[lev], x1[lev], x1b[lev], x1b[lev]], [h2[lev], h2b[lev], h2[lev], h2b[lev]],
+                                                        [1.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 1.0 / 3.0], lev=lev, scale=scale) for lev in range(nk)])
+        out["y_Uvec"] = np.array([R.uvec_apply(x1[lev], lev=lev, scale=scale)[0] for lev in range(nk)])
     elif variant == "src":
         out["y_Umat"] = run("Umat", x1)
         out["y_Wmat"] = run("Wmat", x2)

@@ -466,6 +466,25 @@ def test_remaining_coefficient_operators(fname, p, ne, tmp_path):
         assert rel_l2(xwr[lev], spla.spsolve(O.wmat(lev, s, 1, rho=g["h2"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < 1e-8, ("WhmatInv, rough", lev)
 
 
+@pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
+def test_matrix_free_twins_vs_reference_uvec(fname, p, ne):
+    """Uvec::assemble and Uvec::assemble_hu (eul/Assembly.cpp:2124-2279) -- golden vectors produced by the reference's OWN
+    matrix-free routines, driven as diagnose_fluxes drives them (eul/HorizSolve.cpp:298-306: four (velocity, density,
+    factor) terms accumulated, then the reverse ADD scatter).  On the device the four terms are two M1(h) applies
+    (the form is bilinear): F(h1)(u1/3 + u2/6) + F(h2)(u1/6 + u2/3)."""
+    g = golden(fname)
+    mesh, eng = _engine("sphere", p, ne, thick=g["thick"])
+    s = float(g["scale"])
+    assert rel_l2(_apply(eng, "M1", g["x1"], scale=s, tpow=1), g["y_Uvec"]) < TOL
+    ya = _apply(eng, "M1h", g["x1"] / 3.0 + g["x1b"] / 6.0, g["h2"], scale=s, tpow=2)
+    yb = _apply(eng, "M1h", g["x1"] / 6.0 + g["x1b"] / 3.0, g["h2b"], scale=s, tpow=2)
+    assert rel_l2(ya + yb, g["y_Uvec_hu"]) < TOL, rel_l2(ya + yb, g["y_Uvec_hu"])
+    # term by term, as the host class Uvec does it
+    terms = [(g["x1"], g["h2"], 1 / 3), (g["x1"], g["h2b"], 1 / 6), (g["x1b"], g["h2"], 1 / 6), (g["x1b"], g["h2b"], 1 / 3)]
+    y4 = sum(_apply(eng, "M1h", u, h, scale=s * f, tpow=2) for u, h, f in terms)
+    assert rel_l2(y4, g["y_Uvec_hu"]) < TOL
+
+
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 4, 30), ("sphere", 4, 3, 60), ("box", 3, 5, 7)])
 def test_l2vecs_relabelling_bit_exact(kind, p, ne, nk):
     """L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): vz[e][k*p^2 + i] = vh[k][elInds2_l(e)[i]], bit for bit."""

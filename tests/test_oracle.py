@@ -45,6 +45,12 @@ def test_oracle_eul_vs_golden():
         assert rel_l2(O.utqwmat(g["u1"][lev], s) @ g["x2"][lev], g["y_UtQWmat"][lev]) < TOL
         if lev < nk - 1:
             assert rel_l2(O.ut_mat(lev, s) @ g["x1"][lev], g["y_Ut_mat"][lev]) < TOL
+        # the reference's matrix-free twins (Uvec::assemble, Uvec::assemble_hu as diagnose_fluxes drives it) against its
+        # own matrices: vl = 1/3 F(h1) u1 + 1/6 F(h2) u1 + 1/6 F(h1) u2 + 1/3 F(h2) u2
+        assert rel_l2(O.umat(lev, s, 1) @ g["x1"][lev], g["y_Uvec"][lev]) < TOL
+        F1, F2 = O.umat(lev, s, 1, h2=g["h2"][lev], tpow_h=1), O.umat(lev, s, 1, h2=g["h2b"][lev], tpow_h=1)
+        hu = F1 @ (g["x1"][lev] / 3.0 + g["x1b"][lev] / 6.0) + F2 @ (g["x1"][lev] / 6.0 + g["x1b"][lev] / 3.0)
+        assert rel_l2(hu, g["y_Uvec_hu"][lev]) < TOL
     E10, E01 = O.e10()
     E21, E12 = O.e21()
     for nm, A in (("E10", E10), ("E01", E01), ("E21", E21), ("E12", E12)):
