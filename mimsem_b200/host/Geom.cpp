@@ -222,3 +222,125 @@ void Geom::interp2_g(int ex, int ey, int px, int py, double* vec, double* val) {
     interp2_l(ex, ey, px, py, vec, &l);
     val[0] = l / det[el][q];
 }
+
+// ------------------------------------------------------------------------------------------------
+// field writers (eul/Geom.cpp:419-631, the non-HDF5 branch)
+
+namespace {
+void view_to(Vec v, const char* name, bool binary) {
+    PetscViewer viewer;
+    if (binary) PetscViewerBinaryOpen(MPI_COMM_WORLD, name, FILE_MODE_WRITE, &viewer);
+    else PetscViewerASCIIOpen(MPI_COMM_WORLD, name, &viewer);
+    VecView(v, viewer);
+    PetscViewerDestroy(&viewer);
+}
+}  // namespace
+
+void Geom::write0(Vec q, char* fieldname, int tstep, int lev) {
+    const int mp1 = quad->n + 1, mp12 = mp1 * mp1;
+    char filename[200];
+    Vec ql, qxl, qxg;
+    PetscScalar *qArray, *qxArray;
+    VecCreateSeq(MPI_COMM_SELF, topo->n0, &ql);
+    VecScatterBegin(topo->gtol_0, q, ql, INSERT_VALUES, SCATTER_FORWARD);
+    VecScatterEnd(topo->gtol_0, q, ql, INSERT_VALUES, SCATTER_FORWARD);
+    VecCreateSeq(MPI_COMM_SELF, n0, &qxl);
+    VecCreateMPI(MPI_COMM_WORLD, n0l, nDofs0G, &qxg);
+    VecGetArray(ql, &qArray);
+    VecGetArray(qxl, &qxArray);
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            int* inds0 = elInds0_l(ex, ey);
+            for (int ii = 0; ii < mp12; ii++) {
+                double val;
+                interp0(ex, ey, ii % mp1, ii / mp1, qArray, &val);
+                qxArray[inds0[ii]] = val / thick[lev][inds0[ii]];   // piecewise constant in the vertical
+            }
+        }
+    VecRestoreArray(ql, &qArray);
+    VecRestoreArray(qxl, &qxArray);
+    VecScatterBegin(gtol_0, qxl, qxg, INSERT_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(gtol_0, qxl, qxg, INSERT_VALUES, SCATTER_REVERSE);
+    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.dat", fieldname, lev, tstep);
+    view_to(qxg, filename, false);
+    VecDestroy(&ql);
+    VecDestroy(&qxl);
+    VecDestroy(&qxg);
+}
+
+void Geom::write1(Vec u, char* fieldname, int tstep, int lev) {
+    const int mp1 = quad->n + 1, mp12 = mp1 * mp1;
+    char filename[200];
+    Vec ul, uxl, vxl, uxg;
+    PetscScalar *uArray, *uxArray, *vxArray;
+    VecCreateSeq(MPI_COMM_SELF, topo->n1, &ul);
+    VecScatterBegin(topo->gtol_1, u, ul, INSERT_VALUES, SCATTER_FORWARD);
+    VecScatterEnd(topo->gtol_1, u, ul, INSERT_VALUES, SCATTER_FORWARD);
+    VecCreateSeq(MPI_COMM_SELF, n0, &uxl);
+    VecCreateSeq(MPI_COMM_SELF, n0, &vxl);
+    VecCreateMPI(MPI_COMM_WORLD, n0l, nDofs0G, &uxg);
+    VecGetArray(ul, &uArray);
+    VecGetArray(uxl, &uxArray);
+    VecGetArray(vxl, &vxArray);
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            int* inds0 = elInds0_l(ex, ey);
+            for (int ii = 0; ii < mp12; ii++) {
+                double val[2];
+                interp1_g(ex, ey, ii % mp1, ii / mp1, uArray, val);
+                uxArray[inds0[ii]] = val[0] / thick[lev][inds0[ii]];
+                vxArray[inds0[ii]] = val[1] / thick[lev][inds0[ii]];
+            }
+        }
+    VecRestoreArray(uxl, &uxArray);
+    VecRestoreArray(vxl, &vxArray);
+    VecRestoreArray(ul, &uArray);
+    VecZeroEntries(uxg);
+    VecScatterBegin(gtol_0, uxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(gtol_0, uxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
+    std::snprintf(filename, sizeof filename, "output/%s_x_%.3u_%.4u.dat", fieldname, lev, tstep);
+    view_to(uxg, filename, false);
+    VecZeroEntries(uxg);
+    VecScatterBegin(gtol_0, vxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(gtol_0, vxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
+    std::snprintf(filename, sizeof filename, "output/%s_y_%.3u_%.4u.dat", fieldname, lev, tstep);
+    view_to(uxg, filename, false);
+    VecDestroy(&ul);
+    VecDestroy(&uxl);
+    VecDestroy(&vxl);
+    VecDestroy(&uxg);
+    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.vec", fieldname, lev, tstep);
+    view_to(u, filename, true);   // also the vector itself
+}
+
+void Geom::write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale) {
+    const int mp1 = quad->n + 1, mp12 = mp1 * mp1;
+    char filename[200];
+    Vec hxl, hxg;
+    PetscScalar *hxArray, *hArray;
+    VecCreateSeq(MPI_COMM_SELF, n0, &hxl);
+    VecCreateMPI(MPI_COMM_WORLD, n0l, nDofs0G, &hxg);
+    VecZeroEntries(hxg);
+    VecGetArray(h, &hArray);
+    VecGetArray(hxl, &hxArray);
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            int* inds0 = elInds0_l(ex, ey);
+            for (int ii = 0; ii < mp12; ii++) {
+                double val;
+                interp2_g(ex, ey, ii % mp1, ii / mp1, hArray, &val);
+                if (vert_scale) val /= thick[lev][inds0[ii]];
+                hxArray[inds0[ii]] = val;
+            }
+        }
+    VecRestoreArray(h, &hArray);
+    VecRestoreArray(hxl, &hxArray);
+    VecScatterBegin(gtol_0, hxl, hxg, INSERT_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(gtol_0, hxl, hxg, INSERT_VALUES, SCATTER_REVERSE);
+    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.dat", fieldname, lev, tstep);
+    view_to(hxg, filename, false);
+    VecDestroy(&hxg);
+    VecDestroy(&hxl);
+    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.vec", fieldname, lev, tstep);
+    view_to(h, filename, true);
+}

@@ -1,6 +1,6 @@
 // Host mirror of the reference's Geom (eul/Geom.h:1-56): coordinates, Jacobians, determinants, layer
 // thicknesses and the DOF -> quadrature-point interpolations, with the reference's member names.
-// Field writers (write0/1/2, HDF5) are outside the hot path and not provided.
+// The field writers write0/1/2 produce the ASCII / PETSc-binary files of a build without HDF5.
 #ifndef MIMSEM_HOST_GEOM_H
 #define MIMSEM_HOST_GEOM_H
 
@@ -44,6 +44,11 @@ class Geom {
         void interp1_g(int ex, int ey, int px, int py, double* vec, double* val);
         void interp2_g(int ex, int ey, int px, int py, double* vec, double* val);
         void initTopog(TopogFunc* ft, LevelFunc* fl);
+        // fields interpolated to the quadrature points -> output/<field>_<lev>_<step>.dat (ASCII VecView) and, for 1- and
+        // 2-forms, the vector itself -> .vec (PETSc binary, the restart format)        eul/Geom.cpp:419-631
+        void write0(Vec q, char* fieldname, int tstep, int lev);
+        void write1(Vec u, char* fieldname, int tstep, int lev);
+        void write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale);
         int* elInds0_l(int ex, int ey);
         int* elInds0_g(int ex, int ey);
         // flat copies for the device engine

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -17,6 +18,7 @@ struct GlobalVec {            // one collective VecCreateMPI across all in-proce
     std::vector<double> a;    // the whole vector
     std::vector<int> nlocal;  // owned size per rank (-1: that rank has not created it yet)
     int refs = 0;
+    int created = 0;          // ranks that have made this collective call so far (storage lives until all have come and gone)
     // Reverse ADD scatters are collective: under MPI every rank zeroes / fills its slice BEFORE any remote
     // contribution lands.  With the ranks played one after the other the contributions are therefore deferred
     // until somebody reads the vector.
@@ -110,6 +112,7 @@ PetscErrorCode VecCreateMPI(MPI_Comm, PetscInt n, PetscInt N, Vec* v) {
     }
     g->nlocal[g_rank] = n;
     g->refs++;
+    g->created++;
     Vec x = new _mimsem_Vec;
     x->mpi = true; x->n = n; x->N = N; x->rank = g_rank; x->g = g; x->seq = seq;
     *v = x;
@@ -117,7 +120,9 @@ PetscErrorCode VecCreateMPI(MPI_Comm, PetscInt n, PetscInt N, Vec* v) {
 }
 PetscErrorCode VecDestroy(Vec* v) {
     if (*v) {
-        if ((*v)->mpi && --(*v)->g->refs == 0) {
+        // a temporary created and destroyed inside a collective routine (Geom::write*, ...) is visited by the in-process
+        // ranks one after the other: its storage must outlive the ranks that are already done with it
+        if ((*v)->mpi && --(*v)->g->refs == 0 && (*v)->g->created >= g_size) {
             g_globals.erase((*v)->seq);
             delete (*v)->g;
         }
@@ -280,6 +285,76 @@ PetscErrorCode VecNorm(Vec x, NormType t, PetscReal* val) {
         else s += a * a;
     }
     *val = (t == NORM_1 || t == NORM_INFINITY) ? s : std::sqrt(s);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- viewers
+struct _mimsem_Viewer {
+    std::string name;
+    bool binary, write;
+};
+PetscErrorCode PetscViewerBinaryOpen(MPI_Comm, const char* name, PetscFileMode mode, PetscViewer* viewer) {
+    *viewer = new _mimsem_Viewer{name, true, mode == FILE_MODE_WRITE};
+    return 0;
+}
+PetscErrorCode PetscViewerASCIIOpen(MPI_Comm, const char* name, PetscViewer* viewer) {
+    *viewer = new _mimsem_Viewer{name, false, true};
+    return 0;
+}
+PetscErrorCode PetscViewerDestroy(PetscViewer* viewer) { delete *viewer; *viewer = NULL; return 0; }
+static void put_be32(FILE* f, unsigned v) {
+    unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v};
+    std::fwrite(b, 1, 4, f);
+}
+static void put_be64(FILE* f, double d) {
+    unsigned long long v;
+    std::memcpy(&v, &d, 8);
+    unsigned char b[8];
+    for (int i = 0; i < 8; i++) b[i] = (unsigned char)(v >> (56 - 8 * i));
+    std::fwrite(b, 1, 8, f);
+}
+PetscErrorCode VecView(Vec v, PetscViewer viewer) {
+    settle(v);
+    if (v->mpi && g_rank != g_size - 1) return 0;   // collective: the last rank to arrive writes the whole vector
+    const double* a = v->mpi ? v->g->a.data() : v->local.data();
+    FILE* f = std::fopen(viewer->name.c_str(), viewer->binary ? "wb" : "w");
+    if (!f) return 65;   /* PETSC_ERR_FILE_OPEN */
+    if (viewer->binary) {
+        put_be32(f, 1211214u);   /* VEC_FILE_CLASSID */
+        put_be32(f, (unsigned)v->N);
+        for (int i = 0; i < v->N; i++) put_be64(f, a[i]);
+    } else {
+        std::fprintf(f, "Vec Object: %d MPI processes\n  type: %s\n", g_size, v->mpi ? "mpi" : "seq");
+        int lo = 0;
+        for (int r = 0; r < (v->mpi ? g_size : 1); r++) {
+            const int n = v->mpi ? v->g->nlocal[r] : v->n;
+            if (v->mpi) std::fprintf(f, "Process [%d]\n", r);
+            for (int i = 0; i < n; i++) std::fprintf(f, "%.16g\n", a[lo + i]);
+            lo += n;
+        }
+    }
+    std::fclose(f);
+    return 0;
+}
+PetscErrorCode VecLoad(Vec v, PetscViewer viewer) {
+    FILE* f = std::fopen(viewer->name.c_str(), "rb");
+    if (!f) return 65;
+    unsigned char h[8];
+    if (std::fread(h, 1, 8, f) != 8) { std::fclose(f); return 66; }
+    const unsigned cid = ((unsigned)h[0] << 24) | ((unsigned)h[1] << 16) | ((unsigned)h[2] << 8) | h[3];
+    const unsigned N = ((unsigned)h[4] << 24) | ((unsigned)h[5] << 16) | ((unsigned)h[6] << 8) | h[7];
+    if (cid != 1211214u || (int)N != v->N) { std::fclose(f); return 79; }   /* PETSC_ERR_FILE_UNEXPECTED */
+    const int lo = v->mpi ? rstart_of(v) : 0;
+    std::fseek(f, 8 + 8L * lo, SEEK_SET);
+    double* dst = own_of(v);
+    for (int i = 0; i < v->n; i++) {
+        unsigned char b[8];
+        if (std::fread(b, 1, 8, f) != 8) { std::fclose(f); return 66; }
+        unsigned long long u = 0;
+        for (int j = 0; j < 8; j++) u = (u << 8) | b[j];
+        std::memcpy(&dst[i], &u, 8);
+    }
+    std::fclose(f);
     return 0;
 }
 

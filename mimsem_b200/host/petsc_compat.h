@@ -49,6 +49,10 @@ typedef struct _mimsem_IS* IS;
 typedef struct _mimsem_VecScatter* VecScatter;
 typedef struct _mimsem_KSP* KSP;
 typedef struct _mimsem_PC* PC;
+typedef struct _mimsem_Viewer* PetscViewer;
+typedef enum { FILE_MODE_READ = 0, FILE_MODE_WRITE = 1 } PetscFileMode;
+#define PETSC_COMM_WORLD MPI_COMM_WORLD
+#define PETSC_COMM_SELF MPI_COMM_SELF
 
 /* which of the R in-process ranks is executing (compat only) */
 void PetscCompatSetRank(int rank, int size);
@@ -83,6 +87,16 @@ PetscErrorCode VecDot(Vec x, Vec y, PetscScalar* val);
 PetscErrorCode VecNorm(Vec x, NormType t, PetscReal* val);
 PetscErrorCode VecPointwiseMult(Vec w, Vec x, Vec y);             /* w = x .* y */
 PetscErrorCode VecPointwiseDivide(Vec w, Vec x, Vec y);           /* w = x ./ y */
+
+/* Viewers.  Binary = PETSc's on-disk Vec format (big-endian: int32 VEC_FILE_CLASSID 1211214, int32 N, N float64), the
+ * format of the reference's restart files output/<field>_<lev>_<step>.vec (eul/UMJS14.cpp:238-267); ASCII = the layout
+ * of VecView on a PetscViewerASCII (header lines, then one value per line).  Collective calls: with several in-process
+ * ranks the LAST rank's VecView writes the whole vector, every rank's VecLoad reads its own slice. */
+PetscErrorCode PetscViewerBinaryOpen(MPI_Comm comm, const char* name, PetscFileMode mode, PetscViewer* viewer);
+PetscErrorCode PetscViewerASCIIOpen(MPI_Comm comm, const char* name, PetscViewer* viewer);
+PetscErrorCode PetscViewerDestroy(PetscViewer* viewer);
+PetscErrorCode VecView(Vec v, PetscViewer viewer);
+PetscErrorCode VecLoad(Vec v, PetscViewer viewer);
 
 PetscErrorCode VecScatterCreate(Vec x, IS ix, Vec y, IS iy, VecScatter* sc);
 PetscErrorCode VecScatterBegin(VecScatter sc, Vec x, Vec y, InsertMode addv, ScatterMode mode);

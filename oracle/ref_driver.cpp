@@ -576,6 +576,61 @@ double ref_uvec_assemble_hu(void* hv, int lev, double scale, int nterms, const d
     }
     return now() - t0;
 }
+
+/*
+ * Geom::interp0 / interp1_l / interp2_l / interp1_g / interp2_g (eul/Geom.cpp:328-417) of one rank at every quadrature
+ * point of every element: which = 0..4, vec = ghosted local DOF vector of the matching space (2-forms: the owned array),
+ * out[nel][q2] (which 1, 3: out[nel][q2][2]).
+ */
+void ref_geom_interp(void* hv, int rank, int which, const double* vec, double* out) {
+    Ref* h = (Ref*)hv;
+    RankObjs& o = h->r[rank];
+    Geom* g = o.geom;
+    Topo* t = o.topo;
+    const int mp1 = g->quad->n + 1, q2 = mp1 * mp1;
+    double* v = const_cast<double*>(vec);
+    for (int ey = 0; ey < t->nElsX; ey++)
+        for (int ex = 0; ex < t->nElsX; ex++) {
+            const long el = (long)ey * t->nElsX + ex;
+            for (int q = 0; q < q2; q++) {
+                double val[2] = {0.0, 0.0};
+                switch (which) {
+                    case 0: g->interp0(ex, ey, q % mp1, q / mp1, v, val); break;
+                    case 1: g->interp1_l(ex, ey, q % mp1, q / mp1, v, val); break;
+                    case 2: g->interp2_l(ex, ey, q % mp1, q / mp1, v, val); break;
+                    case 3: g->interp1_g(ex, ey, q % mp1, q / mp1, v, val); break;
+                    default: g->interp2_g(ex, ey, q % mp1, q / mp1, v, val); break;
+                }
+                if (which == 1 || which == 3) {
+                    out[(el * q2 + q) * 2 + 0] = val[0];
+                    out[(el * q2 + q) * 2 + 1] = val[1];
+                } else {
+                    out[el * q2 + q] = val[0];
+                }
+            }
+        }
+}
+
+/* Geom::initTopog (eul/Geom.cpp:743-764) with the level function of the baroclinic test case (eul/UMJS14.cpp:124-129:
+ * stretched levels, mu = 15, ZTOP = 30 km) over a smooth hill  topog = 2000 (z/R)^2;  thick_out[nk][n0q]. */
+static int g_topog_nk = 1;
+static double ref_topog_fn(double* x) {
+    const double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    return 2000.0 * x[2] * x[2] / r2;
+}
+static double ref_level_fn(double* x, int ki) {
+    (void)x;
+    const double mu = 15.0, ztop = 30000.0, f = (double)ki / g_topog_nk;
+    return ztop * (sqrt(mu * f * f + 1.0) - 1.0) / (sqrt(mu + 1.0) - 1.0);
+}
+void ref_init_topog(void* hv, int rank, double* thick_out) {
+    Ref* h = (Ref*)hv;
+    Geom* g = h->r[rank].geom;
+    g_topog_nk = h->nk;
+    g->initTopog(ref_topog_fn, ref_level_fn);
+    for (int k = 0; k < h->nk; k++)
+        for (int i = 0; i < g->n0; i++) thick_out[(long)k * g->n0 + i] = g->thick[k][i];
+}
 #endif
 
 }  // extern "C"

@@ -63,6 +63,8 @@ class Reference:
         if variant == "eul":
             L.ref_uvec_apply.restype = C.c_double
             L.ref_uvec_apply.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, C.c_int]
+            L.ref_geom_interp.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
+            L.ref_init_topog.argtypes = [C.c_void_p, C.c_int, _dp]
             L.ref_uvec_assemble_hu.restype = C.c_double
             L.ref_uvec_assemble_hu.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, _dp, _dp, _dp, _dp, C.c_int]
         self.nthreads = nthreads or min(os.cpu_count() or 1, nranks)
@@ -181,3 +183,18 @@ class Reference:
         y = np.zeros(self.N1)
         self.lib.ref_uvec_assemble_hu(self.h, lev, scale, len(facs), _d(us), _d(hs), _d(facs), _d(y), self.nthreads)
         return y
+
+    def geom_interp(self, rank, which, vec):
+        """The reference's Geom::interp0 / interp1_l / interp2_l / interp1_g / interp2_g (which = 0..4) of one rank at all
+        quadrature points (eul/Geom.cpp:328-417); eul only."""
+        vec = np.ascontiguousarray(vec, dtype=np.float64)
+        nel, q2 = self.nelsx ** 2, (self.m + 1) ** 2
+        out = np.zeros((nel, q2, 2) if which in (1, 3) else (nel, q2))
+        self.lib.ref_geom_interp(self.h, rank, which, _d(vec), _d(out))
+        return out
+
+    def init_topog(self, rank):
+        """Geom::initTopog with the UMJS14 level function over a smooth hill (see oracle/ref_driver.cpp); returns thick[nk][n0q]."""
+        out = np.zeros((self.nk, self.n0q))
+        self.lib.ref_init_topog(self.h, rank, _d(out))
+        return out

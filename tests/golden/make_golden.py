@@ -150,7 +150,27 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
     np.savez_compressed(os.path.join(HERE, fname), **out)
 
 
+def geom_fixture(p, ne, nprocs, nk, rank, fname, seed):
+    """Geom::interp* and Geom::initTopog of the reference (SURVEY section 8a G4, G5) on one rank."""
+    rng = np.random.default_rng(seed)
+    R = rb.Reference("eul", rb.mesh_dir("sphere", p, ne, nprocs), nprocs, nk=nk)
+    i = R.info(rank)
+    v0 = rng.uniform(-1, 1, i["n0"])
+    v1 = rng.uniform(-1, 1, i["n1x"] + i["n1y"])
+    v2 = rng.uniform(-1, 1, i["n2"])
+    out = dict(p=p, ne=ne, nprocs=nprocs, nk=nk, rank=rank, v0=v0, v1=v1, v2=v2)
+    out["interp0"] = R.geom_interp(rank, 0, v0)
+    out["interp1_l"] = R.geom_interp(rank, 1, v1)
+    out["interp2_l"] = R.geom_interp(rank, 2, v2)
+    out["interp1_g"] = R.geom_interp(rank, 3, v1)
+    out["interp2_g"] = R.geom_interp(rank, 4, v2)
+    out["thick"] = R.init_topog(rank)
+    R.close()
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+
+
 def main():
+    geom_fixture(3, 4, 6, 5, 2, "geom_eul_sphere_p3_ne4_rank2.npz", seed=11)
     for name, nprocs in (("sphere_p3_ne4_np6", 6), ("sphere_p3_ne4_np24", 24), ("sphere_p4_ne2_np6", 6),
                          ("sphere_p2_ne2_np6", 6), ("box_p3_ne4_np4", 4), ("box_p3_ne4_np1", 1)):
         topo_fixture(name, nprocs)

@@ -225,3 +225,40 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
     its, err = take(2)
     assert o == out.size
     assert 0 < its < 200 and err < 1e-11, (its, err)
+
+
+def test_host_geom_interp_topog_and_writers_vs_reference(tmp_path):
+    """SURVEY section 8a G4 / G5 and 8f-4 without a GPU: the host Geom's interp0 / interp1_l / interp2_l / interp1_g /
+    interp2_g and initTopog against values computed by the REFERENCE's own Geom (tests/golden/geom_*.npz, generated by
+    tests/golden/make_golden.py through oracle/_ref), the field writers write0/1/2 (ASCII VecView layout) and the PETSc
+    binary Vec format of the restart files (big-endian classid 1211214, length, float64 payload)."""
+    _build()
+    g = golden("geom_eul_sphere_p3_ne4_rank2.npz")
+    p, ne, nprocs, nk, rank = (int(g[k]) for k in ("p", "ne", "nprocs", "nk", "rank"))
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([g["v0"], g["v1"], g["v2"]]).astype("<f8").tofile(fin)
+    r = subprocess.run([os.path.join(HOST, "build", "host_geom_check"), str(p), str(ne), str(nprocs), str(nk), str(rank), fin, fout,
+                        str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host_geom_check ok" in r.stdout, r.stdout + r.stderr
+    out = np.fromfile(fout, dtype="<f8")
+    o = 0
+    for key in ("interp0", "interp1_l", "interp2_l", "interp1_g", "interp2_g", "thick"):
+        ref = g[key]
+        got = out[o:o + ref.size].reshape(ref.shape)
+        o += ref.size
+        assert rel_l2(got, ref) < 1e-14, (key, rel_l2(got, ref))
+    assert o == out.size
+    # the restart file is PETSc's binary Vec: readable with numpy as big-endian
+    raw = (tmp_path / "output" / "rho_001_0007.vec").read_bytes()
+    cid, n = np.frombuffer(raw[:8], dtype=">i4")
+    assert cid == 1211214 and n == 6 * (p * ne) ** 2
+    vals = np.frombuffer(raw[8:], dtype=">f8")
+    assert vals.size == n and np.array_equal(vals, 1.0e4 * (1.0 + 0.001 * (np.arange(n) % 97)) + 0.25)
+    # write2 with vert_scale: interp2_g(h) / thick at every quadrature point, one value per line after the header
+    lines = (tmp_path / "output" / "rho_001_0007.dat").read_text().splitlines()
+    body = [float(x) for x in lines if x and x[0] in "-0123456789"]
+    # (played rank after rank, a later rank's VecZeroEntries wipes what earlier ranks INSERTed into its slice: the two
+    #  hanging corner nodes, which only ghost copies write, may come out zero here; under MPI every rank zeroes first)
+    assert len(body) == 6 * (p * ne) ** 2 + 2 and min(body) >= 0.0 and sum(1 for v in body if v == 0.0) <= 2
+    for nm in ("velocity_x_001_0007.dat", "velocity_y_001_0007.dat", "velocity_001_0007.vec", "vorticity_001_0007.dat"):
+        assert (tmp_path / "output" / nm).exists(), nm
