@@ -475,11 +475,17 @@ def main():
         total_ms = ev[0].elapsed_time(ev[-1])
         per = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
         launches = launches_per_step * args.steps if replays is not None else eng.launch_count - l_before
-        # sustained leg: the same step replayed back to back for about 1 s (clocks settle, power rises); the count is
-        # a multiple of the ring so that a pipelined sequence ends where it began
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t[0])
+        # sustained leg: the same step replayed back to back for about 1 s (clocks settle, power rises).  The count is
+        # derived from the REDUCED time (every rank must replay the same number of collective steps) and is a multiple
+        # of the ring so that a pipelined sequence ends where it began
         sustained_ms = None
         if not args.no_sustained:
-            n_sus = int(max(args.steps, min(100000, 1.0e3 / max(total_ms / args.steps, 1e-3))))
+            n_sus = int(max(args.steps, min(100000 if world == 1 else 4000, 1.0e3 / max(total_ms / args.steps, 1e-3))))
             n_sus = -(-n_sus // RING) * RING
             first = args.warmup + args.steps
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -489,14 +495,13 @@ def main():
                 step(first + i)
             e1.record()
             barrier()
-            sustained_ms = (e0.elapsed_time(e1) / n_sus, n_sus)
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([total_ms, sustained_ms[0] if sustained_ms else 0.0], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t[0])
-            if sustained_ms:
-                sustained_ms = (float(t[1]), sustained_ms[1])
+            sus = e0.elapsed_time(e1) / n_sus
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([sus], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sus = float(t[0])
+            sustained_ms = (sus, n_sus)
         return total_ms / args.steps, float(np.mean(per)), launches, sustained_ms, replays is not None
 
     sampler = ClockSampler(local)
