@@ -345,6 +345,29 @@ int mimsem_gpu_apply_M1_halo_ll(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld,
                                 const void* d_pull, const void* d_inbox_cells, int64_t cell_stride, int nbuf, int push_ctas,
                                 void* d_epoch, int* d_err, void* stream);
 
+/*
+ * Element-partitioned M1 solve (N GPUs of one box; KSPSolve(ksp1, ...) of eul/HorizSolve.cpp:224, 310, 322 on the
+ * partitioned operator).  Same iteration as mimsem_gpu_solve_M1; the operator is the fused ghost-refresh + M1 launch
+ * (descriptor fields as the arguments of mimsem_gpu_apply_M1_halo / _halo_ll, ll = 1 for the in-band cells), the vectors
+ * live on this rank's OWNED rows (d_b, d_x: local fields; ghost rows of d_x are not written), and each of the two dot
+ * products per iteration is completed over peer memory inside the finishing kernel: every rank stores its per-level
+ * partial sums into the peers' reduction areas as self-validating 16-byte cells and adds all ranks' sums in rank order,
+ * so every rank computes bit-identical step lengths and stops at the same iteration (the call is collective).
+ * d_peer_areas: device array of `world` pointers to the ranks' reduction areas ([rank] = this rank's own, the others
+ * peer-mapped), each 2 * world * 3 * 64 16-byte cells, zero-initialised; d_seq: device counter (starts at 0, advanced
+ * by every reduction, in step on all ranks).
+ */
+typedef struct mimsem_halo_desc {
+    int npush; const void* d_push; int npull; const void* d_pull;
+    const void* d_inbox; int64_t stride; int nbuf; int push_ctas; void* d_epoch; int* d_err; int ll;
+} mimsem_halo_desc;
+typedef struct mimsem_reduce_desc {
+    int world, rank; const void* d_peer_areas; void* d_seq; int* d_err;
+} mimsem_reduce_desc;
+int mimsem_gpu_solve_M1_dist(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_b,
+                             double* d_x, double rtol, int maxit, int* iters, double* relres, const mimsem_halo_desc* halo,
+                             const mimsem_reduce_desc* reduce, void* stream);
+
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
 

@@ -1001,24 +1001,55 @@ int diag_m1(mimsem_gpu_ctx* c, bool invert, int lev0, int nlev, int ld, double s
     return finish_launch(c, "diag_M1");
 }
 
-// x = M1^-1 b by Jacobi-preconditioned CG, all levels at once (per-level step lengths)
+// HaloFused of one fused launch in mode 0 (push and consume the rows of `x` itself) from the C-ABI descriptor
+HaloFused fused_from_desc(const mimsem_halo_desc* d, const double* x) {
+    HaloFused hf;
+    std::memset(&hf, 0, sizeof(hf));
+    hf.npush = d->npush;
+    hf.npull = d->npull;
+    hf.push_ctas = d->push_ctas;
+    hf.push = (const HaloPeer*)d->d_push;
+    hf.pull = (const HaloPeer*)d->d_pull;
+    hf.inbox = (const double*)d->d_inbox;
+    hf.parity_stride = d->stride;
+    hf.nbuf = d->nbuf;
+    hf.ll = d->ll;
+    hf.epoch = (unsigned long long*)d->d_epoch;
+    hf.err = d->d_err;
+    hf.x_push = x;
+    return hf;
+}
+
+// x = M1^-1 b by Jacobi-preconditioned CG, all levels at once (per-level step lengths).  hd / rd: element-partitioned
+// solve -- the operator is the fused ghost-refresh + M1 launch, vectors live on the OWNED rows (the first
+// nel_owned 2 p^2 rows of the engine's edge order) and the dot products are completed over peer memory in k_cg_finish.
 int solve_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
-             double rtol, int maxit, int* iters, double* relres, cudaStream_t st) {
+             double rtol, int maxit, int* iters, double* relres, cudaStream_t st, const mimsem_halo_desc* hd = nullptr,
+             const mimsem_reduce_desc* rd = nullptr) {
     int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
     if (rc) return rc;
     if ((rc = bind_device(c))) return rc;
     if (!b || !x) return fail(MIMSEM_ERR_ARG, "null field");
-    if (c->mode != 0 || c->nel_owned != c->nel_total)
-        return fail(MIMSEM_ERR_UNSUPPORTED, "solve_M1 works on a whole mesh in owner-computes mode (the dot products are not partitioned yet)");
+    const bool dist = hd != nullptr || rd != nullptr;
+    if (dist && (!hd || !rd || rd->world < 2 || rd->rank < 0 || rd->rank >= rd->world || !rd->d_peer_areas || !rd->d_seq || !rd->d_err))
+        return fail(MIMSEM_ERR_ARG, "partitioned solve_M1 needs both a halo and a reduction descriptor");
+    if (c->mode != 0 || (!dist && c->nel_owned != c->nel_total))
+        return fail(MIMSEM_ERR_UNSUPPORTED, "solve_M1 on a subdomain needs mimsem_gpu_solve_M1_dist (ghost refresh + reduction descriptors)");
     if (nlev > 64) return fail(MIMSEM_ERR_UNSUPPORTED, "solve_M1: at most 64 levels per call");
     if (flags & (MIMSEM_SUBSET_INTERIOR | MIMSEM_SUBSET_BOUNDARY)) return fail(MIMSEM_ERR_ARG, "solve_M1 takes no element subset");
     if (!(rtol > 0.0) || maxit < 1) return fail(MIMSEM_ERR_ARG, "bad tolerance / iteration limit");
     const size_t nfield = (size_t)c->n1 * ld;
     CgArgs g;
-    g.nrows = c->n1;
+    std::memset(&g, 0, sizeof(g));
+    g.nrows = dist ? (int64_t)c->nel_owned * 2 * c->p * c->p : c->n1;
     g.nlev = nlev;
     g.ld = ld;
-    g.nblocks = (int)((c->n1 + CG_ROWS - 1) / CG_ROWS);
+    g.nblocks = (int)((g.nrows + CG_ROWS - 1) / CG_ROWS);
+    g.world = dist ? rd->world : 1;
+    g.rank = dist ? rd->rank : 0;
+    g.peer_area = dist ? (uint4* const*)rd->d_peer_areas : nullptr;
+    g.seq = dist ? (unsigned long long*)rd->d_seq : nullptr;
+    g.err = dist ? rd->d_err : nullptr;
     CUDA_OK(c->cg_r.resize(nfield));
     CUDA_OK(c->cg_p.resize(nfield));
     CUDA_OK(c->cg_q.resize(nfield));
@@ -1041,7 +1072,12 @@ int solve_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tp
     bool done = false;
     while (!done) {
         for (int j = 0; j < check_every && it < maxit; j++, it++) {
-            if ((rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, g.p, c->cg_q.p, st))) return rc;
+            if (dist) {
+                const HaloFused hf = fused_from_desc(hd, g.p);
+                if ((rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, g.p, c->cg_q.p, st, &hf))) return rc;
+            } else if ((rc = apply_m1(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, g.p, c->cg_q.p, st))) {
+                return rc;
+            }
             k_cg_step<1><<<g.nblocks, 256, 0, st>>>(g);
             k_cg_finish<1><<<1, 64, 0, st>>>(g);
             k_cg_step<2><<<g.nblocks, 256, 0, st>>>(g);
@@ -1674,6 +1710,13 @@ int mimsem_gpu_apply_M0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, doubl
 int mimsem_gpu_solve_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
                         double rtol, int maxit, int* iters, double* relres, void* st) {
     return solve_m1(c, lev0, nlev, ld, scale, tpow, flags, b, x, rtol, maxit, iters, relres, (cudaStream_t)st);
+}
+int mimsem_gpu_solve_M1_dist(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
+                             double rtol, int maxit, int* iters, double* relres, const mimsem_halo_desc* halo,
+                             const mimsem_reduce_desc* reduce, void* st) {
+    if (!halo || !reduce) return fail(MIMSEM_ERR_ARG, "null descriptor");
+    if (int rcl = check_halo_levels(c, nlev, ld, halo->nbuf)) return rcl;
+    return solve_m1(c, lev0, nlev, ld, scale, tpow, flags, b, x, rtol, maxit, iters, relres, (cudaStream_t)st, halo, reduce);
 }
 int mimsem_gpu_solve_M0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
                         void* st) {

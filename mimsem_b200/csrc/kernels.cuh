@@ -699,7 +699,37 @@ struct CgArgs {
     double* partial;      // [3][nblocks][64]
     double* scal;         // [8][64]: 0 rz, 1 pq, 2 rr, 3 bb, 4 rz_new, 5 alpha, 6 beta, 7 frozen (converged levels)
     double tol2;
+    // element-partitioned solve (N GPUs): every rank contributes its sums over OWNED rows; k_cg_finish exchanges them
+    // over peer memory and adds them in rank order, so that every rank computes bit-identical step lengths
+    int world, rank;
+    uint4* const* peer_area;          // [world] reduction areas (mine at [rank]): [2 parities][world][3][64] 16-byte cells
+    unsigned long long* seq;          // device counter of reductions performed so far (same on every rank)
+    int* err;
 };
+
+// 16-byte self-validating cells {lo32, tag, hi32, tag} (the in-band protocol of the fused ghost refresh, m1_tile.cuh)
+__device__ __forceinline__ void cg_cell_store(uint4* cell, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ double cg_cell_load(const uint4* cell, unsigned tag, int* err) {
+    unsigned x, f0, y, f1;
+    long long t0 = 0;
+    for (unsigned spin = 0;; spin++) {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(cell) : "memory");
+        if (f0 == tag && f1 == tag) break;
+        if ((spin & 1023u) == 1023u) {
+            const long long t = clock64();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ll) {
+                atomicExch(err, 1);
+                break;
+            }
+        }
+    }
+    return __longlong_as_double((long long)(((unsigned long long)y << 32) | (unsigned long long)x));
+}
 
 __device__ __forceinline__ void cg_block_reduce(double v0, double v1, double v2, double* partial, int nblocks, int nsums) {
     __shared__ double red[3][4][64];
@@ -749,12 +779,31 @@ __global__ void __launch_bounds__(256) k_cg_step(const __grid_constant__ CgArgs 
 template <int MODE>
 __global__ void k_cg_finish(const __grid_constant__ CgArgs a) {
     const int k = threadIdx.x;
-    if (k >= a.nlev) return;
+    const bool active = k < a.nlev;
     double s[3] = {0.0, 0.0, 0.0};
-    const int nsums = MODE == 0 ? 3 : (MODE == 1 ? 1 : 2);
+    const int nsums = !active ? 0 : (MODE == 0 ? 3 : (MODE == 1 ? 1 : 2));
     for (int j = 0; j < nsums; j++)
         for (int bI = 0; bI < a.nblocks; bI++) s[j] += a.partial[((size_t)j * a.nblocks + bI) * 64 + k];
+    if (a.world > 1) {
+        // all-gather of the per-rank sums over peer memory, then the same rank-ordered sum on every rank.  Two parities:
+        // a rank can be at most one reduction ahead of a peer (it cannot finish the next one without that peer's sums).
+        const unsigned long long n = *a.seq + 1;
+        const unsigned tag = (unsigned)n;
+        const size_t base = (size_t)(n & 1) * a.world * 3 * 64;
+        for (int j = 0; j < nsums; j++)
+            for (int r = 0; r < a.world; r++)
+                if (r != a.rank) cg_cell_store(a.peer_area[r] + base + ((size_t)a.rank * 3 + j) * 64 + k, s[j], tag);
+        for (int j = 0; j < nsums; j++) {
+            double t = 0.0;
+            for (int r = 0; r < a.world; r++)
+                t += (r == a.rank) ? s[j] : cg_cell_load(a.peer_area[a.rank] + base + ((size_t)r * 3 + j) * 64 + k, tag, a.err);
+            s[j] = t;
+        }
+        __syncthreads();
+        if (k == 0) *a.seq = n;
+    }
     double* S = a.scal;
+    if (!active) return;
     if (MODE == 0) {
         S[0 * 64 + k] = s[0]; S[3 * 64 + k] = s[1]; S[2 * 64 + k] = s[2];
         S[7 * 64 + k] = (s[1] == 0.0) ? 1.0 : 0.0;                    // zero right-hand side: x = 0 is the solution

@@ -19,6 +19,7 @@ struct GlobalVec {            // one collective VecCreateMPI across all in-proce
     std::vector<int> nlocal;  // owned size per rank (-1: that rank has not created it yet)
     int refs = 0;
     int created = 0;          // ranks that have made this collective call so far (storage lives until all have come and gone)
+    long zero_calls = 0;      // VecZeroEntries is collective: the first rank of a round clears the WHOLE vector
     // Reverse ADD scatters are collective: under MPI every rank zeroes / fills its slice BEFORE any remote
     // contribution lands.  With the ranks played one after the other the contributions are therefore deferred
     // until somebody reads the vector.
@@ -143,8 +144,19 @@ static int rstart_of(Vec v) {
     return lo;
 }
 PetscErrorCode VecZeroEntries(Vec v) {
-    if (v->mpi) std::memset(v->g->a.data() + rstart_of(v), 0, sizeof(double) * v->n);
-    else std::fill(v->local.begin(), v->local.end(), 0.0);
+    if (v->mpi) {
+        // Under MPI every rank clears its slice BEFORE any rank's contribution of the next phase arrives.  Played rank
+        // after rank, a later rank's clear would wipe what earlier ranks have already added or inserted into its slice:
+        // the first rank of each round therefore clears the whole vector and the other ranks' calls are no-ops.
+        GlobalVec* g = v->g;
+        if (g->zero_calls % g_size == 0) {
+            g->pending.clear();
+            std::fill(g->a.begin(), g->a.end(), 0.0);
+        }
+        g->zero_calls++;
+    } else {
+        std::fill(v->local.begin(), v->local.end(), 0.0);
+    }
     return 0;
 }
 PetscErrorCode VecGetArray(Vec v, PetscScalar** a) {

@@ -71,8 +71,22 @@ SIGNATURES = {
                                            C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_apply_M1_halo_ll": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int,
                                               C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_solve_M1_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
+                                           _ip, _dp, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
 }
+
+
+class HaloDesc(C.Structure):
+    """mimsem_halo_desc (include/mimsem_gpu.h)"""
+    _fields_ = [("npush", C.c_int), ("d_push", C.c_void_p), ("npull", C.c_int), ("d_pull", C.c_void_p), ("d_inbox", C.c_void_p),
+                ("stride", C.c_int64), ("nbuf", C.c_int), ("push_ctas", C.c_int), ("d_epoch", C.c_void_p), ("d_err", C.c_void_p),
+                ("ll", C.c_int)]
+
+
+class ReduceDesc(C.Structure):
+    """mimsem_reduce_desc (include/mimsem_gpu.h)"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("d_peer_areas", C.c_void_p), ("d_seq", C.c_void_p), ("d_err", C.c_void_p)]
 
 
 class MimsemError(RuntimeError):

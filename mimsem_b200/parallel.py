@@ -264,12 +264,15 @@ class DistributedEngine:
         ll_cells = region[1][1] * nk
         ll_region = (off, ll_cells)
         off += self.NBUF * ll_cells * 16
+        # reduction area of the partitioned CG (mimsem_gpu_solve_M1_dist): [2 parities][world][3 sums][64 levels] cells
+        red_off = off
+        off += 2 * self.world * 3 * 64 * 16
         total = max(off, hdr_bytes + 16)
         base = C.c_void_p()
         handle = C.create_string_buffer(64)
         from .lib import check
         check(eng.L.mimsem_gpu_ipc_alloc(eng._h, total, C.byref(base), handle))
-        mine = dict(handle=handle.raw, layout=layout, region=region, ll_region=ll_region,
+        mine = dict(handle=handle.raw, layout=layout, region=region, ll_region=ll_region, red_off=red_off,
                     send_slot={(s, q): i for s in spaces for i, q in enumerate(send_peers[s])})
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine)
@@ -277,7 +280,7 @@ class DistributedEngine:
         for q in range(self.world):
             if q == self.rank:
                 continue
-            if any(q in recv_peers[s] or q in send_peers[s] for s in spaces):
+            if True:   # every peer is mapped: the CG reduction is all-to-all even where no ghost row is shared
                 ptr = C.c_void_p()
                 check(eng.L.mimsem_gpu_ipc_open(eng._h, everyone[q]["handle"], C.byref(ptr)))
                 peer_base[q] = ptr.value
@@ -333,6 +336,8 @@ class DistributedEngine:
         self._ll = dict(npush=len(push), dpush=torch.from_numpy(push.view(np.uint8).copy()).to(dev), npull=len(pull),
                         dpull=torch.from_numpy(pull.view(np.uint8).copy()).to(dev), epochs=torch.zeros(2, dtype=torch.int64, device=dev),
                         inbox=my + ll_region[0], stride=ll_region[1], push_rows=int(sum(int(r["nrows"]) for r in push)))
+        areas = np.array([(my if q == self.rank else peer_base[q]) + everyone[q]["red_off"] for q in range(self.world)], dtype=np.uint64)
+        self._red = dict(areas=torch.from_numpy(areas.view(np.int64).copy()).to(dev), seq=torch.zeros(1, dtype=torch.int64, device=dev))
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.p2p = dict(plans=plans, err=err, keep=keep, base=base, peer_base=peer_base)
         self.graph_safe = True
@@ -516,6 +521,37 @@ class DistributedEngine:
                                              npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, self.NBUF, push_ctas,
                                              epochs.data_ptr(), self.p2p["err"].data_ptr(), eng._stream()))
         return out
+
+    def solve(self, op, b, out=None, lev0=0, scale=1.0, tpow=0, flags=0, rtol=1e-13, maxit=200):
+        """x = M1^-1 b on the partitioned mesh (collective): Jacobi-PCG whose operator is the fused ghost-refresh + M1
+        launch and whose dot products are completed over peer memory (mimsem_gpu_solve_M1_dist).  b, x: local fields
+        (owned rows matter).  Returns (x, iterations, worst relative residual) -- identical on every rank."""
+        import ctypes as C
+        from .lib import check, MimsemError, HaloDesc, ReduceDesc
+        if op != "M1":
+            raise MimsemError("partitioned solve: M1 (M0 is diagonal: Engine.solve('M0') on the owned rows)")
+        if self.p2p is None:
+            raise MimsemError("the partitioned solve needs the peer-to-peer halo (MIMSEM_HALO=p2p)")
+        eng = self.engine
+        nlev = b.shape[1]
+        self._check_levels(b)
+        if out is None:
+            out = eng.zeros(eng.n1, nlev)
+        if self.ll:
+            L = self._ll
+            hd = HaloDesc(L["npush"], L["dpush"].data_ptr(), L["npull"], L["dpull"].data_ptr(), L["inbox"], L["stride"], self.NBUF,
+                          max(1, min(148, L["push_rows"] // 16)), L["epochs"].data_ptr(), self.p2p["err"].data_ptr(), 1)
+        else:
+            npush, dpush, npull, dpull, epochs = self.p2p["plans"][1]
+            inbox, stride, push_rows = self._inbox[1]
+            hd = HaloDesc(npush, dpush.data_ptr(), npull, dpull.data_ptr(), inbox, stride, self.NBUF, max(1, min(148, push_rows // 16)),
+                          epochs.data_ptr(), self.p2p["err"].data_ptr(), 0)
+        rd = ReduceDesc(self.world, self.rank, self._red["areas"].data_ptr(), self._red["seq"].data_ptr(), self.p2p["err"].data_ptr())
+        it = C.c_int(0)
+        rr = C.c_double(0.0)
+        check(eng.L.mimsem_gpu_solve_M1_dist(eng._h, lev0, nlev, nlev, scale, tpow, flags, b.data_ptr(), out.data_ptr(), rtol, maxit,
+                                             C.byref(it), C.byref(rr), C.addressof(hd), C.addressof(rd), eng._stream()))
+        return out, it.value, rr.value
 
     def capture(self, op, x, coeff=None, out=None, **kw):
         """Capture one full step (pack, NCCL ghost refresh, unpack, interior and boundary kernels) into a CUDA

@@ -118,6 +118,26 @@ def main():
                     ys = to_np(single, single.apply(op, to_cols(single, f["x1"], 1), coeff=cs, scale=1e8, tpow=1 if op == "M1" else 2), sp_)
                     if not np.array_equal(tt.cpu().numpy(), ys):
                         failures.append((what, kind, p, ne, "back-to-back M1 / K: %s differs from single GPU" % op))
+        # partitioned mass-matrix solve: x -> b = M1 x (partitioned) -> CG over peer memory recovers x; every rank
+        # stops at the same iteration with the same residual
+        if deng.p2p is not None and deng.fused and nk % 2 == 0:
+            xt = deng.scatter_from_global(f["x1"], 1)
+            bb = deng.apply("M1", xt, scale=1e8, tpow=1)
+            xs, its, rr = deng.solve("M1", bb, scale=1e8, tpow=1, rtol=1e-13, maxit=300)
+            stat = torch.tensor([float(its), rr], dtype=torch.float64, device="cuda")
+            lo, hi = stat.clone(), stat.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                failures.append((what, kind, p, ne, "partitioned solve: ranks disagree on iterations / residual", lo.tolist(), hi.tolist()))
+            xg = np.zeros((nk, mesh.N1))
+            deng.owned_to_global(xs, 1, xg)
+            tt = torch.from_numpy(xg).cuda()
+            dist.all_reduce(tt)
+            if rank == 0:
+                err = rel_l2(tt.cpu().numpy(), f["x1"])
+                if not (its < 300 and err < 1e-10):
+                    failures.append((what, kind, p, ne, "partitioned solve", its, rr, err))
         if rank == 0:
             print("case", what, kind, p, ne, nk, "world", world, "halo bytes/rank (1-form)", deng.halo_bytes(1, f["x1"].shape[0]), flush=True)
         if deng.halo_error():
