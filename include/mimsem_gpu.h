@@ -92,7 +92,8 @@ int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx);
  *   "m1_variant" 2 tile kernel (default) | 1 line tasks | 0 thread per element-level;  "k_variant" 1 tile | 0 registers;
  *   "ell_vec" 4 | 2 | 1 levels per thread of the incidence kernels;  "prefetch_ahead" L2 prefetch distance in tiles;
  *   "m1_min_blocks" register-budget variant of the M1 tile kernel;  "host_chunk" levels per stage of apply_host;
- *   "halo_max_levels" levels per ghost row the caller's halo inboxes hold (0 = unchecked). */
+ *   "halo_max_levels" levels per ghost row the caller's halo inboxes hold (0 = unchecked);
+ *   "n0_owned" 0-form operators compute node rows [0, n0_owned) only (-1 = all; see mimsem_gpu_set_element_keys). */
 int mimsem_gpu_set_option(mimsem_gpu_ctx* ctx, const char* name, long long value);
 
 /* Basis tables (host pointers): quadrature weights w[m+1], ljxi[(m+1)(p+1)], ejxi[(m+1)p].
@@ -109,6 +110,13 @@ int mimsem_gpu_set_basis(mimsem_gpu_ctx* ctx, int p, int m, const double* h_w, c
  *           eul/Assembly.cpp:2194-2195). */
 int mimsem_gpu_set_topo(mimsem_gpu_ctx* ctx, int nel_total, int nel_owned, int n0, int n1, int n2, int nq, int mode,
                         const int* h_el0, const int* h_el1x, const int* h_el1y, const int* h_el2, const int* h_elq);
+
+/* Canonical order of the elements of the NEXT set_topo (one key per element, e.g. global element ids): sums over the
+ * elements around a node (M0, M0h, M0h_up, E01) then run in key order instead of local element order, which makes the
+ * results of a partitioned mesh bitwise equal to the single-GPU ones.  nel = 0 clears it.  Together with the option
+ * "n0_owned" (0-form operators compute rows [0, n0_owned) only: the caller numbers its owned nodes first and holds
+ * every element around them) this is what a node-partitioned subdomain needs. */
+int mimsem_gpu_set_element_keys(mimsem_gpu_ctx* ctx, int nel, const int* h_keys);
 
 /* Declare which rows are ghosts (refreshed from other subdomains): caller indices >= n1_owned (1-forms) and
  * >= n2_owned (2-forms).  Builds the INTERIOR / BOUNDARY element subsets; out_counts = {n_interior, n_boundary}. */

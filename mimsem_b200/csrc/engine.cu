@@ -90,6 +90,8 @@ struct mimsem_gpu_ctx {
     int m1_min_blocks = 0;                   // register-budget variant of the M1 tile kernel (0: default)
     int host_chunk = 12;                     // levels per pipeline stage of mimsem_gpu_apply_host
     int halo_max_levels = 0;                 // levels per ghost row the caller's halo inboxes were allocated for (0: unknown)
+    int n0_owned = -1;                       // subdomains: 0-form operators compute rows [0, n0_owned) only (-1: all rows)
+    std::vector<int> h_elem_key;             // canonical (partition-independent) order of the elements, e.g. global ids
 #ifdef MIMSEM_DIAG
     int diag_debug = 0;
     long long* diag_times = nullptr;
@@ -263,7 +265,8 @@ void csr_from_triplets(int64_t nrows, int64_t ncols, std::vector<std::array<int6
 // results are bitwise identical on 1 and on N GPUs.
 struct StencilEnt {
     int64_t row, col;
-    int sign, key;
+    int sign;
+    long long key;
 };
 int upload_ell(int64_t nrows, std::vector<StencilEnt> ents, DevEll& d, const std::vector<int>* rows,
                const std::vector<int>* rowperm, const std::vector<int>* colperm) {
@@ -342,7 +345,13 @@ int build_incidence(mimsem_gpu_ctx* c) {
     for (size_t i = 0; i < t10.size(); i++) s10.push_back({t10[i][0], t10[i][1], (int)t10[i][2], (int)(i & 1)});
     for (size_t i = 0; i < t21.size(); i++) s21.push_back({t21[i][0], t21[i][1], (int)t21[i][2], (int)(i & 3)});
     for (auto& v : t12) s12.push_back({v[0], v[1], (int)v[2], v[2] > 0 ? 0 : 1});
-    for (auto& v : t01) s01.push_back({v[0], v[1], (int)v[2], (int)v[1]});
+    // E01 rows add their (up to four) edges in the order (element that lists the edge, position in that element), with the
+    // elements in the caller's canonical order if one was given: independent of the local numbering
+    for (size_t i = 0; i < t01.size(); i++) {
+        const int e = (int)(i / (4 * (size_t)P * P)), slot = (int)(i % (4 * (size_t)P * P));
+        const long long ek = c->h_elem_key.empty() ? e : c->h_elem_key[e];
+        s01.push_back({t01[i][0], t01[i][1], (int)t01[i][2], ek * (4 * P * P) + slot});
+    }
     csr_from_triplets(c->n1, c->n0, t10, c->csr[MIMSEM_E10]);
     csr_from_triplets(c->n0, c->n1, t01, c->csr[MIMSEM_E01]);
     csr_from_triplets(c->n2, c->n1, t21, c->csr[MIMSEM_E21]);
@@ -375,6 +384,18 @@ int build_node_adjacency(mimsem_gpu_ctx* c) {
     std::vector<int> pos(c->h_adj_ptr.begin(), c->h_adj_ptr.end() - 1);
     for (int e = 0; e < c->nel_total; e++)
         for (int q = 0; q < Q2; q++) c->h_adj_eq[pos[c->h_el0[(size_t)e * Q2 + q]]++] = e * Q2 + q;
+    // canonical order of every node's (element, point) pairs: by the caller's element keys (global element ids on a
+    // partitioned mesh), so that sums over the pairs do not depend on the local element order -- N-GPU results of the
+    // 0-form operators are then bitwise equal to the single-GPU ones
+    if (!c->h_elem_key.empty()) {
+        if ((int)c->h_elem_key.size() != c->nel_total) return fail(MIMSEM_ERR_ARG, "set_element_keys: one key per element of set_topo");
+        const std::vector<int>& key = c->h_elem_key;
+        for (int n = 0; n < c->n0; n++)
+            std::sort(c->h_adj_eq.begin() + c->h_adj_ptr[n], c->h_adj_eq.begin() + c->h_adj_ptr[n + 1], [&](int a, int b) {
+                const int ea = a / Q2, eb = b / Q2;
+                return key[ea] != key[eb] ? key[ea] < key[eb] : a < b;
+            });
+    }
     return MIMSEM_OK;
 }
 
@@ -874,7 +895,7 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     if (rc) return rc;
     if ((rc = bind_device(c))) return rc;
     NodeArgs a;
-    a.n0 = c->n0;
+    a.n0 = c->n0_owned >= 0 ? c->n0_owned : c->n0;   // subdomain: owned nodes first, their (element, point) pairs all local
     a.nlev = nlev;
     a.ld = ld;
     a.lev0 = lev0;
@@ -893,6 +914,7 @@ int apply_m0(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.x = x;
     a.y = y;
     copy_basis(c, a);
+    if (a.n0 == 0) return MIMSEM_OK;
     {
         const FastDiv fd = make_fastdiv((unsigned)nlev);
         a.div_m = fd.m;
@@ -947,9 +969,10 @@ int apply_m0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, in
     if (rc) return rc;
     if ((rc = bind_device(c))) return rc;
     if (!h2 || !u1 || !x || !y) return fail(MIMSEM_ERR_ARG, "null field");
-    if (c->nel_owned != c->nel_total) return fail(MIMSEM_ERR_UNSUPPORTED, "0-form operators are not partitioned");
+    if (c->nel_owned != c->nel_total && c->n0_owned < 0)
+        return fail(MIMSEM_ERR_UNSUPPORTED, "0-form operators on a subdomain need the option n0_owned (owned nodes first, all their elements local)");
     NodeArgs a;
-    a.n0 = c->n0;
+    a.n0 = c->n0_owned >= 0 ? c->n0_owned : c->n0;
     a.nlev = nlev;
     a.ld = ld;
     a.lev0 = lev0;
@@ -1109,7 +1132,7 @@ int solve_m0(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tp
     if (!b || !x) return fail(MIMSEM_ERR_ARG, "null field");
     NodeArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.n0 = c->n0;
+    a.n0 = c->n0_owned >= 0 ? c->n0_owned : c->n0;
     a.nlev = nlev;
     a.ld = ld;
     a.lev0 = lev0;
@@ -1138,6 +1161,7 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
     const DevEll& d = c->ell[which];
     EllArgs a;
     a.nrows = d.nrows_active;
+    if (which == MIMSEM_E01 && c->n0_owned >= 0) a.nrows = c->n0_owned;   // node rows are identity-ordered: owned nodes first
     a.width = d.width;
     a.nlev = nlev;
     a.ld = ld;
@@ -1281,6 +1305,7 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
     else if (n == "host_chunk" && v >= 1) c->host_chunk = v;
     else if (n == "halo_max_levels" && v >= 0) c->halo_max_levels = v;
+    else if (n == "n0_owned" && v >= -1) c->n0_owned = v;
 #ifdef MIMSEM_DIAG
     else if (n == "diag_debug") c->diag_debug = v;
     else if (n == "diag_times") c->diag_times = (long long*)value;
@@ -1439,6 +1464,13 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
     return MIMSEM_OK;
 }
 
+int mimsem_gpu_set_element_keys(mimsem_gpu_ctx* c, int nel, const int* h_keys) {
+    if (!c || (nel > 0 && !h_keys) || nel < 0) return fail(MIMSEM_ERR_ARG, "bad argument");
+    c->h_elem_key.assign(h_keys, h_keys + nel);
+    c->have_topo = c->have_geom = false;   // takes effect at the next set_topo / set_geom
+    return MIMSEM_OK;
+}
+
 int mimsem_gpu_set_ghosts(mimsem_gpu_ctx* c, int n1_owned, int n2_owned, int out_counts[2]) {
     if (!c || !c->have_topo) return fail(MIMSEM_ERR_STATE, "set_topo first");
     if (n1_owned < 0 || n1_owned > c->n1 || n2_owned < 0 || n2_owned > c->n2) return fail(MIMSEM_ERR_ARG, "bad owned counts");
@@ -1514,8 +1546,14 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
         G1h[i * 3 + 0] = gaa * wdd; G1h[i * 3 + 1] = gab * wdd; G1h[i * 3 + 2] = gbb * wdd;
         W2[i] = wd;
         W2h[i] = wdd;
-        D0[c->h_el0[i]] += w * det;   // element order, as MatSetValues(ADD_VALUES) accumulates
     }
+    // sum over the (element, point) pairs at each node in adjacency order: element order as MatSetValues(ADD_VALUES)
+    // accumulates, or the caller's canonical order (set_element_keys)
+    for (int n = 0; n < c->n0; n++)
+        for (int j = c->h_adj_ptr[n]; j < c->h_adj_ptr[n + 1]; j++) {
+            const size_t i = (size_t)c->h_adj_eq[j];
+            D0[n] += wq[i % Q2] * h_det[i];
+        }
     {
         // line-ordered copies of the metric: Gc[e][qx][qy] = (g0,g1), Gr[e][qy][qx] = (g1,g2)
         std::vector<double> Gc(npts * 2), Gr(npts * 2), Gch(npts * 2), Grh(npts * 2);

@@ -105,6 +105,21 @@ __device__ __forceinline__ double ll_load(const uint4* cell, unsigned ep, int* e
     return __longlong_as_double((long long)(((unsigned long long)y << 32) | (unsigned long long)x));
 }
 
+// N cells at once: all loads are issued before the first one is examined (memory-level parallelism; a cell-by-cell poll
+// serialises N round trips to L2 / HBM), then only the cells that had not landed yet are polled again.
+template <int N>
+__device__ __forceinline__ void ll_load_many(const uint4* const (&cell)[N], unsigned ep, int* err, double (&out)[N]) {
+    unsigned x[N], f0[N], y[N], f1[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[i]), "=r"(f0[i]), "=r"(y[i]), "=r"(f1[i]) : "l"(cell[i]) : "memory");
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if (f0[i] == ep && f1[i] == ep) out[i] = __longlong_as_double((long long)(((unsigned long long)y[i] << 32) | (unsigned long long)x[i]));
+        else out[i] = ll_load(cell[i], ep, err);
+    }
+}
+
 static __device__ __noinline__ void halo_push_role_ll(const TArgs& a, unsigned long long epoch) {
     const HaloFused& h = a.halo;
     __shared__ HaloPeer peers[kMaxPushPeers];
@@ -222,15 +237,56 @@ __device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, in
     }
     double oth[P + 1][P];
     const double* xk = a.x + k;
+    if (HALO == 2 && (flags & (side ? TF_LIST_S : TF_LIST_W)) && rows[0] < 0 && rows[NF - 1] < 0) {
+        // every row of this side lives in the cell inbox (the common case of a ghost far line): two batches of loads
+        constexpr int H0 = NF / 2, H1 = NF - H0;
+        const uint4* cb = reinterpret_cast<const uint4*>(inbox) + k;
+        double* of = &oth[0][0];
+        {
+            const uint4* cell[H0];
+            double v[H0];
 #pragma unroll
-    for (int q = 0; q <= P; q++)
+            for (int i = 0; i < H0; i++) cell[i] = rows[i] < 0 ? cb + (size_t)(-rows[i] - 1) * a.nlev : nullptr;
+            bool all = true;
 #pragma unroll
-        for (int t = 0; t < P; t++) {
-            const int r = rows[q * P + t];
-            if (HALO == 1 && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
-            else if (HALO == 2 && r < 0) oth[q][t] = ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(-r - 1) * a.nlev + k, ep, a.halo.err);
-            else oth[q][t] = xk[(size_t)r * a.ld];
+            for (int i = 0; i < H0; i++) all = all && cell[i];
+            if (all) {
+                ll_load_many<H0>(cell, ep, a.halo.err, v);
+#pragma unroll
+                for (int i = 0; i < H0; i++) of[i] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < H0; i++) of[i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[i] * a.ld];
+            }
         }
+        {
+            const uint4* cell[H1];
+            double v[H1];
+#pragma unroll
+            for (int i = 0; i < H1; i++) cell[i] = rows[H0 + i] < 0 ? cb + (size_t)(-rows[H0 + i] - 1) * a.nlev : nullptr;
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < H1; i++) all = all && cell[i];
+            if (all) {
+                ll_load_many<H1>(cell, ep, a.halo.err, v);
+#pragma unroll
+                for (int i = 0; i < H1; i++) of[H0 + i] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < H1; i++) of[H0 + i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[H0 + i] * a.ld];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q <= P; q++)
+#pragma unroll
+            for (int t = 0; t < P; t++) {
+                const int r = rows[q * P + t];
+                if (HALO == 1 && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+                else if (HALO == 2 && r < 0) oth[q][t] = ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(-r - 1) * a.nlev + k, ep, a.halo.err);
+                else oth[q][t] = xk[(size_t)r * a.ld];
+            }
+    }
     double hv[WITH_H ? P : 1][WITH_H ? P : 1];
     if (WITH_H) {
         const TileFarH fh = *reinterpret_cast<const TileFarH*>(rec + 2);
@@ -499,9 +555,16 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
             if (k < nl)
                 for (int ci = fh.first4; ci < fh.first4 + fh.n4; ci++) {
                     const CopyEnt c = ents[ci];
-                    for (int j = part; j < c.count; j += 2)
-                        tile[(size_t)(c.slot + j) * nl + k] =
-                            ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(c.src + j) * a.nlev + k, (unsigned)epoch, a.halo.err);
+                    const uint4* cb = reinterpret_cast<const uint4*>(inbox) + (size_t)c.src * a.nlev + k;
+                    int j = part;
+                    for (; j + 2 < c.count; j += 4) {   // two rows of this warp-pair in flight
+                        const uint4* cell[2] = {cb + (size_t)j * a.nlev, cb + (size_t)(j + 2) * a.nlev};
+                        double v[2];
+                        ll_load_many<2>(cell, (unsigned)epoch, a.halo.err, v);
+                        tile[(size_t)(c.slot + j) * nl + k] = v[0];
+                        tile[(size_t)(c.slot + j + 2) * nl + k] = v[1];
+                    }
+                    for (; j < c.count; j += 2) tile[(size_t)(c.slot + j) * nl + k] = ll_load(cb + (size_t)j * a.nlev, (unsigned)epoch, a.halo.err);
                 }
             __syncthreads();   // generic-proxy writes of one warp-pair are read by the other
         }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mimsem_gpu_set_basis": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp]),
     "mimsem_gpu_set_topo": (C.c_int, [_vp] + [C.c_int] * 7 + [_ip] * 5),
     "mimsem_gpu_set_geom": (C.c_int, [_vp, _dp, _dp]),
+    "mimsem_gpu_set_element_keys": (C.c_int, [_vp, C.c_int, _ip]),
     "mimsem_gpu_set_ghosts": (C.c_int, [_vp, C.c_int, C.c_int, _ip]),
     "mimsem_gpu_set_thickness": (C.c_int, [_vp, C.c_int, _dp]),
     "mimsem_gpu_sizes": (C.c_int, [_vp, _lp]),
