@@ -139,37 +139,37 @@ static __device__ __noinline__ void halo_push_role_ll(const TArgs& a, unsigned l
         pre[h.npush] = acc;
     }
     __syncthreads();
-    const int nl2 = a.nlev >> 1;
+    // one VALUE per lane and store: consecutive lanes write consecutive 16-byte cells, i.e. every warp store is 512
+    // contiguous bytes = four full 128-byte lines on the wire (two cells per lane left 16-byte holes in every sector of
+    // each store and cost more NVLink time than the whole tile work of a step)
+    const int nl = a.nlev;
     const int R = pre[h.npush];
     const int f0 = (int)(((long long)R * blockIdx.x) / h.push_ctas);
     const int f1 = (int)(((long long)R * (blockIdx.x + 1)) / h.push_ctas);
-    const int total = (f1 - f0) * nl2;
+    const int total = (f1 - f0) * nl;
     const unsigned ep = (unsigned)epoch;
-    constexpr int U = 4;
+    constexpr int U = 8;
     for (int base = threadIdx.x; base < total; base += U * blockDim.x) {
-        double2 v[U];
+        double v[U];
         uint4* dst[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int i = base + u * blockDim.x;
             dst[u] = nullptr;
             if (i < total) {
-                const int f = f0 + i / nl2, k2 = i - (f - f0) * nl2;
+                const int f = f0 + i / nl, k = i - (f - f0) * nl;
                 int p = 0;
                 while (f >= pre[p + 1]) p++;
                 const int r = f - pre[p];
                 const HaloPeer& pp = peers[p];
-                v[u] = __ldg(reinterpret_cast<const double2*>(h.x_push + (size_t)pp.rows[r] * a.ld) + k2);
+                v[u] = __ldg(h.x_push + (size_t)pp.rows[r] * a.ld + k);
                 // LL inbox of the peer: 16-byte cells, [copy][row][level]
-                dst[u] = reinterpret_cast<uint4*>(pp.inbox) + (epoch % h.nbuf) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev + 2 * k2;
+                dst[u] = reinterpret_cast<uint4*>(pp.inbox) + (epoch % h.nbuf) * pp.inbox_parity_stride + (size_t)(pp.row0 + r) * a.nlev + k;
             }
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (dst[u]) {
-                ll_store(dst[u], v[u].x, ep);
-                ll_store(dst[u] + 1, v[u].y, ep);
-            }
+            if (dst[u]) ll_store(dst[u], v[u], ep);
     }
 }
 

@@ -60,6 +60,26 @@ def west_south_neighbours(mesh):
     return nbr
 
 
+def node_min_element(mesh):
+    """For every global node the lowest-numbered element around it (its owner element: nodes follow elements)."""
+    if getattr(mesh, "_node_min_el", None) is None:
+        nme = np.full(mesh.N0, mesh.nel, dtype=np.int64)
+        np.minimum.at(nme, mesh.el0.ravel().astype(np.int64), np.repeat(np.arange(mesh.nel, dtype=np.int64), mesh.el0.shape[1]))
+        mesh._node_min_el = nme
+    return mesh._node_min_el
+
+
+def node_elements(mesh):
+    """CSR node -> elements around it: (ptr[N0 + 1], elems)."""
+    if getattr(mesh, "_node_els", None) is None:
+        nodes = mesh.el0.ravel().astype(np.int64)
+        els = np.repeat(np.arange(mesh.nel, dtype=np.int64), mesh.el0.shape[1])
+        order = np.argsort(nodes, kind="stable")
+        ptr = np.searchsorted(nodes[order], np.arange(mesh.N0 + 1))
+        mesh._node_els = (ptr, els[order])
+    return mesh._node_els
+
+
 class Partition:
     """Local view of rank `rank` of `world`: owned + halo elements, owned-first local DOF numbering,
     ghost lists grouped by owner rank.  All index arrays are numpy int32/int64."""
@@ -73,7 +93,17 @@ class Partition:
         owned = np.arange(e0, e1, dtype=np.int64)
         nbr = west_south_neighbours(mesh)[e0:e1].ravel()
         nbr = nbr[nbr >= 0]
-        halo = np.setdiff1d(np.unique(nbr), owned)
+        halo_ws = np.setdiff1d(np.unique(nbr), owned)
+        # 0-forms: a node belongs to the rank of the lowest-numbered element around it; for the operators that SUM over
+        # the elements around a node (M0h, E01, M0h_up) every element around an owned node is held as a halo element too
+        nme = node_min_element(mesh)
+        self.node_owner_of = lambda ids: owner_rank_of_element(nme[ids], nel, world)
+        own_nodes = np.nonzero((nme >= e0) & (nme < e1))[0]
+        nptr, nels = node_elements(mesh)
+        around = np.unique(np.concatenate([nels[nptr[n]:nptr[n + 1]] for n in own_nodes])) if len(own_nodes) else np.zeros(0, np.int64)
+        halo_node = np.setdiff1d(around, owned)
+        halo = np.union1d(halo_ws, halo_node)
+        self.halo_ws = halo_ws
         # owned elements that read no row owned elsewhere (interior) come first, the others (boundary) last: the
         # engine's interior / boundary subsets are then index ranges, and the fused ghost-refresh kernel walks the
         # elements in storage order (same rule as mimsem_gpu_set_ghosts)
@@ -123,8 +153,16 @@ class Partition:
         # 1-forms: edge g is owned by element g // (2 p^2); 2-forms: face g by element g // p^2
         self.g1, self.n1_owned, n1_need = local_numbering(np.concatenate([mesh.el1x[L].ravel(), mesh.el1y[L].ravel()]), b1, needed1)
         self.n1_halo = self.n1_owned + n1_need          # rows [n1_owned, n1_halo) are refreshed from their owners
-        self.g2, self.n2_owned, _ = local_numbering(mesh.el2[L].ravel(), b2)
-        self.g0, _, _ = local_numbering(mesh.el0[L].ravel(), 0)
+        # 2-forms the element kernels read: the faces of the west / south halo elements (M1h's neighbour coefficient, E12)
+        needed2 = np.unique(mesh.el2[np.concatenate([owned, halo_ws])].ravel().astype(np.int64))
+        self.g2, self.n2_owned, n2_need = local_numbering(mesh.el2[L].ravel(), b2, needed2)
+        self.n2_halo = self.n2_owned + n2_need
+        # nodes: owned first (ascending), then the ghosts grouped by owner rank
+        ids0 = np.unique(mesh.el0[L].ravel().astype(np.int64))
+        own0 = ids0[(nme[ids0] >= e0) & (nme[ids0] < e1)]
+        gh0 = np.setdiff1d(ids0, own0)
+        gh0 = gh0[np.lexsort((gh0, self.node_owner_of(gh0)))] if len(gh0) else gh0
+        self.g0, self.n0_owned = np.concatenate([own0, gh0]), len(own0)
         self.gq, _, _ = local_numbering(mesh.elq[L].ravel(), 0)
         self.n0, self.n1, self.n2, self.nq = len(self.g0), len(self.g1), len(self.g2), len(self.gq)
 
@@ -140,12 +178,16 @@ class Partition:
         self.el2 = to_local(self.g2, mesh.el2[L])
         self.el0 = to_local(self.g0, mesh.el0[L])
         self.elq = to_local(self.gq, mesh.elq[L])
-        # ghosts grouped by owner rank (ascending global id inside a group)
-        self.recv = {1: self._group(self.g1[self.n1_owned:self.n1_halo], b1, nel, self.n1_owned),
-                     2: self._group(self.g2[self.n2_owned:], b2, nel, self.n2_owned)}
+        # ghosts grouped by owner rank (ascending global id inside a group): the rows the element kernels read ...
+        self.recv = {0: self._group(self.g0[self.n0_owned:], 0, nel, self.n0_owned),
+                     1: self._group(self.g1[self.n1_owned:self.n1_halo], b1, nel, self.n1_owned),
+                     2: self._group(self.g2[self.n2_owned:self.n2_halo], b2, nel, self.n2_owned)}
+        # ... and ALL ghost rows (the node-sum operators M0h, E01, M0h_up read every element around an owned node)
+        self.recv_ext = {1: self._group(self.g1[self.n1_owned:], b1, nel, self.n1_owned),
+                         2: self._group(self.g2[self.n2_owned:], b2, nel, self.n2_owned)}
 
     def _group(self, ghosts, block, nel, offset):
-        owner = owner_rank_of_element(ghosts // block, nel, self.world)
+        owner = owner_rank_of_element(ghosts // block, nel, self.world) if block else self.node_owner_of(ghosts)
         out = {}
         for q in np.unique(owner):
             sel = np.nonzero(owner == q)[0]
@@ -153,25 +195,32 @@ class Partition:
         return out
 
     def owned_global(self, space):
-        return {1: self.g1[:self.n1_owned], 2: self.g2[:self.n2_owned]}[space]
+        return {0: self.g0[:self.n0_owned], 1: self.g1[:self.n1_owned], 2: self.g2[:self.n2_owned]}[space]
+
+    def n_owned(self, space):
+        return {0: self.n0_owned, 1: self.n1_owned, 2: self.n2_owned}[space]
 
 
 def send_lists(mesh, rank, world):
     """For every peer q: the LOCAL (owned) ids on `rank` that q holds as ghosts, in q's receive order.
     Every rank can build every partition, so no index exchange is needed at setup."""
     me = Partition(mesh, rank, world)
-    p = mesh.p
-    out = {1: {}, 2: {}}
+    out = {0: {}, 1: {}, 2: {}}
+    ext = {1: {}, 2: {}}
     for q in range(world):
         if q == rank:
             continue
         other = Partition(mesh, q, world)
-        for space, block in ((1, 2 * p * p), (2, p * p)):
-            grp = other.recv[space].get(rank)
-            if grp is None:
-                continue
-            first = me.e0 * block
-            out[space][q] = (grp["glob"] - first).astype(np.int32)   # owned DOFs are numbered contiguously from e0*block
+        for space in (0, 1, 2):
+            own = me.owned_global(space)          # ascending: local id of an owned DOF = its position
+            for table, dst in ((other.recv, out), (getattr(other, "recv_ext", {}), ext)):
+                grp = table.get(space, {}).get(rank) if space in dst else None
+                if grp is None:
+                    continue
+                loc = np.searchsorted(own, grp["glob"])
+                assert np.array_equal(own[loc], grp["glob"])
+                dst[space][q] = loc.astype(np.int32)
+    me.sends_ext = ext
     return me, out
 
 
@@ -179,7 +228,7 @@ class DistributedEngine:
     """Engine of one rank + the ghost-refresh plan.  Fields are local column-layout tensors with
     n_space rows (owned rows are complete after an apply; ghost rows are refreshed by exchange())."""
 
-    SUPPORTED = ("M1", "M1h", "M2", "M2h", "K", "E21", "E12")
+    SUPPORTED = ("M1", "M1h", "M2", "M2h", "K", "E21", "E12", "M0", "M0h", "E10", "E01", "R", "R_up", "M0h_up", "UtQW")
 
     def __init__(self, mesh, thick, rank, world, device, max_levels=None):
         import torch
@@ -190,7 +239,12 @@ class DistributedEngine:
         P = self.part
         eng = Engine(device)
         eng.set_basis(Basis(mesh.p, mesh.m))
+        # sums over the elements around a node run in GLOBAL element order: bitwise equal to the single-GPU result
+        keys = np.ascontiguousarray(P.elements, dtype=np.int32)
+        from .lib import check, _ip
+        check(eng.L.mimsem_gpu_set_element_keys(eng._h, len(keys), keys.ctypes.data_as(_ip)))
         eng.set_topo(P.el0, P.el1x, P.el1y, P.el2, P.elq, P.n0, P.n1, P.n2, P.nq, nel_owned=P.nel_owned, mode=0)
+        eng.set_option("n0_owned", P.n0_owned)
         self.n_interior, self.n_boundary = eng.set_ghosts(P.n1_owned, P.n2_owned)
         assert self.n_interior == P.n_interior, "partition and engine disagree on the interior / boundary split"
         eng.set_geom(mesh.J[P.elements], mesh.det[P.elements])
@@ -199,18 +253,18 @@ class DistributedEngine:
         self.engine = eng
         self.device = device
         dev = "cuda:%d" % device
-        self.plan = {}
-        for space in (1, 2):
+        def build_plan(space, recv, send):
             perm = eng.permutation(space).astype(np.int64)
-            peers = sorted(set(P.recv[space]) | set(sends[space]))
             plan = []
-            for q in peers:
-                r = P.recv[space].get(q)
-                s = sends[space].get(q)
+            for q in sorted(set(recv) | set(send)):
+                r, s = recv.get(q), send.get(q)
                 rrows = torch.from_numpy(perm[r["local"]].astype(np.int32)).to(dev) if r is not None else None
                 srows = torch.from_numpy(perm[s].astype(np.int32)).to(dev) if s is not None else None
                 plan.append((q, srows, rrows))
-            self.plan[space] = plan
+            return plan
+        # the rows the element kernels read (peer-to-peer inboxes) and, for the node-sum operators, ALL ghost rows (NCCL)
+        self.plan = {space: build_plan(space, P.recv[space], sends[space]) for space in (0, 1, 2)}
+        self.plan_ext = {space: build_plan(space, P.recv_ext[space], P.sends_ext[space]) for space in (1, 2)}
         self._bufs = {}
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1)   # halo kernels get SM slots ahead of the bulk kernel
         self.overlap = True
@@ -237,18 +291,19 @@ class DistributedEngine:
         import ctypes as C
         torch, dist, eng = self.torch, self.dist, self.engine
         MAXP, nk = self.MAXP, self.nk_max
-        spaces = (1, 2)
+        spaces = (0, 1, 2)
+        nsp = len(spaces)
         recv_peers = {s: sorted(P.recv[s]) for s in spaces}
         send_peers = {s: sorted(sends[s]) for s in spaces}
         assert all(len(v) <= MAXP for v in list(recv_peers.values()) + list(send_peers.values()))
-        hdr_bytes = 5 * MAXP * 8                       # flags[2][MAXP], acks[2][MAXP], acks of the in-band (LL) 1-form inbox [MAXP]
+        hdr_bytes = (2 * nsp + 1) * MAXP * 8           # flags[nsp][MAXP], acks[nsp][MAXP], acks of the in-band (LL) 1-form inbox [MAXP]
         # inbox of a space: [NBUF copies][ghost rows of the space, in ghost order][nk]; a peer's share is the run of
         # rows it owns (ghosts are sorted by global id, owners hold contiguous id ranges)
         layout = {}                                    # (space, peer) -> (slot, first inbox row, nrows)
         region = {}                                    # space -> (offset in bytes, total ghost rows)
         off = hdr_bytes
         for si, s in enumerate(spaces):
-            n_own = {1: P.n1_owned, 2: P.n2_owned}[s]
+            n_own = P.n_owned(s)
             row = 0
             for slot, q in enumerate(recv_peers[s]):
                 loc = P.recv[s][q]["local"].astype(np.int64)
@@ -302,7 +357,7 @@ class DistributedEngine:
                 assert n_on_q == rows.numel()
                 push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, stride_on_q,
                            peer_base[q] + (si * MAXP + slot_on_q) * 8,            # flag on q
-                           my + (2 * MAXP + si * MAXP + i) * 8)                    # ack from q, in my memory
+                           my + ((nsp + si) * MAXP + i) * 8)                       # ack from q, in my memory
             pull = np.zeros(len(recv_peers[s]), dtype=dt)
             off_b, nghost, stride_b = region[s]
             for i, q in enumerate(recv_peers[s]):
@@ -311,7 +366,7 @@ class DistributedEngine:
                 slot, row0, n = layout[(s, q)]
                 ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
                 pull[i] = (rows.data_ptr(), n, row0, my + off_b, stride_b,
-                           peer_base[q] + (2 * MAXP + si * MAXP + ack_slot_on_q) * 8,   # ack on q
+                           peer_base[q] + ((nsp + si) * MAXP + ack_slot_on_q) * 8,   # ack on q
                            my + (si * MAXP + slot) * 8)                                # flag from q, in my memory
             dpush = torch.from_numpy(push.view(np.uint8).copy()).to(dev)
             dpull = torch.from_numpy(pull.view(np.uint8).copy()).to(dev)
@@ -327,12 +382,12 @@ class DistributedEngine:
             keep.append(rows)
             slot_on_q, row0_on_q, n_on_q = everyone[q]["layout"][(s, self.rank)]
             off_on_q, cells_on_q = everyone[q]["ll_region"]
-            push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, cells_on_q, 0, my + (4 * MAXP + i) * 8)
+            push[i] = (rows.data_ptr(), rows.numel(), row0_on_q, peer_base[q] + off_on_q, cells_on_q, 0, my + (2 * nsp * MAXP + i) * 8)
         pull = np.zeros(len(recv_peers[s]), dtype=dt)
         for i, q in enumerate(recv_peers[s]):
             slot, row0, n = layout[(s, q)]
             ack_slot_on_q = everyone[q]["send_slot"][(s, self.rank)]
-            pull[i] = (0, n, row0, my + ll_region[0], ll_region[1], peer_base[q] + (4 * MAXP + ack_slot_on_q) * 8, 0)
+            pull[i] = (0, n, row0, my + ll_region[0], ll_region[1], peer_base[q] + (2 * nsp * MAXP + ack_slot_on_q) * 8, 0)
         self._ll = dict(npush=len(push), dpush=torch.from_numpy(push.view(np.uint8).copy()).to(dev), npull=len(pull),
                         dpull=torch.from_numpy(pull.view(np.uint8).copy()).to(dev), epochs=torch.zeros(2, dtype=torch.int64, device=dev),
                         inbox=my + ll_region[0], stride=ll_region[1], push_rows=int(sum(int(r["nrows"]) for r in push)))
@@ -381,10 +436,11 @@ class DistributedEngine:
     def halo_bytes(self, space, nlev):
         return sum((0 if s is None else s.numel()) for _, s, _ in self.plan[space]) * nlev * 8
 
-    def exchange(self, field, space):
+    def exchange(self, field, space, ext=False):
         """Ghost refresh of a local field.  p2p mode: push kernel (stores into the peers' inboxes) + pull kernel;
-        otherwise pack -> NCCL send/recv -> unpack."""
-        if self.p2p is not None:
+        otherwise pack -> NCCL send/recv -> unpack.  ext: ALL ghost rows of the space (what the operators that sum over
+        the elements around a node read), always through NCCL -- those are not on the hot path."""
+        if self.p2p is not None and not ext:
             self.push(field, space)
             self.pull(field, space)
             return field
@@ -392,13 +448,13 @@ class DistributedEngine:
         nlev = field.shape[1]
         st = eng._stream()
         ops, unpack = [], []
-        for q, srows, rrows in self.plan[space]:
+        for q, srows, rrows in (self.plan_ext if ext else self.plan)[space]:
             if srows is not None:
-                sb = self._buf(("s", space, q, nlev), srows.numel() * nlev, field.device)
+                sb = self._buf(("s", space, q, nlev, ext), srows.numel() * nlev, field.device)
                 eng.L.mimsem_gpu_gather_rows(eng._h, srows.numel(), nlev, nlev, srows.data_ptr(), field.data_ptr(), sb.data_ptr(), st)
                 ops.append(dist.P2POp(dist.isend, sb, q))
             if rrows is not None:
-                rb = self._buf(("r", space, q, nlev), rrows.numel() * nlev, field.device)
+                rb = self._buf(("r", space, q, nlev, ext), rrows.numel() * nlev, field.device)
                 ops.append(dist.P2POp(dist.irecv, rb, q))
                 unpack.append((rrows, rb))
         if ops:
@@ -415,9 +471,14 @@ class DistributedEngine:
             self._bufs[key] = b
         return b[:n]
 
-    # which inputs of an operator are read through ghost rows at all (2-forms are element-local)
-    NEEDS = {"M1": (True, False), "M1h": (True, True), "M2": (False, False), "M2h": (False, False), "K": (True, True),
-             "E21": (True, False), "E12": (True, False)}
+    # which inputs of an operator are read through ghost rows: (space, "min" = the rows the element kernels read |
+    # "ext" = every ghost row) for the field x, the coefficient c and the advecting velocity u1.  2-form operators are
+    # element-local; M0 is diagonal (its weights are summed once, from the elements this rank holds around its nodes).
+    NEEDS = {"M1": dict(x=(1, "min")), "M1h": dict(x=(1, "min"), c=(2, "min")), "M2": {}, "M2h": {}, "K": dict(x=(1, "min"), c=(1, "min")),
+             "E21": dict(x=(1, "min")), "E12": dict(x=(2, "min")), "UtQW": dict(x=(2, "min"), c=(1, "min")),
+             "M0": {}, "M0h": dict(c=(2, "ext")), "E10": dict(x=(0, "min")), "E01": dict(x=(1, "ext")),
+             "R": dict(x=(1, "min"), c=(0, "min")), "R_up": dict(x=(1, "min"), c=(0, "min"), u1=(1, "min")),
+             "M0h_up": dict(x=(0, "min"), c=(2, "ext"), u1=(1, "ext"))}
 
     def apply(self, op, x, coeff=None, out=None, exchange=True, flags=0, x_next=None, pipeline_last=False, **kw):
         """Ghost refresh of the inputs + local apply.  For the element kernels the refresh runs on a side stream
@@ -426,21 +487,28 @@ class DistributedEngine:
         x_next, the input of the NEXT call, and consumes what the previous call (or prologue_push) sent for x;
         pipeline_last=True ends such a sequence (consume only)."""
         if op not in self.SUPPORTED:
-            raise NotImplementedError("operator %s is not partitioned yet (0-form operators need node ownership)" % op)
+            raise NotImplementedError("operator %s" % op)
         torch = self.torch
         sin, sout, sc = self.engine.SPACES[op]
-        need_x, need_c = self.NEEDS[op]
-        do_x = exchange and need_x
-        do_c = exchange and need_c and coeff is not None
+        need = self.NEEDS[op] if exchange else {}
+        fields = dict(x=x, c=coeff, u1=kw.get("u1"))
+        todo = [(fields[k], sp, how == "ext") for k, (sp, how) in need.items() if fields[k] is not None]
+        do_x = "x" in need
+        do_c = "c" in need and coeff is not None
         if out is None:
             out = self.engine.zeros(self.engine.space_sizes(op)[1], x.shape[1])
-        if not (do_x or do_c):
+        if not todo:
+            return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
+        if op not in ("M1", "M1h", "K"):
+            # not on the hot path: refresh, then apply (E21 / E12 / UtQW and the 0-form family)
+            for f, sp, ext in todo:
+                self.exchange(f, sp, ext=ext)
             return self.engine.apply(op, x, coeff=coeff, out=out, flags=flags, **kw)
         if op == "M1" and self.p2p is not None and self.fused and self._fused_ok(x, kw):
             return self._apply_m1_fused(x, out, flags, x_next=x_next, mode=3 if pipeline_last else None, **kw)
         if x_next is not None or pipeline_last:
             raise NotImplementedError("pipelined ghost refresh needs the fused M1 path")
-        overlap = self.overlap and op in ("M1", "M1h", "K") and self.n_interior > 0
+        overlap = self.overlap and self.n_interior > 0
         if overlap and self.p2p is not None:
             # side stream: push kernels (store into the peers' inboxes over NVLink) and pull kernels (wait for the
             # peers' flags, fill my ghost rows); main stream: interior elements meanwhile, boundary elements after
@@ -584,6 +652,6 @@ class DistributedEngine:
     def owned_to_global(self, field, space, out_global):
         """write the owned rows of a local column tensor into a numpy (nlev, N_space) global array"""
         loc = self.engine.to_levels(field, space).cpu().numpy()
-        n_own = {1: self.part.n1_owned, 2: self.part.n2_owned}[space]
+        n_own = self.part.n_owned(space)
         out_global[:, self.part.owned_global(space)] = loc[:, :n_own]
         return out_global

@@ -28,29 +28,43 @@ def main():
         mesh = mb.Mesh(kind, p, ne)
         if what == "golden":
             g = golden("ops_eul_sphere_p3_ne4.npz")
-            thick, f = g["thick"], {k: g[k] for k in ("x1", "x2", "h2", "u1")}
+            thick, f = g["thick"], {k: g[k] for k in ("x1", "x2", "x0", "h2", "u1", "q0")}
         else:
             thick = synthetic_thickness(mesh.xyz, nk, kind)
             f = synthetic_fields(np.random.default_rng(5), nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+            f["q0"] = np.random.default_rng(6).uniform(-1, 1, (nk, mesh.N0)) * 1e-4
         deng = DistributedEngine(mesh, thick, rank, world, local)
         single = mb.Engine.from_mesh(mesh, local, thick=thick) if rank == 0 else None
+        # all fourteen operators of the path (+ UtQW): 1- and 2-form operators, then the 0-form family (node-partitioned:
+        # M0, M0h, E01, M0h_up sum over the elements around a node; E10, R, R_up read node values of their elements)
+        f["uu"] = f["u1"] * 1.0e-3
         ops = [("M1", "x1", None, 1), ("M1h", "x1", "h2", 2), ("M2", "x2", None, 1), ("M2h", "x2", "h2", 2), ("K", "x1", "u1", 2),
-               ("E21", "x1", None, 0), ("E12", "x2", None, 0)]
+               ("E21", "x1", None, 0), ("E12", "x2", None, 0), ("UtQW", "x2", "u1", 0),
+               ("M0", "x0", None, 1), ("M0h", "x0", "h2", 2), ("E10", "x0", None, 0), ("E01", "x1", None, 0), ("R", "x1", "q0", 2),
+               ("R_up", "x1", "q0", 0), ("M0h_up", "x0", "h2", 0)]
         for op, xk, ck, tpow in ops:
             sin, sout, sc = deng.engine.SPACES[op]
             x = deng.scatter_from_global(f[xk], sin)
-            n_own_in = {1: deng.part.n1_owned, 2: deng.part.n2_owned}[sin]
+            n_own_in = deng.part.n_owned(sin)
             perm_in = torch.from_numpy(deng.engine.permutation(sin).astype(np.int64)).cuda()
             x[perm_in[n_own_in:]] = 0.0                       # ghosts must come from the exchange
             c = None
             if ck is not None:
                 c = deng.scatter_from_global(f[ck], sc)
-                n_own_c = {1: deng.part.n1_owned, 2: deng.part.n2_owned}[sc]
+                n_own_c = deng.part.n_owned(sc)
                 perm_c = torch.from_numpy(deng.engine.permutation(sc).astype(np.int64)).cuda()
                 c[perm_c[n_own_c:]] = 0.0
             kw = dict(scale=1e8, tpow=tpow) if op[0] != "E" else {}
+            if op == "UtQW":
+                kw = dict(scale=1e8)
+            skw = dict(kw)
+            if op in ("R_up", "M0h_up"):
+                u = deng.scatter_from_global(f["uu"], 1)
+                perm_u = torch.from_numpy(deng.engine.permutation(1).astype(np.int64)).cuda()
+                u[perm_u[deng.part.n1_owned:]] = 0.0
+                kw.update(u1=u, tau=150.0)
             y = deng.apply(op, x, coeff=c, **kw)
-            N = {1: mesh.N1, 2: mesh.N2}[sout]
+            N = {0: mesh.N0, 1: mesh.N1, 2: mesh.N2}[sout]
             yg = np.zeros((f[xk].shape[0], N))
             deng.owned_to_global(y, sout, yg)
             t = torch.from_numpy(yg).cuda()
@@ -58,7 +72,9 @@ def main():
             if rank == 0:
                 yg = t.cpu().numpy()
                 cs = None if ck is None else to_cols(single, f[ck], sc)
-                ys = to_np(single, single.apply(op, to_cols(single, f[xk], sin), coeff=cs, **kw), sout)
+                if op in ("R_up", "M0h_up"):
+                    skw.update(u1=to_cols(single, f["uu"], 1), tau=150.0)
+                ys = to_np(single, single.apply(op, to_cols(single, f[xk], sin), coeff=cs, **skw), sout)
                 if not np.array_equal(yg, ys):
                     failures.append((what, kind, p, ne, op, "differs from single GPU", rel_l2(yg, ys)))
                 if what == "golden":

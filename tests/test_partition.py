@@ -91,19 +91,22 @@ def _worker(rank, world, port, q):
         part, sends = send_lists(mesh, rank, world)
         rng = np.random.default_rng(0)
         ok = True
-        for space, N in ((1, mesh.N1), (2, mesh.N2)):
+        # the rows the element kernels read (spaces 0, 1, 2) and, for the node-sum operators, ALL ghost rows (ext)
+        for space, N, ext in ((0, mesh.N0, False), (1, mesh.N1, False), (2, mesh.N2, False), (1, mesh.N1, True), (2, mesh.N2, True)):
             glob = rng.uniform(-1, 1, (N, 3))                 # same on every rank
-            g = {1: part.g1, 2: part.g2}[space]
-            n_own = {1: part.n1_owned, 2: part.n2_owned}[space]
+            g = {0: part.g0, 1: part.g1, 2: part.g2}[space]
+            n_own = part.n_owned(space)
+            recv = (part.recv_ext if ext else part.recv)[space]
+            send = (part.sends_ext if ext else sends)[space]
             loc = torch.zeros((len(g), 3), dtype=torch.float64)
             loc[:n_own] = torch.from_numpy(glob[g[:n_own]])   # ghosts start as zero
             ops, unpack = [], []
-            for peer in sorted(set(part.recv[space]) | set(sends[space])):
-                if peer in sends[space]:
-                    sb = loc[torch.from_numpy(sends[space][peer].astype(np.int64))].contiguous()
+            for peer in sorted(set(recv) | set(send)):
+                if peer in send:
+                    sb = loc[torch.from_numpy(send[peer].astype(np.int64))].contiguous()
                     ops.append(dist.P2POp(dist.isend, sb, peer))
-                if peer in part.recv[space]:
-                    rows = torch.from_numpy(part.recv[space][peer]["local"].astype(np.int64))
+                if peer in recv:
+                    rows = torch.from_numpy(recv[peer]["local"].astype(np.int64))
                     rb = torch.empty((len(rows), 3), dtype=torch.float64)
                     ops.append(dist.P2POp(dist.irecv, rb, peer))
                     unpack.append((rows, rb))
@@ -111,10 +114,11 @@ def _worker(rank, world, port, q):
                 w.wait()
             for rows, rb in unpack:
                 loc[rows] = rb
-            # every row some kernel reads is filled (1-forms: rows beyond n1_halo belong to halo elements but are never read)
-            n_filled = part.n1_halo if space == 1 else len(g)
+            # minimal plans fill the rows some element kernel reads (rows beyond n*_halo belong to halo elements but are
+            # only read by the node-sum operators); the ext plans and the node plan fill every ghost row
+            n_filled = len(g) if (ext or space == 0) else {1: part.n1_halo, 2: part.n2_halo}[space]
             ok = ok and bool(np.array_equal(loc.numpy()[:n_filled], glob[g][:n_filled]))
-            ok = ok and (space != 1 or n_filled < len(g))
+            ok = ok and (ext or space != 1 or n_filled < len(g))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
