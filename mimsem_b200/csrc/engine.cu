@@ -13,6 +13,7 @@
 #include "errors.hpp"
 #include "kernels.cuh"
 #include "launch.hpp"
+#include "m2_tile.cuh"
 
 using namespace mimsem;
 
@@ -111,7 +112,14 @@ struct mimsem_gpu_ctx {
     DevBuf<TileHdr> d_recs_k;           // K (WtQUmat) tile records
     int rec_stride_k = 0;
     bool k_plan_ok = false;
-    DevBuf<double> d_geo, d_geo_h, d_geo_k;
+    DevBuf<TileHdr> d_recs_m2, d_recs_m2h;   // M2 / M2(rho) tile records
+    int rec_stride_m2 = 0, rec_stride_m2h = 0;
+    bool m2_plan_ok = false;
+    int m2_variant = 1;                      // 1: TMA tile kernel (default), 0: one thread per element-level
+    DevBuf<int> d_inc_recs;                  // per owned element: e1, f0, xe[P], yn[P], wf[P], sf[P] (k_inc_tile)
+    bool inc_plan_ok = false;
+    int inc_variant = 1;                     // 1: element kernel for E21 / E12 (default), 0: ELL stencils
+    DevBuf<double> d_geo, d_geo_h, d_geo_k, d_geo_m2, d_geo_m2h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
     DevBuf<double> d_tmean;   // [nq][nkT]: mean thickness of levels k and k+1 (Ut_mat::assemble), selected by MIMSEM_THICK_MEAN
@@ -365,6 +373,47 @@ int build_incidence(mimsem_gpu_ctx* c) {
     if ((rc = upload_ell(c->n2, s21, c->ell[MIMSEM_E21], all ? nullptr : &rows21, nullptr, pm))) return rc;
     if ((rc = upload_ell(c->n0, s01, c->ell[MIMSEM_E01], nullptr, nullptr, pm))) return rc;
     if ((rc = upload_ell(c->n1, s12, c->ell[MIMSEM_E12], nullptr, pm, nullptr))) return rc;
+    return MIMSEM_OK;
+}
+
+// Records of the element kernel for E21 / E12 (k_inc_tile): needs the engine's contiguous edge and face blocks
+int build_inc_plan(mimsem_gpu_ctx* c) {
+    const int P = c->p, NP1 = P + 1, N1E = P * NP1, N2E = P * P;
+    c->inc_plan_ok = false;
+    // the face on the far side of every edge that is some element's EAST or NORTH edge (the -1 entry of its E12 row)
+    std::vector<int> far_face(c->n1, -1);
+    for (int e = 0; e < c->nel_total; e++) {
+        const int* ix = &c->h_el1x[(size_t)e * N1E];
+        const int* iy = &c->h_el1y[(size_t)e * N1E];
+        const int* i2 = &c->h_el2[(size_t)e * N2E];
+        for (int b = 0; b < P; b++) {
+            far_face[ix[b * NP1 + P]] = i2[b * P + P - 1];          // east column  <- face (P-1, b)
+            far_face[iy[P * P + b]] = i2[(P - 1) * P + b];          // north row    <- face (b, P-1)
+        }
+    }
+    const int W = 2 + 4 * P;
+    std::vector<int> rec((size_t)c->nel_owned * W);
+    for (int e = 0; e < c->nel_owned; e++) {
+        const int* ix = &c->h_el1x[(size_t)e * N1E];
+        const int* iy = &c->h_el1y[(size_t)e * N1E];
+        const int* i2 = &c->h_el2[(size_t)e * N2E];
+        int* r = &rec[(size_t)e * W];
+        r[0] = ix[0];
+        r[1] = i2[0];
+        for (int j = 0; j < N2E; j++)
+            if (i2[j] != i2[0] + j) return MIMSEM_OK;                                   // faces not contiguous: keep the ELL kernels
+        for (int a = 0; a < P; a++)
+            for (int b = 0; b < P; b++)
+                if (ix[b * NP1 + a] != r[0] + a * P + b || iy[b * P + a] != r[0] + P * P + b * P + a) return MIMSEM_OK;
+        for (int b = 0; b < P; b++) {
+            r[2 + b] = ix[b * NP1 + P];
+            r[2 + P + b] = iy[P * P + b];
+            r[2 + 2 * P + b] = far_face[ix[b * NP1]];     // across my west edge xx(0, b)
+            r[2 + 3 * P + b] = far_face[iy[b]];           // across my south edge xy(b, 0)
+        }
+    }
+    CUDA_OK(c->d_inc_recs.upload(rec));
+    c->inc_plan_ok = true;
     return MIMSEM_OK;
 }
 
@@ -623,6 +672,66 @@ int build_k_plan_p(mimsem_gpu_ctx* c) {
     return MIMSEM_OK;
 }
 
+// Tile records of the M2 / M2(rho) kernel (M2Slots): the element's faces, thickness, optionally the coefficient's faces
+template <int P>
+int build_m2_plan_p(mimsem_gpu_ctx* c) {
+    using S = M2Slots<P>;
+    constexpr int NP1 = P + 1, N2E = P * P, Q2 = NP1 * NP1;
+    bool ok = true;
+    for (int with_h = 0; with_h < 2; with_h++) {
+        std::vector<std::vector<CopyEnt>> ents(c->nel_owned);
+        std::vector<TileHdr> hdr(c->nel_owned);
+        int nents = 1;
+        for (int e = 0; e < c->nel_owned; e++) {
+            const int* e2 = &c->h_el2[(size_t)e * N2E];
+            std::vector<std::pair<int, int>> xs, ts;
+            for (int j = 0; j < N2E; j++) xs.push_back({e2[j], S::X + j});
+            for (int q = 0; q < Q2; q++) ts.push_back({c->h_elq[(size_t)e * Q2 + q], S::T + q});
+            auto runs = [&](const std::vector<std::pair<int, int>>& ds, int kind, int slot_off) {
+                size_t i = 0;
+                while (i < ds.size()) {
+                    size_t j = i + 1;
+                    while (j < ds.size() && ds[j].first == ds[j - 1].first + 1 && ds[j].second == ds[j - 1].second + 1) j++;
+                    ents[e].push_back(CopyEnt{kind, ds[i].first, ds[i].second + slot_off, (int)(j - i)});
+                    i = j;
+                }
+            };
+            ents[e].push_back(CopyEnt{3, e, 0, 1});
+            runs(xs, 0, 0);
+            if (with_h) runs(xs, 1, S::H - S::X);
+            runs(ts, 2, 0);
+            for (int j = 0; j < N2E; j++)
+                if (e2[j] != e2[0] + j) ok = false;
+            TileHdr h;
+            h.st_dof = e2[0];
+            h.cp_count = (int)ents[e].size();
+            h.flags = 0;
+            h.nslots = (int)((with_h ? 2 : 1) * xs.size()) | ((int)ts.size() << 20);
+            hdr[e] = h;
+            nents = std::max(nents, h.cp_count);
+        }
+        std::vector<TileHdr> rec((size_t)c->nel_owned * (1 + nents), TileHdr{0, 0, 0, 0});
+        for (int e = 0; e < c->nel_owned; e++) {
+            rec[(size_t)e * (1 + nents)] = hdr[e];
+            std::memcpy(&rec[(size_t)e * (1 + nents) + 1], ents[e].data(), ents[e].size() * sizeof(CopyEnt));
+        }
+        CUDA_OK((with_h ? c->d_recs_m2h : c->d_recs_m2).upload(rec));
+        (with_h ? c->rec_stride_m2h : c->rec_stride_m2) = 1 + nents;
+    }
+    c->m2_plan_ok = ok;
+    return MIMSEM_OK;
+}
+
+// geometry records of the M2 tile kernel: the point weights w/det (M2) resp. w/det^2 (M2h), padded to an even count
+int build_m2_geo(mimsem_gpu_ctx* c, const std::vector<double>& W, DevBuf<double>& out) {
+    const int Q2 = (c->p + 1) * (c->p + 1), GM = (Q2 + 1) / 2 * 2;
+    std::vector<double> geo((size_t)c->nel_owned * GM, 0.0);
+    for (int e = 0; e < c->nel_owned; e++)
+        for (int q = 0; q < Q2; q++) geo[(size_t)e * GM + q] = W[(size_t)e * Q2 + q];
+    CUDA_OK(out.upload(geo));
+    return MIMSEM_OK;
+}
+
 // geometry records of the M1 tile kernel: gl[part][line][q] = (g_own, g_oth) of the element's own lines, then the
 // (g_own, g_oth) pairs of the west and south far lines (M1Slots)
 template <int P>
@@ -845,6 +954,30 @@ int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     a.y = y;
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads == 0) return MIMSEM_OK;
+    // TMA tile kernel (same eligibility as M1's)
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
+    const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
+    if (c->m2_variant != 0 && c->m2_plan_ok && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64) {
+        TArgs t;
+        std::memset(&t, 0, sizeof(t));
+        t.nlev = nlev; t.ld = ld; t.lev0 = lev0; t.nkT = c->nkT; t.tpow = tpow;
+        t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
+        t.scale = scale;
+        t.prefetch_ahead = c->prefetch_ahead * 2;   // 64-thread CTAs: about twice as many tiles are resident
+        t.prefetch_own_slots = c->p * c->p;
+        t.elist = a.elist;
+        t.recs = with_h ? c->d_recs_m2h.p : c->d_recs_m2.p;
+        t.rec_stride = with_h ? c->rec_stride_m2h : c->rec_stride_m2;
+        t.rec_hdr = 1;
+        t.geo = with_h ? c->d_geo_m2h.p : c->d_geo_m2.p;
+        t.x = x; t.c = h2; t.tinv = a.tinv; t.y = y;
+        copy_basis(c, t);
+        for (size_t i = 0; i < sizeof(t.E) / sizeof(double); i++) t.Es[i] = scale * t.E[i];
+        std::string err;
+        const int rc3 = launch_m2_tile(c->p, with_h, t, a.nel, st, &err);
+        if (rc3 < 0) return fail(MIMSEM_ERR_CUDA, err);
+        if (rc3 == 0) return finish_launch(c, "apply_M2 (tile)");
+    }
     launch_m2(c->p, with_h, a, grid_for(threads, 128), st);
     return finish_launch(c, "apply_M2");
 }
@@ -1176,6 +1309,18 @@ int apply_inc(mimsem_gpu_ctx* c, int which, int nlev, int ld, const double* x, d
         a.div_s = fd.s;
     }
     if (a.nrows == 0) return MIMSEM_OK;
+    if ((which == MIMSEM_E21 || which == MIMSEM_E12) && c->inc_variant != 0 && c->inc_plan_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64 &&
+        (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+        IncArgs ia;
+        ia.nel = c->nel_owned;
+        ia.nl2 = nlev / 2;
+        ia.ld = ld;
+        ia.recs = c->d_inc_recs.p;
+        ia.x = x;
+        ia.y = y;
+        launch_inc_tile(c->p, which == MIMSEM_E21, ia, (cudaStream_t)st);
+        return finish_launch(c, "apply_incidence (element kernel)");
+    }
     if (a.width > 4) return fail(MIMSEM_ERR_UNSUPPORTED, "incidence stencil wider than 4");
     const int vmax = c->ell_vec;
     if (vmax >= 4 && nlev % 4 == 0 && ld % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
@@ -1286,9 +1431,9 @@ int mimsem_gpu_create(int device, mimsem_gpu_ctx** out) {
         return fail(MIMSEM_ERR_CUDA, cudaGetErrorString(e));
     }
     // test / tuning knobs: the environment is consulted here, once -- never on a launch path
-    static const char* const names[] = {"m1_variant", "k_variant", "ell_vec", "prefetch_ahead", "m1_min_blocks", "host_chunk"};
-    static const char* const envs[] = {"MIMSEM_M1_VARIANT", "MIMSEM_K_VARIANT", "MIMSEM_ELL_VEC", "MIMSEM_PREFETCH", "MIMSEM_M1_MINB", "MIMSEM_HOST_CHUNK"};
-    for (int i = 0; i < 6; i++)
+    static const char* const names[] = {"m1_variant", "k_variant", "ell_vec", "prefetch_ahead", "m1_min_blocks", "host_chunk", "m2_variant", "inc_variant"};
+    static const char* const envs[] = {"MIMSEM_M1_VARIANT", "MIMSEM_K_VARIANT", "MIMSEM_ELL_VEC", "MIMSEM_PREFETCH", "MIMSEM_M1_MINB", "MIMSEM_HOST_CHUNK", "MIMSEM_M2_VARIANT", "MIMSEM_INC_VARIANT"};
+    for (int i = 0; i < 8; i++)
         if (const char* v = getenv(envs[i])) mimsem_gpu_set_option(c, names[i], atoll(v));
     *out = c;
     return MIMSEM_OK;
@@ -1300,6 +1445,8 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     const int v = (int)value;
     if (n == "m1_variant" && v >= 0 && v <= 2) c->m1_variant = v;
     else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
+    else if (n == "m2_variant" && v >= 0 && v <= 1) c->m2_variant = v;
+    else if (n == "inc_variant" && v >= 0 && v <= 1) c->inc_variant = v;
     else if (n == "ell_vec" && (v == 1 || v == 2 || v == 4)) c->ell_vec = v;
     else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
@@ -1410,6 +1557,7 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
     for (auto& v : c->h_el1y) v = c->h_perm1[v];
     if ((rc = build_neighbours(c))) return rc;
     if ((rc = build_node_adjacency(c))) return rc;
+    if ((rc = build_inc_plan(c))) return rc;
     {
         // column-major copies so that every GLL line of an element is contiguous (line-task kernels)
         const int N1E = P * NP1, Q2 = NP1 * NP1;
@@ -1440,6 +1588,15 @@ int mimsem_gpu_set_topo(mimsem_gpu_ctx* c, int nel_total, int nel_owned, int n0,
         }
         if (rc) return rc;
     }
+    c->m2_plan_ok = false;
+    switch (P) {
+        case 2: rc = build_m2_plan_p<2>(c); break;
+        case 3: rc = build_m2_plan_p<3>(c); break;
+        case 4: rc = build_m2_plan_p<4>(c); break;
+        case 5: rc = build_m2_plan_p<5>(c); break;
+        default: rc = MIMSEM_OK;
+    }
+    if (rc) return rc;
     c->k_plan_ok = false;
     switch (P) {
         case 2: rc = build_k_plan_p<2>(c); break;
@@ -1581,6 +1738,8 @@ int mimsem_gpu_set_geom(mimsem_gpu_ctx* c, const double* h_J, const double* h_de
         if (rc) return rc;
         if ((rc = build_k_geo(c, G1h, c->d_geo_k))) return rc;
     }
+    if ((rc = build_m2_geo(c, W2, c->d_geo_m2))) return rc;
+    if ((rc = build_m2_geo(c, W2h, c->d_geo_m2h))) return rc;
     CUDA_OK(c->d_G1.upload(G1));
     CUDA_OK(c->d_G1h.upload(G1h));
     CUDA_OK(c->d_W2.upload(W2));

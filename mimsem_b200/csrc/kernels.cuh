@@ -1157,6 +1157,92 @@ __global__ void __launch_bounds__(256) k_rows(int64_t nrows, int nlev, int ld, u
     else dst[(size_t)rows[i] * ld + k] = src[idx];
 }
 
+// E21 (div) and E12 = -E21^T (weak gradient) element by element, without index loads: one record of 2 + 4 P row numbers per
+// owned element -- its first edge row and first face row (both blocks are contiguous in the engine's numbering), its
+// east column / north row of edges (E21) and the faces across its west column / south row (E12; -1 where the mesh
+// ends) -- and closed-form positions inside the blocks.  A thread owns one element and two adjacent levels (16-byte
+// accesses, lanes along the levels).  The sums run in the order of the reference's MatSetValues calls (E21: -x(a,b)
+// +x(a+1,b) -y(a,b) +y(a,b+1), eul/Assembly.cpp:1196-1205; E12: the edge's own face first), exactly as the ELL kernel
+// does, so integer data stays exact and the two kernels agree bitwise.
+struct IncArgs {
+    int nel, nl2, ld;            // owned elements, level PAIRS per row, leading dimension
+    const int* recs;             // [nel][2 + 4 P]: e1, f0, xe[P], yn[P], wf[P], sf[P]
+    const double* x;
+    double* y;
+};
+
+template <int P, bool DIV>
+__global__ void __launch_bounds__(128) k_inc_tile(const __grid_constant__ IncArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= a.nel || lane >= a.nl2) return;
+    const int* __restrict__ r = a.recs + (size_t)e * (2 + 4 * P);
+    const int e1 = r[0], f0 = r[1];
+    const size_t ld = a.ld;
+    const double2* __restrict__ x = reinterpret_cast<const double2*>(a.x) + lane;
+    double2* __restrict__ y = reinterpret_cast<double2*>(a.y) + lane;
+    auto ldx = [&](int row) { return __ldg(x + (size_t)row * (ld >> 1)); };
+    const double2 zero = make_double2(0.0, 0.0);
+    if (DIV) {
+        // faces row by row: y_f(a,b) = ((0 - xx(a,b)) + xx(a+1,b)) - xy(a,b)) + xy(a,b+1)
+        double2 ylo[P];
+#pragma unroll
+        for (int a_ = 0; a_ < P; a_++) ylo[a_] = ldx(e1 + P * P + a_);   // xy(a, 0)
+#pragma unroll
+        for (int b = 0; b < P; b++) {
+            double2 xv[P + 1], yhi[P];
+#pragma unroll
+            for (int a_ = 0; a_ < P; a_++) xv[a_] = ldx(e1 + a_ * P + b);            // xx(a, b): column-major block
+            xv[P] = ldx(r[2 + b]);                                                   // east column
+#pragma unroll
+            for (int a_ = 0; a_ < P; a_++) yhi[a_] = (b + 1 < P) ? ldx(e1 + P * P + (b + 1) * P + a_) : ldx(r[2 + P + a_]);   // xy(a, b+1)
+#pragma unroll
+            for (int a_ = 0; a_ < P; a_++) {
+                double2 s;
+                s.x = 0.0 - xv[a_].x; s.y = 0.0 - xv[a_].y;
+                s.x += xv[a_ + 1].x;  s.y += xv[a_ + 1].y;
+                s.x -= ylo[a_].x;     s.y -= ylo[a_].y;
+                s.x += yhi[a_].x;     s.y += yhi[a_].y;
+                y[(size_t)(f0 + b * P + a_) * (ld >> 1)] = s;
+                ylo[a_] = yhi[a_];
+            }
+        }
+    } else {
+        // edges: y_x(a,b) = (0 + f(a,b)) - f(a-1,b) ; y_y(a,b) = (0 + f(a,b)) - f(a,b-1)
+        double2 f[P][P];
+#pragma unroll
+        for (int b = 0; b < P; b++)
+#pragma unroll
+            for (int a_ = 0; a_ < P; a_++) f[b][a_] = ldx(f0 + b * P + a_);
+#pragma unroll
+        for (int b = 0; b < P; b++) {
+            const int wr = r[2 + 2 * P + b];
+            const double2 w = wr >= 0 ? ldx(wr) : zero;
+#pragma unroll
+            for (int a_ = 0; a_ < P; a_++) {
+                const double2 o = a_ > 0 ? f[b][a_ - 1] : w;
+                double2 s;
+                s.x = (0.0 + f[b][a_].x) - o.x; s.y = (0.0 + f[b][a_].y) - o.y;
+                if (a_ == 0 && wr < 0) s = f[b][a_];
+                y[(size_t)(e1 + a_ * P + b) * (ld >> 1)] = s;
+            }
+        }
+#pragma unroll
+        for (int a_ = 0; a_ < P; a_++) {
+            const int sr = r[2 + 3 * P + a_];
+            const double2 sv = sr >= 0 ? ldx(sr) : zero;
+#pragma unroll
+            for (int b = 0; b < P; b++) {
+                const double2 o = b > 0 ? f[b - 1][a_] : sv;
+                double2 s;
+                s.x = (0.0 + f[b][a_].x) - o.x; s.y = (0.0 + f[b][a_].y) - o.y;
+                if (b == 0 && sr < 0) s = f[b][a_];
+                y[(size_t)(e1 + P * P + b * P + a_) * (ld >> 1)] = s;
+            }
+        }
+    }
+}
+
 // L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): 2-form fields between the engine's column layout
 // cols[el2[e][i]*ld + k] and the reference's per-element vertical vectors vert[e][k*p2 + i] (vz[ei] of size nk*p2, all
 // elements back to back).  A pure relabelling -- bit exact -- through a padded shared-memory tile, one CTA per element,

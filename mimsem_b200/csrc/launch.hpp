@@ -6,6 +6,7 @@
 #include <string>
 
 #include "engine.cuh"
+#include "kernels.cuh"
 
 namespace mimsem {
 
@@ -22,6 +23,7 @@ struct M1TileLaunch {
 // return: 0 launched, 1 not applicable (tile does not fit in shared memory: use a register kernel), < 0 CUDA error (*err set)
 int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string* err);
 int launch_k_tile(int p, TArgs& t, int nel, cudaStream_t st, std::string* err);
+int launch_m2_tile(int p, bool with_h, TArgs& t, int nel, cudaStream_t st, std::string* err);
 
 void launch_m1_regs(int p, bool with_h, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m1_lines(int p, bool with_h, bool far, const KArgs& a, dim3 grid, cudaStream_t st);
@@ -32,6 +34,7 @@ void launch_k_regs(int p, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_rot(int p, bool up, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m0h_up(int p, const NodeArgs& a, unsigned grid, cudaStream_t st);
 void launch_m0(int p, bool with_h, const NodeArgs& a, unsigned grid, cudaStream_t st);
+void launch_inc_tile(int p, bool div, const IncArgs& a, cudaStream_t st);
 
 // p = 2..5 -> integral_constant dispatch (callers have validated p)
 template <class F>

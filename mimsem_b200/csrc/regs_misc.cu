@@ -33,6 +33,15 @@ int launch_solve_m2(int p, bool with_h, const KArgs& a, cudaStream_t st, std::st
     return rc;
 }
 
+void launch_inc_tile(int p, bool div, const IncArgs& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.nel + 3) / 4);
+    for_p(p, [&](auto Pc) {
+        constexpr int P = decltype(Pc)::value;
+        if (div) k_inc_tile<P, true><<<grid, 128, 0, st>>>(a);
+        else k_inc_tile<P, false><<<grid, 128, 0, st>>>(a);
+    });
+}
+
 void launch_k_regs(int p, const KArgs& a, unsigned grid, cudaStream_t st) {
     for_p(p, [&](auto Pc) { k_apply_k<decltype(Pc)::value><<<grid, 128, 0, st>>>(a); });
 }

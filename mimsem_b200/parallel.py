@@ -276,8 +276,9 @@ class DistributedEngine:
         self._inbox = {}
         import os
         self.fused = os.environ.get("MIMSEM_FUSED_HALO", "1") != "0"
-        # fused M1: hand the ghost rows over in self-validating 16-byte cells (no fence, no flag) instead of data + flag
-        self.ll = os.environ.get("MIMSEM_HALO_LL", "1") != "0"
+        # fused M1: data + flag (default), or self-validating 16-byte cells without fence and flag (MIMSEM_HALO_LL=1;
+        # measured slower at 2 and 4 GPUs, see profiles/r02_summary.md)
+        self.ll = os.environ.get("MIMSEM_HALO_LL", "0") != "0"
         if world > 1 and os.environ.get("MIMSEM_HALO", "p2p") == "p2p":
             self._setup_p2p(P, sends)
 

@@ -344,6 +344,26 @@ def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
 
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
                                           ("sphere", 5, 2, 20)])
+def test_m2_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
+    """M2 / M2(rho) (Wmat, Whmat): the TMA tile kernel (default) and the thread-per-element-level kernel agree up to FP
+    summation order; the tile kernel is pinned to the reference by the golden-vector and oracle tests above."""
+    mesh = mb.Mesh(kind, p, ne)
+    thick = synthetic_thickness(mesh.xyz, nk, kind)
+    rng = np.random.default_rng(13)
+    f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
+    res = {}
+    for variant in ("0", "1"):
+        monkeypatch.setenv("MIMSEM_M2_VARIANT", variant)
+        eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
+        res[variant] = (_apply(eng, "M2", f["x2"], scale=1e8, tpow=1), _apply(eng, "M2h", f["x2"], f["h2"], scale=1e8, tpow=2),
+                        _apply(eng, "M2", f["x2"], scale=1.0, tpow=0))
+        eng.close()
+    for a, b in zip(res["1"], res["0"]):
+        assert rel_l2(a, b) < 1e-14, rel_l2(a, b)
+
+
+@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
+                                          ("sphere", 5, 2, 20)])
 def test_k_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
     """K (WtQUmat): the TMA tile kernel (default) and the thread-per-element-level kernel agree up to FP summation order."""
     mesh = mb.Mesh(kind, p, ne)
