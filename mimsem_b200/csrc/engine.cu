@@ -119,6 +119,7 @@ struct mimsem_gpu_ctx {
     DevBuf<int> d_inc_recs;                  // per owned element: e1, f0, xe[P], yn[P], wf[P], sf[P] (k_inc_tile)
     bool inc_plan_ok = false;
     int inc_variant = 1;                     // 1: element kernel for E21 / E12 (default), 0: ELL stencils
+    int stream_stores = 0;                   // M1 tile kernel: streaming stores for the output
     DevBuf<double> d_geo, d_geo_h, d_geo_k, d_geo_m2, d_geo_m2h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
@@ -885,6 +886,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.scale = scale;
         t.prefetch_ahead = c->prefetch_ahead;
         t.prefetch_own_slots = 2 * c->p * c->p;
+        t.stream_stores = c->stream_stores;
         t.elist = a.elist;
         t.recs = with_h ? c->d_recs_h.p : c->d_recs.p;
         t.rec_stride = with_h ? c->rec_stride_h : c->rec_stride;
@@ -1447,6 +1449,7 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
     else if (n == "m2_variant" && v >= 0 && v <= 1) c->m2_variant = v;
     else if (n == "inc_variant" && v >= 0 && v <= 1) c->inc_variant = v;
+    else if (n == "stream_stores" && v >= 0 && v <= 1) c->stream_stores = v;
     else if (n == "ell_vec" && (v == 1 || v == 2 || v == 4)) c->ell_vec = v;
     else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;

@@ -45,6 +45,7 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
             if constexpr (P == 4) {   // register-budget variants kept for tuning runs (mimsem_gpu_set_option "m1_min_blocks")
                 if (l.min_blocks == 5) kern = pick_nl<P, false, 0, 5>(t.nlev, t.tpow);
                 if (l.min_blocks == 6) kern = pick_nl<P, false, 0, 6>(t.nlev, t.tpow);
+                if (l.min_blocks == 7) kern = pick_nl<P, false, 0, 7>(t.nlev, t.tpow);
             }
         }
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

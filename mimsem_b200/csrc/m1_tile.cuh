@@ -427,7 +427,7 @@ __device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part)
 // record is laid out per part for this, gl[part][line][q] = (g_own, g_oth):
 //   part 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; part 1: f1 = c (Gbb ul1 + Gab ul0), ul1 = ua.
 // Each line is stored as soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
-template <int P, bool WITH_H, int NL, int TPOW>
+template <int P, bool WITH_H, int NL, int TPOW, bool OTH_REGS>
 __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, int part, const double (&cfar)[P],
                                            double* __restrict__ y) {
     using S = M1Slots<P>;
@@ -439,12 +439,16 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
     const double* tp = col + (size_t)S::T * nl;                          // thickness at point (line ln, q): tp[q sq + ln sl]
     const int sq = (part ? 1 : NP1) * nl, sl = (part ? NP1 : 1) * nl;
     const double* gl = geo + S::GL + part * (P * NP1 * 2);
-    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (part 0) / xx(qx=q, iy=t) (part 1): used P times each, kept in registers
-    double othr[P + 1][P];
+    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (part 0) / xx(qx=q, iy=t) (part 1) are used P times each: kept in
+    // registers (OTH_REGS), or -- in the lean variant that fits more resident tiles per SM -- read from shared memory at
+    // every use
+    double othr[OTH_REGS ? P + 1 : 1][OTH_REGS ? P : 1];
+    if (OTH_REGS) {
 #pragma unroll
-    for (int q = 0; q <= P; q++)
+        for (int q = 0; q <= P; q++)
 #pragma unroll
-        for (int t = 0; t < P; t++) othr[q][t] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
+            for (int t = 0; t < P; t++) othr[OTH_REGS ? q : 0][OTH_REGS ? t : 0] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
+    }
 #pragma unroll
     for (int ln = 0; ln < P; ln++) {
         double own[P];
@@ -457,7 +461,8 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
 #pragma unroll
             for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
 #pragma unroll
-            for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * othr[q][t];
+            for (int t = 0; t < P; t++)
+                ub += a.E[ln * P + t] * (OTH_REGS ? othr[OTH_REGS ? q : 0][OTH_REGS ? t : 0] : (q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl]));
             double g = gl[(ln * NP1 + q) * 2 + 0] * ua + gl[(ln * NP1 + q) * 2 + 1] * ub;
             if (WITH_H) {
                 g *= tp[q * sq + ln * sl];   // h_prepass left t^tpow * hl(q) in the thickness slot
@@ -476,7 +481,10 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
             double s = (ln == 0) ? cfar[j] : 0.0;
 #pragma unroll
             for (int q = 0; q <= P; q++) s += a.Es[q * P + j] * f[q];
-            y[(size_t)(ln * P + j) * a.ld] = s;
+            // the output is never read again by this launch: a streaming store keeps it from displacing the rows that
+            // neighbouring tiles and the L2 prefetch still need
+            if (a.stream_stores) __stcs(&y[(size_t)(ln * P + j) * a.ld], s);
+            else y[(size_t)(ln * P + j) * a.ld] = s;
         }
     }
 }
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
                 if (active) h_prepass<P, NL, TPOW>(a, col, part);
                 __syncthreads();
             }
-            if (active) tile_lines<P, WITH_H, NL, TPOW>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
+            if (active) tile_lines<P, WITH_H, NL, TPOW, (MINB < 6)>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
         }
         DBG_T(3);
         if (tile_i + tile_stride < a.ntiles) __syncthreads();   // the next tile's bulk loads overwrite the buffer
