@@ -222,6 +222,13 @@ int mimsem_gpu_solve_M0(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double 
                         const double* d_b, double* d_x, void* stream);
 int mimsem_gpu_diag_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                        double* d_diag, void* stream);
+/* z = blockdiag(M1)^-1 r with one block per owned element -- the preconditioner the reference selects for ksp1:
+ * PCBJACOBI with PCBJacobiSetTotalBlocks(pc, size * nElsX^2, NULL) (eul/HorizSolve.cpp:77-84).  With the reference's
+ * element-blocked edge numbering PETSc's equal consecutive row blocks are exactly the 2 p^2 edges each element owns.
+ * Every block is tabulated from closed forms, factorised (L D L^T) and solved in shared memory, one thread per
+ * (element, level); the arguments before d_r are those of the apply_M1 that defines the matrix.  Owner-computes mode. */
+int mimsem_gpu_pc_bjacobi_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_r,
+                             double* d_z, void* stream);
 
 /*
  * Remaining coefficient operators of the vorticity / forcing terms:
@@ -266,7 +273,7 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_s
  * (levels[k*n + dof]): copies in, converts, applies, converts back and copies out on the
  * engine's own streams.  op: 0 M1, 1 M2, 2 M0, 3 M1h, 4 K, 5 M2h, 6 M0h, 10+which incidence, 14 UtQW (h_coeff = u1, h_x the
  * 2-form), 15 / 16 diagonal of M0 / M0(h) (Pvec / Phvec; h_x is read but ignored), 17 / 18 M2^-1 / M2(rho)^-1 (WmatInv / WhmatInv),
- * 19 diagonal of M1 (MatGetDiagonal of the Umat shell).
+ * 19 diagonal of M1 (MatGetDiagonal of the Umat shell), 20 element-block Jacobi of M1 (h_x = r, h_y = z).
  * h_coeff may be NULL for operators without a coefficient field.
  */
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,

@@ -119,7 +119,6 @@ struct mimsem_gpu_ctx {
     DevBuf<int> d_inc_recs;                  // per owned element: e1, f0, xe[P], yn[P], wf[P], sf[P] (k_inc_tile)
     bool inc_plan_ok = false;
     int inc_variant = 1;                     // 1: element kernel for E21 / E12 (default), 0: ELL stencils
-    int stream_stores = 0;                   // M1 tile kernel: streaming stores for the output
     DevBuf<double> d_geo, d_geo_h, d_geo_k, d_geo_m2, d_geo_m2h;
     DevBuf<unsigned char> d_eflags;
     DevBuf<double> d_G1, d_G1h, d_W2, d_W2h, d_D0, d_wq, d_tinv;
@@ -886,7 +885,6 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.scale = scale;
         t.prefetch_ahead = c->prefetch_ahead;
         t.prefetch_own_slots = 2 * c->p * c->p;
-        t.stream_stores = c->stream_stores;
         t.elist = a.elist;
         t.recs = with_h ? c->d_recs_h.p : c->d_recs.p;
         t.rec_stride = with_h ? c->rec_stride_h : c->rec_stride;
@@ -1157,6 +1155,26 @@ int diag_m1(mimsem_gpu_ctx* c, bool invert, int lev0, int nlev, int ld, double s
     if (threads == 0) return MIMSEM_OK;
     launch_diag_m1(c->p, invert, a, grid_for(threads, 128), st);
     return finish_launch(c, "diag_M1");
+}
+
+// z = blockdiag(M1)^-1 r, one block per owned element (PCBJACOBI of eul/HorizSolve.cpp:77-84)
+int bjacobi_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* r, double* z, cudaStream_t st) {
+    int rc = check_ready(c, tpow > 0, lev0, nlev, ld, flags);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!r || !z) return fail(MIMSEM_ERR_ARG, "null field");
+    if (c->mode != 0) return fail(MIMSEM_ERR_UNSUPPORTED, "element-block Jacobi needs owner-computes mode");
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, tpow, flags);
+    a.G = c->d_G1.p;
+    a.x = r;
+    a.y = z;
+    if ((int64_t)a.nel * nlev == 0) return MIMSEM_OK;
+    std::string err;
+    const int rl = launch_bjacobi_m1(c->p, a, st, &err);
+    if (rl == -2) return fail(MIMSEM_ERR_UNSUPPORTED, err);
+    if (rl < 0) return fail(MIMSEM_ERR_CUDA, err);
+    return finish_launch(c, "pc_bjacobi_M1");
 }
 
 // HaloFused of one fused launch in mode 0 (push and consume the rows of `x` itself) from the C-ABI descriptor
@@ -1449,7 +1467,6 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
     else if (n == "m2_variant" && v >= 0 && v <= 1) c->m2_variant = v;
     else if (n == "inc_variant" && v >= 0 && v <= 1) c->inc_variant = v;
-    else if (n == "stream_stores" && v >= 0 && v <= 1) c->stream_stores = v;
     else if (n == "ell_vec" && (v == 1 || v == 2 || v == 4)) c->ell_vec = v;
     else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
@@ -1911,6 +1928,10 @@ int mimsem_gpu_solve_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double sc
                         double rtol, int maxit, int* iters, double* relres, void* st) {
     return solve_m1(c, lev0, nlev, ld, scale, tpow, flags, b, x, rtol, maxit, iters, relres, (cudaStream_t)st);
 }
+int mimsem_gpu_pc_bjacobi_M1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* r, double* z,
+                             void* st) {
+    return bjacobi_m1(c, lev0, nlev, ld, scale, tpow, flags, r, z, (cudaStream_t)st);
+}
 int mimsem_gpu_solve_M1_dist(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* b, double* x,
                              double rtol, int maxit, int* iters, double* relres, const mimsem_halo_desc* halo,
                              const mimsem_reduce_desc* reduce, void* st) {
@@ -1997,6 +2018,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         case 17: sin = sout = 2; break;                     // M2^-1 (WmatInv)
         case 18: sin = sout = 2; scoef = 2; break;          // M2(rho)^-1 (WhmatInv)
         case 19: sin = sout = 1; break;                     // diag M1 (MatGetDiagonal of the Umat shell): h_x is ignored
+        case 20: sin = sout = 1; break;                     // element-block Jacobi of M1 (PCBJACOBI of the Umat shell)
         default: return fail(MIMSEM_ERR_ARG, "unknown operator id");
     }
     const int64_t nsp[3] = {c->n0, c->n1, c->n2};
@@ -2063,6 +2085,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
             case 17: rc = solve_m2(c, false, levk, nl, nl, scale, tpow, flags, nullptr, xc, yc, st); break;
             case 18: rc = solve_m2(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
             case 19: rc = diag_m1(c, false, levk, nl, nl, scale, tpow, flags, yc, st); break;
+            case 20: rc = bjacobi_m1(c, levk, nl, nl, scale, tpow, flags, xc, yc, st); break;
             default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
         }
         if (rc) return rc;

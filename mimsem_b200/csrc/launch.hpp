@@ -27,6 +27,7 @@ int launch_m2_tile(int p, bool with_h, TArgs& t, int nel, cudaStream_t st, std::
 
 void launch_m1_regs(int p, bool with_h, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m1_lines(int p, bool with_h, bool far, const KArgs& a, dim3 grid, cudaStream_t st);
+int launch_bjacobi_m1(int p, const KArgs& a, cudaStream_t st, std::string* err);
 void launch_diag_m1(int p, bool invert, const KArgs& a, unsigned grid, cudaStream_t st);
 void launch_m2(int p, bool with_h, const KArgs& a, unsigned grid, cudaStream_t st);
 int launch_solve_m2(int p, bool with_h, const KArgs& a, cudaStream_t st, std::string* err);

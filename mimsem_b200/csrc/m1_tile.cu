@@ -19,6 +19,8 @@ void (*pick_nl(int nlev, int tpow))(const TArgs) {
 
 // register budget: CTAs per SM the shared-memory footprint allows at the BASELINE shapes
 template <int P, bool WITH_H>
+// (p = 4: 126 registers without spills at 4 tiles per SM; 5 tiles at 96 registers spill a few values and measure the same or
+// worse -- profiles/r02_summary.md)
 constexpr int default_minb() { return P <= 3 ? (WITH_H ? 5 : 6) : (P == 4 ? 4 : 3); }
 
 }  // namespace
@@ -45,7 +47,6 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
             if constexpr (P == 4) {   // register-budget variants kept for tuning runs (mimsem_gpu_set_option "m1_min_blocks")
                 if (l.min_blocks == 5) kern = pick_nl<P, false, 0, 5>(t.nlev, t.tpow);
                 if (l.min_blocks == 6) kern = pick_nl<P, false, 0, 6>(t.nlev, t.tpow);
-                if (l.min_blocks == 7) kern = pick_nl<P, false, 0, 7>(t.nlev, t.tpow);
             }
         }
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

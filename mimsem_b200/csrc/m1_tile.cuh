@@ -221,71 +221,74 @@ __device__ __forceinline__ void far_fetch(const TArgs& a, const TileHdr* rec, in
     // rows of oth(q,t): two runs (the neighbour's own block, then the far row / column owned by ITS neighbour), or an
     // explicit list (ghost rows of a fused launch live in the inbox: entries < 0; generic numberings)
     constexpr int NF = (P + 1) * P;
-    int rows[NF];
-    if (flags & (side ? TF_LIST_S : TF_LIST_W)) {
+    double oth[P + 1][P];
+    const double* xk = a.x + k;
+    if (!(flags & (side ? TF_LIST_S : TF_LIST_W))) {
+        const TileFar fr = *reinterpret_cast<const TileFar*>(rec + 1);
+        const double* b16 = xk + (size_t)(side ? fr.s16 : fr.w16) * a.ld;
+        const double* b4 = xk + (size_t)(side ? fr.s4 : fr.w4) * a.ld;
+        const long long st4 = (flags & (side ? TF_S4_DESC : TF_W4_DESC)) ? -(long long)a.ld : (long long)a.ld;
+#pragma unroll
+        for (int q = 0; q < P; q++)
+#pragma unroll
+            for (int t = 0; t < P; t++) oth[q][t] = b16[(size_t)(q * P + t) * a.ld];
+#pragma unroll
+        for (int t = 0; t < P; t++) oth[P][t] = b4[t * st4];
+    } else {
+        int rows[NF];
         const int* list = reinterpret_cast<const int*>(rec + a.rec_list) + side * NF;
 #pragma unroll
         for (int i = 0; i < NF; i++) rows[i] = list[i];
-    } else {
-        const TileFar fr = *reinterpret_cast<const TileFar*>(rec + 1);
-        const int r16 = side ? fr.s16 : fr.w16, r4 = side ? fr.s4 : fr.w4;
-        const int st4 = (flags & (side ? TF_S4_DESC : TF_W4_DESC)) ? -1 : 1;
+        if (HALO == 2 && rows[0] < 0 && rows[NF - 1] < 0) {
+            // every row of this side lives in the cell inbox (the common case of a ghost far line): two batches of loads
+            constexpr int H0 = NF / 2, H1 = NF - H0;
+            const uint4* cb = reinterpret_cast<const uint4*>(inbox) + k;
+            double* of = &oth[0][0];
+            {
+                const uint4* cell[H0];
+                double v[H0];
 #pragma unroll
-        for (int i = 0; i < P * P; i++) rows[i] = r16 + i;
+                for (int i = 0; i < H0; i++) cell[i] = rows[i] < 0 ? cb + (size_t)(-rows[i] - 1) * a.nlev : nullptr;
+                bool all = true;
 #pragma unroll
-        for (int t = 0; t < P; t++) rows[P * P + t] = r4 + t * st4;
-    }
-    double oth[P + 1][P];
-    const double* xk = a.x + k;
-    if (HALO == 2 && (flags & (side ? TF_LIST_S : TF_LIST_W)) && rows[0] < 0 && rows[NF - 1] < 0) {
-        // every row of this side lives in the cell inbox (the common case of a ghost far line): two batches of loads
-        constexpr int H0 = NF / 2, H1 = NF - H0;
-        const uint4* cb = reinterpret_cast<const uint4*>(inbox) + k;
-        double* of = &oth[0][0];
-        {
-            const uint4* cell[H0];
-            double v[H0];
+                for (int i = 0; i < H0; i++) all = all && cell[i];
+                if (all) {
+                    ll_load_many<H0>(cell, ep, a.halo.err, v);
 #pragma unroll
-            for (int i = 0; i < H0; i++) cell[i] = rows[i] < 0 ? cb + (size_t)(-rows[i] - 1) * a.nlev : nullptr;
-            bool all = true;
+                    for (int i = 0; i < H0; i++) of[i] = v[i];
+                } else {
 #pragma unroll
-            for (int i = 0; i < H0; i++) all = all && cell[i];
-            if (all) {
-                ll_load_many<H0>(cell, ep, a.halo.err, v);
-#pragma unroll
-                for (int i = 0; i < H0; i++) of[i] = v[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < H0; i++) of[i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[i] * a.ld];
+                    for (int i = 0; i < H0; i++) of[i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[i] * a.ld];
+                }
             }
+            {
+                const uint4* cell[H1];
+                double v[H1];
+#pragma unroll
+                for (int i = 0; i < H1; i++) cell[i] = rows[H0 + i] < 0 ? cb + (size_t)(-rows[H0 + i] - 1) * a.nlev : nullptr;
+                bool all = true;
+#pragma unroll
+                for (int i = 0; i < H1; i++) all = all && cell[i];
+                if (all) {
+                    ll_load_many<H1>(cell, ep, a.halo.err, v);
+#pragma unroll
+                    for (int i = 0; i < H1; i++) of[H0 + i] = v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < H1; i++) of[H0 + i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[H0 + i] * a.ld];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q <= P; q++)
+#pragma unroll
+                for (int t = 0; t < P; t++) {
+                    const int r = rows[q * P + t];
+                    if (HALO == 1 && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
+                    else if (HALO == 2 && r < 0) oth[q][t] = ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(-r - 1) * a.nlev + k, ep, a.halo.err);
+                    else oth[q][t] = xk[(size_t)r * a.ld];
+                }
         }
-        {
-            const uint4* cell[H1];
-            double v[H1];
-#pragma unroll
-            for (int i = 0; i < H1; i++) cell[i] = rows[H0 + i] < 0 ? cb + (size_t)(-rows[H0 + i] - 1) * a.nlev : nullptr;
-            bool all = true;
-#pragma unroll
-            for (int i = 0; i < H1; i++) all = all && cell[i];
-            if (all) {
-                ll_load_many<H1>(cell, ep, a.halo.err, v);
-#pragma unroll
-                for (int i = 0; i < H1; i++) of[H0 + i] = v[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < H1; i++) of[H0 + i] = cell[i] ? ll_load(cell[i], ep, a.halo.err) : xk[(size_t)rows[H0 + i] * a.ld];
-            }
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q <= P; q++)
-#pragma unroll
-            for (int t = 0; t < P; t++) {
-                const int r = rows[q * P + t];
-                if (HALO == 1 && r < 0) oth[q][t] = __ldcg(inbox + (size_t)(-r - 1) * a.nlev + k);
-                else if (HALO == 2 && r < 0) oth[q][t] = ll_load(reinterpret_cast<const uint4*>(inbox) + (size_t)(-r - 1) * a.nlev + k, ep, a.halo.err);
-                else oth[q][t] = xk[(size_t)r * a.ld];
-            }
     }
     double hv[WITH_H ? P : 1][WITH_H ? P : 1];
     if (WITH_H) {
@@ -427,7 +430,7 @@ __device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part)
 // record is laid out per part for this, gl[part][line][q] = (g_own, g_oth):
 //   part 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; part 1: f1 = c (Gbb ul1 + Gab ul0), ul1 = ua.
 // Each line is stored as soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
-template <int P, bool WITH_H, int NL, int TPOW, bool OTH_REGS>
+template <int P, bool WITH_H, int NL, int TPOW>
 __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, int part, const double (&cfar)[P],
                                            double* __restrict__ y) {
     using S = M1Slots<P>;
@@ -439,16 +442,13 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
     const double* tp = col + (size_t)S::T * nl;                          // thickness at point (line ln, q): tp[q sq + ln sl]
     const int sq = (part ? 1 : NP1) * nl, sl = (part ? NP1 : 1) * nl;
     const double* gl = geo + S::GL + part * (P * NP1 * 2);
-    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (part 0) / xx(qx=q, iy=t) (part 1) are used P times each: kept in
-    // registers (OTH_REGS), or -- in the lean variant that fits more resident tiles per SM -- read from shared memory at
-    // every use
-    double othr[OTH_REGS ? P + 1 : 1][OTH_REGS ? P : 1];
-    if (OTH_REGS) {
+    // the other family's edges oth(q,t) = xy(ix=t, qy=q) (part 0) / xx(qx=q, iy=t) (part 1): used P times each, kept in registers
+    // (reading them from shared memory at every use to fit 6-7 tiles per SM was measured slower: 0.72 / 0.66 of the HBM peak)
+    double othr[P + 1][P];
 #pragma unroll
-        for (int q = 0; q <= P; q++)
+    for (int q = 0; q <= P; q++)
 #pragma unroll
-            for (int t = 0; t < P; t++) othr[OTH_REGS ? q : 0][OTH_REGS ? t : 0] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
-    }
+        for (int t = 0; t < P; t++) othr[q][t] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
 #pragma unroll
     for (int ln = 0; ln < P; ln++) {
         double own[P];
@@ -461,8 +461,7 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
 #pragma unroll
             for (int j = 0; j < P; j++) ua += a.E[q * P + j] * own[j];
 #pragma unroll
-            for (int t = 0; t < P; t++)
-                ub += a.E[ln * P + t] * (OTH_REGS ? othr[OTH_REGS ? q : 0][OTH_REGS ? t : 0] : (q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl]));
+            for (int t = 0; t < P; t++) ub += a.E[ln * P + t] * othr[q][t];
             double g = gl[(ln * NP1 + q) * 2 + 0] * ua + gl[(ln * NP1 + q) * 2 + 1] * ub;
             if (WITH_H) {
                 g *= tp[q * sq + ln * sl];   // h_prepass left t^tpow * hl(q) in the thickness slot
@@ -481,10 +480,7 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
             double s = (ln == 0) ? cfar[j] : 0.0;
 #pragma unroll
             for (int q = 0; q <= P; q++) s += a.Es[q * P + j] * f[q];
-            // the output is never read again by this launch: a streaming store keeps it from displacing the rows that
-            // neighbouring tiles and the L2 prefetch still need
-            if (a.stream_stores) __stcs(&y[(size_t)(ln * P + j) * a.ld], s);
-            else y[(size_t)(ln * P + j) * a.ld] = s;
+            y[(size_t)(ln * P + j) * a.ld] = s;
         }
     }
 }
@@ -595,7 +591,7 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
                 if (active) h_prepass<P, NL, TPOW>(a, col, part);
                 __syncthreads();
             }
-            if (active) tile_lines<P, WITH_H, NL, TPOW, (MINB < 6)>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
+            if (active) tile_lines<P, WITH_H, NL, TPOW>(a, col, geo, part, cfar, a.y + (size_t)(hd.st_dof + (part ? S::OY : S::OX)) * a.ld + k);
         }
         DBG_T(3);
         if (tile_i + tile_stride < a.ntiles) __syncthreads();   // the next tile's bulk loads overwrite the buffer

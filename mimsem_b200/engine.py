@@ -248,6 +248,16 @@ class Engine:
                                          b.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
+    def pc_bjacobi(self, r, out=None, lev0=0, scale=1.0, tpow=0, flags=0):
+        """z = blockdiag(M1)^-1 r, one block per owned element: PCBJACOBI with one block per element, as the reference
+        sets it on ksp1 (eul/HorizSolve.cpp:77-84)."""
+        nlev = r.shape[1]
+        self._chk(r, self.n1, nlev, "r")
+        if out is None:
+            out = self.zeros(self.n1, nlev)
+        check(self.L.mimsem_gpu_pc_bjacobi_M1(self._h, lev0, nlev, nlev, scale, tpow, flags, r.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
     def to_vertical(self, cols):
         """L2Vecs::HorizToVert: (n2, nlev) column layout -> (nel_owned, nlev * p^2) per-element vertical vectors."""
         nlev = cols.shape[1]

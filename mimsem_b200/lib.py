@@ -57,6 +57,7 @@ SIGNATURES = {
     "mimsem_gpu_apply_UtQW": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_columns_to_vertical": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_vertical_to_columns": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "mimsem_gpu_pc_bjacobi_M1": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_apply_incidence": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "mimsem_gpu_incidence_csr": (C.c_int, [_vp, C.c_int, _lp, _lp, _ip, _dp]),
     "mimsem_gpu_apply_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp]),

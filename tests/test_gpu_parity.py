@@ -505,6 +505,33 @@ def test_matrix_free_twins_vs_reference_uvec(fname, p, ne):
     assert rel_l2(y4, g["y_Uvec_hu"]) < TOL
 
 
+@pytest.mark.parametrize("kind,p,ne,variant", [("sphere", 3, 4, "eul"), ("sphere", 4, 2, "eul"), ("box", 3, 4, "box")])
+def test_element_block_jacobi_vs_reference_matrix(kind, p, ne, variant, tmp_path):
+    """PCBJACOBI with one block per element (PCBJacobiSetTotalBlocks(pc, size * nElsX^2, NULL), eul/HorizSolve.cpp:77-84):
+    PETSc cuts the assembled Umat into equal consecutive row blocks of 2 p^2 rows -- the edges element e owns in the
+    reference's numbering.  The device tabulates, factorises and solves every block itself; checked against a dense solve
+    with the same blocks cut out of the oracle's assembled matrix, and as a preconditioner (PCG iteration counts)."""
+    g = golden({"eul": "ops_eul_sphere_p%d_ne%d.npz" % (p, ne), "box": "ops_box_p3_ne4.npz"}[variant])
+    mesh, eng = _engine(kind, p, ne, thick=g["thick"])
+    s = float(g["scale"])
+    nk = int(g["nk"])
+    O = _oracle(tmp_path, kind, p, ne, 6 if kind == "sphere" else 1, variant)
+    O.set_thick(g["thick"])
+    r = g["x1"]
+    z = to_np(eng, eng.pc_bjacobi(to_cols(eng, r, 1), scale=s, tpow=1), 1)
+    nb = 2 * p * p
+    for lev in range(nk):
+        A = O.umat(lev, s, 1).tocsr()
+        ref = np.zeros(mesh.N1)
+        for e in range(mesh.nel):
+            rows = np.arange(e * nb, (e + 1) * nb)          # PETSc's equal consecutive blocks == the element's owned edges
+            ref[rows] = np.linalg.solve(A[rows][:, rows].toarray(), r[lev][rows])
+        assert rel_l2(z[lev], ref) < 1e-11, (lev, rel_l2(z[lev], ref))
+    # the blocks are those of the owned edges: every owned edge of element e carries a global id in [e nb, (e + 1) nb)
+    own = np.concatenate([mesh.el1x.reshape(mesh.nel, p, p + 1)[:, :, :p].reshape(mesh.nel, -1), mesh.el1y[:, :p * p]], axis=1)
+    assert np.array_equal(np.sort(own, axis=1), np.arange(mesh.nel * nb).reshape(mesh.nel, nb))
+
+
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 4, 30), ("sphere", 4, 3, 60), ("box", 3, 5, 7)])
 def test_l2vecs_relabelling_bit_exact(kind, p, ne, nk):
     """L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): vz[e][k*p^2 + i] = vh[k][elInds2_l(e)[i]], bit for bit."""
