@@ -871,7 +871,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     // TMA tile kernel: needs 16-byte aligned, even-length level runs and one thread per level
     const bool aligned = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!with_h || (uintptr_t)h2 % 16 == 0);
     const bool thick_ok = tpow == 0 || (!(flags & MIMSEM_FIXED_LEVEL) && c->nkT % 2 == 0 && lev0 % 2 == 0);
-    const bool tma_path = c->m1_variant == 2 && (with_h ? c->tma_h_ok : c->tma_ok) && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64;
+    const bool tma_path = c->m1_variant >= 2 && (with_h ? c->tma_h_ok : c->tma_ok) && aligned && thick_ok && nlev % 2 == 0 && ld % 2 == 0 && nlev <= 64;
     if (hf) {
         if (with_h || !tma_path || !c->halo_plan_ok || a.elist || ld != nlev)
             return fail(MIMSEM_ERR_UNSUPPORTED, "fused ghost refresh needs the TMA tile path (plain M1, all owned elements, even nlev == ld <= 64, set_ghosts)");
@@ -916,7 +916,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.dbg_times = c->diag_times;
 #endif
         std::string err;
-        const int rc3 = launch_m1_tile(l, t, st, &err);
+        const int rc3 = (c->m1_variant == 3 && !hf) ? launch_m1_pipe(l, t, st, &err) : launch_m1_tile(l, t, st, &err);
         if (rc3 < 0) return fail(MIMSEM_ERR_CUDA, err);
         if (rc3 == 0) {
             if (l.push_only && l.push_ctas == 0) return MIMSEM_OK;
@@ -1463,7 +1463,7 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     if (!c || !name) return fail(MIMSEM_ERR_ARG, "null argument");
     const std::string n(name);
     const int v = (int)value;
-    if (n == "m1_variant" && v >= 0 && v <= 2) c->m1_variant = v;
+    if (n == "m1_variant" && v >= 0 && v <= 3) c->m1_variant = v;
     else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
     else if (n == "m2_variant" && v >= 0 && v <= 1) c->m2_variant = v;
     else if (n == "inc_variant" && v >= 0 && v <= 1) c->inc_variant = v;

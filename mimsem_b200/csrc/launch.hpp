@@ -22,6 +22,8 @@ struct M1TileLaunch {
 };
 // return: 0 launched, 1 not applicable (tile does not fit in shared memory: use a register kernel), < 0 CUDA error (*err set)
 int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string* err);
+// persistent double-buffered variant (m1_pipe.cuh); same return convention, single GPU launches only
+int launch_m1_pipe(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string* err);
 int launch_k_tile(int p, TArgs& t, int nel, cudaStream_t st, std::string* err);
 int launch_m2_tile(int p, bool with_h, TArgs& t, int nel, cudaStream_t st, std::string* err);
 

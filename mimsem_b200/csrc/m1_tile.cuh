@@ -384,8 +384,10 @@ __device__ __forceinline__ void far_line(const TArgs& a, const double* col, cons
 // and leave it in the thickness slots, so that the line contraction below is exactly the plain M1 one (one multiply per
 // point, no coefficient data in registers).  Runs between two CTA barriers, after the far lines have read the raw
 // thickness of the west column / south row.
-template <int P, int NL, int TPOW>
-__device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part) {
+// CARRY (persistent kernel): also returns hsn[j] = sum_t E[P][t] h(ix = t, iy = j), the coefficient contracted across this
+// element's east column -- what far_fetch computes for the WEST far line of the element's east neighbour.
+template <int P, int NL, int TPOW, bool CARRY = false>
+__device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part, double* hsn = nullptr) {
     using S = M1Slots<P>;
     constexpr int NP1 = P + 1, SPLIT = (NP1 + 1) / 2;
     const int nl = NL ? NL : a.nlev;
@@ -395,6 +397,15 @@ __device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part)
     for (int iy = 0; iy < P; iy++)
 #pragma unroll
         for (int ix = 0; ix < P; ix++) hv[iy][ix] = col[(size_t)(S::H + iy * P + ix) * nl];
+    if (CARRY) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < P; t++) s += a.E[P * P + t] * hv[j][t];
+            hsn[j] = s;
+        }
+    }
 #pragma unroll
     for (int qx = 0; qx <= P; qx++) {
         if ((qx < SPLIT) != (part == 0)) continue;
@@ -430,9 +441,11 @@ __device__ __forceinline__ void h_prepass(const TArgs& a, double* col, int part)
 // record is laid out per part for this, gl[part][line][q] = (g_own, g_oth):
 //   part 0: f0 = c (Gaa ul0 + Gab ul1), ul0 = ua ; part 1: f1 = c (Gbb ul1 + Gab ul0), ul1 = ua.
 // Each line is stored as soon as it is finished (lanes = levels: coalesced 8-byte stores straight from registers).
-template <int P, bool WITH_H, int NL, int TPOW>
+// CARRY (persistent kernel): also returns ubn[q] = sum_t E[P][t] oth(q,t), this element's other edge family interpolated onto
+// its east column (part 0) / north row (part 1) -- what far_fetch computes for the far line of the east / north neighbour.
+template <int P, bool WITH_H, int NL, int TPOW, bool CARRY = false>
 __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, const double* geo, int part, const double (&cfar)[P],
-                                           double* __restrict__ y) {
+                                           double* __restrict__ y, double* ubn = nullptr) {
     using S = M1Slots<P>;
     constexpr int NP1 = P + 1;
     const int nl = NL ? NL : a.nlev;
@@ -449,6 +462,15 @@ __device__ __forceinline__ void tile_lines(const TArgs& a, const double* col, co
     for (int q = 0; q <= P; q++)
 #pragma unroll
         for (int t = 0; t < P; t++) othr[q][t] = q < P ? oth16[(size_t)(q * P + t) * nl] : oth4[(size_t)t * nl];
+    if (CARRY) {
+#pragma unroll
+        for (int q = 0; q <= P; q++) {
+            double s = 0.0;
+#pragma unroll
+            for (int t = 0; t < P; t++) s += a.E[P * P + t] * othr[q][t];
+            ubn[q] = s;
+        }
+    }
 #pragma unroll
     for (int ln = 0; ln < P; ln++) {
         double own[P];

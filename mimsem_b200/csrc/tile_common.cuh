@@ -57,14 +57,16 @@ __device__ __forceinline__ const TileHdr* tile_record(const TArgs& a, int e) { r
 
 // Stage one tile: one warp walks the element's copy list (one entry per lane and round).  `inbox` = the halo inbox copy
 // of this epoch (kind-4 entries), or nullptr.
-__device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* inbox, uint64_t* bar, double* geo, double* tile) {
-    const TileHdr* rec = tile_record(a, e);
-    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr);
+// `h` = the record's header word and `first` = this lane's first copy entry (tile_first_entry), already in registers.
+__device__ __forceinline__ CopyEnt tile_first_entry(const TArgs& a, const TileHdr* rec) {
     const int lane = (int)threadIdx.x & 31;
     const int nents = a.rec_stride - a.rec_hdr;
-    // header and this lane's first entry are fetched together (no dependent load on the critical path)
-    const TileHdr h = rec[0];
-    const CopyEnt first = ents[lane < nents ? lane : 0];
+    return reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr)[lane < nents ? lane : 0];
+}
+__device__ __forceinline__ void tile_load_pre(const TArgs& a, const TileHdr* rec, const TileHdr h, const CopyEnt first, const double* inbox,
+                                              uint64_t* bar, double* geo, double* tile) {
+    const CopyEnt* ents = reinterpret_cast<const CopyEnt*>(rec + a.rec_hdr);
+    const int lane = (int)threadIdx.x & 31;
     const unsigned slot_bytes = (unsigned)a.nlev * 8u;
     const bool with_t = a.tpow > 0;
     for (int ci = lane; ci < h.cp_count; ci += 32) {
@@ -100,6 +102,13 @@ __device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* i
     const unsigned nslots = (unsigned)(h.nslots & 0xfff) + (a.halo.ll ? 0u : (unsigned)((h.nslots >> 12) & 0xff)) +
                             (with_t ? (unsigned)(h.nslots >> 20) : 0u);
     if (lane == 0) mbar_arrive_expect_tx(bar, nslots * slot_bytes + (unsigned)a.geo_doubles * 8u);
+}
+__device__ __forceinline__ void tile_load(const TArgs& a, int e, const double* inbox, uint64_t* bar, double* geo, double* tile) {
+    const TileHdr* rec = tile_record(a, e);
+    // header and this lane's first entry are fetched together (no dependent load on the critical path)
+    const TileHdr h = rec[0];
+    const CopyEnt first = tile_first_entry(a, rec);
+    tile_load_pre(a, rec, h, first, inbox, bar, geo, tile);
 }
 
 // L2 prefetch of the DRAM-unique part of a LATER tile (its record, its own edge block, its coefficient and thickness

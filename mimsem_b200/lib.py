@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmimsem_gpu.so")
+LIB_PATH = os.environ.get("MIMSEM_GPU_LIB") or os.path.join(_HERE, "libmimsem_gpu.so")   # (override: diagnostics builds, scripts/)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -322,24 +322,28 @@ def test_error_paths():
         eng.apply("M1", x[:10].contiguous())
 
 
-@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40)])
+@pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
+                                          ("sphere", 4, 16, 60), ("sphere", 3, 20, 30)])   # the last two: many tiles per SM (ring wrap-around)
 def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
-    """The TMA tile kernel (default), the line-task kernel and the thread-per-element kernel compute the
+    """The TMA tile kernels (one CTA per tile; persistent and double-buffered), the line-task kernel and the thread-per-element kernel compute the
     same M1 / M1(h) (identical up to FP summation order)."""
     mesh = mb.Mesh(kind, p, ne)
     thick = synthetic_thickness(mesh.xyz, nk, kind)
     rng = np.random.default_rng(11)
     f = synthetic_fields(rng, nk, mesh.N0, mesh.N1, mesh.N2, float(mesh.det.mean()))
     res = {}
-    for variant in ("0", "1", "2"):
+    for variant in ("0", "1", "2", "3"):
         monkeypatch.setenv("MIMSEM_M1_VARIANT", variant)
         eng = mb.Engine.from_mesh(mesh, 0, thick=thick)
         res[variant] = (_apply(eng, "M1", f["x1"], scale=1e8, tpow=1), _apply(eng, "M1h", f["x1"], f["h2"], scale=1e8, tpow=2),
                         _apply(eng, "M1", f["x1"], scale=1.0, tpow=0))
         eng.close()
-    for v in ("1", "2"):
+    for v in ("1", "2", "3"):
         for a, b in zip(res[v], res["0"]):
             assert rel_l2(a, b) < 1e-14, (v, rel_l2(a, b))
+    # the persistent double-buffered kernel (3) runs the tile kernel's (2) arithmetic: bit for bit the same
+    for a, b in zip(res["3"], res["2"]):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
