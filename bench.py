@@ -315,6 +315,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true",
+                    help="1 GPU: one CUDA graph per step and ordinary stream order between steps (default: graphs of several consecutive "
+                         "steps, launched with programmatic dependent launch -- the steps of the ring are independent applies)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the bitwise comparison with a single-GPU apply")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="engine tuning knob (mimsem_gpu_set_option), e.g. --opt m1_min_blocks=5; recorded in config")
@@ -350,7 +353,15 @@ def main():
         eng = DistributedEngine(mesh, thick, rank, world, local)
     else:
         eng = mb.Engine.from_mesh(mesh, local, thick=thick)
-    for kv in args.opt:
+    # 1 GPU: consecutive steps are independent applies (ring of distinct fields), so a launch may start while the CTAs of
+    # the previous one retire (programmatic dependent launch); plain M1 then runs best as the persistent ring kernel
+    burst = not args.no_graph and not args.no_pdl and (world == 1 or (args.op == "M1" and not args.chain and not args.pipelined))
+    auto_opts = []
+    if burst:
+        auto_opts.append("pdl_independent=1")
+        if world == 1 and args.op == "M1" and not args.chain and not any(o.startswith("m1_variant=") for o in args.opt):
+            auto_opts.append("m1_variant=3")
+    for kv in auto_opts + args.opt:
         name, val = kv.split("=")
         (eng if world == 1 else eng.engine).set_option(name, int(val))
     op = "M1h" if args.chain else args.op
@@ -424,6 +435,68 @@ def main():
             raise SystemExit("rank %d: the %d-GPU output differs from the single-GPU output -- refusing to print a number" % (rank, world))
 
     fused = world > 1 and op == "M1" and getattr(eng, "p2p", None) is not None and eng.fused
+    if world > 1 and burst and not (fused and getattr(eng, "graph_safe", False)):
+        burst = False
+        eng.engine.set_option("pdl_independent", 0)
+        auto_opts = []
+
+    def measure_burst():
+        """1 GPU: W warm-up + exactly K timed steps, replayed from CUDA graphs that hold several consecutive steps each
+        (slot = step % RING), so that programmatic dependent launch can overlap a launch with the tail of the previous one."""
+        B = RING * max(1, 18 // RING)
+
+        def capture(nsteps):
+            if world > 1:
+                class _G:   # same interface as a CUDAGraph
+                    replay = staticmethod(eng.capture_burst(op, xs, cs, ys, nsteps, **kw_of(0)))
+                return _G
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for i in range(min(nsteps, RING)):
+                    apply_slot(i % RING)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=st):
+                    for i in range(nsteps):
+                        apply_slot(i % RING)
+            return gr
+        g_full = capture(B)
+        n_full, n_rem = args.steps // B, args.steps % B
+        g_rem = capture(n_rem) if n_rem else None
+        for _ in range(-(-args.warmup // B)):
+            g_full.replay()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_full):
+            g_full.replay()
+        if g_rem is not None:
+            g_rem.replay()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        sustained_ms = None
+        if not args.no_sustained:
+            n_rep = max(1, min(100000 if world == 1 else 4000, int(1.0e3 / max(ms, 1e-3))) // B)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(n_rep):
+                g_full.replay()
+            s1.record()
+            barrier()
+            sus = s0.elapsed_time(s1) / (n_rep * B)
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([sus], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                sus = float(t[0])
+            sustained_ms = (sus, n_rep * B)
+        return ms, ms, launches_per_step * args.steps, sustained_ms, True
 
     def measure(pipelined):
         """W warm-up + K timed steps (CUDA-graph replays of the captured step, one graph per ring slot)."""
@@ -432,6 +505,8 @@ def main():
             eng.prologue_push(xs[0])
             barrier()
         replays = None
+        if burst:
+            return measure_burst()
         if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
             try:
                 # (each capture warms up with real applies of its slot; after the last slot a pipelined sequence
@@ -511,7 +586,15 @@ def main():
     ms_per_step, kern_ms, launches, sustained, graphed = measure(headline_pipelined)
     clocks = sampler.stop() if rank == 0 else None
     second = None
-    if fused and not headline_pipelined:
+    strict = None
+    if fused and burst:
+        # the same launches in ordinary stream order, one graph per step: what a chain of DEPENDENT applies gets
+        barrier()
+        eng.engine.set_option("pdl_independent", 0)
+        burst = False
+        strict = measure(False)[0]
+        burst = True
+    elif fused and not headline_pipelined:
         barrier()
         second = measure(True)[0]
 
@@ -587,7 +670,7 @@ def main():
             if fused:
                 mode = "fused into the M1 launch over NVLink peer memory; " + (
                     "push of step i+1's input overlapped with step i (ring of independent inputs)" if headline_pipelined
-                    else "lockstep: push and consume in the same launch (dependent applies)")
+                    else "push and consume in the same launch")
             else:
                 mode = "push / pull kernels over NVLink peer memory on a side stream"
         line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -596,11 +679,18 @@ def main():
                 "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels; %s (Nel=%d, out DOF-levels=%d)"
                                        % (args.workload, variant, p, ne, ne, nk, what, mesh.nel, out_dofs),
                            "cache": "ring of %d distinct field sets per GPU (%.1f MB each, %.0f MB in total per GPU vs 126 MB L2)" % (RING, 16e-6 * nin * nk, RING * 16e-6 * nin * nk),
-                           "parallelism": "element-block x%d" % world, "cuda_graph": graphed, "options": args.opt,
+                           "parallelism": "element-block x%d" % world, "cuda_graph": graphed, "options": auto_opts + args.opt,
+                           "launch": ("CUDA graphs of up to %d consecutive steps; the steps are independent applies (ring), launched with "
+                                      "programmatic dependent launch: a step starts while the CTAs of the previous one retire" % (RING * max(1, 18 // RING))
+                                      if burst else "one CUDA graph replay (or eager launch) per step, stream order between steps"),
                            "ghost_refresh": mode},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         if parity is not None:
             line["parity_check"] = parity
+        if strict is not None:
+            line["dependent_applies"] = {"value": out_dofs / (strict * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": strict,
+                                         "note": "the same fused launches in ordinary stream order (one CUDA graph per step, no overlap between "
+                                                 "consecutive launches): the rate of a chain of dependent applies"}
         if second is not None:
             line["pipelined"] = {"value": out_dofs / (second * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": second,
                                  "note": "ghost rows of step i+1's INDEPENDENT input pushed during step i; not the headline"}

@@ -89,6 +89,8 @@ struct mimsem_gpu_ctx {
     int ell_vec = 4;                         // widest level group of the incidence kernels (4, 2, 1)
     int prefetch_ahead = 444;                // L2 prefetch distance of the tile kernels in tiles (0: off)
     int m1_min_blocks = 0;                   // register-budget variant of the M1 tile kernel (0: default)
+    int pdl = 0;                             // 1: the caller guarantees that consecutive launches on a stream are independent
+                                             //    (tile kernels are launched with programmatic stream serialization)
     int host_chunk = 12;                     // levels per pipeline stage of mimsem_gpu_apply_host
     int halo_max_levels = 0;                 // levels per ghost row the caller's halo inboxes were allocated for (0: unknown)
     int n0_owned = -1;                       // subdomains: 0-form operators compute rows [0, n0_owned) only (-1: all rows)
@@ -885,6 +887,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.scale = scale;
         t.prefetch_ahead = c->prefetch_ahead;
         t.prefetch_own_slots = 2 * c->p * c->p;
+        t.pdl = c->pdl;
         t.elist = a.elist;
         t.recs = with_h ? c->d_recs_h.p : c->d_recs.p;
         t.rec_stride = with_h ? c->rec_stride_h : c->rec_stride;
@@ -964,6 +967,7 @@ int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
         t.prefetch_ahead = c->prefetch_ahead * 2;   // 64-thread CTAs: about twice as many tiles are resident
+        t.pdl = c->pdl;
         t.prefetch_own_slots = c->p * c->p;
         t.elist = a.elist;
         t.recs = with_h ? c->d_recs_m2h.p : c->d_recs_m2.p;
@@ -1005,6 +1009,7 @@ int apply_k(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpo
         t.contig_x = (ld == nlev); t.contig_t = (c->nkT == nlev);
         t.scale = scale;
         t.prefetch_ahead = c->prefetch_ahead;
+        t.pdl = c->pdl;
         t.prefetch_own_slots = 2 * c->p * c->p + 2 * c->p;
         t.elist = a.elist;
         t.recs = c->d_recs_k.p;
@@ -1470,6 +1475,7 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     else if (n == "ell_vec" && (v == 1 || v == 2 || v == 4)) c->ell_vec = v;
     else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
+    else if (n == "pdl_independent" && v >= 0 && v <= 1) c->pdl = v;
     else if (n == "host_chunk" && v >= 1) c->host_chunk = v;
     else if (n == "halo_max_levels" && v >= 0) c->halo_max_levels = v;
     else if (n == "n0_owned" && v >= -1) c->n0_owned = v;

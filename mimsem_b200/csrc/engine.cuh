@@ -254,6 +254,7 @@ struct TArgs {
     int ntiles;               // tiles (elements) of this launch
     int prefetch_ahead;       // L2-prefetch the tile this many CTAs ahead (0: off)
     int prefetch_own_slots;   // x-field slots below this number are the element's own block
+    int pdl;                  // programmatic dependent launch: let the next launch on the stream start as CTAs of this one retire
     double scale;
     const int* elist;         // optional element subset; nullptr: element = blockIdx.x
     const TileHdr* recs;      // [nel][rec_stride] 16-byte words: kRecHdr header words (K tile: 1), copy entries, far-row list

@@ -24,7 +24,10 @@ int launch_k_tile(int p, TArgs& t, int nel, cudaStream_t st, std::string* err) {
         }
         rc = 0;
         t.ntiles = nel;
-        if (nel > 0) kern<<<nel, 128, smem, st>>>(t);
+        if (nel > 0 && launch_maybe_pdl(kern, dim3(nel), dim3(128), smem, st, t.pdl != 0, t) != cudaSuccess) {
+            *err = std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(cudaGetLastError());
+            rc = -1;
+        }
     });
     return rc;
 }

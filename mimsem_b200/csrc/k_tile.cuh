@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(128, (P <= 4 ? 4 : 2)) k_apply_k_tma(const __g
         mbar_init(bar, 1);
         fence_async_smem();
     }
+    if (a.pdl) pdl_launch_dependents();
     __syncthreads();
     unsigned phase = 0;
     for (int tile_i = blockIdx.x; tile_i < a.ntiles; tile_i += gridDim.x, phase ^= 1) {

@@ -46,7 +46,11 @@ int launch_m1_pipe(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         t.ntiles = l.nel;
         const int grid = std::min(l.nel, sms);
         if (getenv("MIMSEM_PIPE_VERBOSE")) fprintf(stderr, "m1_pipe: smem %zu ring %d sms %d grid %d ntiles %d\n", smem, nb, sms, grid, l.nel);
-        kern<<<grid, M1Pipe<P, false>::threads(nb), smem, st>>>(t, nb);
+        ce = launch_maybe_pdl(kern, dim3(grid), dim3(M1Pipe<P, false>::threads(nb)), smem, st, t.pdl != 0, t, nb);
+        if (ce != cudaSuccess) {
+            *err = std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(ce);
+            rc = -1;
+        }
     });
     return rc;
 }

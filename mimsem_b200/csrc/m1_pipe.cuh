@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(M1Pipe<P, WITH_H>::MAX_THREADS, 1) k_apply_m1_
         }
         fence_async_smem();
     }
+    if (a.pdl) pdl_launch_dependents();
     __syncthreads();
 
     if (threadIdx.x >= PP::G * 128) {

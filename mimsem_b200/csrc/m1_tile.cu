@@ -64,6 +64,14 @@ int launch_m1_tile(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         }
         if (l.nel == 0) return;
         t.ntiles = l.nel;
+        if (t.pdl) {
+            ce = launch_maybe_pdl(kern, dim3(l.nel + l.push_ctas), dim3(128), smem, st, true, t);
+            if (ce != cudaSuccess) {
+                *err = std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(ce);
+                rc = -1;
+            }
+            return;
+        }
         kern<<<l.nel + l.push_ctas, 128, smem, st>>>(t);
     });
     return rc;

@@ -526,7 +526,13 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
     unsigned long long epoch = 0;
     int first_tile = blockIdx.x, tile_stride = gridDim.x;
     if (HALO) {
-        if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) epoch = *a.halo.epoch + 1;
+        if (a.pdl) pdl_launch_dependents();
+        if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) {
+            // push CTAs and boundary tiles share the epoch word and the counters with the previous launch: under programmatic
+            // dependent launch they wait for it; interior tiles (no ghost rows) run on while it drains
+            if (a.pdl) pdl_wait_primary();
+            epoch = *a.halo.epoch + 1;
+        }
         if ((int)blockIdx.x < a.halo.push_ctas) {
             // data epoch of the pushed field = epoch + lead
             if (HALO == 2) halo_push_role_ll(a, epoch + (unsigned long long)a.halo.lead);
@@ -541,6 +547,7 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
         mbar_init(bar, 1);
         fence_async_smem();
     }
+    if (!HALO && a.pdl) pdl_launch_dependents();
     __syncthreads();
     unsigned phase = 0;
     for (int tile_i = first_tile; tile_i < a.ntiles; tile_i += tile_stride, phase ^= 1) {

@@ -30,7 +30,10 @@ int launch_m2_tile(int p, bool with_h, TArgs& t, int nel, cudaStream_t st, std::
         }
         rc = 0;
         t.ntiles = nel;
-        if (nel > 0) kern<<<nel, 64, smem, st>>>(t);
+        if (nel > 0 && launch_maybe_pdl(kern, dim3(nel), dim3(64), smem, st, t.pdl != 0, t) != cudaSuccess) {
+            *err = std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(cudaGetLastError());
+            rc = -1;
+        }
     });
     return rc;
 }

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(64) k_apply_m2_tile(const __grid_constant__ TA
         mbar_init(bar, 1);
         fence_async_smem();
     }
+    if (a.pdl) pdl_launch_dependents();
     __syncthreads();
     const int e = a.elist ? a.elist[blockIdx.x] : (int)blockIdx.x;
     if (threadIdx.x < 32) tile_load(a, e, nullptr, bar, geo, tile);

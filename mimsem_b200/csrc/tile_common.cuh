@@ -39,6 +39,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+// programmatic dependent launch: the next kernel on the stream (launched with programmatic stream serialization) may
+// begin once every CTA of this grid has passed this point or exited
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... and the dependent side: blocks until the previous kernel on the stream has completed and its memory is visible (a no-op
+// in a launch without the attribute)
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// launch with (pdl) or without the programmatic-stream-serialization attribute
+template <class... KArgsT, class... ArgsT>
+inline cudaError_t launch_maybe_pdl(void (*kern)(KArgsT...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, ArgsT... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -642,6 +642,25 @@ class DistributedEngine:
             self.apply(op, x, coeff=coeff, out=out, **kw)
         return graph.replay, out
 
+    def capture_burst(self, op, xs, coeffs, outs, nsteps, **kw):
+        """Capture `nsteps` consecutive steps, step i on slot i % len(xs), into ONE CUDA graph and return its replay.  With
+        the engine option "pdl_independent" the launches inside carry programmatic dependencies: a step starts while the
+        previous one drains (the slots must then be independent fields).  All ranks must capture and replay alike."""
+        torch = self.torch
+        n = len(xs)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for i in range(2 * n):
+                self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(nsteps):
+                self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
+        return graph.replay
+
     # test / IO helpers ------------------------------------------------------------------
     def scatter_from_global(self, levels_global, space):
         """numpy (nlev, N_space) global field -> local column tensor with owned AND ghost rows filled."""

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--workload", default="C5")
     ap.add_argument("--sweep", action="append", default=[], metavar="NAME=v1,v2,...")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--burst", type=int, default=0, help="capture this many consecutive steps in ONE CUDA graph and time replays of it")
     args = ap.parse_args()
     import torch
     import bench
@@ -60,6 +61,27 @@ def main():
             torch.cuda.synchronize()
             ms = ev[0].elapsed_time(ev[-1]) / args.steps
             best = min(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+            if args.burst:
+                s = torch.cuda.Stream()
+                with torch.cuda.stream(s):
+                    for i in range(args.burst):
+                        step(i)
+                    torch.cuda.synchronize()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=s):
+                        for i in range(args.burst):
+                            step(i)
+                for _ in range(2):
+                    gr.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(1, args.steps // args.burst * 3)
+                e0.record()
+                for _ in range(reps):
+                    gr.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = best = e0.elapsed_time(e1) / (reps * args.burst)
             print(json.dumps({"workload": args.workload, "op": op, "options": dict(zip(names, combo)), "ms": ms, "ms_best": best,
                               "gdofs": dofs / ms / 1e6, "frac": alg / (ms * 1e-3) / 1e9 / peak, "alg_bytes": alg}), flush=True)
         del xs, ys, cs

@@ -134,6 +134,30 @@ def main():
                     ys = to_np(single, single.apply(op, to_cols(single, f["x1"], 1), coeff=cs, scale=1e8, tpow=1 if op == "M1" else 2), sp_)
                     if not np.array_equal(tt.cpu().numpy(), ys):
                         failures.append((what, kind, p, ne, "back-to-back M1 / K: %s differs from single GPU" % op))
+        # programmatic dependent launch: six fused steps over three INDEPENDENT fields in one CUDA graph; a step starts while
+        # the previous one drains (interior tiles), its push CTAs and boundary tiles wait for the previous launch
+        if deng.p2p is not None and deng.fused and getattr(deng, "graph_safe", False) and nk % 2 == 0:
+            xsl, refs = [], []
+            perm1 = torch.from_numpy(deng.engine.permutation(1).astype(np.int64)).cuda()
+            for i in range(3):
+                xi = deng.scatter_from_global(f["x1"] * (1.0 + 0.25 * i), 1)
+                xi[perm1[deng.part.n1_owned:]] = 0.0
+                xsl.append(xi)
+                refs.append(deng.apply("M1", xi, scale=1e8, tpow=1).clone())
+            outs = [torch.empty_like(r) for r in refs]
+            deng.engine.set_option("pdl_independent", 1)
+            replay = deng.capture_burst("M1", xsl, None, outs, 6, scale=1e8, tpow=1)
+            for o in outs:
+                o.zero_()
+            for _ in range(3):
+                replay()
+            torch.cuda.synchronize()
+            deng.engine.set_option("pdl_independent", 0)
+            n_own = deng.part.n1_owned
+            for i in range(3):
+                rows = perm1[:n_own]
+                if not torch.equal(outs[i][rows], refs[i][rows]):
+                    failures.append((what, kind, p, ne, "fused M1 under programmatic dependent launch differs (slot %d, rank %d)" % (i, rank)))
         # partitioned mass-matrix solve: x -> b = M1 x (partitioned) -> CG over peer memory recovers x; every rank
         # stops at the same iteration with the same residual
         if deng.p2p is not None and deng.fused and nk % 2 == 0:

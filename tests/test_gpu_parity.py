@@ -346,6 +346,51 @@ def test_m1_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("variant", [2, 3])
+def test_programmatic_dependent_launch_of_independent_applies(variant):
+    """"pdl_independent": the caller promises that consecutive launches do not depend on each other; the tile kernels are
+    then launched with programmatic stream serialization (a launch starts while the previous one drains).  Eight
+    back-to-back applies on distinct fields, eagerly and from one CUDA graph, must equal the ordinary launches bit for bit."""
+    import torch
+    mesh = mb.Mesh("sphere", 4, 16)
+    nk = 60
+    eng = mb.Engine.from_mesh(mesh, 0, thick=synthetic_thickness(mesh.xyz, nk))
+    eng.set_option("m1_variant", variant)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.rand((mesh.N1, nk), dtype=torch.float64, device="cuda", generator=g) for _ in range(8)]
+    hs = [torch.rand((mesh.N2, nk), dtype=torch.float64, device="cuda", generator=g) + 0.5 for _ in range(8)]
+    def run():
+        out = []
+        for x, h in zip(xs, hs):
+            out.append(eng.apply("M1", x, scale=1e8, tpow=1))
+            out.append(eng.apply("M1h", x, coeff=h, scale=1e8, tpow=2))
+            out.append(eng.apply("K", x, coeff=x, scale=1e8, tpow=2))
+            out.append(eng.apply("M2", h, scale=1e8, tpow=1))
+        torch.cuda.synchronize()
+        return out
+    ref = run()
+    eng.set_option("pdl_independent", 1)
+    got = run()
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    ys = [torch.empty_like(xs[0]) for _ in xs]
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for x, y in zip(xs, ys):
+            eng.apply("M1", x, out=y, scale=1e8, tpow=1)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for x, y in zip(xs, ys):
+                eng.apply("M1", x, out=y, scale=1e8, tpow=1)
+    for y in ys:
+        y.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    for i, y in enumerate(ys):
+        assert torch.equal(y, ref[4 * i])
+
+
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 6, 30), ("sphere", 4, 4, 60), ("sphere", 2, 3, 8), ("box", 3, 5, 40),
                                           ("sphere", 5, 2, 20)])
 def test_m2_kernel_variants_agree(kind, p, ne, nk, monkeypatch):
