@@ -344,6 +344,13 @@ int mimsem_gpu_halo_pull(mimsem_gpu_ctx* ctx, int npeers, const void* d_peers, i
  * pipelined sequence starts with one mode-2 call (push d_x_push only; nothing is applied, the epoch is unchanged)
  * and ends with one mode-3 call (consume only, push nothing); every rank must use the same mode in the same call.
  * mode 0 (d_x_push ignored): push and consume in one call.
+ *
+ * Bursts (flag protocol, mode 0, option "pdl_independent" = 1): B <= 32 consecutive calls on INDEPENDENT fields, captured
+ * in one CUDA graph, may overlap completely under programmatic dependent launch.  Announce each call with
+ * mimsem_gpu_set_option(ctx, "halo_burst_len", B) and (ctx, "halo_burst_pos", i), i = 0 .. B-1 in launch order (reset
+ * halo_burst_len to 0 afterwards): launch i works on epoch *d_epoch + 1 + i with its own counters, flags and
+ * acknowledgements still rise in launch order, and the last launch advances d_epoch by B.  The graph must hold the whole
+ * burst; replays of it (and anything else on the stream) are ordered after it as usual.
  */
 int mimsem_gpu_apply_M1_halo(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags,
                              const double* d_x, double* d_y, const double* d_x_push, int mode, int npush, const void* d_push,

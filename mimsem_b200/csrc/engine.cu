@@ -89,6 +89,7 @@ struct mimsem_gpu_ctx {
     int ell_vec = 4;                         // widest level group of the incidence kernels (4, 2, 1)
     int prefetch_ahead = 444;                // L2 prefetch distance of the tile kernels in tiles (0: off)
     int m1_min_blocks = 0;                   // register-budget variant of the M1 tile kernel (0: default)
+    int halo_burst_pos = 0, halo_burst_len = 0;   // the next fused M1 launches are launch pos of a burst of len (see HaloFused)
     int pdl = 0;                             // 1: the caller guarantees that consecutive launches on a stream are independent
                                              //    (tile kernels are launched with programmatic stream serialization)
     int host_chunk = 12;                     // levels per pipeline stage of mimsem_gpu_apply_host
@@ -899,12 +900,20 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         for (size_t i = 0; i < sizeof(t.E) / sizeof(double); i++) t.Es[i] = scale * t.E[i];
         M1TileLaunch l{c->p, with_h, hf ? (hf->ll ? 2 : 1) : 0, a.nel, 0, false, c->m1_min_blocks};
         if (hf) {
+            constexpr int NCTR = (kMaxBurst + 1) * kCtrStride;   // counter slots of a burst, then the sequence words
             if (!c->d_fused_counters.p) {
-                CUDA_OK(c->d_fused_counters.resize(80));
-                CUDA_OK(cudaMemset(c->d_fused_counters.p, 0, 80 * sizeof(unsigned)));
+                CUDA_OK(c->d_fused_counters.resize(NCTR));
+                CUDA_OK(cudaMemset(c->d_fused_counters.p, 0, NCTR * sizeof(unsigned)));
             }
             t.halo_on = 1;
             t.halo = *hf;
+            t.halo.seq = c->d_fused_counters.p + kMaxBurst * kCtrStride;
+            if (c->halo_burst_len > 1 && c->pdl && !hf->ll && !hf->lead && !hf->push_only) {
+                if (c->halo_burst_pos < 0 || c->halo_burst_pos >= c->halo_burst_len || c->halo_burst_len > kMaxBurst)
+                    return fail(MIMSEM_ERR_ARG, "fused ghost refresh: burst position / length out of range");
+                t.halo.burst_pos = c->halo_burst_pos;
+                t.halo.burst_len = c->halo_burst_len;
+            }
             t.halo.n_int = hf->push_only ? 0 : c->n_int;
             t.halo.counters = c->d_fused_counters.p;
             t.elist = c->elist_all_identity ? nullptr : c->d_elist_all.p;
@@ -1476,6 +1485,8 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     else if (n == "prefetch_ahead" && v >= 0) c->prefetch_ahead = v;
     else if (n == "m1_min_blocks" && v >= 0 && v <= 8) c->m1_min_blocks = v;
     else if (n == "pdl_independent" && v >= 0 && v <= 1) c->pdl = v;
+    else if (n == "halo_burst_len" && v >= 0 && v <= kMaxBurst) c->halo_burst_len = v;
+    else if (n == "halo_burst_pos" && v >= 0 && v < kMaxBurst) c->halo_burst_pos = v;
     else if (n == "host_chunk" && v >= 1) c->host_chunk = v;
     else if (n == "halo_max_levels" && v >= 0) c->halo_max_levels = v;
     else if (n == "n0_owned" && v >= -1) c->n0_owned = v;

@@ -242,7 +242,15 @@ struct HaloFused {
     int lead;                        // 0 or 1
     int nbuf;                        // inbox copies (2, or 3 so that a pipelined push never waits for the current consumer)
     int push_only;                   // prologue of a pipelined sequence: push data epoch e+1... nothing else, epoch unchanged
+    // burst of launches that overlap under programmatic dependent launch (flag protocol, mode 0): launch `burst_pos` of
+    // `burst_len` works on epoch  *epoch + 1 + burst_pos  (every launch of the burst reads the epoch word before the last
+    // one advances it by burst_len), keeps its counters in slot burst_pos of `counters`, and hands its flags and
+    // acknowledgements over in launch order through the local sequence words seq[0] (acks) and seq[1 + peer] (flags)
+    int burst_pos, burst_len;
+    unsigned* seq;
 };
+constexpr int kMaxBurst = 32;                    // launches of one burst (counter slots)
+constexpr int kCtrStride = 1 + kMaxPushPeers;    // words per counter slot
 
 struct TArgs {
     int halo_on;

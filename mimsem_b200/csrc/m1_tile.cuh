@@ -62,11 +62,22 @@ static __device__ __noinline__ void halo_push_role(const TArgs& a, unsigned long
     if (threadIdx.x < h.npush) {
         const int p = threadIdx.x;
         __threadfence_system();
-        const unsigned done = atomicAdd(&h.counters[1 + p], 1u);
+        unsigned* ctr = h.counters + h.burst_pos * kCtrStride;
+        const unsigned done = atomicAdd(&ctr[1 + p], 1u);
         if (done == (unsigned)h.push_ctas - 1) {
-            h.counters[1 + p] = 0;
+            ctr[1 + p] = 0;
+            if (h.burst_len > 1) {
+                // launches of a burst overlap: flags must still rise in launch order (a receiver that sees flag e takes
+                // every epoch <= e for delivered)
+                volatile unsigned* sq = h.seq + 1 + p;
+                while (*sq != (unsigned)h.burst_pos) __nanosleep(20);
+            }
             __threadfence_system();
             st_release_sys(peers[p].signal, epoch);
+            if (h.burst_len > 1) {
+                __threadfence();
+                h.seq[1 + p] = h.burst_pos == h.burst_len - 1 ? 0u : (unsigned)h.burst_pos + 1u;
+            }
         }
     }
 }
@@ -178,19 +189,32 @@ static __device__ __noinline__ void halo_push_role_ll(const TArgs& a, unsigned l
 static __device__ __noinline__ void halo_cta_done(const TArgs& a, unsigned long long epoch) {
     __shared__ int last;
     __syncthreads();
+    const bool burst = a.halo.burst_len > 1;
     if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(&a.halo.counters[0], 1u);
+        unsigned* ctr = a.halo.counters + a.halo.burst_pos * kCtrStride;
+        const unsigned done = atomicAdd(&ctr[0], 1u);
         last = (done == (unsigned)(a.halo.push_ctas + a.ntiles - a.halo.n_int) - 1) ? 1 : 0;
-        if (last) a.halo.counters[0] = 0;
+        if (last) {
+            ctr[0] = 0;
+            if (burst) {
+                // acknowledgements (and the epoch word) in launch order
+                volatile unsigned* sq = a.halo.seq;
+                while (*sq != (unsigned)a.halo.burst_pos) __nanosleep(20);
+            }
+        }
     }
     __syncthreads();
     if (!last || a.halo.push_only) return;
     // one thread per peer: the release stores cross NVLink concurrently (a serial loop costs a round trip per peer)
     if ((int)threadIdx.x < a.halo.npull) st_release_sys(a.halo.pull[threadIdx.x].signal, epoch);
+    if (burst) __syncthreads();
     if (threadIdx.x == 0) {
-        a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
-        a.halo.epoch[1] = epoch;
+        if (!burst || a.halo.burst_pos == a.halo.burst_len - 1) {
+            a.halo.epoch[0] = epoch;   // [push counter, pull counter] of mimsem_gpu_halo_push / _pull: kept in step
+            a.halo.epoch[1] = epoch;
+        }
         __threadfence();
+        if (burst) a.halo.seq[0] = a.halo.burst_pos == a.halo.burst_len - 1 ? 0u : (unsigned)a.halo.burst_pos + 1u;
     }
 }
 
@@ -529,9 +553,10 @@ __global__ void __launch_bounds__(128, MINB) k_apply_m1_tile(const __grid_consta
         if (a.pdl) pdl_launch_dependents();
         if ((int)blockIdx.x < a.halo.push_ctas || (int)blockIdx.x - a.halo.push_ctas >= a.halo.n_int) {
             // push CTAs and boundary tiles share the epoch word and the counters with the previous launch: under programmatic
-            // dependent launch they wait for it; interior tiles (no ghost rows) run on while it drains
-            if (a.pdl) pdl_wait_primary();
-            epoch = *a.halo.epoch + 1;
+            // dependent launch they wait for it (interior tiles, no ghost rows, run on while it drains) -- unless the launch
+            // is part of a burst, whose launches have their own epoch offsets and counter slots and overlap completely
+            if (a.pdl && a.halo.burst_len <= 1) pdl_wait_primary();
+            epoch = *reinterpret_cast<volatile unsigned long long*>(a.halo.epoch) + 1 + (unsigned long long)a.halo.burst_pos;
         }
         if ((int)blockIdx.x < a.halo.push_ctas) {
             // data epoch of the pushed field = epoch + lead

@@ -655,10 +655,21 @@ class DistributedEngine:
                 self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # fused M1 launches of one graph form a burst: each works on its own epoch offset and counter slot, so that under
+        # programmatic dependent launch they overlap completely (push of step i+1 during step i); see HaloFused
+        as_burst = (op == "M1" and self.p2p is not None and self.fused and not self.ll and 1 < nsteps <= 32
+                    and self._fused_ok(xs[0], kw))
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            for i in range(nsteps):
-                self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
+        try:
+            with torch.cuda.graph(graph):
+                for i in range(nsteps):
+                    if as_burst:
+                        self.engine.set_option("halo_burst_len", nsteps)
+                        self.engine.set_option("halo_burst_pos", i)
+                    self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
+        finally:
+            self.engine.set_option("halo_burst_len", 0)
+            self.engine.set_option("halo_burst_pos", 0)
         return graph.replay
 
     # test / IO helpers ------------------------------------------------------------------
