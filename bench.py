@@ -355,7 +355,7 @@ def main():
         eng = mb.Engine.from_mesh(mesh, local, thick=thick)
     # 1 GPU: consecutive steps are independent applies (ring of distinct fields), so a launch may start while the CTAs of
     # the previous one retire (programmatic dependent launch); plain M1 then runs best as the persistent ring kernel
-    burst = not args.no_graph and not args.no_pdl and (world == 1 or (args.op == "M1" and not args.chain and not args.pipelined))
+    burst = not args.no_graph and not args.no_pdl and (world == 1 or (args.op == "M1" and not args.chain))
     auto_opts = []
     if burst:
         auto_opts.append("pdl_independent=1")
@@ -440,7 +440,7 @@ def main():
         eng.engine.set_option("pdl_independent", 0)
         auto_opts = []
 
-    def measure_burst():
+    def measure_burst(pipelined=False):
         """1 GPU: W warm-up + exactly K timed steps, replayed from CUDA graphs that hold several consecutive steps each
         (slot = step % RING), so that programmatic dependent launch can overlap a launch with the tail of the previous one."""
         B = RING * max(1, 18 // RING)
@@ -448,7 +448,7 @@ def main():
         def capture(nsteps):
             if world > 1:
                 class _G:   # same interface as a CUDAGraph
-                    replay = staticmethod(eng.capture_burst(op, xs, cs, ys, nsteps, **kw_of(0)))
+                    replay = staticmethod(eng.capture_burst(op, xs, cs, ys, nsteps, pipelined=pipelined, **kw_of(0)))
                 return _G
             st = torch.cuda.Stream()
             with torch.cuda.stream(st):
@@ -463,6 +463,10 @@ def main():
         g_full = capture(B)
         n_full, n_rem = args.steps // B, args.steps % B
         g_rem = capture(n_rem) if n_rem else None
+        if pipelined:
+            barrier()
+            eng.prologue_push(xs[0])
+            barrier()
         for _ in range(-(-args.warmup // B)):
             g_full.replay()
         barrier()
@@ -496,6 +500,10 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 sus = float(t[0])
             sustained_ms = (sus, n_rep * B)
+        if pipelined:
+            # end of the pipelined sequence: consume what the last step pushed, push nothing
+            eng.apply(op, xs[0], coeff=None if cs is None else cs[0], out=ys[0], pipeline_last=True, **kw_of(0))
+            barrier()
         return ms, ms, launches_per_step * args.steps, sustained_ms, True
 
     def measure(pipelined):
@@ -506,7 +514,7 @@ def main():
             barrier()
         replays = None
         if burst:
-            return measure_burst()
+            return measure_burst(pipelined)
         if not args.no_graph and (world == 1 or getattr(eng, 'graph_safe', False)):
             try:
                 # (each capture warms up with real applies of its slot; after the last slot a pipelined sequence
@@ -587,6 +595,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     second = None
     strict = None
+    if fused and burst and not headline_pipelined:
+        barrier()
+        second = measure(True)[0]
     if fused and burst:
         # the same launches in ordinary stream order, one graph per step: what a chain of DEPENDENT applies gets
         barrier()
@@ -597,6 +608,7 @@ def main():
     elif fused and not headline_pipelined:
         barrier()
         second = measure(True)[0]
+
 
     q2 = (p + 1) ** 2
     if args.chain:

@@ -908,7 +908,7 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
             t.halo_on = 1;
             t.halo = *hf;
             t.halo.seq = c->d_fused_counters.p + kMaxBurst * kCtrStride;
-            if (c->halo_burst_len > 1 && c->pdl && !hf->ll && !hf->lead && !hf->push_only) {
+            if (c->halo_burst_len > 1 && c->pdl && !hf->ll && !hf->push_only) {
                 if (c->halo_burst_pos < 0 || c->halo_burst_pos >= c->halo_burst_len || c->halo_burst_len > kMaxBurst)
                     return fail(MIMSEM_ERR_ARG, "fused ghost refresh: burst position / length out of range");
                 t.halo.burst_pos = c->halo_burst_pos;

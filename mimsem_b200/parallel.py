@@ -276,6 +276,9 @@ class DistributedEngine:
         self._inbox = {}
         import os
         self.fused = os.environ.get("MIMSEM_FUSED_HALO", "1") != "0"
+        # upper limit of push CTAs per fused launch (0: none).  Launches of a burst overlap, the push is off the critical
+        # path there, and every push CTA holds a tile's worth of shared memory while it waits for NVLink
+        self.push_ctas_cap = int(os.environ.get("MIMSEM_PUSH_CTAS", "0"))
         # fused M1: data + flag (default), or self-validating 16-byte cells without fence and flag (MIMSEM_HALO_LL=1;
         # measured slower at 2 and 4 GPUs, see profiles/r02_summary.md)
         self.ll = os.environ.get("MIMSEM_HALO_LL", "0") != "0"
@@ -575,6 +578,8 @@ class DistributedEngine:
         inbox, stride, push_rows = self._inbox[1]
         nlev = x.shape[1]
         push_ctas = max(1, min(148, push_rows // 16))    # ~16 rows per CTA: one pass with four loads in flight per thread
+        if self.push_ctas_cap:
+            push_ctas = max(1, min(push_ctas, self.push_ctas_cap))
         if mode is None:
             mode = 0 if x_next is None else 1
         xp = x.data_ptr() if x_next is None else x_next.data_ptr()
@@ -642,10 +647,12 @@ class DistributedEngine:
             self.apply(op, x, coeff=coeff, out=out, **kw)
         return graph.replay, out
 
-    def capture_burst(self, op, xs, coeffs, outs, nsteps, **kw):
+    def capture_burst(self, op, xs, coeffs, outs, nsteps, pipelined=False, **kw):
         """Capture `nsteps` consecutive steps, step i on slot i % len(xs), into ONE CUDA graph and return its replay.  With
         the engine option "pdl_independent" the launches inside carry programmatic dependencies: a step starts while the
-        previous one drains (the slots must then be independent fields).  All ranks must capture and replay alike."""
+        previous one drains (the slots must then be independent fields).  pipelined (fused M1): step i also pushes the
+        boundary rows of the NEXT step's input (the last step those of xs[0], so that replays chain); the caller starts the
+        sequence with prologue_push(xs[0]) + a barrier.  All ranks must capture and replay alike."""
         torch = self.torch
         n = len(xs)
         side = torch.cuda.Stream(device=self.device)
@@ -666,7 +673,10 @@ class DistributedEngine:
                     if as_burst:
                         self.engine.set_option("halo_burst_len", nsteps)
                         self.engine.set_option("halo_burst_pos", i)
-                    self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **kw)
+                    nxt = {}
+                    if pipelined:
+                        nxt = {"x_next": xs[(i + 1) % n if i < nsteps - 1 else 0]}
+                    self.apply(op, xs[i % n], coeff=None if coeffs is None else coeffs[i % n], out=outs[i % n], **nxt, **kw)
         finally:
             self.engine.set_option("halo_burst_len", 0)
             self.engine.set_option("halo_burst_pos", 0)

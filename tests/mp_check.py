@@ -158,6 +158,27 @@ def main():
                 rows = perm1[:n_own]
                 if not torch.equal(outs[i][rows], refs[i][rows]):
                     failures.append((what, kind, p, ne, "fused M1 under programmatic dependent launch differs (slot %d, rank %d)" % (i, rank)))
+            # the same burst with the ghost rows of step i+1 pushed during step i (pipelined), replays chained
+            deng.engine.set_option("pdl_independent", 1)
+            replay = deng.capture_burst("M1", xsl, None, outs, 6, pipelined=True, scale=1e8, tpow=1)
+            for o in outs:
+                o.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            deng.prologue_push(xsl[0])
+            torch.cuda.synchronize()
+            dist.barrier()
+            for _ in range(3):
+                replay()
+            last = deng.apply("M1", xsl[0], scale=1e8, tpow=1, pipeline_last=True)
+            torch.cuda.synchronize()
+            deng.engine.set_option("pdl_independent", 0)
+            for i in range(3):
+                rows = perm1[:n_own]
+                if not torch.equal(outs[i][rows], refs[i][rows]):
+                    failures.append((what, kind, p, ne, "pipelined burst differs (slot %d, rank %d)" % (i, rank)))
+            if not torch.equal(last[perm1[:n_own]], refs[0][perm1[:n_own]]):
+                failures.append((what, kind, p, ne, "consume-only apply after a pipelined burst differs (rank %d)" % rank))
         # partitioned mass-matrix solve: x -> b = M1 x (partitioned) -> CG over peer memory recovers x; every rank
         # stops at the same iteration with the same residual
         if deng.p2p is not None and deng.fused and nk % 2 == 0:
