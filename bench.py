@@ -359,7 +359,8 @@ def main():
     auto_opts = []
     if burst:
         auto_opts.append("pdl_independent=1")
-        if world == 1 and args.op == "M1" and not args.chain and not any(o.startswith("m1_variant=") for o in args.opt):
+        # (the ring kernel wants many tiles per SM: on C3 / C4, 400-864 elements, the tile kernel is the faster one)
+        if world == 1 and args.op == "M1" and not args.chain and mesh.nel >= 4000 and not any(o.startswith("m1_variant=") for o in args.opt):
             auto_opts.append("m1_variant=3")
     for kv in auto_opts + args.opt:
         name, val = kv.split("=")
