@@ -394,6 +394,14 @@ int mimsem_gpu_solve_M1_dist(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, do
                              double* d_x, double rtol, int maxit, int* iters, double* relres, const mimsem_halo_desc* halo,
                              const mimsem_reduce_desc* reduce, void* stream);
 
+/* Device memory for hosts that do not link the CUDA runtime themselves (the C++ host layer, mimsem_b200/host/DistEngine):
+ * plain cudaMalloc (zero-filled) / cudaFree / cudaMemcpy on the context's device; kind 0 host -> device, 1 device -> host,
+ * 2 device -> device (synchronous); _sync waits for the given stream (NULL: the whole device). */
+int mimsem_gpu_dev_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** d_ptr);
+int mimsem_gpu_dev_free(mimsem_gpu_ctx* ctx, void* d_ptr);
+int mimsem_gpu_dev_copy(mimsem_gpu_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
+int mimsem_gpu_dev_sync(mimsem_gpu_ctx* ctx, void* stream);
+
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);
 

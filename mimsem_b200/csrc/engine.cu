@@ -2139,6 +2139,38 @@ int mimsem_gpu_scatter_rows(mimsem_gpu_ctx* c, int64_t nrows, int nlev, int ld, 
     return finish_launch(c, "scatter_rows");
 }
 
+int mimsem_gpu_dev_alloc(mimsem_gpu_ctx* c, int64_t bytes, void** d_ptr) {
+    if (!c || !d_ptr || bytes < 1) return fail(MIMSEM_ERR_ARG, "bad argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaMalloc(d_ptr, (size_t)bytes));
+    CUDA_OK(cudaMemset(*d_ptr, 0, (size_t)bytes));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_dev_free(mimsem_gpu_ctx* c, void* d_ptr) {
+    if (!c || !d_ptr) return MIMSEM_OK;
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaFree(d_ptr));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_dev_copy(mimsem_gpu_ctx* c, void* dst, const void* src, int64_t bytes, int kind) {
+    if (!c || !dst || !src || bytes < 0 || kind < 0 || kind > 2) return fail(MIMSEM_ERR_ARG, "bad argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : (kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+    if (bytes > 0) CUDA_OK(cudaMemcpy(dst, src, (size_t)bytes, k));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_dev_sync(mimsem_gpu_ctx* c, void* st) {
+    if (!c) return fail(MIMSEM_ERR_ARG, "null context");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    if (st) CUDA_OK(cudaStreamSynchronize((cudaStream_t)st));
+    else CUDA_OK(cudaDeviceSynchronize());
+    return MIMSEM_OK;
+}
+
 int mimsem_gpu_ipc_alloc(mimsem_gpu_ctx* c, int64_t bytes, void** d_ptr, unsigned char handle[64]) {
     if (!c || !d_ptr || !handle || bytes < 1) return fail(MIMSEM_ERR_ARG, "bad argument");
     int rc = bind_device(c);

@@ -140,3 +140,44 @@ def test_ghost_refresh_gloo_world2():
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("kind,p,ne,world", [("sphere", 3, 4, 2), ("sphere", 4, 6, 4), ("sphere", 3, 6, 8), ("box", 3, 6, 3)])
+def test_cpp_partition_equals_python_partition(kind, p, ne, world):
+    """The C++ host layer (mimsem_b200/host/Partition.cpp, libmimsem_host.so) builds the same subdomains, numberings and
+    ghost / send lists as parallel.py, array for array."""
+    import ctypes as C
+    import os
+    import mimsem_b200 as mb
+    from mimsem_b200.parallel import send_lists
+    lib = C.CDLL(os.path.join(os.path.dirname(mb.__file__), "libmimsem_host.so"))
+    lib.mimsem_host_partition_create.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_void_p)]
+    lib.mimsem_host_partition_array.restype = C.c_int64
+    lib.mimsem_host_partition_array.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    lib.mimsem_host_partition_sizes.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mimsem_host_partition_destroy.argtypes = [C.c_void_p]
+    mesh = mb.Mesh(kind, p, ne)
+
+    def arr(h, name):
+        n = lib.mimsem_host_partition_array(h, name.encode(), None)
+        assert n >= 0, name
+        out = np.zeros(n, dtype=np.int64)
+        lib.mimsem_host_partition_array(h, name.encode(), out.ctypes.data_as(C.c_void_p))
+        return out
+    for rank in range(world):
+        P, sends = send_lists(mesh, rank, world)
+        h = C.c_void_p()
+        assert lib.mimsem_host_partition_create(0 if kind == "sphere" else 1, p, ne, rank, world, C.byref(h)) == 0
+        sz = np.zeros(12, dtype=np.int64)
+        lib.mimsem_host_partition_sizes(h, sz.ctypes.data_as(C.c_void_p))
+        assert list(sz) == [P.nel_owned, P.nel_total, P.n_interior, P.n0, P.n1, P.n2, P.nq, P.n0_owned, P.n1_owned, P.n2_owned,
+                            P.n1_halo, P.n2_halo]
+        for name in ("elements", "g0", "g1", "g2", "gq", "el0", "el1x", "el1y", "el2", "elq"):
+            assert np.array_equal(arr(h, name), np.asarray(getattr(P, name)).ravel()), (rank, name)
+        for space in (0, 1, 2):
+            for q in range(world):
+                r = P.recv[space].get(q)
+                assert np.array_equal(arr(h, "recv%d_%d" % (space, q)), r["local"] if r is not None else np.zeros(0)), (rank, space, q)
+                s = sends[space].get(q)
+                assert np.array_equal(arr(h, "send%d_%d" % (space, q)), s if s is not None else np.zeros(0)), (rank, space, q)
+        lib.mimsem_host_partition_destroy(h)
