@@ -1,0 +1,155 @@
+// Multi-GPU check of the C++ host layer (DistEngine): N plain processes of one box, rank r on GPU r, rendezvous through
+// files.  Every rank applies the partitioned operators to its element block with zeroed ghost rows (so the ghost
+// refresh is exercised); rank 0 gathers the owned rows and compares them BITWISE with a one-GPU apply on the whole mesh.
+//   for r in 0 1; do MIMSEM_RANK=$r MIMSEM_WORLD=2 build/host_dist_check sphere 3 6 30 /tmp/rdv & done; wait
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "DistEngine.h"
+
+using namespace mimsem_host;
+
+namespace {
+
+struct SelfComm : Comm {
+    SelfComm() { rank = 0; world = 1; }
+    void allgather(const void* s, int64_t b, void* r) { std::memcpy(r, s, (size_t)b); }
+    void barrier() {}
+};
+
+std::vector<double> pseudo_random(size_t n, unsigned long long seed, double lo, double hi) {
+    std::vector<double> v(n);
+    unsigned long long s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    for (size_t i = 0; i < n; i++) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        v[i] = lo + (hi - lo) * (double)(s >> 11) / 9007199254740992.0;
+    }
+    return v;
+}
+
+// rank r contributes its owned rows (zeros elsewhere); the sum over ranks is the global field
+void gather_sum(Comm& comm, std::vector<double>& v) {
+    std::vector<double> all((size_t)comm.world * v.size());
+    comm.allgather(v.data(), (int64_t)v.size() * 8, all.data());
+    for (size_t i = 0; i < v.size(); i++) {
+        double s = 0.0;
+        for (int q = 0; q < comm.world; q++) s += all[(size_t)q * v.size() + i];
+        v[i] = s;
+    }
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 6) {
+        std::fprintf(stderr, "usage: MIMSEM_RANK=r MIMSEM_WORLD=n host_dist_check sphere|box p ne nk rendezvous_dir\n");
+        return 2;
+    }
+    const int kind = std::string(argv[1]) == "box" ? MIMSEM_MESH_BOX : MIMSEM_MESH_SPHERE;
+    const int p = std::atoi(argv[2]), ne = std::atoi(argv[3]), nk = std::atoi(argv[4]);
+    const int rank = std::atoi(getenv("MIMSEM_RANK") ? getenv("MIMSEM_RANK") : "0");
+    const int world = std::atoi(getenv("MIMSEM_WORLD") ? getenv("MIMSEM_WORLD") : "1");
+    int failures = 0;
+    try {
+        GlobalMesh mesh;
+        if (mesh.create(kind, p, ne)) throw std::runtime_error(mimsem_last_error());
+        // layer thickness: a level profile times a horizontally non-uniform factor
+        std::vector<double> thick((size_t)nk * mesh.NQ);
+        for (int k = 0; k < nk; k++)
+            for (int64_t q = 0; q < mesh.NQ; q++) {
+                const double* x = &mesh.xyz[(size_t)q * 3];
+                const double r = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+                thick[(size_t)k * mesh.NQ + q] = (200.0 + 30.0 * k) * (1.0 + 0.1 * (kind == MIMSEM_MESH_SPHERE ? x[2] / r : std::cos(x[0] * 6.283e-3)));
+            }
+        const std::vector<double> x1 = pseudo_random((size_t)nk * mesh.N1, 1, -1, 1), x2 = pseudo_random((size_t)nk * mesh.N2, 2, -1, 1);
+        const std::vector<double> h2 = pseudo_random((size_t)nk * mesh.N2, 3, 0.5e4, 1.5e4), u1 = pseudo_random((size_t)nk * mesh.N1, 4, -1e9, 1e9);
+        const std::vector<double> x0 = pseudo_random((size_t)nk * mesh.N0, 5, -1, 1);
+        FileComm comm(argv[5], rank, world);
+        DistEngine eng(mesh, thick.data(), nk, &comm, rank);
+        SelfComm self;
+        DistEngine* one = rank == 0 ? new DistEngine(mesh, thick.data(), nk, &self, 0) : NULL;
+        struct Case { const char* op; int sin, sout, sc; const std::vector<double>* x; const std::vector<double>* c; int tpow; };
+        const Case cases[] = {{"M1", 1, 1, -1, &x1, NULL, 1}, {"M1h", 1, 1, 2, &x1, &h2, 2}, {"K", 1, 2, 1, &x1, &u1, 2}, {"M2", 2, 2, -1, &x2, NULL, 1},
+                              {"E21", 1, 2, -1, &x1, NULL, 0}, {"E12", 2, 1, -1, &x2, NULL, 0}, {"M0", 0, 0, -1, &x0, NULL, 1}, {"E10", 0, 1, -1, &x0, NULL, 0}};
+        auto N_of = [&](int s) { return s == 0 ? mesh.N0 : (s == 1 ? mesh.N1 : mesh.N2); };
+        auto run = [&](DistEngine& e, const Case& c, std::vector<double>& yg) {
+            double* dx = e.alloc_field(c.sin, nk);
+            double* dc = c.c ? e.alloc_field(c.sc, nk) : NULL;
+            double* dy = e.alloc_field(c.sout, nk);
+            // owned rows from the global field, ghost rows ZERO: they must come from the exchange
+            auto load = [&](const std::vector<double>& g, int space, double* d) {
+                std::vector<double> own((size_t)nk * N_of(space), 0.0);
+                const std::vector<int64_t>& ids = e.part().gids(space);
+                for (int i = 0; i < e.part().n_owned(space); i++)
+                    for (int k = 0; k < nk; k++) own[(size_t)k * N_of(space) + ids[i]] = g[(size_t)k * N_of(space) + ids[i]];
+                e.scatter_from_global(own.data(), space, nk, d);
+            };
+            load(*c.x, c.sin, dx);
+            if (dc) load(*c.c, c.sc, dc);
+            for (int rep = 0; rep < 3; rep++) e.apply(c.op, dx, dc, dy, nk, 1.0e8, c.tpow);
+            e.sync();
+            yg.assign((size_t)nk * N_of(c.sout), 0.0);
+            e.owned_to_global(dy, c.sout, nk, yg.data());
+            e.free_field(dx);
+            if (dc) e.free_field(dc);
+            e.free_field(dy);
+        };
+        for (size_t ci = 0; ci < sizeof(cases) / sizeof(cases[0]); ci++) {
+            std::vector<double> yg, ys;
+            run(eng, cases[ci], yg);
+            gather_sum(comm, yg);
+            if (rank == 0) {
+                run(*one, cases[ci], ys);
+                const bool same = std::memcmp(yg.data(), ys.data(), yg.size() * 8) == 0;
+                std::printf("%-4s on %d GPUs vs 1 GPU: %s\n", cases[ci].op, world, same ? "bitwise equal" : "DIFFERENT");
+                if (!same) failures++;
+            }
+        }
+        // partitioned solve: b = M1 x, then M1^-1 b recovers x; every rank stops at the same iteration
+        {
+            double* dx = eng.alloc_field(1, nk);
+            double* db = eng.alloc_field(1, nk);
+            double* ds = eng.alloc_field(1, nk);
+            eng.scatter_from_global(x1.data(), 1, nk, dx);
+            eng.apply_M1(dx, db, nk, 1.0e8, 1);
+            double rr = 0.0;
+            const int its = eng.solve_M1(db, ds, nk, 1.0e8, 1, 1e-13, 300, &rr);
+            eng.sync();
+            std::vector<double> xs((size_t)nk * mesh.N1, 0.0);
+            eng.owned_to_global(ds, 1, nk, xs.data());
+            gather_sum(comm, xs);
+            double num = 0.0, den = 0.0;
+            for (size_t i = 0; i < xs.size(); i++) {
+                num += (xs[i] - x1[i]) * (xs[i] - x1[i]);
+                den += x1[i] * x1[i];
+            }
+            std::vector<int> all_its(world);
+            comm.allgather(&its, 4, all_its.data());
+            bool agree = true;
+            for (int q = 0; q < world; q++) agree = agree && all_its[q] == its;
+            if (rank == 0) {
+                std::printf("solve_M1 on %d GPUs: %d iterations, relres %.2e, error %.2e, ranks %s\n", world, its, rr, std::sqrt(num / den), agree ? "agree" : "DISAGREE");
+                if (!(its < 300 && std::sqrt(num / den) < 1e-10 && agree)) failures++;
+            }
+            eng.free_field(dx);
+            eng.free_field(db);
+            eng.free_field(ds);
+        }
+        if (eng.halo_error()) {
+            std::printf("rank %d: a ghost refresh timed out\n", rank);
+            failures++;
+        }
+        comm.barrier();
+        delete one;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "rank %d: %s\n", rank, e.what());
+        return 1;
+    }
+    if (rank == 0) std::printf("HOST_DIST_CHECK %s\n", failures ? "FAIL" : "OK");
+    return failures ? 1 : 0;
+}

@@ -615,3 +615,24 @@ def test_multi_gpu_partitioned_apply():
     for ll in ("1", "0"):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MIMSEM_HALO_LL=ll))
         assert r.returncode == 0 and "MP_CHECK OK" in r.stdout, (ll, r.stdout[-2000:] + r.stderr[-2000:])
+
+
+def test_multi_gpu_cpp_host_layer(tmp_path):
+    """N>1 without Python on the data or the control path: the C++ host layer (mimsem_b200/host/DistEngine, Partition) as N
+    plain processes with a file rendezvous; eight operators and the partitioned solve, bitwise equal to one GPU
+    (mimsem_b200/host/host_dist_check.cpp)."""
+    import os
+    import subprocess
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (the partition itself is compared with parallel.py on CPU: tests/test_partition.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "mimsem_b200", "host", "build", "host_dist_check")
+    for cfg in (["sphere", "3", "6", "30"], ["box", "3", "6", "40"]):
+        rdv = tmp_path / ("rdv_" + cfg[0])
+        rdv.mkdir()
+        procs = [subprocess.Popen([exe] + cfg + [str(rdv)], env=dict(os.environ, MIMSEM_RANK=str(r), MIMSEM_WORLD=str(n)),
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(n)]
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs) and "HOST_DIST_CHECK OK" in outs[0], outs
