@@ -1102,6 +1102,12 @@ int apply_rot(mimsem_gpu_ctx* c, bool up, int lev0, int nlev, int ld, double sca
     a.Wr = c->d_Wr.p;
     a.tau = tau;
     for (int i = 0; i <= kMaxP; i++) a.xn[i] = i <= c->p ? c->xn[i] : 0.0;
+    for (int i = 0; i <= kMaxP; i++) {
+        double d = 1.0;
+        for (int j = 0; j <= c->p; j++)
+            if (j != i && i <= c->p) d *= c->xn[i] - c->xn[j];
+        a.wb[i] = i <= c->p ? 1.0 / d : 0.0;
+    }
     const int64_t threads = (int64_t)a.nel * nlev;
     if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
     if (threads == 0) return MIMSEM_OK;
@@ -1145,6 +1151,12 @@ int apply_m0h_up(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, in
     a.det = c->d_det.p;
     a.tau = tau;
     for (int i = 0; i <= kMaxP; i++) a.xn[i] = i <= c->p ? c->xn[i] : 0.0;
+    for (int i = 0; i <= kMaxP; i++) {
+        double d = 1.0;
+        for (int j = 0; j <= c->p; j++)
+            if (j != i && i <= c->p) d *= c->xn[i] - c->xn[j];
+        a.wb[i] = i <= c->p ? 1.0 / d : 0.0;
+    }
     copy_basis(c, a);
     const FastDiv fd = make_fastdiv((unsigned)nlev);
     a.div_m = fd.m;

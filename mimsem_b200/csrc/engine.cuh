@@ -52,6 +52,7 @@ struct KArgs {
     const double* Wr;             // [nel_total][q2] w_q * (J00 J11 - J01 J10) / det   (= +-w_q)
     double tau;                   // upwinding time scale fac*dt
     double xn[kMaxP + 1];         // GLL nodes
+    double wb[kMaxP + 1];         // barycentric weights 1 / prod_{j != i} (xn[i] - xn[j])
 };
 
 // Division of a 32-bit index by a launch-constant divisor (Granlund-Montgomery):
@@ -126,6 +127,7 @@ struct NodeArgs {
     const double* det;
     double tau;
     double xn[kMaxP + 1];
+    double wb[kMaxP + 1];
 };
 
 }  // namespace mimsem

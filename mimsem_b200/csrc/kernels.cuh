@@ -388,15 +388,20 @@ __global__ void __launch_bounds__(128) k_apply_m1_lines(const __grid_constant__ 
 // (src/Assembly.cpp:1346-1395, 1784-1853; eul/Assembly.cpp:1030-1083 adds t^2 and scale; sigma = det J / |det|).
 // One thread per (element, level), structured like k_apply_m1: shared edges by gather from the west / south neighbour.
 
-// Lagrange polynomials through the GLL nodes at x (LagrangeNode::eval_q, src/Basis.cpp:183-190)
+// Lagrange polynomials through the GLL nodes at x (LagrangeNode::eval_q, src/Basis.cpp:183-190: prod_{j != i}
+// (x - x_j) / (x_i - x_j)), with the denominators folded into the barycentric weights wb[i] on the host: the reference's 2 P (P+1)
+// FP64 divisions per quadrature point were the whole cost of the upwinded kernels (a few ulps of difference).
 template <int P>
-__device__ __forceinline__ void lagrange_at(const double* xn, double x, double (&l)[P + 1]) {
+__device__ __forceinline__ void lagrange_at(const double* xn, const double* wb, double x, double (&l)[P + 1]) {
+    double d[P + 1];
+#pragma unroll
+    for (int j = 0; j <= P; j++) d[j] = x - xn[j];
 #pragma unroll
     for (int i = 0; i <= P; i++) {
-        double y = 1.0;
+        double y = wb[i];
 #pragma unroll
         for (int j = 0; j <= P; j++)
-            if (j != i) y *= (x - xn[j]) / (xn[i] - xn[j]);
+            if (j != i) y *= d[j];
         l[i] = y;
     }
 }
@@ -410,12 +415,13 @@ __device__ __forceinline__ void departure_basis(const A& a, int n, int qx, int q
     const double* __restrict__ J = a.J4 + ((size_t)n * Q2 + q) * 4;
     const double det = a.det[(size_t)n * Q2 + q];
     // interp1_g (src/Geom.cpp:302-313), then J^-1 (src/Assembly.cpp:1815-1816)
-    const double ux0 = (J[0] * ul0 + J[1] * ul1) / det;
-    const double ux1 = (J[2] * ul0 + J[3] * ul1) / det;
-    const double v0 = +J[3] * ux0 / det - J[1] * ux1 / det;
-    const double v1 = -J[2] * ux0 / det + J[0] * ux1 / det;
-    lagrange_at<P>(a.xn, a.xn[qx] - a.tau * v0, lx);
-    lagrange_at<P>(a.xn, a.xn[qy] - a.tau * v1, ly);
+    const double idet = 1.0 / det;
+    const double ux0 = (J[0] * ul0 + J[1] * ul1) * idet;
+    const double ux1 = (J[2] * ul0 + J[3] * ul1) * idet;
+    const double v0 = (J[3] * ux0 - J[1] * ux1) * idet;
+    const double v1 = (J[0] * ux1 - J[2] * ux0) * idet;
+    lagrange_at<P>(a.xn, a.wb, a.xn[qx] - a.tau * v0, lx);
+    lagrange_at<P>(a.xn, a.wb, a.xn[qy] - a.tau * v1, ly);
 }
 
 // potential vorticity seen by quadrature point (qx,qy) of element n, column k
