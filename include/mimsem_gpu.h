@@ -234,6 +234,13 @@ int mimsem_gpu_diag_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double s
 int mimsem_gpu_pc_bjacobi_M1(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* d_r,
                              double* d_z, void* stream);
 
+/* Umat_ray::assemble(lev, scale, dt, exner_k, exner_s) + MatMult (eul/Assembly.cpp:1846-1979; eul/Euler_2.cpp:1218-1229,
+ * 1276-1277, 1437-1448): the Rayleigh-friction mass matrix, point weight dt k_v(exner(q), exner_s(q)) / thick with
+ * k_v = compute_k_v of the reference.  d_exner: the Exner-pressure 2-form in column layout (columns = levels lev0 ..),
+ * d_exner_s: its level-0 values, ONE per face (n2 doubles).  Columns are levels lev0 + j as for apply_M1. */
+int mimsem_gpu_apply_M1ray(mimsem_gpu_ctx* ctx, int lev0, int nlev, int ld, double scale, double dt, const double* d_exner,
+                           const double* d_exner_s, const double* d_x, double* d_y, void* stream);
+
 /*
  * Remaining coefficient operators of the vorticity / forcing terms:
  *   Pvec::assemble(lev, scale)            -> diag_M0 (d_h2 = NULL, tpow = 1): M0 is diagonal when m == p, so the lumped
@@ -283,7 +290,8 @@ int mimsem_gpu_incidence_csr(const mimsem_gpu_ctx* ctx, int which, int64_t out_s
 int mimsem_gpu_apply_host(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
                           const double* h_coeff, const double* h_x, double* h_y);
 /* The same with the operators of BASELINE config 2: op 7 R (h_coeff = q0), 8 R_up (h_coeff = q0, h_u1, tau),
- * 9 M0h_up (h_coeff = h2, h_u1, tau); every other op ignores h_u1 and tau. */
+ * 9 M0h_up (h_coeff = h2, h_u1, tau); and op 21 Umat_ray (h_coeff = Exner 2-form of the levels, h_u1 = its level-0 values,
+ * n2 doubles, tau = dt).  Every other op ignores h_u1 and tau. */
 int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* ctx, int op, int lev0, int nlev, double scale, int tpow, int flags,
                              const double* h_coeff, const double* h_u1, double tau, const double* h_x, double* h_y);
 

@@ -137,6 +137,7 @@ struct mimsem_gpu_ctx {
     DevBuf<unsigned> d_halo_counters;   // [2][64] finished-CTA counters of the p2p halo kernels (push, pull)
     // staging for the host-buffer entry point
     DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[2], s_out2[2], s_x2[2], s_y2[2], s_c2[2], s_u2[2];
+    DevBuf<double> s_ray;                    // level-0 Exner values of Umat_ray (apply_host)
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_host[3] = {nullptr, nullptr, nullptr};
 
@@ -828,6 +829,9 @@ void fill_common(const mimsem_gpu_ctx* c, KArgs& a, int lev0, int nlev, int ld, 
     a.eflags = c->d_eflags.p;
     a.tinv = (flags & MIMSEM_THICK_MEAN) ? c->d_tmean.p : c->d_tinv.p;
     a.c = nullptr;
+    a.c2 = nullptr;
+    a.ray_dt = 0.0;
+    a.det = c->d_det.p;
     a.el1xT = c->d_el1xT.p;
     a.elqT = c->d_elqT.p;
     a.Gc = a.Gr = nullptr;
@@ -951,6 +955,34 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
     b.nbr = c->d_far.p;
     launch_m1_lines(c->p, with_h, true, b, dim3(grid_for((int64_t)b.nel * nlev, 128)), st);
     return finish_launch(c, "apply_M1 far lines");
+}
+
+// y = M1_ray(exner, exner_s) x: Umat_ray::assemble(lev, scale, dt, exner_k, exner_s) + MatMult (eul/Assembly.cpp:1858-1979,
+// called from eul/Euler_2.cpp:1218-1229, 1276-1277, 1437-1448).  A mass matrix whose point weight is
+// dt k_v(exner(q), exner_s(q)) / thick: the M1(h) register kernel with the coefficient turned into the friction weight.
+int apply_m1_ray(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, double dt, const double* exner, const double* exner_s,
+                 const double* x, double* y, cudaStream_t st) {
+    int rc = check_ready(c, true, lev0, nlev, ld, 0);
+    if (rc) return rc;
+    if ((rc = bind_device(c))) return rc;
+    if (!exner || !exner_s || !x || !y) return fail(MIMSEM_ERR_ARG, "null field");
+    if (!c->d_det.p) return fail(MIMSEM_ERR_STATE, "set_geom first");
+    KArgs a;
+    fill_common(c, a, lev0, nlev, ld, scale, 1, 0);
+    a.G = c->d_G1.p;   // the weight carries its own 1/det
+    a.c = exner;
+    a.c2 = exner_s;
+    a.ray_dt = dt;
+    a.x = x;
+    a.y = y;
+    const int64_t threads = (int64_t)a.nel * nlev;
+    if (threads >= (1ll << 31)) return fail(MIMSEM_ERR_UNSUPPORTED, "more than 2^31 element-levels in one launch");
+    if (threads == 0 || dt == 0.0) {
+        if (threads && dt == 0.0) return fail(MIMSEM_ERR_ARG, "Umat_ray with dt = 0 is the zero operator");
+        return MIMSEM_OK;
+    }
+    launch_m1_regs(c->p, true, a, grid_for(threads, 128), st);
+    return finish_launch(c, "apply_M1ray");
 }
 
 int apply_m2(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double scale, int tpow, int flags,
@@ -1918,6 +1950,10 @@ int mimsem_gpu_apply_M1h(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double s
     if (!h2) return fail(MIMSEM_ERR_ARG, "null coefficient field");
     return apply_m1(c, true, lev0, nlev, ld, scale, tpow, flags, h2, x, y, (cudaStream_t)st);
 }
+int mimsem_gpu_apply_M1ray(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, double dt, const double* exner,
+                           const double* exner_s, const double* x, double* y, void* st) {
+    return apply_m1_ray(c, lev0, nlev, ld, scale, dt, exner, exner_s, x, y, (cudaStream_t)st);
+}
 int mimsem_gpu_apply_M2(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tpow, int flags, const double* x,
                         double* y, void* st) {
     return apply_m2(c, false, lev0, nlev, ld, scale, tpow, flags, nullptr, x, y, (cudaStream_t)st);
@@ -2048,6 +2084,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         case 18: sin = sout = 2; scoef = 2; break;          // M2(rho)^-1 (WhmatInv)
         case 19: sin = sout = 1; break;                     // diag M1 (MatGetDiagonal of the Umat shell): h_x is ignored
         case 20: sin = sout = 1; break;                     // element-block Jacobi of M1 (PCBJACOBI of the Umat shell)
+        case 21: sin = sout = 1; scoef = 2; break;          // Umat_ray: h_coeff = Exner 2-form of the levels, h_u1 = its level-0 values (n2), tau = dt
         default: return fail(MIMSEM_ERR_ARG, "unknown operator id");
     }
     const int64_t nsp[3] = {c->n0, c->n1, c->n2};
@@ -2055,6 +2092,11 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
     if (ncoef && !h_coeff) return fail(MIMSEM_ERR_ARG, "this operator needs a coefficient field");
     const bool need_u = (op == 8 || op == 9);
     if (need_u && !h_u1) return fail(MIMSEM_ERR_ARG, "this operator needs the advecting velocity");
+    if (op == 21) {
+        if (!h_u1) return fail(MIMSEM_ERR_ARG, "Umat_ray needs the level-0 Exner field");
+        CUDA_OK(c->s_ray.resize((size_t)c->n2));
+        CUDA_OK(cudaMemcpy(c->s_ray.p, h_u1, (size_t)c->n2 * sizeof(double), cudaMemcpyHostToDevice));
+    }
     // Pipeline over chunks of levels (levels are independent): while chunk c is being computed, chunk c+1 is on
     // its way in and chunk c-1 on its way out; two streams ping-pong so that both PCIe directions stay busy.
     const int ld = nlev;
@@ -2115,6 +2157,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
             case 18: rc = solve_m2(c, true, levk, nl, nl, scale, tpow, flags, cc, xc, yc, st); break;
             case 19: rc = diag_m1(c, false, levk, nl, nl, scale, tpow, flags, yc, st); break;
             case 20: rc = bjacobi_m1(c, levk, nl, nl, scale, tpow, flags, xc, yc, st); break;
+            case 21: rc = apply_m1_ray(c, levk, nl, nl, scale, tau, cc, c->s_ray.p, xc, yc, st); break;
             default: rc = apply_inc(c, op - 10, nl, nl, xc, yc, st); break;
         }
         if (rc) return rc;

@@ -39,6 +39,10 @@ struct KArgs {
     const double* tinv;           // [nq][nkT] inverse layer thickness, level fastest
     // fields
     const double* c;              // coefficient field (h2 or u1) or nullptr
+    // Umat_ray (eul/Assembly.cpp:1846-1979): Rayleigh friction; c = Exner pressure 2-form of the column's level, c2 = the same
+    // field's LEVEL-0 column (one value per face), ray_dt = dt (0: off); needs det and the level-0 thickness
+    const double* c2;
+    double ray_dt;
     const double* x;
     double* y;
     // basis

@@ -48,6 +48,19 @@ __device__ __forceinline__ double thick_factor(const KArgs& a, int gq, int k) {
     return f;
 }
 
+// Umat_ray's point weight dt k_v(exner, exner_s) (compute_k_v, eul/Assembly.cpp:1846-1856) from the interpolated (without
+// 1/det) Exner 2-forms hl (this level) and hls (level 0) at local quadrature point gq of element point (n, q)
+__device__ __forceinline__ double ray_weight(const KArgs& a, double hl, double hls, int n_q2_plus_q, int gq, int k) {
+    const double idet = 1.0 / ldro(a.det + n_q2_plus_q);
+    const double t = ldro(a.tinv + (size_t)gq * a.nkT + a.lev0 + k * a.lev_stride), t0 = ldro(a.tinv + (size_t)gq * a.nkT);
+    const double ex = hl * idet * t, exs = hls * idet * t0;
+    const double CP = 1004.5, RD = 287.0;
+    const double sigma = pow(ex / CP, CP / RD) / pow(exs / CP, CP / RD);
+    const double sigma_b = 0.7, k_f = 1.1574074074074073e-05;
+    if (sigma < sigma_b) return 0.0;
+    return a.ray_dt * (k_f * (sigma - sigma_b) / (1.0 - sigma_b));
+}
+
 // Contribution of neighbour element n to the P edges of one of its far sides:
 //   side 0: n's east column of x-normal edges  (quadrature points (P, qy))
 //   side 1: n's north row of y-normal edges    (quadrature points (qx, P))
@@ -62,11 +75,13 @@ __device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, boo
     const double* __restrict__ G = a.G + (size_t)n * D::Q2 * 3;
     double f[P + 1];
     double hs[P];   // h contracted along the side-normal direction at the far abscissa
+    double hss[P];  // Umat_ray: the same for the level-0 Exner field
+    const bool ray = WITH_H && a.ray_dt != 0.0;
     if (WITH_H) {
         const double* __restrict__ h = a.c + k;
         const int* __restrict__ n2 = a.el2 + (size_t)n * D::N2E;
 #pragma unroll
-        for (int i = 0; i < P; i++) hs[i] = 0.0;
+        for (int i = 0; i < P; i++) hs[i] = hss[i] = 0.0;
 #pragma unroll
         for (int iy = 0; iy < P; iy++)
 #pragma unroll
@@ -74,6 +89,11 @@ __device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, boo
                 const double hv = ldro(h + (size_t)n2[iy * P + ix] * ld);
                 if (side == 0) hs[iy] += a.E[P * P + ix] * hv;   // E[P][ix]
                 else hs[ix] += a.E[P * P + iy] * hv;             // E[P][iy]
+                if (ray) {
+                    const double hv0 = ldro(a.c2 + (size_t)n2[iy * P + ix]);
+                    if (side == 0) hss[iy] += a.E[P * P + ix] * hv0;
+                    else hss[ix] += a.E[P * P + iy] * hv0;
+                }
             }
     }
     if (side == 0) {
@@ -93,6 +113,12 @@ __device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, boo
                 double hl = 0.0;
 #pragma unroll
                 for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hs[iy];
+                if (ray) {
+                    double hls = 0.0;
+#pragma unroll
+                    for (int iy = 0; iy < P; iy++) hls += a.E[qy * P + iy] * hss[iy];
+                    hl = ray_weight(a, hl, hls, n * D::Q2 + q, nq[q], k);
+                }
                 c *= hl;
             }
             f[qy] = c * (G[q * 3 + 0] * ul0 + G[q * 3 + 1] * ul1);
@@ -114,6 +140,12 @@ __device__ __forceinline__ void m1_far_side(const KArgs& a, int n, int side, boo
                 double hl = 0.0;
 #pragma unroll
                 for (int ix = 0; ix < P; ix++) hl += a.E[qx * P + ix] * hs[ix];
+                if (ray) {
+                    double hls = 0.0;
+#pragma unroll
+                    for (int ix = 0; ix < P; ix++) hls += a.E[qx * P + ix] * hss[ix];
+                    hl = ray_weight(a, hl, hls, n * D::Q2 + q, nq[q], k);
+                }
                 c *= hl;
             }
             f[qx] = c * (G[q * 3 + 1] * ul0 + G[q * 3 + 2] * ul1);
@@ -160,20 +192,29 @@ __global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs 
 #pragma unroll
         for (int ix = 0; ix <= P; ix++) xx[iy][ix] = ldro(x + (size_t)ex[iy * D::NP1 + ix] * ld);
     double hx[P][P + 1];   // h contracted in x: hx[iy][qx]
+    double hxs[WITH_H ? P : 1][WITH_H ? P + 1 : 1];   // Umat_ray: the same for the level-0 Exner field
+    const bool ray = WITH_H && a.ray_dt != 0.0;
     if (WITH_H) {
         const double* __restrict__ h = a.c + k;
         const int* __restrict__ e2 = a.el2 + (size_t)e * D::N2E;
 #pragma unroll
         for (int iy = 0; iy < P; iy++) {
-            double hv[P];
+            double hv[P], hv0[P];
 #pragma unroll
-            for (int ix = 0; ix < P; ix++) hv[ix] = ldro(h + (size_t)e2[iy * P + ix] * ld);
+            for (int ix = 0; ix < P; ix++) {
+                hv[ix] = ldro(h + (size_t)e2[iy * P + ix] * ld);
+                hv0[ix] = ray ? ldro(a.c2 + (size_t)e2[iy * P + ix]) : 0.0;
+            }
 #pragma unroll
             for (int qx = 0; qx <= P; qx++) {
-                double s = 0.0;
+                double s = 0.0, s0 = 0.0;
 #pragma unroll
-                for (int ix = 0; ix < P; ix++) s += a.E[qx * P + ix] * hv[ix];
+                for (int ix = 0; ix < P; ix++) {
+                    s += a.E[qx * P + ix] * hv[ix];
+                    s0 += a.E[qx * P + ix] * hv0[ix];
+                }
                 hx[iy][qx] = s;
+                hxs[WITH_H ? iy : 0][WITH_H ? qx : 0] = s0;
             }
         }
     }
@@ -209,6 +250,12 @@ __global__ void __launch_bounds__(128) k_apply_m1(const __grid_constant__ KArgs 
                 double hl = 0.0;
 #pragma unroll
                 for (int iy = 0; iy < P; iy++) hl += a.E[qy * P + iy] * hx[iy][qx];
+                if (ray) {
+                    double hls = 0.0;
+#pragma unroll
+                    for (int iy = 0; iy < P; iy++) hls += a.E[qy * P + iy] * hxs[WITH_H ? iy : 0][WITH_H ? qx : 0];
+                    hl = ray_weight(a, hl, hls, e * D::Q2 + q, eq[q], k);
+                }
                 c *= hl;
             }
             const double g0 = G[q * 3 + 0], g1 = G[q * 3 + 1], g2 = G[q * 3 + 2];

@@ -147,6 +147,20 @@ class Engine:
                                                   self._stream()))
         return out
 
+    def apply_ray(self, x, exner, exner_s, dt, out=None, lev0=0, scale=1.0):
+        """Umat_ray::assemble(lev, scale, dt, exner_k, exner_s) + MatMult for all levels (eul/Assembly.cpp:1846-1979):
+        exner = the Exner-pressure 2-form in column layout (n2, nlev), exner_s = its level-0 column, one value per face (n2,)."""
+        nlev = x.shape[1]
+        self._chk(x, self.n1, nlev, "x")
+        self._chk(exner, self.n2, nlev, "exner")
+        if exner_s.dtype != self.torch.float64 or exner_s.numel() != self.n2 or not exner_s.is_contiguous():
+            raise MimsemError("exner_s: one float64 per face")
+        if out is None:
+            out = self.zeros(self.n1, nlev)
+        check(self.L.mimsem_gpu_apply_M1ray(self._h, lev0, nlev, nlev, scale, dt, exner.data_ptr(), exner_s.data_ptr(), x.data_ptr(),
+                                            out.data_ptr(), self._stream()))
+        return out
+
     def permutation(self, space):
         """row of each caller-numbered DOF in the engine's column layout."""
         n = (self.n0, self.n1, self.n2)[space]

@@ -333,6 +333,24 @@ void Uhmat::assemble(Vec h2) {   // src/Assembly.cpp:675-734
     sh->tpow = 0;
 }
 
+Umat_ray::Umat_ray(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    attach(topo, geom);
+    sh = make_shell(topo, 21 /* Umat_ray */, 1, 1, &M);
+}
+Umat_ray::~Umat_ray() { free_shell(sh, &M); }
+void Umat_ray::assemble(int lev, double scale, double dt, Vec exner, Vec exner_s) {   // eul/Assembly.cpp:1875-1979
+    copy_coeff(sh, exner, topo->n2);
+    // the level-0 Exner field rides in the shell's second coefficient slot, dt in its time-scale slot
+    PetscScalar* a;
+    VecGetArray(exner_s, &a);
+    sh->u1.assign(a, a + topo->n2);
+    VecRestoreArray(exner_s, &a);
+    sh->tau = dt;
+    sh->lev = lev;
+    sh->scale = scale;
+    sh->tpow = 1;
+}
+
 Whmat::Whmat(Topo* _topo, Geom* _geom, LagrangeEdge* _e) : topo(_topo), geom(_geom), e(_e) {
     attach(topo, geom);
     sh = make_shell(topo, OP_M2H, 2, 2, &M);

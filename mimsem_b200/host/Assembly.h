@@ -88,6 +88,18 @@ class Uhmat {
         MimsemShell* sh;
 };
 
+// 1-form mass matrix with the Rayleigh-friction point weight          eul/Assembly.h:325-335, eul/Assembly.cpp:1846-1979
+class Umat_ray {
+    public:
+        Umat_ray(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~Umat_ray();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble(int lev, double scale, double dt, Vec exner, Vec exner_s);
+    private:
+        MimsemShell* sh;
+};
+
 // 2-form mass matrix weighted by a 2-form                              eul/Assembly.h:186-199
 class Whmat {
     public:

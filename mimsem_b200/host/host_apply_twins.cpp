@@ -4,8 +4,9 @@
 // Krylov solve is a collective and cannot be played rank after rank), KSPSolve(ksp1, ...) on Umat::M as :77-84, 224 do.
 //
 //   host_apply_twins <p> <ne> <nk> <in.bin> <out.bin>
-// in.bin : doubles  thick[nk][N0] x1[nk][N1] x1b[nk][N1] x2[nk][N2] h2[nk][N2] h2b[nk][N2] u1[nk][N1]   (global numbering)
-// out.bin: doubles  per level: Uvec::assemble, Uvec::assemble_hu (4 terms), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv (rho = h2b);
+// in.bin : doubles  thick[nk][N0] x1[nk][N1] x1b[nk][N1] x2[nk][N2] h2[nk][N2] h2b[nk][N2] u1[nk][N1] ex2[nk][N2]  (global numbering)
+// out.bin: doubles  per level: Uvec::assemble, Uvec::assemble_hu (4 terms), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv (rho = h2b),
+//                   Umat_ray (exner = ex2[lev], exner_s = ex2[0], dt = 300, as eul/Euler_2.cpp:1218-1229 calls it);
 //                   then { its, |x - x_true| / |x_true| } of the box solve
 #include <cmath>
 #include <cstdio>
@@ -32,7 +33,7 @@ int main(int argc, char** argv) {
     std::vector<double> in = read_all(argv[4]);
     const int np = 6;
     struct Rank { Topo* topo; Geom* geom; GaussLobatto* quad; LagrangeNode* node; LagrangeEdge* edge;
-                  Uvec* m1; UtQWmat* Rh; Pvec* m0; Phvec* m0h; WmatInv* Wi; WhmatInv* Whi; };
+                  Uvec* m1; UtQWmat* Rh; Pvec* m0; Phvec* m0h; WmatInv* Wi; WhmatInv* Whi; Umat_ray* ray; };
     std::vector<Rank> R(np);
     for (int r = 0; r < np; r++) {
         PetscCompatSetRank(r, np);
@@ -44,7 +45,7 @@ int main(int argc, char** argv) {
         k.edge = new LagrangeEdge(k.topo->elOrd, k.node);
     }
     const long N0 = R[0].topo->nDofs0G, N1 = R[0].topo->nDofs1G, N2 = R[0].topo->nDofs2G;
-    if ((long)in.size() != (long)nk * (N0 + 3 * N1 + 3 * N2)) { std::fprintf(stderr, "bad input size\n"); return 2; }
+    if ((long)in.size() != (long)nk * (N0 + 3 * N1 + 4 * N2)) { std::fprintf(stderr, "bad input size\n"); return 2; }
     const double* thick = in.data();
     const double* x1 = thick + (long)nk * N0;
     const double* x1b = x1 + (long)nk * N1;
@@ -52,6 +53,7 @@ int main(int argc, char** argv) {
     const double* h2 = x2 + (long)nk * N2;
     const double* h2b = h2 + (long)nk * N2;
     const double* u1 = h2b + (long)nk * N2;
+    const double* ex2 = u1 + (long)nk * N1;
     for (int r = 0; r < np; r++) {
         PetscCompatSetRank(r, np);
         Rank& k = R[r];
@@ -67,10 +69,11 @@ int main(int argc, char** argv) {
         k.m0h = new Phvec(k.topo, k.geom, k.node);
         k.Wi = new WmatInv(k.topo, k.geom, k.edge);
         k.Whi = new WhmatInv(k.topo, k.geom, k.edge);
+        k.ray = new Umat_ray(k.topo, k.geom, k.node, k.edge);
     }
     FILE* out = std::fopen(argv[5], "wb");
     if (!out) { std::perror(argv[5]); return 2; }
-    std::vector<Vec> g1(np), g1b(np), g2(np), gh(np), ghb(np), gu(np), l1(np), l1b(np), lu(np), w1(np), w2(np);
+    std::vector<Vec> g1(np), g1b(np), g2(np), gh(np), ghb(np), gu(np), l1(np), l1b(np), lu(np), w1(np), w2(np), gex(np), gex0(np);
     for (int r = 0; r < np; r++) {
         PetscCompatSetRank(r, np);
         Topo* t = R[r].topo;
@@ -79,6 +82,8 @@ int main(int argc, char** argv) {
         VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &g2[r]);
         VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &gh[r]);
         VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &ghb[r]);
+        VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &gex[r]);
+        VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &gex0[r]);
         VecCreateMPI(MPI_COMM_WORLD, t->n1l, t->nDofs1G, &gu[r]);
         VecCreateMPI(MPI_COMM_WORLD, t->n1l, t->nDofs1G, &w1[r]);
         VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &w2[r]);
@@ -124,6 +129,8 @@ int main(int argc, char** argv) {
         fill(gh, h2 + (long)lev * N2);
         fill(ghb, h2b + (long)lev * N2);
         fill(gu, u1 + (long)lev * N1);
+        fill(gex, ex2 + (long)lev * N2);
+        fill(gex0, ex2);
         ghost(g1, l1);
         ghost(g1b, l1b);
         ghost(gu, lu);
@@ -141,6 +148,8 @@ int main(int argc, char** argv) {
         ALL_RANKS(k.m0h->assemble(gh[r], lev, SCALE))                                                       dump(4);
         ALL_RANKS(k.Wi->assemble(lev, SCALE); MatMult(k.Wi->M, g2[r], w2[r]))                               dump(2);
         ALL_RANKS(k.Whi->assemble(ghb[r], lev, SCALE); MatMult(k.Whi->M, g2[r], w2[r]))                     dump(2);
+        ALL_RANKS(k.ray->assemble(lev, SCALE, 300.0, gex[r], gex0[r]))
+        ALL_RANKS(MatMult(k.ray->M, g1[r], w1[r]))                                                          dump(1);
     }
     // ---- KSPSolve on the box: x -> b = M1 x -> KSPSolve(M1, b) recovers x (GMRES + block Jacobi requested, as the reference does)
     {

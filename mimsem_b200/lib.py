@@ -76,6 +76,7 @@ SIGNATURES = {
     "mimsem_gpu_solve_M1_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _vp, C.c_double, C.c_int,
                                            _ip, _dp, _vp, _vp, _vp]),
     "mimsem_gpu_launch_count": (C.c_int64, [_vp]),
+    "mimsem_gpu_apply_M1ray": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "mimsem_gpu_dev_free": (C.c_int, [_vp, _vp]),
     "mimsem_gpu_dev_copy": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int]),

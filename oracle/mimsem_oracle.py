@@ -354,6 +354,29 @@ class Oracle:
             self._add(e1y, e1y, np.einsum("qi,eq,qj->eij", V, Qbb, V), trip)
         return self._csr(trip, (self.N1, self.N1))
 
+    def umat_ray(self, lev, scale, dt, exner_k, exner_s):
+        """Umat_ray::assemble(lev, scale, dt, exner_k, exner_s) (eul/Assembly.cpp:1846-1979): the 1-form mass matrix with
+        the point weight dt k_v(exner, exner_s) thickInv[lev]; exner = interp2_g(exner_k) thickInv[lev], exner_s =
+        interp2_g(exner_s) thickInv[0]; k_v = compute_k_v (:1846-1856) with CP = 1004.5, RD = 287 (:15-16)."""
+        CP, RD, sigma_b, k_f = 1004.5, 287.0, 0.7, 1.1574074074074073e-05
+        U, V, Q = self.em["U"], self.em["V"], self.em["Q"]
+        trip = []
+        for r in range(self.nprocs):
+            gaa, gab, gbb = self._metric(r)
+            ti = self._tinv(r, lev)
+            e = self._interp2_g(r, exner_k) * ti
+            es = self._interp2_g(r, exner_s) * self._tinv(r, 0)
+            sigma = (e / CP) ** (CP / RD) / (es / CP) ** (CP / RD)
+            k_v = np.where(sigma < sigma_b, 0.0, k_f * (sigma - sigma_b) / (1.0 - sigma_b)) * dt
+            c = Q[None, :] * (scale / self.det[r]) * k_v * ti
+            Qaa, Qab, Qbb = gaa * c, gab * c, gbb * c
+            _, e1x, e1y, _ = self.inds[r]
+            self._add(e1x, e1x, np.einsum("qi,eq,qj->eij", U, Qaa, U), trip)
+            self._add(e1x, e1y, np.einsum("qi,eq,qj->eij", U, Qab, V), trip)
+            self._add(e1y, e1x, np.einsum("qi,eq,qj->eij", V, Qab, U), trip)
+            self._add(e1y, e1y, np.einsum("qi,eq,qj->eij", V, Qbb, V), trip)
+        return self._csr(trip, (self.N1, self.N1))
+
     def wmat(self, lev=0, scale=1.0, tpow=0, rho=None, tpow_rho=0):
         """Wmat::_assemble (eul/Assembly.cpp:341-360); with rho: Whmat::assemble (:1262-1287)."""
         W, Q = self.em["W"], self.em["Q"]

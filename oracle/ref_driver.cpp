@@ -260,7 +260,9 @@ enum {
     OP_E10 = 5, OP_E01 = 6, OP_E21 = 7, OP_E12 = 8, OP_PMAT_H = 9, OP_WHMAT = 10, OP_ROTMAT = 11,
     OP_PHMAT_UP = 12, OP_ROTMAT_UP = 13,
     /* eul/: operators of the horizontal-vorticity / vertical-momentum terms */
-    OP_UT_MAT = 14, OP_UT_MAT_H = 15, OP_UTQWMAT = 16, OP_WTQDUDZ = 17
+    OP_UT_MAT = 14, OP_UT_MAT_H = 15, OP_UTQWMAT = 16, OP_WTQDUDZ = 17,
+    /* eul/: Rayleigh friction; c2 = Exner 2-form of the level, c1 = the LEVEL-0 Exner 2-form (a second global 2-form) */
+    OP_UMAT_RAY = 18
 };
 
 /*
@@ -290,7 +292,11 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
             /* faces: global = local + pi*n2 (reference Topo::elInds2_g) */
             for (int i = 0; i < topo->n2l; i++) v2->a[i] = c2[(long)rk * topo->n2 + i];
         }
-        if (c1) {
+        Vec v2b = NULL;
+        if (c1 && op == OP_UMAT_RAY) {
+            VecCreateMPI(MPI_COMM_WORLD, topo->n2l, topo->nDofs2G, &v2b);
+            for (int i = 0; i < topo->n2l; i++) v2b->a[i] = c1[(long)rk * topo->n2 + i];
+        } else if (c1) {
             VecCreateSeq(MPI_COMM_SELF, topo->n1, &v1);
             for (int i = 0; i < topo->n1; i++) v1->a[i] = c1[topo->loc1[i]];
         }
@@ -359,6 +365,11 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
             case OP_WTQDUDZ: {
                 WtQdUdz_mat* A = new WtQdUdz_mat(topo, geom, o.node, o.edge);
                 A->assemble(v1, scale);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_UMAT_RAY: {
+                Umat_ray* A = new Umat_ray(topo, geom, o.node, o.edge);
+                A->assemble(lev, scale, dt, v2, v2b);
                 keep[rk] = A->M->t; delete A; break;
             }
 #elif defined(REF_SRC)
@@ -444,13 +455,14 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
         (void)M;
         if (v2) VecDestroy(&v2);
         if (v1) VecDestroy(&v1);
+        if (v2b) VecDestroy(&v2b);
         if (v0) VecDestroy(&v0);
     });
     if (bad) return -1;
     double t1 = now();
     Topo* t = h->r[0].topo;
     switch (op) {
-        case OP_UMAT: case OP_UHMAT: case OP_ROTMAT: case OP_ROTMAT_UP: case OP_UT_MAT: case OP_UT_MAT_H: nrows = ncols = t->nDofs1G; break;
+        case OP_UMAT: case OP_UHMAT: case OP_ROTMAT: case OP_ROTMAT_UP: case OP_UT_MAT: case OP_UT_MAT_H: case OP_UMAT_RAY: nrows = ncols = t->nDofs1G; break;
         case OP_WTQDUDZ: nrows = t->nDofs2G; ncols = t->nDofs1G; break;
         case OP_UTQWMAT: nrows = t->nDofs1G; ncols = t->nDofs2G; break;
         case OP_WMAT: case OP_WHMAT: nrows = ncols = t->nDofs2G; break;

@@ -125,6 +125,14 @@ def ops_fixture(variant, kind, p, ne, nprocs, nk, fname, seed):
         out["y_Uvec_hu"] = np.array([R.uvec_assemble_hu([x1[lev], x1[lev], x1b[lev], x1b[lev]], [h2[lev], h2b[lev], h2[lev], h2b[lev]],
                                                         [1.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 1.0 / 3.0], lev=lev, scale=scale) for lev in range(nk)])
         out["y_Uvec"] = np.array([R.uvec_apply(x1[lev], lev=lev, scale=scale)[0] for lev in range(nk)])
+        # Rayleigh friction (Umat_ray, eul/Assembly.cpp:1846-1979): Exner-pressure 2-forms whose ratio to level 0, times the
+        # thickness ratio, puts sigma = (p / p_s) on both sides of the 0.7 threshold of compute_k_v (drawn last, see above)
+        ex2 = 1.0e3 * (1.0 + 0.03 * rng.uniform(-1, 1, (nk, N2)))
+        ex2 *= (np.linspace(1.0, 0.9, nk) * thick.mean(axis=1) / thick[0].mean())[:, None]
+        ray_dt = 300.0
+        out.update(ex2=ex2, ray_dt=ray_dt)
+        out["y_Umat_ray"] = np.array([R.assemble("Umat_ray", lev=lev, scale=scale, c2=ex2[lev], c1=ex2[0], dt=ray_dt) @ x1[lev]
+                                      for lev in range(nk)])
     elif variant == "src":
         out["y_Umat"] = run("Umat", x1)
         out["y_Wmat"] = run("Wmat", x2)

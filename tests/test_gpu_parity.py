@@ -581,6 +581,23 @@ def test_element_block_jacobi_vs_reference_matrix(kind, p, ne, variant, tmp_path
     assert np.array_equal(np.sort(own, axis=1), np.arange(mesh.nel * nb).reshape(mesh.nel, nb))
 
 
+@pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
+def test_rayleigh_friction_vs_reference_golden(fname, p, ne):
+    """Umat_ray::assemble(lev, scale, dt, exner_k, exner_s) + MatMult (eul/Assembly.cpp:1846-1979; eul/Euler_2.cpp:1218-1229):
+    all levels in one launch against vectors of the reference's own class; level by level gives the same."""
+    import torch
+    g = golden(fname)
+    mesh, eng = _engine("sphere", p, ne, thick=g["thick"])
+    s, dt = float(g["scale"]), float(g["ray_dt"])
+    exs = torch.from_numpy(np.ascontiguousarray(g["ex2"][0])).cuda()
+    y = to_np(eng, eng.apply_ray(to_cols(eng, g["x1"], 1), to_cols(eng, g["ex2"], 2), exs, dt, scale=s), 1)
+    assert rel_l2(y, g["y_Umat_ray"]) < TOL, rel_l2(y, g["y_Umat_ray"])
+    for lev in range(int(g["nk"])):
+        yl = to_np(eng, eng.apply_ray(to_cols(eng, g["x1"][lev:lev + 1], 1), to_cols(eng, g["ex2"][lev:lev + 1], 2), exs, dt, lev0=lev,
+                                      scale=s), 1)
+        assert rel_l2(yl[0], g["y_Umat_ray"][lev]) < TOL
+
+
 @pytest.mark.parametrize("kind,p,ne,nk", [("sphere", 3, 4, 30), ("sphere", 4, 3, 60), ("box", 3, 5, 7)])
 def test_l2vecs_relabelling_bit_exact(kind, p, ne, nk):
     """L2Vecs::HorizToVert / VertToHoriz (eul/L2Vecs.cpp:55-101): vz[e][k*p^2 + i] = vh[k][elInds2_l(e)[i]], bit for bit."""

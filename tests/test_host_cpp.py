@@ -187,7 +187,7 @@ def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, varian
 @pytest.mark.gpu
 @pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
 def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
-    """Uvec (assemble, assemble_hu exactly as diagnose_fluxes calls it), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv through the
+    """Uvec (assemble, assemble_hu exactly as diagnose_fluxes calls it), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv, Umat_ray through the
     C++ mirror on six emulated ranks against the reference's golden vectors / the oracle's matrices, and KSPSolve on the
     Umat shell of the periodic box (GMRES + block Jacobi requested as eul/HorizSolve.cpp:77-84 does)."""
     import scipy.sparse.linalg as spla
@@ -196,7 +196,7 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
     g = golden(fname)
     nk = int(g["nk"])
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
-    np.concatenate([g[k].ravel() for k in ("thick", "x1", "x1b", "x2", "h2", "h2b", "u1")]).astype("<f8").tofile(fin)
+    np.concatenate([g[k].ravel() for k in ("thick", "x1", "x1b", "x2", "h2", "h2b", "u1", "ex2")]).astype("<f8").tofile(fin)
     r = subprocess.run([BIN + "_twins", str(p), str(ne), str(nk), fin, fout], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "host_apply_twins ok" in r.stdout, r.stdout + r.stderr
     out = np.fromfile(fout, dtype="<f8")
@@ -222,6 +222,7 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
             assert rel_l2(phv, O.pmat(lev, s, h2=g["h2"][lev]).diagonal()) < TOL, ("Phvec", lev)
             assert rel_l2(wi, spla.spsolve(O.wmat(lev, s, 1).tocsc(), g["x2"][lev])) < TOL, ("WmatInv", lev)
             assert rel_l2(whi, spla.spsolve(O.wmat(lev, s, 1, rho=g["h2b"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < 1e-8, ("WhmatInv", lev)
+        assert rel_l2(take(N1), g["y_Umat_ray"][lev]) < TOL, ("Umat_ray", lev)
     its, err = take(2)
     assert o == out.size
     assert 0 < its < 200 and err < 1e-11, (its, err)

@@ -59,6 +59,21 @@ def test_oracle_eul_vs_golden():
 
 
 @needs_mesh
+@pytest.mark.parametrize("fname,p,ne", [("ops_eul_sphere_p3_ne4.npz", 3, 4), ("ops_eul_sphere_p4_ne2.npz", 4, 2)])
+def test_oracle_rayleigh_friction_vs_golden(fname, p, ne):
+    """Umat_ray (eul/Assembly.cpp:1846-1979): the numpy restatement against vectors of the reference's own class."""
+    g = golden(fname)
+    O = mo.Oracle(ref_mesh_dir("sphere", p, ne, 6), 6, "sphere", "eul")
+    O.set_thick(g["thick"])
+    s, dt = float(g["scale"]), float(g["ray_dt"])
+    for lev in range(int(g["nk"])):
+        y = O.umat_ray(lev, s, dt, g["ex2"][lev], g["ex2"][0]) @ g["x1"][lev]
+        assert rel_l2(y, g["y_Umat_ray"][lev]) < TOL, (lev, rel_l2(y, g["y_Umat_ray"][lev]))
+    # both branches of compute_k_v are exercised: some points sit below the sigma = 0.7 threshold, most above
+    assert 0 < (g["y_Umat_ray"] == 0).mean() < 0.5
+
+
+@needs_mesh
 def test_oracle_src_vs_golden():
     g = golden("ops_src_sphere_p3_ne4.npz")
     O = mo.Oracle(ref_mesh_dir("sphere", 3, 4, 6), 6, "sphere", "src")
