@@ -358,10 +358,7 @@ def main():
     burst = not args.no_graph and not args.no_pdl and (world == 1 or (args.op == "M1" and not args.chain))
     auto_opts = []
     if burst:
-        auto_opts.append("pdl_independent=1")
-        # (the ring kernel wants many tiles per SM: on C3 / C4, 400-864 elements, the tile kernel is the faster one)
-        if world == 1 and args.op == "M1" and not args.chain and mesh.nel >= 4000 and not any(o.startswith("m1_variant=") for o in args.opt):
-            auto_opts.append("m1_variant=3")
+        auto_opts.append("pdl_independent=1")   # (plain M1 on >= 4000 elements then runs as the persistent ring kernel: the engine's default rule)
     for kv in auto_opts + args.opt:
         name, val = kv.split("=")
         (eng if world == 1 else eng.engine).set_option(name, int(val))

@@ -89,8 +89,8 @@ int mimsem_gpu_create(int device, mimsem_gpu_ctx** out);
 int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx);
 /* Tuning / test knobs of a context (never read from the environment on a launch path; mimsem_gpu_create consults
  * MIMSEM_M1_VARIANT, MIMSEM_K_VARIANT, MIMSEM_ELL_VEC, MIMSEM_PREFETCH, MIMSEM_M1_MINB, MIMSEM_HOST_CHUNK once):
- *   "m1_variant" 2 tile kernel (default) | 3 persistent warp-specialised ring kernel | 1 line tasks | 0 thread per
- *   element-level;  "k_variant" 1 tile | 0 registers;  "m2_variant", "inc_variant" 1 tile / element kernels | 0;
+ *   "m1_variant" 4 automatic (default: the ring kernel for plain M1 on >= 4000 elements under "pdl_independent", else the
+ *   tile kernel) | 3 persistent warp-specialised ring kernel | 2 tile kernel | 1 line tasks | 0 thread per element-level;  "k_variant" 1 tile | 0 registers;  "m2_variant", "inc_variant" 1 tile / element kernels | 0;
  *   "pdl_independent" 1: the caller guarantees that consecutive launches on a stream do not depend on each other (several
  *   fields per time step): the M1 tile kernels are launched with programmatic stream serialization, so a launch starts
  *   as the CTAs of the previous one retire instead of after its last CTA (default 0: ordinary stream order);

@@ -84,7 +84,9 @@ struct mimsem_gpu_ctx {
     int n_int = 0, n_bnd = 0;
     std::vector<int> h_el1x_ext, h_el1y_ext;   // caller numbering (before perm1), kept for set_ghosts
     // tuning / test knobs: read from the environment ONCE at mimsem_gpu_create, or set with mimsem_gpu_set_option
-    int m1_variant = 2;                      // 2: TMA tile kernel (default), 1: line tasks, 0: one thread per element-level
+    int m1_variant = 4;                      // 4: automatic (default: the persistent ring kernel for plain M1 on >= 4000 elements when
+                                             //    launches may overlap (pdl_independent), else the TMA tile kernel), 3: ring kernel,
+                                             //    2: tile kernel, 1: line tasks, 0: one thread per element-level
     int k_variant = 1;                       // 1: TMA tile kernel (default), 0: one thread per element-level
     int ell_vec = 4;                         // widest level group of the incidence kernels (4, 2, 1)
     int prefetch_ahead = 444;                // L2 prefetch distance of the tile kernels in tiles (0: off)
@@ -932,7 +934,10 @@ int apply_m1(mimsem_gpu_ctx* c, bool with_h, int lev0, int nlev, int ld, double 
         t.dbg_times = c->diag_times;
 #endif
         std::string err;
-        const int rc3 = (c->m1_variant == 3 && !hf) ? launch_m1_pipe(l, t, st, &err) : launch_m1_tile(l, t, st, &err);
+        // the ring kernel wants many tiles per SM and neighbouring launches to hide its ramp and tail behind
+        const bool ring = !hf && (c->m1_variant == 3 || (c->m1_variant == 4 && !with_h && c->pdl && a.nel >= 4000 && !a.elist));
+        int rc3 = ring ? launch_m1_pipe(l, t, st, &err) : 1;
+        if (rc3 == 1) rc3 = launch_m1_tile(l, t, st, &err);
         if (rc3 < 0) return fail(MIMSEM_ERR_CUDA, err);
         if (rc3 == 0) {
             if (l.push_only && l.push_ctas == 0) return MIMSEM_OK;
@@ -1521,7 +1526,7 @@ int mimsem_gpu_set_option(mimsem_gpu_ctx* c, const char* name, long long value) 
     if (!c || !name) return fail(MIMSEM_ERR_ARG, "null argument");
     const std::string n(name);
     const int v = (int)value;
-    if (n == "m1_variant" && v >= 0 && v <= 3) c->m1_variant = v;
+    if (n == "m1_variant" && v >= 0 && v <= 4) c->m1_variant = v;
     else if (n == "k_variant" && v >= 0 && v <= 1) c->k_variant = v;
     else if (n == "m2_variant" && v >= 0 && v <= 1) c->m2_variant = v;
     else if (n == "inc_variant" && v >= 0 && v <= 1) c->inc_variant = v;

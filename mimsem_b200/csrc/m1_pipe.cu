@@ -1,7 +1,5 @@
 // Instantiations and launcher of the persistent, warp-specialised M1 / M1(h) tile kernel.
 #include <algorithm>
-#include <cstdio>
-#include <cstdlib>
 
 #include "launch.hpp"
 #include "m1_pipe.cuh"
@@ -45,7 +43,6 @@ int launch_m1_pipe(const M1TileLaunch& l, TArgs& t, cudaStream_t st, std::string
         if (l.nel == 0) return;
         t.ntiles = l.nel;
         const int grid = std::min(l.nel, sms);
-        if (getenv("MIMSEM_PIPE_VERBOSE")) fprintf(stderr, "m1_pipe: smem %zu ring %d sms %d grid %d ntiles %d\n", smem, nb, sms, grid, l.nel);
         ce = launch_maybe_pdl(kern, dim3(grid), dim3(M1Pipe<P, false>::threads(nb)), smem, st, t.pdl != 0, t, nb);
         if (ce != cudaSuccess) {
             *err = std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(ce);
