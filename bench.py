@@ -302,6 +302,59 @@ def parity_vs_one_gpu(eng, mesh, thick, op, x, coeff, y, kw, rank, world, local)
     return bool(flag.item())
 
 
+def run_dependent_chain(args, eng, mesh, nk, scale, world, rank, dev, variant, p, ne):
+    """Every kernel of a step depends on the one before it (and the solve on its own dot products): no overlap between
+    launches is possible, each pays its ramp, its ghost refresh and its tail.  Stream order, no CUDA graph (the solve reads
+    its convergence flags back every four iterations)."""
+    import torch
+    n1, n2 = eng.space_sizes("M1h")[0], eng.space_sizes("M1h")[2]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    u = torch.rand((n1, nk), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    rho = torch.rand((n2, nk), dtype=torch.float64, device=dev, generator=g) + 0.5
+    F = torch.empty_like(u)
+    d = torch.empty((eng.space_sizes("E21")[1], nk), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+    its = [0]
+
+    def step():
+        eng.apply("M1h", u, coeff=rho, out=F, scale=scale, tpow=2)
+        us, it, _ = eng.solve("M1", F, scale=scale, tpow=1, rtol=1e-10, maxit=200)
+        its[0] = it
+        eng.apply("E21", us, out=d)
+    for _ in range(max(2, min(args.warmup, 3))):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nstep = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(nstep):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / nstep
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        if eng.halo_error():
+            raise SystemExit("rank %d: a ghost refresh timed out" % rank)
+    if rank == 0:
+        dofs = mesh.N1 * nk
+        print(json.dumps({"metric": "dependent chain M1h -> solve_M1 -> E21 (GDOF/s of the 1-form field per chain)", "value": dofs / (ms * 1e-3) / 1e9,
+                          "unit": "GDOF/s", "n_gpus": world, "steps": nstep, "ms_per_step": ms, "cg_iterations": its[0],
+                          "config": {"workload": "%s: %s p=%d, %dx%d elems/face, %d levels" % (args.workload, variant, p, ne, ne, nk),
+                                     "launch": "stream order, no CUDA graph; solve: batched Jacobi-PCG, rtol 1e-10, dot products over peer memory"}}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -311,6 +364,9 @@ def main():
     ap.add_argument("--op", default="M1", choices=OPS)
     ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
     ap.add_argument("--chain", action="store_true", help="time the diagnose chain (4 x M1h + E21) under one CUDA graph instead of --op")
+    ap.add_argument("--dependent-chain", action="store_true",
+                    help="time the DEPENDENT chain F = M1h(rho) u -> u' = M1^-1 F (PCG, rtol 1e-10) -> div = E21 u' (the mass flux of "
+                         "diagnose_fluxes, eul/HorizSolve.cpp:298-310) instead of --op; prints its own JSON line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -355,13 +411,16 @@ def main():
         eng = mb.Engine.from_mesh(mesh, local, thick=thick)
     # 1 GPU: consecutive steps are independent applies (ring of distinct fields), so a launch may start while the CTAs of
     # the previous one retire (programmatic dependent launch); plain M1 then runs best as the persistent ring kernel
-    burst = not args.no_graph and not args.no_pdl and (world == 1 or (args.op == "M1" and not args.chain))
+    burst = not args.no_graph and not args.no_pdl and not args.dependent_chain and (world == 1 or (args.op == "M1" and not args.chain))
     auto_opts = []
     if burst:
         auto_opts.append("pdl_independent=1")   # (plain M1 on >= 4000 elements then runs as the persistent ring kernel: the engine's default rule)
     for kv in auto_opts + args.opt:
         name, val = kv.split("=")
         (eng if world == 1 else eng.engine).set_option(name, int(val))
+    if args.dependent_chain:
+        run_dependent_chain(args, eng, mesh, nk, scale, world, rank, dev, variant, p, ne)
+        return
     op = "M1h" if args.chain else args.op
     if world > 1 and (args.chain or op not in eng.SUPPORTED):
         raise SystemExit("operator %s is not available on more than one GPU" % ("chain" if args.chain else op))

@@ -1302,7 +1302,7 @@ int solve_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tp
     g.tol2 = rtol * rtol;
     if ((rc = diag_m1(c, true, lev0, nlev, ld, scale, tpow, flags, c->cg_dinv.p, st))) return rc;
     k_cg_step<0><<<g.nblocks, 256, 0, st>>>(g);
-    k_cg_finish<0><<<1, 64, 0, st>>>(g);
+    k_cg_finish<0><<<1, 64 * CG_FIN_G, 0, st>>>(g);
     c->launches += 2;
     std::vector<double> h(8 * 64);
     int it = 0;
@@ -1318,9 +1318,9 @@ int solve_m1(mimsem_gpu_ctx* c, int lev0, int nlev, int ld, double scale, int tp
                 return rc;
             }
             k_cg_step<1><<<g.nblocks, 256, 0, st>>>(g);
-            k_cg_finish<1><<<1, 64, 0, st>>>(g);
+            k_cg_finish<1><<<1, 64 * CG_FIN_G, 0, st>>>(g);
             k_cg_step<2><<<g.nblocks, 256, 0, st>>>(g);
-            k_cg_finish<2><<<1, 64, 0, st>>>(g);
+            k_cg_finish<2><<<1, 64 * CG_FIN_G, 0, st>>>(g);
             k_cg_step<3><<<g.nblocks, 256, 0, st>>>(g);
             c->launches += 5;
         }

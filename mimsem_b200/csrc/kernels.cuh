@@ -745,6 +745,7 @@ __global__ void __launch_bounds__(128) k_diag_m1(const __grid_constant__ KArgs a
 // Batched CG building blocks.  Fields are [rows][ld] with lanes along the levels; every reduction is per level and
 // deterministic: a block sums 256 rows into partial[block][k], k_cg_finish adds the partials in block order.
 constexpr int CG_ROWS = 256;
+constexpr int CG_FIN_G = 16;   // lane groups of k_cg_finish (threads = 64 * CG_FIN_G)
 struct CgArgs {
     int64_t nrows;
     int nlev, ld, nblocks;
@@ -807,21 +808,43 @@ __global__ void __launch_bounds__(256) k_cg_step(const __grid_constant__ CgArgs 
         double alpha = 0.0, beta = 0.0;
         if (MODE == 2) alpha = a.scal[5 * 64 + k];
         if (MODE == 3) beta = a.scal[6 * 64 + k];
-        for (int64_t row = r0 + g; row < r1; row += 4) {
-            const size_t i = (size_t)row * a.ld + k;
-            if (MODE == 0) {
-                const double bv = a.b[i], z = a.dinv[i] * bv;
-                a.x[i] = 0.0; a.r[i] = bv; a.p[i] = z;
-                s0 += bv * z; s1 += bv * bv; s2 += bv * bv;
-            } else if (MODE == 1) {
-                s0 += a.p[i] * a.q[i];
-            } else if (MODE == 2) {
-                a.x[i] += alpha * a.p[i];
-                const double rv = a.r[i] - alpha * a.q[i];
-                a.r[i] = rv;
-                s0 += rv * (a.dinv[i] * rv); s1 += rv * rv;
-            } else {
-                a.p[i] = a.dinv[i] * a.r[i] + beta * a.p[i];
+        // U rows per pass, every load issued before the first store: the field pointers may alias as far as the compiler
+        // knows, so a row-by-row loop kept ONE row of each field in flight per thread (45 % of the HBM rate)
+        constexpr int U = 8;
+        for (int64_t rb = r0 + g; rb < r1; rb += 4 * U) {
+            size_t i[U];
+            bool ok[U];
+            double v0[U], v1[U], v2[U], v3[U], v4[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t row = rb + 4 * u;
+                ok[u] = row < r1;
+                i[u] = (size_t)(ok[u] ? row : rb) * a.ld + k;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (MODE == 0) { v0[u] = a.b[i[u]]; v1[u] = a.dinv[i[u]]; }
+                else if (MODE == 1) { v0[u] = a.p[i[u]]; v1[u] = a.q[i[u]]; }
+                else if (MODE == 2) { v0[u] = a.x[i[u]]; v1[u] = a.p[i[u]]; v2[u] = a.r[i[u]]; v3[u] = a.q[i[u]]; v4[u] = a.dinv[i[u]]; }
+                else { v0[u] = a.dinv[i[u]]; v1[u] = a.r[i[u]]; v2[u] = a.p[i[u]]; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (!ok[u]) continue;
+                if (MODE == 0) {
+                    const double bv = v0[u], z = v1[u] * bv;
+                    a.x[i[u]] = 0.0; a.r[i[u]] = bv; a.p[i[u]] = z;
+                    s0 += bv * z; s1 += bv * bv; s2 += bv * bv;
+                } else if (MODE == 1) {
+                    s0 += v0[u] * v1[u];
+                } else if (MODE == 2) {
+                    a.x[i[u]] = v0[u] + alpha * v1[u];
+                    const double rv = v2[u] - alpha * v3[u];
+                    a.r[i[u]] = rv;
+                    s0 += rv * (v4[u] * rv); s1 += rv * rv;
+                } else {
+                    a.p[i[u]] = v0[u] * v1[u] + beta * v2[u];
+                }
             }
         }
     }
@@ -831,12 +854,32 @@ __global__ void __launch_bounds__(256) k_cg_step(const __grid_constant__ CgArgs 
 // one thread per level: add the block partials in order and update the per-level scalars
 template <int MODE>
 __global__ void k_cg_finish(const __grid_constant__ CgArgs a) {
-    const int k = threadIdx.x;
+    // CG_FIN_G groups of 64 level lanes: group g adds the block partials g, g + G, ... in order, then lane group 0 adds the G group
+    // sums in order (fixed order: deterministic).  One group alone walked 1 700 partials per sum, 0.2 ms per call on C5.
+    const int k = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const bool active = k < a.nlev;
+    constexpr int NS = MODE == 0 ? 3 : (MODE == 1 ? 1 : 2);
+    __shared__ double part[3][CG_FIN_G][64];
+    {
+        double t[3] = {0.0, 0.0, 0.0};
+        if (active)
+            for (int bI = grp; bI < a.nblocks; bI += CG_FIN_G)
+#pragma unroll
+                for (int j = 0; j < NS; j++) t[j] += a.partial[((size_t)j * a.nblocks + bI) * 64 + k];
+#pragma unroll
+        for (int j = 0; j < NS; j++) part[j][grp][k] = t[j];
+    }
+    __syncthreads();
     double s[3] = {0.0, 0.0, 0.0};
-    const int nsums = !active ? 0 : (MODE == 0 ? 3 : (MODE == 1 ? 1 : 2));
-    for (int j = 0; j < nsums; j++)
-        for (int bI = 0; bI < a.nblocks; bI++) s[j] += a.partial[((size_t)j * a.nblocks + bI) * 64 + k];
+    const int nsums = !active ? 0 : NS;
+    if (grp == 0)
+        for (int j = 0; j < nsums; j++)
+            for (int g2 = 0; g2 < CG_FIN_G; g2++) s[j] += part[j][g2][k];
+    if (a.world > 1 && grp > 0) {
+        __syncthreads();   // (the barrier of the exchange below)
+        return;
+    }
+    if (grp > 0) return;
     if (a.world > 1) {
         // all-gather of the per-rank sums over peer memory, then the same rank-ordered sum on every rank.  Two parities:
         // a rank can be at most one reduction ahead of a peer (it cannot finish the next one without that peer's sums).
