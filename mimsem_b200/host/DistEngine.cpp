@@ -60,10 +60,11 @@ namespace {
 const int MAXW = 64;            // ranks of one box
 struct Wire {                   // what a rank tells the others about its IPC buffer
     unsigned char handle[64];
-    int64_t region_off[3], region_rows[3], region_stride[3];
+    // plans 0, 1, 2 = the k-form spaces (rows the element kernels read); 3, 4 = ALL ghost rows of the 1- and 2-forms
+    int64_t region_off[5], region_rows[5], region_stride[5];
     int64_t red_off;
-    int layout_slot[3][MAXW], layout_row0[3][MAXW], layout_n[3][MAXW];   // my inbox share of peer q (slot -1: none)
-    int send_slot[3][MAXW];                                              // position of q among the peers I send to
+    int layout_slot[5][MAXW], layout_row0[5][MAXW], layout_n[5][MAXW];   // my inbox share of peer q (slot -1: none)
+    int send_slot[5][MAXW];                                              // position of q among the peers I send to
 };
 struct PeerDesc {               // HaloPeer of csrc/engine.cuh (48 bytes)
     const int* rows;
@@ -133,24 +134,28 @@ DistEngine::DistEngine(const GlobalMesh& mesh, const double* thick, int nk, Comm
 
 void DistEngine::setup_p2p() {
     const Partition& P = *part_;
-    const int rank = comm_->rank, world = comm_->world, nsp = 3, nk = nk_max_;
+    const int rank = comm_->rank, world = comm_->world, nsp = 5, nk = nk_max_;
+    auto space_of = [](int s) { return s < 3 ? s : s - 2; };
+    auto recv_of = [&](int s) -> const std::map<int, GhostGroup>& { return s < 3 ? P.recv[s] : P.recv_ext[s - 2]; };
+    auto send_of = [&](int s) -> const std::map<int, std::vector<int> >& { return s < 3 ? P.send[s] : P.send_ext[s - 2]; };
     Wire mine;
     std::memset(&mine, 0, sizeof(mine));
-    for (int s = 0; s < 3; s++)
+    for (int s = 0; s < nsp; s++)
         for (int q = 0; q < MAXW; q++) mine.layout_slot[s][q] = mine.send_slot[s][q] = -1;
-    std::vector<int> recv_peers[3], send_peers[3];
+    std::vector<int> recv_peers[5], send_peers[5];
     const int64_t hdr_bytes = (int64_t)(2 * nsp + 1) * MAXP * 8;   // flags[nsp][MAXP], acks[nsp][MAXP] (+ one spare row)
     int64_t off = hdr_bytes;
-    for (int s = 0; s < 3; s++) {
-        for (std::map<int, GhostGroup>::const_iterator it = P.recv[s].begin(); it != P.recv[s].end(); ++it) recv_peers[s].push_back(it->first);
-        for (std::map<int, std::vector<int> >::const_iterator it = P.send[s].begin(); it != P.send[s].end(); ++it) send_peers[s].push_back(it->first);
+    for (int s = 0; s < nsp; s++) {
+        for (std::map<int, GhostGroup>::const_iterator it = recv_of(s).begin(); it != recv_of(s).end(); ++it) recv_peers[s].push_back(it->first);
+        for (std::map<int, std::vector<int> >::const_iterator it = send_of(s).begin(); it != send_of(s).end(); ++it) send_peers[s].push_back(it->first);
         if ((int)recv_peers[s].size() > MAXP || (int)send_peers[s].size() > MAXP) throw std::runtime_error("DistEngine: too many halo peers");
         // inbox of a space: [NBUF copies][ghost rows of the space, in ghost order][nk]; a peer's share is one run of rows
         int row = 0;
         for (size_t slot = 0; slot < recv_peers[s].size(); slot++) {
             const int q = recv_peers[s][slot];
-            const std::vector<int>& loc = P.recv[s].find(q)->second.local;
-            for (size_t i = 0; i < loc.size(); i++)
+            const std::vector<int>& loc = recv_of(s).find(q)->second.local;
+            // (the fused M1 launch reads inbox row i as ghost row n_owned + i; the extended plans only go through the pull kernel)
+            for (size_t i = 0; s < 3 && i < loc.size(); i++)
                 if (loc[i] != P.n_owned(s) + row + (int)i) throw std::runtime_error("DistEngine: ghost rows of a peer must be one run");
             mine.layout_slot[s][q] = (int)slot;
             mine.layout_row0[s][q] = row;
@@ -188,15 +193,15 @@ void DistEngine::setup_p2p() {
         keep_.push_back(d);
         return (const int*)d;
     };
-    for (int s = 0; s < 3; s++) {
+    for (int s = 0; s < nsp; s++) {
         std::vector<PeerDesc> push(send_peers[s].size()), pull(recv_peers[s].size());
         int push_rows = 0;
         for (size_t i = 0; i < push.size(); i++) {
             const int q = send_peers[s][i];
-            const std::vector<int>& loc = P.send[s].find(q)->second;
+            const std::vector<int>& loc = send_of(s).find(q)->second;
             const Wire& W = all[q];
             if (W.layout_slot[s][rank] < 0 || W.layout_n[s][rank] != (int)loc.size()) throw std::runtime_error("DistEngine: send / receive lists disagree");
-            push[i].rows = upload_rows(loc, s);
+            push[i].rows = upload_rows(loc, space_of(s));
             push[i].nrows = (int)loc.size();
             push[i].row0 = W.layout_row0[s][rank];
             push[i].inbox = (double*)(peer_base_[q] + W.region_off[s]);
@@ -209,7 +214,7 @@ void DistEngine::setup_p2p() {
             const int q = recv_peers[s][i];
             const Wire& W = all[q];
             if (W.send_slot[s][rank] < 0) throw std::runtime_error("DistEngine: peer does not send what this rank receives");
-            pull[i].rows = upload_rows(P.recv[s].find(q)->second.local, s);
+            pull[i].rows = upload_rows(recv_of(s).find(q)->second.local, space_of(s));
             pull[i].nrows = mine.layout_n[s][q];
             pull[i].row0 = mine.layout_row0[s][q];
             pull[i].inbox = (double*)(base_ + mine.region_off[s]);
@@ -248,7 +253,7 @@ DistEngine::~DistEngine() {
         mimsem_gpu_dev_sync(ctx_, NULL);
         if (comm_ && comm_->world > 1) comm_->barrier();   // nobody unmaps a buffer a peer may still write
         for (size_t i = 0; i < keep_.size(); i++) mimsem_gpu_dev_free(ctx_, keep_[i]);
-        for (int s = 0; s < 3; s++) {
+        for (int s = 0; s < 5; s++) {
             mimsem_gpu_dev_free(ctx_, plan_[s].d_push);
             mimsem_gpu_dev_free(ctx_, plan_[s].d_pull);
             mimsem_gpu_dev_free(ctx_, plan_[s].d_epochs);
@@ -298,10 +303,11 @@ void DistEngine::owned_to_global(const double* d_field, int space, int nlev, dou
         for (int k = 0; k < nlev; k++) levels[(size_t)k * N + g[i]] = cols[(size_t)perm_[space][i] * nlev + k];
 }
 
-void DistEngine::exchange(double* d_field, int space, int nlev) {
+void DistEngine::exchange(double* d_field, int space, int nlev, bool ext) {
     if (comm_->world == 1) return;
     if (nlev > nk_max_) throw std::runtime_error("DistEngine: more levels than the halo inboxes hold");
-    const Plan& pl = plan_[space];
+    if (ext && space == 0) ext = false;   // every ghost node is already in the plain plan
+    const Plan& pl = plan_[ext ? space + 2 : space];
     check(mimsem_gpu_halo_push(ctx_, pl.npush, pl.d_push, nlev, nlev, NBUF, d_field, pl.d_epochs, d_err_, NULL), "mimsem_gpu_halo_push");
     check(mimsem_gpu_halo_pull(ctx_, pl.npull, pl.d_pull, nlev, nlev, NBUF, d_field, pl.d_epochs + 1, d_err_, NULL), "mimsem_gpu_halo_pull");
 }
@@ -323,7 +329,8 @@ void DistEngine::apply_M1(const double* d_x, double* d_y, int nlev, double scale
           "mimsem_gpu_apply_M1_halo");
 }
 
-void DistEngine::apply(const std::string& op, double* x, double* c, double* y, int nlev, double scale, int tpow, int lev0) {
+void DistEngine::apply(const std::string& op, double* x, double* c, double* y, int nlev, double scale, int tpow, int lev0, double* u1,
+                       double tau) {
     const int ld = nlev;
     if (op == "M1") {
         apply_M1(x, y, nlev, scale, tpow, lev0);
@@ -349,6 +356,26 @@ void DistEngine::apply(const std::string& op, double* x, double* c, double* y, i
         exchange(x, 1, nlev);
         exchange(c, 0, nlev);
         check(mimsem_gpu_apply_R(ctx_, lev0, nlev, ld, scale, tpow, 0, c, x, y, NULL), "mimsem_gpu_apply_R");
+    } else if (op == "R_up") {
+        exchange(x, 1, nlev);
+        exchange(c, 0, nlev);
+        exchange(u1, 1, nlev);
+        check(mimsem_gpu_apply_R_up(ctx_, lev0, nlev, ld, scale, tpow, 0, c, u1, tau, x, y, NULL), "mimsem_gpu_apply_R_up");
+    } else if (op == "UtQW") {
+        exchange(x, 2, nlev);
+        exchange(c, 1, nlev);
+        check(mimsem_gpu_apply_UtQW(ctx_, nlev, ld, scale, c, x, y, NULL), "mimsem_gpu_apply_UtQW");
+    } else if (op == "M0h") {   // sums over the elements around a node: every ghost face of the coefficient
+        exchange(c, 2, nlev, true);
+        check(mimsem_gpu_apply_M0h(ctx_, lev0, nlev, ld, scale, tpow, 0, c, x, y, NULL), "mimsem_gpu_apply_M0h");
+    } else if (op == "E01") {
+        exchange(x, 1, nlev, true);
+        check(mimsem_gpu_apply_incidence(ctx_, MIMSEM_E01, nlev, ld, x, y, NULL), "mimsem_gpu_apply_incidence");
+    } else if (op == "M0h_up") {
+        exchange(x, 0, nlev);
+        exchange(c, 2, nlev, true);
+        exchange(u1, 1, nlev, true);
+        check(mimsem_gpu_apply_M0h_up(ctx_, lev0, nlev, ld, scale, tpow, 0, c, u1, tau, x, y, NULL), "mimsem_gpu_apply_M0h_up");
     } else {
         throw std::runtime_error("DistEngine::apply: operator " + op + " is not available in the C++ host layer");
     }

@@ -54,14 +54,16 @@ public:
     void scatter_from_global(const double* levels_global, int space, int nlev, double* d_field);
     void owned_to_global(const double* d_field, int space, int nlev, double* levels_global);
 
-    // ghost refresh of a local field (push kernel into the peers' inboxes + pull kernel), collective
-    void exchange(double* d_field, int space, int nlev);
+    // ghost refresh of a local field (push kernel into the peers' inboxes + pull kernel), collective.  ext: ALL ghost rows of
+    // the space (1- and 2-forms), what the operators that sum over the elements around a node read (M0h, E01, M0h_up)
+    void exchange(double* d_field, int space, int nlev, bool ext = false);
     // y = M1 x with the ghost refresh of x fused into the launch (mimsem_gpu_apply_M1_halo), collective
     void apply_M1(const double* d_x, double* d_y, int nlev, double scale, int tpow, int lev0 = 0, int flags = 0);
     // the other operators of the path: ghost refresh of the inputs that need one, then the local apply.
-    // op: "M1h", "M2", "M2h", "K", "E21", "E12", "M0", "E10", "R" (the node-sum operators M0h, E01, M0h_up need the
-    // extended ghost plan, which this layer does not carry yet)
-    void apply(const std::string& op, double* d_x, double* d_coeff, double* d_y, int nlev, double scale, int tpow, int lev0 = 0);
+    // op: "M1", "M1h", "M2", "M2h", "K", "UtQW", "E21", "E12", "M0", "M0h", "E10", "E01", "R", "R_up", "M0h_up" -- all fifteen
+    // operators of the path; d_u1 / tau: advecting velocity and time scale of the upwinded ones
+    void apply(const std::string& op, double* d_x, double* d_coeff, double* d_y, int nlev, double scale, int tpow, int lev0 = 0,
+               double* d_u1 = NULL, double tau = 0.0);
     // x = M1^-1 b on the partitioned mesh (mimsem_gpu_solve_M1_dist); returns the iteration count
     int solve_M1(const double* d_b, double* d_x, int nlev, double scale, int tpow, double rtol, int maxit, double* relres);
     bool halo_error();
@@ -85,7 +87,7 @@ private:
     mimsem_gpu_ctx* ctx_;
     int device_, nk_max_;
     std::vector<int> perm_[3];          // caller row -> engine row
-    Plan plan_[3];
+    Plan plan_[5];                      // spaces 0, 1, 2, then the extended plans of spaces 1 and 2
     char* base_;                        // my IPC buffer
     std::vector<char*> peer_base_;
     std::vector<void*> keep_;           // device row lists

@@ -68,18 +68,27 @@ int main(int argc, char** argv) {
             }
         const std::vector<double> x1 = pseudo_random((size_t)nk * mesh.N1, 1, -1, 1), x2 = pseudo_random((size_t)nk * mesh.N2, 2, -1, 1);
         const std::vector<double> h2 = pseudo_random((size_t)nk * mesh.N2, 3, 0.5e4, 1.5e4), u1 = pseudo_random((size_t)nk * mesh.N1, 4, -1e9, 1e9);
-        const std::vector<double> x0 = pseudo_random((size_t)nk * mesh.N0, 5, -1, 1);
+        const std::vector<double> x0 = pseudo_random((size_t)nk * mesh.N0, 5, -1, 1), q0 = pseudo_random((size_t)nk * mesh.N0, 6, -1e-4, 1e-4);
+        // advecting velocity of the upwinded operators: departure points stay well inside the element (tau = 150)
+        double det_mean = 0.0;
+        for (size_t i = 0; i < mesh.det.size(); i++) det_mean += std::fabs(mesh.det[i]) / (double)mesh.det.size();
+        const std::vector<double> uu = pseudo_random((size_t)nk * mesh.N1, 7, -1e-3 * det_mean, 1e-3 * det_mean);
         FileComm comm(argv[5], rank, world);
         DistEngine eng(mesh, thick.data(), nk, &comm, rank);
         SelfComm self;
         DistEngine* one = rank == 0 ? new DistEngine(mesh, thick.data(), nk, &self, 0) : NULL;
-        struct Case { const char* op; int sin, sout, sc; const std::vector<double>* x; const std::vector<double>* c; int tpow; };
-        const Case cases[] = {{"M1", 1, 1, -1, &x1, NULL, 1}, {"M1h", 1, 1, 2, &x1, &h2, 2}, {"K", 1, 2, 1, &x1, &u1, 2}, {"M2", 2, 2, -1, &x2, NULL, 1},
-                              {"E21", 1, 2, -1, &x1, NULL, 0}, {"E12", 2, 1, -1, &x2, NULL, 0}, {"M0", 0, 0, -1, &x0, NULL, 1}, {"E10", 0, 1, -1, &x0, NULL, 0}};
+        // all fifteen operators of the path (the set tests/mp_check.py runs through parallel.py)
+        struct Case { const char* op; int sin, sout, sc; const std::vector<double>* x; const std::vector<double>* c; int tpow; bool up; };
+        const Case cases[] = {{"M1", 1, 1, -1, &x1, NULL, 1, false},   {"M1h", 1, 1, 2, &x1, &h2, 2, false}, {"K", 1, 2, 1, &x1, &u1, 2, false},
+                              {"M2", 2, 2, -1, &x2, NULL, 1, false},   {"M2h", 2, 2, 2, &x2, &h2, 2, false}, {"UtQW", 2, 1, 1, &x2, &u1, 0, false},
+                              {"E21", 1, 2, -1, &x1, NULL, 0, false},  {"E12", 2, 1, -1, &x2, NULL, 0, false}, {"M0", 0, 0, -1, &x0, NULL, 1, false},
+                              {"M0h", 0, 0, 2, &x0, &h2, 2, false},    {"E10", 0, 1, -1, &x0, NULL, 0, false}, {"E01", 1, 0, -1, &x1, NULL, 0, false},
+                              {"R", 1, 1, 0, &x1, &q0, 2, false},      {"R_up", 1, 1, 0, &x1, &q0, 0, true},   {"M0h_up", 0, 0, 2, &x0, &h2, 0, true}};
         auto N_of = [&](int s) { return s == 0 ? mesh.N0 : (s == 1 ? mesh.N1 : mesh.N2); };
         auto run = [&](DistEngine& e, const Case& c, std::vector<double>& yg) {
             double* dx = e.alloc_field(c.sin, nk);
             double* dc = c.c ? e.alloc_field(c.sc, nk) : NULL;
+            double* du = c.up ? e.alloc_field(1, nk) : NULL;
             double* dy = e.alloc_field(c.sout, nk);
             // owned rows from the global field, ghost rows ZERO: they must come from the exchange
             auto load = [&](const std::vector<double>& g, int space, double* d) {
@@ -91,12 +100,14 @@ int main(int argc, char** argv) {
             };
             load(*c.x, c.sin, dx);
             if (dc) load(*c.c, c.sc, dc);
-            for (int rep = 0; rep < 3; rep++) e.apply(c.op, dx, dc, dy, nk, 1.0e8, c.tpow);
+            if (du) load(uu, 1, du);
+            for (int rep = 0; rep < 3; rep++) e.apply(c.op, dx, dc, dy, nk, 1.0e8, c.tpow, 0, du, c.up ? 150.0 : 0.0);
             e.sync();
             yg.assign((size_t)nk * N_of(c.sout), 0.0);
             e.owned_to_global(dy, c.sout, nk, yg.data());
             e.free_field(dx);
             if (dc) e.free_field(dc);
+            if (du) e.free_field(du);
             e.free_field(dy);
         };
         for (size_t ci = 0; ci < sizeof(cases) / sizeof(cases[0]); ci++) {
@@ -106,7 +117,7 @@ int main(int argc, char** argv) {
             if (rank == 0) {
                 run(*one, cases[ci], ys);
                 const bool same = std::memcmp(yg.data(), ys.data(), yg.size() * 8) == 0;
-                std::printf("%-4s on %d GPUs vs 1 GPU: %s\n", cases[ci].op, world, same ? "bitwise equal" : "DIFFERENT");
+                std::printf("%-6s on %d GPUs vs 1 GPU: %s\n", cases[ci].op, world, same ? "bitwise equal" : "DIFFERENT");
                 if (!same) failures++;
             }
         }
