@@ -94,7 +94,7 @@ struct mimsem_gpu_ctx {
     int halo_burst_pos = 0, halo_burst_len = 0;   // the next fused M1 launches are launch pos of a burst of len (see HaloFused)
     int pdl = 0;                             // 1: the caller guarantees that consecutive launches on a stream are independent
                                              //    (tile kernels are launched with programmatic stream serialization)
-    int host_chunk = 12;                     // levels per pipeline stage of mimsem_gpu_apply_host
+    int host_chunk = 8;                      // levels per pipeline stage of mimsem_gpu_apply_host (measured: scripts/tune_e2e.py)
     int halo_max_levels = 0;                 // levels per ghost row the caller's halo inboxes were allocated for (0: unknown)
     int n0_owned = -1;                       // subdomains: 0-form operators compute rows [0, n0_owned) only (-1: all rows)
     std::vector<int> h_elem_key;             // canonical (partition-independent) order of the elements, e.g. global ids
@@ -138,9 +138,11 @@ struct mimsem_gpu_ctx {
 
     DevBuf<unsigned> d_halo_counters;   // [2][64] finished-CTA counters of the p2p halo kernels (push, pull)
     // staging for the host-buffer entry point
-    DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[2], s_out2[2], s_x2[2], s_y2[2], s_c2[2], s_u2[2];
+    static constexpr int HOST_SLOTS = 4;     // chunks in flight in mimsem_gpu_apply_host (one stream and one buffer set each)
+    DevBuf<double> s_lev, s_x, s_y, s_c, s_lev2[HOST_SLOTS], s_out2[HOST_SLOTS], s_x2[HOST_SLOTS], s_y2[HOST_SLOTS], s_c2[HOST_SLOTS],
+        s_u2[HOST_SLOTS];
     DevBuf<double> s_ray;                    // level-0 Exner values of Umat_ray (apply_host)
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, host_stream[HOST_SLOTS - 1] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_host[3] = {nullptr, nullptr, nullptr};
 
     int64_t launches = 0;
@@ -1551,7 +1553,8 @@ int mimsem_gpu_destroy(mimsem_gpu_ctx* ctx) {
     if (!ctx) return MIMSEM_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int b = 0; b < mimsem_gpu_ctx::HOST_SLOTS - 1; b++)
+        if (ctx->host_stream[b]) cudaStreamDestroy(ctx->host_stream[b]);
     for (int b = 0; b < 3; b++)
         if (ctx->ev_host[b]) cudaEventDestroy(ctx->ev_host[b]);
     delete ctx;
@@ -2102,29 +2105,36 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         CUDA_OK(c->s_ray.resize((size_t)c->n2));
         CUDA_OK(cudaMemcpy(c->s_ray.p, h_u1, (size_t)c->n2 * sizeof(double), cudaMemcpyHostToDevice));
     }
-    // Pipeline over chunks of levels (levels are independent): while chunk c is being computed, chunk c+1 is on
-    // its way in and chunk c-1 on its way out; two streams ping-pong so that both PCIe directions stay busy.
+    // Pipeline over chunks of levels (levels are independent).  A chunk goes host -> device, through the operator and back
+    // on ONE stream; consecutive chunks use HOST_SLOTS streams (and buffer sets) in turn, so the upload of chunk i + 2 is
+    // not held back by the download of chunk i that shares a stream with chunk i + HOST_SLOTS: the host -> device copy
+    // engine runs back to back from the first chunk to the last and the device -> host engine trails it by one chunk.
+    // (With two slots every stream alternated upload / download and each PCIe direction idled half of the time.)
     const int ld = nlev;
+    constexpr int NS = mimsem_gpu_ctx::HOST_SLOTS;
     int CH = std::max(1, c->host_chunk);
     if (CH % 2) CH++;
     CH = std::min(CH, nlev);
     const int nchunk = (nlev + CH - 1) / CH;
+    const int nslot = std::min(NS, nchunk);
     const size_t big = (size_t)std::max(std::max(std::max(nin, nout), ncoef), need_u ? (int64_t)c->n1 : (int64_t)0) * CH;
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < nslot; b++) {
         CUDA_OK(c->s_lev2[b].resize(big));
         CUDA_OK(c->s_out2[b].resize((size_t)nout * CH));
-    }
-    for (int b = 0; b < 2; b++) {
         CUDA_OK(c->s_x2[b].resize((size_t)nin * CH));
         CUDA_OK(c->s_y2[b].resize((size_t)nout * CH));
         if (ncoef) CUDA_OK(c->s_c2[b].resize((size_t)ncoef * CH));
         if (need_u) CUDA_OK(c->s_u2[b].resize((size_t)c->n1 * CH));
     }
-    if (!c->stream2) CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    cudaStream_t sts[2] = {c->stream, c->stream2};
+    cudaStream_t sts[NS];
+    sts[0] = c->stream;
+    for (int b = 1; b < nslot; b++) {
+        if (!c->host_stream[b - 1]) CUDA_OK(cudaStreamCreateWithFlags(&c->host_stream[b - 1], cudaStreamNonBlocking));
+        sts[b] = c->host_stream[b - 1];
+    }
     for (int ck = 0; ck < nchunk; ck++) {
-        cudaStream_t st = sts[ck & 1];
-        const int b = ck & 1;
+        const int b = ck % nslot;
+        cudaStream_t st = sts[b];
         const int k0 = ck * CH, nl = std::min(CH, nlev - k0);
         // each chunk lives in its own column-layout buffers with leading dimension nl (contiguous DOF runs)
         if (ncoef) {
@@ -2169,9 +2179,7 @@ int mimsem_gpu_apply_host_up(mimsem_gpu_ctx* c, int op, int lev0, int nlev, doub
         if ((rc = transpose(c, false, sout, nout, nl, nl, yc, c->s_out2[b].p, st))) return rc;
         CUDA_OK(cudaMemcpyAsync(h_y + (size_t)k0 * nout, c->s_out2[b].p, (size_t)nout * nl * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    CUDA_OK(cudaStreamSynchronize(sts[1]));
-    cudaStream_t st = sts[0];
-    CUDA_OK(cudaStreamSynchronize(st));
+    for (int b = nslot - 1; b >= 0; b--) CUDA_OK(cudaStreamSynchronize(sts[b]));
     return MIMSEM_OK;
 }
 
