@@ -1,5 +1,7 @@
 #include "Assembly.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -7,6 +9,7 @@
 #include <vector>
 
 #include "../../include/mimsem_gpu.h"
+#include "Partition.h"
 
 // ------------------------------------------------------------------------------------------------
 // one device context per Topo (patch), shared by every operator built on it
@@ -18,6 +21,13 @@ struct Patch {
     Geom* geom = NULL;
     unsigned long thick_version = (unsigned long)-1;
     int refs = 0;
+    // second context of the element-block Jacobi preconditioner (pc_patch): the patch's elements in owner-computes
+    // mode plus one copy of the west / south neighbour of every element on the patch's west / south boundary
+    mimsem_gpu_ctx* pc_ctx = NULL;
+    bool pc_failed = false;
+    int pc_n1 = 0, pc_nq = 0;
+    unsigned long pc_thick_version = (unsigned long)-1;
+    std::vector<double> pc_x, pc_y;
 };
 std::map<Topo*, Patch> g_patches;
 
@@ -75,6 +85,188 @@ void sync_thickness(Patch* p) {
     p->thick_version = g->thick_version;
 }
 
+
+// canonical global meshes (closed form, csrc/mesh.cpp), shared by the patches of a process
+const mimsem_host::GlobalMesh* canonical_mesh(int kind, int p, int ne) {
+    static std::map<std::vector<int>, mimsem_host::GlobalMesh*> cache;
+    const std::vector<int> key = {kind, p, ne};
+    std::map<std::vector<int>, mimsem_host::GlobalMesh*>::iterator it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    mimsem_host::GlobalMesh* m = new mimsem_host::GlobalMesh;
+    if (m->create(kind, p, ne)) {
+        delete m;
+        m = NULL;
+    }
+    cache[key] = m;
+    return m;
+}
+
+// The reference preconditions its 1-form solves with PCBJACOBI, one block per element (PCBJacobiSetTotalBlocks(pc,
+// size * nElsX^2, NULL), eul/HorizSolve.cpp:77-84): block e = the 2 p^2 edges element e owns.  Its west / south edges also
+// carry the far-line terms of the element on the other side, which for the elements along the patch's west / south boundary
+// lives on another rank (or, on a one-patch periodic box, at the other end of the same patch, under different local
+// rows).  The block kernel (csrc/m1_bjacobi.cuh) runs in owner-computes mode on an element list with neighbours, so the
+// preconditioner gets a context of its own: the patch's elements with the patch's local rows, plus one read-only copy of
+// each such neighbour whose shared line is mapped onto the patch's rows and whose geometry comes from the closed-form
+// canonical mesh (an element's Jacobians do not depend on the partition; placement of a rank's patch: scr/Proc2.py:52-61).
+// Returns NULL when the configuration is not covered (the caller falls back to the diagonal).
+struct PcTables {
+    int nel = 0, nhalo = 0, n0 = 0, n1 = 0, n2 = 0, nq = 0;
+    std::vector<int> e0, e1x, e1y, e2, eq;
+    std::vector<double> J, det;
+};
+
+// host part of pc_patch: element tables and geometry of the preconditioner's context.  false: configuration not covered.
+bool pc_tables(Topo* topo, Geom* geom, PcTables& T) {
+    const int p = topo->elOrd, m = geom->quad->n, np1 = p + 1, mp1 = m + 1, nelx = topo->nElsX, nel = nelx * nelx;
+    if (m != p) return false;
+    int size = 1;
+    MPI_Comm_size(MPI_COMM_WORLD, &size);
+    const int per_face = topo->kind == MIMSEM_MESH_SPHERE ? size / 6 : size;
+    int npx = 1;
+    while ((npx + 1) * (npx + 1) <= per_face) npx++;
+    if (npx * npx != per_face || (topo->kind == MIMSEM_MESH_SPHERE && size % 6)) return false;
+    const int ne = nelx * npx, rank = topo->pi;
+    const mimsem_host::GlobalMesh* G = canonical_mesh(topo->kind, p, ne);
+    if (!G) return false;
+    const int face = topo->kind == MIMSEM_MESH_SPHERE ? rank / per_face : 0, pj = rank % per_face, px = pj % npx, py = pj / npx;
+    const double* Jown = geom->flatJ();
+    const double* Down = geom->flatDet();
+    for (size_t i = 0; i < (size_t)nel * mp1 * mp1; i++)
+        if (!(Down[i] > 0.0)) return false;   // signed determinants (src/Geom.cpp:251): not covered
+    const int w0 = np1 * np1, w1 = p * np1, w2 = p * p, wq = mp1 * mp1;
+    std::vector<int>&e0 = T.e0, &e1x = T.e1x, &e1y = T.e1y, &e2 = T.e2, &eq = T.eq;
+    std::vector<double>&J = T.J, &det = T.det;
+    auto canon = [&](int ex, int ey) { return (int64_t)face * ne * ne + (int64_t)(py * nelx + ey) * ne + px * nelx + ex; };
+    // a canonical quadrature point and a point of this patch are the same point of the mesh (the placement of the patch
+    // is checked against the coordinates, not trusted; the neighbour copies are tied to it through shared canonical ids)
+    double diam = 0.0;
+    for (int i = 0; i < 3; i++) diam = std::max(diam, std::fabs(G->xyz[i]) + std::fabs(G->xyz[(size_t)(G->NQ - 1) * 3 + i]));
+    double period = 0.0;
+    if (topo->kind == MIMSEM_MESH_BOX) {
+        // side length of the periodic box from the point set itself: the gap that closes the period equals the first gap
+        double lo = G->xyz[0], hi = G->xyz[0], second = 1.0e300;
+        for (int64_t q = 0; q < G->NQ; q++) {
+            lo = std::min(lo, G->xyz[(size_t)q * 3]);
+            hi = std::max(hi, G->xyz[(size_t)q * 3]);
+        }
+        for (int64_t q = 0; q < G->NQ; q++)
+            if (G->xyz[(size_t)q * 3] > lo + 1.0e-9 * (hi - lo)) second = std::min(second, G->xyz[(size_t)q * 3]);
+        period = hi - lo + (second - lo);
+    }
+    auto same_point = [&](int64_t canon_q, int local_q) {
+        double d = 0.0;
+        for (int i = 0; i < 3; i++) d = std::max(d, std::fabs(G->xyz[(size_t)canon_q * 3 + i] - geom->x[local_q][i]));
+        if (d <= 1.0e-6 * diam) return true;
+        // doubly periodic box: the same point up to a period (an east / north ghost column of the patch)
+        if (topo->kind != MIMSEM_MESH_BOX) return false;
+        for (int i = 0; i < 2; i++) {
+            const double dx = std::fabs(G->xyz[(size_t)canon_q * 3 + i] - geom->x[local_q][i]);
+            if (dx > 1.0e-6 * diam && std::fabs(dx - period) > 1.0e-6 * diam) return false;
+        }
+        return true;
+    };
+    for (int ey = 0; ey < nelx; ey++)
+        for (int ex = 0; ex < nelx; ex++) {
+            const size_t el = (size_t)ey * nelx + ex;
+            e0.insert(e0.end(), topo->elInds0_l(ex, ey), topo->elInds0_l(ex, ey) + w0);
+            e1x.insert(e1x.end(), topo->elInds1x_l(ex, ey), topo->elInds1x_l(ex, ey) + w1);
+            e1y.insert(e1y.end(), topo->elInds1y_l(ex, ey), topo->elInds1y_l(ex, ey) + w1);
+            e2.insert(e2.end(), topo->elInds2_l(ex, ey), topo->elInds2_l(ex, ey) + w2);
+            eq.insert(eq.end(), geom->elInds0_l(ex, ey), geom->elInds0_l(ex, ey) + wq);
+            J.insert(J.end(), Jown + el * wq * 4, Jown + (el + 1) * wq * 4);
+            det.insert(det.end(), Down + el * wq, Down + (el + 1) * wq);
+            // (element corners: the points inside an element are re-projected per element by Geom, eul/Geom.cpp:682-724)
+            const int64_t c = canon(ex, ey);
+            const int corner[4] = {0, m, m * mp1, wq - 1};
+            for (int j = 0; j < 4; j++)
+                if (!same_point(G->elq[(size_t)c * wq + corner[j]], eq[el * wq + corner[j]])) return false;
+        }
+    int n0 = topo->n0, n1 = topo->n1, n2 = topo->n2, nq = geom->n0, nhalo = 0;
+    for (int ey = 0; ey < nelx; ey++)
+        for (int ex = 0; ex < nelx; ex++)
+            for (int side = 0; side < 2; side++) {
+                if ((side == 0 ? ex : ey) != 0) continue;   // the neighbour is one of the patch's own elements, same rows
+                const int64_t c = canon(ex, ey), n = G->ws_nbr[(size_t)c * 2 + side];
+                if (n < 0) continue;
+                // canonical id -> patch-local row, for what the element has on the shared line
+                std::map<int, int> edge_row, node_row, quad_row;
+                const size_t el = (size_t)ey * nelx + ex;
+                for (int i = 0; i < p; i++) {
+                    const int j = side == 0 ? i * np1 : i;
+                    if (side == 0) edge_row[G->el1x[(size_t)c * w1 + j]] = e1x[el * w1 + j];
+                    else edge_row[G->el1y[(size_t)c * w1 + j]] = e1y[el * w1 + j];
+                }
+                for (int i = 0; i <= p; i++) {
+                    const int j = side == 0 ? i * np1 : i;
+                    node_row[G->el0[(size_t)c * w0 + j]] = e0[el * w0 + j];
+                    quad_row[G->elq[(size_t)c * wq + j]] = eq[el * wq + j];
+                }
+                int shared = 0;
+                auto row_of = [&](const std::map<int, int>& known, int id, int* fresh) {
+                    std::map<int, int>::const_iterator it = known.find(id);
+                    if (it == known.end()) return (*fresh)++;
+                    shared++;
+                    return it->second;
+                };
+                for (int j = 0; j < w0; j++) e0.push_back(row_of(node_row, G->el0[(size_t)n * w0 + j], &n0));
+                shared = 0;
+                for (int j = 0; j < w1; j++) e1x.push_back(row_of(edge_row, G->el1x[(size_t)n * w1 + j], &n1));
+                for (int j = 0; j < w1; j++) e1y.push_back(row_of(edge_row, G->el1y[(size_t)n * w1 + j], &n1));
+                if (shared != p) return false;
+                shared = 0;
+                for (int j = 0; j < wq; j++) eq.push_back(row_of(quad_row, G->elq[(size_t)n * wq + j], &nq));
+                if (shared != p + 1) return false;
+                for (int j = 0; j < w2; j++) e2.push_back(n2++);
+                J.insert(J.end(), G->J.begin() + (size_t)n * wq * 4, G->J.begin() + (size_t)(n + 1) * wq * 4);
+                det.insert(det.end(), G->det.begin() + (size_t)n * wq, G->det.begin() + (size_t)(n + 1) * wq);
+                nhalo++;
+            }
+    T.nel = nel; T.nhalo = nhalo; T.n0 = n0; T.n1 = n1; T.n2 = n2; T.nq = nq;
+    return true;
+}
+
+mimsem_gpu_ctx* pc_patch(Patch* P, Topo* topo) {
+    if (P->pc_ctx || P->pc_failed) return P->pc_ctx;
+    P->pc_failed = true;   // until everything below went through
+    Geom* geom = P->geom;
+    PcTables T;
+    if (!pc_tables(topo, geom, T)) return NULL;
+    const int p = topo->elOrd, m = geom->quad->n, np1 = p + 1, mp1 = m + 1;
+    mimsem_gpu_ctx* ctx = NULL;
+    int dev = 0;
+    if (const char* s = std::getenv("MIMSEM_DEVICE")) dev = std::atoi(s);
+    if (mimsem_gpu_create(dev, &ctx)) die("mimsem_gpu_create (preconditioner)");
+    std::vector<double> lj((size_t)mp1 * np1), ej((size_t)mp1 * p);
+    for (int q = 0; q < mp1; q++) {
+        for (int j = 0; j < np1; j++) lj[(size_t)q * np1 + j] = geom->node->ljxi[q][j];
+        for (int j = 0; j < p; j++) ej[(size_t)q * p + j] = geom->edge->ejxi[q][j];
+    }
+    if (mimsem_gpu_set_basis(ctx, p, m, geom->quad->w, lj.data(), ej.data())) die("mimsem_gpu_set_basis (preconditioner)");
+    if (mimsem_gpu_set_topo(ctx, T.nel + T.nhalo, T.nel, T.n0, T.n1, T.n2, T.nq, 0, T.e0.data(), T.e1x.data(), T.e1y.data(), T.e2.data(),
+                            T.eq.data()))
+        die("mimsem_gpu_set_topo (preconditioner)");
+    if (mimsem_gpu_set_geom(ctx, T.J.data(), T.det.data())) die("mimsem_gpu_set_geom (preconditioner)");
+    P->pc_ctx = ctx;
+    P->pc_n1 = T.n1;
+    P->pc_nq = T.nq;
+    P->pc_x.assign(T.n1, 0.0);
+    P->pc_y.assign(T.n1, 0.0);
+    P->pc_failed = false;
+    return ctx;
+}
+
+void sync_pc_thickness(Patch* P) {
+    Geom* g = P->geom;
+    if (P->pc_thick_version == g->thick_version) return;
+    // the neighbour copies' far lines are the patch's own quadrature points; their other points are never read
+    std::vector<double> t((size_t)g->nk * P->pc_nq, 1.0);
+    for (int k = 0; k < g->nk; k++)
+        for (int i = 0; i < g->n0; i++) t[(size_t)k * P->pc_nq + i] = g->thick[k][i];
+    if (mimsem_gpu_set_thickness(P->pc_ctx, g->nk, t.data())) die("mimsem_gpu_set_thickness (preconditioner)");
+    P->pc_thick_version = g->thick_version;
+}
+
 }  // namespace
 
 int MimsemAttachPatch(Topo* topo, Geom* geom, LagrangeNode* l, LagrangeEdge* e) {
@@ -84,6 +276,19 @@ int MimsemAttachPatch(Topo* topo, Geom* geom, LagrangeNode* l, LagrangeEdge* e) 
     return 0;
 }
 const char* MimsemLastError(void) { return mimsem_last_error(); }
+int MimsemPCTablesCheck(Topo* topo, Geom* geom, int sizes[6]) {
+    PcTables T;
+    if (!pc_tables(topo, geom, T)) return 1;
+    const int v[6] = {T.nel, T.nhalo, T.n0, T.n1, T.n2, T.nq};
+    for (int i = 0; i < 6; i++) sizes[i] = v[i];
+    // what mimsem_gpu_set_topo will insist on: an edge row belongs to at most two elements of the context
+    std::vector<int> uses(T.n1, 0);
+    for (size_t i = 0; i < T.e1x.size(); i++) uses[T.e1x[i]]++;
+    for (size_t i = 0; i < T.e1y.size(); i++) uses[T.e1y[i]]++;
+    for (int i = 0; i < T.n1; i++)
+        if (uses[i] > 2) return 2;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // the MatShell
@@ -175,6 +380,37 @@ PetscErrorCode shell_getdiag(Mat A, Vec d) {
     return 0;
 }
 
+// z = blockdiag(M1)^-1 r with the reference's element blocks (PCBJACOBI, eul/HorizSolve.cpp:77-84) for the Umat shell:
+// ghosted local r -> block solves on the device -> owned rows of z.  Nonzero (PETSC_ERR_SUP) when A is not such a shell.
+PetscErrorCode shell_pcbjacobi(Mat A, Vec r, Vec z) {
+    MimsemShell* s;
+    MatShellGetContext(A, &s);
+    if (!s || s->op != 0 /* M1 */ || (s->flags & MIMSEM_THICK_MEAN)) return 56;
+    Topo* topo = s->topo;
+    std::map<Topo*, Patch>::iterator it = g_patches.find(topo);
+    if (it == g_patches.end() || !it->second.ctx) return 56;
+    Patch* p = &it->second;
+    mimsem_gpu_ctx* pc = pc_patch(p, topo);
+    if (!pc) return 56;
+    if (s->tpow > 0) sync_pc_thickness(p);
+    VecScatterBegin(topo->gtol_1, r, s->xl, INSERT_VALUES, SCATTER_FORWARD);
+    VecScatterEnd(topo->gtol_1, r, s->xl, INSERT_VALUES, SCATTER_FORWARD);
+    PetscScalar *xa, *ya;
+    VecGetArray(s->xl, &xa);
+    std::memcpy(p->pc_x.data(), xa, sizeof(double) * topo->n1);   // rows beyond n1 belong to the neighbour copies: never read
+    VecRestoreArray(s->xl, &xa);
+    if (mimsem_gpu_apply_host_up(pc, 20, s->lev, 1, s->scale, s->tpow, s->flags, NULL, NULL, 0.0, p->pc_x.data(), p->pc_y.data()))
+        die("mimsem_gpu_apply_host (element-block Jacobi)");
+    // the blocks cover exactly the edges the patch's elements own; its east / north ghost rows stay zero
+    VecGetArray(s->yl, &ya);
+    std::memcpy(ya, p->pc_y.data(), sizeof(double) * topo->n1);
+    VecRestoreArray(s->yl, &ya);
+    VecZeroEntries(z);
+    VecScatterBegin(topo->gtol_1, s->yl, z, ADD_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(topo->gtol_1, s->yl, z, ADD_VALUES, SCATTER_REVERSE);
+    return 0;
+}
+
 MimsemShell* make_shell(Topo* topo, int op, int sin, int sout, Mat* M) {
     MimsemShell* s = new MimsemShell;
     s->topo = topo;
@@ -187,6 +423,10 @@ MimsemShell* make_shell(Topo* topo, int op, int sin, int sout, Mat* M) {
                    space_size_global(topo, sin), s, M);
     MatShellSetOperation(*M, MATOP_MULT, (void (*)(void))shell_mult);
     if (sin == sout && sin != 2) MatShellSetOperation(*M, MATOP_GET_DIAGONAL, (void (*)(void))shell_getdiag);
+#ifndef MIMSEM_HAVE_PETSC
+    // the compatibility layer's KSP asks the operator itself for the blocks of a PCBJACOBI request (real PETSc: MimsemPCApplyBJacobi)
+    if (op == 0) MatShellSetOperation(*M, MATOP_COMPAT_PCBJACOBI, (void (*)(void))shell_pcbjacobi);
+#endif
     s->mat = *M;
     return s;
 }
@@ -218,6 +458,23 @@ Patch* patch_of(Topo* topo) {
 }
 
 }  // namespace
+
+PetscErrorCode MimsemPCApplyBJacobi(PC pc, Vec r, Vec z) {
+    Mat M = NULL;
+    PCShellGetContext(pc, &M);
+    return M ? shell_pcbjacobi(M, r, z) : 56;
+}
+PetscErrorCode MimsemKSPSetElementBlockJacobi(KSP ksp, Mat M) {
+    MimsemShell* s = NULL;
+    MatShellGetContext(M, &s);
+    if (!s || s->op != 0 /* M1 */) return 56;
+    PC pc;
+    KSPGetPC(ksp, &pc);
+    PCSetType(pc, PCSHELL);
+    PCShellSetContext(pc, M);
+    PCShellSetApply(pc, MimsemPCApplyBJacobi);
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // operators

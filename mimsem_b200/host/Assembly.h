@@ -314,4 +314,19 @@ int MimsemAttachPatch(Topo* topo, Geom* geom, LagrangeNode* l, LagrangeEdge* e);
 // last error text of the device library for the calling thread
 const char* MimsemLastError(void);
 
+// The reference's preconditioner of its 1-form solves -- PCBJACOBI with one block per element
+// (PCBJacobiSetTotalBlocks(pc, size * nElsX * nElsX, NULL), eul/HorizSolve.cpp:77-84, 791-796) -- for a Umat shell:
+// PETSc's PCBJACOBI cuts its blocks out of an ASSEMBLED matrix, which a MatShell does not have, so the blocks are
+// tabulated, factorised and solved on the device (mimsem_gpu_pc_bjacobi_M1) and handed to the KSP as a PCSHELL:
+//     KSPSetOperators(ksp1, M1->M, M1->M);  MimsemKSPSetElementBlockJacobi(ksp1, M1->M);   // instead of PCSetType(pc, PCBJACOBI)
+// The block data follow M1->assemble(lev, scale, vert_scale) like the shell's MatMult.  (The in-tree compatibility layer
+// routes a plain PCBJACOBI request on such a shell here by itself, so that the reference's callers run unchanged.)
+// Returns nonzero when M is not a Umat shell.
+PetscErrorCode MimsemPCApplyBJacobi(PC pc, Vec r, Vec z);     /* PCShellSetApply callback; PCShellSetContext(pc, M) */
+PetscErrorCode MimsemKSPSetElementBlockJacobi(KSP ksp, Mat M);
+// host half of that preconditioner's set-up, for tests without a GPU: builds the element tables of its context (the patch
+// plus copies of the west / south neighbours across the patch boundary, checked against the point coordinates);
+// sizes = {elements, neighbour copies, n0, n1, n2, nq}.  0: fine, 1: configuration not covered, 2: inconsistent tables
+int MimsemPCTablesCheck(Topo* topo, Geom* geom, int sizes[6]);
+
 #endif

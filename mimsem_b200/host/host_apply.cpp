@@ -4,7 +4,8 @@
 //
 //   host_apply <input-dir or -> <kind 0|1> <p> <ne> <nprocs> <nk> <in.bin> <out.bin>
 // in.bin : doubles  thick[nk][N0] x1[nk][N1] x2[nk][N2] x0[nk][N0] h2[nk][N2] u1[nk][N1]   (global numbering)
-// out.bin: doubles  per level: Umat Wmat Pmat Pmat_h Uhmat Whmat WtQUmat E21 E12 E10 E01 results
+// out.bin: doubles  per level: Umat, element-block Jacobi of Umat (the PCBJACOBI of eul/HorizSolve.cpp:77-84 applied to x1),
+//                   Wmat Pmat Pmat_h Uhmat Whmat WtQUmat E21 E12 E10 E01 results
 #include <unistd.h>
 
 #include <cstdio>
@@ -28,6 +29,7 @@ static std::vector<double> read_all(const char* fn) {
 struct Rank {
     Topo* topo; Geom* geom; GaussLobatto* quad; LagrangeNode* node; LagrangeEdge* edge;
     Umat* M1; Wmat* M2; Pmat* M0; Uhmat* F; Whmat* M2h; WtQUmat* K; E10mat* NtoE; E21mat* EtoF;
+    KSP ksp1; PC pc1;
 };
 
 int main(int argc, char** argv) {
@@ -75,6 +77,11 @@ int main(int argc, char** argv) {
         k.K = new WtQUmat(k.topo, k.geom, k.node, k.edge);
         k.NtoE = new E10mat(k.topo);
         k.EtoF = new E21mat(k.topo);
+        // eul/HorizSolve.cpp:77-84 with the element blocks served by the shell (Assembly.h: MimsemKSPSetElementBlockJacobi)
+        KSPCreate(MPI_COMM_WORLD, &k.ksp1);
+        KSPSetOperators(k.ksp1, k.M1->M, k.M1->M);
+        if (MimsemKSPSetElementBlockJacobi(k.ksp1, k.M1->M)) { std::fprintf(stderr, "no element-block Jacobi for this shell\n"); return 1; }
+        KSPGetPC(k.ksp1, &k.pc1);
     }
 
     FILE* out = std::fopen(argv[8], "wb");
@@ -131,6 +138,7 @@ int main(int argc, char** argv) {
         }
 #define ALL_RANKS(stmt) for (int r = 0; r < np; r++) { PetscCompatSetRank(r, np); Rank& k = R[r]; stmt; }
         ALL_RANKS(k.M1->assemble(lev, SCALE, true); MatMult(k.M1->M, v1[r], w1[r]))            dump(w1);
+        ALL_RANKS(if (PCApply(k.pc1, v1[r], w1[r])) return 1)                                  dump(w1);
         ALL_RANKS(k.M2->assemble(lev, SCALE, true); MatMult(k.M2->M, v2[r], w2[r]))            dump(w2);
         ALL_RANKS(k.M0->assemble(lev, SCALE); MatMult(k.M0->M, v0[r], w0[r]))                  dump(w0);
         ALL_RANKS(k.M0->assemble_h(lev, SCALE, hv[r]); MatMult(k.M0->M, v0[r], w0[r]))         dump(w0);
@@ -148,6 +156,7 @@ int main(int argc, char** argv) {
         Rank& k = R[r];
         VecDestroy(&v0[r]); VecDestroy(&v1[r]); VecDestroy(&v2[r]); VecDestroy(&w0[r]); VecDestroy(&w1[r]); VecDestroy(&w2[r]);
         VecDestroy(&hv[r]); VecDestroy(&uv[r]); VecDestroy(&ul[r]);
+        KSPDestroy(&k.ksp1);
         delete k.EtoF; delete k.NtoE; delete k.K; delete k.M2h; delete k.F; delete k.M0; delete k.M2; delete k.M1;
         delete k.edge; delete k.node; delete k.quad; delete k.geom; delete k.topo;
     }

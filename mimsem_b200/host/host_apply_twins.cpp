@@ -7,7 +7,7 @@
 // in.bin : doubles  thick[nk][N0] x1[nk][N1] x1b[nk][N1] x2[nk][N2] h2[nk][N2] h2b[nk][N2] u1[nk][N1] ex2[nk][N2]  (global numbering)
 // out.bin: doubles  per level: Uvec::assemble, Uvec::assemble_hu (4 terms), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv (rho = h2b),
 //                   Umat_ray (exner = ex2[lev], exner_s = ex2[0], dt = 300, as eul/Euler_2.cpp:1218-1229 calls it);
-//                   then { its, |x - x_true| / |x_true| } of the box solve
+//                   then { its, |x - x_true| / |x_true|, its with PCJACOBI } of the box solve
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -195,8 +195,14 @@ int main(int argc, char** argv) {
         VecAXPY(s, -1.0, x);
         VecNorm(s, NORM_2, &en);
         VecNorm(x, NORM_2, &xn);
-        const double res[2] = {(double)its, en / xn};
-        std::fwrite(res, 8, 2, out);
+        // the same solve with the shell's diagonal instead of its element blocks
+        PCSetType(pc, PCJACOBI);
+        VecZeroEntries(s);
+        KSPSolve(ksp1, b, s);
+        PetscInt its_diag;
+        KSPGetIterationNumber(ksp1, &its_diag);
+        const double res[3] = {(double)its, en / xn, (double)its_diag};
+        std::fwrite(res, 8, 3, out);
         KSPDestroy(&ksp1);
         VecDestroy(&x); VecDestroy(&b); VecDestroy(&s);
         delete M1; delete e; delete n; delete q; delete bg; delete bt;

@@ -3,6 +3,7 @@
 #include "petsc_compat.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +52,7 @@ struct _mimsem_Mat {
     PetscErrorCode (*mult)(Mat, Vec, Vec);
     PetscErrorCode (*destroy)(Mat);
     PetscErrorCode (*getdiag)(Mat, Vec);
+    PetscErrorCode (*pcbjacobi)(Mat, Vec, Vec);
 };
 struct _mimsem_PC {
     const char* type;
@@ -60,8 +62,9 @@ struct _mimsem_PC {
 };
 struct _mimsem_KSP {
     Mat A, P;
-    double rtol, abstol;
+    double rtol, abstol, rnorm;
     int maxits, its;
+    bool cg;
     _mimsem_PC pc;
 };
 
@@ -207,12 +210,14 @@ PetscErrorCode MatCreateShell(MPI_Comm, PetscInt, PetscInt, PetscInt, PetscInt, 
     (*A)->mult = NULL;
     (*A)->destroy = NULL;
     (*A)->getdiag = NULL;
+    (*A)->pcbjacobi = NULL;
     return 0;
 }
 PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void)) {
     if (op == MATOP_MULT) A->mult = (PetscErrorCode(*)(Mat, Vec, Vec))f;
     else if (op == MATOP_DESTROY) A->destroy = (PetscErrorCode(*)(Mat))f;
     else if (op == MATOP_GET_DIAGONAL) A->getdiag = (PetscErrorCode(*)(Mat, Vec))f;
+    else if (op == MATOP_COMPAT_PCBJACOBI) A->pcbjacobi = (PetscErrorCode(*)(Mat, Vec, Vec))f;
     else return 56;   /* PETSC_ERR_SUP */
     return 0;
 }
@@ -378,6 +383,8 @@ PetscErrorCode KSPCreate(MPI_Comm, KSP* ksp) {
     k->abstol = 1.0e-50;
     k->maxits = 10000;
     k->its = 0;
+    k->rnorm = 0.0;
+    k->cg = false;      // KSPGMRES is PETSc's default type
     k->pc.type = PCJACOBI;
     k->pc.apply = NULL;
     k->pc.ctx = NULL;
@@ -393,44 +400,67 @@ PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, Petsc
     if (maxits != PETSC_DEFAULT) ksp->maxits = maxits;
     return 0;
 }
-PetscErrorCode KSPSetType(KSP, KSPType) { return 0; }
+PetscErrorCode KSPSetType(KSP ksp, KSPType type) { ksp->cg = type && std::strcmp(type, KSPCG) == 0; return 0; }
 PetscErrorCode KSPSetOptionsPrefix(KSP, const char*) { return 0; }
 PetscErrorCode KSPSetFromOptions(KSP) { return 0; }
 PetscErrorCode KSPGetPC(KSP ksp, PC* pc) { *pc = &ksp->pc; return 0; }
 PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt* its) { *its = ksp->its; return 0; }
+PetscErrorCode KSPGetResidualNorm(KSP ksp, PetscReal* rnorm) { *rnorm = ksp->rnorm; return 0; }
 PetscErrorCode PCSetType(PC pc, PCType type) { pc->type = type; return 0; }
 PetscErrorCode PCBJacobiSetTotalBlocks(PC pc, PetscInt blocks, const PetscInt*) { pc->blocks = blocks; return 0; }
 PetscErrorCode PCShellSetApply(PC pc, PetscErrorCode (*apply)(PC, Vec, Vec)) { pc->apply = apply; return 0; }
+PetscErrorCode PCApply(PC pc, Vec x, Vec y) { return pc->apply ? pc->apply(pc, x, y) : 56; }
 PetscErrorCode PCShellSetContext(PC pc, void* ctx) { pc->ctx = ctx; return 0; }
 PetscErrorCode PCShellGetContext(PC pc, void* ctx) { *(void**)ctx = pc->ctx; return 0; }
 
-// preconditioned conjugate gradients on the (symmetric positive definite) shell operator
-PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
-    if (g_size != 1) {
-        std::fprintf(stderr, "petsc_compat: KSPSolve needs real PETSc when more than one rank is played in-process\n");
-        std::abort();
+namespace {
+
+// the preconditioner of a solve: see the comment at KSPCreate in petsc_compat.h
+struct Precond {
+    KSP ksp;
+    Vec d;
+    int kind;   // 0 identity, 1 diagonal, 2 shell callback, 3 the operator's own element blocks
+    Precond(KSP k, Vec like) : ksp(k), d(NULL), kind(0), like_(like) {
+        const char* t = k->pc.type ? k->pc.type : PCJACOBI;
+        Mat P = k->P ? k->P : k->A;
+        if (k->pc.apply && std::strcmp(t, PCSHELL) == 0) kind = 2;
+        else if (std::strcmp(t, PCNONE) == 0) kind = 0;
+        else if (std::strcmp(t, PCBJACOBI) == 0 && P->pcbjacobi) kind = 3;
+        else use_diagonal();
     }
-    Vec r, z, p, q, d = NULL;
-    VecDuplicate(b, &r); VecDuplicate(b, &z); VecDuplicate(b, &p); VecDuplicate(b, &q);
-    const bool shell_pc = ksp->pc.apply != NULL;
-    if (!shell_pc && ksp->P && ksp->P->getdiag) {
-        VecDuplicate(b, &d);
-        MatGetDiagonal(ksp->P, d);
+    ~Precond() { if (d) VecDestroy(&d); }
+    void use_diagonal() {
+        Mat P = ksp->P ? ksp->P : ksp->A;
+        kind = 0;
+        if (!P->getdiag) return;
+        VecDuplicate(like_, &d);
+        if (MatGetDiagonal(P, d) == 0) kind = 1;
     }
-    auto precond = [&](Vec in, Vec out) {
-        if (shell_pc) ksp->pc.apply(&ksp->pc, in, out);
-        else if (d) VecPointwiseDivide(out, in, d);
+    void operator()(Vec in, Vec out) {
+        Mat P = ksp->P ? ksp->P : ksp->A;
+        // the shell says with a nonzero code that it has no blocks for this operator: its first answer decides (the
+        // first application opens the solve), the diagonal takes over
+        if (kind == 3 && P->pcbjacobi(P, in, out) != 0) use_diagonal();
+        if (kind == 3) return;
+        if (kind == 2) ksp->pc.apply(&ksp->pc, in, out);
+        else if (kind == 1) VecPointwiseDivide(out, in, d);
         else VecCopy(in, out);
-    };
+    }
+    Vec like_;
+};
+
+// preconditioned conjugate gradients (KSPCG)
+void solve_cg(KSP ksp, Precond& B, Vec b, Vec x) {
+    Vec r, z, p, q;
+    VecDuplicate(b, &r); VecDuplicate(b, &z); VecDuplicate(b, &p); VecDuplicate(b, &q);
     double bn, rn, rz, rz_new, pq;
     VecNorm(b, NORM_2, &bn);
     MatMult(ksp->A, x, q);             // nonzero initial guess, as PETSc's KSPSolve with the caller's x
     VecCopy(b, r);
     VecAXPY(r, -1.0, q);
-    precond(r, z);
+    B(r, z);
     VecCopy(z, p);
     VecDot(r, z, &rz);
-    ksp->its = 0;
     VecNorm(r, NORM_2, &rn);
     while (rn > ksp->rtol * bn && rn > ksp->abstol && ksp->its < ksp->maxits) {
         MatMult(ksp->A, p, q);
@@ -438,15 +468,101 @@ PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
         const double alpha = rz / pq;
         VecAXPY(x, alpha, p);
         VecAXPY(r, -alpha, q);
-        precond(r, z);
+        B(r, z);
         VecDot(r, z, &rz_new);
         VecAYPX(p, rz_new / rz, z);
         rz = rz_new;
         VecNorm(r, NORM_2, &rn);
         ksp->its++;
     }
+    ksp->rnorm = rn;
     VecDestroy(&r); VecDestroy(&z); VecDestroy(&p); VecDestroy(&q);
-    if (d) VecDestroy(&d);
+}
+
+// restarted GMRES(30), left preconditioning: minimises |B (b - A x)| over x0 + K_m(B A, B r0)
+void solve_gmres(KSP ksp, Precond& B, Vec b, Vec x) {
+    const int m = 30;
+    std::vector<Vec> V(m + 1);
+    for (int i = 0; i <= m; i++) VecDuplicate(b, &V[i]);
+    Vec w, t;
+    VecDuplicate(b, &w); VecDuplicate(b, &t);
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+    B(b, w);
+    double bnorm;
+    VecNorm(w, NORM_2, &bnorm);
+    const double ttol = std::max(ksp->rtol * bnorm, ksp->abstol);
+    bool done = false;
+    while (!done) {
+        MatMult(ksp->A, x, t);
+        VecAYPX(t, -1.0, b);           // t = b - A x
+        B(t, V[0]);
+        double beta;
+        VecNorm(V[0], NORM_2, &beta);
+        ksp->rnorm = beta;
+        if (beta <= ttol || ksp->its >= ksp->maxits) break;
+        VecScale(V[0], 1.0 / beta);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int k = 0;
+        for (; k < m && ksp->its < ksp->maxits; k++) {
+            MatMult(ksp->A, V[k], t);
+            B(t, w);
+            for (int i = 0; i <= k; i++) {
+                double h;
+                VecDot(w, V[i], &h);
+                H[(size_t)i * m + k] = h;
+                VecAXPY(w, -h, V[i]);
+            }
+            double hn;
+            VecNorm(w, NORM_2, &hn);
+            H[(size_t)(k + 1) * m + k] = hn;
+            for (int i = 0; i < k; i++) {   // the rotations so far, then a new one that removes the subdiagonal entry
+                const double a = H[(size_t)i * m + k], c = H[(size_t)(i + 1) * m + k];
+                H[(size_t)i * m + k] = cs[i] * a + sn[i] * c;
+                H[(size_t)(i + 1) * m + k] = -sn[i] * a + cs[i] * c;
+            }
+            const double a = H[(size_t)k * m + k], rho = std::sqrt(a * a + hn * hn);
+            cs[k] = rho > 0.0 ? a / rho : 1.0;
+            sn[k] = rho > 0.0 ? hn / rho : 0.0;
+            H[(size_t)k * m + k] = rho;
+            H[(size_t)(k + 1) * m + k] = 0.0;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            ksp->its++;
+            ksp->rnorm = std::fabs(g[k + 1]);
+            if (hn > 0.0) {
+                VecCopy(w, V[k + 1]);
+                VecScale(V[k + 1], 1.0 / hn);
+            }
+            if (ksp->rnorm <= ttol || hn == 0.0) {
+                done = true;
+                k++;
+                break;
+            }
+        }
+        for (int i = k - 1; i >= 0; i--) {   // back substitution, x += V y
+            double s = g[i];
+            for (int j = i + 1; j < k; j++) s -= H[(size_t)i * m + j] * y[j];
+            y[i] = s / H[(size_t)i * m + i];
+        }
+        for (int i = 0; i < k; i++) VecAXPY(x, y[i], V[i]);
+        if (ksp->its >= ksp->maxits) break;
+    }
+    for (int i = 0; i <= m; i++) VecDestroy(&V[i]);
+    VecDestroy(&w); VecDestroy(&t);
+}
+
+}  // namespace
+
+PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x) {
+    if (g_size != 1) {
+        std::fprintf(stderr, "petsc_compat: KSPSolve needs real PETSc when more than one rank is played in-process\n");
+        std::abort();
+    }
+    ksp->its = 0;
+    Precond B(ksp, b);
+    if (ksp->cg) solve_cg(ksp, B, b, x);
+    else solve_gmres(ksp, B, b, x);
     return 0;
 }
 #endif

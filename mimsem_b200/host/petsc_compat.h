@@ -31,7 +31,10 @@ typedef int MPI_Comm;
 typedef enum { NOT_SET_VALUES = 0, INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
 typedef enum { SCATTER_FORWARD = 0, SCATTER_REVERSE = 1 } ScatterMode;
 typedef enum { PETSC_COPY_VALUES = 0, PETSC_OWN_POINTER = 1, PETSC_USE_POINTER = 2 } PetscCopyMode;
-typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_GET_DIAGONAL = 17, MATOP_DESTROY = 60 } MatOperation;
+typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_GET_DIAGONAL = 17, MATOP_DESTROY = 60,
+               /* compat only: z = blockdiag(A)^-1 r for a PCBJACOBI request on a shell (PETSc cuts the blocks out of an
+                  assembled matrix; a shell that can apply them itself offers this operation) */
+               MATOP_COMPAT_PCBJACOBI = 1000 } MatOperation;
 typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
 #define PETSC_DEFAULT (-2)
 typedef const char* KSPType;
@@ -110,10 +113,12 @@ PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatDestroy(Mat* A);
 PetscErrorCode MatGetDiagonal(Mat A, Vec d);                      /* MATOP_GET_DIAGONAL of the shell */
 
-/* Krylov solver on a shell operator.  Without PETSc this is a (diagonally preconditioned, when the shell offers
- * MATOP_GET_DIAGONAL, or PCSHELL-preconditioned) conjugate-gradient iteration for ONE rank -- the operators of the hot
- * path are symmetric positive definite mass matrices; GMRES / block-Jacobi requests are accepted and mapped onto it.
- * With several in-process ranks KSPSolve is not available (a collective cannot be played rank after rank). */
+/* Krylov solver on a shell operator, ONE rank (with several in-process ranks KSPSolve is not available: a collective
+ * cannot be played rank after rank).  KSPGMRES (PETSc's default type, what the reference runs): restarted GMRES(30), left
+ * preconditioning, modified Gram-Schmidt, converged when the preconditioned residual norm falls below
+ * max(rtol |B b|, abstol) -- PETSc's default test.  KSPCG: preconditioned conjugate gradients, same test on the true residual.
+ * Preconditioner B: PCSHELL -> the callback; PCBJACOBI -> the shell's MATOP_COMPAT_PCBJACOBI if it offers one (the Umat
+ * shell: the reference's element blocks); otherwise, and for PCJACOBI, the shell's MATOP_GET_DIAGONAL; PCNONE -> identity. */
 PetscErrorCode KSPCreate(MPI_Comm comm, KSP* ksp);
 PetscErrorCode KSPDestroy(KSP* ksp);
 PetscErrorCode KSPSetOperators(KSP ksp, Mat A, Mat P);
@@ -124,8 +129,10 @@ PetscErrorCode KSPSetFromOptions(KSP ksp);
 PetscErrorCode KSPGetPC(KSP ksp, PC* pc);
 PetscErrorCode KSPSolve(KSP ksp, Vec b, Vec x);
 PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt* its);
+PetscErrorCode KSPGetResidualNorm(KSP ksp, PetscReal* rnorm);
 PetscErrorCode PCSetType(PC pc, PCType type);
 PetscErrorCode PCBJacobiSetTotalBlocks(PC pc, PetscInt blocks, const PetscInt lens[]);
+PetscErrorCode PCApply(PC pc, Vec x, Vec y);                      /* PCSHELL only */
 PetscErrorCode PCShellSetApply(PC pc, PetscErrorCode (*apply)(PC, Vec, Vec));
 PetscErrorCode PCShellSetContext(PC pc, void* ctx);
 PetscErrorCode PCShellGetContext(PC pc, void* ctx);

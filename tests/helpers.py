@@ -66,3 +66,14 @@ def to_cols(engine, a, space):
 def to_np(engine, t, space):
     """engine column-layout device tensor (n, nlev) -> numpy (nlev, n) in the reference numbering."""
     return engine.to_levels(t, space).cpu().numpy()
+
+
+def block_jacobi_reference(A, r, nb):
+    """blockdiag(A)^-1 r with PETSc's PCBJACOBI blocks for PCBJacobiSetTotalBlocks(pc, N / nb, NULL): equal consecutive
+    row blocks of nb rows (eul/HorizSolve.cpp:77-84: nb = 2 p^2, the edges element e owns), dense solves."""
+    A = A.tocsr()
+    z = np.zeros(A.shape[0])
+    for r0 in range(0, A.shape[0], nb):
+        rows = np.arange(r0, r0 + nb)
+        z[rows] = np.linalg.solve(A[rows][:, rows].toarray(), r[rows])
+    return z

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import ROOT, TOL, golden, have_ref_mesh, ref_mesh_dir, rel_l2
+from helpers import ROOT, TOL, block_jacobi_reference, golden, have_ref_mesh, ref_mesh_dir, rel_l2
 
 HOST = os.path.join(ROOT, "mimsem_b200", "host")
 BIN = os.path.join(HOST, "build", "host_apply")
@@ -15,6 +15,26 @@ BIN = os.path.join(HOST, "build", "host_apply")
 
 def _build():
     subprocess.run(["make", "-C", HOST], check=True, stdout=subprocess.DEVNULL)
+
+
+def test_compat_krylov_solver_on_cpu():
+    """KSPSolve of the compatibility layer (GMRES(30) with restarts, CG, the four preconditioner routes) on small dense
+    shell operators: mimsem_b200/host/compat_ksp_check.cpp.  No GPU."""
+    _build()
+    r = subprocess.run([os.path.join(HOST, "build", "compat_ksp_check")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "compat_ksp_check ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("kind,p,ne,nprocs", [(0, 3, 4, 6), (0, 3, 4, 24), (0, 4, 2, 6), (0, 3, 6, 54), (1, 3, 4, 1), (1, 3, 4, 4)])
+def test_block_jacobi_context_tables_on_cpu(kind, p, ne, nprocs):
+    """Host half of the element-block Jacobi preconditioner of the Umat shell (PCBJACOBI, eul/HorizSolve.cpp:77-84): every
+    rank's patch plus copies of the west / south neighbours across the patch boundary -- on another rank of the cubed
+    sphere (across cube seams and inside a face) or at the other end of a periodic box patch; placement checked against
+    the point coordinates: mimsem_b200/host/host_pc_tables_check.cpp.  No GPU."""
+    _build()
+    r = subprocess.run([os.path.join(HOST, "build", "host_pc_tables_check"), str(kind), str(p), str(ne), str(nprocs), "2"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host_pc_tables_check ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_host_library_builds_and_links():
@@ -31,7 +51,7 @@ def _run(tmp_path, g, kind, p, ne, nprocs, nk, meshdir="-"):
     assert r.returncode == 0 and "host_apply ok" in r.stdout, r.stdout + r.stderr
     out = np.fromfile(fout, dtype="<f8")
     N0, N1, N2 = int(g["N0"]), int(g["N1"]), int(g["N2"])
-    sizes = [("Umat", N1), ("Wmat", N2), ("Pmat", N0), ("Pmat_h", N0), ("Uhmat", N1), ("Whmat", N2), ("WtQUmat", N2), ("E21", N2),
+    sizes = [("Umat", N1), ("BJacobi", N1), ("Wmat", N2), ("Pmat", N0), ("Pmat_h", N0), ("Uhmat", N1), ("Whmat", N2), ("WtQUmat", N2), ("E21", N2),
              ("E12", N1), ("E10", N1), ("E01", N0)]
     per_lev = sum(n for _, n in sizes)
     assert out.size == nk * per_lev
@@ -61,6 +81,15 @@ def test_host_classes_vs_reference_golden(tmp_path, from_files):
     for k, xk in (("E21", "x1"), ("E12", "x2"), ("E10", "x0"), ("E01", "x1")):
         A = sp.csr_matrix((g[k + "_data"], g[k + "_indices"], g[k + "_indptr"]))
         assert rel_l2(res[k], (A @ g[xk].T).T) < TOL, k
+    # PCBJACOBI of the Umat shell (one block per element, eul/HorizSolve.cpp:77-84) on six patches: the blocks of the
+    # elements along a patch's west / south boundary carry the far-line terms of an element on ANOTHER rank
+    if have_ref_mesh("sphere", 3, 4, 6):
+        from oracle import mimsem_oracle as mo
+        O = mo.Oracle(ref_mesh_dir("sphere", 3, 4, 6), 6, "sphere", "eul")
+        O.set_thick(g["thick"])
+        for lev in range(3):
+            ref = block_jacobi_reference(O.umat(lev, float(g["scale"]), 1), g["x1"][lev], 2 * 3 * 3)
+            assert rel_l2(res["BJacobi"][lev], ref) < 1e-11, (lev, rel_l2(res["BJacobi"][lev], ref))
 
 
 @pytest.mark.gpu
@@ -81,6 +110,9 @@ def test_host_classes_24_ranks_vs_oracle(tmp_path):
     res = _run(tmp_path, g, 0, 3, 4, 24, nk, str(tmp_path / "mesh"))
     for lev in range(nk):
         assert rel_l2(res["Umat"][lev], O.umat(lev, 1e8, 1) @ g["x1"][lev]) < TOL
+        # element blocks in the np = 24 numbering; patches now also meet INSIDE a cube face
+        ref = block_jacobi_reference(O.umat(lev, 1e8, 1), g["x1"][lev], 2 * 3 * 3)
+        assert rel_l2(res["BJacobi"][lev], ref) < 1e-11, (lev, rel_l2(res["BJacobi"][lev], ref))
         assert rel_l2(res["Uhmat"][lev], O.umat(lev, 1e8, 1, h2=g["h2"][lev], tpow_h=1) @ g["x1"][lev]) < TOL
         assert rel_l2(res["WtQUmat"][lev], O.wtqumat(g["u1"][lev], lev, 1e8) @ g["x1"][lev]) < TOL
         assert rel_l2(res["Pmat"][lev], O.pmat(lev, 1e8) @ g["x0"][lev]) < TOL
@@ -223,9 +255,11 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
             assert rel_l2(wi, spla.spsolve(O.wmat(lev, s, 1).tocsc(), g["x2"][lev])) < TOL, ("WmatInv", lev)
             assert rel_l2(whi, spla.spsolve(O.wmat(lev, s, 1, rho=g["h2b"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < 1e-8, ("WhmatInv", lev)
         assert rel_l2(take(N1), g["y_Umat_ray"][lev]) < TOL, ("Umat_ray", lev)
-    its, err = take(2)
+    its, err, its_diag = take(3)
     assert o == out.size
-    assert 0 < its < 200 and err < 1e-11, (its, err)
+    # GMRES(30) + the element blocks of the periodic box (every west / south neighbour sits at the other end of the same
+    # patch) against GMRES(30) + the diagonal
+    assert 0 < its < its_diag < 200 and err < 1e-11, (its, err, its_diag)
 
 
 def test_host_geom_interp_topog_and_writers_vs_reference(tmp_path):
