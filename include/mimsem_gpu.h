@@ -409,6 +409,10 @@ int mimsem_gpu_dev_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** d_ptr);
 int mimsem_gpu_dev_free(mimsem_gpu_ctx* ctx, void* d_ptr);
 int mimsem_gpu_dev_copy(mimsem_gpu_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
 int mimsem_gpu_dev_sync(mimsem_gpu_ctx* ctx, void* stream);
+/* Page-locked host memory (cudaMallocHost / cudaFreeHost) for the buffers handed to mimsem_gpu_apply_host: from pageable
+ * memory the copies of its pipeline stages cannot overlap each other or the kernels. */
+int mimsem_gpu_host_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** h_ptr);
+int mimsem_gpu_host_free(mimsem_gpu_ctx* ctx, void* h_ptr);
 
 /* number of kernels this library has launched since the context was created */
 int64_t mimsem_gpu_launch_count(const mimsem_gpu_ctx* ctx);

@@ -2222,6 +2222,20 @@ int mimsem_gpu_dev_free(mimsem_gpu_ctx* c, void* d_ptr) {
     CUDA_OK(cudaFree(d_ptr));
     return MIMSEM_OK;
 }
+int mimsem_gpu_host_alloc(mimsem_gpu_ctx* c, int64_t bytes, void** h_ptr) {
+    if (!c || !h_ptr || bytes < 1) return fail(MIMSEM_ERR_ARG, "bad argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaMallocHost(h_ptr, (size_t)bytes));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_host_free(mimsem_gpu_ctx* c, void* h_ptr) {
+    if (!c || !h_ptr) return MIMSEM_OK;
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaFreeHost(h_ptr));
+    return MIMSEM_OK;
+}
 int mimsem_gpu_dev_copy(mimsem_gpu_ctx* c, void* dst, const void* src, int64_t bytes, int kind) {
     if (!c || !dst || !src || bytes < 0 || kind < 0 || kind > 2) return fail(MIMSEM_ERR_ARG, "bad argument");
     int rc = bind_device(c);

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,8 +29,19 @@ struct Patch {
     int pc_n1 = 0, pc_nq = 0;
     unsigned long pc_thick_version = (unsigned long)-1;
     std::vector<double> pc_x, pc_y;
+    // page-locked staging of MimsemMatMultLevels: input, output, coefficient ([nlev][local size] each)
+    double* stage[3] = {NULL, NULL, NULL};
+    size_t stage_cap[3] = {0, 0, 0};
 };
 std::map<Topo*, Patch> g_patches;
+
+// wall time spent inside the device library's host-buffer calls (copies in, kernels, copies out), for MimsemDeviceSeconds
+double g_device_seconds = 0.0;
+struct DeviceTimer {
+    std::chrono::steady_clock::time_point t0;
+    DeviceTimer() : t0(std::chrono::steady_clock::now()) {}
+    ~DeviceTimer() { g_device_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 void die(const char* where) {
     // the reference has no error convention (PETSc codes are dropped everywhere); a device failure here
@@ -276,6 +288,11 @@ int MimsemAttachPatch(Topo* topo, Geom* geom, LagrangeNode* l, LagrangeEdge* e) 
     return 0;
 }
 const char* MimsemLastError(void) { return mimsem_last_error(); }
+double MimsemDeviceSeconds(int reset) {
+    const double t = g_device_seconds;
+    if (reset) g_device_seconds = 0.0;
+    return t;
+}
 int MimsemPCTablesCheck(Topo* topo, Geom* geom, int sizes[6]) {
     PcTables T;
     if (!pc_tables(topo, geom, T)) return 1;
@@ -336,9 +353,12 @@ PetscErrorCode shell_mult(Mat A, Vec x, Vec y) {
     if (s->sout == 2) VecGetArray(y, &ya);
     else VecGetArray(s->yl, &ya);
     // 2. the CUDA kernels (single level: one column)
-    if (mimsem_gpu_apply_host_up(p->ctx, s->op, s->lev, 1, s->scale, s->tpow, s->flags, s->coeff.empty() ? NULL : s->coeff.data(),
-                                 s->u1.empty() ? NULL : s->u1.data(), s->tau, xa, ya))
-        die("mimsem_gpu_apply_host");
+    {
+        DeviceTimer timer;
+        if (mimsem_gpu_apply_host_up(p->ctx, s->op, s->lev, 1, s->scale, s->tpow, s->flags, s->coeff.empty() ? NULL : s->coeff.data(),
+                                     s->u1.empty() ? NULL : s->u1.data(), s->tau, xa, ya))
+            die("mimsem_gpu_apply_host");
+    }
     if (s->sin == 2) VecRestoreArray(x, &xa);
     else VecRestoreArray(s->xl, &xa);
     // 3. sum the partial results of shared DOFs into the global vector
@@ -458,6 +478,74 @@ Patch* patch_of(Topo* topo) {
 }
 
 }  // namespace
+
+// y[k] = Op(level lev0 + k) x[k] for nlev consecutive levels in ONE device call: what the reference writes as
+//   for (kk = 0; kk < nk; kk++) { M1->assemble(kk, SCALE, true); MatMult(M1->M, velx[kk], Mu[kk]); }      (eul/Euler_2.cpp:1427-1456)
+// The ghost refresh and the shared-DOF sum stay PETSc's, level by level; between them all levels cross PCIe and the
+// kernels as one pipelined mimsem_gpu_apply_host call (the shell's own MatMult pays a launch, two copies and a
+// synchronisation per level).  Scale, thickness power, flags (and the operator) are the shell's current ones; coeff[k]:
+// the coefficient of level k in the convention of the class's assemble() (NULL for M1 / M2 / M0 and the incidence shells).
+PetscErrorCode MimsemMatMultLevels(Mat A, int lev0, int nlev, Vec* x, Vec* y, Vec* coeff) {
+    MimsemShell* s = NULL;
+    MatShellGetContext(A, &s);
+    if (!s || nlev < 1 || !x || !y) return 62;   // PETSC_ERR_ARG_WRONG
+    if (!s->u1.empty() || s->op == 21 /* Umat_ray */ || s->op == OP_M2INV || s->op == OP_M2HINV) return 56;
+    const bool need_c = !s->coeff.empty();
+    if (need_c && !coeff) return 62;
+    Topo* topo = s->topo;
+    Patch* p = patch_of(topo);
+    if (s->tpow > 0) sync_thickness(p);
+    const size_t nin = space_size_local(topo, s->sin), nout = space_size_local(topo, s->sout), nc = s->coeff.size();
+    const size_t want[3] = {nin * nlev, nout * nlev, nc * nlev};
+    for (int b = 0; b < 3; b++)
+        if (want[b] > p->stage_cap[b]) {
+            if (p->stage[b]) mimsem_gpu_host_free(p->ctx, p->stage[b]);
+            if (mimsem_gpu_host_alloc(p->ctx, (int64_t)want[b] * 8, (void**)&p->stage[b])) die("mimsem_gpu_host_alloc");
+            p->stage_cap[b] = want[b];
+        }
+    PetscScalar* a;
+    for (int k = 0; k < nlev; k++) {
+        if (s->sin == 2) {
+            VecGetArray(x[k], &a);
+            std::memcpy(p->stage[0] + k * nin, a, 8 * nin);
+            VecRestoreArray(x[k], &a);
+        } else {
+            VecScatter sc = s->sin == 0 ? topo->gtol_0 : topo->gtol_1;
+            VecScatterBegin(sc, x[k], s->xl, INSERT_VALUES, SCATTER_FORWARD);
+            VecScatterEnd(sc, x[k], s->xl, INSERT_VALUES, SCATTER_FORWARD);
+            VecGetArray(s->xl, &a);
+            std::memcpy(p->stage[0] + k * nin, a, 8 * nin);
+            VecRestoreArray(s->xl, &a);
+        }
+        if (need_c) {
+            VecGetArray(coeff[k], &a);
+            std::memcpy(p->stage[2] + k * nc, a, 8 * nc);
+            VecRestoreArray(coeff[k], &a);
+        }
+    }
+    {
+        DeviceTimer timer;
+        if (mimsem_gpu_apply_host_up(p->ctx, s->op, lev0, nlev, s->scale, s->tpow, s->flags, need_c ? p->stage[2] : NULL, NULL, 0.0,
+                                     p->stage[0], p->stage[1]))
+            die("mimsem_gpu_apply_host (all levels)");
+    }
+    for (int k = 0; k < nlev; k++) {
+        if (s->sout == 2) {
+            VecGetArray(y[k], &a);
+            std::memcpy(a, p->stage[1] + k * nout, 8 * nout);
+            VecRestoreArray(y[k], &a);
+        } else {
+            VecGetArray(s->yl, &a);
+            std::memcpy(a, p->stage[1] + k * nout, 8 * nout);
+            VecRestoreArray(s->yl, &a);
+            VecScatter sc = s->sout == 0 ? topo->gtol_0 : topo->gtol_1;
+            VecZeroEntries(y[k]);
+            VecScatterBegin(sc, s->yl, y[k], ADD_VALUES, SCATTER_REVERSE);
+            VecScatterEnd(sc, s->yl, y[k], ADD_VALUES, SCATTER_REVERSE);
+        }
+    }
+    return 0;
+}
 
 PetscErrorCode MimsemPCApplyBJacobi(PC pc, Vec r, Vec z) {
     Mat M = NULL;

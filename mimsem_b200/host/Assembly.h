@@ -313,6 +313,17 @@ class E21mat {
 int MimsemAttachPatch(Topo* topo, Geom* geom, LagrangeNode* l, LagrangeEdge* e);
 // last error text of the device library for the calling thread
 const char* MimsemLastError(void);
+// wall-clock seconds the shells of this process have spent inside the device library (host -> device copies, kernels,
+// device -> host copies) since the last reset: separates the device half of a MatMult from PETSc's scatters around it
+double MimsemDeviceSeconds(int reset);
+
+// All levels of one operator in ONE device call: y[k] = Op(level lev0 + k) x[k], k = 0 .. nlev-1 -- the reference's
+//     for (kk = 0; kk < nk; kk++) { M1->assemble(kk, SCALE, true); MatMult(M1->M, velx[kk], Mu[kk]); }   (eul/Euler_2.cpp:1427-1456)
+// with the levels crossing PCIe and the kernels as one pipelined call (equal to the level-by-level result to rounding).  Scale,
+// thickness power and flags are those of the shell's last assemble(); coeff[k] = the coefficient of level k in the
+// convention of the class's assemble() (Uhmat: 2-form Vec, WtQUmat: ghosted local 1-form, ...; NULL when there is none).
+// Nonzero: not a shell of this library / operator without a batched form (the upwinded ones, Umat_ray, the inverses).
+PetscErrorCode MimsemMatMultLevels(Mat M, int lev0, int nlev, Vec* x, Vec* y, Vec* coeff);
 
 // The reference's preconditioner of its 1-form solves -- PCBJACOBI with one block per element
 // (PCBJacobiSetTotalBlocks(pc, size * nElsX * nElsX, NULL), eul/HorizSolve.cpp:77-84, 791-796) -- for a Umat shell:

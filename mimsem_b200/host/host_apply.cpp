@@ -5,7 +5,8 @@
 //   host_apply <input-dir or -> <kind 0|1> <p> <ne> <nprocs> <nk> <in.bin> <out.bin>
 // in.bin : doubles  thick[nk][N0] x1[nk][N1] x2[nk][N2] x0[nk][N0] h2[nk][N2] u1[nk][N1]   (global numbering)
 // out.bin: doubles  per level: Umat, element-block Jacobi of Umat (the PCBJACOBI of eul/HorizSolve.cpp:77-84 applied to x1),
-//                   Wmat Pmat Pmat_h Uhmat Whmat WtQUmat E21 E12 E10 E01 results
+//                   Wmat Pmat Pmat_h Uhmat Whmat WtQUmat E21 E12 E10 E01 results;
+//                   then Umat, Wmat, Pmat, Uhmat, WtQUmat, E21 of ALL levels in one device call each (MimsemMatMultLevels), [op][lev]
 #include <unistd.h>
 
 #include <cstdio>
@@ -149,6 +150,78 @@ int main(int argc, char** argv) {
         ALL_RANKS(MatMult(k.EtoF->E12, v2[r], w1[r]))                                          dump(w1);
         ALL_RANKS(MatMult(k.NtoE->E10, v0[r], w1[r]))                                          dump(w1);
         ALL_RANKS(MatMult(k.NtoE->E01, v1[r], w0[r]))                                          dump(w0);
+    }
+    // ---- all levels per call: the loop over levels of eul/Euler_2.cpp:1427-1456 as ONE pipelined device call per operator
+    {
+        typedef std::vector<std::vector<Vec> > VV;   // [rank][level]
+        VV X1(np), X2(np), X0(np), H(np), UL(np), Y1(np), Y2(np), Y0(np);
+        for (int r = 0; r < np; r++) {
+            PetscCompatSetRank(r, np);
+            Topo* t = R[r].topo;
+            for (int lev = 0; lev < nk; lev++) {
+                Vec v;
+                VecCreateMPI(MPI_COMM_WORLD, t->n1l, t->nDofs1G, &v); X1[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &v); X2[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n0l, t->nDofs0G, &v); X0[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &v); H[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n1l, t->nDofs1G, &v); Y1[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &v); Y2[r].push_back(v);
+                VecCreateMPI(MPI_COMM_WORLD, t->n0l, t->nDofs0G, &v); Y0[r].push_back(v);
+                VecCreateSeq(MPI_COMM_SELF, t->n1, &v); UL[r].push_back(v);
+            }
+        }
+        auto fill_lev = [&](VV& V, const double* src, long N) {
+            for (int lev = 0; lev < nk; lev++)
+                for (int r = 0; r < np; r++) {
+                    PetscCompatSetRank(r, np);
+                    PetscScalar* a;
+                    PetscInt lo, hi;
+                    VecGetOwnershipRange(V[r][lev], &lo, &hi);
+                    VecGetArray(V[r][lev], &a);
+                    for (int i = lo; i < hi; i++) a[i - lo] = src[lev * N + i];
+                    VecRestoreArray(V[r][lev], &a);
+                }
+        };
+        auto dump_lev = [&](VV& V) {
+            for (int lev = 0; lev < nk; lev++)
+                for (int r = 0; r < np; r++) {
+                    PetscCompatSetRank(r, np);
+                    PetscScalar* a;
+                    PetscInt n;
+                    VecGetLocalSize(V[r][lev], &n);
+                    VecGetArray(V[r][lev], &a);
+                    std::fwrite(a, 8, n, out);
+                    VecRestoreArray(V[r][lev], &a);
+                }
+        };
+        fill_lev(X1, x1, N1);
+        fill_lev(X2, x2, N2);
+        fill_lev(X0, x0, N0);
+        fill_lev(H, h2, N2);
+        for (int lev = 0; lev < nk; lev++) {
+            fill(uv, u1 + (long)lev * N1);
+            for (int r = 0; r < np; r++) {
+                PetscCompatSetRank(r, np);
+                VecScatterBegin(R[r].topo->gtol_1, uv[r], UL[r][lev], INSERT_VALUES, SCATTER_FORWARD);
+                VecScatterEnd(R[r].topo->gtol_1, uv[r], UL[r][lev], INSERT_VALUES, SCATTER_FORWARD);
+            }
+        }
+#define CHECKED(call) if (call) { std::fprintf(stderr, "MimsemMatMultLevels failed: " #call "\n"); return 1; }
+        ALL_RANKS(k.M1->assemble(0, SCALE, true); CHECKED(MimsemMatMultLevels(k.M1->M, 0, nk, X1[r].data(), Y1[r].data(), NULL)))   dump_lev(Y1);
+        ALL_RANKS(k.M2->assemble(0, SCALE, true); CHECKED(MimsemMatMultLevels(k.M2->M, 0, nk, X2[r].data(), Y2[r].data(), NULL)))   dump_lev(Y2);
+        ALL_RANKS(k.M0->assemble(0, SCALE); CHECKED(MimsemMatMultLevels(k.M0->M, 0, nk, X0[r].data(), Y0[r].data(), NULL)))         dump_lev(Y0);
+        ALL_RANKS(k.F->assemble(H[r][0], 0, true, SCALE);
+                  CHECKED(MimsemMatMultLevels(k.F->M, 0, nk, X1[r].data(), Y1[r].data(), H[r].data())))                           dump_lev(Y1);
+        ALL_RANKS(k.K->assemble(UL[r][0], 0, SCALE);
+                  CHECKED(MimsemMatMultLevels(k.K->M, 0, nk, X1[r].data(), Y2[r].data(), UL[r].data())))                          dump_lev(Y2);
+        ALL_RANKS(CHECKED(MimsemMatMultLevels(k.EtoF->E21, 0, nk, X1[r].data(), Y2[r].data(), NULL)))                             dump_lev(Y2);
+        for (int r = 0; r < np; r++) {
+            PetscCompatSetRank(r, np);
+            for (int lev = 0; lev < nk; lev++) {
+                VecDestroy(&X1[r][lev]); VecDestroy(&X2[r][lev]); VecDestroy(&X0[r][lev]); VecDestroy(&H[r][lev]); VecDestroy(&UL[r][lev]);
+                VecDestroy(&Y1[r][lev]); VecDestroy(&Y2[r][lev]); VecDestroy(&Y0[r][lev]);
+            }
+        }
     }
     std::fclose(out);
     for (int r = 0; r < np; r++) {
