@@ -321,6 +321,10 @@ struct MimsemShell {
     double tau = 0.0;            // fac*dt
     Vec xl = NULL, yl = NULL;    // ghosted local work vectors
     Mat mat = NULL;
+    // MatAXPY(this, a, other): the terms added since the last assemble() (the reference adds the Rayleigh friction matrix to
+    // the assembled M1 this way, eul/Euler_2.cpp:1229, 1448); applied with the operator itself in MatMult
+    std::vector<std::pair<double, MimsemShell*> > plus;
+    std::vector<double> plus_tmp;
 };
 
 namespace {
@@ -358,6 +362,17 @@ PetscErrorCode shell_mult(Mat A, Vec x, Vec y) {
         if (mimsem_gpu_apply_host_up(p->ctx, s->op, s->lev, 1, s->scale, s->tpow, s->flags, s->coeff.empty() ? NULL : s->coeff.data(),
                                      s->u1.empty() ? NULL : s->u1.data(), s->tau, xa, ya))
             die("mimsem_gpu_apply_host");
+        // terms added with MatAXPY: same ghosted input, summed into the local result before the one shared-DOF sum
+        const int nloc = space_size_local(topo, s->sout);
+        for (size_t t = 0; t < s->plus.size(); t++) {
+            MimsemShell* o = s->plus[t].second;
+            if (o->tpow > 0) sync_thickness(p);
+            s->plus_tmp.resize(nloc);
+            if (mimsem_gpu_apply_host_up(p->ctx, o->op, o->lev, 1, o->scale, o->tpow, o->flags, o->coeff.empty() ? NULL : o->coeff.data(),
+                                         o->u1.empty() ? NULL : o->u1.data(), o->tau, xa, s->plus_tmp.data()))
+                die("mimsem_gpu_apply_host (MatAXPY term)");
+            for (int i = 0; i < nloc; i++) ya[i] += s->plus[t].first * s->plus_tmp[i];
+        }
     }
     if (s->sin == 2) VecRestoreArray(x, &xa);
     else VecRestoreArray(s->xl, &xa);
@@ -431,6 +446,17 @@ PetscErrorCode shell_pcbjacobi(Mat A, Vec r, Vec z) {
     return 0;
 }
 
+// MatAXPY(Y, a, X, ...) on two shells of this library over the same spaces: Y's MatMult becomes (Op_Y + a Op_X) until Y's
+// next assemble() -- the reference's assemble() starts with MatZeroEntries, which drops what was added
+PetscErrorCode shell_axpy(Mat Y, PetscScalar a, Mat X, MatStructure) {
+    MimsemShell *y = NULL, *x = NULL;
+    MatShellGetContext(Y, &y);
+    MatShellGetContext(X, &x);
+    if (!y || !x || y == x || y->topo != x->topo || y->sin != x->sin || y->sout != x->sout) return 56;
+    y->plus.push_back(std::make_pair((double)a, x));
+    return 0;
+}
+
 MimsemShell* make_shell(Topo* topo, int op, int sin, int sout, Mat* M) {
     MimsemShell* s = new MimsemShell;
     s->topo = topo;
@@ -443,6 +469,7 @@ MimsemShell* make_shell(Topo* topo, int op, int sin, int sout, Mat* M) {
                    space_size_global(topo, sin), s, M);
     MatShellSetOperation(*M, MATOP_MULT, (void (*)(void))shell_mult);
     if (sin == sout && sin != 2) MatShellSetOperation(*M, MATOP_GET_DIAGONAL, (void (*)(void))shell_getdiag);
+    MatShellSetOperation(*M, MATOP_AXPY, (void (*)(void))shell_axpy);
 #ifndef MIMSEM_HAVE_PETSC
     // the compatibility layer's KSP asks the operator itself for the blocks of a PCBJACOBI request (real PETSc: MimsemPCApplyBJacobi)
     if (op == 0) MatShellSetOperation(*M, MATOP_COMPAT_PCBJACOBI, (void (*)(void))shell_pcbjacobi);
@@ -489,7 +516,7 @@ PetscErrorCode MimsemMatMultLevels(Mat A, int lev0, int nlev, Vec* x, Vec* y, Ve
     MimsemShell* s = NULL;
     MatShellGetContext(A, &s);
     if (!s || nlev < 1 || !x || !y) return 62;   // PETSC_ERR_ARG_WRONG
-    if (!s->u1.empty() || s->op == 21 /* Umat_ray */ || s->op == OP_M2INV || s->op == OP_M2HINV) return 56;
+    if (!s->u1.empty() || !s->plus.empty() || s->op == 21 /* Umat_ray */ || s->op == OP_M2INV || s->op == OP_M2HINV) return 56;
     const bool need_c = !s->coeff.empty();
     if (need_c && !coeff) return 62;
     Topo* topo = s->topo;
@@ -589,11 +616,13 @@ Umat::~Umat() {
     if (sho) free_shell(sho, &Mo);
 }
 void Umat::assemble(int lev, double scale, bool vert_scale) {
+    sh->plus.clear();
     sh->lev = lev;
     sh->scale = scale;
     sh->tpow = vert_scale ? 1 : 0;
 }
 void Umat::assemble() {
+    sh->plus.clear();
     sh->lev = 0;
     sh->scale = 1.0;
     sh->tpow = 0;
@@ -878,10 +907,21 @@ Pvec::Pvec(Topo* _topo, Geom* _geom, LagrangeNode* _l) : topo(_topo), geom(_geom
     attach(topo, geom);
     VecCreateSeq(MPI_COMM_SELF, topo->n0, &vl);
     VecCreateMPI(MPI_COMM_WORLD, topo->n0l, topo->nDofs0G, &vg);
+    vg1 = NULL;
+    if (topo->kind == MIMSEM_MESH_BOX) {
+        // box/Assembly.cpp:357-372: the constructor assembles level 0 twice, vg with SCALE and vg1 with scale 1; assemble is private there
+        VecCreateMPI(MPI_COMM_WORLD, topo->n0l, topo->nDofs0G, &vg1);
+        Vec keep = vg;
+        vg = vg1;
+        assemble(0, 1.0);
+        vg = keep;
+        assemble(0, SCALE);
+    }
 }
 Pvec::~Pvec() {
     VecDestroy(&vl);
     VecDestroy(&vg);
+    if (vg1) VecDestroy(&vg1);
 }
 void Pvec::assemble(int lev, double scale) {
     PetscScalar* a;
@@ -1040,6 +1080,124 @@ PtQmat::PtQmat(Topo* _topo, Geom* _geom, LagrangeNode* _l) : topo(_topo), geom(_
 }
 PtQmat::~PtQmat() { MatDestroy(&M); }
 void PtQmat::assemble() {}
+
+namespace {
+
+// ghosted local copy (Geom's quadrature-point numbering) of component c of a global quadrature-point vector with
+// ncomp interleaved components per point
+void quad_values_local(Geom* geom, Vec x, int ncomp, int c, std::vector<double>& out) {
+    // global index of component c of local point i: ncomp * loc0[i] + c (eul/Assembly.cpp, UtQmat::assemble: inds_0x = 2 inds_0 + 0)
+    std::vector<PetscInt> idx(geom->n0);
+    for (int i = 0; i < geom->n0; i++) idx[i] = ncomp * geom->loc0[i] + c;
+    IS isg, isl;
+    Vec tmp;
+    VecScatter sc;
+    ISCreateGeneral(MPI_COMM_WORLD, geom->n0, idx.data(), PETSC_COPY_VALUES, &isg);
+    ISCreateStride(MPI_COMM_SELF, geom->n0, 0, 1, &isl);
+    VecCreateSeq(MPI_COMM_SELF, geom->n0, &tmp);
+    VecScatterCreate(x, isg, tmp, isl, &sc);
+    VecScatterBegin(sc, x, tmp, INSERT_VALUES, SCATTER_FORWARD);
+    VecScatterEnd(sc, x, tmp, INSERT_VALUES, SCATTER_FORWARD);
+    PetscScalar* xa;
+    VecGetArray(tmp, &xa);
+    out.assign(xa, xa + geom->n0);
+    VecRestoreArray(tmp, &xa);
+    VecScatterDestroy(&sc);
+    ISDestroy(&isg);
+    ISDestroy(&isl);
+    VecDestroy(&tmp);
+}
+
+// eul/Assembly.cpp, WtQmat::assemble: M = sum over elements of W^T diag(w_q); faces are element-interior (no ghosts)
+PetscErrorCode wtq_mult(Mat A, Vec x, Vec y) {
+    WtQmat* self;
+    MatShellGetContext(A, &self);
+    Topo* topo = self->topo;
+    Geom* geom = self->geom;
+    const int mp1 = geom->quad->n + 1, mp12 = mp1 * mp1;
+    std::vector<double> xl;
+    quad_values_local(geom, x, 1, 0, xl);
+    M2_j_xy_i W(self->e);
+    PetscScalar* ya;
+    VecZeroEntries(y);
+    VecGetArray(y, &ya);
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            const int* iq = geom->elInds0_l(ex, ey);
+            const int* i2 = topo->elInds2_l(ex, ey);
+            for (int j = 0; j < W.nDofsJ; j++) {
+                double s = 0.0;
+                for (int q = 0; q < mp12; q++) s += W.A[q * W.nDofsJ + j] * geom->quad->w[q % mp1] * geom->quad->w[q / mp1] * xl[iq[q]];
+                ya[i2[j]] += s;
+            }
+        }
+    VecRestoreArray(y, &ya);
+    return 0;
+}
+
+// eul/Assembly.cpp, UtQmat::assemble: x-edges take U^T diag(w_q) (J00 u_x + J10 u_y), y-edges V^T diag(w_q) (J01 u_x + J11 u_y)
+PetscErrorCode utq_mult(Mat A, Vec x, Vec y) {
+    UtQmat* self;
+    MatShellGetContext(A, &self);
+    Topo* topo = self->topo;
+    Geom* geom = self->geom;
+    const int mp1 = geom->quad->n + 1, mp12 = mp1 * mp1;
+    std::vector<double> ux, uy;
+    quad_values_local(geom, x, 2, 0, ux);
+    quad_values_local(geom, x, 2, 1, uy);
+    M1x_j_xy_i U(self->l, self->e);
+    M1y_j_xy_i V(self->l, self->e);
+    Vec yv;
+    VecCreateSeq(MPI_COMM_SELF, topo->n1, &yv);
+    VecZeroEntries(yv);
+    PetscScalar* ya;
+    VecGetArray(yv, &ya);
+    std::vector<double> fa(mp12), fb(mp12);
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            const int ei = ey * topo->nElsX + ex;
+            const int* iq = geom->elInds0_l(ex, ey);
+            const int* ix = topo->elInds1x_l(ex, ey);
+            const int* iy = topo->elInds1y_l(ex, ey);
+            for (int q = 0; q < mp12; q++) {
+                const double w = geom->quad->w[q % mp1] * geom->quad->w[q / mp1];
+                double** J = geom->J[ei][q];
+                fa[q] = w * (J[0][0] * ux[iq[q]] + J[1][0] * uy[iq[q]]);
+                fb[q] = w * (J[0][1] * ux[iq[q]] + J[1][1] * uy[iq[q]]);
+            }
+            for (int j = 0; j < U.nDofsJ; j++) {
+                double sx = 0.0, sy = 0.0;
+                for (int q = 0; q < mp12; q++) {
+                    sx += U.A[q * U.nDofsJ + j] * fa[q];
+                    sy += V.A[q * V.nDofsJ + j] * fb[q];
+                }
+                ya[ix[j]] += sx;
+                ya[iy[j]] += sy;
+            }
+        }
+    VecRestoreArray(yv, &ya);
+    VecZeroEntries(y);
+    VecScatterBegin(topo->gtol_1, yv, y, ADD_VALUES, SCATTER_REVERSE);
+    VecScatterEnd(topo->gtol_1, yv, y, ADD_VALUES, SCATTER_REVERSE);
+    VecDestroy(&yv);
+    return 0;
+}
+
+}  // namespace
+
+WtQmat::WtQmat(Topo* _topo, Geom* _geom, LagrangeEdge* _e) : topo(_topo), geom(_geom), e(_e) {
+    MatCreateShell(MPI_COMM_WORLD, topo->n2l, geom->n0l, topo->nDofs2G, geom->nDofs0G, this, &M);
+    MatShellSetOperation(M, MATOP_MULT, (void (*)(void))wtq_mult);
+}
+WtQmat::~WtQmat() { MatDestroy(&M); }
+void WtQmat::assemble() {}
+
+UtQmat::UtQmat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e) : topo(_topo), geom(_geom), l(_l), e(_e) {
+    MatCreateShell(MPI_COMM_WORLD, topo->n1l, 2 * geom->n0l, topo->nDofs1G, 2 * geom->nDofs0G, this, &M);
+    MatShellSetOperation(M, MATOP_MULT, (void (*)(void))utq_mult);
+}
+UtQmat::~UtQmat() { MatDestroy(&M); }
+void UtQmat::assemble() {}
 
 E10mat::E10mat(Topo* _topo) : topo(_topo) {
     sh10 = make_shell(topo, OP_INC + MIMSEM_E10, 0, 1, &E10);

@@ -230,6 +230,7 @@ class Pvec {
         Topo* topo; Geom* geom; LagrangeNode* l;
         Vec vl;
         Vec vg;
+        Vec vg1;                                           // box/Assembly.h:69: level 0 with scale 1, built once (box only)
         void assemble(int lev, double scale);              // eul/Assembly.cpp:602-628
 };
 class Phvec {
@@ -252,6 +253,28 @@ class PtQmat {
         void assemble();                                   // eul/Assembly.cpp:758-800: a no-op here, the shell is matrix-free
     private:
         Vec xl, yl;
+};
+
+// quadrature-point values -> 2-form: y2 = W^T Q x (start-up only: the initial density / pressure fields,
+// eul/Euler_2.cpp:493, 535); host loop                                              eul/Assembly.h (WtQmat)
+class WtQmat {
+    public:
+        WtQmat(Topo* _topo, Geom* _geom, LagrangeEdge* _e);
+        ~WtQmat();
+        Topo* topo; Geom* geom; LagrangeEdge* e;
+        Mat M;
+        void assemble();                                   // a no-op here, the shell is matrix-free
+};
+
+// quadrature-point vector values (two interleaved Cartesian-tangent components per point) -> 1-form:
+// y1 = [U V]^T Q J^T u (start-up only: the initial velocity, eul/Euler_2.cpp:432); host loop    eul/Assembly.h (UtQmat)
+class UtQmat {
+    public:
+        UtQmat(Topo* _topo, Geom* _geom, LagrangeNode* _l, LagrangeEdge* _e);
+        ~UtQmat();
+        Topo* topo; Geom* geom; LagrangeNode* l; LagrangeEdge* e;
+        Mat M;
+        void assemble();
 };
 
 // matrix-free twins: the action of the 1-form mass matrix (optionally weighted by a 2-form) on a ghosted local

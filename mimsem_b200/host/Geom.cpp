@@ -344,3 +344,28 @@ void Geom::write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale) {
     std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.vec", fieldname, lev, tstep);
     view_to(h, filename, true);
 }
+
+void Geom::writeVertToHoriz(Vec* vecs, char* fieldname, int tstep, int nv) {
+    const int n2e = topo->elOrd * topo->elOrd;
+    std::vector<Vec> hvecs(nv);
+    for (int kk = 0; kk < nv; kk++) {
+        VecCreateMPI(MPI_COMM_WORLD, topo->n2l, topo->nDofs2G, &hvecs[kk]);
+        VecZeroEntries(hvecs[kk]);
+    }
+    for (int ey = 0; ey < topo->nElsX; ey++)
+        for (int ex = 0; ex < topo->nElsX; ex++) {
+            const int* inds2 = topo->elInds2_l(ex, ey);
+            PetscScalar *vArray, *hArray;
+            VecGetArray(vecs[ey * topo->nElsX + ex], &vArray);
+            for (int kk = 0; kk < nv; kk++) {
+                VecGetArray(hvecs[kk], &hArray);
+                for (int ii = 0; ii < n2e; ii++) hArray[inds2[ii]] += vArray[kk * n2e + ii];
+                VecRestoreArray(hvecs[kk], &hArray);
+            }
+            VecRestoreArray(vecs[ey * topo->nElsX + ex], &vArray);
+        }
+    for (int kk = 0; kk < nv; kk++) {
+        write2(hvecs[kk], fieldname, tstep, kk, false);
+        VecDestroy(&hvecs[kk]);
+    }
+}

@@ -49,6 +49,9 @@ class Geom {
         void write0(Vec q, char* fieldname, int tstep, int lev);
         void write1(Vec u, char* fieldname, int tstep, int lev);
         void write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale);
+        // per-element vertical vectors (L2Vecs::vz: vecs[element][level p^2 + i]) relabelled to one 2-form per level and
+        // written with write2, levels 0 .. nv-1                                        eul/Geom.cpp:633-679
+        void writeVertToHoriz(Vec* vecs, char* fieldname, int tstep, int nv);
         int* elInds0_l(int ex, int ey);
         int* elInds0_g(int ex, int ey);
         // flat copies for the device engine

@@ -6,8 +6,10 @@
 //   host_apply_twins <p> <ne> <nk> <in.bin> <out.bin>
 // in.bin : doubles  thick[nk][N0] x1[nk][N1] x1b[nk][N1] x2[nk][N2] h2[nk][N2] h2b[nk][N2] u1[nk][N1] ex2[nk][N2]  (global numbering)
 // out.bin: doubles  per level: Uvec::assemble, Uvec::assemble_hu (4 terms), UtQWmat, Pvec, Phvec, WmatInv, WhmatInv (rho = h2b),
-//                   Umat_ray (exner = ex2[lev], exner_s = ex2[0], dt = 300, as eul/Euler_2.cpp:1218-1229 calls it);
-//                   then { its, |x - x_true| / |x_true|, its with PCJACOBI } of the box solve
+//                   Umat_ray (exner = ex2[lev], exner_s = ex2[0], dt = 300, as eul/Euler_2.cpp:1218-1229 calls it),
+//                   Umat + Umat_ray through MatAXPY(M1->M, 1.0, M1ray->M, DIFFERENT_NONZERO_PATTERN) (eul/Euler_2.cpp:1229), and the
+//                   plain Umat again after the next assemble() (which drops the added term);
+//                   then { its, |x - x_true| / |x_true|, its with PCJACOBI } of the box solve and the box Pvec's vg, vg1 [N0 box each]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +35,7 @@ int main(int argc, char** argv) {
     std::vector<double> in = read_all(argv[4]);
     const int np = 6;
     struct Rank { Topo* topo; Geom* geom; GaussLobatto* quad; LagrangeNode* node; LagrangeEdge* edge;
-                  Uvec* m1; UtQWmat* Rh; Pvec* m0; Phvec* m0h; WmatInv* Wi; WhmatInv* Whi; Umat_ray* ray; };
+                  Uvec* m1; UtQWmat* Rh; Pvec* m0; Phvec* m0h; WmatInv* Wi; WhmatInv* Whi; Umat_ray* ray; Umat* M1; };
     std::vector<Rank> R(np);
     for (int r = 0; r < np; r++) {
         PetscCompatSetRank(r, np);
@@ -70,6 +72,7 @@ int main(int argc, char** argv) {
         k.Wi = new WmatInv(k.topo, k.geom, k.edge);
         k.Whi = new WhmatInv(k.topo, k.geom, k.edge);
         k.ray = new Umat_ray(k.topo, k.geom, k.node, k.edge);
+        k.M1 = new Umat(k.topo, k.geom, k.node, k.edge);
     }
     FILE* out = std::fopen(argv[5], "wb");
     if (!out) { std::perror(argv[5]); return 2; }
@@ -150,6 +153,12 @@ int main(int argc, char** argv) {
         ALL_RANKS(k.Whi->assemble(ghb[r], lev, SCALE); MatMult(k.Whi->M, g2[r], w2[r]))                     dump(2);
         ALL_RANKS(k.ray->assemble(lev, SCALE, 300.0, gex[r], gex0[r]))
         ALL_RANKS(MatMult(k.ray->M, g1[r], w1[r]))                                                          dump(1);
+        // eul/Euler_2.cpp:1226-1231
+        ALL_RANKS(k.M1->assemble(lev, SCALE, true); k.ray->assemble(lev, SCALE, 300.0, gex[r], gex0[r]);
+                  if (MatAXPY(k.M1->M, 1.0, k.ray->M, DIFFERENT_NONZERO_PATTERN)) return 1;
+                  MatAssemblyBegin(k.M1->M, MAT_FINAL_ASSEMBLY); MatAssemblyEnd(k.M1->M, MAT_FINAL_ASSEMBLY))
+        ALL_RANKS(MatMult(k.M1->M, g1[r], w1[r]))                                                           dump(1);
+        ALL_RANKS(k.M1->assemble(lev, SCALE, true); MatMult(k.M1->M, g1[r], w1[r]))                         dump(1);
     }
     // ---- KSPSolve on the box: x -> b = M1 x -> KSPSolve(M1, b) recovers x (GMRES + block Jacobi requested, as the reference does)
     {
@@ -159,7 +168,7 @@ int main(int argc, char** argv) {
         Geom* bg = new Geom(bt, 2);
         for (int lev = 0; lev < 2; lev++)
             for (int i = 0; i < bg->n0; i++) {
-                bg->thick[lev][i] = 750.0 * (1.0 + 0.05 * ((i * 7 + lev) % 5));
+                bg->thick[lev][i] = 750.0 * (1.0 + 0.05 * ((bg->loc0[i] * 7 + lev) % 5));   // a function of the GLOBAL point
                 bg->thickInv[lev][i] = 1.0 / bg->thick[lev][i];
             }
         bg->thick_version++;
@@ -204,6 +213,17 @@ int main(int argc, char** argv) {
         const double res[3] = {(double)its, en / xn, (double)its_diag};
         std::fwrite(res, 8, 3, out);
         KSPDestroy(&ksp1);
+        {   // box/Assembly.cpp:357-372: the Pvec constructor assembles vg (SCALE) and vg1 (scale 1) at level 0
+            Pvec* m0 = new Pvec(bt, bg, n);
+            PetscScalar* pa;
+            VecGetArray(m0->vg, &pa);
+            std::fwrite(pa, 8, bt->n0l, out);
+            VecRestoreArray(m0->vg, &pa);
+            VecGetArray(m0->vg1, &pa);
+            std::fwrite(pa, 8, bt->n0l, out);
+            VecRestoreArray(m0->vg1, &pa);
+            delete m0;
+        }
         VecDestroy(&x); VecDestroy(&b); VecDestroy(&s);
         delete M1; delete e; delete n; delete q; delete bg; delete bt;
     }

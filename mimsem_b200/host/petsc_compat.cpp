@@ -53,6 +53,7 @@ struct _mimsem_Mat {
     PetscErrorCode (*destroy)(Mat);
     PetscErrorCode (*getdiag)(Mat, Vec);
     PetscErrorCode (*pcbjacobi)(Mat, Vec, Vec);
+    PetscErrorCode (*axpy)(Mat, PetscScalar, Mat, MatStructure);
 };
 struct _mimsem_PC {
     const char* type;
@@ -211,6 +212,7 @@ PetscErrorCode MatCreateShell(MPI_Comm, PetscInt, PetscInt, PetscInt, PetscInt, 
     (*A)->destroy = NULL;
     (*A)->getdiag = NULL;
     (*A)->pcbjacobi = NULL;
+    (*A)->axpy = NULL;
     return 0;
 }
 PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void)) {
@@ -218,11 +220,15 @@ PetscErrorCode MatShellSetOperation(Mat A, MatOperation op, void (*f)(void)) {
     else if (op == MATOP_DESTROY) A->destroy = (PetscErrorCode(*)(Mat))f;
     else if (op == MATOP_GET_DIAGONAL) A->getdiag = (PetscErrorCode(*)(Mat, Vec))f;
     else if (op == MATOP_COMPAT_PCBJACOBI) A->pcbjacobi = (PetscErrorCode(*)(Mat, Vec, Vec))f;
+    else if (op == MATOP_AXPY) A->axpy = (PetscErrorCode(*)(Mat, PetscScalar, Mat, MatStructure))f;
     else return 56;   /* PETSC_ERR_SUP */
     return 0;
 }
 PetscErrorCode MatShellGetContext(Mat A, void* ctx) { *(void**)ctx = A->ctx; return 0; }
 PetscErrorCode MatMult(Mat A, Vec x, Vec y) { return A->mult ? A->mult(A, x, y) : 56; }
+PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure str) { return Y->axpy ? Y->axpy(Y, a, X, str) : 56; }
+PetscErrorCode MatAssemblyBegin(Mat, MatAssemblyType) { return 0; }
+PetscErrorCode MatAssemblyEnd(Mat, MatAssemblyType) { return 0; }
 PetscErrorCode MatDestroy(Mat* A) {
     if (*A) {
         if ((*A)->destroy) (*A)->destroy(*A);

@@ -31,10 +31,12 @@ typedef int MPI_Comm;
 typedef enum { NOT_SET_VALUES = 0, INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
 typedef enum { SCATTER_FORWARD = 0, SCATTER_REVERSE = 1 } ScatterMode;
 typedef enum { PETSC_COPY_VALUES = 0, PETSC_OWN_POINTER = 1, PETSC_USE_POINTER = 2 } PetscCopyMode;
-typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_GET_DIAGONAL = 17, MATOP_DESTROY = 60,
+typedef enum { MATOP_MULT = 3, MATOP_MULT_TRANSPOSE = 5, MATOP_GET_DIAGONAL = 17, MATOP_AXPY = 43, MATOP_DESTROY = 60,
                /* compat only: z = blockdiag(A)^-1 r for a PCBJACOBI request on a shell (PETSc cuts the blocks out of an
                   assembled matrix; a shell that can apply them itself offers this operation) */
                MATOP_COMPAT_PCBJACOBI = 1000 } MatOperation;
+typedef enum { DIFFERENT_NONZERO_PATTERN = 0, SUBSET_NONZERO_PATTERN = 1, SAME_NONZERO_PATTERN = 2 } MatStructure;
+typedef enum { MAT_FLUSH_ASSEMBLY = 1, MAT_FINAL_ASSEMBLY = 0 } MatAssemblyType;
 typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
 #define PETSC_DEFAULT (-2)
 typedef const char* KSPType;
@@ -112,6 +114,9 @@ PetscErrorCode MatShellGetContext(Mat A, void* ctx);
 PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PetscErrorCode MatDestroy(Mat* A);
 PetscErrorCode MatGetDiagonal(Mat A, Vec d);                      /* MATOP_GET_DIAGONAL of the shell */
+PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure str);   /* Y += a X: MATOP_AXPY of the shell Y */
+PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType type);     /* shells have nothing to assemble */
+PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType type);
 
 /* Krylov solver on a shell operator, ONE rank (with several in-process ranks KSPSolve is not available: a collective
  * cannot be played rank after rank).  KSPGMRES (PETSc's default type, what the reference runs): restarted GMRES(30), left

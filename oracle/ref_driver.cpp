@@ -262,7 +262,10 @@ enum {
     /* eul/: operators of the horizontal-vorticity / vertical-momentum terms */
     OP_UT_MAT = 14, OP_UT_MAT_H = 15, OP_UTQWMAT = 16, OP_WTQDUDZ = 17,
     /* eul/: Rayleigh friction; c2 = Exner 2-form of the level, c1 = the LEVEL-0 Exner 2-form (a second global 2-form) */
-    OP_UMAT_RAY = 18
+    OP_UMAT_RAY = 18,
+    /* eul/: quadrature-point projections of the initial conditions (eul/Euler_2.cpp:432, 493, 535; eul/Assembly.cpp WtQmat, UtQmat,
+       PtQmat): columns = quadrature points of Geom (UtQmat: two interleaved components per point) */
+    OP_WTQMAT = 19, OP_UTQMAT = 20, OP_PTQMAT = 21
 };
 
 /*
@@ -372,6 +375,18 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
                 A->assemble(lev, scale, dt, v2, v2b);
                 keep[rk] = A->M->t; delete A; break;
             }
+            case OP_WTQMAT: {
+                WtQmat* A = new WtQmat(topo, geom, o.edge); /* ctor assembles */
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_UTQMAT: {
+                UtQmat* A = new UtQmat(topo, geom, o.node, o.edge);
+                keep[rk] = A->M->t; delete A; break;
+            }
+            case OP_PTQMAT: {
+                PtQmat* A = new PtQmat(topo, geom, o.node);
+                keep[rk] = A->M->t; delete A; break;
+            }
 #elif defined(REF_SRC)
             case OP_UMAT: {
                 Umat* A = new Umat(topo, geom, o.node, o.edge); /* ctor assembles */
@@ -471,6 +486,11 @@ long ref_assemble(void* hv, int op, int lev, double scale, int flag, const doubl
         case OP_E12: nrows = t->nDofs1G; ncols = t->nDofs2G; break;
         case OP_E10: nrows = t->nDofs1G; ncols = t->nDofs0G; break;
         case OP_E01: nrows = t->nDofs0G; ncols = t->nDofs1G; break;
+#if defined(REF_EUL)
+        case OP_WTQMAT: nrows = t->nDofs2G; ncols = h->r[0].geom->nDofs0G; break;
+        case OP_UTQMAT: nrows = t->nDofs1G; ncols = 2L * h->r[0].geom->nDofs0G; break;
+        case OP_PTQMAT: nrows = t->nDofs0G; ncols = h->r[0].geom->nDofs0G; break;
+#endif
     }
     std::vector<std::vector<ShimTriplet>*> lists;
     for (int rk = 0; rk < h->nranks; rk++) lists.push_back(&keep[rk]);

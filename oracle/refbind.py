@@ -16,7 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(HERE, "_ref")
 
 OPS = dict(Umat=0, Wmat=1, Pmat=2, Uhmat=3, WtQUmat=4, E10=5, E01=6, E21=7, E12=8, Pmat_h=9,
-           Whmat=10, RotMat=11, Phmat_up=12, RotMat_up=13, Ut_mat=14, Ut_mat_h=15, UtQWmat=16, WtQdUdz_mat=17, Umat_ray=18)
+           Whmat=10, RotMat=11, Phmat_up=12, RotMat_up=13, Ut_mat=14, Ut_mat_h=15, UtQWmat=16, WtQdUdz_mat=17, Umat_ray=18,
+           WtQmat=19, UtQmat=20, PtQmat=21)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -37,6 +37,36 @@ def test_block_jacobi_context_tables_on_cpu(kind, p, ne, nprocs):
     assert r.returncode == 0 and "host_pc_tables_check ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("p,ne", [(3, 4), (4, 2)])
+def test_quadrature_projections_vs_reference_golden(tmp_path, p, ne):
+    """WtQmat, UtQmat, PtQmat of the mirror (host loops; the reference initialises its fields with them, eul/Euler_2.cpp:432,
+    493, 535) on six emulated ranks against vectors of the reference's own classes (tests/golden/make_golden_quadproj.py), and
+    Geom::writeVertToHoriz (eul/Geom.cpp:633-679) against write2, file for file.  No GPU."""
+    _build()
+    g = golden("quadproj_eul_sphere_p%d_ne%d.npz" % (p, ne))
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([g["xq"], g["uq"]]).astype("<f8").tofile(fin)
+    r = subprocess.run([os.path.join(HOST, "build", "host_quadproj_check"), str(p), str(ne), fin, fout, str(tmp_path)], capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0 and "host_quadproj_check ok" in r.stdout, r.stdout + r.stderr
+    out = np.fromfile(fout, dtype="<f8")
+    N0, N1, N2 = int(g["N0"]), int(g["N1"]), int(g["N2"])
+    assert out.size == N0 + N1 + N2 + 1
+    assert rel_l2(out[:N2], g["y_WtQmat"]) < 1e-14
+    assert rel_l2(out[N2:N2 + N1], g["y_UtQmat"]) < 1e-14
+    assert rel_l2(out[N2 + N1:N2 + N1 + N0], g["y_PtQmat"]) < 1e-14
+    assert out[-1] == 1.0, "writeVertToHoriz and write2 wrote different files"
+
+
+def test_element_tabulations_row_view_on_cpu():
+    """src/ and box/ callers index the element tabulations as rows (double** A); the mirror keeps both views in every object
+    (host/ElMats.h, -DMIMSEM_ELMATS_ROWS): mimsem_b200/host/elmats_rows_check.cpp, compiled with the flag against the
+    library compiled without.  No GPU."""
+    _build()
+    r = subprocess.run([os.path.join(HOST, "build", "elmats_rows_check")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "elmats_rows_check ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_host_library_builds_and_links():
     _build()
     assert os.path.exists(BIN) and os.path.exists(os.path.join(ROOT, "mimsem_b200", "libmimsem_host.so"))
@@ -191,24 +221,36 @@ PETSC_HEADERS = ("petsc.h", "petscis.h", "petscvec.h", "petscmat.h", "petscksp.h
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "eul")), reason="the reference sources are only mounted in the build container")
-@pytest.mark.parametrize("variant,caller", [("eul", "HorizSolve.cpp"), ("box", "HorizSolve.cpp")])
-def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, variant, caller):
+@pytest.mark.parametrize("variant,caller,decls_only", [("eul", "HorizSolve.cpp", False), ("box", "HorizSolve.cpp", False),
+                                                       ("eul", "L2Vecs.cpp", False), ("eul", "Euler_2.cpp", True),
+                                                       ("eul", "VertSolve.cpp", True), ("eul", "VertOps.cpp", True),
+                                                       ("eul", "UMJS14.cpp", True), ("box", "Euler_2.cpp", True),
+                                                       ("box", "VertSolve.cpp", True), ("box", "VertOps.cpp", True),
+                                                       ("box", "Bubble.cpp", True)])
+def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, variant, caller, decls_only):
     """The drop-in claim, mechanically: the reference's own caller translation unit -- eul/HorizSolve.cpp (constructs Umat,
     Wmat, Pmat, Uhmat, WtQUmat, RotMat, Ut_mat, UtQWmat, Whmat, E10mat, E21mat, Uvec, Wvec, PtQmat; calls assemble(...) /
     assemble_hu(...), reads ->M, ->vl, ->vg, KSPSolve on M1 and M0) and box/HorizSolve.cpp (Umat / Wmat with M and Mo, the
     box signatures of Uvec::assemble_hu and Wvec::assemble_K) -- compiles UNCHANGED against mimsem_b200/host/*.h (the
     reference's other headers stay the reference's), and every symbol it needs from the mirrored classes and from the
     PETSc subset is defined by libmimsem_host.so.  The sources are reached through symbolic links in a scratch directory
-    (a quoted #include looks beside the including file first); nothing is copied."""
+    (a quoted #include looks beside the including file first); nothing is copied.
+    decls_only: eul/Euler_2.cpp (constructs WtQmat, UtQmat, Umat_ray; MatAXPY of the friction matrix into M1->M; Geom::
+    writeVertToHoriz), eul/VertSolve.cpp and the driver eul/UMJS14.cpp also build the vertical solver's ASSEMBLED SeqAIJ
+    matrices -- PETSc proper, outside the path and not part of the compatibility layer: for these the PETSc headers
+    forward to tests/petsc_decls_only.h (prototypes without bodies) and the symbol check covers the mirrored classes.
+    box/ (like src/) keeps its element tabulations as rows (double** A, box/ElMats.h): its callers are compiled with
+    -DMIMSEM_ELMATS_ROWS, which names the row view of the mirror's tabulations `A` (host/ElMats.h)."""
     _build()
     src = os.path.join(REFERENCE, variant)
     for f in os.listdir(src):
         if f not in MIRRORED and (f.endswith(".h") or f == caller):
             os.symlink(os.path.join(src, f), str(tmp_path / f))
-    for f in PETSC_HEADERS:
-        (tmp_path / f).write_text('#include "petsc_compat.h"\n')
+    for f in PETSC_HEADERS + ("petscsnes.h",):
+        (tmp_path / f).write_text('#include "%s"\n' % ("petsc_decls_only.h" if decls_only else "petsc_compat.h"))
     obj = str(tmp_path / "caller.o")
-    r = subprocess.run(["g++", "-std=c++11", "-w", "-c", "-I", str(tmp_path), "-I", HOST, str(tmp_path / caller), "-o", obj],
+    r = subprocess.run(["g++", "-std=c++11", "-w", "-c"] + (["-DMIMSEM_ELMATS_ROWS"] if variant == "box" else []) +
+                       ["-I", str(tmp_path), "-I", HOST, "-I", os.path.join(ROOT, "tests"), str(tmp_path / caller), "-o", obj],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     undef = subprocess.run(["nm", "-u", "-C", obj], capture_output=True, text=True, check=True).stdout
@@ -217,10 +259,12 @@ def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, varian
     have = subprocess.run(["nm", "-D", "-C", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
     defined = {l.split(None, 2)[2].strip() for l in have.splitlines() if len(l.split(None, 2)) == 3}
     classes = ("Umat", "Wmat", "Pmat", "Uhmat", "Whmat", "WtQUmat", "RotMat", "Ut_mat", "UtQWmat", "WtQdUdz_mat", "E10mat", "E21mat", "Uvec",
-               "Wvec", "PtQmat", "Pvec", "Phvec", "WmatInv", "WhmatInv", "Topo", "Geom", "GaussLobatto", "LagrangeNode", "LagrangeEdge")
-    petsc = ("Vec", "Mat", "KSP", "PC", "IS", "MPI_Comm_")
-    mine = [s for s in need if s.split("::")[0] in classes or (s.split("(")[0].startswith(petsc) and "::" not in s.split("(")[0])]
-    assert len(mine) > 20, need                      # the caller really uses the mirrored surface
+               "Wvec", "PtQmat", "WtQmat", "UtQmat", "Umat_ray", "Pvec", "Phvec", "WmatInv", "WhmatInv", "Topo", "Geom", "GaussLobatto", "LagrangeNode", "LagrangeEdge",
+               "M1x_j_xy_i", "M1y_j_xy_i", "M2_j_xy_i", "M0_j_xy_i", "Wii")
+    petsc = () if decls_only else ("Vec", "Mat", "KSP", "PC", "IS", "MPI_Comm_")
+    mine = [s for s in need if s.split("::")[0] in classes or (petsc and s.split("(")[0].startswith(petsc) and "::" not in s.split("(")[0])]
+    floor = {"HorizSolve.cpp": 20, "Euler_2.cpp": 20}.get(caller, 2)
+    assert len(mine) > floor, need                   # the caller really uses the mirrored surface
     missing = [s for s in mine if s not in defined]
     assert not missing, missing
 
@@ -264,7 +308,18 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
             assert rel_l2(wi, spla.spsolve(O.wmat(lev, s, 1).tocsc(), g["x2"][lev])) < TOL, ("WmatInv", lev)
             assert rel_l2(whi, spla.spsolve(O.wmat(lev, s, 1, rho=g["h2b"][lev], tpow_rho=1).tocsc(), g["x2"][lev])) < 1e-8, ("WhmatInv", lev)
         assert rel_l2(take(N1), g["y_Umat_ray"][lev]) < TOL, ("Umat_ray", lev)
+        # MatAXPY(M1->M, 1.0, M1ray->M, ...) as eul/Euler_2.cpp:1229 adds the friction to the mass matrix; the next assemble() drops it
+        assert rel_l2(take(N1), g["y_Umat_vs1"][lev] + g["y_Umat_ray"][lev]) < TOL, ("Umat + Umat_ray (MatAXPY)", lev)
+        assert rel_l2(take(N1), g["y_Umat_vs1"][lev]) < TOL, ("Umat after re-assembly", lev)
     its, err, its_diag = take(3)
+    # the box Pvec (box/Assembly.cpp:357-372): vg = SCALE vg1 = the diagonal 0-form mass matrix of level 0
+    nb0 = (3 * 4) ** 2
+    vg, vg1 = take(nb0), take(nb0)
+    assert rel_l2(vg, 1.0e8 * vg1) < 1e-15 and vg1.min() > 0.0
+    if have_ref_mesh("box", 3, 4, 1):
+        Ob = mo.Oracle(ref_mesh_dir("box", 3, 4, 1), 1, "box", "box")
+        Ob.set_thick(np.array([750.0 * (1.0 + 0.05 * ((np.arange(nb0) * 7 + lev) % 5)) for lev in range(2)]))
+        assert rel_l2(vg1, Ob.pmat(0, 1.0).diagonal()) < TOL, "box Pvec::vg1"
     assert o == out.size
     # GMRES(30) + the element blocks of the periodic box (every west / south neighbour sits at the other end of the same
     # patch) against GMRES(30) + the diagonal
