@@ -409,6 +409,16 @@ int mimsem_gpu_dev_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** d_ptr);
 int mimsem_gpu_dev_free(mimsem_gpu_ctx* ctx, void* d_ptr);
 int mimsem_gpu_dev_copy(mimsem_gpu_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
 int mimsem_gpu_dev_sync(mimsem_gpu_ctx* ctx, void* stream);
+/* Streams and CUDA graphs for hosts that do not link the CUDA runtime themselves: a non-blocking stream of the context's
+ * device; capture of everything subsequently launched on it (thread-local capture mode; warm the sequence up once before,
+ * first calls allocate) into an executable graph -- the launch-bound inner loop of a time step, and the form in which a
+ * burst of fused launches is issued (see "Bursts" above) --, its replay on a stream, and their release. */
+int mimsem_gpu_stream_create(mimsem_gpu_ctx* ctx, void** stream);
+int mimsem_gpu_stream_destroy(mimsem_gpu_ctx* ctx, void* stream);
+int mimsem_gpu_graph_begin(mimsem_gpu_ctx* ctx, void* stream);
+int mimsem_gpu_graph_end(mimsem_gpu_ctx* ctx, void* stream, void** graph_exec);
+int mimsem_gpu_graph_launch(mimsem_gpu_ctx* ctx, void* graph_exec, void* stream);
+int mimsem_gpu_graph_destroy(mimsem_gpu_ctx* ctx, void* graph_exec);
 /* Page-locked host memory (cudaMallocHost / cudaFreeHost) for the buffers handed to mimsem_gpu_apply_host: from pageable
  * memory the copies of its pipeline stages cannot overlap each other or the kernels. */
 int mimsem_gpu_host_alloc(mimsem_gpu_ctx* ctx, int64_t bytes, void** h_ptr);

@@ -2222,6 +2222,56 @@ int mimsem_gpu_dev_free(mimsem_gpu_ctx* c, void* d_ptr) {
     CUDA_OK(cudaFree(d_ptr));
     return MIMSEM_OK;
 }
+int mimsem_gpu_stream_create(mimsem_gpu_ctx* c, void** stream) {
+    if (!c || !stream) return fail(MIMSEM_ERR_ARG, "null argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    cudaStream_t st;
+    CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = (void*)st;
+    return MIMSEM_OK;
+}
+int mimsem_gpu_stream_destroy(mimsem_gpu_ctx* c, void* stream) {
+    if (!c || !stream) return MIMSEM_OK;
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamDestroy((cudaStream_t)stream));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_graph_begin(mimsem_gpu_ctx* c, void* stream) {
+    if (!c || !stream) return fail(MIMSEM_ERR_ARG, "capture needs a stream of its own (mimsem_gpu_stream_create)");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_graph_end(mimsem_gpu_ctx* c, void* stream, void** graph_exec) {
+    if (!c || !stream || !graph_exec) return fail(MIMSEM_ERR_ARG, "null argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    cudaGraph_t g = nullptr;
+    CUDA_OK(cudaStreamEndCapture((cudaStream_t)stream, &g));
+    cudaGraphExec_t ex = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    CUDA_OK(e);
+    *graph_exec = (void*)ex;
+    return MIMSEM_OK;
+}
+int mimsem_gpu_graph_launch(mimsem_gpu_ctx* c, void* graph_exec, void* stream) {
+    if (!c || !graph_exec) return fail(MIMSEM_ERR_ARG, "null argument");
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return MIMSEM_OK;
+}
+int mimsem_gpu_graph_destroy(mimsem_gpu_ctx* c, void* graph_exec) {
+    if (!c || !graph_exec) return MIMSEM_OK;
+    int rc = bind_device(c);
+    if (rc) return rc;
+    CUDA_OK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return MIMSEM_OK;
+}
 int mimsem_gpu_host_alloc(mimsem_gpu_ctx* c, int64_t bytes, void** h_ptr) {
     if (!c || !h_ptr || bytes < 1) return fail(MIMSEM_ERR_ARG, "bad argument");
     int rc = bind_device(c);

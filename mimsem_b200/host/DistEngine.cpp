@@ -82,7 +82,7 @@ void DistEngine::check(int rc, const char* what) {
 }
 
 DistEngine::DistEngine(const GlobalMesh& mesh, const double* thick, int nk, Comm* comm, int device, int max_levels)
-    : mesh_(mesh), comm_(comm), part_(NULL), ctx_(NULL), device_(device), base_(NULL), d_err_(NULL), d_red_areas_(NULL), d_red_seq_(NULL) {
+    : mesh_(mesh), comm_(comm), part_(NULL), ctx_(NULL), device_(device), base_(NULL), d_err_(NULL), stream_(NULL), d_red_areas_(NULL), d_red_seq_(NULL) {
     static_assert(sizeof(PeerDesc) == 48, "descriptor layout of csrc/engine.cuh");
     std::memset(plan_, 0, sizeof(plan_));
     const int rank = comm->rank, world = comm->world;
@@ -251,6 +251,7 @@ void DistEngine::setup_p2p() {
 DistEngine::~DistEngine() {
     if (ctx_) {
         mimsem_gpu_dev_sync(ctx_, NULL);
+        if (stream_) mimsem_gpu_stream_destroy(ctx_, stream_);
         if (comm_ && comm_->world > 1) comm_->barrier();   // nobody unmaps a buffer a peer may still write
         for (size_t i = 0; i < keep_.size(); i++) mimsem_gpu_dev_free(ctx_, keep_[i]);
         for (int s = 0; s < 5; s++) {
@@ -312,21 +313,76 @@ void DistEngine::exchange(double* d_field, int space, int nlev, bool ext) {
     check(mimsem_gpu_halo_pull(ctx_, pl.npull, pl.d_pull, nlev, nlev, NBUF, d_field, pl.d_epochs + 1, d_err_, NULL), "mimsem_gpu_halo_pull");
 }
 
-void DistEngine::apply_M1(const double* d_x, double* d_y, int nlev, double scale, int tpow, int lev0, int flags) {
+void DistEngine::apply_M1(const double* d_x, double* d_y, int nlev, double scale, int tpow, int lev0, int flags, void* stream) {
     if (comm_->world == 1) {
-        check(mimsem_gpu_apply_M1(ctx_, lev0, nlev, nlev, scale, tpow, flags, d_x, d_y, NULL), "mimsem_gpu_apply_M1");
+        check(mimsem_gpu_apply_M1(ctx_, lev0, nlev, nlev, scale, tpow, flags, d_x, d_y, stream), "mimsem_gpu_apply_M1");
         return;
     }
     const Plan& pl = plan_[1];
     if (nlev % 2 || nlev > 64 || nlev > nk_max_) {   // the fused launch needs even nlev <= 64: refresh, then apply
+        if (stream) throw std::runtime_error("DistEngine::apply_M1: only the fused launch runs on a caller's stream");
         exchange(const_cast<double*>(d_x), 1, nlev);
         check(mimsem_gpu_apply_M1(ctx_, lev0, nlev, nlev, scale, tpow, flags, d_x, d_y, NULL), "mimsem_gpu_apply_M1");
         return;
     }
     const int push_ctas = std::max(1, std::min(148, pl.push_rows / 16));
     check(mimsem_gpu_apply_M1_halo(ctx_, lev0, nlev, nlev, scale, tpow, flags, d_x, d_y, d_x, 0, pl.npush, pl.d_push, pl.npull, pl.d_pull,
-                                   (const double*)pl.inbox, pl.stride, NBUF, push_ctas, pl.d_epochs, d_err_, NULL),
+                                   (const double*)pl.inbox, pl.stride, NBUF, push_ctas, pl.d_epochs, d_err_, stream),
           "mimsem_gpu_apply_M1_halo");
+}
+
+struct DistEngine::Burst {
+    void* graph;
+};
+
+DistEngine::Burst* DistEngine::capture_burst_M1(const std::vector<const double*>& xs, const std::vector<double*>& ys, int nsteps, int nlev,
+                                                 double scale, int tpow, int lev0) {
+    const int n = (int)xs.size();
+    if (n < 1 || ys.size() != xs.size() || nsteps < 1 || nsteps > 32) throw std::runtime_error("DistEngine::capture_burst_M1: bad arguments");
+    const bool fused = comm_->world > 1 && !(nlev % 2 || nlev > 64 || nlev > nk_max_);
+    if (comm_->world > 1 && !fused) throw std::runtime_error("DistEngine::capture_burst_M1: needs the fused launch (even nlev <= 64)");
+    if (!stream_) check(mimsem_gpu_stream_create(ctx_, &stream_), "mimsem_gpu_stream_create");
+    check(mimsem_gpu_set_option(ctx_, "pdl_independent", 1), "pdl_independent");
+    // warm-up outside the capture (first calls allocate counters; every pair is touched), in ordinary epochs
+    sync();
+    for (int i = 0; i < 2 * n; i++) apply_M1(xs[i % n], ys[i % n], nlev, scale, tpow, lev0, 0, stream_);
+    check(mimsem_gpu_dev_sync(ctx_, stream_), "mimsem_gpu_dev_sync");
+    if (comm_->world > 1) comm_->barrier();
+    Burst* b = new Burst;
+    b->graph = NULL;
+    check(mimsem_gpu_graph_begin(ctx_, stream_), "mimsem_gpu_graph_begin");
+    int rc = 0;
+    try {
+        for (int i = 0; i < nsteps; i++) {
+            if (fused && nsteps > 1) {
+                // launch i of the burst works on epoch *epoch + 1 + i with its own counter slot (include/mimsem_gpu.h, "Bursts")
+                check(mimsem_gpu_set_option(ctx_, "halo_burst_len", nsteps), "halo_burst_len");
+                check(mimsem_gpu_set_option(ctx_, "halo_burst_pos", i), "halo_burst_pos");
+            }
+            apply_M1(xs[i % n], ys[i % n], nlev, scale, tpow, lev0, 0, stream_);
+        }
+    } catch (...) {
+        rc = 1;
+    }
+    mimsem_gpu_set_option(ctx_, "halo_burst_len", 0);
+    mimsem_gpu_set_option(ctx_, "halo_burst_pos", 0);
+    // the programmatic edges are part of the graph now; launches outside it are dependent unless the caller says otherwise
+    mimsem_gpu_set_option(ctx_, "pdl_independent", 0);
+    const int rc_end = mimsem_gpu_graph_end(ctx_, stream_, &b->graph);
+    if (rc || rc_end) {
+        delete b;
+        throw std::runtime_error(std::string("DistEngine::capture_burst_M1: capture failed: ") + mimsem_last_error());
+    }
+    return b;
+}
+
+void DistEngine::replay(Burst* b) { check(mimsem_gpu_graph_launch(ctx_, b->graph, stream_), "mimsem_gpu_graph_launch"); }
+
+void DistEngine::free_burst(Burst* b) {
+    if (!b) return;
+    mimsem_gpu_dev_sync(ctx_, NULL);
+    mimsem_gpu_graph_destroy(ctx_, b->graph);
+    delete b;
 }
 
 void DistEngine::apply(const std::string& op, double* x, double* c, double* y, int nlev, double scale, int tpow, int lev0, double* u1,

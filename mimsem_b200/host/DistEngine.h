@@ -58,7 +58,17 @@ public:
     // the space (1- and 2-forms), what the operators that sum over the elements around a node read (M0h, E01, M0h_up)
     void exchange(double* d_field, int space, int nlev, bool ext = false);
     // y = M1 x with the ghost refresh of x fused into the launch (mimsem_gpu_apply_M1_halo), collective
-    void apply_M1(const double* d_x, double* d_y, int nlev, double scale, int tpow, int lev0 = 0, int flags = 0);
+    void apply_M1(const double* d_x, double* d_y, int nlev, double scale, int tpow, int lev0 = 0, int flags = 0, void* stream = NULL);
+    // A burst: nsteps consecutive M1 applies, step i on field pair i % n (n = xs.size(); the pairs must be independent
+    // fields), captured in ONE CUDA graph.  The launches carry programmatic dependencies and work on consecutive epochs of
+    // the ghost hand-over, so that a step starts while the previous one drains and the boundary rows of step i + 1 travel
+    // while step i computes (engine option "pdl_independent" is on during the capture only: the edges live in the graph).
+    // Collective: every rank captures and replays the same bursts in the same order.  replay() only enqueues (sync() waits).
+    struct Burst;
+    Burst* capture_burst_M1(const std::vector<const double*>& xs, const std::vector<double*>& ys, int nsteps, int nlev, double scale,
+                            int tpow, int lev0 = 0);
+    void replay(Burst* burst);
+    void free_burst(Burst* burst);
     // the other operators of the path: ghost refresh of the inputs that need one, then the local apply.
     // op: "M1", "M1h", "M2", "M2h", "K", "UtQW", "E21", "E12", "M0", "M0h", "E10", "E01", "R", "R_up", "M0h_up" -- all fifteen
     // operators of the path; d_u1 / tau: advecting velocity and time scale of the upwinded ones
@@ -92,6 +102,7 @@ private:
     std::vector<char*> peer_base_;
     std::vector<void*> keep_;           // device row lists
     int* d_err_;
+    void* stream_;                      // stream of the captured bursts
     void* d_red_areas_;
     void* d_red_seq_;
     static const int MAXP = 16, NBUF = 3;

@@ -2,6 +2,9 @@
 // files.  Every rank applies the partitioned operators to its element block with zeroed ghost rows (so the ghost
 // refresh is exercised); rank 0 gathers the owned rows and compares them BITWISE with a one-GPU apply on the whole mesh.
 //   for r in 0 1; do MIMSEM_RANK=$r MIMSEM_WORLD=2 build/host_dist_check sphere 3 6 30 /tmp/rdv & done; wait
+// A sixth argument "time" adds a timing of the M1 apply (stream order and as bursts of 16 launches) on that mesh and prints
+// one JSON line (for the benchmark shape: sphere 4 48 60).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -54,6 +57,7 @@ int main(int argc, char** argv) {
     const int p = std::atoi(argv[2]), ne = std::atoi(argv[3]), nk = std::atoi(argv[4]);
     const int rank = std::atoi(getenv("MIMSEM_RANK") ? getenv("MIMSEM_RANK") : "0");
     const int world = std::atoi(getenv("MIMSEM_WORLD") ? getenv("MIMSEM_WORLD") : "1");
+    const bool timing = argc > 6 && std::string(argv[6]) == "time";   // timing only: the parity checks run on the small meshes
     int failures = 0;
     try {
         GlobalMesh mesh;
@@ -76,7 +80,7 @@ int main(int argc, char** argv) {
         FileComm comm(argv[5], rank, world);
         DistEngine eng(mesh, thick.data(), nk, &comm, rank);
         SelfComm self;
-        DistEngine* one = rank == 0 ? new DistEngine(mesh, thick.data(), nk, &self, 0) : NULL;
+        DistEngine* one = (rank == 0 && !timing) ? new DistEngine(mesh, thick.data(), nk, &self, 0) : NULL;
         // all fifteen operators of the path (the set tests/mp_check.py runs through parallel.py)
         struct Case { const char* op; int sin, sout, sc; const std::vector<double>* x; const std::vector<double>* c; int tpow; bool up; };
         const Case cases[] = {{"M1", 1, 1, -1, &x1, NULL, 1, false},   {"M1h", 1, 1, 2, &x1, &h2, 2, false}, {"K", 1, 2, 1, &x1, &u1, 2, false},
@@ -110,7 +114,7 @@ int main(int argc, char** argv) {
             if (du) e.free_field(du);
             e.free_field(dy);
         };
-        for (size_t ci = 0; ci < sizeof(cases) / sizeof(cases[0]); ci++) {
+        for (size_t ci = 0; ci < sizeof(cases) / sizeof(cases[0]) && !timing; ci++) {
             std::vector<double> yg, ys;
             run(eng, cases[ci], yg);
             gather_sum(comm, yg);
@@ -122,7 +126,7 @@ int main(int argc, char** argv) {
             }
         }
         // partitioned solve: b = M1 x, then M1^-1 b recovers x; every rank stops at the same iteration
-        {
+        if (!timing) {
             double* dx = eng.alloc_field(1, nk);
             double* db = eng.alloc_field(1, nk);
             double* ds = eng.alloc_field(1, nk);
@@ -150,6 +154,79 @@ int main(int argc, char** argv) {
             eng.free_field(dx);
             eng.free_field(db);
             eng.free_field(ds);
+        }
+        // bursts: six launches on two independent field pairs in one CUDA graph (programmatic dependencies between the
+        // launches, consecutive epochs of the ghost hand-over), replayed three times; every pair bitwise equal to one GPU
+        if (nk % 2 == 0) {
+            const std::vector<double> x1b = pseudo_random((size_t)nk * mesh.N1, 9, -1, 1);
+            const std::vector<double>* src[2] = {&x1, &x1b};
+            std::vector<const double*> xs;
+            std::vector<double*> ys;
+            for (int i = 0; i < 2; i++) {
+                double* dx = eng.alloc_field(1, nk);
+                std::vector<double> own((size_t)nk * mesh.N1, 0.0);   // ghost rows zero: they must come over NVLink
+                const std::vector<int64_t>& ids = eng.part().gids(1);
+                for (int r = 0; r < eng.part().n_owned(1); r++)
+                    for (int k = 0; k < nk; k++) own[(size_t)k * mesh.N1 + ids[r]] = (*src[i])[(size_t)k * mesh.N1 + ids[r]];
+                eng.scatter_from_global(own.data(), 1, nk, dx);
+                xs.push_back(dx);
+                ys.push_back(eng.alloc_field(1, nk));
+            }
+            DistEngine::Burst* burst = eng.capture_burst_M1(xs, ys, 6, nk, 1.0e8, 1);
+            for (int rep = 0; rep < 3; rep++) eng.replay(burst);
+            eng.sync();
+            for (int i = 0; i < 2 && !timing; i++) {
+                std::vector<double> yg((size_t)nk * mesh.N1, 0.0);
+                eng.owned_to_global(ys[i], 1, nk, yg.data());
+                gather_sum(comm, yg);
+                if (rank == 0) {
+                    double* dx = one->alloc_field(1, nk);
+                    double* dy = one->alloc_field(1, nk);
+                    one->scatter_from_global(src[i]->data(), 1, nk, dx);
+                    one->apply_M1(dx, dy, nk, 1.0e8, 1);
+                    one->sync();
+                    std::vector<double> y1((size_t)nk * mesh.N1, 0.0);
+                    one->owned_to_global(dy, 1, nk, y1.data());
+                    const bool same = std::memcmp(yg.data(), y1.data(), yg.size() * 8) == 0;
+                    std::printf("burst of 6 x M1, field pair %d, on %d GPUs vs 1 GPU: %s\n", i, world, same ? "bitwise equal" : "DIFFERENT");
+                    if (!same) failures++;
+                    one->free_field(dx);
+                    one->free_field(dy);
+                }
+            }
+            if (timing) {
+                // stream order (every launch waits for the one before) against bursts of 16 launches on three field pairs
+                double* dx3 = eng.alloc_field(1, nk);
+                eng.scatter_from_global(x1.data(), 1, nk, dx3);
+                xs.push_back(dx3);
+                ys.push_back(eng.alloc_field(1, nk));
+                auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+                const int steps = 320;
+                eng.sync(); comm.barrier();
+                double t0 = now();
+                for (int i = 0; i < steps; i++) eng.apply_M1(xs[i % 3], ys[i % 3], nk, 1.0e8, 1);
+                eng.sync();
+                double t_stream = now() - t0;
+                DistEngine::Burst* b16 = eng.capture_burst_M1(xs, ys, 16, nk, 1.0e8, 1);
+                for (int i = 0; i < 3; i++) eng.replay(b16);
+                eng.sync(); comm.barrier();
+                t0 = now();
+                for (int i = 0; i < steps / 16; i++) eng.replay(b16);
+                eng.sync();
+                double t_burst = now() - t0;
+                double tt[2] = {t_stream, t_burst};
+                std::vector<double> all(2 * world);
+                comm.allgather(tt, 16, all.data());
+                for (int q = 0; q < world; q++) { t_stream = std::max(t_stream, all[2 * q]); t_burst = std::max(t_burst, all[2 * q + 1]); }
+                if (rank == 0)
+                    std::printf("{\"host\": \"C++ DistEngine, %d plain processes\", \"mesh\": \"%s p=%d ne=%d nk=%d\", \"steps\": %d, "
+                                "\"stream_order_us_per_step\": %.2f, \"burst16_us_per_step\": %.2f, \"stream_order_gdofs\": %.1f, \"burst16_gdofs\": %.1f}\n",
+                                world, argv[1], p, ne, nk, steps, t_stream / steps * 1e6, t_burst / steps * 1e6,
+                                (double)mesh.N1 * nk * steps / t_stream / 1e9, (double)mesh.N1 * nk * steps / t_burst / 1e9);
+                eng.free_burst(b16);
+            }
+            eng.free_burst(burst);
+            for (size_t i = 0; i < xs.size(); i++) { eng.free_field(const_cast<double*>(xs[i])); eng.free_field(ys[i]); }
         }
         if (eng.halo_error()) {
             std::printf("rank %d: a ghost refresh timed out\n", rank);

@@ -79,6 +79,12 @@ SIGNATURES = {
     "mimsem_gpu_apply_M1ray": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "mimsem_gpu_dev_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "mimsem_gpu_dev_free": (C.c_int, [_vp, _vp]),
+    "mimsem_gpu_stream_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "mimsem_gpu_stream_destroy": (C.c_int, [_vp, _vp]),
+    "mimsem_gpu_graph_begin": (C.c_int, [_vp, _vp]),
+    "mimsem_gpu_graph_end": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "mimsem_gpu_graph_launch": (C.c_int, [_vp, _vp, _vp]),
+    "mimsem_gpu_graph_destroy": (C.c_int, [_vp, _vp]),
     "mimsem_gpu_host_alloc": (C.c_int, [_vp, C.c_int64, C.POINTER(_vp)]),
     "mimsem_gpu_host_free": (C.c_int, [_vp, _vp]),
     "mimsem_gpu_dev_copy": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int]),

@@ -636,7 +636,7 @@ def test_multi_gpu_partitioned_apply():
 
 def test_multi_gpu_cpp_host_layer(tmp_path):
     """N>1 without Python on the data or the control path: the C++ host layer (mimsem_b200/host/DistEngine, Partition) as N
-    plain processes with a file rendezvous; all fifteen operators and the partitioned solve, bitwise equal to one GPU
+    plain processes with a file rendezvous; all fifteen operators, the partitioned solve and bursts of fused M1 launches, bitwise equal to one GPU
     (mimsem_b200/host/host_dist_check.cpp)."""
     import os
     import subprocess
