@@ -634,6 +634,21 @@ def test_multi_gpu_partitioned_apply():
         assert r.returncode == 0 and "MP_CHECK OK" in r.stdout, (ll, r.stdout[-2000:] + r.stderr[-2000:])
 
 
+def test_cpp_host_layer_one_process(tmp_path):
+    """The C++ host layer (DistEngine) as ONE process on one GPU: the same program as the multi-GPU check with a world of one
+    -- every operator and the solve through DistEngine::apply / solve_M1 against a second engine, and a burst of M1 launches
+    captured into a CUDA graph through the C ABI's stream / graph helpers (mimsem_gpu_stream_create, _graph_begin / _end /
+    _launch) and replayed."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "mimsem_b200", "host", "build", "host_dist_check")
+    r = subprocess.run([exe, "sphere", "3", "4", "30", str(tmp_path)], env=dict(os.environ, MIMSEM_RANK="0", MIMSEM_WORLD="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "HOST_DIST_CHECK OK" in r.stdout and "burst of 6 x M1, field pair 1" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_multi_gpu_cpp_host_layer(tmp_path):
     """N>1 without Python on the data or the control path: the C++ host layer (mimsem_b200/host/DistEngine, Partition) as N
     plain processes with a file rendezvous; all fifteen operators, the partitioned solve and bursts of fused M1 launches, bitwise equal to one GPU
