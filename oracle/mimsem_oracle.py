@@ -523,6 +523,57 @@ class Oracle:
         (eul/Geom.cpp:392-406), i.e. the transpose of WtQdUdz_mat."""
         return self.wtqdudz_mat(u1, scale).T.tocsr()
 
+    # ---- quadrature-point projections of the initial fields (columns: Geom's global quadrature points) ----
+    def _elq_global(self, r):
+        """Geom::elInds0_g for every element of rank r (eul/Geom.cpp:813-825): global ids of its (m+1)^2 quadrature points."""
+        t = self.topos[r]
+        m, ne = self.m, t.nElsX
+        nxq = m * ne
+        out = np.zeros((ne * ne, (m + 1) ** 2), dtype=np.int64)
+        for ey in range(ne):
+            for ex in range(ne):
+                loc = np.array([(ey * m + iy) * (nxq + 1) + ex * m + ix for iy in range(m + 1) for ix in range(m + 1)])
+                out[ey * ne + ex] = self.locq[r][loc]
+        return out
+
+    def _nq_global(self):
+        return int(max(int(lq.max()) for lq in self.locq)) + 1
+
+    def wtqmat(self):
+        """WtQmat::assemble (eul/Assembly.cpp:707-751): W^T diag(w_q) per element, rows = faces, columns = quadrature points."""
+        W, Q = self.em["W"], self.em["Q"]
+        trip = []
+        blk = (W * Q[:, None]).T                                  # [face j][point q]
+        for r in range(self.nprocs):
+            e2 = self.inds[r][3]
+            self._add(e2, self._elq_global(r), np.broadcast_to(blk, (e2.shape[0],) + blk.shape).copy(), trip)
+        return self._csr(trip, (self.N2, self._nq_global()))
+
+    def ptqmat(self):
+        """PtQmat::assemble (eul/Assembly.cpp:766-808): P^T diag(w_q det_q) per element, rows = nodes."""
+        P, Q = self.em["P"], self.em["Q"]
+        trip = []
+        for r in range(self.nprocs):
+            e0 = self.inds[r][0]
+            c = Q[None, :] * self.det[r]
+            self._add(e0, self._elq_global(r), np.einsum("qj,eq->ejq", P, c), trip)
+        return self._csr(trip, (self.N0, self._nq_global()))
+
+    def utqmat(self):
+        """UtQmat::assemble (eul/Assembly.cpp:824-902): x-edges U^T diag(w_q) (J00 u_x + J10 u_y), y-edges V^T diag(w_q) (J01 u_x +
+        J11 u_y); columns 2 q + c, the two components of a point interleaved."""
+        U, V, Q = self.em["U"], self.em["V"], self.em["Q"]
+        trip = []
+        for r in range(self.nprocs):
+            J = self.J[r]
+            _, e1x, e1y, _ = self.inds[r]
+            q = self._elq_global(r)
+            for rows, T, a in ((e1x, U, 0), (e1y, V, 1)):
+                for comp in (0, 1):
+                    c = Q[None, :] * J[:, :, comp, a]             # J[comp][a]: Qaa = J00, Qab = J10 (x-edges); Qba = J01, Qbb = J11
+                    self._add(rows, 2 * q + comp, np.einsum("qj,eq->ejq", T, c), trip)
+        return self._csr(trip, (self.N1, 2 * self._nq_global()))
+
     def e10(self):
         """E10mat::E10mat, eul/Assembly.cpp:1102-1162 (INSERT_VALUES); returns (E10, E01 = -E10^T)."""
         p = self.p

@@ -74,6 +74,18 @@ def test_oracle_rayleigh_friction_vs_golden(fname, p, ne):
 
 
 @needs_mesh
+@pytest.mark.parametrize("p,ne", [(3, 4), (4, 2)])
+def test_oracle_quadrature_projections_vs_golden(p, ne):
+    """WtQmat, UtQmat, PtQmat (eul/Assembly.cpp:707-751, 824-902, 766-808): the numpy restatement against vectors of the
+    reference's own classes (tests/golden/make_golden_quadproj.py)."""
+    g = golden("quadproj_eul_sphere_p%d_ne%d.npz" % (p, ne))
+    O = mo.Oracle(ref_mesh_dir("sphere", p, ne, 6), 6, "sphere", "eul")
+    assert rel_l2(O.wtqmat() @ g["xq"], g["y_WtQmat"]) < 1e-14
+    assert rel_l2(O.utqmat() @ g["uq"], g["y_UtQmat"]) < 1e-14
+    assert rel_l2(O.ptqmat() @ g["xq"], g["y_PtQmat"]) < 1e-14
+
+
+@needs_mesh
 def test_oracle_src_vs_golden():
     g = golden("ops_src_sphere_p3_ne4.npz")
     O = mo.Oracle(ref_mesh_dir("sphere", 3, 4, 6), 6, "sphere", "src")
