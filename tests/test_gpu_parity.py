@@ -642,6 +642,7 @@ def test_cpp_host_layer_one_process(tmp_path):
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "mimsem_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     exe = os.path.join(root, "mimsem_b200", "host", "build", "host_dist_check")
     r = subprocess.run([exe, "sphere", "3", "4", "30", str(tmp_path)], env=dict(os.environ, MIMSEM_RANK="0", MIMSEM_WORLD="1"),
                        capture_output=True, text=True, timeout=300)
@@ -660,6 +661,7 @@ def test_multi_gpu_cpp_host_layer(tmp_path):
     if n < 2:
         pytest.skip("needs >= 2 GPUs (the partition itself is compared with parallel.py on CPU: tests/test_partition.py)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "mimsem_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     exe = os.path.join(root, "mimsem_b200", "host", "build", "host_dist_check")
     for cfg in (["sphere", "3", "6", "30"], ["box", "3", "6", "40"]):
         rdv = tmp_path / ("rdv_" + cfg[0])
