@@ -236,6 +236,18 @@ void view_to(Vec v, const char* name, bool binary) {
 }
 }  // namespace
 
+// lev < 0: the src/ forms (no levels: no thickness factor, file names without the level; src/Geom.cpp:326-520)
+void Geom::write0(Vec q, char* fieldname, int tstep) { write0(q, fieldname, tstep, -1); }
+void Geom::write1(Vec u, char* fieldname, int tstep) { write1(u, fieldname, tstep, -1); }
+void Geom::write2(Vec h, char* fieldname, int tstep) { write2(h, fieldname, tstep, -1, false); }
+
+namespace {
+void field_file(char* out, size_t n, const char* fieldname, const char* comp, int lev, int tstep, const char* ext) {
+    if (lev >= 0) std::snprintf(out, n, "output/%s%s_%.3u_%.4u.%s", fieldname, comp, lev, tstep, ext);
+    else std::snprintf(out, n, "output/%s%s_%.4u.%s", fieldname, comp, tstep, ext);
+}
+}  // namespace
+
 void Geom::write0(Vec q, char* fieldname, int tstep, int lev) {
     const int mp1 = quad->n + 1, mp12 = mp1 * mp1;
     char filename[200];
@@ -254,14 +266,14 @@ void Geom::write0(Vec q, char* fieldname, int tstep, int lev) {
             for (int ii = 0; ii < mp12; ii++) {
                 double val;
                 interp0(ex, ey, ii % mp1, ii / mp1, qArray, &val);
-                qxArray[inds0[ii]] = val / thick[lev][inds0[ii]];   // piecewise constant in the vertical
+                qxArray[inds0[ii]] = lev >= 0 ? val / thick[lev][inds0[ii]] : val;   // piecewise constant in the vertical
             }
         }
     VecRestoreArray(ql, &qArray);
     VecRestoreArray(qxl, &qxArray);
     VecScatterBegin(gtol_0, qxl, qxg, INSERT_VALUES, SCATTER_REVERSE);
     VecScatterEnd(gtol_0, qxl, qxg, INSERT_VALUES, SCATTER_REVERSE);
-    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.dat", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "", lev, tstep, "dat");
     view_to(qxg, filename, false);
     VecDestroy(&ql);
     VecDestroy(&qxl);
@@ -288,8 +300,8 @@ void Geom::write1(Vec u, char* fieldname, int tstep, int lev) {
             for (int ii = 0; ii < mp12; ii++) {
                 double val[2];
                 interp1_g(ex, ey, ii % mp1, ii / mp1, uArray, val);
-                uxArray[inds0[ii]] = val[0] / thick[lev][inds0[ii]];
-                vxArray[inds0[ii]] = val[1] / thick[lev][inds0[ii]];
+                uxArray[inds0[ii]] = lev >= 0 ? val[0] / thick[lev][inds0[ii]] : val[0];
+                vxArray[inds0[ii]] = lev >= 0 ? val[1] / thick[lev][inds0[ii]] : val[1];
             }
         }
     VecRestoreArray(uxl, &uxArray);
@@ -298,18 +310,18 @@ void Geom::write1(Vec u, char* fieldname, int tstep, int lev) {
     VecZeroEntries(uxg);
     VecScatterBegin(gtol_0, uxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
     VecScatterEnd(gtol_0, uxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
-    std::snprintf(filename, sizeof filename, "output/%s_x_%.3u_%.4u.dat", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "_x", lev, tstep, "dat");
     view_to(uxg, filename, false);
     VecZeroEntries(uxg);
     VecScatterBegin(gtol_0, vxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
     VecScatterEnd(gtol_0, vxl, uxg, INSERT_VALUES, SCATTER_REVERSE);
-    std::snprintf(filename, sizeof filename, "output/%s_y_%.3u_%.4u.dat", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "_y", lev, tstep, "dat");
     view_to(uxg, filename, false);
     VecDestroy(&ul);
     VecDestroy(&uxl);
     VecDestroy(&vxl);
     VecDestroy(&uxg);
-    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.vec", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "", lev, tstep, "vec");
     view_to(u, filename, true);   // also the vector itself
 }
 
@@ -329,7 +341,7 @@ void Geom::write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale) {
             for (int ii = 0; ii < mp12; ii++) {
                 double val;
                 interp2_g(ex, ey, ii % mp1, ii / mp1, hArray, &val);
-                if (vert_scale) val /= thick[lev][inds0[ii]];
+                if (vert_scale && lev >= 0) val /= thick[lev][inds0[ii]];
                 hxArray[inds0[ii]] = val;
             }
         }
@@ -337,11 +349,11 @@ void Geom::write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale) {
     VecRestoreArray(hxl, &hxArray);
     VecScatterBegin(gtol_0, hxl, hxg, INSERT_VALUES, SCATTER_REVERSE);
     VecScatterEnd(gtol_0, hxl, hxg, INSERT_VALUES, SCATTER_REVERSE);
-    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.dat", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "", lev, tstep, "dat");
     view_to(hxg, filename, false);
     VecDestroy(&hxg);
     VecDestroy(&hxl);
-    std::snprintf(filename, sizeof filename, "output/%s_%.3u_%.4u.vec", fieldname, lev, tstep);
+    field_file(filename, sizeof filename, fieldname, "", lev, tstep, "vec");
     view_to(h, filename, true);
 }
 

@@ -49,6 +49,10 @@ class Geom {
         void write0(Vec q, char* fieldname, int tstep, int lev);
         void write1(Vec u, char* fieldname, int tstep, int lev);
         void write2(Vec h, char* fieldname, int tstep, int lev, bool vert_scale);
+        // src/Geom.h: no levels -- output/<field>_<step>.dat (the ASCII branch; the reference's optional HDF5 branch is not provided)
+        void write0(Vec q, char* fieldname, int tstep);
+        void write1(Vec u, char* fieldname, int tstep);
+        void write2(Vec h, char* fieldname, int tstep);
         // per-element vertical vectors (L2Vecs::vz: vecs[element][level p^2 + i]) relabelled to one 2-form per level and
         // written with write2, levels 0 .. nv-1                                        eul/Geom.cpp:633-679
         void writeVertToHoriz(Vec* vecs, char* fieldname, int tstep, int nv);

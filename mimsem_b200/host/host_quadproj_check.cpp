@@ -3,7 +3,8 @@
 // emulated `mpirun -np 6`, and for Geom::writeVertToHoriz (eul/Geom.cpp:633-679) against write2 level by level.  No GPU.
 //   host_quadproj_check <p> <ne> <in.bin> <out.bin> <scratch dir>
 // in.bin : doubles xq[nq] uq[2 nq]      (global quadrature-point numbering; uq: two interleaved components per point)
-// out.bin: doubles WtQmat xq [N2], UtQmat uq [N1], PtQmat xq [N0], then 1.0 / 0.0: writeVertToHoriz wrote what write2 writes
+// out.bin: doubles WtQmat xq [N2], UtQmat uq [N1], PtQmat xq [N0], then 1.0 / 0.0: writeVertToHoriz wrote what write2 writes,
+//                   then 1.0 / 0.0: the level-less src/ writers wrote what the eul/ writers write at unit thickness
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -147,6 +148,35 @@ int main(int argc, char** argv) {
             }
     }
     std::fwrite(&same, 8, 1, out);
+    // the level-less writers of src/ (src/Geom.cpp:326-520): with unit thickness they write what the eul/ forms write for a level
+    double same_src = 1.0;
+    {
+        std::vector<Vec> q0(np), u1(np), h2(np);
+        for (int r = 0; r < np; r++) {
+            PetscCompatSetRank(r, np);
+            Topo* t = R[r].topo;
+            for (int i = 0; i < R[r].geom->n0; i++) R[r].geom->thick[0][i] = 1.0;
+            VecCreateMPI(MPI_COMM_WORLD, t->n0l, t->nDofs0G, &q0[r]);
+            VecCreateMPI(MPI_COMM_WORLD, t->n1l, t->nDofs1G, &u1[r]);
+            VecCreateMPI(MPI_COMM_WORLD, t->n2l, t->nDofs2G, &h2[r]);
+            PetscScalar* a;
+            VecGetArray(q0[r], &a); for (int i = 0; i < t->n0l; i++) a[i] = std::cos(0.02 * i + r); VecRestoreArray(q0[r], &a);
+            VecGetArray(u1[r], &a); for (int i = 0; i < t->n1l; i++) a[i] = std::sin(0.03 * i - r); VecRestoreArray(u1[r], &a);
+            VecGetArray(h2[r], &a); for (int i = 0; i < t->n2l; i++) a[i] = 1.0 + 0.5 * std::sin(0.05 * i + r); VecRestoreArray(h2[r], &a);
+        }
+        char s0[8] = "sq", s1[8] = "su", s2[8] = "sh", e0[8] = "eq", e1[8] = "eu", e2[8] = "eh";
+        ALL_RANKS(k.geom->write0(q0[r], s0, 3))  ALL_RANKS(k.geom->write0(q0[r], e0, 3, 0))
+        ALL_RANKS(k.geom->write1(u1[r], s1, 3))  ALL_RANKS(k.geom->write1(u1[r], e1, 3, 0))
+        ALL_RANKS(k.geom->write2(h2[r], s2, 3))  ALL_RANKS(k.geom->write2(h2[r], e2, 3, 0, true))
+        const char* pairs[7][2] = {{"sq_0003.dat", "eq_000_0003.dat"}, {"su_x_0003.dat", "eu_x_000_0003.dat"}, {"su_y_0003.dat", "eu_y_000_0003.dat"},
+                                   {"su_0003.vec", "eu_000_0003.vec"}, {"sh_0003.dat", "eh_000_0003.dat"}, {"sh_0003.vec", "eh_000_0003.vec"},
+                                   {"sh_0003.dat", "sh_0003.dat"}};
+        for (int i = 0; i < 7; i++) {
+            const std::vector<char> A = read_bytes(std::string("output/") + pairs[i][0]), B = read_bytes(std::string("output/") + pairs[i][1]);
+            if (A.empty() || A != B) same_src = 0.0;
+        }
+    }
+    std::fwrite(&same_src, 8, 1, out);
     std::fclose(out);
     std::printf("host_quadproj_check ok\n");
     return 0;

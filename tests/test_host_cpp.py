@@ -51,11 +51,12 @@ def test_quadrature_projections_vs_reference_golden(tmp_path, p, ne):
     assert r.returncode == 0 and "host_quadproj_check ok" in r.stdout, r.stdout + r.stderr
     out = np.fromfile(fout, dtype="<f8")
     N0, N1, N2 = int(g["N0"]), int(g["N1"]), int(g["N2"])
-    assert out.size == N0 + N1 + N2 + 1
+    assert out.size == N0 + N1 + N2 + 2
     assert rel_l2(out[:N2], g["y_WtQmat"]) < 1e-14
     assert rel_l2(out[N2:N2 + N1], g["y_UtQmat"]) < 1e-14
     assert rel_l2(out[N2 + N1:N2 + N1 + N0], g["y_PtQmat"]) < 1e-14
-    assert out[-1] == 1.0, "writeVertToHoriz and write2 wrote different files"
+    assert out[-2] == 1.0, "writeVertToHoriz and write2 wrote different files"
+    assert out[-1] == 1.0, "the level-less src/ writers (Geom::write0/1/2(Vec, char*, int)) differ from the eul/ writers at unit thickness"
 
 
 def test_element_tabulations_row_view_on_cpu():
