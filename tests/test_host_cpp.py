@@ -227,7 +227,8 @@ PETSC_HEADERS = ("petsc.h", "petscis.h", "petscvec.h", "petscmat.h", "petscksp.h
                                                        ("eul", "VertSolve.cpp", True), ("eul", "VertOps.cpp", True),
                                                        ("eul", "UMJS14.cpp", True), ("box", "Euler_2.cpp", True),
                                                        ("box", "VertSolve.cpp", True), ("box", "VertOps.cpp", True),
-                                                       ("box", "Bubble.cpp", True)])
+                                                       ("box", "Bubble.cpp", True), ("eul", "HeldSuarez.cpp", True),
+                                                       ("src", "Williamson2.cpp", True), ("src", "Williamson5.cpp", True)])
 def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, variant, caller, decls_only):
     """The drop-in claim, mechanically: the reference's own caller translation unit -- eul/HorizSolve.cpp (constructs Umat,
     Wmat, Pmat, Uhmat, WtQUmat, RotMat, Ut_mat, UtQWmat, Whmat, E10mat, E21mat, Uvec, Wvec, PtQmat; calls assemble(...) /
@@ -241,7 +242,9 @@ def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, varian
     matrices -- PETSc proper, outside the path and not part of the compatibility layer: for these the PETSc headers
     forward to tests/petsc_decls_only.h (prototypes without bodies) and the symbol check covers the mirrored classes.
     box/ (like src/) keeps its element tabulations as rows (double** A, box/ElMats.h): its callers are compiled with
-    -DMIMSEM_ELMATS_ROWS, which names the row view of the mirror's tabulations `A` (host/ElMats.h)."""
+    -DMIMSEM_ELMATS_ROWS, which names the row view of the mirror's tabulations `A` (host/ElMats.h).  Of src/ only the
+    drivers are here (Topo, Geom incl. the level-less write0/1/2): src/SWEqn_Picard.cpp feeds the operator matrices to
+    MatMatMult / MatGetRow, i.e. needs assembled matrices."""
     _build()
     src = os.path.join(REFERENCE, variant)
     for f in os.listdir(src):
@@ -250,7 +253,7 @@ def test_reference_caller_compiles_unchanged_against_the_mirror(tmp_path, varian
     for f in PETSC_HEADERS + ("petscsnes.h",):
         (tmp_path / f).write_text('#include "%s"\n' % ("petsc_decls_only.h" if decls_only else "petsc_compat.h"))
     obj = str(tmp_path / "caller.o")
-    r = subprocess.run(["g++", "-std=c++11", "-w", "-c"] + (["-DMIMSEM_ELMATS_ROWS"] if variant == "box" else []) +
+    r = subprocess.run(["g++", "-std=c++11", "-w", "-c"] + (["-DMIMSEM_ELMATS_ROWS"] if variant in ("box", "src") else []) +
                        ["-I", str(tmp_path), "-I", HOST, "-I", os.path.join(ROOT, "tests"), str(tmp_path / caller), "-o", obj],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
