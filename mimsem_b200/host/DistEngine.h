@@ -63,7 +63,9 @@ public:
     // fields), captured in ONE CUDA graph.  The launches carry programmatic dependencies and work on consecutive epochs of
     // the ghost hand-over, so that a step starts while the previous one drains and the boundary rows of step i + 1 travel
     // while step i computes (engine option "pdl_independent" is on during the capture only: the edges live in the graph).
-    // Collective: every rank captures and replays the same bursts in the same order.  replay() only enqueues (sync() waits).
+    // Collective: every rank captures and replays the same bursts in the same order.  replay() only enqueues, on the engine's
+    // own non-blocking stream: call sync() before the fields are used by any other call of this class (they run on the
+    // default stream) and before the host reads them.
     struct Burst;
     Burst* capture_burst_M1(const std::vector<const double*>& xs, const std::vector<double*>& ys, int nsteps, int nlev, double scale,
                             int tpow, int lev0 = 0);
