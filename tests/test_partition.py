@@ -181,3 +181,19 @@ def test_cpp_partition_equals_python_partition(kind, p, ne, world):
                 s = sends[space].get(q)
                 assert np.array_equal(arr(h, "send%d_%d" % (space, q)), s if s is not None else np.zeros(0)), (rank, space, q)
         lib.mimsem_host_partition_destroy(h)
+
+
+def test_cpp_file_rendezvous_three_processes(tmp_path):
+    """The control-plane transport of the C++ multi-GPU host layer between plain processes of one box (FileComm in
+    mimsem_b200/host/DistEngine.cpp: allgather and barrier through files): three processes, forty rounds of changing size,
+    every contribution verified by every rank (mimsem_b200/host/filecomm_check.cpp).  No GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "mimsem_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    exe = os.path.join(host, "build", "filecomm_check")
+    procs = [subprocess.Popen([exe, str(tmp_path / "rdv")], env=dict(os.environ, MIMSEM_RANK=str(r), MIMSEM_WORLD="3"),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(3)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs) and all("ok" in o for o in outs), outs
