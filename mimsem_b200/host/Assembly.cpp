@@ -420,6 +420,17 @@ PetscErrorCode shell_getdiag(Mat A, Vec d) {
 PetscErrorCode shell_pcbjacobi(Mat A, Vec r, Vec z) {
     MimsemShell* s;
     MatShellGetContext(A, &s);
+    if (s && (s->op == 2 /* M0 */ || s->op == 6 /* M0(h) */)) {
+        // diagonal when the quadrature order equals the element order (eul/Assembly.cpp:602-628: the reference keeps it as a
+        // vector for that reason): block Jacobi with any blocks is the exact inverse, KSPSolve(ksp0, ...) of
+        // eul/HorizSolve.cpp:87-96 converges in one iteration
+        Vec d;
+        VecDuplicate(r, &d);
+        PetscErrorCode rc = shell_getdiag(A, d);
+        if (!rc) VecPointwiseDivide(z, r, d);
+        VecDestroy(&d);
+        return rc;
+    }
     if (!s || s->op != 0 /* M1 */ || (s->flags & MIMSEM_THICK_MEAN)) return 56;
     Topo* topo = s->topo;
     std::map<Topo*, Patch>::iterator it = g_patches.find(topo);
@@ -472,7 +483,7 @@ MimsemShell* make_shell(Topo* topo, int op, int sin, int sout, Mat* M) {
     MatShellSetOperation(*M, MATOP_AXPY, (void (*)(void))shell_axpy);
 #ifndef MIMSEM_HAVE_PETSC
     // the compatibility layer's KSP asks the operator itself for the blocks of a PCBJACOBI request (real PETSc: MimsemPCApplyBJacobi)
-    if (op == 0) MatShellSetOperation(*M, MATOP_COMPAT_PCBJACOBI, (void (*)(void))shell_pcbjacobi);
+    if (op == 0 || op == 2 || op == 6) MatShellSetOperation(*M, MATOP_COMPAT_PCBJACOBI, (void (*)(void))shell_pcbjacobi);
 #endif
     s->mat = *M;
     return s;
@@ -582,7 +593,7 @@ PetscErrorCode MimsemPCApplyBJacobi(PC pc, Vec r, Vec z) {
 PetscErrorCode MimsemKSPSetElementBlockJacobi(KSP ksp, Mat M) {
     MimsemShell* s = NULL;
     MatShellGetContext(M, &s);
-    if (!s || s->op != 0 /* M1 */) return 56;
+    if (!s || (s->op != 0 /* M1 */ && s->op != 2 /* M0 */ && s->op != 6 /* M0(h) */)) return 56;
     PC pc;
     KSPGetPC(ksp, &pc);
     PCSetType(pc, PCSHELL);

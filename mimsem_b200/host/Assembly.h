@@ -355,7 +355,8 @@ PetscErrorCode MimsemMatMultLevels(Mat M, int lev0, int nlev, Vec* x, Vec* y, Ve
 //     KSPSetOperators(ksp1, M1->M, M1->M);  MimsemKSPSetElementBlockJacobi(ksp1, M1->M);   // instead of PCSetType(pc, PCBJACOBI)
 // The block data follow M1->assemble(lev, scale, vert_scale) like the shell's MatMult.  (The in-tree compatibility layer
 // routes a plain PCBJACOBI request on such a shell here by itself, so that the reference's callers run unchanged.)
-// Returns nonzero when M is not a Umat shell.
+// Also accepts the Pmat shell (KSPSolve(ksp0, ...), eul/HorizSolve.cpp:87-96): M0 is diagonal, its blocks are its diagonal.
+// Returns nonzero when M is neither.
 PetscErrorCode MimsemPCApplyBJacobi(PC pc, Vec r, Vec z);     /* PCShellSetApply callback; PCShellSetContext(pc, M) */
 PetscErrorCode MimsemKSPSetElementBlockJacobi(KSP ksp, Mat M);
 // host half of that preconditioner's set-up, for tests without a GPU: builds the element tables of its context (the patch

@@ -9,7 +9,7 @@
 //                   Umat_ray (exner = ex2[lev], exner_s = ex2[0], dt = 300, as eul/Euler_2.cpp:1218-1229 calls it),
 //                   Umat + Umat_ray through MatAXPY(M1->M, 1.0, M1ray->M, DIFFERENT_NONZERO_PATTERN) (eul/Euler_2.cpp:1229), and the
 //                   plain Umat again after the next assemble() (which drops the added term);
-//                   then { its, |x - x_true| / |x_true|, its with PCJACOBI } of the box solve and the box Pvec's vg, vg1 [N0 box each]
+//                   then { its, |x - x_true| / |x_true|, its with PCJACOBI } of the box solve, { its, error } of KSPSolve on the Pmat shell, and the box Pvec's vg, vg1 [N0 box each]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -213,6 +213,41 @@ int main(int argc, char** argv) {
         const double res[3] = {(double)its, en / xn, (double)its_diag};
         std::fwrite(res, 8, 3, out);
         KSPDestroy(&ksp1);
+        {   // KSPSolve(ksp0, ...) on the Pmat shell with the block-Jacobi request of eul/HorizSolve.cpp:87-96: M0 is diagonal
+            Pmat* M0 = new Pmat(bt, bg, n);
+            M0->assemble(0, SCALE);
+            KSP ksp0;
+            PC pc0;
+            KSPCreate(MPI_COMM_WORLD, &ksp0);
+            KSPSetOperators(ksp0, M0->M, M0->M);
+            KSPSetTolerances(ksp0, 1.0e-14, 1.0e-50, PETSC_DEFAULT, 1000);
+            KSPSetType(ksp0, KSPGMRES);
+            KSPGetPC(ksp0, &pc0);
+            PCSetType(pc0, PCBJACOBI);
+            PCBJacobiSetTotalBlocks(pc0, bt->nElsX * bt->nElsX, NULL);
+            Vec x0, b0, s0;
+            VecCreateMPI(MPI_COMM_WORLD, bt->n0l, bt->nDofs0G, &x0);
+            VecCreateMPI(MPI_COMM_WORLD, bt->n0l, bt->nDofs0G, &b0);
+            VecCreateMPI(MPI_COMM_WORLD, bt->n0l, bt->nDofs0G, &s0);
+            PetscScalar* pa;
+            VecGetArray(x0, &pa);
+            for (int i = 0; i < bt->n0l; i++) pa[i] = std::cos(0.21 * i) + 0.5;
+            VecRestoreArray(x0, &pa);
+            MatMult(M0->M, x0, b0);
+            VecZeroEntries(s0);
+            KSPSolve(ksp0, b0, s0);
+            PetscInt its0;
+            KSPGetIterationNumber(ksp0, &its0);
+            double e0n, x0n;
+            VecAXPY(s0, -1.0, x0);
+            VecNorm(s0, NORM_2, &e0n);
+            VecNorm(x0, NORM_2, &x0n);
+            const double res0[2] = {(double)its0, e0n / x0n};
+            std::fwrite(res0, 8, 2, out);
+            KSPDestroy(&ksp0);
+            VecDestroy(&x0); VecDestroy(&b0); VecDestroy(&s0);
+            delete M0;
+        }
         {   // box/Assembly.cpp:357-372: the Pvec constructor assembles vg (SCALE) and vg1 (scale 1) at level 0
             Pvec* m0 = new Pvec(bt, bg, n);
             PetscScalar* pa;

@@ -316,6 +316,9 @@ def test_host_twins_and_remaining_classes_vs_reference(tmp_path, fname, p, ne):
         assert rel_l2(take(N1), g["y_Umat_vs1"][lev] + g["y_Umat_ray"][lev]) < TOL, ("Umat + Umat_ray (MatAXPY)", lev)
         assert rel_l2(take(N1), g["y_Umat_vs1"][lev]) < TOL, ("Umat after re-assembly", lev)
     its, err, its_diag = take(3)
+    # KSPSolve(ksp0, ...) on the Pmat shell (eul/HorizSolve.cpp:87-96): M0 is diagonal, the block-Jacobi request is its exact inverse
+    its0, err0 = take(2)
+    assert 1 <= its0 <= 2 and err0 < 1e-13, (its0, err0)
     # the box Pvec (box/Assembly.cpp:357-372): vg = SCALE vg1 = the diagonal 0-form mass matrix of level 0
     nb0 = (3 * 4) ** 2
     vg, vg1 = take(nb0), take(nb0)
