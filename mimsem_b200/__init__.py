@@ -8,4 +8,3 @@ CPU fallback: anything that computes raises if the CUDA library or a GPU is miss
 from .lib import load_library, MimsemError  # noqa: F401
 from .mesh import Basis, Mesh, patch_topology, write_input  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .operators import (Umat, Wmat, Pmat, Uhmat, Whmat, WtQUmat, E10mat, E21mat)  # noqa: F401
