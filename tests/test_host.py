@@ -29,6 +29,17 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/mimsem_gpu.h compiles as strict C99 (plain pointers and sizes, no C++ or
+    torch types in any signature)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mimsem_gpu.h"\nint main(void) { return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():
